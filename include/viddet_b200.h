@@ -1,0 +1,173 @@
+/* viddet_b200 -- C ABI of the B200-native VidDet detection-head hot path.
+ *
+ * The reference (HaydenFaulkner/VidDet) is pure Python on MXNet/Gluon and has no FFI boundary of
+ * its own; its "operator API" for this path is the Gluon block / mx.nd.contrib operator call
+ * surface.  Each entry point below replaces one such surface and cites it (paths relative to the
+ * reference root).  The Python mirror (viddet_b200/blocks.py) binds these with ctypes; the stub a
+ * VidDet maintainer would add is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes only.  Every pointer is a DEVICE pointer unless the
+ *     name ends in `_host`.  The caller owns every buffer (inputs, outputs, workspace).
+ *   - All work is enqueued on `stream` (a cudaStream_t passed as void*; NULL = legacy default
+ *     stream); no entry point synchronises with the host (mirrors MXNet's async engine).
+ *   - Return value: 0 (VD_OK) or a negative VD_ERR_* code; vd_last_error() returns a
+ *     thread-local message.  Nothing throws or aborts across the boundary.
+ *   - fp32 tensors are dense row-major in the reference's own layouts unless stated.
+ *     "NHWC bf16" = channels-last bfloat16 feature map (B, H, W, C): the carrier layout of the
+ *     tensor-core path (TMA needs 16-byte strides, which NCHW 13x13/26x26 maps do not have).
+ */
+#ifndef VIDDET_B200_H_
+#define VIDDET_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VD_OK 0
+#define VD_ERR_INVALID_ARG (-1)
+#define VD_ERR_UNSUPPORTED (-2)
+#define VD_ERR_WORKSPACE   (-3)
+#define VD_ERR_CUDA        (-4)
+
+#define VD_MAX_SCALES 3
+#define VD_MAX_TOPK   1024      /* largest nms_topk the device NMS handles */
+
+/* YOLOOutputV3 decode modes (yolo3.py:179-199) */
+#define VD_MODE_INFER    0      /* (B, C*HW*A, 6) rows [id, score, x1, y1, x2, y2]            */
+#define VD_MODE_TRAIN    1      /* bbox + raw centers/scales/objness/class_pred               */
+#define VD_MODE_AGNOSTIC 2      /* (B, HW*A, 6) rows [0, objness, box]                        */
+
+/* temporal join in front of the prediction conv */
+#define VD_JOIN_NONE 0
+#define VD_JOIN_CAT  1          /* yolo3.py:1134-1136  (B,K,C,H,W)->(B,K*C,H,W)               */
+#define VD_JOIN_MAX  2          /* yolo3.py:1137-1138 / layers.py:202-203                      */
+#define VD_JOIN_MEAN 3          /* layers.py:204-205                                          */
+
+int vd_version(void);
+const char* vd_last_error(void);
+/* sm count / compute capability of `device`; fails unless it is an sm_100 part. */
+int vd_device_info(int device, int* sm_count, int* cc_major, int* cc_minor);
+
+/* ------------------------------------------------------------------------------------------
+ * box_nms -- replaces mx.nd.contrib.box_nms as called at yolo3.py:526-528 (x5 sites) and
+ * yolo3_temporal.py:545-547.  data/out: (num_batch, num_elem, width) fp32 (leading dims
+ * flattened by the caller); record_or_null: (num_batch, num_elem) int32 = MXNet's hidden second
+ * output (original row of each kept element, -1 elsewhere).  in/out_format: 0 corner, 1 center.
+ * topk <= 0 means num_elem; min(topk, num_elem) must be <= VD_MAX_TOPK.
+ * ------------------------------------------------------------------------------------------ */
+size_t vd_box_nms_workspace_bytes(int64_t num_batch, int64_t num_elem, int width, int topk);
+int vd_box_nms(const float* data, int64_t num_batch, int64_t num_elem, int width,
+               float overlap_thresh, float valid_thresh, int topk, int coord_start,
+               int score_index, int id_index, int background_id, int force_suppress,
+               int in_format, int out_format, float* out, int32_t* record_or_null,
+               void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * YOLOOutputV3 decode -- replaces YOLOOutputV3.hybrid_forward after the conv
+ * (yolo3.py:158-199; twin yolo3_temporal.py:139-179).  pred: (B, A*(5+C), H, W) fp32 NCHW (the
+ * prediction conv's output).  anchors: 2*A floats (w,h px) on the HOST.
+ * VD_MODE_INFER / VD_MODE_AGNOSTIC: writes this scale's rows into det[(b*det_rows_total +
+ *   det_row_offset + row)*6 ...], so the three scales can be written straight into the
+ *   concatenated tensor of yolo3.py:523.
+ * VD_MODE_TRAIN: det = bbox (B, HW*A, 4) (det_rows_total/offset apply likewise, width 4);
+ *   raw_centers (B,HW,A,2), raw_scales (B,HW,A,2), objness (B,HW,A,1), class_pred (B,HW,A,C).
+ * ------------------------------------------------------------------------------------------ */
+int vd_yolo_decode(const float* pred, int B, int H, int W, int num_class, int num_anchors,
+                   const float* anchors_host, float stride, int mode,
+                   float* det, int64_t det_rows_total, int64_t det_row_offset,
+                   float* raw_centers, float* raw_scales, float* objness, float* class_pred,
+                   void* stream);
+
+/* Layout helper for reference-layout callers: (B, C, H, W) fp32 -> (B, H, W, C) bf16. */
+int vd_repack_nchw_f32_to_nhwc_bf16(const float* src, void* dst_bf16, int B, int C, int H, int W,
+                                    void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Prediction conv -- replaces nn.Conv2D(A*(5+C), 1x1) (yolo3.py:62,157).  tcgen05 GEMM:
+ * x NHWC bf16 (B,H,W,Cin) [with join != NONE: (B,K,H,W,Cin)], weight bf16 (N, Cin_total) row-major
+ * (= the Gluon (N,Cin,1,1) weight), bias fp32 (N) or NULL -> pred (B, N, H, W) fp32 NCHW.
+ * ------------------------------------------------------------------------------------------ */
+int vd_pred_conv(const void* x_nhwc_bf16, int B, int H, int W, int Cin, int K_frames, int join,
+                 const void* weight_bf16, const float* bias_or_null, int N,
+                 float* pred_nchw, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Fused detector tail -- replaces, for one forward call of YOLOV3 / YOLOV3T / YOLOV3Temporal in
+ * inference mode: the three YOLOOutputV3 blocks (yolo3.py:496 -> :132-199), the scale concat
+ * (:523), box_nms (:526-528), the post_nms slice (:529-530) and the id/score/bbox split
+ * (:531-534).  Optionally first applies the temporal tip cell Conv3D((3,1,1))+BN+LeakyReLU
+ * (layers.py:82-89, yolo3_temporal.py:226-227) to each (B,T,...) window.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct VdHeadScale {
+    const void* tip_nhwc_bf16;   /* (frames, H, W, Cin) bf16; frames = B (or B*T) ; join!=NONE: (B,K,H,W,Cin) */
+    const void* weight_bf16;     /* (N_out, Cin_total) bf16, N_out = A*(5+C), Cin_total = Cin (*K for CAT)  */
+    const float* bias;           /* (N_out) fp32 or NULL                                         */
+    int H, W, Cin;
+    float stride;
+    float anchors[6];            /* A = 3 anchors (w,h) px                                       */
+    /* optional temporal tip cell in front of the prediction conv (NULL = absent) */
+    const void* tconv_weight_bf16;  /* (3, Cin, Cin) bf16: [tap][cout][cin]                      */
+    const float* tconv_scale;       /* (Cin) folded BN scale  gamma/sqrt(var+eps)                */
+    const float* tconv_shift;       /* (Cin) folded BN shift  beta - mean*scale                  */
+    void* tconv_out_nhwc_bf16;      /* (frames, H, W, Cin) bf16 scratch for the cell's output    */
+} VdHeadScale;
+
+typedef struct VdHeadParams {
+    int num_scales;              /* 3, output order s32, s16, s8 (yolo3.py:416-417)             */
+    int num_class;
+    int frames;                  /* B, or B*T for TimeDistributed heads (layers.py:241-250)     */
+    int T;                       /* window length for the temporal cell (frames % T == 0), else 1 */
+    int K_frames, join;          /* late temporal join (VD_JOIN_*), K frames per output frame   */
+    float nms_thresh;            /* yolo3.py:525: NMS only if 0 < nms_thresh < 1                */
+    float valid_thresh;          /* 0.01 at yolo3.py:527                                        */
+    int nms_topk;                /* 400 (detect_yolo3.py:200)                                   */
+    int post_nms;                /* 100 (yolo3.py:395)                                          */
+    VdHeadScale scale[VD_MAX_SCALES];
+} VdHeadParams;
+
+size_t vd_head_workspace_bytes(const VdHeadParams* p);
+/* ids (frames, post_nms, 1), scores (frames, post_nms, 1), bboxes (frames, post_nms, 4) fp32;
+ * keep_rows_or_null (frames, post_nms) int32 = row in the (frames, rows, 6) tensor of each output
+ * (the NMS keep-indices), -1 for padding. */
+int vd_head_forward(const VdHeadParams* p, float* ids, float* scores, float* bboxes,
+                    int32_t* keep_rows_or_null, void* workspace, size_t workspace_bytes,
+                    void* stream);
+/* Same conv + decode, but materialises the reference's (frames, rows, 6) detection tensor
+ * (what `concat(all_detections)` holds at yolo3.py:523) instead of running NMS. */
+int vd_head_detections(const VdHeadParams* p, float* det, void* workspace, size_t workspace_bytes,
+                       void* stream);
+
+/* Temporal tip cell alone: Conv3D((3,1,1), pad (1,0,0), no bias) + BN + LeakyReLU(0.1)
+ * (layers.py:82-89).  x, y: (B, T, H, W, C) bf16 channels-last; weight (3, C, C) bf16
+ * [tap][cout][cin]; scale/shift fp32 (C) folded inference BatchNorm. */
+int vd_temporal_conv(const void* x_bf16, void* y_bf16, int B, int T, int H, int W, int C,
+                     const void* weight_bf16, const float* scale, const float* shift,
+                     float slope, void* stream);
+
+/* TemporalPooling 'direct' (layers.py:202-205): (B,K,H,W,C) bf16 -> (B,H,W,C) bf16. */
+int vd_temporal_pool(const void* x_bf16, void* y_bf16, int B, int K, int64_t inner, int mode,
+                     void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * YOLOV3PrefetchTargetGenerator.forward -- replaces yolo_target.py:31-148.
+ * hw_host: 3x{H,W} of the feature maps in output order; anchors_host: 9x{w,h} in output order
+ * (s32,s16,s8).  gt_boxes (B,M,4) corner px padded with -1; gt_ids (B,M,ids_width) with
+ * ids_width 1 (class index) or C (multi-hot); mix_or_null (B,M,1).
+ * Outputs, already in the `_slice`d final layout (N = 3*sum HW): objectness (B,N,1),
+ * center (B,N,2), scale (B,N,2), weight (B,N,2), class (B,N,C).  match/row_or_null (B,M) int32:
+ * matched anchor (0..8) and final row of every GT that was written (-1 otherwise).
+ * ------------------------------------------------------------------------------------------ */
+int vd_prefetch_targets(int B, int M, int C, int orig_h, int orig_w, const int* hw_host,
+                        const float* anchors_host, const float* gt_boxes, const float* gt_ids,
+                        int ids_width, const float* mix_or_null,
+                        float* objectness, float* center, float* scale, float* weight, float* cls,
+                        int32_t* match_or_null, int32_t* row_or_null, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VIDDET_B200_H_ */

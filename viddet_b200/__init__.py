@@ -1,0 +1,12 @@
+"""viddet_b200 -- B200-native (sm_100a) implementation of VidDet's detection-head hot path:
+temporal tip conv -> 1x1 prediction conv -> YOLOOutputV3 decode -> per-class box_nms / top-k, plus
+the YOLOV3PrefetchTargetGenerator anchor-IoU matching.  Python here is a thin ctypes layer over
+the C ABI in include/viddet_b200.h; torch tensors are carriers only.  There is no CPU fallback.
+"""
+from ._lib import VidDetError, load, SO_PATH  # noqa: F401
+from .blocks import (  # noqa: F401
+    DEFAULT_ANCHORS, DEFAULT_CHANNELS, DEFAULT_STRIDES, TemporalPooling, TemporalTipConv, TimeDistributed,
+    YOLOOutputV3, YOLOV3Head, YOLOV3PrefetchTargetGenerator, box_nms, to_nhwc_bf16,
+)
+
+__version__ = "0.1.0"

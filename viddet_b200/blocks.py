@@ -1,0 +1,528 @@
+"""Host-side mirror of the reference's block / operator surface for the detection-head hot path.
+
+Same names, argument meaning and return layouts as HaydenFaulkner/VidDet (MXNet/Gluon), on torch
+CUDA tensors used purely as carriers: every function below is a thin ctypes call into one C-ABI
+symbol of libviddet_b200.so (include/viddet_b200.h).  No CPU path, no torch math on the hot path.
+
+reference surface                                             here
+---------------------------------------------------------------------------------------------
+mx.nd.contrib.box_nms        (yolo3.py:526-528)               box_nms()
+YOLOOutputV3                 (yolo3.py:25-199)                YOLOOutputV3
+TimeDistributed              (layers.py:208-264)              TimeDistributed
+TemporalPooling              (layers.py:161-205)              TemporalPooling
+Conv('21') temporal cell     (layers.py:82-89)                TemporalTipConv
+YOLOV3 / YOLOV3Temporal tail (yolo3.py:496,522-556;           YOLOV3Head
+                              yolo3_temporal.py:468,542-555)
+YOLOV3PrefetchTargetGenerator(yolo_target.py:13-148)          YOLOV3PrefetchTargetGenerator
+"""
+from __future__ import annotations
+
+import ctypes
+import warnings
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import VdHeadParams, check, load, ptr, stream_ptr
+
+# wrappers.py:80-84 lists (s8,s16,s32); yolo3.py:416-417 reverses -> output order s32,s16,s8
+DEFAULT_ANCHORS = [[116, 90, 156, 198, 373, 326], [30, 61, 62, 45, 59, 119], [10, 13, 16, 30, 33, 23]]
+DEFAULT_STRIDES = [32, 16, 8]
+DEFAULT_CHANNELS = [1024, 512, 256]
+_FMT = {"corner": 0, "center": 1}
+
+
+def _require_cuda(t, name):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise _lib.VidDetError(-1, "%s must be a CUDA tensor (viddet_b200 has no CPU path)" % name)
+
+
+# ------------------------------------------------------------------------------------------------
+# layout carriers
+# ------------------------------------------------------------------------------------------------
+def to_nhwc_bf16(x: torch.Tensor) -> torch.Tensor:
+    """(B,C,H,W) tensor in any layout/dtype -> bf16 tensor of the same logical shape whose memory is
+    channels-last (B,H,W,C).  fp32 NCHW (the reference's layout) goes through the repack kernel."""
+    _require_cuda(x, "x")
+    assert x.dim() == 4, "expected (B,C,H,W)"
+    if x.dtype == torch.bfloat16 and x.is_contiguous(memory_format=torch.channels_last):
+        return x
+    if x.dtype == torch.float32 and x.is_contiguous():
+        B, C, H, W = x.shape
+        out = torch.empty((B, C, H, W), dtype=torch.bfloat16, device=x.device, memory_format=torch.channels_last)
+        check(load().vd_repack_nchw_f32_to_nhwc_bf16(ptr(x), ptr(out), B, C, H, W, stream_ptr()))
+        return out
+    return x.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+
+
+# ------------------------------------------------------------------------------------------------
+# box_nms
+# ------------------------------------------------------------------------------------------------
+_ws_cache = {}
+
+
+def _workspace(nbytes, device):
+    key = (device.index if device.index is not None else torch.cuda.current_device())
+    buf = _ws_cache.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(int(nbytes * 1.25) + 1024, dtype=torch.uint8, device=device)
+        _ws_cache[key] = buf
+    return buf
+
+
+def box_nms(data, overlap_thresh=0.5, valid_thresh=0, topk=-1, coord_start=2, score_index=1, id_index=-1,
+            background_id=-1, force_suppress=False, in_format="corner", out_format="corner",
+            return_record=False):
+    """mx.nd.contrib.box_nms (signature and semantics of the MXNet operator).
+
+    data (..., num_elem, width) fp32 -> tensor of the same shape; with return_record also the
+    operator's hidden second output: original row index of every kept element, -1 elsewhere."""
+    _require_cuda(data, "data")
+    if data.dtype != torch.float32:
+        raise _lib.VidDetError(-1, "box_nms: data must be float32")
+    if in_format not in _FMT or out_format not in _FMT:
+        raise _lib.VidDetError(-1, "box_nms: format must be 'corner' or 'center'")
+    assert data.dim() >= 2
+    d = data.contiguous()
+    n_elem, width = d.shape[-2], d.shape[-1]
+    nb = 1
+    for s in d.shape[:-2]:
+        nb *= s
+    out = torch.empty_like(d)
+    rec = torch.empty(d.shape[:-1], dtype=torch.int32, device=d.device) if return_record else None
+    lib = load()
+    ws = _workspace(lib.vd_box_nms_workspace_bytes(nb, n_elem, width, int(topk)), d.device)
+    check(lib.vd_box_nms(ptr(d), nb, n_elem, width, float(overlap_thresh), float(valid_thresh), int(topk),
+                         int(coord_start), int(score_index), int(id_index), int(background_id),
+                         int(bool(force_suppress)), _FMT[in_format], _FMT[out_format], ptr(out), ptr(rec),
+                         ptr(ws), ws.numel(), stream_ptr()))
+    return (out, rec) if return_record else out
+
+
+# ------------------------------------------------------------------------------------------------
+# YOLOOutputV3
+# ------------------------------------------------------------------------------------------------
+class _Conv1x1:
+    """Parameter holder standing in for `nn.Conv2D(all_pred, kernel_size=1)` (yolo3.py:62)."""
+
+    def __init__(self):
+        self.weight = None      # (N, Cin, 1, 1) fp32 master copy, Gluon layout
+        self.bias = None        # (N,) fp32
+        self._w_bf16 = None
+
+    def set_data(self, weight, bias=None):
+        weight = torch.as_tensor(weight)
+        assert weight.dim() == 4 and weight.shape[2] == 1 and weight.shape[3] == 1
+        self.weight = weight.detach().to(torch.float32).cuda().contiguous()
+        n = self.weight.shape[0]
+        self.bias = (torch.zeros(n, device="cuda") if bias is None
+                     else torch.as_tensor(bias).detach().to(torch.float32).cuda().contiguous())
+        self._w_bf16 = self.weight.reshape(n, -1).to(torch.bfloat16).contiguous()
+
+    @property
+    def weight_bf16(self):
+        return self._w_bf16
+
+
+class YOLOOutputV3:
+    """YOLO output layer V3 (yolo3.py:25-199): 1x1 prediction conv + decode.
+
+    Parameters as in the reference: index, num_class, anchors, stride, alloc_size, agnostic.
+    (`k`/`rnn_shape`, the ConvRNN option at yolo3.py:58-60, is out of scope.)
+    `__call__(x)` takes (B,Cin,H,W) [fp32 NCHW like the reference, or bf16 channels-last] and returns
+      inference: (B, C*H*W*A, 6) rows [id, score, x1, y1, x2, y2]     (yolo3.py:191-197)
+      agnostic:  (B, H*W*A, 6)                                           (yolo3.py:184-188)
+      training=True: (bbox (B,HW*A,4), raw_centers (B,HW,A,2), raw_scales (B,HW,A,2),
+                      objness (B,HW,A,1), class_pred (B,HW,A,C), anchors, offsets)   (yolo3.py:179-182)
+    """
+
+    def __init__(self, index, num_class, anchors, stride, alloc_size=(128, 128), k=None, rnn_shape=None,
+                 k_join_type="max", agnostic=False, in_channels=None):
+        if k is not None and rnn_shape is not None:
+            raise NotImplementedError("ConvRNN prediction (yolo3.py:58-60) is outside the hot path")
+        anchors = np.array(anchors).astype("float32")
+        self._index = index
+        self._classes = num_class
+        self._num_pred = 1 + 4 + num_class
+        self._num_anchors = anchors.size // 2
+        self._stride = stride
+        self._agnostic = agnostic
+        self._alloc_size = tuple(alloc_size)
+        self.prediction = _Conv1x1()
+        self._anchors_np = anchors.reshape(-1)
+        self.anchors = torch.from_numpy(anchors.reshape(1, 1, -1, 2)).cuda()
+        gx, gy = np.meshgrid(np.arange(alloc_size[1]), np.arange(alloc_size[0]))
+        off = np.concatenate((gx[:, :, None], gy[:, :, None]), axis=-1)[None, None].astype("float32")
+        self.offsets = torch.from_numpy(off).cuda()
+        if in_channels is not None:
+            self.initialize(in_channels)
+
+    # -- parameters ------------------------------------------------------------------------------
+    def initialize(self, in_channels, scale=0.07, generator=None):
+        """net.initialize() default: weight ~ U(-0.07, 0.07), bias 0 (detect_yolo3.py:885)."""
+        n = self._num_pred * self._num_anchors
+        w = (torch.rand((n, in_channels, 1, 1), generator=generator) * 2 - 1) * scale
+        self.prediction.set_data(w, torch.zeros(n))
+        return self
+
+    def reset_class(self, classes, reuse_weights=None):
+        """yolo3.py:76-129: new predictor for len(classes) classes, optionally re-using rows."""
+        old_classes, old_num_pred = self._classes, self._num_pred
+        old_w, old_b = self.prediction.weight, self.prediction.bias
+        self._classes = len(classes)
+        self._num_pred = 1 + 4 + len(classes)
+        in_channels = old_w.shape[1]
+        self.initialize(in_channels)
+        if reuse_weights:
+            assert isinstance(reuse_weights, dict)
+            new_w, new_b = self.prediction.weight.clone(), self.prediction.bias.clone()
+            for k, v in reuse_weights.items():
+                if k >= self._classes or v >= old_classes:
+                    warnings.warn("reuse mapping {}/{} -> {}/{} out of range".format(k, self._classes, v, old_classes))
+                    continue
+                for i in range(self._num_anchors):
+                    off_new, off_old = i * self._num_pred, i * old_num_pred
+                    new_w[1 + 4 + k + off_new] = old_w[1 + 4 + v + off_old]
+                    new_b[1 + 4 + k + off_new] = old_b[1 + 4 + v + off_old]
+                    new_w[off_new:1 + 4 + off_new] = old_w[off_old:1 + 4 + off_old]
+                    new_b[off_new:1 + 4 + off_new] = old_b[off_old:1 + 4 + off_old]
+            self.prediction.set_data(new_w, new_b)
+
+    # -- forward ---------------------------------------------------------------------------------
+    def predict(self, x):
+        """The prediction conv alone: (B,Cin,H,W) -> pred (B, A*(5+C), H, W) fp32 (yolo3.py:157)."""
+        xb = to_nhwc_bf16(x)
+        B, Cin, H, W = xb.shape
+        n = self._num_pred * self._num_anchors
+        if self.prediction.weight is None or self.prediction.weight.shape[1] != Cin:
+            raise _lib.VidDetError(-1, "YOLOOutputV3: prediction weights not set for Cin=%d" % Cin)
+        pred = torch.empty((B, n, H, W), dtype=torch.float32, device=xb.device)
+        check(load().vd_pred_conv(ptr(xb), B, H, W, Cin, 1, _lib.VD_JOIN_NONE, ptr(self.prediction.weight_bf16),
+                                  ptr(self.prediction.bias), n, ptr(pred), stream_ptr()))
+        return pred
+
+    def decode(self, pred, training=False, out=None, rows_total=None, row_offset=0):
+        """yolo3.py:158-199 on a conv output `pred` (B, A*(5+C), H, W) fp32."""
+        _require_cuda(pred, "pred")
+        pred = pred.contiguous()
+        B, N, H, W = pred.shape
+        A, C = self._num_anchors, self._classes
+        assert N == A * (5 + C)
+        if H > self._alloc_size[0] or W > self._alloc_size[1]:
+            raise _lib.VidDetError(-1, "feature map larger than alloc_size")
+        anc = (ctypes.c_float * (2 * A))(*self._anchors_np.tolist())
+        lib, dev = load(), pred.device
+        if training:
+            bbox = torch.empty((B, H * W * A, 4), device=dev)
+            rc = torch.empty((B, H * W, A, 2), device=dev)
+            rs = torch.empty((B, H * W, A, 2), device=dev)
+            ob = torch.empty((B, H * W, A, 1), device=dev)
+            cp = torch.empty((B, H * W, A, C), device=dev)
+            check(lib.vd_yolo_decode(ptr(pred), B, H, W, C, A, anc, float(self._stride), _lib.VD_MODE_TRAIN,
+                                     ptr(bbox), H * W * A, 0, ptr(rc), ptr(rs), ptr(ob), ptr(cp), stream_ptr()))
+            offsets = self.offsets[:, :, :H, :W, :].reshape(1, -1, 1, 2)
+            return bbox, rc, rs, ob, cp, self.anchors, offsets
+        mode = _lib.VD_MODE_AGNOSTIC if self._agnostic else _lib.VD_MODE_INFER
+        rows = H * W * A * (1 if self._agnostic else C)
+        if out is None:
+            out = torch.empty((B, rows, 6), device=dev)
+            rows_total, row_offset = rows, 0
+        check(lib.vd_yolo_decode(ptr(pred), B, H, W, C, A, anc, float(self._stride), mode, ptr(out),
+                                 rows_total, row_offset, None, None, None, None, stream_ptr()))
+        return out
+
+    def __call__(self, x, training=False):
+        return self.decode(self.predict(x), training=training)
+
+    hybrid_forward = __call__
+
+
+# ------------------------------------------------------------------------------------------------
+# temporal pieces
+# ------------------------------------------------------------------------------------------------
+class TimeDistributed:
+    """layers.py:208-264, style 'reshape1': (B,T,...) -> (B*T,...) -> model -> (B,T,...)."""
+
+    def __init__(self, model, style="reshape1"):
+        assert style in ["reshape1", "reshape2", "for"]
+        self._style = style
+        self.model = model
+
+    def __call__(self, x, *args, **kwargs):
+        B, T = x.shape[0], x.shape[1]
+        y = self.model(x.reshape((B * T,) + tuple(x.shape[2:])), *args, **kwargs)
+        if isinstance(y, (tuple, list)):
+            return type(y)(yi.reshape((B, T) + tuple(yi.shape[1:])) if yi.shape[0] == B * T else yi for yi in y)
+        return y.reshape((B, T) + tuple(y.shape[1:]))
+
+
+class TemporalPooling:
+    """layers.py:161-205, style 'direct': max / mean over axis 1 of (B,K,C,H,W) (bf16 carriers)."""
+
+    def __init__(self, k, type="max", pool_size=None, strides=None, padding=0, style="direct"):
+        assert type in ["max", "mean"]
+        assert style in ["direct", "layer"]
+        if pool_size is not None or style == "layer":
+            raise NotImplementedError("only the 'direct' style (pool over the whole window) is on the hot path")
+        self._type = type
+        self._k = k
+
+    def __call__(self, x):
+        _require_cuda(x, "x")
+        B, K = x.shape[0], x.shape[1]
+        flat = x.reshape((B * K,) + tuple(x.shape[2:]))
+        xb = to_nhwc_bf16(flat)                       # (B*K, C, H, W) channels-last
+        _, C, H, W = xb.shape
+        out = torch.empty((B, C, H, W), dtype=torch.bfloat16, device=x.device, memory_format=torch.channels_last)
+        mode = _lib.VD_JOIN_MAX if self._type == "max" else _lib.VD_JOIN_MEAN
+        check(load().vd_temporal_pool(ptr(xb), ptr(out), B, K, C * H * W, mode, stream_ptr()))
+        return out
+
+
+class TemporalTipConv:
+    """The temporal cell of Conv('21', C, 3, 1, 1) (layers.py:82-89 second `_conv3d`):
+    Conv3D(C, (3,1,1), pad (1,0,0), no bias) + BatchNorm(eps=1e-5) + LeakyReLU(0.1) on (B,T,C,H,W)."""
+
+    def __init__(self, channels, epsilon=1e-5, slope=0.1):
+        self.channels = channels
+        self.epsilon = epsilon
+        self.slope = slope
+        self.weight = None                 # (Cout, Cin, 3, 1, 1) fp32, Gluon Conv3D layout
+        self.gamma = torch.ones(channels, device="cuda")
+        self.beta = torch.zeros(channels, device="cuda")
+        self.running_mean = torch.zeros(channels, device="cuda")
+        self.running_var = torch.ones(channels, device="cuda")
+        self._w_taps = self._scale = self._shift = None
+
+    def initialize(self, scale=0.07, generator=None):
+        c = self.channels
+        self.set_data((torch.rand((c, c, 3, 1, 1), generator=generator) * 2 - 1) * scale)
+        return self
+
+    def set_data(self, weight, gamma=None, beta=None, running_mean=None, running_var=None):
+        c = self.channels
+        self.weight = torch.as_tensor(weight).detach().to(torch.float32).cuda().reshape(c, c, 3)
+        for name, v in (("gamma", gamma), ("beta", beta), ("running_mean", running_mean), ("running_var", running_var)):
+            if v is not None:
+                setattr(self, name, torch.as_tensor(v).detach().to(torch.float32).cuda().contiguous())
+        # [tap][cout][cin] bf16 + folded inference BatchNorm
+        self._w_taps = self.weight.permute(2, 0, 1).contiguous().to(torch.bfloat16)
+        self._scale = (self.gamma / torch.sqrt(self.running_var + self.epsilon)).contiguous()
+        self._shift = (self.beta - self.running_mean * self._scale).contiguous()
+
+    def __call__(self, x):
+        """x (B,T,C,H,W) -> (B,T,C,H,W) bf16 (channels-last per frame)."""
+        _require_cuda(x, "x")
+        B, T, C, H, W = x.shape
+        xb = to_nhwc_bf16(x.reshape(B * T, C, H, W))
+        y = torch.empty((B * T, C, H, W), dtype=torch.bfloat16, device=x.device, memory_format=torch.channels_last)
+        check(load().vd_temporal_conv(ptr(xb), ptr(y), B, T, H, W, C, ptr(self._w_taps), ptr(self._scale),
+                                      ptr(self._shift), float(self.slope), stream_ptr()))
+        return y.reshape(B, T, C, H, W)
+
+
+# ------------------------------------------------------------------------------------------------
+# detector tail
+# ------------------------------------------------------------------------------------------------
+class YOLOV3Head:
+    """Inference tail of YOLOV3 / YOLOV3T / YOLOV3Temporal: three YOLOOutputV3 blocks, scale concat,
+    box_nms, post_nms slice, id/score/bbox split (yolo3.py:496,522-534; yolo3_temporal.py:468,542-555).
+
+    `__call__(tips)` with tips = [s32, s16, s8] feature maps (B,Cin,H,W) -- or (B,T,Cin,H,W) for
+    TimeDistributed heads -- returns ids (B[,T],post_nms,1), scores (B[,T],post_nms,1),
+    bboxes (B[,T],post_nms,4).  One fused C-ABI call (vd_head_forward).
+
+    temporal: None | 'conv21' (TemporalTipConv per scale in front of the output blocks, cfg T1)
+              | 'cat' | 'max' | 'mean' (late joins of yolo3.py:1134-1138 collapsing K frames).
+    """
+
+    def __init__(self, classes, anchors=None, strides=None, channels=None, nms_thresh=0.45, nms_topk=400,
+                 post_nms=100, temporal=None, k=1, agnostic=False):
+        self.classes = list(classes) if not isinstance(classes, int) else list(range(classes))
+        self._num_class = len(self.classes)
+        anchors = DEFAULT_ANCHORS if anchors is None else anchors
+        strides = DEFAULT_STRIDES if strides is None else strides
+        self.channels = DEFAULT_CHANNELS if channels is None else list(channels)
+        assert temporal in (None, "conv21", "cat", "max", "mean")
+        self.temporal, self.k = temporal, k
+        self.nms_thresh, self.nms_topk, self.post_nms = nms_thresh, nms_topk, post_nms
+        self.valid_thresh = 0.01                      # hard-coded at yolo3.py:527
+        if agnostic:
+            raise NotImplementedError("agnostic detector tail: use YOLOOutputV3(agnostic=True) + box_nms")
+        self.yolo_outputs = [YOLOOutputV3(i, self._num_class, a, s) for i, (a, s) in enumerate(zip(anchors, strides))]
+        self.tip_convs = [TemporalTipConv(c) for c in self.channels] if temporal == "conv21" else None
+        self.pool = TemporalPooling(k, temporal) if temporal in ("max", "mean") else None
+        self._keep = None
+
+    def initialize(self, generator=None):
+        mult = self.k if self.temporal == "cat" else 1
+        for o, c in zip(self.yolo_outputs, self.channels):
+            o.initialize(c * mult, generator=generator)
+        if self.tip_convs:
+            for t in self.tip_convs:
+                t.initialize(generator=generator)
+        return self
+
+    def set_nms(self, nms_thresh=0.45, nms_topk=400, post_nms=100):
+        """yolo3.py:536-556."""
+        self.nms_thresh, self.nms_topk, self.post_nms = nms_thresh, nms_topk, post_nms
+
+    def reset_class(self, classes, reuse_weights=None):
+        self.classes = list(classes)
+        self._num_class = len(self.classes)
+        for o in self.yolo_outputs:
+            o.reset_class(classes, reuse_weights)
+
+    # -- helpers ---------------------------------------------------------------------------------
+    def _params(self, tips, scratch):
+        """Build VdHeadParams for already-channels-last tips [(frames,C,H,W) or (B,K,C,H,W)-flattened]."""
+        p = VdHeadParams()
+        p.num_scales = len(tips)
+        p.num_class = self._num_class
+        p.T = 1
+        p.K_frames, p.join = 1, _lib.VD_JOIN_NONE
+        p.nms_thresh, p.valid_thresh = float(self.nms_thresh), float(self.valid_thresh)
+        p.nms_topk, p.post_nms = int(self.nms_topk), int(self.post_nms)
+        frames = None
+        for i, (t, o) in enumerate(zip(tips, self.yolo_outputs)):
+            F, C, H, W = t.shape
+            s = p.scale[i]
+            if self.temporal == "cat":
+                assert F % self.k == 0
+                p.K_frames, p.join = self.k, _lib.VD_JOIN_CAT
+                F = F // self.k
+            frames = F if frames is None else frames
+            assert frames == F, "all scales must carry the same number of frames"
+            s.tip_nhwc_bf16 = t.data_ptr()
+            s.weight_bf16 = o.prediction.weight_bf16.data_ptr()
+            s.bias = o.prediction.bias.data_ptr()
+            s.H, s.W, s.Cin = H, W, C
+            s.stride = float(o._stride)
+            for j in range(6):
+                s.anchors[j] = float(o._anchors_np[j])
+            if self.tip_convs is not None:
+                tc = self.tip_convs[i]
+                s.tconv_weight_bf16 = tc._w_taps.data_ptr()
+                s.tconv_scale = tc._scale.data_ptr()
+                s.tconv_shift = tc._shift.data_ptr()
+                s.tconv_out_nhwc_bf16 = scratch[i].data_ptr()
+        p.frames = frames
+        return p
+
+    def _prepare(self, tips):
+        lead = None
+        flat = []
+        for t in tips:
+            _require_cuda(t, "tip")
+            if t.dim() == 5:
+                lead = (t.shape[0], t.shape[1])
+                t = t.reshape((t.shape[0] * t.shape[1],) + tuple(t.shape[2:]))
+            flat.append(to_nhwc_bf16(t))
+        T = 1
+        if self.temporal in ("max", "mean"):
+            assert lead is not None, "temporal pooling needs (B,K,C,H,W) tips"
+            flat = [self.pool(f.reshape(lead + tuple(f.shape[1:]))) for f in flat]
+            lead = None
+        elif self.temporal == "cat":
+            assert lead is not None and lead[1] == self.k
+            lead = None
+        elif self.temporal == "conv21":
+            assert lead is not None, "the temporal tip cell needs (B,T,C,H,W) tips"
+            T = lead[1]
+        scratch = [torch.empty_like(f) for f in flat] if self.tip_convs is not None else None
+        p = self._params(flat, scratch)
+        p.T = T
+        return p, flat, scratch, lead
+
+    def __call__(self, tips, return_keep=False):
+        if not (0 < self.nms_thresh < 1) or self.post_nms <= 0:
+            # yolo3.py:525/529: NMS (or the slice) disabled -> plain rows
+            det = self.detections(tips)
+            if 0 < self.nms_thresh < 1:
+                det = box_nms(det, overlap_thresh=self.nms_thresh, valid_thresh=self.valid_thresh, topk=self.nms_topk,
+                              id_index=0, score_index=1, coord_start=2, force_suppress=False)
+            return det[..., 0:1], det[..., 1:2], det[..., 2:]
+        p, flat, scratch, lead = self._prepare(tips)
+        dev = flat[0].device
+        F, post = p.frames, self.post_nms
+        ids = torch.empty((F, post, 1), device=dev)
+        scores = torch.empty((F, post, 1), device=dev)
+        bboxes = torch.empty((F, post, 4), device=dev)
+        keep = torch.empty((F, post), dtype=torch.int32, device=dev) if return_keep else None
+        lib = load()
+        ws = _workspace(lib.vd_head_workspace_bytes(ctypes.byref(p)), dev)
+        check(lib.vd_head_forward(ctypes.byref(p), ptr(ids), ptr(scores), ptr(bboxes), ptr(keep), ptr(ws), ws.numel(),
+                                  stream_ptr()))
+        if lead is not None:
+            ids, scores, bboxes = (t.reshape(lead + tuple(t.shape[1:])) for t in (ids, scores, bboxes))
+            if keep is not None:
+                keep = keep.reshape(lead + (post,))
+        return (ids, scores, bboxes, keep) if return_keep else (ids, scores, bboxes)
+
+    def detections(self, tips):
+        """The concatenated (B[,T], rows, 6) tensor of yolo3.py:523 (before NMS)."""
+        p, flat, scratch, lead = self._prepare(tips)
+        dev = flat[0].device
+        rows = sum(self._num_class * int(p.scale[i].H) * int(p.scale[i].W) * 3 for i in range(p.num_scales))
+        det = torch.empty((p.frames, rows, 6), device=dev)
+        lib = load()
+        ws = _workspace(max(lib.vd_head_workspace_bytes(ctypes.byref(p)), 256), dev)
+        check(lib.vd_head_detections(ctypes.byref(p), ptr(det), ptr(ws), ws.numel(), stream_ptr()))
+        if lead is not None:
+            det = det.reshape(lead + (rows, 6))
+        return det
+
+
+# ------------------------------------------------------------------------------------------------
+# training targets
+# ------------------------------------------------------------------------------------------------
+class YOLOV3PrefetchTargetGenerator:
+    """yolo_target.py:13-148.  `__call__(img, xs, anchors, offsets, gt_boxes, gt_ids, gt_mixratio=None)`
+    -> objectness (B,N,1), center_targets (B,N,2), scale_targets (B,N,2), weights (B,N,2),
+    class_targets (B,N,C), N = 3*sum(H_i*W_i), rows in the order of the train-mode predictions.
+
+    img / xs are used for their shapes only (yolo_target.py:72-73,110-111) and may be tensors or
+    shape tuples; anchors: 3 x (1,1,3,2); offsets: 3 x (1,HW_i,1,2) (sizes only)."""
+
+    def __init__(self, num_class, **kwargs):
+        self._num_class = num_class
+
+    def __call__(self, img, xs, anchors, offsets, gt_boxes, gt_ids, gt_mixratio=None, return_assign=False):
+        assert isinstance(anchors, (list, tuple)) and isinstance(offsets, (list, tuple)) and isinstance(xs, (list, tuple))
+        assert len(xs) == len(anchors) == len(offsets) == 3
+        _require_cuda(gt_boxes, "gt_boxes")
+        _require_cuda(gt_ids, "gt_ids")
+        ishape = tuple(img.shape) if hasattr(img, "shape") else tuple(img)
+        hw = []
+        for x, o in zip(xs, offsets):
+            xshape = tuple(x.shape) if hasattr(x, "shape") else tuple(x)
+            hw += [int(xshape[2]), int(xshape[3])]
+            n_off = int(np.prod(tuple(o.shape))) // 2
+            assert n_off == xshape[2] * xshape[3], "offsets must cover the feature map"
+        anc = np.concatenate([np.asarray(a.detach().cpu() if isinstance(a, torch.Tensor) else a,
+                                         dtype=np.float32).reshape(-1, 2) for a in anchors], 0)
+        assert anc.shape == (9, 2)
+        gb = gt_boxes.to(torch.float32).contiguous()
+        gi = gt_ids.to(torch.float32).contiguous()
+        mix = gt_mixratio.to(torch.float32).contiguous() if gt_mixratio is not None else None
+        B, M = gb.shape[0], gb.shape[1]
+        C = self._num_class
+        N = 3 * sum(hw[2 * i] * hw[2 * i + 1] for i in range(3))
+        dev = gb.device
+        obj = torch.empty((B, N, 1), device=dev)
+        ctr = torch.empty((B, N, 2), device=dev)
+        scl = torch.empty((B, N, 2), device=dev)
+        wgt = torch.empty((B, N, 2), device=dev)
+        cls = torch.empty((B, N, C), device=dev)
+        match = torch.empty((B, M), dtype=torch.int32, device=dev) if return_assign else None
+        row = torch.empty((B, M), dtype=torch.int32, device=dev) if return_assign else None
+        hw_c = (ctypes.c_int * 6)(*hw)
+        anc_c = (ctypes.c_float * 18)(*anc.reshape(-1).tolist())
+        check(load().vd_prefetch_targets(B, M, C, int(ishape[2]), int(ishape[3]), hw_c, anc_c, ptr(gb), ptr(gi),
+                                         int(gi.shape[-1]), ptr(mix), ptr(obj), ptr(ctr), ptr(scl), ptr(wgt), ptr(cls),
+                                         ptr(match), ptr(row), stream_ptr()))
+        outs = (obj, ctr, scl, wgt, cls)
+        return outs + (match, row) if return_assign else outs
+
+    forward = __call__

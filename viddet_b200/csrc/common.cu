@@ -1,0 +1,46 @@
+// Error plumbing + device queries for the C ABI.
+#include "common.cuh"
+#include <stdarg.h>
+
+namespace vd {
+
+static thread_local char g_err[512] = "";
+
+char* last_error_buf() { return g_err; }
+
+int set_error(int code, const char* fmt, ...) {
+    va_list ap; va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+int sm_count() {
+    static int cached[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    if (!cached[dev]) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        cached[dev] = n;
+    }
+    return cached[dev];
+}
+
+}  // namespace vd
+
+extern "C" int vd_version(void) { return 100; }
+extern "C" const char* vd_last_error(void) { return vd::last_error_buf(); }
+
+extern "C" int vd_device_info(int device, int* sm_count, int* cc_major, int* cc_minor) {
+    int n = 0, maj = 0, min = 0;
+    VD_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, device));
+    VD_CUDA(cudaDeviceGetAttribute(&maj, cudaDevAttrComputeCapabilityMajor, device));
+    VD_CUDA(cudaDeviceGetAttribute(&min, cudaDevAttrComputeCapabilityMinor, device));
+    if (sm_count) *sm_count = n;
+    if (cc_major) *cc_major = maj;
+    if (cc_minor) *cc_minor = min;
+    if (maj != 10)
+        return vd::set_error(VD_ERR_UNSUPPORTED, "device %d is sm_%d%d; viddet_b200 is built for sm_100a only", device, maj, min);
+    return VD_OK;
+}

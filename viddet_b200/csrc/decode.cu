@@ -1,0 +1,145 @@
+// vd_yolo_decode -- YOLOOutputV3.hybrid_forward after the prediction conv
+// (yolo3.py:158-199; twin yolo3_temporal.py:139-179), on a materialised NCHW fp32 `pred`.
+// Compatibility surface (the fused head never materialises these rows); HBM-bound elementwise.
+//
+// One thread per (cell, anchor): reads its 5+C logits (coalesced across cells: pred is NCHW so
+// consecutive threads of a channel read consecutive cells), computes box / conf once, then
+// writes C detection rows.  Row order: row = c*(HW*A) + cell*A + a.
+#include "common.cuh"
+
+namespace vd {
+
+struct DecodeArgs {
+    const float* pred; int B, H, W, C, A; float stride; float anchors[12]; int mode;
+    float* det; int64_t det_rows_total, det_row_offset;
+    float* raw_centers; float* raw_scales; float* objness; float* class_pred;
+};
+
+__global__ void __launch_bounds__(256)
+yolo_decode_kernel(DecodeArgs a) {
+    const int HW = a.H * a.W, P = 5 + a.C;
+    const int b = blockIdx.y;
+    const int cell = blockIdx.x * blockDim.x + threadIdx.x;
+    if (cell >= HW) return;
+    const int gx = cell % a.W, gy = cell / a.W;
+    const float* pb = a.pred + (size_t)b * a.A * P * HW + cell;
+    for (int an = 0; an < a.A; ++an) {
+        const float* pa = pb + (size_t)an * P * HW;
+        float tx = __ldg(pa), ty = __ldg(pa + HW), tw = __ldg(pa + 2 * (size_t)HW), th = __ldg(pa + 3 * (size_t)HW);
+        float to = __ldg(pa + 4 * (size_t)HW);
+        Box4 bx = vd_decode_box(tx, ty, tw, th, (float)gx, (float)gy, a.stride, a.anchors[2 * an], a.anchors[2 * an + 1]);
+        const int slot = cell * a.A + an;                       // row inside (HW*A)
+        if (a.mode == VD_MODE_TRAIN) {
+            float* d = a.det + ((size_t)b * a.det_rows_total + a.det_row_offset + slot) * 4;
+            d[0] = bx.x1; d[1] = bx.y1; d[2] = bx.x2; d[3] = bx.y2;
+            size_t o = (size_t)b * HW * a.A + slot;
+            a.raw_centers[o * 2] = tx; a.raw_centers[o * 2 + 1] = ty;
+            a.raw_scales[o * 2] = tw; a.raw_scales[o * 2 + 1] = th;
+            a.objness[o] = to;
+            for (int c = 0; c < a.C; ++c) a.class_pred[o * a.C + c] = __ldg(pa + (size_t)(5 + c) * HW);
+            continue;
+        }
+        float conf = vd_sigmoid(to);
+        if (a.mode == VD_MODE_AGNOSTIC) {
+            float* d = a.det + ((size_t)b * a.det_rows_total + a.det_row_offset + slot) * 6;
+            d[0] = __fadd_rn(__fmul_rn(conf, 0.0f), 0.0f); d[1] = conf;
+            d[2] = bx.x1; d[3] = bx.y1; d[4] = bx.x2; d[5] = bx.y2;
+            continue;
+        }
+        for (int c = 0; c < a.C; ++c) {
+            float s = vd_score(__ldg(pa + (size_t)(5 + c) * HW), conf);
+            size_t row = (size_t)c * HW * a.A + slot;
+            float* d = a.det + ((size_t)b * a.det_rows_total + a.det_row_offset + row) * 6;
+            // ids = scores*0 + c (yolo3.py:194): NaN/Inf scores give NaN ids
+            float2* d2 = reinterpret_cast<float2*>(d);
+            d2[0] = make_float2(__fadd_rn(__fmul_rn(s, 0.0f), (float)c), s);
+            d2[1] = make_float2(bx.x1, bx.y1);
+            d2[2] = make_float2(bx.x2, bx.y2);
+        }
+    }
+}
+
+// (B, C, H, W) fp32 -> (B, H, W, C) bf16 through a 32x32 shared-memory transpose tile.
+__global__ void __launch_bounds__(256)
+repack_nchw_to_nhwc_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int C, int HW) {
+    __shared__ float tile[32][33];
+    const int b = blockIdx.z, c0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;       // 32 x 8
+    const float* s = src + (size_t)b * C * HW;
+    __nv_bfloat16* d = dst + (size_t)b * HW * C;
+    for (int i = ty; i < 32; i += 8) {
+        int c = c0 + i, p = p0 + tx;
+        tile[i][tx] = (c < C && p < HW) ? s[(size_t)c * HW + p] : 0.0f;
+    }
+    __syncthreads();
+    for (int i = ty; i < 32; i += 8) {
+        int p = p0 + i, c = c0 + tx;
+        if (p < HW && c < C) d[(size_t)p * C + c] = __float2bfloat16_rn(tile[tx][i]);
+    }
+}
+
+// TemporalPooling 'direct' (layers.py:202-205) over axis 1 of (B,K,inner) bf16.
+__global__ void __launch_bounds__(256)
+temporal_pool_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int K, int64_t inner, int mode) {
+    const int b = blockIdx.y;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= inner) return;
+    const __nv_bfloat16* p = x + (size_t)b * K * inner + i;
+    float acc = __bfloat162float(p[0]);
+    for (int k = 1; k < K; ++k) {
+        float v = __bfloat162float(p[(size_t)k * inner]);
+        acc = (mode == VD_JOIN_MAX) ? fmaxf(acc, v) : __fadd_rn(acc, v);
+    }
+    if (mode == VD_JOIN_MEAN) acc = __fdiv_rn(acc, (float)K);
+    y[(size_t)b * inner + i] = __float2bfloat16_rn(acc);
+}
+
+}  // namespace vd
+
+using namespace vd;
+
+extern "C" int vd_yolo_decode(const float* pred, int B, int H, int W, int num_class, int num_anchors,
+                              const float* anchors_host, float stride, int mode,
+                              float* det, int64_t det_rows_total, int64_t det_row_offset,
+                              float* raw_centers, float* raw_scales, float* objness, float* class_pred,
+                              void* stream) {
+    VD_CHECK_ARG(pred && det && anchors_host, "yolo_decode: null pointer");
+    VD_CHECK_ARG(B >= 0 && H > 0 && W > 0 && num_class > 0, "yolo_decode: bad shape");
+    VD_CHECK_ARG(H <= 128 && W <= 128, "yolo_decode: feature map %dx%d exceeds alloc_size (128,128) (yolo3.py:44)", H, W);
+    VD_CHECK_ARG(num_anchors >= 1 && num_anchors <= 6, "yolo_decode: num_anchors %d not in 1..6", num_anchors);
+    VD_CHECK_ARG(mode >= 0 && mode <= 2, "yolo_decode: bad mode %d", mode);
+    VD_CHECK_ARG(B <= 65535, "yolo_decode: batch > 65535");
+    if (mode == VD_MODE_TRAIN) VD_CHECK_ARG(raw_centers && raw_scales && objness && class_pred, "yolo_decode: train mode needs the four raw outputs");
+    if (B == 0) return VD_OK;
+    DecodeArgs a;
+    a.pred = pred; a.B = B; a.H = H; a.W = W; a.C = num_class; a.A = num_anchors; a.stride = stride; a.mode = mode;
+    for (int i = 0; i < 2 * num_anchors; ++i) a.anchors[i] = anchors_host[i];
+    a.det = det; a.det_rows_total = det_rows_total; a.det_row_offset = det_row_offset;
+    a.raw_centers = raw_centers; a.raw_scales = raw_scales; a.objness = objness; a.class_pred = class_pred;
+    dim3 grid(ceil_div(H * W, 256), B);
+    yolo_decode_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a);
+    VD_LAUNCH_CHECK();
+    return VD_OK;
+}
+
+extern "C" int vd_repack_nchw_f32_to_nhwc_bf16(const float* src, void* dst, int B, int C, int H, int W, void* stream) {
+    VD_CHECK_ARG(src && dst && B >= 0 && C > 0 && H > 0 && W > 0, "repack: bad argument");
+    VD_CHECK_ARG(B <= 65535, "repack: batch > 65535");
+    if (B == 0) return VD_OK;
+    int HW = H * W;
+    dim3 grid(ceil_div(HW, 32), ceil_div(C, 32), B);
+    repack_nchw_to_nhwc_bf16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(src, (__nv_bfloat16*)dst, C, HW);
+    VD_LAUNCH_CHECK();
+    return VD_OK;
+}
+
+extern "C" int vd_temporal_pool(const void* x, void* y, int B, int K, int64_t inner, int mode, void* stream) {
+    VD_CHECK_ARG(x && y && B >= 0 && K >= 1 && inner > 0, "temporal_pool: bad argument");
+    VD_CHECK_ARG(mode == VD_JOIN_MAX || mode == VD_JOIN_MEAN, "temporal_pool: mode must be VD_JOIN_MAX or VD_JOIN_MEAN");
+    VD_CHECK_ARG(B <= 65535, "temporal_pool: batch > 65535");
+    if (B == 0) return VD_OK;
+    dim3 grid((unsigned)ceil_div64(inner, 256), B);
+    temporal_pool_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, K, inner, mode);
+    VD_LAUNCH_CHECK();
+    return VD_OK;
+}

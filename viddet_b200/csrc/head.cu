@@ -1,0 +1,774 @@
+// Fused detection head for sm_100a: 1x1 prediction conv (tcgen05 GEMM, TMEM accumulators, TMA
+// operand ring) with the YOLOOutputV3 decode and an exact top-k candidate filter in the epilogue,
+// followed by the per-frame top-k / NMS kernel (nms_core.cuh).
+//
+// Replaces, per forward call (reference, inference mode):
+//   nn.Conv2D(A*(5+C), 1x1)                      yolo3.py:62,157      -> GEMM  [M=pixels, N=A*(5+C), K=Cin]
+//   YOLOOutputV3 decode (~15 elementwise ops)    yolo3.py:158-197     -> epilogue math on TMEM rows
+//   concat of the 3 scales                       yolo3.py:523         -> row index arithmetic
+//   contrib.box_nms + slice + split              yolo3.py:526-534     -> candidate lists -> nms_final
+//   late 'cat' temporal join                     yolo3.py:1134-1136   -> K loop over the K frames
+//
+// Kernel head_kernel<EPI, C>: persistent (one CTA per SM), 192 threads:
+//   warp 0      TMA producer: A tile [128 px x 64 ch] (4-D map: Cin, HW, K, frames; out-of-range
+//               pixels zero-filled) + W tile [NPAD x 64 ch] per stage, mbarrier ring
+//   warp 1      MMA issuer: tcgen05.mma.cta_group::1.kind::f16 M=128 N=NPAD K=16, fp32 accumulators
+//               double-buffered in TMEM, tcgen05.commit -> empty/full barriers
+//   warps 2-5   epilogue: tcgen05.ld of the pixel's logits, decode, then
+//        EPI_FILTER  per-anchor boxes -> box array; class scores -> 32-bit orderable keys in
+//                    registers; streaming exact selection of the tile's top-k (pivot search on
+//                    (score,row) keys, warm-started from the previous tile) -> <=cap candidates
+//                    per tile in the tile's list
+//        EPI_DET     materialise the reference's (frames, rows, 6) detection rows
+//        EPI_PRED    write the conv output (B, N, H, W) fp32
+// Tiles are ordered scale-major (s32 first: most bytes per tile) and dealt round-robin.
+#include "tc.cuh"
+#include "nms_core.cuh"
+
+namespace vd {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;
+constexpr int UMMA_K = 16;
+constexpr int kHeadThreads = 192;
+constexpr int kEpiThreads = 128;
+constexpr int kEpiWarp0 = 2;
+constexpr int A_TILE_BYTES = BLOCK_M * BLOCK_K * 2;
+
+enum { EPI_FILTER = 0, EPI_DET = 1, EPI_PRED = 2 };
+
+struct HeadKernelParams {
+    HeadGeom g;
+    int frames, K_frames;
+    int cin[VD_MAX_SCALES];
+    int pb[VD_MAX_SCALES];               // pixel blocks per frame
+    int tile_start[VD_MAX_SCALES + 1];   // scale-major cumulative tile index
+    int tif_base[VD_MAX_SCALES];         // tile-in-frame index of the scale's first pixel block
+    int tiles_per_frame, total_tiles, n_pad;
+    int n_valid;                         // prediction channels actually present (<= n_pad)
+    const float* bias[VD_MAX_SCALES];
+    // EPI_FILTER
+    float4* boxes; uint64_t* lists; uint32_t* counts; float valid_thresh; int k, cap;
+    // EPI_DET
+    float* det; long long det_rows_total;
+    // EPI_PRED
+    float* pred[VD_MAX_SCALES]; long long pred_frame_stride;   // floats between frames (N_total*HW)
+};
+
+struct HeadMaps { CUtensorMap a[VD_MAX_SCALES]; CUtensorMap w[VD_MAX_SCALES]; };
+
+template <int NPAD> struct HeadCfg {
+    static constexpr int B_TILE_BYTES = NPAD * BLOCK_K * 2;
+    static constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
+    static constexpr int EPI_BYTES = 2 * kListCap * 8 + VD_MAX_SCALES * NPAD * 4 + 1024;
+    static constexpr int STAGES_RAW = (225 * 1024 - EPI_BYTES - 1024) / STAGE_BYTES;
+    static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
+    static constexpr int TMEM_STRIDE = NPAD <= 128 ? 128 : 256;
+    static constexpr int TMEM_COLS = 2 * TMEM_STRIDE;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 1024;   // +1024 alignment slack
+    static_assert(NPAD % 16 == 0 && NPAD >= 16 && NPAD <= 256, "NPAD");
+    static_assert(STAGE_BYTES % 1024 == 0, "stage must keep 1024-byte alignment");
+    static_assert(STAGES >= 3, "pipeline too shallow");
+};
+
+struct EpiShared {
+    uint64_t full[8], empty[8], tmem_full[2], tmem_empty[2];
+    uint32_t tmem_base;
+    uint32_t cnt[3];
+    uint32_t cursor;
+    uint32_t pad_;
+    uint64_t red[2];
+};
+
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory"); }
+
+// block_sum over the 128 epilogue threads (named barrier 1), see select.cuh::block_sum
+__device__ __forceinline__ uint32_t epi_sum(uint32_t v, EpiShared* s, int et, int& it) {
+    uint32_t w = __reduce_add_sync(0xffffffffu, v);
+    const int slot = it % 3;
+    if ((et & 31) == 0 && w) atomicAdd(&s->cnt[slot], w);
+    if (et == 0) s->cnt[(it + 1) % 3] = 0;
+    epi_bar();
+    uint32_t r = s->cnt[slot];
+    ++it;
+    return r;
+}
+
+__device__ __forceinline__ void tile_coords(const HeadKernelParams& p, int tile, int& s, int& f, int& pblk) {
+    s = 0;
+#pragma unroll
+    for (int i = 1; i < VD_MAX_SCALES; ++i) if (i < p.g.num_scales && tile >= p.tile_start[i]) s = i;
+    int local = tile - p.tile_start[s];
+    f = local / p.pb[s];
+    pblk = local - f * p.pb[s];
+}
+
+template <int EPI, int C, int NPAD>
+__global__ void __launch_bounds__(kHeadThreads, 1)
+head_kernel(const __grid_constant__ HeadMaps maps, const __grid_constant__ HeadKernelParams p) {
+    using Cfg = HeadCfg<NPAD>;
+    constexpr int P = 5 + C;
+    extern __shared__ unsigned char smem_dyn[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+    unsigned char* ring = smem;
+    uint64_t* slist = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);     // [2][kListCap]
+    float* sbias = reinterpret_cast<float*>(slist + 2 * kListCap);                            // [3][NPAD]
+    EpiShared* sh = reinterpret_cast<EpiShared*>(sbias + VD_MAX_SCALES * NPAD);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    // ---------------- one-time setup
+    for (int i = threadIdx.x; i < VD_MAX_SCALES * NPAD; i += kHeadThreads) {
+        int s = i / NPAD, n = i % NPAD;
+        sbias[i] = (s < p.g.num_scales && p.bias[s] && n < p.n_valid) ? p.bias[s][n] : 0.0f;
+    }
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < Cfg::STAGES; ++i) { tc::mbar_init(&sh->full[i], 1); tc::mbar_init(&sh->empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { tc::mbar_init(&sh->tmem_full[i], 1); tc::mbar_init(&sh->tmem_empty[i], 4); }
+        sh->cnt[0] = sh->cnt[1] = sh->cnt[2] = 0; sh->cursor = 0; sh->red[0] = ~0ull; sh->red[1] = 0ull;
+        tc::fence_barrier_init();
+    }
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < p.g.num_scales; ++s) { tc::prefetch_tmap(&maps.a[s]); tc::prefetch_tmap(&maps.w[s]); }
+    }
+    if (warp == 1) tc::tmem_alloc<Cfg::TMEM_COLS>(&sh->tmem_base);
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem_base = sh->tmem_base;
+
+    if (warp == 0) {
+        // =========================== TMA producer ===========================
+        if (tc::elect_one()) {
+            int stage = 0; uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+                int s, f, pblk; tile_coords(p, tile, s, f, pblk);
+                const int kb_per_frame = p.cin[s] / BLOCK_K;
+                const int nkb = kb_per_frame * p.K_frames;
+                for (int kb = 0; kb < nkb; ++kb) {
+                    tc::mbar_wait(&sh->empty[stage], phase ^ 1u);
+                    unsigned char* a_dst = ring + stage * Cfg::STAGE_BYTES;
+                    unsigned char* b_dst = a_dst + A_TILE_BYTES;
+                    tc::mbar_expect_tx(&sh->full[stage], Cfg::STAGE_BYTES);
+                    const int kf = kb / kb_per_frame, c0 = (kb - kf * kb_per_frame) * BLOCK_K;
+                    tc::tma_load_4d(a_dst, &maps.a[s], &sh->full[stage], c0, pblk * BLOCK_M, kf, f);
+                    tc::tma_load_2d(b_dst, &maps.w[s], &sh->full[stage], kf * p.cin[s] + c0, 0);
+                    if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // =========================== MMA issuer ===========================
+        if (tc::elect_one()) {
+            constexpr uint32_t idesc = tc::make_idesc_bf16(BLOCK_M, NPAD);
+            int stage = 0; uint32_t phase = 0; uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+                int s, f, pblk; tile_coords(p, tile, s, f, pblk);
+                const int nkb = (p.cin[s] / BLOCK_K) * p.K_frames;
+                const uint32_t buf = it & 1u;
+                tc::mbar_wait(&sh->tmem_empty[buf], ((it >> 1) & 1u) ^ 1u);
+                tc::fence_after_sync();
+                const uint32_t d_tmem = tmem_base + buf * Cfg::TMEM_STRIDE;
+                for (int kb = 0; kb < nkb; ++kb) {
+                    tc::mbar_wait(&sh->full[stage], phase);
+                    tc::fence_after_sync();
+                    const uint32_t a_addr = tc::smem_u32(ring + stage * Cfg::STAGE_BYTES);
+                    const uint64_t da = tc::make_smem_desc_sw128(a_addr);
+                    const uint64_t db = tc::make_smem_desc_sw128(a_addr + A_TILE_BYTES);
+#pragma unroll
+                    for (int k = 0; k < BLOCK_K / UMMA_K; ++k)      // +32 bytes along K inside the swizzle atom
+                        tc::umma_bf16(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (uint32_t)((kb | k) != 0));
+                    tc::umma_commit(&sh->empty[stage]);
+                    if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
+                }
+                tc::umma_commit(&sh->tmem_full[buf]);
+            }
+        }
+    } else {
+        // =========================== epilogue (128 threads) ===========================
+        const int et = threadIdx.x - kEpiWarp0 * 32;
+        const int q = warp & 3;                               // TMEM lane quarter this warp may read
+        const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+        int sum_it = 0;
+        uint64_t tau_guess = 0ull;                            // warm start for the next tile (FILTER)
+        uint32_t it = 0;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+            int s, f, pblk; tile_coords(p, tile, s, f, pblk);
+            const uint32_t buf = it & 1u;
+            const int HW = p.g.HW[s], Wd = p.g.W[s];
+            const int cell = pblk * BLOCK_M + q * 32 + lane;
+            const bool inb = cell < HW;
+            const float gx = (float)(cell % Wd), gy = (float)(cell / Wd);
+            const float* bias = sbias + s * NPAD;
+            tc::mbar_wait(&sh->tmem_full[buf], (it >> 1) & 1u);
+            tc::fence_after_sync();
+            const uint32_t tbase = tmem_base + buf * Cfg::TMEM_STRIDE + lane_addr;
+
+            if constexpr (EPI == EPI_PRED) {
+                float* out = p.pred[s] + (size_t)f * p.pred_frame_stride;
+#pragma unroll 1
+                for (int n0 = 0; n0 < NPAD; n0 += 16) {
+                    uint32_t r[16];
+                    tc::tmem_ld16(tbase + n0, r); tc::tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        int n = n0 + i;
+                        if (inb && n < p.n_valid) out[(size_t)n * HW + cell] = __uint_as_float(r[i]) + bias[n];
+                    }
+                }
+                tc::fence_before_sync();
+                __syncwarp();
+                if (lane == 0) tc::mbar_arrive(&sh->tmem_empty[buf]);
+                continue;
+            }
+
+            // ---- per-anchor box + objectness (yolo3.py:172-177)
+            float conf[3];
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                uint32_t r[5];
+                tc::tmem_ld<5>(tbase + a * P, r); tc::tmem_ld_wait();
+                float tx = __uint_as_float(r[0]) + bias[a * P + 0], ty = __uint_as_float(r[1]) + bias[a * P + 1];
+                float tw = __uint_as_float(r[2]) + bias[a * P + 2], th = __uint_as_float(r[3]) + bias[a * P + 3];
+                float to = __uint_as_float(r[4]) + bias[a * P + 4];
+                Box4 bx = vd_decode_box(tx, ty, tw, th, gx, gy, p.g.stride[s], p.g.anchors[s][2 * a], p.g.anchors[s][2 * a + 1]);
+                conf[a] = vd_sigmoid(to);
+                if constexpr (EPI == EPI_FILTER) {
+                    if (inb) p.boxes[(size_t)f * p.g.anc_base[p.g.num_scales] + p.g.anc_base[s] + cell * 3 + a] =
+                        make_float4(bx.x1, bx.y1, bx.x2, bx.y2);
+                } else {   // EPI_DET: class rows of this (cell, anchor)
+                    const size_t rows_scale = (size_t)HW * 3;
+                    float* drow = p.det + ((size_t)f * p.det_rows_total + p.g.row_base[s] + (size_t)cell * 3 + a) * 6;
+                    // 8-column windows; the last one may read up to 7 columns past 3*P, which stays inside
+                    // this accumulator buffer's TMEM_STRIDE columns (checked at compile time)
+                    static_assert(2 * P + 5 + (C + 7) / 8 * 8 <= Cfg::TMEM_STRIDE, "class window leaves the TMEM buffer");
+#pragma unroll 1
+                    for (int c0 = 0; c0 < C; c0 += 8) {
+                        uint32_t rc[8];
+                        tc::tmem_ld8(tbase + a * P + 5 + c0, rc); tc::tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const int c = c0 + i;
+                            if (c < C && inb) {
+                                float sc = vd_score(__uint_as_float(rc[i]) + bias[a * P + 5 + c], conf[a]);
+                                float2* o = reinterpret_cast<float2*>(drow + (size_t)c * rows_scale * 6);
+                                o[0] = make_float2(__fadd_rn(__fmul_rn(sc, 0.0f), (float)c), sc);
+                                o[1] = make_float2(bx.x1, bx.y1);
+                                o[2] = make_float2(bx.x2, bx.y2);
+                            }
+                        }
+                    }
+                }
+            }
+            if constexpr (EPI == EPI_DET) {
+                tc::fence_before_sync();
+                __syncwarp();
+                if (lane == 0) tc::mbar_arrive(&sh->tmem_empty[buf]);
+                continue;
+            }
+
+            if constexpr (EPI == EPI_FILTER) {
+                // ---- class scores -> orderable 32-bit keys; streaming exact selection of the tile's top-k
+                constexpr int NCH = (C + 31) / 32;                  // class chunks (register budget)
+                constexpr int CCH = (C + NCH - 1) / NCH;
+                const uint32_t k = (uint32_t)p.k, cap = (uint32_t)p.cap;
+                const uint32_t HW3 = (uint32_t)HW * 3u;
+                const uint32_t row0 = (uint32_t)p.g.row_base[s] + (uint32_t)cell * 3u;    // + c*HW3 + a
+                uint64_t tau = 1ull;                                // every valid candidate seen so far with key >= tau is in the list
+                uint32_t list_n = 0; int cur = 0;
+                uint64_t* L = slist;
+#pragma unroll 1
+                for (int ch = 0; ch < NCH; ++ch) {
+                    uint32_t sk[3][CCH];
+                    const bool last_short = (ch == NCH - 1) && (C - (NCH - 1) * CCH < CCH);
+#pragma unroll
+                    for (int a = 0; a < 3; ++a) {
+                        uint32_t r[CCH];
+                        const int col0 = a * P + 5 + ch * CCH;
+                        if (!last_short) { tc::tmem_ld<CCH>(tbase + col0, r); }
+                        else {              // last chunk is shorter: read exactly the remaining classes
+                            constexpr int REM = (C - (NCH - 1) * CCH) > 0 ? (C - (NCH - 1) * CCH) : 1;
+                            tc::tmem_ld<REM>(tbase + col0, r);
+#pragma unroll
+                            for (int i = REM; i < CCH; ++i) r[i] = 0u;
+                        }
+                        tc::tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < CCH; ++i) {
+                            const int c = ch * CCH + i;
+                            const uint32_t raw = r[i];
+                            uint32_t key = 0u;
+                            if (c < C && inb) {
+                                float sc = vd_score(__uint_as_float(raw) + bias[a * P + 5 + c], conf[a]);
+                                if (sc > p.valid_thresh) key = orderable_f32(sc);          // strict; NaN invalid
+                            }
+                            sk[a][i] = key;
+                        }
+                    }
+                    if (ch == NCH - 1) {                            // accumulator fully consumed: hand TMEM back
+                        tc::fence_before_sync();
+                        __syncwarp();
+                        if (lane == 0) tc::mbar_arrive(&sh->tmem_empty[buf]);
+                    }
+                    // count of (chunk U list) keys >= pivot; pivot low word 0 => pure score compare
+                    auto count_ge = [&](uint64_t piv) -> uint32_t {
+                        const uint32_t ph = (uint32_t)(piv >> 32), pl = (uint32_t)piv;
+                        uint32_t c = 0;
+                        if (pl == 0u) {
+#pragma unroll
+                            for (int a = 0; a < 3; ++a)
+#pragma unroll
+                                for (int i = 0; i < CCH; ++i) c += (sk[a][i] >= ph) ? 1u : 0u;
+                        } else {
+#pragma unroll
+                            for (int a = 0; a < 3; ++a)
+#pragma unroll
+                                for (int i = 0; i < CCH; ++i) {
+                                    uint32_t sv = sk[a][i];
+                                    uint32_t nrow = ~(row0 + (uint32_t)(ch * CCH + i) * HW3 + (uint32_t)a);
+                                    c += (sv > ph || (sv == ph && nrow >= pl)) ? 1u : 0u;
+                                }
+                        }
+                        for (uint32_t j = et; j < list_n; j += kEpiThreads) c += (L[cur * kListCap + j] >= piv) ? 1u : 0u;
+                        return epi_sum(c, sh, et, sum_it);
+                    };
+                    // ---- find tau' >= tau with  k <= count(>= tau') <= cap   (or keep tau if everything fits)
+                    uint64_t ntau = tau;
+                    {
+                        uint64_t probe = tau_guess > tau ? tau_guess : tau;
+                        uint32_t t = count_ge(probe);
+                        uint64_t lo = 0ull, hi = 0ull; bool have_lo = false, have_hi = false, done = false;
+                        if (t >= k && t <= cap) { ntau = probe; done = true; }
+                        else if (t > cap) { lo = probe; have_lo = true; }
+                        else {                                       // t < k: too high, or everything fits
+                            hi = probe; have_hi = true;
+                            if (probe == tau) { ntau = tau; done = true; }
+                            else {
+                                uint32_t t0 = count_ge(tau);
+                                if (t0 <= cap) { ntau = tau; done = true; }
+                                else { lo = tau; have_lo = true; }
+                            }
+                        }
+                        if (!done && !have_hi) {                     // gallop upwards for an upper bracket
+                            uint64_t step = 1ull << 49;
+                            uint64_t mid = lo;
+                            for (int g = 0; g < 40 && !done && !have_hi; ++g) {
+                                uint64_t nm = mid + step; if (nm < mid) nm = ~0ull;
+                                nm &= ~0xffffffffull; if (nm <= mid) nm = ~0ull;
+                                mid = nm;
+                                uint32_t t2 = count_ge(mid);
+                                if (t2 > cap) { lo = mid; if (mid == ~0ull) break; }
+                                else if (t2 < k) { hi = mid; have_hi = true; }
+                                else { ntau = mid; done = true; }
+                                step <<= 1; if (step == 0) step = 1ull << 63;
+                            }
+                        }
+                        if (!done) {
+                            for (int g = 0; g < 96; ++g) {          // bisection; snap to pure-score pivots while possible
+                                if (hi - lo <= 1ull) break;
+                                uint64_t mid = lo + ((hi - lo) >> 1);
+                                if (hi - lo > (2ull << 32)) { mid &= ~0xffffffffull; if (mid <= lo) mid += 1ull << 32; }
+                                uint32_t t2 = count_ge(mid);
+                                if (t2 > cap) lo = mid; else if (t2 < k) hi = mid; else { ntau = mid; done = true; break; }
+                            }
+                            if (!done) ntau = lo;                    // unreachable for unique keys (superset, still exact)
+                        }
+                    }
+                    // ---- rebuild the list for ntau: surviving old entries, then this chunk's entries
+                    {
+                        const bool shrink = ntau > tau && list_n > 0;
+                        const int dst = shrink ? (cur ^ 1) : cur;
+                        if (shrink) {
+                            if (et == 0) sh->cursor = 0;
+                            epi_bar();
+                            for (uint32_t j0 = 0; j0 < list_n; j0 += kEpiThreads) {
+                                uint32_t j = j0 + et;
+                                uint64_t v = (j < list_n) ? L[cur * kListCap + j] : 0ull;
+                                bool keep = v >= ntau && v != 0ull;
+                                unsigned m = __ballot_sync(0xffffffffu, keep);
+                                uint32_t base = 0;
+                                if (lane == 0 && m) base = atomicAdd(&sh->cursor, (uint32_t)__popc(m));
+                                base = __shfl_sync(0xffffffffu, base, 0);
+                                if (keep) L[dst * kListCap + base + __popc(m & ((1u << lane) - 1u))] = v;
+                            }
+                        } else if (list_n == 0) {
+                            if (et == 0) sh->cursor = 0;
+                            epi_bar();
+                        }
+                        // chunk entries >= ntau
+                        const uint32_t ph = (uint32_t)(ntau >> 32), pl = (uint32_t)ntau;
+                        uint32_t mine = 0;
+#pragma unroll
+                        for (int a = 0; a < 3; ++a)
+#pragma unroll
+                            for (int i = 0; i < CCH; ++i) {
+                                uint32_t sv = sk[a][i];
+                                uint32_t nrow = ~(row0 + (uint32_t)(ch * CCH + i) * HW3 + (uint32_t)a);
+                                mine += (sv > ph || (sv == ph && nrow >= pl)) ? 1u : 0u;
+                            }
+                        uint32_t incl = mine;
+#pragma unroll
+                        for (int o = 1; o < 32; o <<= 1) { uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+                        uint32_t tot = __shfl_sync(0xffffffffu, incl, 31);
+                        uint32_t base = 0;
+                        if (lane == 31 && tot) base = atomicAdd(&sh->cursor, tot);
+                        base = __shfl_sync(0xffffffffu, base, 31);
+                        uint32_t pos = base + incl - mine;
+                        if (mine) {
+#pragma unroll
+                            for (int a = 0; a < 3; ++a)
+#pragma unroll
+                                for (int i = 0; i < CCH; ++i) {
+                                    uint32_t sv = sk[a][i];
+                                    uint32_t nrow = ~(row0 + (uint32_t)(ch * CCH + i) * HW3 + (uint32_t)a);
+                                    if (sv > ph || (sv == ph && nrow >= pl)) {
+                                        if (pos < (uint32_t)kListCap) L[dst * kListCap + pos] = ((uint64_t)sv << 32) | nrow;
+                                        ++pos;
+                                    }
+                                }
+                        }
+                        epi_bar();
+                        list_n = sh->cursor; if (list_n > (uint32_t)kListCap) list_n = kListCap;
+                        cur = dst; tau = ntau;
+                    }
+                }
+                // ---- flush the tile's candidate list
+                {
+                    const size_t li = (size_t)f * p.tiles_per_frame + p.tif_base[s] + pblk;
+                    uint64_t* gl = p.lists + li * kListCap;
+                    for (uint32_t j = et; j < list_n; j += kEpiThreads) gl[j] = L[cur * kListCap + j];
+                    if (et == 0) p.counts[li] = list_n;
+                    if (tau > 1ull) tau_guess = tau;
+                    epi_bar();                                      // list buffers are reused by the next tile
+                }
+            }
+        }
+    }
+
+    // ---------------- teardown
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 1) tc::tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+}
+
+// ----------------------------------------------------------------------------------------------
+// per-frame top-k + NMS on the tile lists (fused-path Source / Sink for nms_final_body)
+// ----------------------------------------------------------------------------------------------
+struct FusedSource {
+    HeadGeom g; const float4* boxes;
+    __device__ __forceinline__ void load(int f, uint32_t row, float, float4& bx, int& c, float& area) const {
+        int s = 0;
+#pragma unroll
+        for (int i = 1; i < VD_MAX_SCALES; ++i) if (i < g.num_scales && (int)row >= g.row_base[i]) s = i;
+        const int rs = (int)row - g.row_base[s];
+        const int per = g.HW[s] * 3;
+        c = rs / per;
+        const int slot = rs - c * per;
+        bx = boxes[(size_t)f * g.anc_base[g.num_scales] + g.anc_base[s] + slot];
+        area = __fmul_rn(__fsub_rn(bx.z, bx.x), __fsub_rn(bx.w, bx.y));
+    }
+};
+struct FusedSink {
+    float* ids; float* scores; float* bboxes; int32_t* keep; int post;
+    __device__ __forceinline__ void emit(int f, int pos, uint32_t row, float score, float4 bx, int c) const {
+        size_t o = (size_t)f * post + pos;
+        ids[o] = __fadd_rn(__fmul_rn(score, 0.0f), (float)c);
+        scores[o] = score;
+        reinterpret_cast<float4*>(bboxes)[o] = bx;
+        if (keep) keep[o] = (int32_t)row;
+    }
+    __device__ __forceinline__ void finish(int f, int kept) const {
+        for (int pos = kept + threadIdx.x; pos < post; pos += blockDim.x) {
+            size_t o = (size_t)f * post + pos;
+            ids[o] = -1.0f; scores[o] = -1.0f;
+            reinterpret_cast<float4*>(bboxes)[o] = make_float4(-1.f, -1.f, -1.f, -1.f);
+            if (keep) keep[o] = -1;
+        }
+    }
+};
+
+__global__ void __launch_bounds__(kFinalThreads, 1)
+nms_final_fused_kernel(const uint64_t* __restrict__ lists, const uint32_t* __restrict__ counts, int n_lists,
+                       NmsParams P, FusedSource src, FusedSink sink) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int f = blockIdx.x;
+    nms_final_body(lists + (size_t)f * n_lists * kListCap, counts + (size_t)f * n_lists, n_lists, f, P, src, sink, smem_raw);
+}
+
+// no-NMS tail (yolo3.py:525 false): rows are the plain concat; only reachable through vd_head_detections.
+
+// ----------------------------------------------------------------------------------------------
+// host side
+// ----------------------------------------------------------------------------------------------
+struct HeadPlan {
+    HeadKernelParams kp;
+    int n_pad, C;
+    int merge_levels;
+    size_t off_boxes, off_lists0, off_counts0, off_listsA, off_listsB, off_countsA, off_countsB, total;
+};
+
+static int head_npad(int C) { int n = 3 * (5 + C); return (n + 15) / 16 * 16; }
+
+static int make_plan(const VdHeadParams* hp, HeadPlan* pl) {
+    VD_CHECK_ARG(hp, "head: null params");
+    VD_CHECK_ARG(hp->num_scales >= 1 && hp->num_scales <= VD_MAX_SCALES, "head: num_scales %d", hp->num_scales);
+    VD_CHECK_ARG(hp->num_class >= 1, "head: num_class %d", hp->num_class);
+    VD_CHECK_ARG(hp->frames >= 0 && hp->frames <= 65535, "head: frames %d out of range", hp->frames);
+    const int C = hp->num_class;
+    const int npad = head_npad(C);
+    if (npad > 256) return set_error(VD_ERR_UNSUPPORTED, "head: 3*(5+%d) = %d prediction channels > 256 not supported by the fused kernel yet", C, 3 * (5 + C));
+    memset(pl, 0, sizeof(*pl));
+    HeadKernelParams& k = pl->kp;
+    pl->n_pad = npad; pl->C = C;
+    k.g.num_scales = hp->num_scales; k.g.num_class = C; k.g.A = 3;
+    k.frames = hp->frames; k.n_pad = npad; k.n_valid = 3 * (5 + C);
+    const int join = hp->join;
+    VD_CHECK_ARG(join == VD_JOIN_NONE || join == VD_JOIN_CAT, "head: join %d must be pre-reduced (use vd_temporal_pool for max/mean)", join);
+    k.K_frames = (join == VD_JOIN_CAT) ? hp->K_frames : 1;
+    VD_CHECK_ARG(k.K_frames >= 1, "head: K_frames %d", k.K_frames);
+    int rows = 0, anc = 0, tif = 0, tiles = 0;
+    for (int s = 0; s < hp->num_scales; ++s) {
+        const VdHeadScale& sc = hp->scale[s];
+        VD_CHECK_ARG(sc.H > 0 && sc.W > 0 && sc.H <= 128 && sc.W <= 128, "head: scale %d feature map %dx%d (alloc_size is 128x128, yolo3.py:44)", s, sc.H, sc.W);
+        VD_CHECK_ARG(sc.Cin > 0 && sc.Cin % BLOCK_K == 0, "head: scale %d Cin %d must be a multiple of %d", s, sc.Cin, BLOCK_K);
+        VD_CHECK_ARG(sc.tip_nhwc_bf16 && sc.weight_bf16, "head: scale %d null tip/weight", s);
+        VD_CHECK_ARG(((uintptr_t)sc.tip_nhwc_bf16 & 15) == 0 && ((uintptr_t)sc.weight_bf16 & 15) == 0, "head: scale %d tensors must be 16-byte aligned", s);
+        k.g.H[s] = sc.H; k.g.W[s] = sc.W; k.g.HW[s] = sc.H * sc.W;
+        k.g.stride[s] = sc.stride;
+        for (int i = 0; i < 6; ++i) k.g.anchors[s][i] = sc.anchors[i];
+        k.g.row_base[s] = rows; k.g.anc_base[s] = anc;
+        rows += C * k.g.HW[s] * 3; anc += k.g.HW[s] * 3;
+        k.cin[s] = sc.Cin; k.bias[s] = sc.bias;
+        k.pb[s] = ceil_div(k.g.HW[s], BLOCK_M);
+        k.tif_base[s] = tif; tif += k.pb[s];
+        k.tile_start[s] = tiles; tiles += k.pb[s] * hp->frames;
+    }
+    for (int s = hp->num_scales; s <= VD_MAX_SCALES; ++s) { k.g.row_base[s] = rows; k.g.anc_base[s] = anc; if (s <= VD_MAX_SCALES) k.tile_start[s] = tiles; }
+    k.g.row_base[hp->num_scales] = rows; k.g.anc_base[hp->num_scales] = anc; k.tile_start[hp->num_scales] = tiles;
+    k.tiles_per_frame = tif; k.total_tiles = tiles;
+    // workspace
+    size_t off = 0;
+    const size_t F = (size_t)(hp->frames > 0 ? hp->frames : 1);
+    pl->off_boxes = off; off += align_up(F * anc * 16, 256);
+    pl->off_lists0 = off; off += align_up(F * tif * kListCap * 8, 256);
+    pl->off_counts0 = off; off += align_up(F * tif * 4, 256);
+    int n1 = ceil_div(tif, kMaxLists);
+    pl->off_listsA = off; off += align_up(F * n1 * kListCap * 8, 256);
+    pl->off_listsB = off; off += align_up(F * n1 * kListCap * 8, 256);
+    pl->off_countsA = off; off += align_up(F * n1 * 4, 256);
+    pl->off_countsB = off; off += align_up(F * n1 * 4, 256);
+    pl->total = off;
+    return VD_OK;
+}
+
+static int make_maps(const VdHeadParams* hp, const HeadPlan& pl, HeadMaps* maps) {
+    for (int s = 0; s < hp->num_scales; ++s) {
+        const VdHeadScale& sc = hp->scale[s];
+        const uint64_t HW = (uint64_t)sc.H * sc.W, Cin = sc.Cin, K = pl.kp.K_frames;
+        const void* aptr = (sc.tconv_weight_bf16 && sc.tconv_out_nhwc_bf16) ? sc.tconv_out_nhwc_bf16 : sc.tip_nhwc_bf16;
+        uint64_t dimsA[4] = {Cin, HW, K, (uint64_t)(hp->frames > 0 ? hp->frames : 1)};
+        uint64_t strA[3] = {Cin * 2, HW * Cin * 2, K * HW * Cin * 2};
+        uint32_t boxA[4] = {BLOCK_K, BLOCK_M, 1, 1};
+        int rc = encode_tmap_bf16(&maps->a[s], aptr, 4, dimsA, strA, boxA);
+        if (rc) return rc;
+        uint64_t dimsW[2] = {Cin * K, (uint64_t)3 * (5 + pl.C)};
+        uint64_t strW[1] = {Cin * K * 2};
+        uint32_t boxW[2] = {BLOCK_K, (uint32_t)pl.n_pad};
+        rc = encode_tmap_bf16(&maps->w[s], sc.weight_bf16, 2, dimsW, strW, boxW);
+        if (rc) return rc;
+    }
+    return VD_OK;
+}
+
+template <int EPI, int C, int NPAD>
+static int launch_head_t(const HeadMaps& maps, const HeadKernelParams& kp, cudaStream_t stream) {
+    using Cfg = HeadCfg<NPAD>;
+    auto kern = head_kernel<EPI, C, NPAD>;
+    VD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    int grid = sm_count(); if (grid > kp.total_tiles) grid = kp.total_tiles;
+    if (grid < 1) return VD_OK;
+    kern<<<grid, kHeadThreads, Cfg::SMEM_BYTES, stream>>>(maps, kp);
+    VD_LAUNCH_CHECK();
+    return VD_OK;
+}
+
+template <int EPI>
+static int launch_head(const HeadMaps& maps, const HeadKernelParams& kp, int C, cudaStream_t stream) {
+    switch (C) {
+        case 20: return launch_head_t<EPI, 20, 80>(maps, kp, stream);     // VOC
+        case 30: return launch_head_t<EPI, 30, 112>(maps, kp, stream);    // ImageNet-VID
+        case 80: return launch_head_t<EPI, 80, 256>(maps, kp, stream);    // COCO
+        case 1:  return launch_head_t<EPI, 1, 32>(maps, kp, stream);
+        case 2:  return launch_head_t<EPI, 2, 32>(maps, kp, stream);
+        case 3:  return launch_head_t<EPI, 3, 32>(maps, kp, stream);
+        case 4:  return launch_head_t<EPI, 4, 32>(maps, kp, stream);
+        case 5:  return launch_head_t<EPI, 5, 32>(maps, kp, stream);
+        default: break;
+    }
+    return set_error(VD_ERR_UNSUPPORTED, "head: num_class %d has no compiled fused instantiation (have 1-5, 20, 30, 80); "
+                     "use vd_pred_conv + vd_yolo_decode + vd_box_nms", C);
+}
+
+// EPI_PRED only depends on the padded width
+static int launch_pred(const HeadMaps& maps, const HeadKernelParams& kp, cudaStream_t stream) {
+    switch (kp.n_pad) {
+        case 16:  return launch_head_t<EPI_PRED, 1, 16>(maps, kp, stream);
+        case 32:  return launch_head_t<EPI_PRED, 1, 32>(maps, kp, stream);
+        case 48:  return launch_head_t<EPI_PRED, 1, 48>(maps, kp, stream);
+        case 64:  return launch_head_t<EPI_PRED, 1, 64>(maps, kp, stream);
+        case 80:  return launch_head_t<EPI_PRED, 1, 80>(maps, kp, stream);
+        case 96:  return launch_head_t<EPI_PRED, 1, 96>(maps, kp, stream);
+        case 112: return launch_head_t<EPI_PRED, 1, 112>(maps, kp, stream);
+        case 128: return launch_head_t<EPI_PRED, 1, 128>(maps, kp, stream);
+        case 144: return launch_head_t<EPI_PRED, 1, 144>(maps, kp, stream);
+        case 160: return launch_head_t<EPI_PRED, 1, 160>(maps, kp, stream);
+        case 176: return launch_head_t<EPI_PRED, 1, 176>(maps, kp, stream);
+        case 192: return launch_head_t<EPI_PRED, 1, 192>(maps, kp, stream);
+        case 208: return launch_head_t<EPI_PRED, 1, 208>(maps, kp, stream);
+        case 224: return launch_head_t<EPI_PRED, 1, 224>(maps, kp, stream);
+        case 240: return launch_head_t<EPI_PRED, 1, 240>(maps, kp, stream);
+        case 256: return launch_head_t<EPI_PRED, 1, 256>(maps, kp, stream);
+        default: break;
+    }
+    return set_error(VD_ERR_INVALID_ARG, "pred_conv: bad padded width %d", kp.n_pad);
+}
+
+}  // namespace vd
+
+using namespace vd;
+
+extern "C" size_t vd_head_workspace_bytes(const VdHeadParams* p) {
+    HeadPlan pl;
+    if (make_plan(p, &pl) != VD_OK) return 0;
+    return pl.total;
+}
+
+extern "C" int vd_head_forward(const VdHeadParams* hp, float* ids, float* scores, float* bboxes,
+                               int32_t* keep_rows_or_null, void* workspace, size_t workspace_bytes, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    HeadPlan pl;
+    int rc = make_plan(hp, &pl);
+    if (rc) return rc;
+    VD_CHECK_ARG(ids && scores && bboxes, "head_forward: null output");
+    VD_CHECK_ARG(hp->nms_thresh > 0.f && hp->nms_thresh < 1.f,
+                 "head_forward: nms_thresh %g disables NMS (yolo3.py:525); use vd_head_detections for the raw rows", hp->nms_thresh);
+    VD_CHECK_ARG(hp->post_nms > 0, "head_forward: post_nms must be > 0 (use vd_head_detections + vd_box_nms for the unsliced output)");
+    const long long rows = pl.kp.g.row_base[hp->num_scales];
+    long long k64 = (hp->nms_topk > 0 && hp->nms_topk < rows) ? hp->nms_topk : rows;
+    if (k64 > VD_MAX_TOPK) return set_error(VD_ERR_UNSUPPORTED, "head_forward: nms_topk %lld > VD_MAX_TOPK %d", k64, VD_MAX_TOPK);
+    if (!workspace || workspace_bytes < pl.total) return set_error(VD_ERR_WORKSPACE, "head_forward: workspace %zu < required %zu", workspace_bytes, pl.total);
+    VD_CHECK_ARG(((uintptr_t)bboxes & 15) == 0, "head_forward: bboxes must be 16-byte aligned");
+    if (hp->frames == 0) return VD_OK;
+    const int k = (int)k64;
+    unsigned char* ws = (unsigned char*)workspace;
+    HeadKernelParams& kp = pl.kp;
+    kp.boxes = (float4*)(ws + pl.off_boxes);
+    kp.lists = (uint64_t*)(ws + pl.off_lists0);
+    kp.counts = (uint32_t*)(ws + pl.off_counts0);
+    kp.valid_thresh = hp->valid_thresh; kp.k = k; kp.cap = (k <= 448) ? 512 : kListCap;
+
+    for (int s = 0; s < hp->num_scales; ++s) {      // optional temporal tip cell in front (layers.py:82-89)
+        const VdHeadScale& sc = hp->scale[s];
+        if (sc.tconv_weight_bf16) {
+            VD_CHECK_ARG(sc.tconv_out_nhwc_bf16 && sc.tconv_scale && sc.tconv_shift, "head_forward: scale %d temporal cell needs out/scale/shift", s);
+            VD_CHECK_ARG(hp->T >= 1 && hp->frames % hp->T == 0, "head_forward: frames %d not a multiple of T %d", hp->frames, hp->T);
+            rc = vd_temporal_conv(sc.tip_nhwc_bf16, sc.tconv_out_nhwc_bf16, hp->frames / hp->T, hp->T, sc.H, sc.W, sc.Cin,
+                                  sc.tconv_weight_bf16, sc.tconv_scale, sc.tconv_shift, 0.1f, stream_);
+            if (rc) return rc;
+        }
+    }
+    HeadMaps maps;
+    rc = make_maps(hp, pl, &maps);
+    if (rc) return rc;
+    rc = launch_head<EPI_FILTER>(maps, kp, pl.C, stream);
+    if (rc) return rc;
+
+    const uint64_t* lists = kp.lists; const uint32_t* counts = kp.counts; int n_lists = kp.tiles_per_frame;
+    uint64_t* lout = (uint64_t*)(ws + pl.off_listsA); uint32_t* cout = (uint32_t*)(ws + pl.off_countsA);
+    uint64_t* lalt = (uint64_t*)(ws + pl.off_listsB); uint32_t* calt = (uint32_t*)(ws + pl.off_countsB);
+    while (n_lists > kMaxLists) {
+        int n_out = ceil_div(n_lists, kMaxLists);
+        nms_merge_kernel<<<dim3(n_out, hp->frames), kFinalThreads, 0, stream>>>(lists, counts, n_lists, lout, cout, n_out, k);
+        VD_LAUNCH_CHECK();
+        lists = lout; counts = cout; n_lists = n_out;
+        uint64_t* tl = lout; lout = lalt; lalt = tl; uint32_t* tcn = cout; cout = calt; calt = tcn;
+    }
+    NmsParams P;
+    P.overlap_thresh = hp->nms_thresh; P.k = k; P.sortn = nms_sortn(k); P.class_aware = 1;
+    P.max_out = hp->post_nms;
+    FusedSource src{kp.g, kp.boxes};
+    FusedSink sink{ids, scores, bboxes, keep_rows_or_null, hp->post_nms};
+    size_t smem = nms_final_smem(k);
+    VD_CUDA(cudaFuncSetAttribute(nms_final_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    nms_final_fused_kernel<<<hp->frames, kFinalThreads, smem, stream>>>(lists, counts, n_lists, P, src, sink);
+    VD_LAUNCH_CHECK();
+    return VD_OK;
+}
+
+extern "C" int vd_head_detections(const VdHeadParams* hp, float* det, void* workspace, size_t workspace_bytes, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    (void)workspace; (void)workspace_bytes;
+    HeadPlan pl;
+    int rc = make_plan(hp, &pl);
+    if (rc) return rc;
+    VD_CHECK_ARG(det, "head_detections: null output");
+    VD_CHECK_ARG(((uintptr_t)det & 7) == 0, "head_detections: det must be 8-byte aligned");
+    if (hp->frames == 0) return VD_OK;
+    HeadKernelParams& kp = pl.kp;
+    kp.det = det; kp.det_rows_total = kp.g.row_base[hp->num_scales];
+    for (int s = 0; s < hp->num_scales; ++s) {
+        const VdHeadScale& sc = hp->scale[s];
+        if (sc.tconv_weight_bf16) {
+            VD_CHECK_ARG(sc.tconv_out_nhwc_bf16 && sc.tconv_scale && sc.tconv_shift, "head_detections: scale %d temporal cell needs out/scale/shift", s);
+            VD_CHECK_ARG(hp->T >= 1 && hp->frames % hp->T == 0, "head_detections: frames %d not a multiple of T %d", hp->frames, hp->T);
+            rc = vd_temporal_conv(sc.tip_nhwc_bf16, sc.tconv_out_nhwc_bf16, hp->frames / hp->T, hp->T, sc.H, sc.W, sc.Cin,
+                                  sc.tconv_weight_bf16, sc.tconv_scale, sc.tconv_shift, 0.1f, stream_);
+            if (rc) return rc;
+        }
+    }
+    HeadMaps maps;
+    rc = make_maps(hp, pl, &maps);
+    if (rc) return rc;
+    return launch_head<EPI_DET>(maps, kp, pl.C, stream);
+}
+
+extern "C" int vd_pred_conv(const void* x, int B, int H, int W, int Cin, int K_frames, int join,
+                            const void* weight, const float* bias, int N, float* pred, void* stream_) {
+    VD_CHECK_ARG(x && weight && pred, "pred_conv: null pointer");
+    VD_CHECK_ARG(B >= 0 && B <= 65535 && H > 0 && W > 0 && N > 0, "pred_conv: bad shape");
+    VD_CHECK_ARG(Cin > 0 && Cin % BLOCK_K == 0, "pred_conv: Cin %d must be a multiple of %d", Cin, BLOCK_K);
+    VD_CHECK_ARG(join == VD_JOIN_NONE || join == VD_JOIN_CAT, "pred_conv: join %d must be pre-reduced (vd_temporal_pool)", join);
+    VD_CHECK_ARG(((uintptr_t)x & 15) == 0 && ((uintptr_t)weight & 15) == 0, "pred_conv: tensors must be 16-byte aligned");
+    if (B == 0) return VD_OK;
+    const int K = (join == VD_JOIN_CAT) ? K_frames : 1;
+    VD_CHECK_ARG(K >= 1, "pred_conv: K_frames %d", K_frames);
+    const uint64_t HW = (uint64_t)H * W;
+    for (int n0 = 0; n0 < N; n0 += 256) {            // output-channel slices of <= 256 rows of W
+        const int nn = (N - n0) < 256 ? (N - n0) : 256;
+        HeadKernelParams kp; memset(&kp, 0, sizeof(kp));
+        kp.g.num_scales = 1; kp.g.num_class = 1; kp.g.A = 3;
+        kp.g.H[0] = H; kp.g.W[0] = W; kp.g.HW[0] = (int)HW; kp.g.stride[0] = 1.f;
+        kp.frames = B; kp.K_frames = K; kp.cin[0] = Cin;
+        kp.pb[0] = ceil_div((int)HW, BLOCK_M);
+        kp.tile_start[0] = 0; kp.tile_start[1] = kp.pb[0] * B;
+        kp.tiles_per_frame = kp.pb[0]; kp.total_tiles = kp.pb[0] * B;
+        kp.n_pad = (nn + 15) / 16 * 16; kp.n_valid = nn;
+        kp.bias[0] = bias ? bias + n0 : nullptr;
+        kp.pred[0] = pred + (size_t)n0 * HW; kp.pred_frame_stride = (long long)N * (long long)HW;
+        HeadMaps maps;
+        uint64_t dimsA[4] = {(uint64_t)Cin, HW, (uint64_t)K, (uint64_t)B};
+        uint64_t strA[3] = {(uint64_t)Cin * 2, HW * Cin * 2, (uint64_t)K * HW * Cin * 2};
+        uint32_t boxA[4] = {BLOCK_K, BLOCK_M, 1, 1};
+        int rc = encode_tmap_bf16(&maps.a[0], x, 4, dimsA, strA, boxA);
+        if (rc) return rc;
+        uint64_t dimsW[2] = {(uint64_t)Cin * K, (uint64_t)nn};
+        uint64_t strW[1] = {(uint64_t)Cin * K * 2};
+        uint32_t boxW[2] = {BLOCK_K, (uint32_t)kp.n_pad};
+        rc = encode_tmap_bf16(&maps.w[0], (const unsigned char*)weight + (size_t)n0 * Cin * K * 2, 2, dimsW, strW, boxW);
+        if (rc) return rc;
+        maps.a[1] = maps.a[2] = maps.a[0]; maps.w[1] = maps.w[2] = maps.w[0];
+        rc = launch_pred(maps, kp, (cudaStream_t)stream_);
+        if (rc) return rc;
+    }
+    return VD_OK;
+}

@@ -1,0 +1,231 @@
+// Per-image exact top-k + class-aware greedy NMS, executed by ONE CTA per image on candidate
+// lists produced upstream (box_nms filter kernel or the fused head epilogue).
+//
+// Replaces the sort + `nms_impl` x topk sequential launches + `nms_assign` inside MXNet's
+// _contrib_box_nms (call sites yolo3.py:526-528, yolo3_temporal.py:545-547); semantics =
+// SURVEY.md Appendix A.3 (stable descending order, topk cut, class-aware IoU > thresh in rank
+// order, compaction, -1 fill).
+//
+// Pipeline inside the CTA:
+//   1. gather <= 8 candidate lists (<= 1024 keys each) into registers
+//   2. block_select_pivot -> compact the best <= SORTN keys to shared memory -> bitonic sort
+//   3. n = min(k, #valid) ranks; gather box / class / area per rank (Source policy)
+//   4. suppression bit-matrix  mask[r][p/32] bit p%32 = "r suppresses p" (p > r)
+//        class-aware: secondary sort by (class, rank) so only same-class pairs are evaluated
+//        class-agnostic / force_suppress: dense warp-ballot rows
+//   5. one warp runs the sequential greedy scan over 32-rank blocks (diagonal words resolved
+//      in-register, alive rows OR-ed into the running removed set)
+//   6. survivors -> consecutive output rows (Sink policy)
+#pragma once
+#include "select.cuh"
+
+namespace vd {
+
+constexpr int kListCap = 1024;          // capacity of one candidate list
+constexpr int kMaxLists = 8;            // lists merged per CTA
+constexpr int kFinalThreads = 512;
+constexpr int kFinalR = kListCap * kMaxLists / kFinalThreads;   // 16 keys / thread
+
+struct NmsParams {
+    float overlap_thresh;
+    int k;              // min(topk, num_elem) <= VD_MAX_TOPK
+    int sortn;          // power of two >= k, >= 512
+    int class_aware;    // !force_suppress && id_index >= 0
+    int max_out;        // rows to emit per image (post_nms for the fused head, k for box_nms)
+};
+
+static inline int nms_sortn(int k) { return k <= 512 ? 512 : 1024; }
+static inline int nms_words(int k) { return (k + 31) / 32; }
+// dynamic shared memory of nms_final_kernel
+static inline size_t nms_final_smem(int k) {
+    size_t sortn = nms_sortn(k);
+    size_t b = sortn * 8;                              // sorted keys
+    b += (size_t)k * 16;                               // boxes (corner)
+    b += (size_t)k * 4 * 2;                            // class, area
+    b += (size_t)k * nms_words(k) * 4;                 // suppression matrix
+    b += (size_t)sortn * 4;                            // (class,rank) secondary sort keys
+    b += 64 * 4 + 64 * 4;                              // alive words + prefix
+    b += sizeof(SelectScratch) + 64;
+    return b;
+}
+
+// bitonic sort of u32 (ascending), SN power of two
+__device__ __forceinline__ void bitonic_sort_u32_asc(uint32_t* s, int SN) {
+    for (int size = 2; size <= SN; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            __syncthreads();
+            for (int t = threadIdx.x; t < (SN >> 1); t += blockDim.x) {
+                int i = 2 * t - (t & (stride - 1));
+                int j = i + stride;
+                bool asc = ((i & size) == 0);
+                uint32_t a = s[i], b = s[j];
+                if ((a > b) == asc) { s[i] = b; s[j] = a; }
+            }
+        }
+    }
+    __syncthreads();
+}
+
+// Source: gives box (corner), integer class and area for (image b, row).  Sink: writes output.
+template <class Source, class Sink>
+__device__ void nms_final_body(const uint64_t* __restrict__ lists, const uint32_t* __restrict__ counts,
+                               int n_lists, int b, NmsParams P, const Source& src, const Sink& sink,
+                               unsigned char* smem_raw) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    const int k = P.k, SN = P.sortn, NW = (k + 31) >> 5;
+    // ---- carve shared memory
+    uint64_t* skeys = reinterpret_cast<uint64_t*>(smem_raw);
+    float4* sbox = reinterpret_cast<float4*>(skeys + SN);
+    int* scls = reinterpret_cast<int*>(sbox + k);
+    float* sarea = reinterpret_cast<float*>(scls + k);
+    uint32_t* smask = reinterpret_cast<uint32_t*>(sarea + k);
+    uint32_t* skey2 = smask + (size_t)k * NW;
+    uint32_t* salive = skey2 + SN;
+    uint32_t* sprefix = salive + 64;
+    SelectScratch* scr = reinterpret_cast<SelectScratch*>(sprefix + 64);
+
+    select_scratch_init(scr);
+    for (int i = tid; i < SN; i += blockDim.x) skeys[i] = 0ull;
+
+    // ---- 1. gather lists into registers
+    uint64_t keys[kFinalR];
+#pragma unroll
+    for (int r = 0; r < kFinalR; ++r) {
+        int slot = r * kFinalThreads + tid;            // list = slot / kListCap
+        int l = slot / kListCap, j = slot % kListCap;
+        uint64_t v = 0ull;
+        if (l < n_lists) {
+            uint32_t c = counts[l]; c = c > (uint32_t)kListCap ? (uint32_t)kListCap : c;
+            if ((uint32_t)j < c) v = lists[(size_t)l * kListCap + j];
+        }
+        keys[r] = v;
+    }
+    // ---- 2. select + sort
+    int it = 0; uint32_t nsel = 0;
+    uint64_t piv = block_select_pivot<kFinalR>(keys, (uint32_t)k, (uint32_t)SN, 0ull, 0ull, scr, it, &nsel);
+    block_compact<kFinalR>(keys, piv, skeys, (uint32_t)SN, &scr->out_count);
+    bitonic_sort_desc(skeys, SN);                      // starts and ends with __syncthreads
+    const int n = (int)(nsel < (uint32_t)k ? nsel : (uint32_t)k);
+
+    // ---- 3. per-rank box / class / area
+    for (int r = tid; r < n; r += blockDim.x) {
+        float4 bx; int c; float ar;
+        src.load(b, key_row(skeys[r]), key_score(skeys[r]), bx, c, ar);
+        sbox[r] = bx; scls[r] = c; sarea[r] = ar;
+    }
+    for (int i = tid; i < n * NW; i += blockDim.x) smask[i] = 0u;
+    __syncthreads();
+
+    // ---- 4. suppression matrix
+    if (P.class_aware) {
+        // secondary key (class bucket, rank): same-class ranks become contiguous, rank ascending
+        for (int i = tid; i < SN; i += blockDim.x)
+            skey2[i] = (i < n) ? (((uint32_t)scls[i] << 10) | (uint32_t)i) : 0xffffffffu;
+        bitonic_sort_u32_asc(skey2, SN);
+        for (int i = tid; i < n; i += blockDim.x) {
+            uint32_t ki = skey2[i];
+            int r = (int)(ki & 1023u); uint32_t ci = ki >> 10;
+            float4 br = sbox[r]; float ar = sarea[r];
+            for (int j = i + 1; j < n; ++j) {
+                uint32_t kj = skey2[j];
+                if ((kj >> 10) != ci) break;
+                int p = (int)(kj & 1023u);             // p > r (rank ascending inside a bucket)
+                if (scls[p] != scls[r]) continue;      // bucket = low 22 bits of the id; compare the full int
+                if (vd_iou_gt(br, ar, sbox[p], sarea[p], P.overlap_thresh))
+                    atomicOr(&smask[r * NW + (p >> 5)], 1u << (p & 31));
+            }
+        }
+    } else {
+        for (int r = warp; r < n; r += nwarps) {
+            float4 br = sbox[r]; float ar = sarea[r];
+            for (int w = r >> 5; w < NW; ++w) {
+                int p = (w << 5) + lane;
+                bool s = false;
+                if (p > r && p < n) s = vd_iou_gt(br, ar, sbox[p], sarea[p], P.overlap_thresh);
+                unsigned m = __ballot_sync(0xffffffffu, s);
+                if (lane == 0) smask[r * NW + w] = m;
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- 5. greedy scan (warp 0): lane l owns removed-bits of ranks 32l .. 32l+31
+    if (warp == 0) {
+        uint32_t removed = 0u;
+        int kept_total = 0;
+        for (int w = 0; w < NW; ++w) {
+            const int base = w << 5;
+            uint32_t cur = __shfl_sync(0xffffffffu, removed, w);
+            const int rr = base + lane;
+            uint32_t diag = (rr < n) ? smask[rr * NW + w] : 0u;
+            unsigned nz = __ballot_sync(0xffffffffu, diag != 0u);
+            while (nz) {                               // rows of this block that suppress inside it
+                int j = __ffs(nz) - 1; nz &= nz - 1;
+                uint32_t dj = __shfl_sync(0xffffffffu, diag, j);
+                if (!((cur >> j) & 1u)) cur |= dj;
+            }
+            uint32_t validbits = (n - base >= 32) ? 0xffffffffu : ((1u << (n - base)) - 1u);
+            uint32_t alive = ~cur & validbits;
+            if (lane == w) removed = cur;
+            if (lane == 0) { salive[w] = alive; sprefix[w] = (uint32_t)kept_total; }
+            kept_total += __popc(alive);
+            if (kept_total >= P.max_out) {             // later ranks cannot reach the output
+                for (int w2 = w + 1 + lane; w2 < NW; w2 += 32) { salive[w2] = 0u; sprefix[w2] = (uint32_t)kept_total; }
+                break;
+            }
+            uint32_t a = alive;
+            while (a) {                                // alive rows suppress later blocks
+                int j = __ffs(a) - 1; a &= a - 1;
+                if (lane > w && lane < NW) removed |= smask[(base + j) * NW + lane];
+            }
+        }
+        if (lane == 0) sprefix[63] = (uint32_t)kept_total;
+    }
+    __syncthreads();
+
+    // ---- 6. emit survivors
+    const int kept_total = (int)sprefix[63];
+    for (int r = tid; r < n; r += blockDim.x) {
+        uint32_t aw = salive[r >> 5];
+        if ((aw >> (r & 31)) & 1u) {
+            int pos = (int)sprefix[r >> 5] + __popc(aw & ((1u << (r & 31)) - 1u));
+            if (pos < P.max_out) sink.emit(b, pos, key_row(skeys[r]), key_score(skeys[r]), sbox[r], scls[r]);
+        }
+    }
+    sink.finish(b, kept_total < P.max_out ? kept_total : P.max_out);
+}
+
+// Intermediate level: merge <= 8 lists into one list holding a superset (<= kListCap) of their
+// joint top-k.  grid (n_groups, num_batch).
+static __global__ void __launch_bounds__(kFinalThreads, 1)
+nms_merge_kernel(const uint64_t* __restrict__ lists_in, const uint32_t* __restrict__ counts_in,
+                 int n_lists_in, uint64_t* __restrict__ lists_out, uint32_t* __restrict__ counts_out,
+                 int n_lists_out, int k) {
+    __shared__ SelectScratch scr;
+    __shared__ uint64_t stage[kListCap];
+    const int g = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+    select_scratch_init(&scr);
+    const uint64_t* lin = lists_in + (size_t)b * n_lists_in * kListCap;
+    const uint32_t* cin = counts_in + (size_t)b * n_lists_in;
+    uint64_t keys[kFinalR];
+#pragma unroll
+    for (int r = 0; r < kFinalR; ++r) {
+        int slot = r * kFinalThreads + tid;
+        int l = g * kMaxLists + slot / kListCap, j = slot % kListCap;
+        uint64_t v = 0ull;
+        if (l < n_lists_in) {
+            uint32_t c = cin[l]; c = c > (uint32_t)kListCap ? (uint32_t)kListCap : c;
+            if ((uint32_t)j < c) v = lin[(size_t)l * kListCap + j];
+        }
+        keys[r] = v;
+    }
+    int it = 0; uint32_t nsel = 0;
+    uint64_t piv = block_select_pivot<kFinalR>(keys, (uint32_t)k, (uint32_t)kListCap, 0ull, 0ull, &scr, it, &nsel);
+    block_compact<kFinalR>(keys, piv, stage, (uint32_t)kListCap, &scr.out_count);
+    __syncthreads();
+    uint64_t* lout = lists_out + ((size_t)b * n_lists_out + g) * kListCap;
+    for (int i = tid; i < (int)nsel; i += blockDim.x) lout[i] = stage[i];
+    if (tid == 0) counts_out[(size_t)b * n_lists_out + g] = nsel;
+}
+
+}  // namespace vd

@@ -1,0 +1,215 @@
+// vd_temporal_conv -- the temporal (3,1,1) cell of the (2+1)D tip:
+//   Conv3D(C -> C, kernel (3,1,1), pad (1,0,0), stride 1, no bias) + BatchNorm(eps 1e-5) + LeakyReLU(0.1)
+//   (models/definitions/layers.py:82-89 `_conv21d` second cell -> :73-79 `_conv3d`; used as the
+//   detection block's tip at yolo3_temporal.py:226-227, whose output feeds YOLOOutputV3 directly).
+//
+// Implicit GEMM on tcgen05:  Y[b, r, :] = lrelu(scale * sum_{dt=-1..1} X[b, r + dt*HW, :] @ W_dt^T + shift)
+// with r = t*HW + pixel flattened over the window, so the zero padding in time IS the TMA
+// out-of-bounds fill of the 3-D map (C, T*HW, B): rows r + dt*HW outside [0, T*HW) read as zeros,
+// and taps that are out of range for a whole tile are skipped (13 of 15 taps do work at T=5).
+//   warp 0: TMA producer (A tile [128 rows x 64 ch] of the shifted frame + W_dt tile [NT x 64])
+//   warp 1: MMA issuer, M=128 x N=NT x K=16, accumulators double-buffered in TMEM
+//   warps 2-5: epilogue: tcgen05.ld -> folded BN -> LeakyReLU -> bf16 -> 128-bit stores
+#include "tc.cuh"
+
+namespace vd {
+
+constexpr int T_BLOCK_M = 128;
+constexpr int T_BLOCK_K = 64;
+constexpr int T_THREADS = 192;
+
+struct TConvParams {
+    int B, T, HW, C, rows;         // rows = T*HW
+    int m_tiles, n_tiles, total_tiles;
+    const float* scale; const float* shift; float slope;
+    __nv_bfloat16* y;
+};
+struct TConvMaps { CUtensorMap x; CUtensorMap w; };
+
+template <int NT> struct TConvCfg {
+    static constexpr int A_BYTES = T_BLOCK_M * T_BLOCK_K * 2;
+    static constexpr int B_BYTES = NT * T_BLOCK_K * 2;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int STAGES = (200 * 1024) / STAGE_BYTES > 8 ? 8 : (200 * 1024) / STAGE_BYTES;
+    static constexpr int TMEM_COLS = 2 * NT;            // NT in {128, 256}
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2048 + 1024;
+};
+
+struct TShared {
+    uint64_t full[8], empty[8], tmem_full[2], tmem_empty[2];
+    uint32_t tmem_base;
+};
+
+template <int NT>
+__global__ void __launch_bounds__(T_THREADS, 1)
+temporal_conv_kernel(const __grid_constant__ TConvMaps maps, const __grid_constant__ TConvParams p) {
+    using Cfg = TConvCfg<NT>;
+    extern __shared__ unsigned char smem_dyn[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+    unsigned char* ring = smem;
+    TShared* sh = reinterpret_cast<TShared*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < Cfg::STAGES; ++i) { tc::mbar_init(&sh->full[i], 1); tc::mbar_init(&sh->empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { tc::mbar_init(&sh->tmem_full[i], 1); tc::mbar_init(&sh->tmem_empty[i], 4); }
+        tc::fence_barrier_init();
+        tc::prefetch_tmap(&maps.x); tc::prefetch_tmap(&maps.w);
+    }
+    if (warp == 1) tc::tmem_alloc<Cfg::TMEM_COLS>(&sh->tmem_base);
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem_base = sh->tmem_base;
+    const int kb_per_tap = p.C / T_BLOCK_K;
+
+    // tile -> (window b, row block mt, channel block nt); nt fastest so A tiles are re-read from L2
+    auto coords = [&](int tile, int& b, int& mt, int& nt) {
+        nt = tile % p.n_tiles; int r = tile / p.n_tiles; mt = r % p.m_tiles; b = r / p.m_tiles;
+    };
+    auto tap_active = [&](int mt, int dt) -> bool {   // does any row of the tile see frame t+dt inside the window?
+        const int r0 = mt * T_BLOCK_M;
+        int r1 = r0 + T_BLOCK_M - 1; if (r1 > p.rows - 1) r1 = p.rows - 1;
+        return (r1 + dt * p.HW >= 0) && (r0 + dt * p.HW <= p.rows - 1);
+    };
+
+    if (warp == 0) {
+        if (tc::elect_one()) {
+            int stage = 0; uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+                int b, mt, nt; coords(tile, b, mt, nt);
+                for (int tap = 0; tap < 3; ++tap) {
+                    const int dt = tap - 1;
+                    if (!tap_active(mt, dt)) continue;
+                    for (int kb = 0; kb < kb_per_tap; ++kb) {
+                        tc::mbar_wait(&sh->empty[stage], phase ^ 1u);
+                        unsigned char* a_dst = ring + stage * Cfg::STAGE_BYTES;
+                        tc::mbar_expect_tx(&sh->full[stage], Cfg::STAGE_BYTES);
+                        tc::tma_load_3d(a_dst, &maps.x, &sh->full[stage], kb * T_BLOCK_K, mt * T_BLOCK_M + dt * p.HW, b);
+                        tc::tma_load_3d(a_dst + Cfg::A_BYTES, &maps.w, &sh->full[stage], kb * T_BLOCK_K, nt * NT, tap);
+                        if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (tc::elect_one()) {
+            constexpr uint32_t idesc = tc::make_idesc_bf16(T_BLOCK_M, NT);
+            int stage = 0; uint32_t phase = 0; uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+                int b, mt, nt; coords(tile, b, mt, nt);
+                const uint32_t buf = it & 1u;
+                tc::mbar_wait(&sh->tmem_empty[buf], ((it >> 1) & 1u) ^ 1u);
+                tc::fence_after_sync();
+                const uint32_t d_tmem = tmem_base + buf * NT;
+                uint32_t first = 1;
+                for (int tap = 0; tap < 3; ++tap) {
+                    if (!tap_active(mt, tap - 1)) continue;
+                    for (int kb = 0; kb < kb_per_tap; ++kb) {
+                        tc::mbar_wait(&sh->full[stage], phase);
+                        tc::fence_after_sync();
+                        const uint32_t a_addr = tc::smem_u32(ring + stage * Cfg::STAGE_BYTES);
+                        const uint64_t da = tc::make_smem_desc_sw128(a_addr);
+                        const uint64_t db = tc::make_smem_desc_sw128(a_addr + Cfg::A_BYTES);
+#pragma unroll
+                        for (int k = 0; k < T_BLOCK_K / 16; ++k) {
+                            tc::umma_bf16(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, first ? 0u : 1u);
+                            first = 0;
+                        }
+                        tc::umma_commit(&sh->empty[stage]);
+                        if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
+                    }
+                }
+                tc::umma_commit(&sh->tmem_full[buf]);
+            }
+        }
+    } else {
+        const int q = warp & 3;
+        const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+        uint32_t it = 0;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+            int b, mt, nt; coords(tile, b, mt, nt);
+            const uint32_t buf = it & 1u;
+            const int row = mt * T_BLOCK_M + q * 32 + lane;
+            const bool inb = row < p.rows;
+            tc::mbar_wait(&sh->tmem_full[buf], (it >> 1) & 1u);
+            tc::fence_after_sync();
+            const uint32_t tbase = tmem_base + buf * NT + lane_addr;
+            __nv_bfloat16* yrow = p.y + ((size_t)b * p.rows + (inb ? row : 0)) * p.C + (size_t)nt * NT;
+            const float* sc = p.scale + (size_t)nt * NT;
+            const float* sf = p.shift + (size_t)nt * NT;
+#pragma unroll 1
+            for (int n0 = 0; n0 < NT; n0 += 16) {
+                uint32_t r[16];
+                tc::tmem_ld16(tbase + n0, r); tc::tmem_ld_wait();
+                uint32_t packed[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    float v0 = fmaf(__uint_as_float(r[2 * i]), __ldg(sc + n0 + 2 * i), __ldg(sf + n0 + 2 * i));
+                    float v1 = fmaf(__uint_as_float(r[2 * i + 1]), __ldg(sc + n0 + 2 * i + 1), __ldg(sf + n0 + 2 * i + 1));
+                    v0 = v0 > 0.f ? v0 : v0 * p.slope;
+                    v1 = v1 > 0.f ? v1 : v1 * p.slope;
+                    __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1);
+                    packed[i] = *reinterpret_cast<uint32_t*>(&h);
+                }
+                if (inb) {
+                    uint4* dst = reinterpret_cast<uint4*>(yrow + n0);
+                    dst[0] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+                    dst[1] = make_uint4(packed[4], packed[5], packed[6], packed[7]);
+                }
+            }
+            tc::fence_before_sync();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(&sh->tmem_empty[buf]);
+        }
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 1) tc::tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+}
+
+template <int NT>
+static int launch_tconv(const TConvMaps& maps, const TConvParams& p, cudaStream_t stream) {
+    using Cfg = TConvCfg<NT>;
+    auto kern = temporal_conv_kernel<NT>;
+    VD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    int grid = sm_count(); if (grid > p.total_tiles) grid = p.total_tiles;
+    kern<<<grid, T_THREADS, Cfg::SMEM_BYTES, stream>>>(maps, p);
+    VD_LAUNCH_CHECK();
+    return VD_OK;
+}
+
+}  // namespace vd
+
+using namespace vd;
+
+extern "C" int vd_temporal_conv(const void* x, void* y, int B, int T, int H, int W, int C,
+                                const void* weight, const float* scale, const float* shift,
+                                float slope, void* stream_) {
+    VD_CHECK_ARG(x && y && weight && scale && shift, "temporal_conv: null pointer");
+    VD_CHECK_ARG(B >= 0 && T >= 1 && H > 0 && W > 0, "temporal_conv: bad shape");
+    VD_CHECK_ARG(C >= 128 && C % 128 == 0, "temporal_conv: C = %d must be a multiple of 128", C);
+    VD_CHECK_ARG(((uintptr_t)x & 15) == 0 && ((uintptr_t)y & 15) == 0 && ((uintptr_t)weight & 15) == 0, "temporal_conv: tensors must be 16-byte aligned");
+    if (B == 0) return VD_OK;
+    const int NT = (C % 256 == 0) ? 256 : 128;
+    TConvParams p;
+    p.B = B; p.T = T; p.HW = H * W; p.C = C; p.rows = T * H * W;
+    p.m_tiles = ceil_div(p.rows, T_BLOCK_M); p.n_tiles = C / NT;
+    long long total = (long long)B * p.m_tiles * p.n_tiles;
+    VD_CHECK_ARG(total < (1ll << 31), "temporal_conv: too many tiles");
+    p.total_tiles = (int)total;
+    p.scale = scale; p.shift = shift; p.slope = slope; p.y = (__nv_bfloat16*)y;
+    TConvMaps maps;
+    uint64_t dimsX[3] = {(uint64_t)C, (uint64_t)p.rows, (uint64_t)B};
+    uint64_t strX[2] = {(uint64_t)C * 2, (uint64_t)p.rows * C * 2};
+    uint32_t boxX[3] = {T_BLOCK_K, T_BLOCK_M, 1};
+    int rc = encode_tmap_bf16(&maps.x, x, 3, dimsX, strX, boxX);
+    if (rc) return rc;
+    uint64_t dimsW[3] = {(uint64_t)C, (uint64_t)C, 3};
+    uint64_t strW[2] = {(uint64_t)C * 2, (uint64_t)C * C * 2};
+    uint32_t boxW[3] = {T_BLOCK_K, (uint32_t)NT, 1};
+    rc = encode_tmap_bf16(&maps.w, weight, 3, dimsW, strW, boxW);
+    if (rc) return rc;
+    if (NT == 256) return launch_tconv<256>(maps, p, (cudaStream_t)stream_);
+    return launch_tconv<128>(maps, p, (cudaStream_t)stream_);
+}

@@ -1,0 +1,63 @@
+"""YOLOOutputV3 decode on the GPU vs the oracle, fp32: 1e-5 relative (scores) / 1e-5 of the image
+size (box corners, which are differences of O(size) terms)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import ref_head
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-5
+
+
+def box_close(a, b, size):
+    np.testing.assert_allclose(a, b, rtol=RTOL, atol=RTOL * size)
+
+
+@pytest.mark.parametrize("C,H,W,stride,anchors", [(20, 13, 13, 32, [116, 90, 156, 198, 373, 326]),
+                                                  (80, 19, 19, 32, [116, 90, 156, 198, 373, 326]),
+                                                  (3, 7, 11, 8, [10, 13, 16, 30, 33, 23]),
+                                                  (285, 4, 5, 16, [30, 61, 62, 45, 59, 119])])
+def test_decode_modes(C, H, W, stride, anchors):
+    import viddet_b200
+    rng = np.random.RandomState(C)
+    pred = (rng.standard_normal((2, 3 * (5 + C), H, W)) * 1.5).astype(np.float32)
+    blk = viddet_b200.YOLOOutputV3(0, C, anchors, stride)
+    pt = torch.from_numpy(pred).cuda()
+    det = blk.decode(pt).cpu().numpy()
+    ref = ref_head.decode(pred, anchors, stride, C)
+    assert det.shape == ref.shape
+    np.testing.assert_array_equal(det[..., 0], ref[..., 0])
+    np.testing.assert_allclose(det[..., 1], ref[..., 1], rtol=RTOL, atol=1e-9)
+    box_close(det[..., 2:], ref[..., 2:], stride * max(H, W))
+    outs = blk.decode(pt, training=True)
+    refs = ref_head.decode(pred, anchors, stride, C, mode="train")
+    box_close(outs[0].cpu().numpy(), refs[0], stride * max(H, W))
+    for o, r in zip(outs[1:5], refs[1:5]):
+        np.testing.assert_array_equal(o.cpu().numpy(), r)        # raw logits are pure copies
+    np.testing.assert_array_equal(outs[5].cpu().numpy(), refs[5])
+    np.testing.assert_array_equal(outs[6].cpu().numpy(), refs[6])
+    ag = viddet_b200.YOLOOutputV3(0, C, anchors, stride, agnostic=True).decode(pt).cpu().numpy()
+    ref_ag = ref_head.decode(pred, anchors, stride, C, mode="agnostic")
+    np.testing.assert_allclose(ag[..., :2], ref_ag[..., :2], rtol=RTOL)
+    box_close(ag[..., 2:], ref_ag[..., 2:], stride * max(H, W))
+
+
+def test_decode_zero_logit_kat_and_nan_ids():
+    import viddet_b200
+    C, H, W = 4, 3, 5
+    pred = np.zeros((1, 3 * (5 + C), H, W), np.float32)
+    pred[0, 5, 0, 0] = np.nan
+    blk = viddet_b200.YOLOOutputV3(0, C, [30, 61, 62, 45, 59, 119], 16)
+    det = blk.decode(torch.from_numpy(pred).cuda()).cpu().numpy()
+    assert np.isnan(det[0, 0, 0]) and np.isnan(det[0, 0, 1])     # ids = score*0 + c (yolo3.py:194)
+    np.testing.assert_allclose(det[0, 1:, 1], 0.25, rtol=1e-6)
+    np.testing.assert_allclose(det[0, 1, 2:], [8 - 31, 8 - 22.5, 8 + 31, 8 + 22.5], rtol=1e-6)
+
+
+def test_repack_layout():
+    import viddet_b200
+    x = torch.randn(3, 70, 5, 9, device="cuda")
+    y = viddet_b200.to_nhwc_bf16(x)
+    assert y.dtype == torch.bfloat16 and y.is_contiguous(memory_format=torch.channels_last)
+    torch.testing.assert_close(y.float(), x.to(torch.bfloat16).float(), rtol=0, atol=0)

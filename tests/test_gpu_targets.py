@@ -1,0 +1,96 @@
+"""YOLOV3PrefetchTargetGenerator on the GPU vs the oracle: assignments (matched anchor, target row,
+which rows are written) BIT-EXACT; values within 2 ulp-ish (logf / fp64 rounding), tolerance 1e-6."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import ref_targets
+from tests.util import make_gt
+
+pytestmark = pytest.mark.gpu
+
+
+def run_gpu(gt, ids, mix, C, size):
+    import viddet_b200
+    img, xs, anchors, offsets = ref_targets.default_generator_inputs(size)
+    gen = viddet_b200.YOLOV3PrefetchTargetGenerator(C)
+    t = lambda a: None if a is None else torch.from_numpy(a).cuda()
+    outs = gen(img, xs, [torch.from_numpy(a) for a in anchors], offsets, t(gt), t(ids), t(mix), return_assign=True)
+    torch.cuda.synchronize()
+    return [o.cpu().numpy() for o in outs]
+
+
+def compare(gt, ids, mix, C, size=416):
+    img, xs, anchors, offsets = ref_targets.default_generator_inputs(size)
+    ref = ref_targets.prefetch_targets(img, xs, anchors, offsets, gt, ids, mix, num_class=C, return_assign=True)
+    got = run_gpu(gt, ids, mix, C, size)
+    np.testing.assert_array_equal(got[5], ref[5])                       # matched anchor per GT
+    np.testing.assert_array_equal(got[6], ref[6])                       # target row per GT
+    np.testing.assert_array_equal(got[0] != 0, ref[0] != 0)             # which rows are positive
+    np.testing.assert_array_equal(got[4].view(np.uint32), ref[4].view(np.uint32))   # class targets exact
+    np.testing.assert_array_equal(got[0], ref[0])                       # objectness exact (1 / mixratio)
+    for g, r in zip(got[1:4], ref[1:4]):
+        np.testing.assert_allclose(g, r, rtol=1e-6, atol=1e-6)
+    return got, ref
+
+
+@pytest.mark.parametrize("C,multi", [(20, False), (80, False), (30, True), (285, True)])
+def test_random(C, multi):
+    rng = np.random.RandomState(C)
+    gt, ids = make_gt(rng, 4, 100, num_class=C, multi_hot=multi)
+    compare(gt, ids, None, C)
+
+
+def test_mixup_608_and_dense_collisions():
+    rng = np.random.RandomState(1)
+    gt, ids = make_gt(rng, 3, 50, size=608, num_class=20)
+    mix = rng.uniform(0.1, 0.9, size=(3, 50, 1)).astype(np.float32)
+    compare(gt, ids, mix, 20, size=608)
+    # many GTs in the same cell / anchor: last writer must win
+    gt = np.full((2, 40, 4), -1, np.float32); ids = np.zeros((2, 40, 1), np.float32)
+    for m in range(40):
+        gt[:, m] = [100 + 0.01 * m, 120, 220 + 0.01 * m, 300]
+        ids[:, m, 0] = m % 20
+    got, ref = compare(gt, ids, None, 20)
+    assert np.count_nonzero(got[0]) == 2
+
+
+def test_break_on_invalid_and_empty():
+    rng = np.random.RandomState(2)
+    gt, ids = make_gt(rng, 4, 30, num_class=20, min_count=10)
+    gt[0, 3] = -1                      # hole in the middle: later GTs are ignored (yolo_target.py:106)
+    gt[1, 0] = -1                      # image with nothing processed
+    gt[2, 5, 0] = -0.5                 # one negative coordinate is enough
+    got, ref = compare(gt, ids, None, 20)
+    assert (got[6][0, 3:] == -1).all() and (got[6][1] == -1).all() and np.count_nonzero(got[0][1]) == 0
+
+
+def test_small_boxes_float64_path():
+    gt = np.full((1, 4, 4), -1, np.float32); ids = np.zeros((1, 4, 1), np.float32)
+    gt[0, 0] = [50, 60, 50.5, 60.25]
+    gt[0, 1] = [300, 200, 301, 201]      # exactly 1 px: fp32 path
+    gt[0, 2] = [10, 20, 10.999, 400]
+    compare(gt, ids, None, 20)
+
+
+def test_config5_shapes_properties():
+    """BASELINE config 5 sizes (C=285, B=128, M=100): property checks instead of the 4.6 GB oracle."""
+    rng = np.random.RandomState(3)
+    B, M, C = 128, 100, 285
+    gt, ids = make_gt(rng, B, M, num_class=C, multi_hot=True)
+    obj, ctr, scl, wgt, cls, match, row = run_gpu(gt, ids, None, C, 416)
+    assert cls.shape == (B, 10647, C)
+    pos = obj[..., 0] > 0
+    nvalid = (gt >= 0).all(-1).cumprod(1).sum(1)
+    for b in range(0, B, 17):
+        rows = row[b, :nvalid[b]]
+        assert (rows >= 0).all() and (row[b, nvalid[b]:] == -1).all()
+        assert pos[b].sum() == len(set(rows.tolist()))
+        assert (cls[b][~pos[b]] == -1).all() and (ctr[b][~pos[b]] == 0).all()
+        last = {}
+        for m, r in enumerate(rows):
+            last[r] = m
+        for r, m in last.items():
+            np.testing.assert_array_equal(cls[b, r], ids[b, m])
+    # oracle parity on a 2-image slice of the same batch
+    compare(gt[:2], ids[:2], None, C)

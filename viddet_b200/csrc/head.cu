@@ -274,7 +274,7 @@ head_kernel(const __grid_constant__ HeadMaps maps, const __grid_constant__ HeadK
                 const uint32_t k = (uint32_t)p.k, cap = (uint32_t)p.cap;
                 const uint32_t HW3 = (uint32_t)HW * 3u;
                 const uint32_t row0 = (uint32_t)p.g.row_base[s] + (uint32_t)cell * 3u;    // + c*HW3 + a
-                uint64_t tau = 1ull;                                // every valid candidate seen so far with key >= tau is in the list
+                uint64_t tau = 1ull << 32;                          // (score key 1, any row): every valid candidate seen so far with key >= tau is in the list
                 uint32_t list_n = 0; int cur = 0;
                 uint64_t* L = slist;
 #pragma unroll 1
@@ -350,7 +350,7 @@ head_kernel(const __grid_constant__ HeadMaps maps, const __grid_constant__ HeadK
                             }
                         }
                         if (!done && !have_hi) {                     // gallop upwards for an upper bracket
-                            uint64_t step = 1ull << 49;
+                            uint64_t step = (tau_guess != 0ull) ? (1ull << 49) : (1ull << 58);   // warm: ~2^17 score ulps; cold: coarse
                             uint64_t mid = lo;
                             for (int g = 0; g < 40 && !done && !have_hi; ++g) {
                                 uint64_t nm = mid + step; if (nm < mid) nm = ~0ull;
@@ -438,7 +438,7 @@ head_kernel(const __grid_constant__ HeadMaps maps, const __grid_constant__ HeadK
                     uint64_t* gl = p.lists + li * kListCap;
                     for (uint32_t j = et; j < list_n; j += kEpiThreads) gl[j] = L[cur * kListCap + j];
                     if (et == 0) p.counts[li] = list_n;
-                    if (tau > 1ull) tau_guess = tau;
+                    if (tau > (1ull << 32)) tau_guess = tau;
                     epi_bar();                                      // list buffers are reused by the next tile
                 }
             }

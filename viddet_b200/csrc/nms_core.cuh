@@ -45,7 +45,7 @@ static inline size_t nms_final_smem(int k) {
     b += (size_t)k * nms_words(k) * 4;                 // suppression matrix
     b += (size_t)sortn * 4;                            // (class,rank) secondary sort keys
     b += 64 * 4 + 64 * 4;                              // alive words + prefix
-    b += sizeof(SelectScratch) + 64;
+    b += 64 + 64;                                      // SelectScratch header + slack
     return b;
 }
 
@@ -74,7 +74,8 @@ __device__ void nms_final_body(const uint64_t* __restrict__ lists, const uint32_
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
     const int k = P.k, SN = P.sortn, NW = (k + 31) >> 5;
     // ---- carve shared memory
-    uint64_t* skeys = reinterpret_cast<uint64_t*>(smem_raw);
+    SelectScratch* scr = reinterpret_cast<SelectScratch*>(smem_raw);          // 8-byte members: keep it first
+    uint64_t* skeys = reinterpret_cast<uint64_t*>(smem_raw + 64);
     float4* sbox = reinterpret_cast<float4*>(skeys + SN);
     int* scls = reinterpret_cast<int*>(sbox + k);
     float* sarea = reinterpret_cast<float*>(scls + k);
@@ -82,7 +83,7 @@ __device__ void nms_final_body(const uint64_t* __restrict__ lists, const uint32_
     uint32_t* skey2 = smask + (size_t)k * NW;
     uint32_t* salive = skey2 + SN;
     uint32_t* sprefix = salive + 64;
-    SelectScratch* scr = reinterpret_cast<SelectScratch*>(sprefix + 64);
+    static_assert(sizeof(SelectScratch) <= 64, "scratch header");
 
     select_scratch_init(scr);
     for (int i = tid; i < SN; i += blockDim.x) skeys[i] = 0ull;

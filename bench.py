@@ -1,0 +1,319 @@
+#!/usr/bin/env python
+"""bench.py -- head+decode+NMS frames/s at 416^2 (BASELINE.json metric) on N B200s.
+
+    python bench.py --gpus N --steps K --warmup W             (N>1: launched under torchrun)
+    python bench.py --impl reference ...                      (CPU restatement of the MXNet path)
+
+A step = one pass of the hot path (fused tcgen05 pred-conv + YOLOOutputV3 decode + exact top-k +
+class-aware NMS) over one 64-frame batch of synthetic VOC-416 tip features resident in HBM
+(configs[1] of BASELINE.json).  Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement".
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "head+decode+NMS frames/s at 416^2"
+WORKLOADS = {
+    # name: (classes, input size, frames per step per GPU)
+    "voc416_b64": (20, 416, 64),
+    "coco608_b64": (80, 608, 64),
+    "vid416_b64": (30, 416, 64),
+}
+CHANNELS = [1024, 512, 256]
+STRIDES = [32, 16, 8]
+NROT = 4          # distinct resident input sets cycled through, so no step re-reads a cached batch
+
+
+def algorithmic_bytes_per_frame(C, size, elem=2):
+    """sum_s HW_s*Cin_s*sizeof + 2400 B of (100,6) fp32 output per frame."""
+    return sum((size // s) ** 2 * c for s, c in zip(STRIDES, CHANNELS)) * elem + 2400
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured"
+    return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def synth_tips(torch, gen, frames, size, device):
+    """leaky_relu(N(0,1), 0.1) tips (what a conv-BN-LReLU tip emits under identity BN), bf16 NHWC."""
+    tips = []
+    for c, s in zip(CHANNELS, STRIDES):
+        h = size // s
+        x = torch.randn((frames, c, h, h), generator=gen, device=device, dtype=torch.float32)
+        x = torch.where(x > 0, x, 0.1 * x).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+        tips.append(x)
+    return tips
+
+
+def run_reference(args):
+    """CPU restatement of the MXNet head (MXNet itself is not installable here), all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import numpy as np
+    from oracle import cpu_baseline
+    from tests.util import make_pred_weights, make_tips
+    C, size, frames = WORKLOADS[args.workload]
+    sample = args.cpu_frames                     # bounded sample of the 64-frame batch per step
+    rng = np.random.RandomState(1234)
+    tips = make_tips(rng, sample, size=size)
+    ws, bs = make_pred_weights(rng, C)
+    threads = os.cpu_count() or 1
+    for _ in range(max(args.warmup, 1)):
+        cpu_baseline.head_forward_cpu([t[:2] for t in tips], ws, bs, C, threads=threads)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_baseline.head_forward_cpu(tips, ws, bs, C, threads=threads)
+    dt = time.perf_counter() - t0
+    fps = sample * args.steps / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "classes": C, "input": size, "frames_per_step": sample,
+                   "note": "CPU restatement of the MXNet path (MXNet unavailable): torch/oneDNN conv + numpy decode + C box_nms"},
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port",
+                         "sample": "%d steps x %d frames of the %s batch" % (args.steps, sample, args.workload)},
+        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="voc416_b64", choices=sorted(WORKLOADS))
+    ap.add_argument("--cpu-frames", type=int, default=64, help="frames per CPU-baseline step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        if args.steps == 200 and args.warmup == 20:       # defaults sized for the GPU arm
+            args.steps, args.warmup = 3, 1
+        return run_reference(args)
+    assert args.warmup >= 3, "timing rules: at least 3 warm-up steps"
+
+    import torch
+    import torch.distributed as dist
+    import viddet_b200
+    from viddet_b200 import _lib, dist as vdist
+
+    rank, world, local = vdist.init_from_env()
+    assert torch.cuda.is_available(), "bench.py (impl=ours) needs a B200; there is no CPU fallback"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    C, size, frames = WORKLOADS[args.workload]
+
+    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+    cpu_gen = torch.Generator().manual_seed(1234)
+    head = viddet_b200.YOLOV3Head(C).initialize(generator=cpu_gen)       # U(-0.07,0.07), bias 0 (detect_yolo3.py:885)
+    head.set_nms(nms_thresh=0.45, nms_topk=400, post_nms=100)            # detect_yolo3.py:200
+    sessions = []
+    for j in range(NROT):
+        s = head.session(synth_tips(torch, gen, frames, size, dev))
+        if not args.no_graph:
+            s.capture()
+        sessions.append(s)
+    step_fn = (lambda s: s.run()) if args.no_graph else (lambda s: s.replay())
+    gather_out = torch.empty((world * frames, 100, 6), device=dev) if world > 1 else None
+
+    def one_step(i):
+        s = sessions[i % NROT]
+        step_fn(s)
+        if world > 1:                                    # the path's only collective: final detection gather
+            dist.all_gather_into_tensor(gather_out, s.packed())
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        one_step(i)
+    barrier()
+    sampler = ClockSampler(local).start() if rank == 0 else None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        one_step(i)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if sampler else None
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = world * frames * args.steps / (ms * 1e-3)
+
+    # ---- dominant kernel alone (fused head kernel), CUDA events on the launching stream
+    for i in range(5):
+        sessions[i % NROT].run(_lib.VD_STAGE_HEAD)
+    torch.cuda.synchronize()
+    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ksteps = max(20, min(args.steps, 200))
+    k0.record()
+    for i in range(ksteps):
+        sessions[i % NROT].run(_lib.VD_STAGE_HEAD)
+    k1.record()
+    torch.cuda.synchronize()
+    head_ms = k0.elapsed_time(k1) / ksteps
+    n0, n1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n0.record()
+    for i in range(ksteps):
+        sessions[i % NROT].run(_lib.VD_STAGE_NMS)
+    n1.record()
+    torch.cuda.synchronize()
+    nms_ms = n0.elapsed_time(n1) / ksteps
+    peak, peak_kind = measured_peaks()
+    alg_bytes = algorithmic_bytes_per_frame(C, size) * frames
+    achieved = alg_bytes / (head_ms * 1e-3) / 1e9
+
+    # ---- end to end through the public API with HOST buffers (pinned), H2D + D2H inside the timed region
+    host_sets = [[t.cpu().pin_memory() for t in s.tips] for s in sessions[:2]]
+    host_out = torch.empty((frames, 100, 6), dtype=torch.float32).pin_memory()
+    h2d = sum(t.numel() * t.element_size() for t in host_sets[0])
+    d2h = host_out.numel() * 4
+    sess = sessions[0]
+
+    def e2e_step(i):
+        for dst, src in zip(sess.tips, host_sets[i % 2]):
+            dst.copy_(src, non_blocking=True)
+        step_fn(sess)
+        host_out.copy_(sess.packed(), non_blocking=True)
+        if world > 1:
+            dist.all_gather_into_tensor(gather_out, sess.packed())
+
+    e2e_steps = max(5, min(args.steps, 30))
+    for i in range(3):
+        e2e_step(i)
+    barrier()
+    x0, x1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    x0.record()
+    for i in range(e2e_steps):
+        e2e_step(i)
+    x1.record()
+    barrier()
+    e2e_ms = x0.elapsed_time(x1)
+    if world > 1:
+        t = torch.tensor([e2e_ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+    e2e_value = world * frames * e2e_steps / (e2e_ms * 1e-3)
+
+    # ---- CPU baseline beside it (rank 0, N = 1 only): the oracle restatement on a bounded sample
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        import numpy as np
+        from oracle import cpu_baseline
+        from tests.util import make_pred_weights, make_tips
+        rng = np.random.RandomState(1234)
+        threads = os.cpu_count() or 1
+        ctips = make_tips(rng, args.cpu_frames, size=size)
+        cws, cbs = make_pred_weights(rng, C)
+        cpu_baseline.head_forward_cpu([t[:2] for t in ctips], cws, cbs, C, threads=threads)
+        reps = 3
+        fps, secs, nfr = cpu_baseline.time_head_cpu(ctips, cws, cbs, C, repeats=reps, threads=threads)
+        cpu = {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port",
+               "sample": "%d passes over %d synthetic %s frames (%.1f s); torch/oneDNN conv + numpy decode + C box_nms"
+                         % (reps, args.cpu_frames, args.workload, secs)}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": args.workload, "classes": C, "input": size, "frames_per_step_per_gpu": frames,
+                       "carrier": "bf16 channels-last tips, bf16 weights, fp32 accumulate/decode/NMS",
+                       "nms": {"thresh": 0.45, "valid": 0.01, "topk": 400, "post": 100},
+                       "l2": "inputs %.0f MB/step > 126 MB L2; %d rotating resident input sets" % (alg_bytes / 1e6, NROT),
+                       "launch": "cuda graph replay" if not args.no_graph else "direct launches",
+                       "sharding": "frames split by rank, final all_gather of (frames,100,6)" if world > 1 else "single GPU"},
+            "roofline": {"bound": "hbm", "kernel": "head_kernel<EPI_FILTER> (pred conv + decode + candidate filter)",
+                         "achieved": achieved, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": None, "algorithmic_bytes_per_launch": alg_bytes,
+                         "kernel_ms": head_ms, "nms_stage_ms": nms_ms},
+            "cpu_baseline": cpu,
+            "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "steps": e2e_steps, "note": "pinned host bf16 NHWC tips -> H2D -> fused head -> D2H of (64,100,6)"},
+            "gpu_launches": args.steps * sess.launches,
+            "clocks": clocks,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -136,6 +136,17 @@ size_t vd_head_workspace_bytes(const VdHeadParams* p);
 int vd_head_forward(const VdHeadParams* p, float* ids, float* scores, float* bboxes,
                     int32_t* keep_rows_or_null, void* workspace, size_t workspace_bytes,
                     void* stream);
+/* The same call restricted to some of its kernels (for per-kernel timing with CUDA events on the
+ * launching stream; later stages read what earlier stages left in the workspace). */
+#define VD_STAGE_TCONV 1        /* temporal tip cell kernels                                   */
+#define VD_STAGE_HEAD  2        /* fused pred-conv + decode + candidate-filter kernel          */
+#define VD_STAGE_NMS   4        /* list merge passes + per-frame top-k / NMS kernel            */
+#define VD_STAGE_ALL   7
+int vd_head_forward_stages(const VdHeadParams* p, float* ids, float* scores, float* bboxes,
+                           int32_t* keep_rows_or_null, void* workspace, size_t workspace_bytes,
+                           void* stream, int stage_mask);
+/* Number of kernels one vd_head_forward call launches for these parameters (-1 on bad params). */
+int vd_head_launch_count(const VdHeadParams* p);
 /* Same conv + decode, but materialises the reference's (frames, rows, 6) detection tensor
  * (what `concat(all_detections)` holds at yolo3.py:523) instead of running NMS. */
 int vd_head_detections(const VdHeadParams* p, float* det, void* workspace, size_t workspace_bytes,

@@ -14,6 +14,7 @@ VD_MAX_SCALES = 3
 VD_MAX_TOPK = 1024
 VD_MODE_INFER, VD_MODE_TRAIN, VD_MODE_AGNOSTIC = 0, 1, 2
 VD_JOIN_NONE, VD_JOIN_CAT, VD_JOIN_MAX, VD_JOIN_MEAN = 0, 1, 2, 3
+VD_STAGE_TCONV, VD_STAGE_HEAD, VD_STAGE_NMS, VD_STAGE_ALL = 1, 2, 4, 7
 ERR_NAMES = {-1: "VD_ERR_INVALID_ARG", -2: "VD_ERR_UNSUPPORTED", -3: "VD_ERR_WORKSPACE", -4: "VD_ERR_CUDA"}
 
 
@@ -58,6 +59,8 @@ SIGNATURES = {
     "vd_pred_conv": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp]),
     "vd_head_workspace_bytes": (_sz, [ctypes.POINTER(VdHeadParams)]),
     "vd_head_forward": (_i, [ctypes.POINTER(VdHeadParams), _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "vd_head_forward_stages": (_i, [ctypes.POINTER(VdHeadParams), _vp, _vp, _vp, _vp, _vp, _sz, _vp, _i]),
+    "vd_head_launch_count": (_i, [ctypes.POINTER(VdHeadParams)]),
     "vd_head_detections": (_i, [ctypes.POINTER(VdHeadParams), _vp, _vp, _sz, _vp]),
     "vd_temporal_conv": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _f, _vp]),
     "vd_temporal_pool": (_i, [_vp, _vp, _i, _i, _i64, _i, _vp]),

@@ -460,6 +460,11 @@ class YOLOV3Head:
                 keep = keep.reshape(lead + (post,))
         return (ids, scores, bboxes, keep) if return_keep else (ids, scores, bboxes)
 
+    def session(self, tips, return_keep=False):
+        """Bind tips/outputs/workspace once; the returned HeadSession re-enqueues the same call with no
+        per-call Python work (and can be captured into a CUDA graph)."""
+        return HeadSession(self, tips, return_keep)
+
     def detections(self, tips):
         """The concatenated (B[,T], rows, 6) tensor of yolo3.py:523 (before NMS)."""
         p, flat, scratch, lead = self._prepare(tips)
@@ -472,6 +477,51 @@ class YOLOV3Head:
         if lead is not None:
             det = det.reshape(lead + (rows, 6))
         return det
+
+
+class HeadSession:
+    """A YOLOV3Head call with everything pre-bound: static channels-last bf16 input buffers
+    (`self.tips`, refill with copy_), static outputs (`ids`, `scores`, `bboxes`, `keep`), private
+    workspace.  `run()` enqueues the kernels on the current stream; `capture()` records them into a
+    CUDA graph whose `replay()` is a single launch."""
+
+    def __init__(self, head, tips, return_keep=False):
+        if not (0 < head.nms_thresh < 1) or head.post_nms <= 0:
+            raise _lib.VidDetError(-1, "HeadSession needs NMS and post_nms enabled")
+        self.head = head
+        self.params, self.tips, self._scratch, self.lead = head._prepare(tips)
+        dev = self.tips[0].device
+        F, post = self.params.frames, head.post_nms
+        self.ids = torch.empty((F, post, 1), device=dev)
+        self.scores = torch.empty((F, post, 1), device=dev)
+        self.bboxes = torch.empty((F, post, 4), device=dev)
+        self.keep = torch.empty((F, post), dtype=torch.int32, device=dev) if return_keep else None
+        lib = load()
+        self._ws = torch.empty(lib.vd_head_workspace_bytes(ctypes.byref(self.params)) + 256, dtype=torch.uint8, device=dev)
+        self.launches = lib.vd_head_launch_count(ctypes.byref(self.params))
+        self.graph = None
+
+    def run(self, stage_mask=_lib.VD_STAGE_ALL):
+        check(load().vd_head_forward_stages(ctypes.byref(self.params), ptr(self.ids), ptr(self.scores), ptr(self.bboxes),
+                                            ptr(self.keep), ptr(self._ws), self._ws.numel(), stream_ptr(), int(stage_mask)))
+        return self.ids, self.scores, self.bboxes
+
+    def capture(self):
+        self.run()                                    # warm-up outside capture (function attributes, lazy init)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self.run()
+        self.graph = g
+        return self
+
+    def replay(self):
+        self.graph.replay()
+        return self.ids, self.scores, self.bboxes
+
+    def packed(self):
+        """(frames, post_nms, 6) rows [id, score, x1, y1, x2, y2] -- the box_nms row layout."""
+        return torch.cat([self.ids, self.scores, self.bboxes], dim=-1)
 
 
 # ------------------------------------------------------------------------------------------------

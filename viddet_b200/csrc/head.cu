@@ -584,7 +584,11 @@ template <int EPI, int C, int NPAD>
 static int launch_head_t(const HeadMaps& maps, const HeadKernelParams& kp, cudaStream_t stream) {
     using Cfg = HeadCfg<NPAD>;
     auto kern = head_kernel<EPI, C, NPAD>;
-    VD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    static bool configured = false;                 // once per instantiation (also keeps graph capture clean)
+    if (!configured) {
+        VD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        configured = true;
+    }
     int grid = sm_count(); if (grid > kp.total_tiles) grid = kp.total_tiles;
     if (grid < 1) return VD_OK;
     kern<<<grid, kHeadThreads, Cfg::SMEM_BYTES, stream>>>(maps, kp);
@@ -643,8 +647,25 @@ extern "C" size_t vd_head_workspace_bytes(const VdHeadParams* p) {
     return pl.total;
 }
 
+extern "C" int vd_head_launch_count(const VdHeadParams* hp) {
+    HeadPlan pl;
+    if (make_plan(hp, &pl) != VD_OK) return -1;
+    int n = 1, lists = pl.kp.tiles_per_frame;                 // head kernel
+    while (lists > kMaxLists) { lists = ceil_div(lists, kMaxLists); ++n; }   // merge passes
+    n += 1;                                                   // per-frame top-k + NMS
+    for (int s = 0; s < hp->num_scales; ++s) if (hp->scale[s].tconv_weight_bf16) ++n;
+    return n;
+}
+
 extern "C" int vd_head_forward(const VdHeadParams* hp, float* ids, float* scores, float* bboxes,
                                int32_t* keep_rows_or_null, void* workspace, size_t workspace_bytes, void* stream_) {
+    return vd_head_forward_stages(hp, ids, scores, bboxes, keep_rows_or_null, workspace, workspace_bytes, stream_,
+                                  VD_STAGE_ALL);
+}
+
+extern "C" int vd_head_forward_stages(const VdHeadParams* hp, float* ids, float* scores, float* bboxes,
+                                      int32_t* keep_rows_or_null, void* workspace, size_t workspace_bytes,
+                                      void* stream_, int stage_mask) {
     cudaStream_t stream = (cudaStream_t)stream_;
     HeadPlan pl;
     int rc = make_plan(hp, &pl);
@@ -669,7 +690,7 @@ extern "C" int vd_head_forward(const VdHeadParams* hp, float* ids, float* scores
 
     for (int s = 0; s < hp->num_scales; ++s) {      // optional temporal tip cell in front (layers.py:82-89)
         const VdHeadScale& sc = hp->scale[s];
-        if (sc.tconv_weight_bf16) {
+        if (sc.tconv_weight_bf16 && (stage_mask & VD_STAGE_TCONV)) {
             VD_CHECK_ARG(sc.tconv_out_nhwc_bf16 && sc.tconv_scale && sc.tconv_shift, "head_forward: scale %d temporal cell needs out/scale/shift", s);
             VD_CHECK_ARG(hp->T >= 1 && hp->frames % hp->T == 0, "head_forward: frames %d not a multiple of T %d", hp->frames, hp->T);
             rc = vd_temporal_conv(sc.tip_nhwc_bf16, sc.tconv_out_nhwc_bf16, hp->frames / hp->T, hp->T, sc.H, sc.W, sc.Cin,
@@ -680,8 +701,11 @@ extern "C" int vd_head_forward(const VdHeadParams* hp, float* ids, float* scores
     HeadMaps maps;
     rc = make_maps(hp, pl, &maps);
     if (rc) return rc;
-    rc = launch_head<EPI_FILTER>(maps, kp, pl.C, stream);
-    if (rc) return rc;
+    if (stage_mask & VD_STAGE_HEAD) {
+        rc = launch_head<EPI_FILTER>(maps, kp, pl.C, stream);
+        if (rc) return rc;
+    }
+    if (!(stage_mask & VD_STAGE_NMS)) return VD_OK;
 
     const uint64_t* lists = kp.lists; const uint32_t* counts = kp.counts; int n_lists = kp.tiles_per_frame;
     uint64_t* lout = (uint64_t*)(ws + pl.off_listsA); uint32_t* cout = (uint32_t*)(ws + pl.off_countsA);
@@ -699,7 +723,11 @@ extern "C" int vd_head_forward(const VdHeadParams* hp, float* ids, float* scores
     FusedSource src{kp.g, kp.boxes};
     FusedSink sink{ids, scores, bboxes, keep_rows_or_null, hp->post_nms};
     size_t smem = nms_final_smem(k);
-    VD_CUDA(cudaFuncSetAttribute(nms_final_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    static bool configured = false;
+    if (!configured) {
+        VD_CUDA(cudaFuncSetAttribute(nms_final_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)nms_final_smem(VD_MAX_TOPK)));
+        configured = true;
+    }
     nms_final_fused_kernel<<<hp->frames, kFinalThreads, smem, stream>>>(lists, counts, n_lists, P, src, sink);
     VD_LAUNCH_CHECK();
     return VD_OK;

@@ -196,7 +196,11 @@ extern "C" int vd_box_nms(const float* data, int64_t num_batch, int64_t num_elem
     P.overlap_thresh = overlap_thresh; P.k = k; P.sortn = nms_sortn(k);
     P.class_aware = (!force_suppress && id_index >= 0) ? 1 : 0; P.max_out = k;
     size_t smem = nms_final_smem(k);
-    VD_CUDA(cudaFuncSetAttribute(nms_final_compat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    static bool configured = false;
+    if (!configured) {
+        VD_CUDA(cudaFuncSetAttribute(nms_final_compat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)nms_final_smem(VD_MAX_TOPK)));
+        configured = true;
+    }
     nms_final_compat_kernel<<<(unsigned)num_batch, kFinalThreads, smem, stream>>>(lists, counts, n_lists, P, a);
     VD_LAUNCH_CHECK();
     return VD_OK;

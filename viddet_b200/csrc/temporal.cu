@@ -172,7 +172,11 @@ template <int NT>
 static int launch_tconv(const TConvMaps& maps, const TConvParams& p, cudaStream_t stream) {
     using Cfg = TConvCfg<NT>;
     auto kern = temporal_conv_kernel<NT>;
-    VD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    static bool configured = false;
+    if (!configured) {
+        VD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        configured = true;
+    }
     int grid = sm_count(); if (grid > p.total_tiles) grid = p.total_tiles;
     kern<<<grid, T_THREADS, Cfg::SMEM_BYTES, stream>>>(maps, p);
     VD_LAUNCH_CHECK();

@@ -30,9 +30,10 @@ namespace vd {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;
 constexpr int UMMA_K = 16;
-constexpr int kHeadThreads = 192;
+constexpr int kEpiGroups = 2;                 // epilogue warpgroups; group g owns TMEM buffer g (tiles it%2 == g)
+constexpr int kEpiWarp0 = 2;                  // warp 0: TMA, warp 1: MMA, then 2 x 4 epilogue warps
 constexpr int kEpiThreads = 128;
-constexpr int kEpiWarp0 = 2;
+constexpr int kHeadThreads = kEpiWarp0 * 32 + kEpiGroups * kEpiThreads;   // 320
 constexpr int A_TILE_BYTES = BLOCK_M * BLOCK_K * 2;
 
 enum { EPI_FILTER = 0, EPI_DET = 1, EPI_PRED = 2 };
@@ -57,10 +58,13 @@ struct HeadKernelParams {
 
 struct HeadMaps { CUtensorMap a[VD_MAX_SCALES]; CUtensorMap w[VD_MAX_SCALES]; };
 
-template <int NPAD> struct HeadCfg {
+template <int EPI, int C, int NPAD> struct HeadCfg {
+    static constexpr int NCH = (3 * C + 63) / 64;              // class chunks per tile: <= 64 score keys in registers
+    static constexpr int LIST_BUFS = (EPI == EPI_FILTER) ? (NCH > 1 ? 2 : 1) : 0;   // ping-pong only if the list can shrink
     static constexpr int B_TILE_BYTES = NPAD * BLOCK_K * 2;
     static constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
-    static constexpr int EPI_BYTES = 2 * kListCap * 8 + VD_MAX_SCALES * NPAD * 4 + 1024;
+    static constexpr int LIST_BYTES = kEpiGroups * LIST_BUFS * kListCap * 8;
+    static constexpr int EPI_BYTES = LIST_BYTES + VD_MAX_SCALES * NPAD * 4 + 1024;
     static constexpr int STAGES_RAW = (225 * 1024 - EPI_BYTES - 1024) / STAGE_BYTES;
     static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
     static constexpr int TMEM_STRIDE = NPAD <= 128 ? 128 : 256;
@@ -71,24 +75,22 @@ template <int NPAD> struct HeadCfg {
     static_assert(STAGES >= 3, "pipeline too shallow");
 };
 
-struct EpiShared {
+struct EpiGroupShared { uint32_t cnt[3]; uint32_t cursor; };
+struct HeadShared {
     uint64_t full[8], empty[8], tmem_full[2], tmem_empty[2];
-    uint32_t tmem_base;
-    uint32_t cnt[3];
-    uint32_t cursor;
-    uint32_t pad_;
-    uint64_t red[2];
+    uint32_t tmem_base, pad_;
+    EpiGroupShared grp[kEpiGroups];
 };
 
-__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory"); }
+__device__ __forceinline__ void epi_bar(int grp) { asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "n"(kEpiThreads) : "memory"); }
 
-// block_sum over the 128 epilogue threads (named barrier 1), see select.cuh::block_sum
-__device__ __forceinline__ uint32_t epi_sum(uint32_t v, EpiShared* s, int et, int& it) {
+// block_sum over the 128 threads of one epilogue group (named barrier 1+grp), see select.cuh::block_sum
+__device__ __forceinline__ uint32_t epi_sum(uint32_t v, EpiGroupShared* s, int grp, int et, int& it) {
     uint32_t w = __reduce_add_sync(0xffffffffu, v);
     const int slot = it % 3;
     if ((et & 31) == 0 && w) atomicAdd(&s->cnt[slot], w);
     if (et == 0) s->cnt[(it + 1) % 3] = 0;
-    epi_bar();
+    epi_bar(grp);
     uint32_t r = s->cnt[slot];
     ++it;
     return r;
@@ -106,14 +108,16 @@ __device__ __forceinline__ void tile_coords(const HeadKernelParams& p, int tile,
 template <int EPI, int C, int NPAD>
 __global__ void __launch_bounds__(kHeadThreads, 1)
 head_kernel(const __grid_constant__ HeadMaps maps, const __grid_constant__ HeadKernelParams p) {
-    using Cfg = HeadCfg<NPAD>;
+    using Cfg = HeadCfg<EPI, C, NPAD>;
     constexpr int P = 5 + C;
     extern __shared__ unsigned char smem_dyn[];
-    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+    // 1024-byte alignment for the 128B-swizzled operand tiles; offset arithmetic keeps the
+    // shared-memory address space visible to the compiler (LDS/STS instead of generic LD/ST)
+    unsigned char* smem = smem_dyn + ((1024u - (tc::smem_u32(smem_dyn) & 1023u)) & 1023u);
     unsigned char* ring = smem;
-    uint64_t* slist = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);     // [2][kListCap]
-    float* sbias = reinterpret_cast<float*>(slist + 2 * kListCap);                            // [3][NPAD]
-    EpiShared* sh = reinterpret_cast<EpiShared*>(sbias + VD_MAX_SCALES * NPAD);
+    uint64_t* slist = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);     // [group][buf][kListCap]
+    float* sbias = reinterpret_cast<float*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES + Cfg::LIST_BYTES);   // [3][NPAD]
+    HeadShared* sh = reinterpret_cast<HeadShared*>(sbias + VD_MAX_SCALES * NPAD);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -125,7 +129,7 @@ head_kernel(const __grid_constant__ HeadMaps maps, const __grid_constant__ HeadK
     if (threadIdx.x == 0) {
         for (int i = 0; i < Cfg::STAGES; ++i) { tc::mbar_init(&sh->full[i], 1); tc::mbar_init(&sh->empty[i], 1); }
         for (int i = 0; i < 2; ++i) { tc::mbar_init(&sh->tmem_full[i], 1); tc::mbar_init(&sh->tmem_empty[i], 4); }
-        sh->cnt[0] = sh->cnt[1] = sh->cnt[2] = 0; sh->cursor = 0; sh->red[0] = ~0ull; sh->red[1] = 0ull;
+        for (int g = 0; g < kEpiGroups; ++g) { sh->grp[g].cnt[0] = sh->grp[g].cnt[1] = sh->grp[g].cnt[2] = 0; sh->grp[g].cursor = 0; }
         tc::fence_barrier_init();
     }
     if (warp == 0 && lane == 0) {
@@ -145,14 +149,15 @@ head_kernel(const __grid_constant__ HeadMaps maps, const __grid_constant__ HeadK
                 int s, f, pblk; tile_coords(p, tile, s, f, pblk);
                 const int kb_per_frame = p.cin[s] / BLOCK_K;
                 const int nkb = kb_per_frame * p.K_frames;
+                int kf = 0, c0 = 0;
                 for (int kb = 0; kb < nkb; ++kb) {
                     tc::mbar_wait(&sh->empty[stage], phase ^ 1u);
                     unsigned char* a_dst = ring + stage * Cfg::STAGE_BYTES;
                     unsigned char* b_dst = a_dst + A_TILE_BYTES;
                     tc::mbar_expect_tx(&sh->full[stage], Cfg::STAGE_BYTES);
-                    const int kf = kb / kb_per_frame, c0 = (kb - kf * kb_per_frame) * BLOCK_K;
                     tc::tma_load_4d(a_dst, &maps.a[s], &sh->full[stage], c0, pblk * BLOCK_M, kf, f);
                     tc::tma_load_2d(b_dst, &maps.w[s], &sh->full[stage], kf * p.cin[s] + c0, 0);
+                    c0 += BLOCK_K; if (c0 == p.cin[s]) { c0 = 0; ++kf; }
                     if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
                 }
             }
@@ -184,17 +189,22 @@ head_kernel(const __grid_constant__ HeadMaps maps, const __grid_constant__ HeadK
                 tc::umma_commit(&sh->tmem_full[buf]);
             }
         }
-    } else {
-        // =========================== epilogue (128 threads) ===========================
-        const int et = threadIdx.x - kEpiWarp0 * 32;
+    } else if (warp >= kEpiWarp0) {
+        // =========================== epilogue: 2 groups x 128 threads ===========================
+        const int grp = (warp - kEpiWarp0) >> 2;              // also the TMEM buffer this group drains
+        const int et = threadIdx.x - kEpiWarp0 * 32 - grp * kEpiThreads;
         const int q = warp & 3;                               // TMEM lane quarter this warp may read
         const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+        EpiGroupShared* gs = &sh->grp[grp];
+        uint64_t* L = slist + (size_t)grp * Cfg::LIST_BUFS * kListCap;
         int sum_it = 0;
-        uint64_t tau_guess = 0ull;                            // warm start for the next tile (FILTER)
-        uint32_t it = 0;
-        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+        uint64_t tau_guess = 0ull;                            // warm start for this group's next tile (FILTER)
+        uint64_t band_w = 1ull << 50;                         // running estimate of the accept band's key width
+        (void)gs; (void)L; (void)sum_it; (void)tau_guess; (void)band_w; (void)et;
+        uint32_t it = (uint32_t)grp;
+        for (int tile = blockIdx.x + grp * gridDim.x; tile < p.total_tiles; tile += kEpiGroups * gridDim.x, it += kEpiGroups) {
             int s, f, pblk; tile_coords(p, tile, s, f, pblk);
-            const uint32_t buf = it & 1u;
+            const uint32_t buf = (uint32_t)grp;
             const int HW = p.g.HW[s], Wd = p.g.W[s];
             const int cell = pblk * BLOCK_M + q * 32 + lane;
             const bool inb = cell < HW;
@@ -268,15 +278,18 @@ head_kernel(const __grid_constant__ HeadMaps maps, const __grid_constant__ HeadK
             }
 
             if constexpr (EPI == EPI_FILTER) {
-                // ---- class scores -> orderable 32-bit keys; streaming exact selection of the tile's top-k
-                constexpr int NCH = (C + 31) / 32;                  // class chunks (register budget)
+                // ---- class scores -> 32-bit orderable keys in registers; streaming exact selection of the
+                //      tile's top-k: find a pivot tau with k <= #{key >= tau} <= cap, keep those keys.
+                constexpr int NCH = Cfg::NCH;
                 constexpr int CCH = (C + NCH - 1) / NCH;
                 const uint32_t k = (uint32_t)p.k, cap = (uint32_t)p.cap;
-                const uint32_t HW3 = (uint32_t)HW * 3u;
-                const uint32_t row0 = (uint32_t)p.g.row_base[s] + (uint32_t)cell * 3u;    // + c*HW3 + a
-                uint64_t tau = 1ull << 32;                          // (score key 1, any row): every valid candidate seen so far with key >= tau is in the list
-                uint32_t list_n = 0; int cur = 0;
-                uint64_t* L = slist;
+                // Low key word inside the tile = ~local, local = (class << 9) | (pixel-in-tile << 2) | anchor: it
+                // orders candidates exactly like ~row does (row = base + c*HW*3 + cell*3 + a) and costs one
+                // IADD-immediate per candidate; the true row is restored when the list is flushed.
+                const uint32_t cellofs = (uint32_t)(q * 32 + lane);
+                const uint64_t tau0 = 1ull << 32;                   // (score key 1, any row): below every valid key
+                uint64_t tau = tau0;                                // every valid candidate seen so far with key >= tau is in the list
+                uint32_t list_n = 0, t_acc = 0; int cur = 0;
 #pragma unroll 1
                 for (int ch = 0; ch < NCH; ++ch) {
                     uint32_t sk[3][CCH];
@@ -296,11 +309,11 @@ head_kernel(const __grid_constant__ HeadMaps maps, const __grid_constant__ HeadK
 #pragma unroll
                         for (int i = 0; i < CCH; ++i) {
                             const int c = ch * CCH + i;
-                            const uint32_t raw = r[i];
                             uint32_t key = 0u;
-                            if (c < C && inb) {
-                                float sc = vd_score(__uint_as_float(raw) + bias[a * P + 5 + c], conf[a]);
-                                if (sc > p.valid_thresh) key = orderable_f32(sc);          // strict; NaN invalid
+                            if (c < C) {
+                                // score = sigmoid(cls)*sigmoid(obj) >= +0 (or NaN): orderable key = bits | sign bit
+                                float sc = vd_score(__uint_as_float(r[i]) + bias[a * P + 5 + c], conf[a]);
+                                key = (sc > p.valid_thresh && inb) ? (__float_as_uint(sc) | 0x80000000u) : 0u;   // strict; NaN invalid
                             }
                             sk[a][i] = key;
                         }
@@ -310,7 +323,10 @@ head_kernel(const __grid_constant__ HeadMaps maps, const __grid_constant__ HeadK
                         __syncwarp();
                         if (lane == 0) tc::mbar_arrive(&sh->tmem_empty[buf]);
                     }
-                    // count of (chunk U list) keys >= pivot; pivot low word 0 => pure score compare
+                    // candidate (a,i) of this chunk >= pivot (ph,pl)?  pl == 0: pure score compare (fast path)
+                    const uint32_t nt = ~((((uint32_t)(ch * CCH)) << 9) | (cellofs << 2));
+                    auto nrow_of = [&](int a, int i) -> uint32_t { return nt - (((uint32_t)i << 9) | (uint32_t)a); };
+                    uint32_t my_cnt = 0;                            // this thread's chunk count at the last probed pivot
                     auto count_ge = [&](uint64_t piv) -> uint32_t {
                         const uint32_t ph = (uint32_t)(piv >> 32), pl = (uint32_t)piv;
                         uint32_t c = 0;
@@ -325,32 +341,46 @@ head_kernel(const __grid_constant__ HeadMaps maps, const __grid_constant__ HeadK
 #pragma unroll
                                 for (int i = 0; i < CCH; ++i) {
                                     uint32_t sv = sk[a][i];
-                                    uint32_t nrow = ~(row0 + (uint32_t)(ch * CCH + i) * HW3 + (uint32_t)a);
-                                    c += (sv > ph || (sv == ph && nrow >= pl)) ? 1u : 0u;
+                                    c += (sv > ph || (sv == ph && nrow_of(a, i) >= pl)) ? 1u : 0u;
                                 }
                         }
+                        my_cnt = c;
                         for (uint32_t j = et; j < list_n; j += kEpiThreads) c += (L[cur * kListCap + j] >= piv) ? 1u : 0u;
-                        return epi_sum(c, sh, et, sum_it);
+                        return epi_sum(c, gs, grp, et, sum_it);
                     };
-                    // ---- find tau' >= tau with  k <= count(>= tau') <= cap   (or keep tau if everything fits)
+                    // ---- find ntau >= tau with  k <= count(>= ntau) <= cap   (or keep tau if everything fits)
                     uint64_t ntau = tau;
                     {
                         uint64_t probe = tau_guess > tau ? tau_guess : tau;
                         uint32_t t = count_ge(probe);
                         uint64_t lo = 0ull, hi = 0ull; bool have_lo = false, have_hi = false, done = false;
-                        if (t >= k && t <= cap) { ntau = probe; done = true; }
+                        if (t >= k && t <= cap) { ntau = probe; done = true; t_acc = t; }
                         else if (t > cap) { lo = probe; have_lo = true; }
                         else {                                       // t < k: too high, or everything fits
                             hi = probe; have_hi = true;
-                            if (probe == tau) { ntau = tau; done = true; }
-                            else {
-                                uint32_t t0 = count_ge(tau);
-                                if (t0 <= cap) { ntau = tau; done = true; }
-                                else { lo = tau; have_lo = true; }
+                            if (probe == tau) { ntau = tau; done = true; t_acc = t; }
+                            else {                                   // gallop downwards before falling back to tau
+                                uint64_t step = band_w;
+                                uint64_t mid = probe;
+                                for (int g = 0; g < 8 && !done && !have_lo; ++g) {
+                                    uint64_t nm = (mid > step && mid - step > tau) ? (mid - step) & ~0xffffffffull : tau;
+                                    if (nm <= tau) break;
+                                    mid = nm;
+                                    uint32_t t2 = count_ge(mid);
+                                    if (t2 > cap) { lo = mid; have_lo = true; }
+                                    else if (t2 < k) { hi = mid; }
+                                    else { ntau = mid; done = true; t_acc = t2; }
+                                    step <<= 1;
+                                }
+                                if (!done && !have_lo) {
+                                    uint32_t t0 = count_ge(tau);
+                                    if (t0 <= cap) { ntau = tau; done = true; t_acc = t0; }
+                                    else { lo = tau; have_lo = true; }
+                                }
                             }
                         }
                         if (!done && !have_hi) {                     // gallop upwards for an upper bracket
-                            uint64_t step = (tau_guess != 0ull) ? (1ull << 49) : (1ull << 58);   // warm: ~2^17 score ulps; cold: coarse
+                            uint64_t step = (tau_guess != 0ull) ? band_w : (1ull << 58);   // warm: band-sized; cold: coarse
                             uint64_t mid = lo;
                             for (int g = 0; g < 40 && !done && !have_hi; ++g) {
                                 uint64_t nm = mid + step; if (nm < mid) nm = ~0ull;
@@ -359,7 +389,7 @@ head_kernel(const __grid_constant__ HeadMaps maps, const __grid_constant__ HeadK
                                 uint32_t t2 = count_ge(mid);
                                 if (t2 > cap) { lo = mid; if (mid == ~0ull) break; }
                                 else if (t2 < k) { hi = mid; have_hi = true; }
-                                else { ntau = mid; done = true; }
+                                else { ntau = mid; done = true; t_acc = t2; }
                                 step <<= 1; if (step == 0) step = 1ull << 63;
                             }
                         }
@@ -369,77 +399,90 @@ head_kernel(const __grid_constant__ HeadMaps maps, const __grid_constant__ HeadK
                                 uint64_t mid = lo + ((hi - lo) >> 1);
                                 if (hi - lo > (2ull << 32)) { mid &= ~0xffffffffull; if (mid <= lo) mid += 1ull << 32; }
                                 uint32_t t2 = count_ge(mid);
-                                if (t2 > cap) lo = mid; else if (t2 < k) hi = mid; else { ntau = mid; done = true; break; }
+                                if (t2 > cap) lo = mid; else if (t2 < k) hi = mid; else { ntau = mid; done = true; t_acc = t2; break; }
                             }
-                            if (!done) ntau = lo;                    // unreachable for unique keys (superset, still exact)
+                            if (done && hi - lo < band_w) band_w = (hi - lo) | (1ull << 32);
+                            if (!done) { ntau = lo; t_acc = count_ge(lo); }      // unreachable for unique keys (superset, still exact)
                         }
                     }
                     // ---- rebuild the list for ntau: surviving old entries, then this chunk's entries
                     {
-                        const bool shrink = ntau > tau && list_n > 0;
+                        const bool shrink = (Cfg::LIST_BUFS > 1) && ntau > tau && list_n > 0;
                         const int dst = shrink ? (cur ^ 1) : cur;
                         if (shrink) {
-                            if (et == 0) sh->cursor = 0;
-                            epi_bar();
+                            if (et == 0) gs->cursor = 0;
+                            epi_bar(grp);
                             for (uint32_t j0 = 0; j0 < list_n; j0 += kEpiThreads) {
                                 uint32_t j = j0 + et;
                                 uint64_t v = (j < list_n) ? L[cur * kListCap + j] : 0ull;
                                 bool keep = v >= ntau && v != 0ull;
                                 unsigned m = __ballot_sync(0xffffffffu, keep);
                                 uint32_t base = 0;
-                                if (lane == 0 && m) base = atomicAdd(&sh->cursor, (uint32_t)__popc(m));
+                                if (lane == 0 && m) base = atomicAdd(&gs->cursor, (uint32_t)__popc(m));
                                 base = __shfl_sync(0xffffffffu, base, 0);
                                 if (keep) L[dst * kListCap + base + __popc(m & ((1u << lane) - 1u))] = v;
                             }
                         } else if (list_n == 0) {
-                            if (et == 0) sh->cursor = 0;
-                            epi_bar();
+                            if (et == 0) gs->cursor = 0;
+                            epi_bar(grp);
                         }
-                        // chunk entries >= ntau
+                        // chunk entries >= ntau; my_cnt is this thread's count at ntau (the last probed pivot)
                         const uint32_t ph = (uint32_t)(ntau >> 32), pl = (uint32_t)ntau;
-                        uint32_t mine = 0;
-#pragma unroll
-                        for (int a = 0; a < 3; ++a)
-#pragma unroll
-                            for (int i = 0; i < CCH; ++i) {
-                                uint32_t sv = sk[a][i];
-                                uint32_t nrow = ~(row0 + (uint32_t)(ch * CCH + i) * HW3 + (uint32_t)a);
-                                mine += (sv > ph || (sv == ph && nrow >= pl)) ? 1u : 0u;
-                            }
+                        const uint32_t mine = my_cnt;
                         uint32_t incl = mine;
 #pragma unroll
                         for (int o = 1; o < 32; o <<= 1) { uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
                         uint32_t tot = __shfl_sync(0xffffffffu, incl, 31);
                         uint32_t base = 0;
-                        if (lane == 31 && tot) base = atomicAdd(&sh->cursor, tot);
+                        if (lane == 31 && tot) base = atomicAdd(&gs->cursor, tot);
                         base = __shfl_sync(0xffffffffu, base, 31);
-                        uint32_t pos = base + incl - mine;
+                        uint64_t* wp = L + dst * kListCap + (base + incl - mine);
                         if (mine) {
+                            if (pl == 0u) {
 #pragma unroll
-                            for (int a = 0; a < 3; ++a)
+                                for (int a = 0; a < 3; ++a)
 #pragma unroll
-                                for (int i = 0; i < CCH; ++i) {
-                                    uint32_t sv = sk[a][i];
-                                    uint32_t nrow = ~(row0 + (uint32_t)(ch * CCH + i) * HW3 + (uint32_t)a);
-                                    if (sv > ph || (sv == ph && nrow >= pl)) {
-                                        if (pos < (uint32_t)kListCap) L[dst * kListCap + pos] = ((uint64_t)sv << 32) | nrow;
-                                        ++pos;
+                                    for (int i = 0; i < CCH; ++i) {
+                                        const uint32_t sv = sk[a][i];
+                                        if (sv >= ph) { *wp = ((uint64_t)sv << 32) | nrow_of(a, i); ++wp; }
                                     }
-                                }
+                            } else {
+#pragma unroll
+                                for (int a = 0; a < 3; ++a)
+#pragma unroll
+                                    for (int i = 0; i < CCH; ++i) {
+                                        const uint32_t sv = sk[a][i];
+                                        const uint32_t nr = nrow_of(a, i);
+                                        if (sv > ph || (sv == ph && nr >= pl)) { *wp = ((uint64_t)sv << 32) | nr; ++wp; }
+                                    }
+                            }
                         }
-                        epi_bar();
-                        list_n = sh->cursor; if (list_n > (uint32_t)kListCap) list_n = kListCap;
+                        epi_bar(grp);
+                        list_n = gs->cursor; if (list_n > (uint32_t)kListCap) list_n = kListCap;
                         cur = dst; tau = ntau;
                     }
                 }
-                // ---- flush the tile's candidate list
+                // ---- flush the tile's candidate list; retarget the warm start towards the band centre
                 {
                     const size_t li = (size_t)f * p.tiles_per_frame + p.tif_base[s] + pblk;
                     uint64_t* gl = p.lists + li * kListCap;
-                    for (uint32_t j = et; j < list_n; j += kEpiThreads) gl[j] = L[cur * kListCap + j];
+                    const uint32_t HW3 = (uint32_t)HW * 3u;
+                    const uint32_t rbase = (uint32_t)p.g.row_base[s] + (uint32_t)(pblk * BLOCK_M) * 3u;
+                    for (uint32_t j = et; j < list_n; j += kEpiThreads) {
+                        const uint64_t v = L[cur * kListCap + j];
+                        const uint32_t local = ~(uint32_t)v;
+                        const uint32_t row = rbase + (local >> 9) * HW3 + ((local >> 2) & 127u) * 3u + (local & 3u);
+                        gl[j] = (v & 0xffffffff00000000ull) | (uint32_t)(~row);
+                    }
                     if (et == 0) p.counts[li] = list_n;
-                    if (tau > (1ull << 32)) tau_guess = tau;
-                    epi_bar();                                      // list buffers are reused by the next tile
+                    if (tau > tau0) {
+                        const uint32_t q4 = (cap - k) / 4u;
+                        const uint64_t nudge = band_w >> 3;
+                        tau_guess = tau;
+                        if (t_acc < k + q4 && tau > tau0 + nudge) tau_guess = (tau - nudge) & ~0xffffffffull;
+                        else if (t_acc > cap - q4) tau_guess = (tau + nudge) & ~0xffffffffull;
+                    }
+                    epi_bar(grp);                                   // list buffers are reused by the next tile
                 }
             }
         }
@@ -582,7 +625,7 @@ static int make_maps(const VdHeadParams* hp, const HeadPlan& pl, HeadMaps* maps)
 
 template <int EPI, int C, int NPAD>
 static int launch_head_t(const HeadMaps& maps, const HeadKernelParams& kp, cudaStream_t stream) {
-    using Cfg = HeadCfg<NPAD>;
+    using Cfg = HeadCfg<EPI, C, NPAD>;
     auto kern = head_kernel<EPI, C, NPAD>;
     static bool configured = false;                 // once per instantiation (also keeps graph capture clean)
     if (!configured) {
@@ -686,7 +729,7 @@ extern "C" int vd_head_forward_stages(const VdHeadParams* hp, float* ids, float*
     kp.boxes = (float4*)(ws + pl.off_boxes);
     kp.lists = (uint64_t*)(ws + pl.off_lists0);
     kp.counts = (uint32_t*)(ws + pl.off_counts0);
-    kp.valid_thresh = hp->valid_thresh; kp.k = k; kp.cap = (k <= 448) ? 512 : kListCap;
+    kp.valid_thresh = hp->valid_thresh; kp.k = k; kp.cap = (k <= 448) ? 640 : kListCap;
 
     for (int s = 0; s < hp->num_scales; ++s) {      // optional temporal tip cell in front (layers.py:82-89)
         const VdHeadScale& sc = hp->scale[s];

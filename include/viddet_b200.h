@@ -129,6 +129,9 @@ typedef struct VdHeadParams {
     VdHeadScale scale[VD_MAX_SCALES];
 } VdHeadParams;
 
+/* The first 256 bytes of the workspace hold warm-start hints (per-scale selection pivots) that the
+ * kernel reads and updates: passing the same workspace to consecutive calls makes later calls
+ * faster.  Any content is valid -- hints change speed, never results. */
 size_t vd_head_workspace_bytes(const VdHeadParams* p);
 /* ids (frames, post_nms, 1), scores (frames, post_nms, 1), bboxes (frames, post_nms, 4) fp32;
  * keep_rows_or_null (frames, post_nms) int32 = row in the (frames, rows, 6) tensor of each output

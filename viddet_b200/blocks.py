@@ -66,7 +66,7 @@ def _workspace(nbytes, device):
     key = (device.index if device.index is not None else torch.cuda.current_device())
     buf = _ws_cache.get(key)
     if buf is None or buf.numel() < nbytes:
-        buf = torch.empty(int(nbytes * 1.25) + 1024, dtype=torch.uint8, device=device)
+        buf = torch.zeros(int(nbytes * 1.25) + 1024, dtype=torch.uint8, device=device)   # zeroed once: holds warm-start hints
         _ws_cache[key] = buf
     return buf
 
@@ -497,7 +497,7 @@ class HeadSession:
         self.bboxes = torch.empty((F, post, 4), device=dev)
         self.keep = torch.empty((F, post), dtype=torch.int32, device=dev) if return_keep else None
         lib = load()
-        self._ws = torch.empty(lib.vd_head_workspace_bytes(ctypes.byref(self.params)) + 256, dtype=torch.uint8, device=dev)
+        self._ws = torch.zeros(lib.vd_head_workspace_bytes(ctypes.byref(self.params)) + 256, dtype=torch.uint8, device=dev)
         self.launches = lib.vd_head_launch_count(ctypes.byref(self.params))
         self.graph = None
 

@@ -22,6 +22,7 @@
 //        EPI_DET     materialise the reference's (frames, rows, 6) detection rows
 //        EPI_PRED    write the conv output (B, N, H, W) fp32
 // Tiles are ordered scale-major (s32 first: most bytes per tile) and dealt round-robin.
+#include <stdlib.h>
 #include "tc.cuh"
 #include "nms_core.cuh"
 
@@ -43,13 +44,15 @@ struct HeadKernelParams {
     int frames, K_frames;
     int cin[VD_MAX_SCALES];
     int pb[VD_MAX_SCALES];               // pixel blocks per frame
-    int tile_start[VD_MAX_SCALES + 1];   // scale-major cumulative tile index
+    int tile_start[VD_MAX_SCALES + 1];   // cumulative tile index per processing slot
+    int order[VD_MAX_SCALES];            // order[j] = scale processed j-th (mid-size tiles first: short pipeline fill)
     int tif_base[VD_MAX_SCALES];         // tile-in-frame index of the scale's first pixel block
     int tiles_per_frame, total_tiles, n_pad;
     int n_valid;                         // prediction channels actually present (<= n_pad)
     const float* bias[VD_MAX_SCALES];
     // EPI_FILTER
     float4* boxes; uint64_t* lists; uint32_t* counts; float valid_thresh; int k, cap;
+    unsigned long long* hints;           // [2*VD_MAX_SCALES][2] (pivot, band) warm starts, persist in the workspace across calls
     // EPI_DET
     float* det; long long det_rows_total;
     // EPI_PRED
@@ -75,7 +78,11 @@ template <int EPI, int C, int NPAD> struct HeadCfg {
     static_assert(STAGES >= 3, "pipeline too shallow");
 };
 
-struct EpiGroupShared { uint32_t cnt[3]; uint32_t cursor; };
+struct EpiGroupShared {
+    uint32_t cnt[3]; uint32_t cursor;
+    uint64_t guess[2 * VD_MAX_SCALES];     // warm-start pivot per (scale, full / partial pixel block)
+    uint64_t band[2 * VD_MAX_SCALES];      // running estimate of the accept band's key width
+};
 struct HeadShared {
     uint64_t full[8], empty[8], tmem_full[2], tmem_empty[2];
     uint32_t tmem_base, pad_;
@@ -97,10 +104,11 @@ __device__ __forceinline__ uint32_t epi_sum(uint32_t v, EpiGroupShared* s, int g
 }
 
 __device__ __forceinline__ void tile_coords(const HeadKernelParams& p, int tile, int& s, int& f, int& pblk) {
-    s = 0;
+    int j = 0;
 #pragma unroll
-    for (int i = 1; i < VD_MAX_SCALES; ++i) if (i < p.g.num_scales && tile >= p.tile_start[i]) s = i;
-    int local = tile - p.tile_start[s];
+    for (int i = 1; i < VD_MAX_SCALES; ++i) if (i < p.g.num_scales && tile >= p.tile_start[i]) j = i;
+    s = p.order[j];
+    int local = tile - p.tile_start[j];
     f = local / p.pb[s];
     pblk = local - f * p.pb[s];
 }
@@ -129,7 +137,14 @@ head_kernel(const __grid_constant__ HeadMaps maps, const __grid_constant__ HeadK
     if (threadIdx.x == 0) {
         for (int i = 0; i < Cfg::STAGES; ++i) { tc::mbar_init(&sh->full[i], 1); tc::mbar_init(&sh->empty[i], 1); }
         for (int i = 0; i < 2; ++i) { tc::mbar_init(&sh->tmem_full[i], 1); tc::mbar_init(&sh->tmem_empty[i], 4); }
-        for (int g = 0; g < kEpiGroups; ++g) { sh->grp[g].cnt[0] = sh->grp[g].cnt[1] = sh->grp[g].cnt[2] = 0; sh->grp[g].cursor = 0; }
+        for (int g = 0; g < kEpiGroups; ++g) {
+            sh->grp[g].cnt[0] = sh->grp[g].cnt[1] = sh->grp[g].cnt[2] = 0; sh->grp[g].cursor = 0;
+            for (int i = 0; i < 2 * VD_MAX_SCALES; ++i) {
+                unsigned long long hg = 0ull, hb = 0ull;
+                if (EPI == EPI_FILTER && p.hints) { hg = p.hints[2 * i]; hb = p.hints[2 * i + 1]; }
+                sh->grp[g].guess[i] = hg; sh->grp[g].band[i] = hb ? hb : (1ull << 50);
+            }
+        }
         tc::fence_barrier_init();
     }
     if (warp == 0 && lane == 0) {
@@ -198,9 +213,7 @@ head_kernel(const __grid_constant__ HeadMaps maps, const __grid_constant__ HeadK
         EpiGroupShared* gs = &sh->grp[grp];
         uint64_t* L = slist + (size_t)grp * Cfg::LIST_BUFS * kListCap;
         int sum_it = 0;
-        uint64_t tau_guess = 0ull;                            // warm start for this group's next tile (FILTER)
-        uint64_t band_w = 1ull << 50;                         // running estimate of the accept band's key width
-        (void)gs; (void)L; (void)sum_it; (void)tau_guess; (void)band_w; (void)et;
+        (void)gs; (void)L; (void)sum_it; (void)et;
         uint32_t it = (uint32_t)grp;
         for (int tile = blockIdx.x + grp * gridDim.x; tile < p.total_tiles; tile += kEpiGroups * gridDim.x, it += kEpiGroups) {
             int s, f, pblk; tile_coords(p, tile, s, f, pblk);
@@ -214,6 +227,14 @@ head_kernel(const __grid_constant__ HeadMaps maps, const __grid_constant__ HeadK
             tc::fence_after_sync();
             const uint32_t tbase = tmem_base + buf * Cfg::TMEM_STRIDE + lane_addr;
 
+            if constexpr (EPI == EPI_FILTER) {
+                if (p.k <= 0) {          // debug (VD_DEBUG_SKIP_EPILOGUE): mainloop only, accumulators dropped
+                    tc::fence_before_sync();
+                    __syncwarp();
+                    if (lane == 0) tc::mbar_arrive(&sh->tmem_empty[buf]);
+                    continue;
+                }
+            }
             if constexpr (EPI == EPI_PRED) {
                 float* out = p.pred[s] + (size_t)f * p.pred_frame_stride;
 #pragma unroll 1
@@ -244,6 +265,7 @@ head_kernel(const __grid_constant__ HeadMaps maps, const __grid_constant__ HeadK
                 Box4 bx = vd_decode_box(tx, ty, tw, th, gx, gy, p.g.stride[s], p.g.anchors[s][2 * a], p.g.anchors[s][2 * a + 1]);
                 conf[a] = vd_sigmoid(to);
                 if constexpr (EPI == EPI_FILTER) {
+                    if (!inb) conf[a] = __uint_as_float(0x7fc00000u);   // NaN: no score of a padding pixel passes `> valid_thresh`
                     if (inb) p.boxes[(size_t)f * p.g.anc_base[p.g.num_scales] + p.g.anc_base[s] + cell * 3 + a] =
                         make_float4(bx.x1, bx.y1, bx.x2, bx.y2);
                 } else {   // EPI_DET: class rows of this (cell, anchor)
@@ -288,6 +310,11 @@ head_kernel(const __grid_constant__ HeadMaps maps, const __grid_constant__ HeadK
                 // IADD-immediate per candidate; the true row is restored when the list is flushed.
                 const uint32_t cellofs = (uint32_t)(q * 32 + lane);
                 const uint64_t tau0 = 1ull << 32;                   // (score key 1, any row): below every valid key
+                // warm start: tiles of the same scale and fill (full / partial pixel block) have similar score
+                // distributions, so the previous such tile's pivot is accepted in ~1 probe
+                const int slot = 2 * s + ((pblk + 1) * BLOCK_M > HW ? 1 : 0);
+                uint64_t tau_guess = gs->guess[slot];
+                uint64_t band_w = gs->band[slot];
                 uint64_t tau = tau0;                                // every valid candidate seen so far with key >= tau is in the list
                 uint32_t list_n = 0, t_acc = 0; int cur = 0;
 #pragma unroll 1
@@ -313,7 +340,7 @@ head_kernel(const __grid_constant__ HeadMaps maps, const __grid_constant__ HeadK
                             if (c < C) {
                                 // score = sigmoid(cls)*sigmoid(obj) >= +0 (or NaN): orderable key = bits | sign bit
                                 float sc = vd_score(__uint_as_float(r[i]) + bias[a * P + 5 + c], conf[a]);
-                                key = (sc > p.valid_thresh && inb) ? (__float_as_uint(sc) | 0x80000000u) : 0u;   // strict; NaN invalid
+                                key = (sc > p.valid_thresh) ? (__float_as_uint(sc) | 0x80000000u) : 0u;   // strict; NaN (incl. padding pixels) invalid
                             }
                             sk[a][i] = key;
                         }
@@ -331,10 +358,12 @@ head_kernel(const __grid_constant__ HeadMaps maps, const __grid_constant__ HeadK
                         const uint32_t ph = (uint32_t)(piv >> 32), pl = (uint32_t)piv;
                         uint32_t c = 0;
                         if (pl == 0u) {
+                            uint32_t c6[6] = {0u, 0u, 0u, 0u, 0u, 0u};     // independent chains (ILP)
 #pragma unroll
                             for (int a = 0; a < 3; ++a)
 #pragma unroll
-                                for (int i = 0; i < CCH; ++i) c += (sk[a][i] >= ph) ? 1u : 0u;
+                                for (int i = 0; i < CCH; ++i) c6[2 * a + (i & 1)] += (sk[a][i] >= ph) ? 1u : 0u;
+                            c = (c6[0] + c6[1]) + (c6[2] + c6[3]) + (c6[4] + c6[5]);
                         } else {
 #pragma unroll
                             for (int a = 0; a < 3; ++a)
@@ -348,61 +377,35 @@ head_kernel(const __grid_constant__ HeadMaps maps, const __grid_constant__ HeadK
                         for (uint32_t j = et; j < list_n; j += kEpiThreads) c += (L[cur * kListCap + j] >= piv) ? 1u : 0u;
                         return epi_sum(c, gs, grp, et, sum_it);
                     };
-                    // ---- find ntau >= tau with  k <= count(>= ntau) <= cap   (or keep tau if everything fits)
+                    // ---- find ntau >= tau with  k <= count(>= ntau) <= cap   (or keep tau if everything fits).
+                    //      One loop, one count_ge call site (the unrolled compare block is large: keeping a
+                    //      single copy keeps the epilogue inside the instruction cache): probe the warm start,
+                    //      gallop until bracketed, then bisect.
                     uint64_t ntau = tau;
                     {
-                        uint64_t probe = tau_guess > tau ? tau_guess : tau;
-                        uint32_t t = count_ge(probe);
-                        uint64_t lo = 0ull, hi = 0ull; bool have_lo = false, have_hi = false, done = false;
-                        if (t >= k && t <= cap) { ntau = probe; done = true; t_acc = t; }
-                        else if (t > cap) { lo = probe; have_lo = true; }
-                        else {                                       // t < k: too high, or everything fits
-                            hi = probe; have_hi = true;
-                            if (probe == tau) { ntau = tau; done = true; t_acc = t; }
-                            else {                                   // gallop downwards before falling back to tau
-                                uint64_t step = band_w;
-                                uint64_t mid = probe;
-                                for (int g = 0; g < 8 && !done && !have_lo; ++g) {
-                                    uint64_t nm = (mid > step && mid - step > tau) ? (mid - step) & ~0xffffffffull : tau;
-                                    if (nm <= tau) break;
-                                    mid = nm;
-                                    uint32_t t2 = count_ge(mid);
-                                    if (t2 > cap) { lo = mid; have_lo = true; }
-                                    else if (t2 < k) { hi = mid; }
-                                    else { ntau = mid; done = true; t_acc = t2; }
-                                    step <<= 1;
-                                }
-                                if (!done && !have_lo) {
-                                    uint32_t t0 = count_ge(tau);
-                                    if (t0 <= cap) { ntau = tau; done = true; t_acc = t0; }
-                                    else { lo = tau; have_lo = true; }
-                                }
-                            }
-                        }
-                        if (!done && !have_hi) {                     // gallop upwards for an upper bracket
-                            uint64_t step = (tau_guess != 0ull) ? band_w : (1ull << 58);   // warm: band-sized; cold: coarse
-                            uint64_t mid = lo;
-                            for (int g = 0; g < 40 && !done && !have_hi; ++g) {
-                                uint64_t nm = mid + step; if (nm < mid) nm = ~0ull;
-                                nm &= ~0xffffffffull; if (nm <= mid) nm = ~0ull;
-                                mid = nm;
-                                uint32_t t2 = count_ge(mid);
-                                if (t2 > cap) { lo = mid; if (mid == ~0ull) break; }
-                                else if (t2 < k) { hi = mid; have_hi = true; }
-                                else { ntau = mid; done = true; t_acc = t2; }
-                                step <<= 1; if (step == 0) step = 1ull << 63;
-                            }
-                        }
-                        if (!done) {
-                            for (int g = 0; g < 96; ++g) {          // bisection; snap to pure-score pivots while possible
-                                if (hi - lo <= 1ull) break;
+                        uint64_t piv = tau_guess > tau ? tau_guess : tau;
+                        uint64_t lo = tau, hi = ~0ull, step = (tau_guess != 0ull) ? band_w : (1ull << 58);
+                        bool have_lo = false, have_hi = false;
+#pragma unroll 1
+                        for (int g = 0; g < 160; ++g) {
+                            const uint32_t t = count_ge(piv);
+                            if ((t >= k && t <= cap) || (piv == tau && t <= cap) || g == 159) { ntau = piv; t_acc = t; break; }
+                            if (t > cap) { lo = piv; have_lo = true; } else { hi = piv; have_hi = true; }
+                            if (have_lo && have_hi) {                        // bisect; snap to pure-score pivots while possible
+                                if (hi - lo <= 1ull) { piv = lo; g = 158; continue; }   // unreachable for unique keys: superset fallback
                                 uint64_t mid = lo + ((hi - lo) >> 1);
                                 if (hi - lo > (2ull << 32)) { mid &= ~0xffffffffull; if (mid <= lo) mid += 1ull << 32; }
-                                uint32_t t2 = count_ge(mid);
-                                if (t2 > cap) lo = mid; else if (t2 < k) hi = mid; else { ntau = mid; done = true; t_acc = t2; break; }
+                                else if (hi - lo < band_w) band_w = (hi - lo) | (1ull << 32);
+                                piv = mid;
+                            } else if (have_lo) {                            // gallop up
+                                uint64_t nm = piv + step; if (nm < piv) nm = ~0ull;
+                                nm &= ~0xffffffffull; if (nm <= piv) nm = ~0ull;
+                                piv = nm; step <<= 1; if (step == 0ull) step = 1ull << 63;
+                            } else {                                         // gallop down, never below tau
+                                uint64_t nm = (piv > step && piv - step > tau) ? ((piv - step) & ~0xffffffffull) : tau;
+                                if (nm <= tau) nm = tau;
+                                piv = nm; step <<= 1; if (step == 0ull) step = 1ull << 63;
                             }
-                            if (done && hi - lo < band_w) band_w = (hi - lo) | (1ull << 32);
-                            if (!done) { ntau = lo; t_acc = count_ge(lo); }      // unreachable for unique keys (superset, still exact)
                         }
                     }
                     // ---- rebuild the list for ntau: surviving old entries, then this chunk's entries
@@ -439,13 +442,28 @@ head_kernel(const __grid_constant__ HeadMaps maps, const __grid_constant__ HeadK
                         uint64_t* wp = L + dst * kListCap + (base + incl - mine);
                         if (mine) {
                             if (pl == 0u) {
+                                // selection bitmask per anchor -> write slot = popc of the lower bits: no serial chain
+                                uint32_t m[3];
 #pragma unroll
-                                for (int a = 0; a < 3; ++a)
+                                for (int a = 0; a < 3; ++a) {
+                                    uint32_t ma = 0u, mb = 0u;
 #pragma unroll
                                     for (int i = 0; i < CCH; ++i) {
-                                        const uint32_t sv = sk[a][i];
-                                        if (sv >= ph) { *wp = ((uint64_t)sv << 32) | nrow_of(a, i); ++wp; }
+                                        const uint32_t bit = (sk[a][i] >= ph) ? (1u << i) : 0u;
+                                        if (i & 1) mb |= bit; else ma |= bit;
                                     }
+                                    m[a] = ma | mb;
+                                }
+                                const uint32_t off1 = __popc(m[0]), off2 = off1 + __popc(m[1]);
+#pragma unroll
+                                for (int a = 0; a < 3; ++a) {
+                                    const uint32_t offa = a == 0 ? 0u : (a == 1 ? off1 : off2);
+#pragma unroll
+                                    for (int i = 0; i < CCH; ++i) {
+                                        if ((m[a] >> i) & 1u)
+                                            wp[offa + __popc(m[a] & ((1u << i) - 1u))] = ((uint64_t)sk[a][i] << 32) | nrow_of(a, i);
+                                    }
+                                }
                             } else {
 #pragma unroll
                                 for (int a = 0; a < 3; ++a)
@@ -475,14 +493,16 @@ head_kernel(const __grid_constant__ HeadMaps maps, const __grid_constant__ HeadK
                         gl[j] = (v & 0xffffffff00000000ull) | (uint32_t)(~row);
                     }
                     if (et == 0) p.counts[li] = list_n;
-                    if (tau > tau0) {
+                    if (tau > tau0 && et == 0) {
                         const uint32_t q4 = (cap - k) / 4u;
                         const uint64_t nudge = band_w >> 3;
-                        tau_guess = tau;
-                        if (t_acc < k + q4 && tau > tau0 + nudge) tau_guess = (tau - nudge) & ~0xffffffffull;
-                        else if (t_acc > cap - q4) tau_guess = (tau + nudge) & ~0xffffffffull;
+                        uint64_t g2 = tau;
+                        if (t_acc < k + q4 && tau > tau0 + nudge) g2 = (tau - nudge) & ~0xffffffffull;
+                        else if (t_acc > cap - q4) g2 = (tau + nudge) & ~0xffffffffull;
+                        gs->guess[slot] = g2; gs->band[slot] = band_w;
+                        if (p.hints) { p.hints[2 * slot] = g2; p.hints[2 * slot + 1] = band_w; }   // racy by design: any value is only a hint
                     }
-                    epi_bar(grp);                                   // list buffers are reused by the next tile
+                    epi_bar(grp);                                   // list buffers / guess slots are reused by the next tile
                 }
             }
         }
@@ -547,7 +567,7 @@ struct HeadPlan {
     HeadKernelParams kp;
     int n_pad, C;
     int merge_levels;
-    size_t off_boxes, off_lists0, off_counts0, off_listsA, off_listsB, off_countsA, off_countsB, total;
+    size_t off_hints, off_boxes, off_lists0, off_counts0, off_listsA, off_listsB, off_countsA, off_countsB, total;
 };
 
 static int head_npad(int C) { int n = 3 * (5 + C); return (n + 15) / 16 * 16; }
@@ -569,7 +589,7 @@ static int make_plan(const VdHeadParams* hp, HeadPlan* pl) {
     VD_CHECK_ARG(join == VD_JOIN_NONE || join == VD_JOIN_CAT, "head: join %d must be pre-reduced (use vd_temporal_pool for max/mean)", join);
     k.K_frames = (join == VD_JOIN_CAT) ? hp->K_frames : 1;
     VD_CHECK_ARG(k.K_frames >= 1, "head: K_frames %d", k.K_frames);
-    int rows = 0, anc = 0, tif = 0, tiles = 0;
+    int rows = 0, anc = 0, tif = 0;
     for (int s = 0; s < hp->num_scales; ++s) {
         const VdHeadScale& sc = hp->scale[s];
         VD_CHECK_ARG(sc.H > 0 && sc.W > 0 && sc.H <= 128 && sc.W <= 128, "head: scale %d feature map %dx%d (alloc_size is 128x128, yolo3.py:44)", s, sc.H, sc.W);
@@ -584,14 +604,22 @@ static int make_plan(const VdHeadParams* hp, HeadPlan* pl) {
         k.cin[s] = sc.Cin; k.bias[s] = sc.bias;
         k.pb[s] = ceil_div(k.g.HW[s], BLOCK_M);
         k.tif_base[s] = tif; tif += k.pb[s];
-        k.tile_start[s] = tiles; tiles += k.pb[s] * hp->frames;
     }
-    for (int s = hp->num_scales; s <= VD_MAX_SCALES; ++s) { k.g.row_base[s] = rows; k.g.anc_base[s] = anc; if (s <= VD_MAX_SCALES) k.tile_start[s] = tiles; }
-    k.g.row_base[hp->num_scales] = rows; k.g.anc_base[hp->num_scales] = anc; k.tile_start[hp->num_scales] = tiles;
+    // processing order: second-largest K first (short pipeline fill), then the largest, smallest tiles last (balance)
+    int ord[VD_MAX_SCALES] = {0, 1, 2};
+    for (int a = 0; a < hp->num_scales; ++a)
+        for (int b = a + 1; b < hp->num_scales; ++b)
+            if (k.cin[ord[b]] > k.cin[ord[a]]) { int t = ord[a]; ord[a] = ord[b]; ord[b] = t; }
+    if (hp->num_scales >= 2) { int t = ord[0]; ord[0] = ord[1]; ord[1] = t; }
+    int tiles = 0;
+    for (int j = 0; j < hp->num_scales; ++j) { k.order[j] = ord[j]; k.tile_start[j] = tiles; tiles += k.pb[ord[j]] * hp->frames; }
+    for (int j = hp->num_scales; j < VD_MAX_SCALES; ++j) k.order[j] = 0;
+    for (int s = hp->num_scales; s <= VD_MAX_SCALES; ++s) { k.g.row_base[s] = rows; k.g.anc_base[s] = anc; k.tile_start[s] = tiles; }
     k.tiles_per_frame = tif; k.total_tiles = tiles;
     // workspace
     size_t off = 0;
     const size_t F = (size_t)(hp->frames > 0 ? hp->frames : 1);
+    pl->off_hints = off; off += 256;
     pl->off_boxes = off; off += align_up(F * anc * 16, 256);
     pl->off_lists0 = off; off += align_up(F * tif * kListCap * 8, 256);
     pl->off_counts0 = off; off += align_up(F * tif * 4, 256);
@@ -726,10 +754,12 @@ extern "C" int vd_head_forward_stages(const VdHeadParams* hp, float* ids, float*
     const int k = (int)k64;
     unsigned char* ws = (unsigned char*)workspace;
     HeadKernelParams& kp = pl.kp;
+    kp.hints = (unsigned long long*)(ws + pl.off_hints);
     kp.boxes = (float4*)(ws + pl.off_boxes);
     kp.lists = (uint64_t*)(ws + pl.off_lists0);
     kp.counts = (uint32_t*)(ws + pl.off_counts0);
     kp.valid_thresh = hp->valid_thresh; kp.k = k; kp.cap = (k <= 448) ? 640 : kListCap;
+    if (getenv("VD_DEBUG_SKIP_EPILOGUE")) kp.k = 0;     // profiling aid: results are garbage
 
     for (int s = 0; s < hp->num_scales; ++s) {      // optional temporal tip cell in front (layers.py:82-89)
         const VdHeadScale& sc = hp->scale[s];
@@ -821,7 +851,7 @@ extern "C" int vd_pred_conv(const void* x, int B, int H, int W, int Cin, int K_f
         kp.g.H[0] = H; kp.g.W[0] = W; kp.g.HW[0] = (int)HW; kp.g.stride[0] = 1.f;
         kp.frames = B; kp.K_frames = K; kp.cin[0] = Cin;
         kp.pb[0] = ceil_div((int)HW, BLOCK_M);
-        kp.tile_start[0] = 0; kp.tile_start[1] = kp.pb[0] * B;
+        kp.tile_start[0] = 0; kp.tile_start[1] = kp.pb[0] * B; kp.order[0] = 0;
         kp.tiles_per_frame = kp.pb[0]; kp.total_tiles = kp.pb[0] * B;
         kp.n_pad = (nn + 15) / 16 * 16; kp.n_valid = nn;
         kp.bias[0] = bias ? bias + n0 : nullptr;

@@ -66,6 +66,34 @@ __device__ __forceinline__ void bitonic_sort_u32_asc(uint32_t* s, int SN) {
     __syncthreads();
 }
 
+// One element per thread (SN == blockDim.x): strides < 32 exchange by warp shuffle, larger strides
+// through shared memory -- 10 barrier rounds instead of 45 for SN = 512.
+template <typename T, bool kDescending>
+__device__ __forceinline__ void bitonic_sort_reg(T* s, int SN) {
+    const int tid = threadIdx.x;
+    T v = s[tid];
+    for (int size = 2; size <= SN; size <<= 1) {
+        const bool dir = ((tid & size) == 0) == kDescending;       // true: this run sorts descending
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            T o;
+            if (stride >= 32) {
+                __syncthreads(); s[tid] = v; __syncthreads();
+                o = s[tid ^ stride];
+            } else {
+                if constexpr (sizeof(T) == 8) o = (T)__shfl_xor_sync(0xffffffffu, (unsigned long long)v, stride);
+                else o = (T)__shfl_xor_sync(0xffffffffu, (unsigned)v, stride);
+            }
+            const bool lower = (tid & stride) == 0;
+            const bool keep_max = (lower == dir);
+            const T mx = v > o ? v : o, mn = v > o ? o : v;
+            v = keep_max ? mx : mn;
+        }
+    }
+    __syncthreads();
+    s[tid] = v;
+    __syncthreads();
+}
+
 // Source: gives box (corner), integer class and area for (image b, row).  Sink: writes output.
 template <class Source, class Sink>
 __device__ void nms_final_body(const uint64_t* __restrict__ lists, const uint32_t* __restrict__ counts,
@@ -105,7 +133,9 @@ __device__ void nms_final_body(const uint64_t* __restrict__ lists, const uint32_
     int it = 0; uint32_t nsel = 0;
     uint64_t piv = block_select_pivot<kFinalR>(keys, (uint32_t)k, (uint32_t)SN, 0ull, 0ull, scr, it, &nsel);
     block_compact<kFinalR>(keys, piv, skeys, (uint32_t)SN, &scr->out_count);
-    bitonic_sort_desc(skeys, SN);                      // starts and ends with __syncthreads
+    __syncthreads();
+    if (SN == (int)blockDim.x) bitonic_sort_reg<uint64_t, true>(skeys, SN);
+    else bitonic_sort_desc(skeys, SN);                 // starts and ends with __syncthreads
     const int n = (int)(nsel < (uint32_t)k ? nsel : (uint32_t)k);
 
     // ---- 3. per-rank box / class / area
@@ -122,16 +152,19 @@ __device__ void nms_final_body(const uint64_t* __restrict__ lists, const uint32_
         // secondary key (class bucket, rank): same-class ranks become contiguous, rank ascending
         for (int i = tid; i < SN; i += blockDim.x)
             skey2[i] = (i < n) ? (((uint32_t)scls[i] << 10) | (uint32_t)i) : 0xffffffffu;
-        bitonic_sort_u32_asc(skey2, SN);
-        for (int i = tid; i < n; i += blockDim.x) {
+        __syncthreads();
+        if (SN == (int)blockDim.x) bitonic_sort_reg<uint32_t, false>(skey2, SN);
+        else bitonic_sort_u32_asc(skey2, SN);
+        // 4 threads per rank walk the rank's bucket tail with stride 4 (buckets are ~n/C long)
+        for (int i = tid >> 2; i < n; i += blockDim.x >> 2) {
             uint32_t ki = skey2[i];
             int r = (int)(ki & 1023u); uint32_t ci = ki >> 10;
-            float4 br = sbox[r]; float ar = sarea[r];
-            for (int j = i + 1; j < n; ++j) {
+            float4 br = sbox[r]; float ar = sarea[r]; const int cr = scls[r];
+            for (int j = i + 1 + (tid & 3); j < n; j += 4) {
                 uint32_t kj = skey2[j];
                 if ((kj >> 10) != ci) break;
                 int p = (int)(kj & 1023u);             // p > r (rank ascending inside a bucket)
-                if (scls[p] != scls[r]) continue;      // bucket = low 22 bits of the id; compare the full int
+                if (scls[p] != cr) continue;           // bucket = low 22 bits of the id; compare the full int
                 if (vd_iou_gt(br, ar, sbox[p], sarea[p], P.overlap_thresh))
                     atomicOr(&smask[r * NW + (p >> 5)], 1u << (p & 31));
             }
@@ -174,10 +207,16 @@ __device__ void nms_final_body(const uint64_t* __restrict__ lists, const uint32_
                 for (int w2 = w + 1 + lane; w2 < NW; w2 += 32) { salive[w2] = 0u; sprefix[w2] = (uint32_t)kept_total; }
                 break;
             }
-            uint32_t a = alive;
-            while (a) {                                // alive rows suppress later blocks
-                int j = __ffs(a) - 1; a &= a - 1;
-                if (lane > w && lane < NW) removed |= smask[(base + j) * NW + lane];
+            // alive rows suppress later blocks: 32 independent (warp-uniformly predicated) row loads
+            if (lane > w && lane < NW) {
+                const uint32_t* mrow = smask + base * NW + lane;
+                uint32_t acc0 = 0u, acc1 = 0u;
+#pragma unroll
+                for (int j = 0; j < 32; j += 2) {
+                    if ((alive >> j) & 1u) acc0 |= mrow[j * NW];
+                    if ((alive >> (j + 1)) & 1u) acc1 |= mrow[(j + 1) * NW];
+                }
+                removed |= acc0 | acc1;
             }
         }
         if (lane == 0) sprefix[63] = (uint32_t)kept_total;

@@ -31,13 +31,28 @@ namespace vd {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;
 constexpr int UMMA_K = 16;
-constexpr int kEpiGroups = 2;                 // epilogue warpgroups; group g owns TMEM buffer g (tiles it%2 == g)
+constexpr int kMaxEpiGroups = 3;              // epilogue warpgroups G (2 or 3); group g owns TMEM buffer g (tiles it%G == g)
 constexpr int kEpiWarp0 = 2;                  // warp 0: TMA, warp 1: MMA, then 2 x 4 epilogue warps
 constexpr int kEpiThreads = 128;
-constexpr int kHeadThreads = kEpiWarp0 * 32 + kEpiGroups * kEpiThreads;   // 320
 constexpr int A_TILE_BYTES = BLOCK_M * BLOCK_K * 2;
 
 enum { EPI_FILTER = 0, EPI_DET = 1, EPI_PRED = 2 };
+
+// Per-frame histogram of the emitted candidates' scores: 4096 bins, 512 per octave over [2^-7, 2).
+// Monotone in the key, so "the highest bin b* whose suffix count reaches k" gives a frame-level
+// pivot with at most k + (population of b*) candidates above it -- no search in the NMS kernel.
+constexpr int kHistBins = 4096;
+constexpr int kHistCap = 2048;                // candidates the NMS kernel can hold after the pivot
+__host__ __device__ __forceinline__ uint32_t hist_bin(uint32_t key_hi) {
+    if (!(key_hi & 0x80000000u)) return 0u;                       // negative scores: lowest bin
+    uint32_t b = (key_hi & 0x7fffffffu) >> 14;
+    const uint32_t lo = (127u - 7u) << 9;
+    b = b > lo ? b - lo : 0u;
+    return b > (uint32_t)(kHistBins - 1) ? (uint32_t)(kHistBins - 1) : b;
+}
+__host__ __device__ __forceinline__ uint32_t hist_edge(uint32_t bin) {   // smallest key_hi that falls in `bin` (0: everything)
+    return bin == 0u ? 0u : ((((bin + ((127u - 7u) << 9)) << 14)) | 0x80000000u);
+}
 
 struct HeadKernelParams {
     HeadGeom g;
@@ -53,6 +68,7 @@ struct HeadKernelParams {
     // EPI_FILTER
     float4* boxes; uint64_t* lists; uint32_t* counts; float valid_thresh; int k, cap;
     unsigned long long* hints;           // [2*VD_MAX_SCALES][2] (pivot, band) warm starts, persist in the workspace across calls
+    uint32_t* hist;                      // [frames][kHistBins] score histogram of the emitted candidates (zeroed per call)
     // EPI_DET
     float* det; long long det_rows_total;
     // EPI_PRED
@@ -66,12 +82,16 @@ template <int EPI, int C, int NPAD> struct HeadCfg {
     static constexpr int LIST_BUFS = (EPI == EPI_FILTER) ? (NCH > 1 ? 2 : 1) : 0;   // ping-pong only if the list can shrink
     static constexpr int B_TILE_BYTES = NPAD * BLOCK_K * 2;
     static constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
-    static constexpr int LIST_BYTES = kEpiGroups * LIST_BUFS * kListCap * 8;
+    static constexpr int TMEM_STRIDE = NPAD <= 128 ? 128 : 256;
+    // 3 groups (12 epilogue warps, 128 registers/thread) when three accumulators fit TMEM and the
+    // per-thread key set is small enough; else 2 groups (168 registers/thread)
+    static constexpr int G = (EPI == EPI_FILTER && TMEM_STRIDE == 128) ? 3 : 2;
+    static constexpr int THREADS = kEpiWarp0 * 32 + G * kEpiThreads;
+    static constexpr int LIST_BYTES = G * LIST_BUFS * kListCap * 8;
     static constexpr int EPI_BYTES = LIST_BYTES + VD_MAX_SCALES * NPAD * 4 + 1024;
     static constexpr int STAGES_RAW = (225 * 1024 - EPI_BYTES - 1024) / STAGE_BYTES;
     static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
-    static constexpr int TMEM_STRIDE = NPAD <= 128 ? 128 : 256;
-    static constexpr int TMEM_COLS = 2 * TMEM_STRIDE;
+    static constexpr int TMEM_COLS = (G * TMEM_STRIDE) <= 256 ? 256 : 512;
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 1024;   // +1024 alignment slack
     static_assert(NPAD % 16 == 0 && NPAD >= 16 && NPAD <= 256, "NPAD");
     static_assert(STAGE_BYTES % 1024 == 0, "stage must keep 1024-byte alignment");
@@ -84,9 +104,9 @@ struct EpiGroupShared {
     uint64_t band[2 * VD_MAX_SCALES];      // running estimate of the accept band's key width
 };
 struct HeadShared {
-    uint64_t full[8], empty[8], tmem_full[2], tmem_empty[2];
+    uint64_t full[8], empty[8], tmem_full[kMaxEpiGroups], tmem_empty[kMaxEpiGroups];
     uint32_t tmem_base, pad_;
-    EpiGroupShared grp[kEpiGroups];
+    EpiGroupShared grp[kMaxEpiGroups];
 };
 
 __device__ __forceinline__ void epi_bar(int grp) { asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "n"(kEpiThreads) : "memory"); }
@@ -114,10 +134,11 @@ __device__ __forceinline__ void tile_coords(const HeadKernelParams& p, int tile,
 }
 
 template <int EPI, int C, int NPAD>
-__global__ void __launch_bounds__(kHeadThreads, 1)
+__global__ void __launch_bounds__((HeadCfg<EPI, C, NPAD>::THREADS), 1)
 head_kernel(const __grid_constant__ HeadMaps maps, const __grid_constant__ HeadKernelParams p) {
     using Cfg = HeadCfg<EPI, C, NPAD>;
     constexpr int P = 5 + C;
+    constexpr int G = Cfg::G;
     extern __shared__ unsigned char smem_dyn[];
     // 1024-byte alignment for the 128B-swizzled operand tiles; offset arithmetic keeps the
     // shared-memory address space visible to the compiler (LDS/STS instead of generic LD/ST)
@@ -130,14 +151,14 @@ head_kernel(const __grid_constant__ HeadMaps maps, const __grid_constant__ HeadK
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     // ---------------- one-time setup
-    for (int i = threadIdx.x; i < VD_MAX_SCALES * NPAD; i += kHeadThreads) {
+    for (int i = threadIdx.x; i < VD_MAX_SCALES * NPAD; i += Cfg::THREADS) {
         int s = i / NPAD, n = i % NPAD;
         sbias[i] = (s < p.g.num_scales && p.bias[s] && n < p.n_valid) ? p.bias[s][n] : 0.0f;
     }
     if (threadIdx.x == 0) {
         for (int i = 0; i < Cfg::STAGES; ++i) { tc::mbar_init(&sh->full[i], 1); tc::mbar_init(&sh->empty[i], 1); }
-        for (int i = 0; i < 2; ++i) { tc::mbar_init(&sh->tmem_full[i], 1); tc::mbar_init(&sh->tmem_empty[i], 4); }
-        for (int g = 0; g < kEpiGroups; ++g) {
+        for (int i = 0; i < G; ++i) { tc::mbar_init(&sh->tmem_full[i], 1); tc::mbar_init(&sh->tmem_empty[i], 4); }
+        for (int g = 0; g < G; ++g) {
             sh->grp[g].cnt[0] = sh->grp[g].cnt[1] = sh->grp[g].cnt[2] = 0; sh->grp[g].cursor = 0;
             for (int i = 0; i < 2 * VD_MAX_SCALES; ++i) {
                 unsigned long long hg = 0ull, hb = 0ull;
@@ -160,6 +181,8 @@ head_kernel(const __grid_constant__ HeadMaps maps, const __grid_constant__ HeadK
         // =========================== TMA producer ===========================
         if (tc::elect_one()) {
             int stage = 0; uint32_t phase = 0;
+            const uint64_t pol_a = tc::policy_evict_first();    // activations are read exactly once
+            const uint64_t pol_w = tc::policy_evict_last();     // weights are re-read by every tile
             for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
                 int s, f, pblk; tile_coords(p, tile, s, f, pblk);
                 const int kb_per_frame = p.cin[s] / BLOCK_K;
@@ -170,8 +193,8 @@ head_kernel(const __grid_constant__ HeadMaps maps, const __grid_constant__ HeadK
                     unsigned char* a_dst = ring + stage * Cfg::STAGE_BYTES;
                     unsigned char* b_dst = a_dst + A_TILE_BYTES;
                     tc::mbar_expect_tx(&sh->full[stage], Cfg::STAGE_BYTES);
-                    tc::tma_load_4d(a_dst, &maps.a[s], &sh->full[stage], c0, pblk * BLOCK_M, kf, f);
-                    tc::tma_load_2d(b_dst, &maps.w[s], &sh->full[stage], kf * p.cin[s] + c0, 0);
+                    tc::tma_load_4d_hint(a_dst, &maps.a[s], &sh->full[stage], c0, pblk * BLOCK_M, kf, f, pol_a);
+                    tc::tma_load_2d_hint(b_dst, &maps.w[s], &sh->full[stage], kf * p.cin[s] + c0, 0, pol_w);
                     c0 += BLOCK_K; if (c0 == p.cin[s]) { c0 = 0; ++kf; }
                     if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
                 }
@@ -185,8 +208,8 @@ head_kernel(const __grid_constant__ HeadMaps maps, const __grid_constant__ HeadK
             for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
                 int s, f, pblk; tile_coords(p, tile, s, f, pblk);
                 const int nkb = (p.cin[s] / BLOCK_K) * p.K_frames;
-                const uint32_t buf = it & 1u;
-                tc::mbar_wait(&sh->tmem_empty[buf], ((it >> 1) & 1u) ^ 1u);
+                const uint32_t buf = it % (uint32_t)G;
+                tc::mbar_wait(&sh->tmem_empty[buf], ((it / (uint32_t)G) & 1u) ^ 1u);
                 tc::fence_after_sync();
                 const uint32_t d_tmem = tmem_base + buf * Cfg::TMEM_STRIDE;
                 for (int kb = 0; kb < nkb; ++kb) {
@@ -215,7 +238,7 @@ head_kernel(const __grid_constant__ HeadMaps maps, const __grid_constant__ HeadK
         int sum_it = 0;
         (void)gs; (void)L; (void)sum_it; (void)et;
         uint32_t it = (uint32_t)grp;
-        for (int tile = blockIdx.x + grp * gridDim.x; tile < p.total_tiles; tile += kEpiGroups * gridDim.x, it += kEpiGroups) {
+        for (int tile = blockIdx.x + grp * gridDim.x; tile < p.total_tiles; tile += G * gridDim.x, it += G) {
             int s, f, pblk; tile_coords(p, tile, s, f, pblk);
             const uint32_t buf = (uint32_t)grp;
             const int HW = p.g.HW[s], Wd = p.g.W[s];
@@ -223,7 +246,7 @@ head_kernel(const __grid_constant__ HeadMaps maps, const __grid_constant__ HeadK
             const bool inb = cell < HW;
             const float gx = (float)(cell % Wd), gy = (float)(cell / Wd);
             const float* bias = sbias + s * NPAD;
-            tc::mbar_wait(&sh->tmem_full[buf], (it >> 1) & 1u);
+            tc::mbar_wait(&sh->tmem_full[buf], (it / (uint32_t)G) & 1u);
             tc::fence_after_sync();
             const uint32_t tbase = tmem_base + buf * Cfg::TMEM_STRIDE + lane_addr;
 
@@ -491,6 +514,7 @@ head_kernel(const __grid_constant__ HeadMaps maps, const __grid_constant__ HeadK
                         const uint32_t local = ~(uint32_t)v;
                         const uint32_t row = rbase + (local >> 9) * HW3 + ((local >> 2) & 127u) * 3u + (local & 3u);
                         gl[j] = (v & 0xffffffff00000000ull) | (uint32_t)(~row);
+                        atomicAdd(&p.hist[(size_t)f * kHistBins + hist_bin((uint32_t)(v >> 32))], 1u);
                     }
                     if (et == 0) p.counts[li] = list_n;
                     if (tau > tau0 && et == 0) {
@@ -558,6 +582,118 @@ nms_final_fused_kernel(const uint64_t* __restrict__ lists, const uint32_t* __res
     nms_final_body(lists + (size_t)f * n_lists * kListCap, counts + (size_t)f * n_lists, n_lists, f, P, src, sink, smem_raw);
 }
 
+// Per-frame top-k + NMS straight from the tile lists: the frame pivot comes from the score histogram
+// (suffix scan), the lists are streamed once and compacted, then sort + nms_tail.  No merge passes,
+// no pivot search (a streaming bisection remains as the fallback for pathologically tied scores).
+__global__ void __launch_bounds__(kFinalThreads, 1)
+nms_final_hist_kernel(const uint64_t* __restrict__ lists, const uint32_t* __restrict__ counts, int n_lists,
+                      const uint32_t* __restrict__ hist, NmsParams P, FusedSource src, FusedSink sink) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    const int k = P.k, NW = (k + 31) >> 5, SNk = P.sortn;
+    SelectScratch* scr = reinterpret_cast<SelectScratch*>(smem_raw);
+    uint32_t* sx = reinterpret_cast<uint32_t*>(smem_raw + 64);          // [48] warp sums + results
+    uint64_t* skeys = reinterpret_cast<uint64_t*>(smem_raw + 256);
+    float4* sbox = reinterpret_cast<float4*>(skeys + kHistCap);
+    int* scls = reinterpret_cast<int*>(sbox + k);
+    float* sarea = reinterpret_cast<float*>(scls + k);
+    uint32_t* smask = reinterpret_cast<uint32_t*>(sarea + k);
+    uint32_t* skey2 = smask + (size_t)k * NW;
+    uint32_t* salive = skey2 + SNk;
+    uint32_t* sprefix = salive + 64;
+    lists += (size_t)f * n_lists * kListCap; counts += (size_t)f * n_lists; hist += (size_t)f * kHistBins;
+
+    VD_STAMP(P, 0);
+    select_scratch_init(scr);
+    // ---- 1. suffix scan of the histogram; thread t owns bins [4095-8t-7, 4095-8t], highest first
+    constexpr int BPT = kHistBins / kFinalThreads;
+    uint32_t h[BPT], local = 0u;
+#pragma unroll
+    for (int i = 0; i < BPT; ++i) { h[i] = hist[kHistBins - 1 - (tid * BPT + i)]; local += h[i]; }
+    uint32_t incl = local;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+    if (lane == 31) sx[warp] = incl;
+    __syncthreads();
+    uint32_t woff = 0u, total = 0u;
+    for (int w = 0; w < nwarps; ++w) { uint32_t v = sx[w]; if (w < warp) woff += v; total += v; }
+    if (tid == 0) { sx[32] = 0u; sx[33] = total; }                     // defaults: fewer than k candidates -> take all
+    __syncthreads();
+    const uint32_t excl = woff + incl - local;
+    if (excl < (uint32_t)k && excl + local >= (uint32_t)k) {
+        uint32_t run = excl;
+#pragma unroll
+        for (int i = 0; i < BPT; ++i) {
+            run += h[i];
+            if (run >= (uint32_t)k) { sx[32] = (uint32_t)(kHistBins - 1 - (tid * BPT + i)); sx[33] = run; break; }
+        }
+    }
+    __syncthreads();
+    VD_STAMP(P, 1);
+    const uint32_t bstar = sx[32];
+    uint32_t cnt = sx[33];
+    uint64_t piv = (uint64_t)hist_edge(bstar) << 32;
+
+    auto stream_count = [&](uint64_t pv, int& it) -> uint32_t {
+        uint32_t c = 0u;
+        for (int l = warp; l < n_lists; l += nwarps) {
+            uint32_t n = counts[l]; n = n > (uint32_t)kListCap ? (uint32_t)kListCap : n;
+            for (uint32_t j = lane; j < n; j += 32) { uint64_t v = lists[(size_t)l * kListCap + j]; c += (v >= pv && v != 0ull) ? 1u : 0u; }
+        }
+        return block_sum(c, scr, it);
+    };
+    if (cnt > (uint32_t)kHistCap) {            // rare: one bin holds a huge tie cluster -> bisect inside it
+        int it = 0;
+        uint64_t lo = piv, hi = (bstar + 1u < (uint32_t)kHistBins) ? ((uint64_t)hist_edge(bstar + 1u) << 32) : ~0ull;
+        for (int g = 0; g < 80 && hi - lo > 1ull; ++g) {
+            uint64_t mid = lo + ((hi - lo) >> 1);
+            uint32_t c = stream_count(mid, it);
+            if (c > (uint32_t)kHistCap) lo = mid; else if (c < (uint32_t)k) hi = mid; else { lo = mid; cnt = c; break; }
+        }
+        piv = lo;
+    }
+    // ---- 2. stream the tile lists once, keep keys >= pivot.  Work items = (list, 32-key chunk); each
+    //         warp issues 8 independent 8-byte loads per lane before consuming them (memory-level parallelism).
+    uint32_t* scount = reinterpret_cast<uint32_t*>(sprefix + 64);     // [n_lists] clamped list lengths
+    for (int l = tid; l < n_lists; l += blockDim.x) { uint32_t n = counts[l]; scount[l] = n > (uint32_t)kListCap ? (uint32_t)kListCap : n; }
+    __syncthreads();
+    for (int l = warp; l < n_lists; l += nwarps) {           // one list per warp pass, 16 loads in flight per lane
+        const uint32_t nl = scount[l];
+        const uint64_t* src_l = lists + (size_t)l * kListCap;
+        for (uint32_t b0 = 0; b0 < nl; b0 += 512u) {
+            uint64_t v[16];
+#pragma unroll
+            for (int u = 0; u < 16; ++u) { const uint32_t j = b0 + (uint32_t)(u * 32 + lane); v[u] = (j < nl) ? src_l[j] : 0ull; }
+#pragma unroll
+            for (int u = 0; u < 16; ++u) {
+                const bool keep = v[u] >= piv && v[u] != 0ull;
+                const unsigned m = __ballot_sync(0xffffffffu, keep);
+                if (m) {
+                    uint32_t base = 0u;
+                    if (lane == 0) base = atomicAdd(&scr->out_count, (uint32_t)__popc(m));
+                    base = __shfl_sync(0xffffffffu, base, 0);
+                    const uint32_t pos = base + __popc(m & ((1u << lane) - 1u));
+                    if (keep && pos < (uint32_t)kHistCap) skeys[pos] = v[u];
+                }
+            }
+        }
+    }
+    __syncthreads();
+    VD_STAMP(P, 2);
+    uint32_t m = scr->out_count; m = m > (uint32_t)kHistCap ? (uint32_t)kHistCap : m;
+    const int SN = m <= 512u ? 512 : (m <= 1024u ? 1024 : 2048);
+    for (int i = (int)m + tid; i < SN; i += blockDim.x) skeys[i] = 0ull;
+    __syncthreads();
+    if (SN == (int)blockDim.x) bitonic_sort_reg<uint64_t, true>(skeys, SN);
+    else bitonic_sort_desc(skeys, SN);
+    VD_STAMP(P, 3);
+    const int n = (int)(m < (uint32_t)k ? m : (uint32_t)k);
+    nms_tail(n, f, P, src, sink, skeys, sbox, scls, sarea, smask, skey2, salive, sprefix);
+}
+static size_t nms_hist_smem(int k) {
+    return 256 + (size_t)kHistCap * 8 + (size_t)k * 16 + (size_t)k * 8 + (size_t)k * nms_words(k) * 4 + (size_t)nms_sortn(k) * 4 + 512 + 64 + 1024;   // + per-list counts (<= 256 lists)
+}
+
 // no-NMS tail (yolo3.py:525 false): rows are the plain concat; only reachable through vd_head_detections.
 
 // ----------------------------------------------------------------------------------------------
@@ -567,7 +703,7 @@ struct HeadPlan {
     HeadKernelParams kp;
     int n_pad, C;
     int merge_levels;
-    size_t off_hints, off_boxes, off_lists0, off_counts0, off_listsA, off_listsB, off_countsA, off_countsB, total;
+    size_t off_hints, off_hist, off_boxes, off_lists0, off_counts0, off_listsA, off_listsB, off_countsA, off_countsB, total;
 };
 
 static int head_npad(int C) { int n = 3 * (5 + C); return (n + 15) / 16 * 16; }
@@ -616,10 +752,12 @@ static int make_plan(const VdHeadParams* hp, HeadPlan* pl) {
     for (int j = hp->num_scales; j < VD_MAX_SCALES; ++j) k.order[j] = 0;
     for (int s = hp->num_scales; s <= VD_MAX_SCALES; ++s) { k.g.row_base[s] = rows; k.g.anc_base[s] = anc; k.tile_start[s] = tiles; }
     k.tiles_per_frame = tif; k.total_tiles = tiles;
+    if (tif > 256) return set_error(VD_ERR_UNSUPPORTED, "head: %d pixel blocks per frame > 256", tif);
     // workspace
     size_t off = 0;
     const size_t F = (size_t)(hp->frames > 0 ? hp->frames : 1);
     pl->off_hints = off; off += 256;
+    pl->off_hist = off; off += align_up(F * kHistBins * 4, 256);
     pl->off_boxes = off; off += align_up(F * anc * 16, 256);
     pl->off_lists0 = off; off += align_up(F * tif * kListCap * 8, 256);
     pl->off_counts0 = off; off += align_up(F * tif * 4, 256);
@@ -662,7 +800,7 @@ static int launch_head_t(const HeadMaps& maps, const HeadKernelParams& kp, cudaS
     }
     int grid = sm_count(); if (grid > kp.total_tiles) grid = kp.total_tiles;
     if (grid < 1) return VD_OK;
-    kern<<<grid, kHeadThreads, Cfg::SMEM_BYTES, stream>>>(maps, kp);
+    kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(maps, kp);
     VD_LAUNCH_CHECK();
     return VD_OK;
 }
@@ -721,9 +859,7 @@ extern "C" size_t vd_head_workspace_bytes(const VdHeadParams* p) {
 extern "C" int vd_head_launch_count(const VdHeadParams* hp) {
     HeadPlan pl;
     if (make_plan(hp, &pl) != VD_OK) return -1;
-    int n = 1, lists = pl.kp.tiles_per_frame;                 // head kernel
-    while (lists > kMaxLists) { lists = ceil_div(lists, kMaxLists); ++n; }   // merge passes
-    n += 1;                                                   // per-frame top-k + NMS
+    int n = 2;                                                // fused head kernel + per-frame top-k / NMS kernel
     for (int s = 0; s < hp->num_scales; ++s) if (hp->scale[s].tconv_weight_bf16) ++n;
     return n;
 }
@@ -755,6 +891,7 @@ extern "C" int vd_head_forward_stages(const VdHeadParams* hp, float* ids, float*
     unsigned char* ws = (unsigned char*)workspace;
     HeadKernelParams& kp = pl.kp;
     kp.hints = (unsigned long long*)(ws + pl.off_hints);
+    kp.hist = (uint32_t*)(ws + pl.off_hist);
     kp.boxes = (float4*)(ws + pl.off_boxes);
     kp.lists = (uint64_t*)(ws + pl.off_lists0);
     kp.counts = (uint32_t*)(ws + pl.off_counts0);
@@ -775,33 +912,24 @@ extern "C" int vd_head_forward_stages(const VdHeadParams* hp, float* ids, float*
     rc = make_maps(hp, pl, &maps);
     if (rc) return rc;
     if (stage_mask & VD_STAGE_HEAD) {
+        VD_CUDA(cudaMemsetAsync(kp.hist, 0, (size_t)hp->frames * kHistBins * 4, stream));
         rc = launch_head<EPI_FILTER>(maps, kp, pl.C, stream);
         if (rc) return rc;
     }
     if (!(stage_mask & VD_STAGE_NMS)) return VD_OK;
 
-    const uint64_t* lists = kp.lists; const uint32_t* counts = kp.counts; int n_lists = kp.tiles_per_frame;
-    uint64_t* lout = (uint64_t*)(ws + pl.off_listsA); uint32_t* cout = (uint32_t*)(ws + pl.off_countsA);
-    uint64_t* lalt = (uint64_t*)(ws + pl.off_listsB); uint32_t* calt = (uint32_t*)(ws + pl.off_countsB);
-    while (n_lists > kMaxLists) {
-        int n_out = ceil_div(n_lists, kMaxLists);
-        nms_merge_kernel<<<dim3(n_out, hp->frames), kFinalThreads, 0, stream>>>(lists, counts, n_lists, lout, cout, n_out, k);
-        VD_LAUNCH_CHECK();
-        lists = lout; counts = cout; n_lists = n_out;
-        uint64_t* tl = lout; lout = lalt; lalt = tl; uint32_t* tcn = cout; cout = calt; calt = tcn;
-    }
     NmsParams P;
     P.overlap_thresh = hp->nms_thresh; P.k = k; P.sortn = nms_sortn(k); P.class_aware = 1;
     P.max_out = hp->post_nms;
+    P.dbg = getenv("VD_DEBUG_NMS_STAMPS") ? (long long*)(ws + pl.off_listsA) : nullptr;   // profiling aid (unused merge area)
     FusedSource src{kp.g, kp.boxes};
     FusedSink sink{ids, scores, bboxes, keep_rows_or_null, hp->post_nms};
-    size_t smem = nms_final_smem(k);
     static bool configured = false;
     if (!configured) {
-        VD_CUDA(cudaFuncSetAttribute(nms_final_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)nms_final_smem(VD_MAX_TOPK)));
+        VD_CUDA(cudaFuncSetAttribute(nms_final_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)nms_hist_smem(VD_MAX_TOPK)));
         configured = true;
     }
-    nms_final_fused_kernel<<<hp->frames, kFinalThreads, smem, stream>>>(lists, counts, n_lists, P, src, sink);
+    nms_final_hist_kernel<<<hp->frames, kFinalThreads, nms_hist_smem(k), stream>>>(kp.lists, kp.counts, kp.tiles_per_frame, kp.hist, P, src, sink);
     VD_LAUNCH_CHECK();
     return VD_OK;
 }

@@ -194,7 +194,7 @@ extern "C" int vd_box_nms(const float* data, int64_t num_batch, int64_t num_elem
     }
     NmsParams P;
     P.overlap_thresh = overlap_thresh; P.k = k; P.sortn = nms_sortn(k);
-    P.class_aware = (!force_suppress && id_index >= 0) ? 1 : 0; P.max_out = k;
+    P.class_aware = (!force_suppress && id_index >= 0) ? 1 : 0; P.max_out = k; P.dbg = nullptr;
     size_t smem = nms_final_smem(k);
     static bool configured = false;
     if (!configured) {

@@ -32,7 +32,9 @@ struct NmsParams {
     int sortn;          // power of two >= k, >= 512
     int class_aware;    // !force_suppress && id_index >= 0
     int max_out;        // rows to emit per image (post_nms for the fused head, k for box_nms)
+    long long* dbg;     // optional per-phase clock64() stamps of block 0 (profiling aid), else null
 };
+#define VD_STAMP(P, i) do { if ((P).dbg && blockIdx.x == 0 && threadIdx.x == 0) (P).dbg[i] = clock64(); } while (0)
 
 static inline int nms_sortn(int k) { return k <= 512 ? 512 : 1024; }
 static inline int nms_words(int k) { return (k + 31) / 32; }
@@ -94,6 +96,117 @@ __device__ __forceinline__ void bitonic_sort_reg(T* s, int SN) {
     __syncthreads();
 }
 
+
+// Steps 3-6 on the sorted keys skeys[0..n): gather boxes, suppression matrix, greedy scan, emit.
+template <class Source, class Sink>
+__device__ void nms_tail(const int n, const int b, const NmsParams P, const Source& src, const Sink& sink,
+                         uint64_t* skeys, float4* sbox, int* scls, float* sarea, uint32_t* smask,
+                         uint32_t* skey2, uint32_t* salive, uint32_t* sprefix) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    const int k = P.k, SN = P.sortn, NW = (k + 31) >> 5;
+    (void)k;
+    VD_STAMP(P, 4);
+    // ---- 3. per-rank box / class / area
+    for (int r = tid; r < n; r += blockDim.x) {
+        float4 bx; int c; float ar;
+        src.load(b, key_row(skeys[r]), key_score(skeys[r]), bx, c, ar);
+        sbox[r] = bx; scls[r] = c; sarea[r] = ar;
+    }
+    for (int i = tid; i < n * NW; i += blockDim.x) smask[i] = 0u;
+    __syncthreads();
+
+    VD_STAMP(P, 5);
+    // ---- 4. suppression matrix
+    if (P.class_aware) {
+        // secondary key (class bucket, rank): same-class ranks become contiguous, rank ascending
+        for (int i = tid; i < SN; i += blockDim.x)
+            skey2[i] = (i < n) ? (((uint32_t)scls[i] << 10) | (uint32_t)i) : 0xffffffffu;
+        __syncthreads();
+        if (SN == (int)blockDim.x) bitonic_sort_reg<uint32_t, false>(skey2, SN);
+        else bitonic_sort_u32_asc(skey2, SN);
+        VD_STAMP(P, 6);
+        // 4 threads per rank walk the rank's bucket tail with stride 4 (buckets are ~n/C long)
+        for (int i = tid >> 2; i < n; i += blockDim.x >> 2) {
+            uint32_t ki = skey2[i];
+            int r = (int)(ki & 1023u); uint32_t ci = ki >> 10;
+            float4 br = sbox[r]; float ar = sarea[r]; const int cr = scls[r];
+            for (int j = i + 1 + (tid & 3); j < n; j += 4) {
+                uint32_t kj = skey2[j];
+                if ((kj >> 10) != ci) break;
+                int p = (int)(kj & 1023u);             // p > r (rank ascending inside a bucket)
+                if (scls[p] != cr) continue;           // bucket = low 22 bits of the id; compare the full int
+                if (vd_iou_gt(br, ar, sbox[p], sarea[p], P.overlap_thresh))
+                    atomicOr(&smask[r * NW + (p >> 5)], 1u << (p & 31));
+            }
+        }
+    } else {
+        for (int r = warp; r < n; r += nwarps) {
+            float4 br = sbox[r]; float ar = sarea[r];
+            for (int w = r >> 5; w < NW; ++w) {
+                int p = (w << 5) + lane;
+                bool s = false;
+                if (p > r && p < n) s = vd_iou_gt(br, ar, sbox[p], sarea[p], P.overlap_thresh);
+                unsigned m = __ballot_sync(0xffffffffu, s);
+                if (lane == 0) smask[r * NW + w] = m;
+            }
+        }
+    }
+    __syncthreads();
+
+    VD_STAMP(P, 7);
+    // ---- 5. greedy scan (warp 0): lane l owns removed-bits of ranks 32l .. 32l+31
+    if (warp == 0) {
+        uint32_t removed = 0u;
+        int kept_total = 0;
+        for (int w = 0; w < NW; ++w) {
+            const int base = w << 5;
+            uint32_t cur = __shfl_sync(0xffffffffu, removed, w);
+            const int rr = base + lane;
+            uint32_t diag = (rr < n) ? smask[rr * NW + w] : 0u;
+            unsigned nz = __ballot_sync(0xffffffffu, diag != 0u);
+            while (nz) {                               // rows of this block that suppress inside it
+                int j = __ffs(nz) - 1; nz &= nz - 1;
+                uint32_t dj = __shfl_sync(0xffffffffu, diag, j);
+                if (!((cur >> j) & 1u)) cur |= dj;
+            }
+            uint32_t validbits = (n - base >= 32) ? 0xffffffffu : ((1u << (n - base)) - 1u);
+            uint32_t alive = ~cur & validbits;
+            if (lane == w) removed = cur;
+            if (lane == 0) { salive[w] = alive; sprefix[w] = (uint32_t)kept_total; }
+            kept_total += __popc(alive);
+            if (kept_total >= P.max_out) {             // later ranks cannot reach the output
+                for (int w2 = w + 1 + lane; w2 < NW; w2 += 32) { salive[w2] = 0u; sprefix[w2] = (uint32_t)kept_total; }
+                break;
+            }
+            // alive rows suppress later blocks: 32 independent (warp-uniformly predicated) row loads
+            if (lane > w && lane < NW) {
+                const uint32_t* mrow = smask + base * NW + lane;
+                uint32_t acc0 = 0u, acc1 = 0u;
+#pragma unroll
+                for (int j = 0; j < 32; j += 2) {
+                    if ((alive >> j) & 1u) acc0 |= mrow[j * NW];
+                    if ((alive >> (j + 1)) & 1u) acc1 |= mrow[(j + 1) * NW];
+                }
+                removed |= acc0 | acc1;
+            }
+        }
+        if (lane == 0) sprefix[63] = (uint32_t)kept_total;
+    }
+    __syncthreads();
+
+    VD_STAMP(P, 8);
+    // ---- 6. emit survivors
+    const int kept_total = (int)sprefix[63];
+    for (int r = tid; r < n; r += blockDim.x) {
+        uint32_t aw = salive[r >> 5];
+        if ((aw >> (r & 31)) & 1u) {
+            int pos = (int)sprefix[r >> 5] + __popc(aw & ((1u << (r & 31)) - 1u));
+            if (pos < P.max_out) sink.emit(b, pos, key_row(skeys[r]), key_score(skeys[r]), sbox[r], scls[r]);
+        }
+    }
+    sink.finish(b, kept_total < P.max_out ? kept_total : P.max_out);
+    VD_STAMP(P, 9);
+}
 // Source: gives box (corner), integer class and area for (image b, row).  Sink: writes output.
 template <class Source, class Sink>
 __device__ void nms_final_body(const uint64_t* __restrict__ lists, const uint32_t* __restrict__ counts,
@@ -137,103 +250,9 @@ __device__ void nms_final_body(const uint64_t* __restrict__ lists, const uint32_
     if (SN == (int)blockDim.x) bitonic_sort_reg<uint64_t, true>(skeys, SN);
     else bitonic_sort_desc(skeys, SN);                 // starts and ends with __syncthreads
     const int n = (int)(nsel < (uint32_t)k ? nsel : (uint32_t)k);
-
-    // ---- 3. per-rank box / class / area
-    for (int r = tid; r < n; r += blockDim.x) {
-        float4 bx; int c; float ar;
-        src.load(b, key_row(skeys[r]), key_score(skeys[r]), bx, c, ar);
-        sbox[r] = bx; scls[r] = c; sarea[r] = ar;
-    }
-    for (int i = tid; i < n * NW; i += blockDim.x) smask[i] = 0u;
-    __syncthreads();
-
-    // ---- 4. suppression matrix
-    if (P.class_aware) {
-        // secondary key (class bucket, rank): same-class ranks become contiguous, rank ascending
-        for (int i = tid; i < SN; i += blockDim.x)
-            skey2[i] = (i < n) ? (((uint32_t)scls[i] << 10) | (uint32_t)i) : 0xffffffffu;
-        __syncthreads();
-        if (SN == (int)blockDim.x) bitonic_sort_reg<uint32_t, false>(skey2, SN);
-        else bitonic_sort_u32_asc(skey2, SN);
-        // 4 threads per rank walk the rank's bucket tail with stride 4 (buckets are ~n/C long)
-        for (int i = tid >> 2; i < n; i += blockDim.x >> 2) {
-            uint32_t ki = skey2[i];
-            int r = (int)(ki & 1023u); uint32_t ci = ki >> 10;
-            float4 br = sbox[r]; float ar = sarea[r]; const int cr = scls[r];
-            for (int j = i + 1 + (tid & 3); j < n; j += 4) {
-                uint32_t kj = skey2[j];
-                if ((kj >> 10) != ci) break;
-                int p = (int)(kj & 1023u);             // p > r (rank ascending inside a bucket)
-                if (scls[p] != cr) continue;           // bucket = low 22 bits of the id; compare the full int
-                if (vd_iou_gt(br, ar, sbox[p], sarea[p], P.overlap_thresh))
-                    atomicOr(&smask[r * NW + (p >> 5)], 1u << (p & 31));
-            }
-        }
-    } else {
-        for (int r = warp; r < n; r += nwarps) {
-            float4 br = sbox[r]; float ar = sarea[r];
-            for (int w = r >> 5; w < NW; ++w) {
-                int p = (w << 5) + lane;
-                bool s = false;
-                if (p > r && p < n) s = vd_iou_gt(br, ar, sbox[p], sarea[p], P.overlap_thresh);
-                unsigned m = __ballot_sync(0xffffffffu, s);
-                if (lane == 0) smask[r * NW + w] = m;
-            }
-        }
-    }
-    __syncthreads();
-
-    // ---- 5. greedy scan (warp 0): lane l owns removed-bits of ranks 32l .. 32l+31
-    if (warp == 0) {
-        uint32_t removed = 0u;
-        int kept_total = 0;
-        for (int w = 0; w < NW; ++w) {
-            const int base = w << 5;
-            uint32_t cur = __shfl_sync(0xffffffffu, removed, w);
-            const int rr = base + lane;
-            uint32_t diag = (rr < n) ? smask[rr * NW + w] : 0u;
-            unsigned nz = __ballot_sync(0xffffffffu, diag != 0u);
-            while (nz) {                               // rows of this block that suppress inside it
-                int j = __ffs(nz) - 1; nz &= nz - 1;
-                uint32_t dj = __shfl_sync(0xffffffffu, diag, j);
-                if (!((cur >> j) & 1u)) cur |= dj;
-            }
-            uint32_t validbits = (n - base >= 32) ? 0xffffffffu : ((1u << (n - base)) - 1u);
-            uint32_t alive = ~cur & validbits;
-            if (lane == w) removed = cur;
-            if (lane == 0) { salive[w] = alive; sprefix[w] = (uint32_t)kept_total; }
-            kept_total += __popc(alive);
-            if (kept_total >= P.max_out) {             // later ranks cannot reach the output
-                for (int w2 = w + 1 + lane; w2 < NW; w2 += 32) { salive[w2] = 0u; sprefix[w2] = (uint32_t)kept_total; }
-                break;
-            }
-            // alive rows suppress later blocks: 32 independent (warp-uniformly predicated) row loads
-            if (lane > w && lane < NW) {
-                const uint32_t* mrow = smask + base * NW + lane;
-                uint32_t acc0 = 0u, acc1 = 0u;
-#pragma unroll
-                for (int j = 0; j < 32; j += 2) {
-                    if ((alive >> j) & 1u) acc0 |= mrow[j * NW];
-                    if ((alive >> (j + 1)) & 1u) acc1 |= mrow[(j + 1) * NW];
-                }
-                removed |= acc0 | acc1;
-            }
-        }
-        if (lane == 0) sprefix[63] = (uint32_t)kept_total;
-    }
-    __syncthreads();
-
-    // ---- 6. emit survivors
-    const int kept_total = (int)sprefix[63];
-    for (int r = tid; r < n; r += blockDim.x) {
-        uint32_t aw = salive[r >> 5];
-        if ((aw >> (r & 31)) & 1u) {
-            int pos = (int)sprefix[r >> 5] + __popc(aw & ((1u << (r & 31)) - 1u));
-            if (pos < P.max_out) sink.emit(b, pos, key_row(skeys[r]), key_score(skeys[r]), sbox[r], scls[r]);
-        }
-    }
-    sink.finish(b, kept_total < P.max_out ? kept_total : P.max_out);
+    nms_tail(n, b, P, src, sink, skeys, sbox, scls, sarea, smask, skey2, salive, sprefix);
 }
+
 
 // Intermediate level: merge <= 8 lists into one list holding a superset (<= kListCap) of their
 // joint top-k.  grid (n_groups, num_batch).

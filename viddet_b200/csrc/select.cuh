@@ -150,7 +150,17 @@ __device__ __forceinline__ float vd_intersect_1d(float a1, float a2, float b1, f
 __device__ __forceinline__ bool vd_iou_gt(float4 r, float area_r, float4 p, float area_p, float thresh) {
     float inter = __fmul_rn(vd_intersect_1d(r.x, r.z, p.x, p.z), vd_intersect_1d(r.y, r.w, p.y, p.w));
     if (inter == 0.0f && thresh >= 0.0f) return false;     // 0/u is 0, -0 or NaN: never > thresh >= 0
-    float iou = __fdiv_rn(inter, __fsub_rn(__fadd_rn(area_r, area_p), inter));
+    const float uni = __fsub_rn(__fadd_rn(area_r, area_p), inter);
+    // Decide without the IEEE division when inter is clearly on one side of thresh*union: for
+    // positive finite uni,  inter/uni > thresh  <=>  inter > thresh*uni  exactly in real arithmetic;
+    // the two fp32 roundings (product, quotient) can only matter within a few ulp of equality.
+    if (uni > 0.0f && thresh >= 0.0f && inter < 3.0e38f && uni < 3.0e38f) {
+        const float tu = __fmul_rn(thresh, uni);
+        const float margin = __fmul_rn(tu, 4.0e-7f) + 1.0e-37f;
+        if (inter > tu + margin) return true;
+        if (inter < tu - margin) return false;
+    }
+    float iou = __fdiv_rn(inter, uni);
     return iou > thresh;
 }
 

@@ -127,6 +127,48 @@ def test_sparse_scores_and_small_topk():
     assert (ids.cpu().numpy() == -1).any() or True
 
 
+@pytest.mark.parametrize("C,fill,bias_scale", [(20, 0.0, 0.2), (20, 0.0, 0.0), (80, 0.0, 0.3), (4, 1.0, 0.2), (20, 60.0, 0.0)])
+def test_fused_heavy_ties_bit_exact(C, fill, bias_scale):
+    """Constant feature maps: every pixel of a scale has the same logits, so scores tie in clusters of HW
+    (fill 60 saturates sigmoid to exactly 1.0).  The logit prefilter cannot separate ties; the exact 64-bit
+    (score, row) bisection must give MXNet's stable order (lower row first)."""
+    import viddet_b200
+    rng = np.random.RandomState(C)
+    size, B = 416, 2
+    tips = [np.full_like(t, fill) for t in make_tips(rng, B, size=size)]
+    ws, bs = make_pred_weights(rng, C, bias_scale=bias_scale)
+    head = build_head(C, ws, bs)
+    tt = [cuda(t) for t in tips]
+    for topk in (400, 37):
+        head.set_nms(nms_thresh=0.45, nms_topk=topk, post_nms=100)
+        det = head.detections(tt)
+        ids, scores, boxes, keep = head(tt, return_keep=True)
+        out, rec = viddet_b200.box_nms(det, overlap_thresh=0.45, valid_thresh=0.01, topk=topk, id_index=0, score_index=1,
+                                       coord_start=2, force_suppress=False, return_record=True)
+        assert torch.equal(keep, rec[:, :100])
+        assert torch.equal(scores.view(torch.int32), out[:, :100, 1:2].contiguous().view(torch.int32))
+
+
+@pytest.mark.parametrize("valid", [-1.0, 0.0, 0.2, 0.26, 0.9])
+def test_fused_valid_thresh_sweep_bit_exact(valid):
+    """valid_thresh <= 0 (everything but NaN valid), inside the score mass, and above every score."""
+    import viddet_b200
+    rng = np.random.RandomState(11)
+    C, B = 20, 2
+    tips = make_tips(rng, B, size=320)
+    ws, bs = make_pred_weights(rng, C, bias_scale=0.1)
+    head = build_head(C, ws, bs)
+    head.valid_thresh = valid
+    head.set_nms(nms_thresh=0.45, nms_topk=400, post_nms=100)
+    tt = [cuda(t) for t in tips]
+    det = head.detections(tt)
+    ids, scores, boxes, keep = head(tt, return_keep=True)
+    out, rec = viddet_b200.box_nms(det, overlap_thresh=0.45, valid_thresh=valid, topk=400, id_index=0, score_index=1,
+                                   coord_start=2, force_suppress=False, return_record=True)
+    assert torch.equal(keep, rec[:, :100])
+    assert torch.equal(scores.view(torch.int32), out[:, :100, 1:2].contiguous().view(torch.int32))
+
+
 def test_time_distributed_head_and_late_joins():
     import viddet_b200
     rng = np.random.RandomState(9)

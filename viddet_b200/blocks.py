@@ -500,28 +500,73 @@ class HeadSession:
         self._ws = torch.zeros(lib.vd_head_workspace_bytes(ctypes.byref(self.params)) + 256, dtype=torch.uint8, device=dev)
         self.launches = lib.vd_head_launch_count(ctypes.byref(self.params))
         self.graph = None
+        self._graphs = {}
 
     def run(self, stage_mask=_lib.VD_STAGE_ALL):
         check(load().vd_head_forward_stages(ctypes.byref(self.params), ptr(self.ids), ptr(self.scores), ptr(self.bboxes),
                                             ptr(self.keep), ptr(self._ws), self._ws.numel(), stream_ptr(), int(stage_mask)))
         return self.ids, self.scores, self.bboxes
 
-    def capture(self):
-        self.run()                                    # warm-up outside capture (function attributes, lazy init)
+    def capture(self, stage_mask=_lib.VD_STAGE_ALL):
+        """Record the call (or the stages in `stage_mask`) into a CUDA graph; `replay(stage_mask)` launches it."""
+        self.run(stage_mask)                          # warm-up outside capture (function attributes, lazy init)
         torch.cuda.synchronize()
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
-            self.run()
-        self.graph = g
+            self.run(stage_mask)
+        self._graphs[int(stage_mask)] = g
+        if stage_mask == _lib.VD_STAGE_ALL:
+            self.graph = g
         return self
 
-    def replay(self):
-        self.graph.replay()
+    def replay(self, stage_mask=_lib.VD_STAGE_ALL):
+        self._graphs[int(stage_mask)].replay()
         return self.ids, self.scores, self.bboxes
 
     def packed(self):
         """(frames, post_nms, 6) rows [id, score, x1, y1, x2, y2] -- the box_nms row layout."""
         return torch.cat([self.ids, self.scores, self.bboxes], dim=-1)
+
+
+class HeadPipeline:
+    """Throughput mode over a ring of HeadSessions (one per in-flight batch).
+
+    `step(j)` launches ONE CUDA graph that runs the fused head kernel (pred conv + decode + candidate
+    filter) of batch j concurrently with the per-frame top-k/NMS kernel of batch j-1: the NMS kernel is
+    a latency-bound chain on 64 CTAs, sized (256 threads, 56 registers, ~42 KB shared) to share SMs with
+    the HBM-bound head kernel of the next batch, whose dynamic tile scheduler absorbs the interference.
+    The detections of batch j are complete after `step(j+1)` (or `flush(j)`)."""
+
+    def __init__(self, sessions):
+        assert len(sessions) >= 2
+        self.sessions = list(sessions)
+        self._side = torch.cuda.Stream()
+        for s in self.sessions:                       # initialise workspaces (scheduler state, warm-start hints)
+            s.run()
+        torch.cuda.synchronize()
+        self._graphs = []
+        n = len(self.sessions)
+        for j in range(n):
+            cur, prev = self.sessions[j], self.sessions[(j - 1) % n]
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                main = torch.cuda.current_stream()
+                self._side.wait_stream(main)
+                with torch.cuda.stream(self._side):
+                    prev.run(_lib.VD_STAGE_NMS)
+                cur.run(_lib.VD_STAGE_HEAD)
+                main.wait_stream(self._side)
+            self._graphs.append(g)
+        self.launches_per_step = 2
+
+    def step(self, j):
+        self._graphs[j % len(self.sessions)].replay()
+
+    def flush(self, j):
+        """Finish batch j (its NMS stage) without starting another batch."""
+        s = self.sessions[j % len(self.sessions)]
+        s.run(_lib.VD_STAGE_NMS)
+        return s.ids, s.scores, s.bboxes
 
 
 # ------------------------------------------------------------------------------------------------

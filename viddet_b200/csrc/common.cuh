@@ -64,6 +64,7 @@ __host__ __device__ __forceinline__ float key_score(uint64_t k) { return unorder
 // relative error ~1e-6 for |x| < 20, far inside the 1e-5 parity bar against the fp32 oracle.
 __device__ __forceinline__ float vd_ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float vd_rcp(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float vd_lg2(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float vd_exp(float x) { return vd_ex2(__fmul_rn(x, 1.4426950408889634f)); }
 __device__ __forceinline__ float vd_sigmoid(float x) {
     return vd_rcp(__fadd_rn(1.0f, vd_ex2(__fmul_rn(x, -1.4426950408889634f))));

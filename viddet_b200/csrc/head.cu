@@ -23,6 +23,7 @@
 //        EPI_PRED    write the conv output (B, N, H, W) fp32
 // Tiles are ordered scale-major (s32 first: most bytes per tile) and dealt round-robin.
 #include <stdlib.h>
+#include <type_traits>
 #include "tc.cuh"
 #include "nms_core.cuh"
 
@@ -31,7 +32,7 @@ namespace vd {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;
 constexpr int UMMA_K = 16;
-constexpr int kMaxEpiGroups = 3;              // epilogue warpgroups G (2 or 3); group g owns TMEM buffer g (tiles it%G == g)
+constexpr int kMaxEpiGroups = 4;              // epilogue warpgroups G (2 or 3); group g owns TMEM buffer g (tiles it%G == g)
 constexpr int kEpiWarp0 = 2;                  // warp 0: TMA, warp 1: MMA, then 2 x 4 epilogue warps
 constexpr int kEpiThreads = 128;
 constexpr int A_TILE_BYTES = BLOCK_M * BLOCK_K * 2;
@@ -42,7 +43,7 @@ enum { EPI_FILTER = 0, EPI_DET = 1, EPI_PRED = 2 };
 // Monotone in the key, so "the highest bin b* whose suffix count reaches k" gives a frame-level
 // pivot with at most k + (population of b*) candidates above it -- no search in the NMS kernel.
 constexpr int kHistBins = 4096;
-constexpr int kHistCap = 2048;                // candidates the NMS kernel can hold after the pivot
+constexpr int kHistCap = 1024;                // candidates the NMS kernel can hold after the pivot
 __host__ __device__ __forceinline__ uint32_t hist_bin(uint32_t key_hi) {
     if (!(key_hi & 0x80000000u)) return 0u;                       // negative scores: lowest bin
     uint32_t b = (key_hi & 0x7fffffffu) >> 14;
@@ -69,6 +70,9 @@ struct HeadKernelParams {
     float4* boxes; uint64_t* lists; uint32_t* counts; float valid_thresh; int k, cap;
     unsigned long long* hints;           // [2*VD_MAX_SCALES][2] (pivot, band) warm starts, persist in the workspace across calls
     uint32_t* hist;                      // [frames][kHistBins] score histogram of the emitted candidates (zeroed per call)
+    unsigned int* tile_counter;          // [0] next tile, [1] finished CTAs, [2] kWsMagic once the workspace is initialised; null: static round-robin
+    long long* stamps;                   // profiling aid (VD_DEBUG_HEAD_STAMPS): clock64 per tile of CTA 0, [it][8]
+    int dbg;                             // profiling aid (VD_DEBUG_SKIP_EPILOGUE=level): stop the epilogue early, results are garbage
     // EPI_DET
     float* det; long long det_rows_total;
     // EPI_PRED
@@ -78,18 +82,26 @@ struct HeadKernelParams {
 struct HeadMaps { CUtensorMap a[VD_MAX_SCALES]; CUtensorMap w[VD_MAX_SCALES]; };
 
 template <int EPI, int C, int NPAD> struct HeadCfg {
-    static constexpr int NCH = (3 * C + 63) / 64;              // class chunks per tile: <= 64 score keys in registers
-    static constexpr int LIST_BUFS = (EPI == EPI_FILTER) ? (NCH > 1 ? 2 : 1) : 0;   // ping-pong only if the list can shrink
+    static constexpr int CPA = (C + 31) / 32;                  // TMEM read chunks per anchor (<= 32 class logits each)
+    static constexpr int CH = (C + CPA - 1) / CPA;
+    // small heads (VOC: 75 columns): the whole accumulator row lives in registers, TMEM is handed back right after one load
+    static constexpr bool REGS = false && (EPI == EPI_FILTER) && (3 * (5 + C) <= 80);   // (register-resident variant spills at 128 registers: off)
+    static constexpr int CH4 = (CH + 3) / 4 * 4;               // class-bias chunk padded for 128-bit shared loads
+    static constexpr int CBIAS_BYTES = (EPI == EPI_FILTER) ? VD_MAX_SCALES * 3 * CPA * CH4 * 4 : 0;
+    static constexpr int CONF_BYTES = (EPI == EPI_FILTER) ? kMaxEpiGroups * 3 * kEpiThreads * 4 : 0;
+    static constexpr int LIST_BUFS = (EPI == EPI_FILTER) ? 1 : 0;
     static constexpr int B_TILE_BYTES = NPAD * BLOCK_K * 2;
     static constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
     static constexpr int TMEM_STRIDE = NPAD <= 128 ? 128 : 256;
-    // 3 groups (12 epilogue warps, 128 registers/thread) when three accumulators fit TMEM and the
-    // per-thread key set is small enough; else 2 groups (168 registers/thread)
+    // 3 groups (12 epilogue warps, 128 registers/thread) when three accumulators fit TMEM; else 2 groups
     static constexpr int G = (EPI == EPI_FILTER && TMEM_STRIDE == 128) ? 3 : 2;
     static constexpr int THREADS = kEpiWarp0 * 32 + G * kEpiThreads;
+    static constexpr int MAXREG = (THREADS > 320) ? 96 : 128;
     static constexpr int LIST_BYTES = G * LIST_BUFS * kListCap * 8;
-    static constexpr int EPI_BYTES = LIST_BYTES + VD_MAX_SCALES * NPAD * 4 + 1024;
-    static constexpr int STAGES_RAW = (225 * 1024 - EPI_BYTES - 1024) / STAGE_BYTES;
+    static constexpr int EPI_BYTES = LIST_BYTES + CBIAS_BYTES + CONF_BYTES + VD_MAX_SCALES * NPAD * 4 + 1024;
+    // EPI_FILTER leaves ~45 KB of the SM's shared memory to a co-resident nms_final_hist_kernel CTA of the previous batch
+    static constexpr int SMEM_BUDGET = (EPI == EPI_FILTER ? 181 : 225) * 1024;
+    static constexpr int STAGES_RAW = (SMEM_BUDGET - EPI_BYTES - 1024) / STAGE_BYTES;
     static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
     static constexpr int TMEM_COLS = (G * TMEM_STRIDE) <= 256 ? 256 : 512;
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 1024;   // +1024 alignment slack
@@ -103,13 +115,26 @@ struct EpiGroupShared {
     uint64_t guess[2 * VD_MAX_SCALES];     // warm-start pivot per (scale, full / partial pixel block)
     uint64_t band[2 * VD_MAX_SCALES];      // running estimate of the accept band's key width
 };
+constexpr unsigned int kWsMagic = 0x56444231u; // 'VDB1': the workspace's counters / histogram are in their between-calls state
+constexpr int kSchedSlots = 8;               // tile-id ring between the producer (which claims tiles) and the MMA / epilogue roles
 struct HeadShared {
     uint64_t full[8], empty[8], tmem_full[kMaxEpiGroups], tmem_empty[kMaxEpiGroups];
+    uint64_t sched_full[kSchedSlots], sched_empty[kSchedSlots];
+    int sched_tile[kSchedSlots];
     uint32_t tmem_base, pad_;
     EpiGroupShared grp[kMaxEpiGroups];
 };
 
-__device__ __forceinline__ void epi_bar(int grp) { asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "n"(kEpiThreads) : "memory"); }
+// named barrier 1 + grp, immediate ids: a register id makes ptxas reserve all 16 hardware barriers for the CTA,
+// which would keep any other kernel's CTA (the co-scheduled NMS kernel) off the SM
+__device__ __forceinline__ void epi_bar(int grp) {
+    switch (grp) {
+        case 0: asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory"); break;
+        case 1: asm volatile("bar.sync 2, %0;" ::"n"(kEpiThreads) : "memory"); break;
+        case 2: asm volatile("bar.sync 3, %0;" ::"n"(kEpiThreads) : "memory"); break;
+        default: asm volatile("bar.sync 4, %0;" ::"n"(kEpiThreads) : "memory"); break;
+    }
+}
 
 // block_sum over the 128 threads of one epilogue group (named barrier 1+grp), see select.cuh::block_sum
 __device__ __forceinline__ uint32_t epi_sum(uint32_t v, EpiGroupShared* s, int grp, int et, int& it) {
@@ -133,8 +158,10 @@ __device__ __forceinline__ void tile_coords(const HeadKernelParams& p, int tile,
     pblk = local - f * p.pb[s];
 }
 
+// Register cap: the register file is split per SM sub-partition (16K registers = 512 per lane); 4 head warps x 96 + 2 NMS
+// warps x 56 = 496 lets a CTA of the co-scheduled NMS kernel share each sub-partition (3 x 128 + 112 for the 10-warp configs).
 template <int EPI, int C, int NPAD>
-__global__ void __launch_bounds__((HeadCfg<EPI, C, NPAD>::THREADS), 1)
+__global__ void __maxnreg__((HeadCfg<EPI, C, NPAD>::MAXREG))
 head_kernel(const __grid_constant__ HeadMaps maps, const __grid_constant__ HeadKernelParams p) {
     using Cfg = HeadCfg<EPI, C, NPAD>;
     constexpr int P = 5 + C;
@@ -145,19 +172,37 @@ head_kernel(const __grid_constant__ HeadMaps maps, const __grid_constant__ HeadK
     unsigned char* smem = smem_dyn + ((1024u - (tc::smem_u32(smem_dyn) & 1023u)) & 1023u);
     unsigned char* ring = smem;
     uint64_t* slist = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);     // [group][buf][kListCap]
-    float* sbias = reinterpret_cast<float*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES + Cfg::LIST_BYTES);   // [3][NPAD]
+    float* scbias = reinterpret_cast<float*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES + Cfg::LIST_BYTES);  // [3 scales][3 anchors][CPA][CH4] class biases, 16-byte aligned chunks
+    float* sconf = scbias + Cfg::CBIAS_BYTES / 4;                                                       // [group][128 px][3] objectness of the tile being filtered
+    float* sbias = sconf + Cfg::CONF_BYTES / 4;                                                         // [3][NPAD]
+    (void)scbias; (void)sconf;
     HeadShared* sh = reinterpret_cast<HeadShared*>(sbias + VD_MAX_SCALES * NPAD);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    auto gtime = []() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return (long long)t; };
+    if (EPI == EPI_FILTER && p.stamps && threadIdx.x == 0) {
+        p.stamps[4096 + blockIdx.x * 4 + 0] = gtime();
+        unsigned int sm; asm volatile("mov.u32 %0, %%smid;" : "=r"(sm)); p.stamps[4096 + blockIdx.x * 4 + 3] = (long long)sm;
+    }
 
     // ---------------- one-time setup
     for (int i = threadIdx.x; i < VD_MAX_SCALES * NPAD; i += Cfg::THREADS) {
         int s = i / NPAD, n = i % NPAD;
         sbias[i] = (s < p.g.num_scales && p.bias[s] && n < p.n_valid) ? p.bias[s][n] : 0.0f;
     }
+    if constexpr (EPI == EPI_FILTER) {
+        constexpr int P = 5 + C;
+        for (int i = threadIdx.x; i < VD_MAX_SCALES * 3 * Cfg::CPA * Cfg::CH4; i += Cfg::THREADS) {
+            const int s = i / (3 * Cfg::CPA * Cfg::CH4), r = i % (3 * Cfg::CPA * Cfg::CH4);
+            const int a = r / (Cfg::CPA * Cfg::CH4), cc = (r / Cfg::CH4) % Cfg::CPA, ci = r % Cfg::CH4;
+            const int c = cc * Cfg::CH + ci;
+            scbias[i] = (s < p.g.num_scales && p.bias[s] && ci < Cfg::CH && c < C) ? p.bias[s][a * P + 5 + c] : 0.0f;
+        }
+    }
     if (threadIdx.x == 0) {
         for (int i = 0; i < Cfg::STAGES; ++i) { tc::mbar_init(&sh->full[i], 1); tc::mbar_init(&sh->empty[i], 1); }
         for (int i = 0; i < G; ++i) { tc::mbar_init(&sh->tmem_full[i], 1); tc::mbar_init(&sh->tmem_empty[i], 4); }
+        for (int i = 0; i < kSchedSlots; ++i) { tc::mbar_init(&sh->sched_full[i], 1); tc::mbar_init(&sh->sched_empty[i], 5); }   // consumers: MMA thread + 4 epilogue warps
         for (int g = 0; g < G; ++g) {
             sh->grp[g].cnt[0] = sh->grp[g].cnt[1] = sh->grp[g].cnt[2] = 0; sh->grp[g].cursor = 0;
             for (int i = 0; i < 2 * VD_MAX_SCALES; ++i) {
@@ -176,6 +221,7 @@ head_kernel(const __grid_constant__ HeadMaps maps, const __grid_constant__ HeadK
     __syncthreads();
     tc::fence_after_sync();
     const uint32_t tmem_base = sh->tmem_base;
+    if (EPI == EPI_FILTER && p.stamps && threadIdx.x == 0) p.stamps[4096 + blockIdx.x * 4 + 1] = gtime();
 
     if (warp == 0) {
         // =========================== TMA producer ===========================
@@ -183,7 +229,21 @@ head_kernel(const __grid_constant__ HeadMaps maps, const __grid_constant__ HeadK
             int stage = 0; uint32_t phase = 0;
             const uint64_t pol_a = tc::policy_evict_first();    // activations are read exactly once
             const uint64_t pol_w = tc::policy_evict_last();     // weights are re-read by every tile
-            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+            // claims tiles (global counter: dynamic load balance, largest tiles first) and publishes them to the other roles
+            const bool dyn = p.tile_counter != nullptr && p.tile_counter[2] == kWsMagic;   // uninitialised workspace: static round-robin
+            auto claim = [&](uint32_t i) -> int {
+                const uint32_t t = dyn ? atomicAdd(p.tile_counter, 1u) : (uint32_t)blockIdx.x + i * gridDim.x;
+                return t < (uint32_t)p.total_tiles ? (int)t : -1;
+            };
+            int next = claim(0u), n_end = 0;
+            for (uint32_t it = 0;; ++it) {
+                const uint32_t slot = it % kSchedSlots;
+                tc::mbar_wait(&sh->sched_empty[slot], ((it / kSchedSlots) & 1u) ^ 1u);
+                const int tile = next;
+                if (tile >= 0) next = claim(it + 1u);               // in flight while this tile's loads are issued
+                sh->sched_tile[slot] = tile;
+                tc::mbar_arrive(&sh->sched_full[slot]);
+                if (tile < 0) { if (++n_end == G) break; continue; }   // one terminator per epilogue group
                 int s, f, pblk; tile_coords(p, tile, s, f, pblk);
                 const int kb_per_frame = p.cin[s] / BLOCK_K;
                 const int nkb = kb_per_frame * p.K_frames;
@@ -205,12 +265,19 @@ head_kernel(const __grid_constant__ HeadMaps maps, const __grid_constant__ HeadK
         if (tc::elect_one()) {
             constexpr uint32_t idesc = tc::make_idesc_bf16(BLOCK_M, NPAD);
             int stage = 0; uint32_t phase = 0; uint32_t it = 0;
-            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+            for (;; ++it) {
+                const uint32_t slot = it % kSchedSlots;
+                tc::mbar_wait(&sh->sched_full[slot], (it / kSchedSlots) & 1u);
+                const int tile = sh->sched_tile[slot];
+                tc::mbar_arrive(&sh->sched_empty[slot]);
+                if (tile < 0) break;
                 int s, f, pblk; tile_coords(p, tile, s, f, pblk);
                 const int nkb = (p.cin[s] / BLOCK_K) * p.K_frames;
                 const uint32_t buf = it % (uint32_t)G;
+                if (p.stamps && blockIdx.x == 0 && it < 250u) p.stamps[it * 16 + 0] = clock64();
                 tc::mbar_wait(&sh->tmem_empty[buf], ((it / (uint32_t)G) & 1u) ^ 1u);
                 tc::fence_after_sync();
+                if (p.stamps && blockIdx.x == 0 && it < 250u) p.stamps[it * 16 + 1] = clock64();
                 const uint32_t d_tmem = tmem_base + buf * Cfg::TMEM_STRIDE;
                 for (int kb = 0; kb < nkb; ++kb) {
                     tc::mbar_wait(&sh->full[stage], phase);
@@ -225,6 +292,7 @@ head_kernel(const __grid_constant__ HeadMaps maps, const __grid_constant__ HeadK
                     if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
                 }
                 tc::umma_commit(&sh->tmem_full[buf]);
+                if (p.stamps && blockIdx.x == 0 && it < 250u) p.stamps[it * 16 + 2] = clock64();
             }
         }
     } else if (warp >= kEpiWarp0) {
@@ -238,7 +306,13 @@ head_kernel(const __grid_constant__ HeadMaps maps, const __grid_constant__ HeadK
         int sum_it = 0;
         (void)gs; (void)L; (void)sum_it; (void)et;
         uint32_t it = (uint32_t)grp;
-        for (int tile = blockIdx.x + grp * gridDim.x; tile < p.total_tiles; tile += G * gridDim.x, it += G) {
+        for (;; it += G) {
+            const uint32_t slot = it % kSchedSlots;
+            tc::mbar_wait(&sh->sched_full[slot], (it / kSchedSlots) & 1u);
+            const int tile = sh->sched_tile[slot];
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(&sh->sched_empty[slot]);
+            if (tile < 0) break;
             int s, f, pblk; tile_coords(p, tile, s, f, pblk);
             const uint32_t buf = (uint32_t)grp;
             const int HW = p.g.HW[s], Wd = p.g.W[s];
@@ -246,12 +320,15 @@ head_kernel(const __grid_constant__ HeadMaps maps, const __grid_constant__ HeadK
             const bool inb = cell < HW;
             const float gx = (float)(cell % Wd), gy = (float)(cell / Wd);
             const float* bias = sbias + s * NPAD;
+            const bool stamp = (EPI == EPI_FILTER) && p.stamps && blockIdx.x == 0 && et == 0 && it < 250u;
+            if (stamp) p.stamps[it * 16 + 3] = clock64();
             tc::mbar_wait(&sh->tmem_full[buf], (it / (uint32_t)G) & 1u);
             tc::fence_after_sync();
+            if (stamp) p.stamps[it * 16 + 4] = clock64();
             const uint32_t tbase = tmem_base + buf * Cfg::TMEM_STRIDE + lane_addr;
 
             if constexpr (EPI == EPI_FILTER) {
-                if (p.k <= 0) {          // debug (VD_DEBUG_SKIP_EPILOGUE): mainloop only, accumulators dropped
+                if (p.dbg == 1) {        // debug (VD_DEBUG_SKIP_EPILOGUE=1): mainloop only, accumulators dropped
                     tc::fence_before_sync();
                     __syncwarp();
                     if (lane == 0) tc::mbar_arrive(&sh->tmem_empty[buf]);
@@ -278,10 +355,26 @@ head_kernel(const __grid_constant__ HeadMaps maps, const __grid_constant__ HeadK
 
             // ---- per-anchor box + objectness (yolo3.py:172-177)
             float conf[3];
+            constexpr int NACC = Cfg::REGS ? 3 * P : 1;
+            uint32_t acc[NACC];                                   // REGS: the pixel's whole accumulator row
+            uint32_t rb[3][5];
+            if constexpr (Cfg::REGS) {
+                tc::tmem_ld<3 * P>(tbase, acc); tc::tmem_ld_wait();
+                tc::fence_before_sync();                           // accumulator copied out: hand TMEM back at once
+                __syncwarp();
+                if (lane == 0) tc::mbar_arrive(&sh->tmem_empty[buf]);
+#pragma unroll
+                for (int a = 0; a < 3; ++a)
+#pragma unroll
+                    for (int i = 0; i < 5; ++i) rb[a][i] = acc[a * P + i];
+            } else {
+#pragma unroll
+                for (int a = 0; a < 3; ++a) tc::tmem_ld<5>(tbase + a * P, rb[a]);
+                tc::tmem_ld_wait();
+            }
 #pragma unroll
             for (int a = 0; a < 3; ++a) {
-                uint32_t r[5];
-                tc::tmem_ld<5>(tbase + a * P, r); tc::tmem_ld_wait();
+                const uint32_t* r = rb[a];
                 float tx = __uint_as_float(r[0]) + bias[a * P + 0], ty = __uint_as_float(r[1]) + bias[a * P + 1];
                 float tw = __uint_as_float(r[2]) + bias[a * P + 2], th = __uint_as_float(r[3]) + bias[a * P + 3];
                 float to = __uint_as_float(r[4]) + bias[a * P + 4];
@@ -323,211 +416,290 @@ head_kernel(const __grid_constant__ HeadMaps maps, const __grid_constant__ HeadK
             }
 
             if constexpr (EPI == EPI_FILTER) {
-                // ---- class scores -> 32-bit orderable keys in registers; streaming exact selection of the
-                //      tile's top-k: find a pivot tau with k <= #{key >= tau} <= cap, keep those keys.
-                constexpr int NCH = Cfg::NCH;
-                constexpr int CCH = (C + NCH - 1) / NCH;
+                // ---- exact selection of the tile's top-k WITHOUT scoring every candidate.
+                // score = sigmoid(x)*conf is monotone in the class logit x, so "score >= t" <=> "x >= logit(t/conf)":
+                // one threshold per (pixel, anchor) turns each probe of the pivot search into a compare on the raw
+                // accumulator.  The threshold is made conservative by 2^-15 relative in score space (>> the ~5e-6
+                // error of the approx ex2/rcp/lg2 chain), so the prefilter set P(t) contains every candidate whose
+                // COMPUTED score is >= t.  Only members of P (3-5 per thread) are scored; the tile's list is
+                // accepted when  k <= #{computed score >= t}  and  |P| <= cap  => list is a superset of the tile's
+                // exact top-k.  Heavily tied scores (fast probes cannot separate) fall back to an exact bisection
+                // on the 64-bit (score,row) keys, which scores every candidate per probe (rare).
+                //   sweep 1  count |P| (compare only)            -> block sum -> accept / move the threshold
+                //   sweep 2  stage P's (logit, local code) at exact list positions (predicated stores)
+                //   score    the staged entries, 128 threads striding the list (balanced), keys kept in registers
+                //   flush    keys -> global tile list (true row restored) + per-frame score histogram
+                if (p.dbg == 2) { if constexpr (!Cfg::REGS) { tc::fence_before_sync(); __syncwarp(); if (lane == 0) tc::mbar_arrive(&sh->tmem_empty[buf]); } continue; }
                 const uint32_t k = (uint32_t)p.k, cap = (uint32_t)p.cap;
-                // Low key word inside the tile = ~local, local = (class << 9) | (pixel-in-tile << 2) | anchor: it
-                // orders candidates exactly like ~row does (row = base + c*HW*3 + cell*3 + a) and costs one
-                // IADD-immediate per candidate; the true row is restored when the list is flushed.
                 const uint32_t cellofs = (uint32_t)(q * 32 + lane);
-                const uint64_t tau0 = 1ull << 32;                   // (score key 1, any row): below every valid key
-                // warm start: tiles of the same scale and fill (full / partial pixel block) have similar score
-                // distributions, so the previous such tile's pivot is accepted in ~1 probe
+                const uint32_t lcode = cellofs << 2;                // local code of (class c, anchor a) = lcode | (c << 9) | a; key low word = ~code
                 const int slot = 2 * s + ((pblk + 1) * BLOCK_M > HW ? 1 : 0);
-                uint64_t tau_guess = gs->guess[slot];
-                uint64_t band_w = gs->band[slot];
-                uint64_t tau = tau0;                                // every valid candidate seen so far with key >= tau is in the list
-                uint32_t list_n = 0, t_acc = 0; int cur = 0;
-#pragma unroll 1
-                for (int ch = 0; ch < NCH; ++ch) {
-                    uint32_t sk[3][CCH];
-                    const bool last_short = (ch == NCH - 1) && (C - (NCH - 1) * CCH < CCH);
+                const float vth = p.valid_thresh;
+                const uint32_t floor_b = vth > 0.0f ? __float_as_uint(vth) : 0u;   // lowest threshold (float bits); 0: everything
+                constexpr uint32_t kTop = 0x3f800001u;              // > 1.0: nothing scores above it
+                constexpr int CH = Cfg::CH, CPA = Cfg::CPA, CH4 = Cfg::CH4, REM = C - (CPA - 1) * CH, NCHUNK = 3 * CPA;
+                const float* cbias = scbias + s * (3 * CPA * CH4);
+                float* cf = sconf + grp * (3 * kEpiThreads);
+#pragma unroll
+                for (int a = 0; a < 3; ++a) cf[cellofs * 3 + a] = conf[a];   // visible to the group after the first block sum
+                float ell[3];
+                auto set_fast = [&](uint32_t tb) {
+                    const float t = __fmul_rn(__uint_as_float(tb), 0.999969482421875f);   // 1 - 2^-15
 #pragma unroll
                     for (int a = 0; a < 3; ++a) {
-                        uint32_t r[CCH];
-                        const int col0 = a * P + 5 + ch * CCH;
-                        if (!last_short) { tc::tmem_ld<CCH>(tbase + col0, r); }
-                        else {              // last chunk is shorter: read exactly the remaining classes
-                            constexpr int REM = (C - (NCH - 1) * CCH) > 0 ? (C - (NCH - 1) * CCH) : 1;
-                            tc::tmem_ld<REM>(tbase + col0, r);
-#pragma unroll
-                            for (int i = REM; i < CCH; ++i) r[i] = 0u;
-                        }
-                        tc::tmem_ld_wait();
-#pragma unroll
-                        for (int i = 0; i < CCH; ++i) {
-                            const int c = ch * CCH + i;
-                            uint32_t key = 0u;
-                            if (c < C) {
-                                // score = sigmoid(cls)*sigmoid(obj) >= +0 (or NaN): orderable key = bits | sign bit
-                                float sc = vd_score(__uint_as_float(r[i]) + bias[a * P + 5 + c], conf[a]);
-                                key = (sc > p.valid_thresh) ? (__float_as_uint(sc) | 0x80000000u) : 0u;   // strict; NaN (incl. padding pixels) invalid
-                            }
-                            sk[a][i] = key;
-                        }
+                        const float r = __fmul_rn(t, vd_rcp(conf[a]));
+                        const float l = __fmul_rn(__fsub_rn(vd_lg2(r), vd_lg2(__fsub_rn(1.0f, r))), 0.6931471805599453f);
+                        float e = (r < 1.0f) ? l : __uint_as_float(0x7f800000u);          // r >= 1 or NaN: nothing passes
+                        if (tb == 0u) e = __uint_as_float(0xff800000u);                   // no positive threshold: everything passes
+                        if (!(conf[a] == conf[a])) e = __uint_as_float(0x7f800000u);      // padding pixel
+                        ell[a] = e;
                     }
-                    if (ch == NCH - 1) {                            // accumulator fully consumed: hand TMEM back
-                        tc::fence_before_sync();
-                        __syncwarp();
-                        if (lane == 0) tc::mbar_arrive(&sh->tmem_empty[buf]);
-                    }
-                    // candidate (a,i) of this chunk >= pivot (ph,pl)?  pl == 0: pure score compare (fast path)
-                    const uint32_t nt = ~((((uint32_t)(ch * CCH)) << 9) | (cellofs << 2));
-                    auto nrow_of = [&](int a, int i) -> uint32_t { return nt - (((uint32_t)i << 9) | (uint32_t)a); };
-                    uint32_t my_cnt = 0;                            // this thread's chunk count at the last probed pivot
-                    auto count_ge = [&](uint64_t piv) -> uint32_t {
-                        const uint32_t ph = (uint32_t)(piv >> 32), pl = (uint32_t)piv;
-                        uint32_t c = 0;
-                        if (pl == 0u) {
-                            uint32_t c6[6] = {0u, 0u, 0u, 0u, 0u, 0u};     // independent chains (ILP)
+                };
+                auto issue = [&](const int j, uint32_t* r) {
+                    const int a = j / CPA, cc = j - a * CPA;
+                    const uint32_t col = tbase + (uint32_t)(a * P + 5 + cc * CH);
+                    if (REM != CH && cc == CPA - 1) tc::tmem_ld<REM>(col, r); else tc::tmem_ld<CH>(col, r);
+                };
+                // fast sweep over the class logits in TMEM (next chunk's load in flight while this one is compared):
+                // STAGE = false: returns |P_thread|;  STAGE = true: stores P_thread's (logit, code) entries at wp
+                auto sweep_fast = [&](auto stage_tag, uint64_t* wp) -> uint32_t {
+                    constexpr bool STAGE = decltype(stage_tag)::value;
+                    uint32_t cnt = 0u, cnt2 = 0u;
+                    uint32_t r[2][Cfg::REGS ? 1 : CH];
+                    if constexpr (!Cfg::REGS) issue(0, r[0]);
 #pragma unroll
-                            for (int a = 0; a < 3; ++a)
+                    for (int j = 0; j < NCHUNK; ++j) {
+                        const int a = j / CPA, cc = j - a * CPA;
+                        const int n = (REM != CH && cc == CPA - 1) ? REM : CH;
+                        float bv[CH4];
 #pragma unroll
-                                for (int i = 0; i < CCH; ++i) c6[2 * a + (i & 1)] += (sk[a][i] >= ph) ? 1u : 0u;
-                            c = (c6[0] + c6[1]) + (c6[2] + c6[3]) + (c6[4] + c6[5]);
-                        } else {
+                        for (int i = 0; i < CH4; i += 4)
+                            *reinterpret_cast<float4*>(bv + i) = *reinterpret_cast<const float4*>(cbias + (a * CPA + cc) * CH4 + i);
+                        if constexpr (!Cfg::REGS) {
+                            tc::tmem_ld_wait();
+                            if (j + 1 < NCHUNK) issue(j + 1, r[(j + 1) & 1]);
+                        }
+                        const float la = ell[a];
 #pragma unroll
-                            for (int a = 0; a < 3; ++a)
-#pragma unroll
-                                for (int i = 0; i < CCH; ++i) {
-                                    uint32_t sv = sk[a][i];
-                                    c += (sv > ph || (sv == ph && nrow_of(a, i) >= pl)) ? 1u : 0u;
+                        for (int i = 0; i < CH; ++i) {
+                            if (i < n) {
+                                uint32_t raw;
+                                if constexpr (Cfg::REGS) raw = acc[a * P + 5 + cc * CH + i]; else raw = r[j & 1][i];
+                                const float x = __fadd_rn(__uint_as_float(raw), bv[i]);
+                                const bool pass = x >= la;
+                                if constexpr (!STAGE) {
+                                    if (i & 1) cnt2 += pass ? 1u : 0u; else cnt += pass ? 1u : 0u;
+                                } else {
+                                    const uint32_t code = lcode | (((uint32_t)(cc * CH + i)) << 9) | (uint32_t)a;
+                                    if (pass) *wp = ((uint64_t)__float_as_uint(x) << 32) | code;
+                                    wp += pass ? 1 : 0;
                                 }
+                            }
                         }
-                        my_cnt = c;
-                        for (uint32_t j = et; j < list_n; j += kEpiThreads) c += (L[cur * kListCap + j] >= piv) ? 1u : 0u;
-                        return epi_sum(c, gs, grp, et, sum_it);
-                    };
-                    // ---- find ntau >= tau with  k <= count(>= ntau) <= cap   (or keep tau if everything fits).
-                    //      One loop, one count_ge call site (the unrolled compare block is large: keeping a
-                    //      single copy keeps the epilogue inside the instruction cache): probe the warm start,
-                    //      gallop until bracketed, then bisect.
-                    uint64_t ntau = tau;
-                    {
-                        uint64_t piv = tau_guess > tau ? tau_guess : tau;
-                        uint64_t lo = tau, hi = ~0ull, step = (tau_guess != 0ull) ? band_w : (1ull << 58);
-                        bool have_lo = false, have_hi = false;
+                    }
+                    return cnt + cnt2;
+                };
+                // exact sweep (rare): every candidate is scored; counts / writes the keys >= piv
+                auto sweep_exact = [&](auto emit_tag, uint64_t* wp, uint64_t* wend, const uint64_t piv) -> uint32_t {
+                    constexpr bool EMIT = decltype(emit_tag)::value;
+                    static_assert(2 * P + 5 + (C + 7) / 8 * 8 <= Cfg::TMEM_STRIDE, "class window leaves the TMEM buffer");
+                    uint32_t cnt = 0u;
+                    if constexpr (Cfg::REGS) {
+#pragma unroll
+                        for (int a = 0; a < 3; ++a) {
+#pragma unroll
+                            for (int c = 0; c < C; ++c) {
+                                const float sc = vd_score(__fadd_rn(__uint_as_float(acc[a * P + 5 + c]), bias[a * P + 5 + c]), conf[a]);
+                                const uint32_t kh = (sc > vth) ? (__float_as_uint(sc) | 0x80000000u) : 0u;
+                                const uint64_t key = ((uint64_t)kh << 32) | (uint32_t)~(lcode | (((uint32_t)c) << 9) | (uint32_t)a);
+                                if (kh && key >= piv) {
+                                    ++cnt;
+                                    if constexpr (EMIT) { if (wp < wend) *wp++ = key; }
+                                }
+                            }
+                        }
+                        return cnt;
+                    }
 #pragma unroll 1
-                        for (int g = 0; g < 160; ++g) {
-                            const uint32_t t = count_ge(piv);
-                            if ((t >= k && t <= cap) || (piv == tau && t <= cap) || g == 159) { ntau = piv; t_acc = t; break; }
-                            if (t > cap) { lo = piv; have_lo = true; } else { hi = piv; have_hi = true; }
-                            if (have_lo && have_hi) {                        // bisect; snap to pure-score pivots while possible
-                                if (hi - lo <= 1ull) { piv = lo; g = 158; continue; }   // unreachable for unique keys: superset fallback
-                                uint64_t mid = lo + ((hi - lo) >> 1);
-                                if (hi - lo > (2ull << 32)) { mid &= ~0xffffffffull; if (mid <= lo) mid += 1ull << 32; }
-                                else if (hi - lo < band_w) band_w = (hi - lo) | (1ull << 32);
-                                piv = mid;
-                            } else if (have_lo) {                            // gallop up
-                                uint64_t nm = piv + step; if (nm < piv) nm = ~0ull;
-                                nm &= ~0xffffffffull; if (nm <= piv) nm = ~0ull;
-                                piv = nm; step <<= 1; if (step == 0ull) step = 1ull << 63;
-                            } else {                                         // gallop down, never below tau
-                                uint64_t nm = (piv > step && piv - step > tau) ? ((piv - step) & ~0xffffffffull) : tau;
-                                if (nm <= tau) nm = tau;
-                                piv = nm; step <<= 1; if (step == 0ull) step = 1ull << 63;
+                    for (int a = 0; a < 3; ++a) {
+                        const float ca = cf[cellofs * 3 + a];
+#pragma unroll 1
+                        for (int c0 = 0; c0 < C; c0 += 8) {
+                            uint32_t rc[8];
+                            tc::tmem_ld8(tbase + (uint32_t)(a * P + 5 + c0), rc); tc::tmem_ld_wait();
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                const int c = c0 + i;
+                                if (c < C) {
+                                    const float sc = vd_score(__fadd_rn(__uint_as_float(rc[i]), bias[a * P + 5 + c]), ca);
+                                    const uint32_t kh = (sc > vth) ? (__float_as_uint(sc) | 0x80000000u) : 0u;
+                                    const uint64_t key = ((uint64_t)kh << 32) | (uint32_t)~(lcode | (((uint32_t)c) << 9) | (uint32_t)a);
+                                    if (kh && key >= piv) {
+                                        ++cnt;
+                                        if constexpr (EMIT) { if (wp < wend) *wp++ = key; }
+                                    }
+                                }
                             }
                         }
                     }
-                    // ---- rebuild the list for ntau: surviving old entries, then this chunk's entries
-                    {
-                        const bool shrink = (Cfg::LIST_BUFS > 1) && ntau > tau && list_n > 0;
-                        const int dst = shrink ? (cur ^ 1) : cur;
-                        if (shrink) {
-                            if (et == 0) gs->cursor = 0;
-                            epi_bar(grp);
-                            for (uint32_t j0 = 0; j0 < list_n; j0 += kEpiThreads) {
-                                uint32_t j = j0 + et;
-                                uint64_t v = (j < list_n) ? L[cur * kListCap + j] : 0ull;
-                                bool keep = v >= ntau && v != 0ull;
-                                unsigned m = __ballot_sync(0xffffffffu, keep);
-                                uint32_t base = 0;
-                                if (lane == 0 && m) base = atomicAdd(&gs->cursor, (uint32_t)__popc(m));
-                                base = __shfl_sync(0xffffffffu, base, 0);
-                                if (keep) L[dst * kListCap + base + __popc(m & ((1u << lane) - 1u))] = v;
-                            }
-                        } else if (list_n == 0) {
-                            if (et == 0) gs->cursor = 0;
-                            epi_bar(grp);
-                        }
-                        // chunk entries >= ntau; my_cnt is this thread's count at ntau (the last probed pivot)
-                        const uint32_t ph = (uint32_t)(ntau >> 32), pl = (uint32_t)ntau;
-                        const uint32_t mine = my_cnt;
-                        uint32_t incl = mine;
+                    return cnt;
+                };
+                // position of this thread's entries in the group's list: warp scan + one cursor bump per warp
+                auto list_base = [&](const uint32_t mine) -> uint32_t {
+                    uint32_t incl = mine;
 #pragma unroll
-                        for (int o = 1; o < 32; o <<= 1) { uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
-                        uint32_t tot = __shfl_sync(0xffffffffu, incl, 31);
-                        uint32_t base = 0;
-                        if (lane == 31 && tot) base = atomicAdd(&gs->cursor, tot);
-                        base = __shfl_sync(0xffffffffu, base, 31);
-                        uint64_t* wp = L + dst * kListCap + (base + incl - mine);
-                        if (mine) {
-                            if (pl == 0u) {
-                                // selection bitmask per anchor -> write slot = popc of the lower bits: no serial chain
-                                uint32_t m[3];
-#pragma unroll
-                                for (int a = 0; a < 3; ++a) {
-                                    uint32_t ma = 0u, mb = 0u;
-#pragma unroll
-                                    for (int i = 0; i < CCH; ++i) {
-                                        const uint32_t bit = (sk[a][i] >= ph) ? (1u << i) : 0u;
-                                        if (i & 1) mb |= bit; else ma |= bit;
-                                    }
-                                    m[a] = ma | mb;
-                                }
-                                const uint32_t off1 = __popc(m[0]), off2 = off1 + __popc(m[1]);
-#pragma unroll
-                                for (int a = 0; a < 3; ++a) {
-                                    const uint32_t offa = a == 0 ? 0u : (a == 1 ? off1 : off2);
-#pragma unroll
-                                    for (int i = 0; i < CCH; ++i) {
-                                        if ((m[a] >> i) & 1u)
-                                            wp[offa + __popc(m[a] & ((1u << i) - 1u))] = ((uint64_t)sk[a][i] << 32) | nrow_of(a, i);
-                                    }
-                                }
-                            } else {
-#pragma unroll
-                                for (int a = 0; a < 3; ++a)
-#pragma unroll
-                                    for (int i = 0; i < CCH; ++i) {
-                                        const uint32_t sv = sk[a][i];
-                                        const uint32_t nr = nrow_of(a, i);
-                                        if (sv > ph || (sv == ph && nr >= pl)) { *wp = ((uint64_t)sv << 32) | nr; ++wp; }
-                                    }
-                            }
-                        }
-                        epi_bar(grp);
-                        list_n = gs->cursor; if (list_n > (uint32_t)kListCap) list_n = kListCap;
-                        cur = dst; tau = ntau;
-                    }
-                }
-                // ---- flush the tile's candidate list; retarget the warm start towards the band centre
-                {
-                    const size_t li = (size_t)f * p.tiles_per_frame + p.tif_base[s] + pblk;
-                    uint64_t* gl = p.lists + li * kListCap;
-                    const uint32_t HW3 = (uint32_t)HW * 3u;
-                    const uint32_t rbase = (uint32_t)p.g.row_base[s] + (uint32_t)(pblk * BLOCK_M) * 3u;
-                    for (uint32_t j = et; j < list_n; j += kEpiThreads) {
-                        const uint64_t v = L[cur * kListCap + j];
+                    for (int o = 1; o < 32; o <<= 1) { uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+                    const uint32_t tot = __shfl_sync(0xffffffffu, incl, 31);
+                    uint32_t base = 0;
+                    if (lane == 31 && tot) base = atomicAdd(&gs->cursor, tot);
+                    base = __shfl_sync(0xffffffffu, base, 31);
+                    return base + incl - mine;
+                };
+                auto release_tmem = [&]() {
+                    if constexpr (Cfg::REGS) return;            // already handed back right after the load
+                    tc::fence_before_sync();
+                    __syncwarp();
+                    if (lane == 0) tc::mbar_arrive(&sh->tmem_empty[buf]);
+                };
+                // global tile list + histogram
+                const size_t li = (size_t)f * p.tiles_per_frame + p.tif_base[s] + pblk;
+                uint64_t* gl = p.lists + li * kListCap;
+                const uint32_t HW3 = (uint32_t)HW * 3u;
+                const uint32_t rbase = (uint32_t)p.g.row_base[s] + (uint32_t)(pblk * BLOCK_M) * 3u;
+                auto flush_one = [&](const uint32_t j, const uint64_t v) {     // v: (key_hi, ~local code) or 0
+                    uint64_t o = 0ull;
+                    if (v != 0ull) {
                         const uint32_t local = ~(uint32_t)v;
                         const uint32_t row = rbase + (local >> 9) * HW3 + ((local >> 2) & 127u) * 3u + (local & 3u);
-                        gl[j] = (v & 0xffffffff00000000ull) | (uint32_t)(~row);
-                        atomicAdd(&p.hist[(size_t)f * kHistBins + hist_bin((uint32_t)(v >> 32))], 1u);
+                        o = (v & 0xffffffff00000000ull) | (uint32_t)(~row);
+                        if (p.dbg != 5) atomicAdd(&p.hist[(size_t)f * kHistBins + hist_bin((uint32_t)(v >> 32))], 1u);
                     }
-                    if (et == 0) p.counts[li] = list_n;
-                    if (tau > tau0 && et == 0) {
-                        const uint32_t q4 = (cap - k) / 4u;
-                        const uint64_t nudge = band_w >> 3;
-                        uint64_t g2 = tau;
-                        if (t_acc < k + q4 && tau > tau0 + nudge) g2 = (tau - nudge) & ~0xffffffffull;
-                        else if (t_acc > cap - q4) g2 = (tau + nudge) & ~0xffffffffull;
+                    if (p.dbg != 6) gl[j] = o;
+                };
+
+                if (stamp) p.stamps[it * 16 + 8] = clock64();          // box decode done
+                uint32_t guess = (uint32_t)gs->guess[slot], band_w = (uint32_t)gs->band[slot];
+                if (band_w == 0u || band_w > (1u << 26)) band_w = 1u << 18;
+                uint32_t piv = guess;
+                if (piv < floor_b) piv = floor_b;
+                if (piv > kTop) piv = kTop;
+                uint32_t lo = floor_b, hi = kTop, step = band_w;
+                bool have_lo = false, have_hi = false, exact = false;
+                uint32_t list_n = 0, t_acc = 0, my_cnt = 0;
+                uint64_t piv64 = 0ull, lo64 = 0ull, hi64 = 0ull;
+                if (et == 0) gs->cursor = 0;                        // ordered before the first bump by the barrier inside epi_sum
+#pragma unroll 1
+                for (int g = 0; g < 200; ++g) {
+                    if (!exact) {
+                        set_fast(piv);
+                        if (stamp) p.stamps[it * 16 + 9] = clock64();      // thresholds set
+                        my_cnt = sweep_fast(std::false_type{}, nullptr);
+                        if (stamp) p.stamps[it * 16 + 10] = clock64();     // count sweep done
+                        const uint32_t t = epi_sum(my_cnt, gs, grp, et, sum_it);
+                        if (stamp) p.stamps[it * 16 + 5] = clock64();
+                        if (p.dbg == 3) { release_tmem(); break; }
+                        if (t <= cap && (t >= k || piv == floor_b)) {
+                            // ---- stage P(piv), score it, check the exact count
+                            const uint32_t ph = (piv == floor_b) ? 1u : (piv | 0x80000000u);
+                            const uint32_t lb0 = list_base(my_cnt);
+                            if (stamp) p.stamps[it * 16 + 11] = clock64(); // positions known
+                            sweep_fast(std::true_type{}, L + lb0);
+                            if (stamp) p.stamps[it * 16 + 12] = clock64(); // stage sweep done
+                            epi_bar(grp);                           // staging complete
+                            constexpr int KPT = kListCap / kEpiThreads;
+                            uint64_t key[KPT];
+                            uint32_t ne = 0u;
+#pragma unroll
+                            for (int u = 0; u < KPT; ++u) {
+                                const uint32_t j = (uint32_t)(u * kEpiThreads + et);
+                                key[u] = 0ull;
+                                if (j < t) {
+                                    const uint64_t e = L[j];
+                                    const uint32_t code = (uint32_t)e;
+                                    const float sc = vd_score(__uint_as_float((uint32_t)(e >> 32)), cf[((code >> 2) & 127u) * 3u + (code & 3u)]);
+                                    const uint32_t kh = (sc > vth) ? (__float_as_uint(sc) | 0x80000000u) : 0u;
+                                    key[u] = kh ? (((uint64_t)kh << 32) | (uint32_t)~code) : 0ull;
+                                    ne += (kh >= ph) ? 1u : 0u;
+                                }
+                            }
+                            if (stamp) p.stamps[it * 16 + 13] = clock64(); // scored
+                            const uint32_t t2 = epi_sum(ne, gs, grp, et, sum_it);
+                            if (p.dbg == 4) { release_tmem(); break; }
+                            if (t2 >= k || piv == floor_b) {
+                                release_tmem();
+                                if (stamp) p.stamps[it * 16 + 6] = clock64();
+#pragma unroll
+                                for (int u = 0; u < KPT; ++u) {
+                                    const uint32_t j = (uint32_t)(u * kEpiThreads + et);
+                                    if (j < t) flush_one(j, key[u]);
+                                }
+                                list_n = t; t_acc = t2;
+                                if (stamp) p.stamps[it * 16 + 14] = clock64(); // flushed
+                                break;
+                            }
+                            // margin ate the k-th candidates (tie cluster right at the threshold): exact search just below
+                            if (et == 0) gs->cursor = 0;
+                            exact = true;
+                            hi64 = (uint64_t)(piv | 0x80000000u) << 32;                       // count(hi64) = t2 < k
+                            const uint32_t lb = __float_as_uint(__fmul_rn(__uint_as_float(piv), 0.9998779296875f));   // 1 - 2^-13
+                            lo64 = (lb <= floor_b) ? 1ull : ((uint64_t)(lb | 0x80000000u) << 32);
+                            piv64 = lo64;
+                            continue;
+                        }
+                        if (t > cap) { lo = piv; have_lo = true; } else { hi = piv; have_hi = true; }
+                        if (have_lo && lo >= kTop) { have_hi = true; hi = kTop; }   // scores saturated at 1.0: exact keys decide
+                        if (have_lo && have_hi) {
+                            if (hi - lo <= 1024u) {                 // below the prefilter's resolution: exact keys decide
+                                exact = true;
+                                hi64 = (uint64_t)(hi | 0x80000000u) << 32;
+                                const uint32_t lb = __float_as_uint(__fmul_rn(__uint_as_float(lo), 0.9998779296875f));
+                                lo64 = (lo == floor_b || lb <= floor_b) ? 1ull : ((uint64_t)(lb | 0x80000000u) << 32);
+                                piv64 = lo64;
+                                continue;
+                            }
+                            if (hi - lo < band_w) band_w = (hi - lo) | 1024u;
+                            piv = lo + ((hi - lo) >> 1);
+                        } else if (have_lo) {                       // gallop up
+                            const uint64_t nm = (uint64_t)piv + step;
+                            piv = nm >= (uint64_t)kTop ? kTop : (uint32_t)nm;
+                            step = step < (1u << 30) ? step << 1 : step;
+                        } else {                                    // gallop down, never below the floor
+                            piv = (piv > floor_b && piv - floor_b > step) ? piv - step : floor_b;
+                            step = step < (1u << 30) ? step << 1 : step;
+                        }
+                    } else {
+                        my_cnt = sweep_exact(std::false_type{}, nullptr, nullptr, piv64);
+                        const uint32_t t = epi_sum(my_cnt, gs, grp, et, sum_it);
+                        const bool last = (hi64 - lo64 <= 1ull) || g >= 198;
+                        if ((t <= cap && (t >= k || piv64 == 1ull)) || last) {
+                            const uint32_t pos = list_base(my_cnt);
+                            const uint32_t pc = pos < (uint32_t)kListCap ? pos : (uint32_t)kListCap;
+                            sweep_exact(std::true_type{}, L + pc, L + kListCap, piv64);
+                            release_tmem();
+                            epi_bar(grp);                           // list complete
+                            list_n = t < (uint32_t)kListCap ? t : (uint32_t)kListCap; t_acc = t;
+                            for (uint32_t j = et; j < list_n; j += kEpiThreads) flush_one(j, L[j]);
+                            piv = (uint32_t)(piv64 >> 32) & 0x7fffffffu;
+                            break;
+                        }
+                        if (t > cap) lo64 = piv64; else hi64 = piv64;
+                        piv64 = lo64 + ((hi64 - lo64) >> 1);
+                    }
+                }
+                // ---- retarget the warm start towards the band centre
+                if (et == 0) {
+                    p.counts[li] = list_n;
+                    if (piv > floor_b) {
+                        const uint32_t q4 = (cap - k) / 4u, nudge = band_w >> 3;
+                        uint32_t g2 = piv;
+                        if (t_acc < k + q4 && piv > floor_b + nudge) g2 = piv - nudge;
+                        else if (list_n > cap - q4) g2 = piv + nudge;
                         gs->guess[slot] = g2; gs->band[slot] = band_w;
                         if (p.hints) { p.hints[2 * slot] = g2; p.hints[2 * slot + 1] = band_w; }   // racy by design: any value is only a hint
                     }
-                    epi_bar(grp);                                   // list buffers / guess slots are reused by the next tile
                 }
+                epi_bar(grp);                                       // list buffer / cursor / conf table / guess slots are reused by the next tile
+                if (stamp) p.stamps[it * 16 + 7] = clock64();
             }
         }
     }
@@ -535,7 +707,13 @@ head_kernel(const __grid_constant__ HeadMaps maps, const __grid_constant__ HeadK
     // ---------------- teardown
     tc::fence_before_sync();
     __syncthreads();
+    if (EPI == EPI_FILTER && p.stamps && threadIdx.x == 0) p.stamps[4096 + blockIdx.x * 4 + 2] = gtime();
     if (warp == 1) tc::tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+    if (threadIdx.x == 0 && p.tile_counter != nullptr && p.tile_counter[2] == kWsMagic) {
+        // last CTA out re-arms the scheduler for the next launch on this workspace
+        __threadfence();
+        if (atomicAdd(&p.tile_counter[1], 1u) == gridDim.x - 1u) { p.tile_counter[0] = 0u; p.tile_counter[1] = 0u; }
+    }
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -574,20 +752,16 @@ struct FusedSink {
     }
 };
 
-__global__ void __launch_bounds__(kFinalThreads, 1)
-nms_final_fused_kernel(const uint64_t* __restrict__ lists, const uint32_t* __restrict__ counts, int n_lists,
-                       NmsParams P, FusedSource src, FusedSink sink) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int f = blockIdx.x;
-    nms_final_body(lists + (size_t)f * n_lists * kListCap, counts + (size_t)f * n_lists, n_lists, f, P, src, sink, smem_raw);
-}
-
 // Per-frame top-k + NMS straight from the tile lists: the frame pivot comes from the score histogram
 // (suffix scan), the lists are streamed once and compacted, then sort + nms_tail.  No merge passes,
-// no pivot search (a streaming bisection remains as the fallback for pathologically tied scores).
-__global__ void __launch_bounds__(kFinalThreads, 1)
+// no pivot search (a streaming bisection remains as the fallback for pathologically tied scores or a
+// histogram that does not describe the lists).  Sized to share an SM with a head_kernel CTA of the
+// NEXT batch (256 threads, <= 64 registers, ~41 KB shared): the step pipeline overlaps the two.
+// The kernel leaves its frame's histogram zeroed for the next call (no memset node per call).
+constexpr int kNmsThreads = 256;
+__global__ void __maxnreg__(56)
 nms_final_hist_kernel(const uint64_t* __restrict__ lists, const uint32_t* __restrict__ counts, int n_lists,
-                      const uint32_t* __restrict__ hist, NmsParams P, FusedSource src, FusedSink sink) {
+                      uint32_t* __restrict__ hist, unsigned int* __restrict__ ctr, NmsParams P, FusedSource src, FusedSink sink) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
     const int k = P.k, NW = (k + 31) >> 5, SNk = P.sortn;
@@ -604,12 +778,27 @@ nms_final_hist_kernel(const uint64_t* __restrict__ lists, const uint32_t* __rest
     lists += (size_t)f * n_lists * kListCap; counts += (size_t)f * n_lists; hist += (size_t)f * kHistBins;
 
     VD_STAMP(P, 0);
+    if (P.dbg && tid == 0) {
+        unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        unsigned int sm; asm volatile("mov.u32 %0, %%smid;" : "=r"(sm));
+        P.dbg[8192 + f * 4 + 0] = (long long)t; P.dbg[8192 + f * 4 + 2] = (long long)sm;
+    }
     select_scratch_init(scr);
-    // ---- 1. suffix scan of the histogram; thread t owns bins [4095-8t-7, 4095-8t], highest first
-    constexpr int BPT = kHistBins / kFinalThreads;
+    // ---- 1. suffix scan of the histogram; thread t owns bins [4095-16t-15, 4095-16t], highest first.
+    //         The bins are zeroed behind the read: the next call's head kernel accumulates from zero.
+    constexpr int BPT = kHistBins / kNmsThreads;
     uint32_t h[BPT], local = 0u;
+    {
+        uint4* h4 = reinterpret_cast<uint4*>(hist + kHistBins - (tid + 1) * BPT);   // ascending bins of this thread's range
 #pragma unroll
-    for (int i = 0; i < BPT; ++i) { h[i] = hist[kHistBins - 1 - (tid * BPT + i)]; local += h[i]; }
+        for (int i = 0; i < BPT / 4; ++i) {
+            const uint4 v = h4[i];
+            h[BPT - 1 - 4 * i] = v.x; h[BPT - 2 - 4 * i] = v.y; h[BPT - 3 - 4 * i] = v.z; h[BPT - 4 - 4 * i] = v.w;
+            h4[i] = make_uint4(0u, 0u, 0u, 0u);
+        }
+#pragma unroll
+        for (int i = 0; i < BPT; ++i) local += h[i];
+    }
     uint32_t incl = local;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
@@ -630,7 +819,7 @@ nms_final_hist_kernel(const uint64_t* __restrict__ lists, const uint32_t* __rest
     }
     __syncthreads();
     VD_STAMP(P, 1);
-    const uint32_t bstar = sx[32];
+    uint32_t bstar = sx[32];
     uint32_t cnt = sx[33];
     uint64_t piv = (uint64_t)hist_edge(bstar) << 32;
 
@@ -642,53 +831,67 @@ nms_final_hist_kernel(const uint64_t* __restrict__ lists, const uint32_t* __rest
         }
         return block_sum(c, scr, it);
     };
-    if (cnt > (uint32_t)kHistCap) {            // rare: one bin holds a huge tie cluster -> bisect inside it
-        int it = 0;
-        uint64_t lo = piv, hi = (bstar + 1u < (uint32_t)kHistBins) ? ((uint64_t)hist_edge(bstar + 1u) << 32) : ~0ull;
-        for (int g = 0; g < 80 && hi - lo > 1ull; ++g) {
-            uint64_t mid = lo + ((hi - lo) >> 1);
-            uint32_t c = stream_count(mid, it);
-            if (c > (uint32_t)kHistCap) lo = mid; else if (c < (uint32_t)k) hi = mid; else { lo = mid; cnt = c; break; }
-        }
-        piv = lo;
-    }
-    // ---- 2. stream the tile lists once, keep keys >= pivot.  Work items = (list, 32-key chunk); each
-    //         warp issues 8 independent 8-byte loads per lane before consuming them (memory-level parallelism).
     uint32_t* scount = reinterpret_cast<uint32_t*>(sprefix + 64);     // [n_lists] clamped list lengths
     for (int l = tid; l < n_lists; l += blockDim.x) { uint32_t n = counts[l]; scount[l] = n > (uint32_t)kListCap ? (uint32_t)kListCap : n; }
-    __syncthreads();
-    for (int l = warp; l < n_lists; l += nwarps) {           // one list per warp pass, 16 loads in flight per lane
-        const uint32_t nl = scount[l];
-        const uint64_t* src_l = lists + (size_t)l * kListCap;
-        for (uint32_t b0 = 0; b0 < nl; b0 += 512u) {
-            uint64_t v[16];
+    int sit = 0;
+    uint32_t m = 0u;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        if (cnt > (uint32_t)kHistCap || attempt == 1) {
+            // rare: one bin holds a huge tie cluster, or (attempt 1) the histogram did not describe the lists
+            // (foreign workspace content): exact streaming bisection on the 64-bit keys
+            uint64_t lo = attempt == 1 ? 1ull : piv;
+            uint64_t hi = (attempt == 0 && bstar + 1u < (uint32_t)kHistBins) ? ((uint64_t)hist_edge(bstar + 1u) << 32) : ~0ull;
+            uint32_t c = stream_count(lo, sit);
+            if (c > (uint32_t)kHistCap) {
+                for (int g = 0; g < 80 && hi - lo > 1ull; ++g) {
+                    const uint64_t mid = lo + ((hi - lo) >> 1);
+                    c = stream_count(mid, sit);
+                    if (c > (uint32_t)kHistCap) lo = mid; else if (c < (uint32_t)k) hi = mid; else { lo = mid; break; }
+                }
+            }
+            piv = lo;
+        }
+        // ---- 2. stream the tile lists once, keep keys >= pivot; 8 independent 8-byte loads per lane in flight
+        __syncthreads();
+        if (tid == 0) scr->out_count = 0u;
+        __syncthreads();
+        for (int l = warp; l < n_lists; l += nwarps) {
+            const uint32_t nl = scount[l];
+            const uint64_t* src_l = lists + (size_t)l * kListCap;
+            for (uint32_t b0 = 0; b0 < nl; b0 += 256u) {
+                uint64_t v[8];
 #pragma unroll
-            for (int u = 0; u < 16; ++u) { const uint32_t j = b0 + (uint32_t)(u * 32 + lane); v[u] = (j < nl) ? src_l[j] : 0ull; }
+                for (int u = 0; u < 8; ++u) { const uint32_t j = b0 + (uint32_t)(u * 32 + lane); v[u] = (j < nl) ? src_l[j] : 0ull; }
 #pragma unroll
-            for (int u = 0; u < 16; ++u) {
-                const bool keep = v[u] >= piv && v[u] != 0ull;
-                const unsigned m = __ballot_sync(0xffffffffu, keep);
-                if (m) {
-                    uint32_t base = 0u;
-                    if (lane == 0) base = atomicAdd(&scr->out_count, (uint32_t)__popc(m));
-                    base = __shfl_sync(0xffffffffu, base, 0);
-                    const uint32_t pos = base + __popc(m & ((1u << lane) - 1u));
-                    if (keep && pos < (uint32_t)kHistCap) skeys[pos] = v[u];
+                for (int u = 0; u < 8; ++u) {
+                    const bool keep = v[u] >= piv && v[u] != 0ull;
+                    const unsigned mm = __ballot_sync(0xffffffffu, keep);
+                    if (mm) {
+                        uint32_t base = 0u;
+                        if (lane == 0) base = atomicAdd(&scr->out_count, (uint32_t)__popc(mm));
+                        base = __shfl_sync(0xffffffffu, base, 0);
+                        const uint32_t pos = base + __popc(mm & ((1u << lane) - 1u));
+                        if (keep && pos < (uint32_t)kHistCap) skeys[pos] = v[u];
+                    }
                 }
             }
         }
+        __syncthreads();
+        m = scr->out_count;
+        // a clean histogram guarantees m >= k whenever a positive pivot was chosen; otherwise redo exactly
+        if (m >= (uint32_t)k || piv <= 1ull || attempt == 1) break;
     }
-    __syncthreads();
     VD_STAMP(P, 2);
-    uint32_t m = scr->out_count; m = m > (uint32_t)kHistCap ? (uint32_t)kHistCap : m;
-    const int SN = m <= 512u ? 512 : (m <= 1024u ? 1024 : 2048);
+    m = m > (uint32_t)kHistCap ? (uint32_t)kHistCap : m;
+    const int SN = m <= 512u ? 512 : 1024;
     for (int i = (int)m + tid; i < SN; i += blockDim.x) skeys[i] = 0ull;
     __syncthreads();
-    if (SN == (int)blockDim.x) bitonic_sort_reg<uint64_t, true>(skeys, SN);
-    else bitonic_sort_desc(skeys, SN);
+    block_sort_u64_desc(skeys, SN);
     VD_STAMP(P, 3);
     const int n = (int)(m < (uint32_t)k ? m : (uint32_t)k);
     nms_tail(n, f, P, src, sink, skeys, sbox, scls, sarea, smask, skey2, salive, sprefix);
+    if (f == 0 && tid == 0) { ctr[0] = 0u; ctr[1] = 0u; ctr[2] = kWsMagic; }   // workspace is in its between-calls state
+    if (P.dbg && tid == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); P.dbg[8192 + f * 4 + 1] = (long long)t; }
 }
 static size_t nms_hist_smem(int k) {
     return 256 + (size_t)kHistCap * 8 + (size_t)k * 16 + (size_t)k * 8 + (size_t)k * nms_words(k) * 4 + (size_t)nms_sortn(k) * 4 + 512 + 64 + 1024;   // + per-list counts (<= 256 lists)
@@ -703,7 +906,7 @@ struct HeadPlan {
     HeadKernelParams kp;
     int n_pad, C;
     int merge_levels;
-    size_t off_hints, off_hist, off_boxes, off_lists0, off_counts0, off_listsA, off_listsB, off_countsA, off_countsB, total;
+    size_t off_hints, off_ctr, off_hist, off_boxes, off_lists0, off_counts0, off_listsA, off_listsB, off_countsA, off_countsB, total;
 };
 
 static int head_npad(int C) { int n = 3 * (5 + C); return (n + 15) / 16 * 16; }
@@ -741,12 +944,11 @@ static int make_plan(const VdHeadParams* hp, HeadPlan* pl) {
         k.pb[s] = ceil_div(k.g.HW[s], BLOCK_M);
         k.tif_base[s] = tif; tif += k.pb[s];
     }
-    // processing order: second-largest K first (short pipeline fill), then the largest, smallest tiles last (balance)
+    // processing order: largest K (most bytes per tile) first, smallest tiles last -- the dynamic scheduler's tail is one small tile
     int ord[VD_MAX_SCALES] = {0, 1, 2};
     for (int a = 0; a < hp->num_scales; ++a)
         for (int b = a + 1; b < hp->num_scales; ++b)
             if (k.cin[ord[b]] > k.cin[ord[a]]) { int t = ord[a]; ord[a] = ord[b]; ord[b] = t; }
-    if (hp->num_scales >= 2) { int t = ord[0]; ord[0] = ord[1]; ord[1] = t; }
     int tiles = 0;
     for (int j = 0; j < hp->num_scales; ++j) { k.order[j] = ord[j]; k.tile_start[j] = tiles; tiles += k.pb[ord[j]] * hp->frames; }
     for (int j = hp->num_scales; j < VD_MAX_SCALES; ++j) k.order[j] = 0;
@@ -757,6 +959,7 @@ static int make_plan(const VdHeadParams* hp, HeadPlan* pl) {
     size_t off = 0;
     const size_t F = (size_t)(hp->frames > 0 ? hp->frames : 1);
     pl->off_hints = off; off += 256;
+    pl->off_ctr = off; off += 256;                      // dynamic tile counter; zeroed together with the histogram that follows it
     pl->off_hist = off; off += align_up(F * kHistBins * 4, 256);
     pl->off_boxes = off; off += align_up(F * anc * 16, 256);
     pl->off_lists0 = off; off += align_up(F * tif * kListCap * 8, 256);
@@ -796,6 +999,7 @@ static int launch_head_t(const HeadMaps& maps, const HeadKernelParams& kp, cudaS
     static bool configured = false;                 // once per instantiation (also keeps graph capture clean)
     if (!configured) {
         VD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        VD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));   // same carve-out as the NMS kernel: CTAs of both can share an SM
         configured = true;
     }
     int grid = sm_count(); if (grid > kp.total_tiles) grid = kp.total_tiles;
@@ -892,11 +1096,13 @@ extern "C" int vd_head_forward_stages(const VdHeadParams* hp, float* ids, float*
     HeadKernelParams& kp = pl.kp;
     kp.hints = (unsigned long long*)(ws + pl.off_hints);
     kp.hist = (uint32_t*)(ws + pl.off_hist);
+    kp.tile_counter = (unsigned int*)(ws + pl.off_ctr);
     kp.boxes = (float4*)(ws + pl.off_boxes);
     kp.lists = (uint64_t*)(ws + pl.off_lists0);
     kp.counts = (uint32_t*)(ws + pl.off_counts0);
     kp.valid_thresh = hp->valid_thresh; kp.k = k; kp.cap = (k <= 448) ? 640 : kListCap;
-    if (getenv("VD_DEBUG_SKIP_EPILOGUE")) kp.k = 0;     // profiling aid: results are garbage
+    kp.stamps = getenv("VD_DEBUG_HEAD_STAMPS") ? (long long*)(ws + pl.off_listsA) : nullptr;   // profiling aid (unused merge area)
+    if (const char* e = getenv("VD_DEBUG_SKIP_EPILOGUE")) kp.dbg = atoi(e);     // profiling aid: results are garbage
 
     for (int s = 0; s < hp->num_scales; ++s) {      // optional temporal tip cell in front (layers.py:82-89)
         const VdHeadScale& sc = hp->scale[s];
@@ -912,7 +1118,8 @@ extern "C" int vd_head_forward_stages(const VdHeadParams* hp, float* ids, float*
     rc = make_maps(hp, pl, &maps);
     if (rc) return rc;
     if (stage_mask & VD_STAGE_HEAD) {
-        VD_CUDA(cudaMemsetAsync(kp.hist, 0, (size_t)hp->frames * kHistBins * 4, stream));
+        // no memset: the previous call's NMS kernel left the tile counter and the histogram zeroed (kWsMagic); a workspace
+        // in any other state is detected on the device and handled exactly (static schedule, streaming selection)
         rc = launch_head<EPI_FILTER>(maps, kp, pl.C, stream);
         if (rc) return rc;
     }
@@ -921,15 +1128,16 @@ extern "C" int vd_head_forward_stages(const VdHeadParams* hp, float* ids, float*
     NmsParams P;
     P.overlap_thresh = hp->nms_thresh; P.k = k; P.sortn = nms_sortn(k); P.class_aware = 1;
     P.max_out = hp->post_nms;
-    P.dbg = getenv("VD_DEBUG_NMS_STAMPS") ? (long long*)(ws + pl.off_listsA) : nullptr;   // profiling aid (unused merge area)
+    P.dbg = (getenv("VD_DEBUG_NMS_STAMPS") || getenv("VD_DEBUG_HEAD_STAMPS")) ? (long long*)(ws + pl.off_listsA) : nullptr;   // profiling aid (unused merge area)
     FusedSource src{kp.g, kp.boxes};
     FusedSink sink{ids, scores, bboxes, keep_rows_or_null, hp->post_nms};
     static bool configured = false;
     if (!configured) {
         VD_CUDA(cudaFuncSetAttribute(nms_final_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)nms_hist_smem(VD_MAX_TOPK)));
+        VD_CUDA(cudaFuncSetAttribute(nms_final_hist_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         configured = true;
     }
-    nms_final_hist_kernel<<<hp->frames, kFinalThreads, nms_hist_smem(k), stream>>>(kp.lists, kp.counts, kp.tiles_per_frame, kp.hist, P, src, sink);
+    nms_final_hist_kernel<<<hp->frames, kNmsThreads, nms_hist_smem(k), stream>>>(kp.lists, kp.counts, kp.tiles_per_frame, kp.hist, kp.tile_counter, P, src, sink);
     VD_LAUNCH_CHECK();
     return VD_OK;
 }

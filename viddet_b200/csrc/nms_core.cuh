@@ -68,34 +68,75 @@ __device__ __forceinline__ void bitonic_sort_u32_asc(uint32_t* s, int SN) {
     __syncthreads();
 }
 
-// One element per thread (SN == blockDim.x): strides < 32 exchange by warp shuffle, larger strides
-// through shared memory -- 10 barrier rounds instead of 45 for SN = 512.
-template <typename T, bool kDescending>
-__device__ __forceinline__ void bitonic_sort_reg(T* s, int SN) {
+// Bitonic sort with E = SN / blockDim.x elements per thread held in registers (thread t owns elements
+// [t*E, t*E+E)): compare-exchange distances < E stay inside the thread, distances < 32*E use warp
+// shuffles, larger ones go through shared memory -- 6 barrier rounds instead of 45 for SN = 512.
+template <typename T, bool kDescending, int E>
+__device__ __forceinline__ void bitonic_sort_regs(T* s, int SN) {
     const int tid = threadIdx.x;
-    T v = s[tid];
+    T v[E];
+#pragma unroll
+    for (int e = 0; e < E; ++e) v[e] = s[tid * E + e];
+    auto cx = [&](T a, T o, int i, int stride, int size) -> T {       // value element i keeps after exchanging with i^stride
+        const bool dir = ((i & size) == 0) == kDescending;             // this run sorts descending
+        const bool lower = (i & stride) == 0;
+        const T mx = a > o ? a : o, mn = a > o ? o : a;
+        return (lower == dir) ? mx : mn;
+    };
     for (int size = 2; size <= SN; size <<= 1) {
-        const bool dir = ((tid & size) == 0) == kDescending;       // true: this run sorts descending
-        for (int stride = size >> 1; stride > 0; stride >>= 1) {
-            T o;
-            if (stride >= 32) {
-                __syncthreads(); s[tid] = v; __syncthreads();
-                o = s[tid ^ stride];
-            } else {
-                if constexpr (sizeof(T) == 8) o = (T)__shfl_xor_sync(0xffffffffu, (unsigned long long)v, stride);
-                else o = (T)__shfl_xor_sync(0xffffffffu, (unsigned)v, stride);
+        int stride = size >> 1;
+        for (; stride >= 32 * E; stride >>= 1) {
+            __syncthreads();
+#pragma unroll
+            for (int e = 0; e < E; ++e) s[tid * E + e] = v[e];
+            __syncthreads();
+#pragma unroll
+            for (int e = 0; e < E; ++e) v[e] = cx(v[e], s[(tid * E + e) ^ stride], tid * E + e, stride, size);
+        }
+        for (; stride >= E; stride >>= 1) {
+#pragma unroll
+            for (int e = 0; e < E; ++e) {
+                T o;
+                if constexpr (sizeof(T) == 8) o = (T)__shfl_xor_sync(0xffffffffu, (unsigned long long)v[e], stride / E);
+                else o = (T)__shfl_xor_sync(0xffffffffu, (unsigned)v[e], stride / E);
+                v[e] = cx(v[e], o, tid * E + e, stride, size);
             }
-            const bool lower = (tid & stride) == 0;
-            const bool keep_max = (lower == dir);
-            const T mx = v > o ? v : o, mn = v > o ? o : v;
-            v = keep_max ? mx : mn;
+        }
+#pragma unroll
+        for (int st = E / 2; st >= 1; st >>= 1) {
+            if (st < size) {
+                T w[E];
+#pragma unroll
+                for (int e = 0; e < E; ++e) w[e] = cx(v[e], v[e ^ st], tid * E + e, st, size);
+#pragma unroll
+                for (int e = 0; e < E; ++e) v[e] = w[e];
+            }
         }
     }
     __syncthreads();
-    s[tid] = v;
+#pragma unroll
+    for (int e = 0; e < E; ++e) s[tid * E + e] = v[e];
     __syncthreads();
 }
+template <typename T, bool kDescending>
+__device__ __forceinline__ void bitonic_sort_reg(T* s, int SN) { bitonic_sort_regs<T, kDescending, 1>(s, SN); }
 
+// Block-wide sort of s[0..SN): register version when SN / blockDim.x is 1, 2, 4 or 8, else shared memory.
+__device__ __forceinline__ void block_sort_u64_desc(uint64_t* s, int SN) {
+    const int nt = (int)blockDim.x;
+    if (SN == nt) bitonic_sort_regs<uint64_t, true, 1>(s, SN);
+    else if (SN == 2 * nt) bitonic_sort_regs<uint64_t, true, 2>(s, SN);
+    else if (SN == 4 * nt) bitonic_sort_regs<uint64_t, true, 4>(s, SN);
+    else if (SN == 8 * nt) bitonic_sort_regs<uint64_t, true, 8>(s, SN);
+    else bitonic_sort_desc(s, SN);
+}
+__device__ __forceinline__ void block_sort_u32_asc(uint32_t* s, int SN) {
+    const int nt = (int)blockDim.x;
+    if (SN == nt) bitonic_sort_regs<uint32_t, false, 1>(s, SN);
+    else if (SN == 2 * nt) bitonic_sort_regs<uint32_t, false, 2>(s, SN);
+    else if (SN == 4 * nt) bitonic_sort_regs<uint32_t, false, 4>(s, SN);
+    else bitonic_sort_u32_asc(s, SN);
+}
 
 // Steps 3-6 on the sorted keys skeys[0..n): gather boxes, suppression matrix, greedy scan, emit.
 template <class Source, class Sink>
@@ -122,8 +163,7 @@ __device__ void nms_tail(const int n, const int b, const NmsParams P, const Sour
         for (int i = tid; i < SN; i += blockDim.x)
             skey2[i] = (i < n) ? (((uint32_t)scls[i] << 10) | (uint32_t)i) : 0xffffffffu;
         __syncthreads();
-        if (SN == (int)blockDim.x) bitonic_sort_reg<uint32_t, false>(skey2, SN);
-        else bitonic_sort_u32_asc(skey2, SN);
+        block_sort_u32_asc(skey2, SN);
         VD_STAMP(P, 6);
         // 4 threads per rank walk the rank's bucket tail with stride 4 (buckets are ~n/C long)
         for (int i = tid >> 2; i < n; i += blockDim.x >> 2) {
@@ -169,7 +209,7 @@ __device__ void nms_tail(const int n, const int b, const NmsParams P, const Sour
                 uint32_t dj = __shfl_sync(0xffffffffu, diag, j);
                 if (!((cur >> j) & 1u)) cur |= dj;
             }
-            uint32_t validbits = (n - base >= 32) ? 0xffffffffu : ((1u << (n - base)) - 1u);
+            uint32_t validbits = (n - base >= 32) ? 0xffffffffu : (n > base ? ((1u << (n - base)) - 1u) : 0u);   // blocks past n: no ranks
             uint32_t alive = ~cur & validbits;
             if (lane == w) removed = cur;
             if (lane == 0) { salive[w] = alive; sprefix[w] = (uint32_t)kept_total; }
@@ -247,8 +287,7 @@ __device__ void nms_final_body(const uint64_t* __restrict__ lists, const uint32_
     uint64_t piv = block_select_pivot<kFinalR>(keys, (uint32_t)k, (uint32_t)SN, 0ull, 0ull, scr, it, &nsel);
     block_compact<kFinalR>(keys, piv, skeys, (uint32_t)SN, &scr->out_count);
     __syncthreads();
-    if (SN == (int)blockDim.x) bitonic_sort_reg<uint64_t, true>(skeys, SN);
-    else bitonic_sort_desc(skeys, SN);                 // starts and ends with __syncthreads
+    block_sort_u64_desc(skeys, SN);                    // starts and ends with __syncthreads
     const int n = (int)(nsel < (uint32_t)k ? nsel : (uint32_t)k);
     nms_tail(n, b, P, src, sink, skeys, sbox, scls, sarea, smask, skey2, salive, sprefix);
 }

@@ -13,13 +13,15 @@ for _ in range(5): s.run()
 torch.cuda.synchronize()
 # stamps live at the start of the (unused) merge area: find its offset by scanning for plausible clocks
 ws = s._ws.view(torch.int64)
-names = ["start", "hist scan", "stream lists", "sort", "tail start", "box gather", "class sort", "pair loop", "greedy scan", "emit"]
+names = ["start", "hist scan", "stream lists", "sort", "tail start", "box gather", "diag tiles", "(unused)", "wavefront", "finish"]
 # offset of listsA: hints 256 + hist + boxes + lists0 + counts0 (mirrors make_plan)
 F = frames; anc = 10647; tif = 30
 def al(x): return (x + 255) // 256 * 256
 off = 256 + 256 + al(F * 4096 * 4) + al(F * anc * 16) + al(F * tif * 1024 * 8) + al(F * tif * 4)
 st = ws[off // 8: off // 8 + 10].cpu().tolist()
 print("clocks:", st)
+prev = st[0]
 for i in range(1, 10):
-    print("%-14s %8d cycles  %6.2f us" % (names[i], st[i] - st[i - 1], (st[i] - st[i - 1]) / 1.9e3))
+    if st[i] < st[0]: continue
+    print("%-14s %8d cycles  %6.2f us" % (names[i], st[i] - prev, (st[i] - prev) / 1.9e3)); prev = st[i]
 print("total %.2f us" % ((st[9] - st[0]) / 1.9e3))

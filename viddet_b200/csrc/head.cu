@@ -752,29 +752,136 @@ struct FusedSink {
     }
 };
 
+// Steps 3-6 of the per-frame NMS for the fused path: class-aware greedy NMS as a WAVEFRONT over 32-rank chunks, with no
+// n x n matrix and no class sort.  Only KEPT boxes ever suppress and the scan stops once max_out boxes are kept, so a
+// chunk's members are tested just in time against the (< max_out + 32) boxes kept so far:
+//   round c, test phase (all warps):  lane = member of chunk c; warp w tests it against kept boxes w, w+8, ... and
+//       against rows 4w..4w+3 of the chunk itself (one ballot per row = the chunk's 32x32 "diagonal" block)
+//   round c, resolve phase (warp 0):  greedy rank-order resolution of the chunk in registers, survivors are emitted
+//       straight to the output and appended to the kept list
+// Semantics = nms_core.cuh::nms_tail (rank order, IoU > thresh, same class, first max_out survivors), same IoU arithmetic.
+constexpr int kNmsThreads = 256;
+struct WaveShared { uint32_t kept_total; uint32_t sup; uint32_t diag[32]; };
+template <class Source, class Sink>
+__device__ void nms_tail_wave(const int n, const int f, const NmsParams P, const Source& src, const Sink& sink,
+                              const uint64_t* skeys, float4* sbox, int* scls, float* sarea,
+                              float4* skbox, float* skarea, int* skcls, WaveShared* wsh) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    const int NB = (n + 31) >> 5;
+    const float thr = P.overlap_thresh;
+    VD_STAMP(P, 4);
+    for (int r = tid; r < n; r += blockDim.x) {
+        float4 bx; int c; float ar;
+        src.load(f, key_row(skeys[r]), key_score(skeys[r]), bx, c, ar);
+        sbox[r] = bx; scls[r] = c; sarea[r] = ar;
+    }
+    if (tid == 0) { wsh->kept_total = 0u; wsh->sup = 0u; }
+    __syncthreads();
+    VD_STAMP(P, 5);
+    uint32_t kept_total = 0u;
+    for (int c = 0; c < NB; ++c) {
+        // ---- test phase
+        const int pm = 32 * c + lane;
+        const bool valid = pm < n;
+        float4 bm = make_float4(0.f, 0.f, 0.f, 0.f); float am_ = 0.f; int cm = -2;
+        if (valid) { bm = sbox[pm]; am_ = sarea[pm]; cm = scls[pm]; }
+        {
+            bool sup = false;
+            for (uint32_t i0 = (uint32_t)warp; i0 < kept_total; i0 += 4u * (uint32_t)nwarps) {     // kept list is padded with never-matching entries
+                bool sp[4], am[4]; bool any_amb = false;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const uint32_t i = i0 + (uint32_t)(u * nwarps);
+                    sp[u] = vd_iou_gt_fast(skbox[i], skarea[i], bm, am_, thr, am[u]);
+                    const bool same = skcls[i] == cm;
+                    sp[u] &= same; am[u] &= same; any_amb |= am[u];
+                }
+                if (__builtin_expect(any_amb, 0)) {
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) { const uint32_t i = i0 + (uint32_t)(u * nwarps); if (am[u]) sp[u] = vd_iou_gt(skbox[i], skarea[i], bm, am_, thr); }
+                }
+                sup |= sp[0] | sp[1] | sp[2] | sp[3];
+            }
+            const unsigned sw = __ballot_sync(0xffffffffu, sup);
+            if (lane == 0 && sw) atomicOr(&wsh->sup, sw);
+            // rows 4w .. 4w+3 of the chunk's own block (row = earlier rank, lane = later rank)
+            bool sp[4], am[4]; bool any_amb = false;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int rr = 4 * warp + u, pr = min(32 * c + rr, n - 1);
+                sp[u] = vd_iou_gt_fast(sbox[pr], sarea[pr], bm, am_, thr, am[u]);
+                const bool rel = (lane > rr) & (scls[pr] == cm) & (32 * c + rr < n);
+                sp[u] &= rel; am[u] &= rel; any_amb |= am[u];
+            }
+            if (__builtin_expect(any_amb, 0)) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) { const int pr = min(32 * c + 4 * warp + u, n - 1); if (am[u]) sp[u] = vd_iou_gt(sbox[pr], sarea[pr], bm, am_, thr); }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const unsigned bal = __ballot_sync(0xffffffffu, sp[u]);
+                if (lane == 0) wsh->diag[4 * warp + u] = bal;
+            }
+        }
+        __syncthreads();
+        // ---- resolve phase
+        if (warp == 0) {
+            uint32_t cur = wsh->sup | (valid ? 0u : 0u);
+            cur |= ~__ballot_sync(0xffffffffu, valid);                 // ranks past n never survive
+            const uint32_t diag = wsh->diag[lane];
+#pragma unroll
+            for (int j0 = 0; j0 < 32; j0 += 8) {
+                uint32_t d[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) d[j] = __shfl_sync(0xffffffffu, diag, j0 + j);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) if (!((cur >> (j0 + j)) & 1u)) cur |= d[j];
+            }
+            const uint32_t alive = ~cur;
+            const uint32_t cnt = (uint32_t)__popc(alive);
+            const uint32_t slot = kept_total + (uint32_t)__popc(alive & ((1u << lane) - 1u));
+            if ((alive >> lane) & 1u) {
+                if (slot < (uint32_t)P.max_out) sink.emit(f, (int)slot, key_row(skeys[pm]), key_score(skeys[pm]), bm, cm);
+                skbox[slot] = bm; skarea[slot] = am_; skcls[slot] = cm;
+            }
+            // pad the list to the test loop's stride with entries that match no class
+            const uint32_t padded = (kept_total + cnt + 4u * (uint32_t)nwarps);
+            for (uint32_t i = kept_total + cnt + (uint32_t)lane; i < padded; i += 32u) skcls[i] = -3;
+            if (lane == 0) { wsh->kept_total = kept_total + cnt; wsh->sup = 0u; }
+        }
+        __syncthreads();
+        kept_total = wsh->kept_total;
+        if (kept_total >= (uint32_t)P.max_out) break;
+    }
+    VD_STAMP(P, 8);
+    sink.finish(f, (int)kept_total < P.max_out ? (int)kept_total : P.max_out);
+    VD_STAMP(P, 9);
+}
+
 // Per-frame top-k + NMS straight from the tile lists: the frame pivot comes from the score histogram
 // (suffix scan), the lists are streamed once and compacted, then sort + nms_tail.  No merge passes,
 // no pivot search (a streaming bisection remains as the fallback for pathologically tied scores or a
 // histogram that does not describe the lists).  Sized to share an SM with a head_kernel CTA of the
 // NEXT batch (256 threads, <= 64 registers, ~41 KB shared): the step pipeline overlaps the two.
 // The kernel leaves its frame's histogram zeroed for the next call (no memset node per call).
-constexpr int kNmsThreads = 256;
 __global__ void __maxnreg__(56)
 nms_final_hist_kernel(const uint64_t* __restrict__ lists, const uint32_t* __restrict__ counts, int n_lists,
                       uint32_t* __restrict__ hist, unsigned int* __restrict__ ctr, NmsParams P, FusedSource src, FusedSink sink) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
-    const int k = P.k, NW = (k + 31) >> 5, SNk = P.sortn;
+    const int k = P.k;
     SelectScratch* scr = reinterpret_cast<SelectScratch*>(smem_raw);
-    uint32_t* sx = reinterpret_cast<uint32_t*>(smem_raw + 64);          // [48] warp sums + results
+    uint32_t* sx = reinterpret_cast<uint32_t*>(smem_raw + 64);          // [40] warp sums + results
     uint64_t* skeys = reinterpret_cast<uint64_t*>(smem_raw + 256);
     float4* sbox = reinterpret_cast<float4*>(skeys + kHistCap);
-    int* scls = reinterpret_cast<int*>(sbox + k);
+    const int KMAX = (P.max_out < k ? P.max_out : k) + 32 + 4 * (kNmsThreads / 32);   // kept list + padding
+    float4* skbox = sbox + k;
+    float* skarea = reinterpret_cast<float*>(skbox + KMAX);
+    int* skcls = reinterpret_cast<int*>(skarea + KMAX);
+    int* scls = skcls + KMAX;
     float* sarea = reinterpret_cast<float*>(scls + k);
-    uint32_t* smask = reinterpret_cast<uint32_t*>(sarea + k);
-    uint32_t* skey2 = smask + (size_t)k * NW;
-    uint32_t* salive = skey2 + SNk;
-    uint32_t* sprefix = salive + 64;
+    uint32_t* scount = reinterpret_cast<uint32_t*>(sarea + k);         // [256] clamped list lengths
+    WaveShared* wsh = reinterpret_cast<WaveShared*>(scount + 256);
     lists += (size_t)f * n_lists * kListCap; counts += (size_t)f * n_lists; hist += (size_t)f * kHistBins;
 
     VD_STAMP(P, 0);
@@ -831,7 +938,6 @@ nms_final_hist_kernel(const uint64_t* __restrict__ lists, const uint32_t* __rest
         }
         return block_sum(c, scr, it);
     };
-    uint32_t* scount = reinterpret_cast<uint32_t*>(sprefix + 64);     // [n_lists] clamped list lengths
     for (int l = tid; l < n_lists; l += blockDim.x) { uint32_t n = counts[l]; scount[l] = n > (uint32_t)kListCap ? (uint32_t)kListCap : n; }
     int sit = 0;
     uint32_t m = 0u;
@@ -889,12 +995,13 @@ nms_final_hist_kernel(const uint64_t* __restrict__ lists, const uint32_t* __rest
     block_sort_u64_desc(skeys, SN);
     VD_STAMP(P, 3);
     const int n = (int)(m < (uint32_t)k ? m : (uint32_t)k);
-    nms_tail(n, f, P, src, sink, skeys, sbox, scls, sarea, smask, skey2, salive, sprefix);
+    nms_tail_wave(n, f, P, src, sink, skeys, sbox, scls, sarea, skbox, skarea, skcls, wsh);
     if (f == 0 && tid == 0) { ctr[0] = 0u; ctr[1] = 0u; ctr[2] = kWsMagic; }   // workspace is in its between-calls state
     if (P.dbg && tid == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); P.dbg[8192 + f * 4 + 1] = (long long)t; }
 }
-static size_t nms_hist_smem(int k) {
-    return 256 + (size_t)kHistCap * 8 + (size_t)k * 16 + (size_t)k * 8 + (size_t)k * nms_words(k) * 4 + (size_t)nms_sortn(k) * 4 + 512 + 64 + 1024;   // + per-list counts (<= 256 lists)
+static size_t nms_hist_smem(int k, int max_out) {
+    const size_t kmax = (size_t)(max_out < k ? max_out : k) + 32 + 4 * (kNmsThreads / 32);
+    return 256 + (size_t)kHistCap * 8 + (size_t)k * 16 + kmax * 24 + (size_t)k * 8 + 256 * 4 + sizeof(WaveShared) + 64;
 }
 
 // no-NMS tail (yolo3.py:525 false): rows are the plain concat; only reachable through vd_head_detections.
@@ -1133,11 +1240,11 @@ extern "C" int vd_head_forward_stages(const VdHeadParams* hp, float* ids, float*
     FusedSink sink{ids, scores, bboxes, keep_rows_or_null, hp->post_nms};
     static bool configured = false;
     if (!configured) {
-        VD_CUDA(cudaFuncSetAttribute(nms_final_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)nms_hist_smem(VD_MAX_TOPK)));
+        VD_CUDA(cudaFuncSetAttribute(nms_final_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)nms_hist_smem(VD_MAX_TOPK, VD_MAX_TOPK)));
         VD_CUDA(cudaFuncSetAttribute(nms_final_hist_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         configured = true;
     }
-    nms_final_hist_kernel<<<hp->frames, kNmsThreads, nms_hist_smem(k), stream>>>(kp.lists, kp.counts, kp.tiles_per_frame, kp.hist, kp.tile_counter, P, src, sink);
+    nms_final_hist_kernel<<<hp->frames, kNmsThreads, nms_hist_smem(k, hp->post_nms), stream>>>(kp.lists, kp.counts, kp.tiles_per_frame, kp.hist, kp.tile_counter, P, src, sink);
     VD_LAUNCH_CHECK();
     return VD_OK;
 }

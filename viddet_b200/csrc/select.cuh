@@ -164,4 +164,21 @@ __device__ __forceinline__ bool vd_iou_gt(float4 r, float area_r, float4 p, floa
     return iou > thresh;
 }
 
+// Straight-line form of vd_iou_gt for unrolled loops (few warps per SM: independent tests must interleave, so no
+// branches inside): returns the decision when inter is clearly on one side of thresh*union (same margin as vd_iou_gt),
+// and sets `amb` for the few-ulp band around equality and for degenerate unions -- the caller resolves those with
+// vd_iou_gt (the IEEE division) outside its unrolled group.  Decisions are identical to vd_iou_gt by construction.
+__device__ __forceinline__ bool vd_iou_gt_fast(float4 r, float area_r, float4 p, float area_p, float thresh, bool& amb) {
+    const float inter = __fmul_rn(vd_intersect_1d(r.x, r.z, p.x, p.z), vd_intersect_1d(r.y, r.w, p.y, p.w));
+    const float uni = __fsub_rn(__fadd_rn(area_r, area_p), inter);
+    const float tu = __fmul_rn(thresh, uni);
+    const float margin = __fmul_rn(tu, 4.0e-7f) + 1.0e-37f;
+    const bool common = (uni > 0.0f) & (thresh >= 0.0f) & (inter < 3.0e38f) & (uni < 3.0e38f);
+    const bool zero = (inter == 0.0f) & (thresh >= 0.0f);
+    const bool yes = common & (inter > tu + margin) & !zero;
+    const bool no = zero | (common & (inter < tu - margin));
+    amb = !(yes | no);
+    return yes;
+}
+
 }  // namespace vd

@@ -153,7 +153,8 @@ def main():
     ap.add_argument("--workload", default="voc416_b64", choices=sorted(WORKLOADS))
     ap.add_argument("--cpu-frames", type=int, default=64, help="frames per CPU-baseline step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-pipeline", action="store_true", help="serial step graphs instead of the overlapped pipeline")
+    ap.add_argument("--rotations", type=int, default=4, help="ring rotations captured per pipeline graph")
     args = ap.parse_args()
     if args.impl == "reference":
         if args.steps == 200 and args.warmup == 20:       # defaults sized for the GPU arm
@@ -176,35 +177,69 @@ def main():
     cpu_gen = torch.Generator().manual_seed(1234)
     head = viddet_b200.YOLOV3Head(C).initialize(generator=cpu_gen)       # U(-0.07,0.07), bias 0 (detect_yolo3.py:885)
     head.set_nms(nms_thresh=0.45, nms_topk=400, post_nms=100)            # detect_yolo3.py:200
+    # ring of NROT resident batches; the detections of the whole ring live in one tensor per field (gathered per cycle)
+    ids_all = torch.empty((NROT * frames, 100, 1), device=dev)
+    scores_all = torch.empty((NROT * frames, 100, 1), device=dev)
+    boxes_all = torch.empty((NROT * frames, 100, 4), device=dev)
     sessions = []
     for j in range(NROT):
-        s = head.session(synth_tips(torch, gen, frames, size, dev))
-        if not args.no_graph:
-            s.capture()
+        sl = slice(j * frames, (j + 1) * frames)
+        s = head.session(synth_tips(torch, gen, frames, size, dev), out=(ids_all[sl], scores_all[sl], boxes_all[sl]))
+        s.capture()
         sessions.append(s)
-    step_fn = (lambda s: s.run()) if args.no_graph else (lambda s: s.replay())
-    gather_out = torch.empty((world * frames, 100, 6), device=dev) if world > 1 else None
+    pipe = None if args.no_pipeline else viddet_b200.HeadPipeline(sessions, rotations=args.rotations)
+    spc = pipe.steps_per_cycle if pipe else 1
+    fields = (ids_all, scores_all, boxes_all)
+    if world > 1:                                        # the path's only collective: final detection gather, off the critical path
+        side = torch.cuda.Stream()
+        snaps = [[torch.empty_like(t) for t in fields] for _ in range(2)]
+        gouts = [torch.empty((world,) + tuple(t.shape), device=dev) for t in fields]
+        gather_done = [None, None]
+    state = {"c": 0}
 
-    def one_step(i):
-        s = sessions[i % NROT]
-        step_fn(s)
-        if world > 1:                                    # the path's only collective: final detection gather
-            dist.all_gather_into_tensor(gather_out, s.packed())
+    def gather_ring():
+        """all_gather of the ring's detections on a side stream (double-buffered snapshot), overlapped with the next cycle."""
+        c = state["c"] % 2
+        state["c"] += 1
+        main = torch.cuda.current_stream()
+        if gather_done[c] is not None:
+            main.wait_event(gather_done[c])
+        for dst, src in zip(snaps[c], fields):
+            dst.copy_(src)
+        ev = torch.cuda.Event(); ev.record(main)
+        with torch.cuda.stream(side):
+            side.wait_event(ev)
+            for g, sn in zip(gouts, snaps[c]):
+                dist.all_gather_into_tensor(g, sn)
+            gather_done[c] = torch.cuda.Event(); gather_done[c].record(side)
+
+    def run_steps(n):
+        """n steps = n batches; whole cycles go through the overlapped pipeline, the remainder through the serial graphs."""
+        i = 0
+        while pipe is not None and n - i >= spc:
+            pipe.cycle(); i += spc
+            if world > 1:
+                gather_ring()
+        while i < n:
+            sessions[i % NROT].replay(); i += 1
+            if world > 1 and (i % NROT == 0 or i == n):
+                gather_ring()
 
     def barrier():
         if world > 1:
+            torch.cuda.current_stream().wait_stream(side)
             dist.barrier()
         torch.cuda.synchronize()
 
-    for i in range(args.warmup):
-        one_step(i)
+    run_steps(max(args.warmup, spc))
     barrier()
     sampler = ClockSampler(local).start() if rank == 0 else None
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
-    for i in range(args.steps):
-        one_step(i)
+    run_steps(args.steps)
+    if world > 1:
+        torch.cuda.current_stream().wait_stream(side)     # the last gather is part of the job
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
@@ -215,28 +250,26 @@ def main():
         ms = float(t.item())
     value = world * frames * args.steps / (ms * 1e-3)
 
-    # ---- dominant kernel alone (fused head kernel), CUDA events on the launching stream
-    for i in range(5):
-        sessions[i % NROT].run(_lib.VD_STAGE_HEAD)
+    # ---- dominant kernel (fused head kernel) timed inside real steps: CUDA events around the kernel on the launching
+    #      stream, each followed by its NMS kernel so the workspace state (histograms, hints) is the steady-state one
+    ksteps = max(20, min(args.steps, 100))
+    pairs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(ksteps)]
+    for i in range(4):
+        sessions[i % NROT].run()
     torch.cuda.synchronize()
-    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ksteps = max(20, min(args.steps, 200))
-    k0.record()
     for i in range(ksteps):
-        sessions[i % NROT].run(_lib.VD_STAGE_HEAD)
-    k1.record()
+        a, b, c = pairs[i]
+        a.record(); sessions[i % NROT].run(_lib.VD_STAGE_HEAD); b.record(); sessions[i % NROT].run(_lib.VD_STAGE_NMS); c.record()
     torch.cuda.synchronize()
-    head_ms = k0.elapsed_time(k1) / ksteps
-    n0, n1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    n0.record()
-    for i in range(ksteps):
-        sessions[i % NROT].run(_lib.VD_STAGE_NMS)
-    n1.record()
-    torch.cuda.synchronize()
-    nms_ms = n0.elapsed_time(n1) / ksteps
+    head_ms = sorted(a.elapsed_time(b) for a, b, c in pairs)[ksteps // 2]
+    nms_ms = sorted(b.elapsed_time(c) for a, b, c in pairs)[ksteps // 2]
     peak, peak_kind = measured_peaks()
     alg_bytes = algorithmic_bytes_per_frame(C, size) * frames
     achieved = alg_bytes / (head_ms * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic_head_kernel_%s.json" % args.workload)
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get("traffic_bytes_per_launch")
 
     # ---- end to end through the public API with HOST buffers (pinned), H2D + D2H inside the timed region
     host_sets = [[t.cpu().pin_memory() for t in s.tips] for s in sessions[:2]]
@@ -245,13 +278,15 @@ def main():
     d2h = host_out.numel() * 4
     sess = sessions[0]
 
+    gather_one = torch.empty((world * frames, 100, 6), device=dev) if world > 1 else None
+
     def e2e_step(i):
         for dst, src in zip(sess.tips, host_sets[i % 2]):
             dst.copy_(src, non_blocking=True)
-        step_fn(sess)
+        sess.replay()
         host_out.copy_(sess.packed(), non_blocking=True)
         if world > 1:
-            dist.all_gather_into_tensor(gather_out, sess.packed())
+            dist.all_gather_into_tensor(gather_one, sess.packed())
 
     e2e_steps = max(5, min(args.steps, 30))
     for i in range(3):
@@ -296,16 +331,17 @@ def main():
                        "carrier": "bf16 channels-last tips, bf16 weights, fp32 accumulate/decode/NMS",
                        "nms": {"thresh": 0.45, "valid": 0.01, "topk": 400, "post": 100},
                        "l2": "inputs %.0f MB/step > 126 MB L2; %d rotating resident input sets" % (alg_bytes / 1e6, NROT),
-                       "launch": "cuda graph replay" if not args.no_graph else "direct launches",
-                       "sharding": "frames split by rank, final all_gather of (frames,100,6)" if world > 1 else "single GPU"},
+                       "launch": ("cuda graph per %d steps: head kernel of batch j+1 overlapped with the top-k/NMS kernel of batch j" % spc) if pipe else "cuda graph per step (serial)",
+                       "sharding": "frames split by rank, all_gather of the detections per cycle on a side stream" if world > 1 else "single GPU"},
             "roofline": {"bound": "hbm", "kernel": "head_kernel<EPI_FILTER> (pred conv + decode + candidate filter)",
                          "achieved": achieved, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "algorithmic_bytes_per_launch": alg_bytes,
-                         "kernel_ms": head_ms, "nms_stage_ms": nms_ms},
+                         "frac": achieved / peak, "traffic": traffic, "algorithmic_bytes_per_launch": alg_bytes,
+                         "kernel_ms": head_ms, "nms_kernel_ms": nms_ms,
+                         "path_frac": (alg_bytes * world * args.steps / (ms * 1e-3) / 1e9 / world) / peak},
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps, "note": "pinned host bf16 NHWC tips -> H2D -> fused head -> D2H of (64,100,6)"},
-            "gpu_launches": args.steps * sess.launches,
+            "gpu_launches": args.steps * sess.launches,                   # head kernel + NMS kernel per step
             "clocks": clocks,
         }
         print(json.dumps(line))

@@ -129,9 +129,15 @@ typedef struct VdHeadParams {
     VdHeadScale scale[VD_MAX_SCALES];
 } VdHeadParams;
 
-/* The first 256 bytes of the workspace hold warm-start hints (per-scale selection pivots) that the
- * kernel reads and updates: passing the same workspace to consecutive calls makes later calls
- * faster.  Any content is valid -- hints change speed, never results. */
+/* Workspace contract.  vd_head_forward keeps state in its workspace BETWEEN calls: warm-start hints for the
+ * per-tile selection, the dynamic tile-scheduler counters, per-frame score histograms (left zeroed by the NMS
+ * kernel, so no memset runs per call) and a marker that says so for the layout of the last call.  Hence:
+ *   - pass the same buffer to consecutive calls and do not write to it in between (do not share it with
+ *     vd_box_nms or other streams' calls);
+ *   - a zero-filled buffer, a buffer last used with other parameters, or arbitrary foreign content are all
+ *     detected on the device and handled exactly (static tile schedule, streaming selection) -- slower for
+ *     that one call, never wrong;
+ *   - hints only change speed, never results. */
 size_t vd_head_workspace_bytes(const VdHeadParams* p);
 /* ids (frames, post_nms, 1), scores (frames, post_nms, 1), bboxes (frames, post_nms, 4) fp32;
  * keep_rows_or_null (frames, post_nms) int32 = row in the (frames, rows, 6) tensor of each output

@@ -18,20 +18,18 @@ for s in sessions:
 pipe = viddet_b200.HeadPipeline(sessions)
 for s in sessions: s.keep.fill_(-7); s.scores.fill_(-7.0)
 n = 200
-for i in range(8): pipe.step(i)
-pipe.flush(7)
+for i in range(2): pipe.cycle()
 torch.cuda.synchronize()
 for j, s in enumerate(sessions):
     assert torch.equal(s.keep, ref[j][0]) and torch.equal(s.scores, ref[j][1]), "pipelined results differ for session %d" % j
 print("pipelined results identical to the serial call")
 for s in sessions: s.capture()
-for name, fn in (("serial graph", lambda i: sessions[i % 4].replay()), ("pipelined", pipe.step)):
+for name, fn in (("serial graph", lambda i: sessions[i % 4].replay()), ("pipelined", lambda i: pipe.cycle() if i % pipe.steps_per_cycle == 0 else None)):
     for i in range(8): fn(i)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(n): fn(i)
-    if name == "pipelined": pipe.flush(n - 1)
     e1.record(); torch.cuda.synchronize()
     us = 1e3 * e0.elapsed_time(e1) / n
     gb = bench.algorithmic_bytes_per_frame(C, size) * frames / (us * 1e-6) / 1e9

@@ -169,6 +169,61 @@ def test_fused_valid_thresh_sweep_bit_exact(valid):
     assert torch.equal(scores.view(torch.int32), out[:, :100, 1:2].contiguous().view(torch.int32))
 
 
+def test_pipeline_matches_serial_calls():
+    """HeadPipeline (head kernel of batch j+1 overlapped with the NMS kernel of batch j, several rotations per
+    graph) must leave exactly the serial call's outputs in every session of the ring."""
+    import viddet_b200
+    rng = np.random.RandomState(3)
+    C, B, size = 20, 5, 320
+    ws, bs = make_pred_weights(rng, C, bias_scale=0.1)
+    head = build_head(C, ws, bs)
+    head.set_nms(0.45, 400, 100)
+    sessions, ref = [], []
+    for j in range(3):
+        tips = [cuda(t) for t in make_tips(rng, B, size=size)]
+        ref.append([t.clone() for t in head(tips, return_keep=True)])
+        sessions.append(head.session(tips, return_keep=True))
+    pipe = viddet_b200.HeadPipeline(sessions, rotations=2)
+    for s in sessions:
+        s.keep.fill_(-7); s.scores.fill_(-7.0); s.ids.fill_(-7.0); s.bboxes.fill_(-7.0)
+    for _ in range(3):
+        pipe.cycle()
+    torch.cuda.synchronize()
+    for s, (ids, scores, boxes, keep) in zip(sessions, ref):
+        assert torch.equal(s.keep, keep)
+        assert torch.equal(s.ids.view(torch.int32), ids.view(torch.int32))
+        assert torch.equal(s.scores.view(torch.int32), scores.view(torch.int32))
+        assert torch.equal(s.bboxes.view(torch.int32), boxes.view(torch.int32))
+
+
+def test_workspace_in_foreign_state_is_exact():
+    """The fused call keeps scheduler / histogram state in its workspace between calls.  A workspace holding
+    arbitrary bytes (or the state of a call with another shape) must still give exact results, and the next
+    call on it must too."""
+    import viddet_b200
+    from viddet_b200 import blocks
+    rng = np.random.RandomState(8)
+    C, B = 20, 3
+    ws, bs = make_pred_weights(rng, C, bias_scale=0.1)
+    head = build_head(C, ws, bs)
+    head.set_nms(0.45, 400, 100)
+    tips = [cuda(t) for t in make_tips(rng, B, size=320)]
+    det = head.detections(tips)
+    out, rec = viddet_b200.box_nms(det, overlap_thresh=0.45, valid_thresh=0.01, topk=400, id_index=0, score_index=1,
+                                   coord_start=2, force_suppress=False, return_record=True)
+    head(tips)                                              # make sure the cached workspace exists
+    for buf in blocks._WS_CACHE.values():
+        buf.copy_(torch.randint(0, 256, buf.shape, dtype=torch.uint8, device=buf.device))
+    for _ in range(3):
+        ids, scores, boxes, keep = head(tips, return_keep=True)
+        assert torch.equal(keep, rec[:, :100])
+        assert torch.equal(scores.view(torch.int32), out[:, :100, 1:2].contiguous().view(torch.int32))
+    tips2 = [cuda(t) for t in make_tips(rng, 2, size=416)]      # another layout on the same buffer, then back
+    head(tips2)
+    ids, scores, boxes, keep = head(tips, return_keep=True)
+    assert torch.equal(keep, rec[:, :100])
+
+
 def test_time_distributed_head_and_late_joins():
     import viddet_b200
     rng = np.random.RandomState(9)

@@ -59,15 +59,17 @@ def to_nhwc_bf16(x: torch.Tensor) -> torch.Tensor:
 # ------------------------------------------------------------------------------------------------
 # box_nms
 # ------------------------------------------------------------------------------------------------
-_ws_cache = {}
+_WS_CACHE = {}
 
 
-def _workspace(nbytes, device):
-    key = (device.index if device.index is not None else torch.cuda.current_device())
-    buf = _ws_cache.get(key)
+def _workspace(nbytes, device, owner="nms"):
+    """Cached scratch buffer per (device, owner).  The fused head keeps state in its workspace between calls
+    (tile-scheduler counters, histograms left zeroed, warm-start hints), so it never shares a buffer with box_nms."""
+    key = (device.index if device.index is not None else torch.cuda.current_device(), owner)
+    buf = _WS_CACHE.get(key)
     if buf is None or buf.numel() < nbytes:
-        buf = torch.zeros(int(nbytes * 1.25) + 1024, dtype=torch.uint8, device=device)   # zeroed once: holds warm-start hints
-        _ws_cache[key] = buf
+        buf = torch.zeros(int(nbytes * 1.25) + 1024, dtype=torch.uint8, device=device)
+        _WS_CACHE[key] = buf
     return buf
 
 
@@ -451,7 +453,7 @@ class YOLOV3Head:
         bboxes = torch.empty((F, post, 4), device=dev)
         keep = torch.empty((F, post), dtype=torch.int32, device=dev) if return_keep else None
         lib = load()
-        ws = _workspace(lib.vd_head_workspace_bytes(ctypes.byref(p)), dev)
+        ws = _workspace(lib.vd_head_workspace_bytes(ctypes.byref(p)), dev, owner="head")
         check(lib.vd_head_forward(ctypes.byref(p), ptr(ids), ptr(scores), ptr(bboxes), ptr(keep), ptr(ws), ws.numel(),
                                   stream_ptr()))
         if lead is not None:
@@ -460,10 +462,10 @@ class YOLOV3Head:
                 keep = keep.reshape(lead + (post,))
         return (ids, scores, bboxes, keep) if return_keep else (ids, scores, bboxes)
 
-    def session(self, tips, return_keep=False):
+    def session(self, tips, return_keep=False, out=None):
         """Bind tips/outputs/workspace once; the returned HeadSession re-enqueues the same call with no
         per-call Python work (and can be captured into a CUDA graph)."""
-        return HeadSession(self, tips, return_keep)
+        return HeadSession(self, tips, return_keep, out)
 
     def detections(self, tips):
         """The concatenated (B[,T], rows, 6) tensor of yolo3.py:523 (before NMS)."""
@@ -472,7 +474,7 @@ class YOLOV3Head:
         rows = sum(self._num_class * int(p.scale[i].H) * int(p.scale[i].W) * 3 for i in range(p.num_scales))
         det = torch.empty((p.frames, rows, 6), device=dev)
         lib = load()
-        ws = _workspace(max(lib.vd_head_workspace_bytes(ctypes.byref(p)), 256), dev)
+        ws = _workspace(max(lib.vd_head_workspace_bytes(ctypes.byref(p)), 256), dev, owner="det")
         check(lib.vd_head_detections(ctypes.byref(p), ptr(det), ptr(ws), ws.numel(), stream_ptr()))
         if lead is not None:
             det = det.reshape(lead + (rows, 6))
@@ -485,16 +487,21 @@ class HeadSession:
     workspace.  `run()` enqueues the kernels on the current stream; `capture()` records them into a
     CUDA graph whose `replay()` is a single launch."""
 
-    def __init__(self, head, tips, return_keep=False):
+    def __init__(self, head, tips, return_keep=False, out=None):
         if not (0 < head.nms_thresh < 1) or head.post_nms <= 0:
             raise _lib.VidDetError(-1, "HeadSession needs NMS and post_nms enabled")
         self.head = head
         self.params, self.tips, self._scratch, self.lead = head._prepare(tips)
         dev = self.tips[0].device
         F, post = self.params.frames, head.post_nms
-        self.ids = torch.empty((F, post, 1), device=dev)
-        self.scores = torch.empty((F, post, 1), device=dev)
-        self.bboxes = torch.empty((F, post, 4), device=dev)
+        if out is not None:                           # caller-owned output buffers (e.g. slices of one tensor per ring)
+            self.ids, self.scores, self.bboxes = out
+            assert tuple(self.ids.shape) == (F, post, 1) and tuple(self.scores.shape) == (F, post, 1) and tuple(self.bboxes.shape) == (F, post, 4)
+            assert self.ids.is_contiguous() and self.scores.is_contiguous() and self.bboxes.is_contiguous()
+        else:
+            self.ids = torch.empty((F, post, 1), device=dev)
+            self.scores = torch.empty((F, post, 1), device=dev)
+            self.bboxes = torch.empty((F, post, 4), device=dev)
         self.keep = torch.empty((F, post), dtype=torch.int32, device=dev) if return_keep else None
         lib = load()
         self._ws = torch.zeros(lib.vd_head_workspace_bytes(ctypes.byref(self.params)) + 256, dtype=torch.uint8, device=dev)
@@ -531,42 +538,50 @@ class HeadSession:
 class HeadPipeline:
     """Throughput mode over a ring of HeadSessions (one per in-flight batch).
 
-    `step(j)` launches ONE CUDA graph that runs the fused head kernel (pred conv + decode + candidate
-    filter) of batch j concurrently with the per-frame top-k/NMS kernel of batch j-1: the NMS kernel is
-    a latency-bound chain on 64 CTAs, sized (256 threads, 56 registers, ~42 KB shared) to share SMs with
-    the HBM-bound head kernel of the next batch, whose dynamic tile scheduler absorbs the interference.
-    The detections of batch j are complete after `step(j+1)` (or `flush(j)`)."""
+    One CUDA graph holds `rotations` rotations of the ring.  The fused head kernels (pred conv + decode +
+    candidate filter) of consecutive batches run back to back on one stream; the per-frame top-k/NMS kernel of
+    batch j runs on a second stream as soon as its head kernel has finished, i.e. concurrently with the head
+    kernel of batch j+1, whose SMs it shares (it is sized for that: 256 threads, 56 registers, ~30 KB shared
+    memory; the head kernel's dynamic tile scheduler absorbs the interference).  A session's next head kernel
+    waits for its previous NMS kernel.  `cycle()` = rotations * len(sessions) steps; every batch is complete
+    when the graph has finished."""
 
-    def __init__(self, sessions):
-        assert len(sessions) >= 2
+    def __init__(self, sessions, rotations=2):
+        assert len(sessions) >= 2 and rotations >= 1
         self.sessions = list(sessions)
-        self._side = torch.cuda.Stream()
+        self._streams = [torch.cuda.Stream() for _ in range(2)]
         for s in self.sessions:                       # initialise workspaces (scheduler state, warm-start hints)
             s.run()
         torch.cuda.synchronize()
-        self._graphs = []
-        n = len(self.sessions)
-        for j in range(n):
-            cur, prev = self.sessions[j], self.sessions[(j - 1) % n]
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                main = torch.cuda.current_stream()
-                self._side.wait_stream(main)
-                with torch.cuda.stream(self._side):
-                    prev.run(_lib.VD_STAGE_NMS)
-                cur.run(_lib.VD_STAGE_HEAD)
-                main.wait_stream(self._side)
-            self._graphs.append(g)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            main = torch.cuda.current_stream()
+            hs, ns = self._streams
+            hs.wait_stream(main)
+            ns.wait_stream(main)
+            nms_done = [None] * len(self.sessions)
+            for r in range(rotations):
+                for j, sess in enumerate(self.sessions):
+                    with torch.cuda.stream(hs):
+                        if nms_done[j] is not None:
+                            hs.wait_event(nms_done[j])            # the session's buffers are free again
+                        sess.run(_lib.VD_STAGE_HEAD)
+                        head_done = torch.cuda.Event()
+                        head_done.record(hs)
+                    with torch.cuda.stream(ns):
+                        ns.wait_event(head_done)
+                        sess.run(_lib.VD_STAGE_NMS)
+                        nms_done[j] = torch.cuda.Event()
+                        nms_done[j].record(ns)
+            main.wait_stream(hs)
+            main.wait_stream(ns)
+        self._graph = g
+        self.steps_per_cycle = rotations * len(self.sessions)
         self.launches_per_step = 2
 
-    def step(self, j):
-        self._graphs[j % len(self.sessions)].replay()
-
-    def flush(self, j):
-        """Finish batch j (its NMS stage) without starting another batch."""
-        s = self.sessions[j % len(self.sessions)]
-        s.run(_lib.VD_STAGE_NMS)
-        return s.ids, s.scores, s.bboxes
+    def cycle(self):
+        """Run rotations * len(sessions) batches, head and NMS kernels overlapped across batches."""
+        self._graph.replay()
 
 
 # ------------------------------------------------------------------------------------------------

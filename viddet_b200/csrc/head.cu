@@ -38,6 +38,7 @@ constexpr int kEpiThreads = 128;
 constexpr int A_TILE_BYTES = BLOCK_M * BLOCK_K * 2;
 
 enum { EPI_FILTER = 0, EPI_DET = 1, EPI_PRED = 2 };
+constexpr int kHeadSharedBytes = 2048;          // room for struct HeadShared (barriers, scheduler ring, per-group state)
 
 // Per-frame histogram of the emitted candidates' scores: 4096 bins, 512 per octave over [2^-7, 2).
 // Monotone in the key, so "the highest bin b* whose suffix count reaches k" gives a frame-level
@@ -68,9 +69,13 @@ struct HeadKernelParams {
     const float* bias[VD_MAX_SCALES];
     // EPI_FILTER
     float4* boxes; uint64_t* lists; uint32_t* counts; float valid_thresh; int k, cap;
+    uint32_t* counts_hi;                 // [frames][tiles] entries at the front of each list that are >= the frame's hint_hi
+    uint32_t* hint_hi;                   // [frames] key_hi below which this frame's pivot is not expected (from the previous call; any value is valid)
     unsigned long long* hints;           // [2*VD_MAX_SCALES][2] (pivot, band) warm starts, persist in the workspace across calls
-    uint32_t* hist;                      // [frames][kHistBins] score histogram of the emitted candidates (zeroed per call)
-    unsigned int* tile_counter;          // [0] next tile, [1] finished CTAs, [2] kWsMagic once the workspace is initialised; null: static round-robin
+    uint32_t* hist;                      // [frames][kHistBins] score histogram of the emitted candidates (left zeroed by the NMS kernel)
+    uint32_t* coarse;                    // [frames][64] the same histogram at 64 fine bins per bin: tiles read it for a running lower bound of the frame's k-th score
+    unsigned int* tile_counter;          // [0] next tile, [1] finished CTAs, [2] ws_magic once the workspace is in its between-calls state; null: static round-robin
+    unsigned int ws_magic;               // kWsMagic mixed with this call's workspace layout (a workspace last used with another shape is treated as uninitialised)
     long long* stamps;                   // profiling aid (VD_DEBUG_HEAD_STAMPS): clock64 per tile of CTA 0, [it][8]
     int dbg;                             // profiling aid (VD_DEBUG_SKIP_EPILOGUE=level): stop the epilogue early, results are garbage
     // EPI_DET
@@ -98,7 +103,7 @@ template <int EPI, int C, int NPAD> struct HeadCfg {
     static constexpr int THREADS = kEpiWarp0 * 32 + G * kEpiThreads;
     static constexpr int MAXREG = (THREADS > 320) ? 96 : 128;
     static constexpr int LIST_BYTES = G * LIST_BUFS * kListCap * 8;
-    static constexpr int EPI_BYTES = LIST_BYTES + CBIAS_BYTES + CONF_BYTES + VD_MAX_SCALES * NPAD * 4 + 1024;
+    static constexpr int EPI_BYTES = LIST_BYTES + CBIAS_BYTES + CONF_BYTES + VD_MAX_SCALES * NPAD * 4 + kHeadSharedBytes;
     // EPI_FILTER leaves ~45 KB of the SM's shared memory to a co-resident nms_final_hist_kernel CTA of the previous batch
     static constexpr int SMEM_BUDGET = (EPI == EPI_FILTER ? 181 : 225) * 1024;
     static constexpr int STAGES_RAW = (SMEM_BUDGET - EPI_BYTES - 1024) / STAGE_BYTES;
@@ -111,7 +116,8 @@ template <int EPI, int C, int NPAD> struct HeadCfg {
 };
 
 struct EpiGroupShared {
-    uint32_t cnt[3]; uint32_t cursor;
+    uint32_t cnt[3]; uint32_t cursor; uint32_t cursor2; uint32_t bound; uint32_t pad_[2];
+    uint32_t chist[64];                    // this tile's contribution to the frame's coarse histogram
     uint64_t guess[2 * VD_MAX_SCALES];     // warm-start pivot per (scale, full / partial pixel block)
     uint64_t band[2 * VD_MAX_SCALES];      // running estimate of the accept band's key width
 };
@@ -127,6 +133,7 @@ struct HeadShared {
 
 // named barrier 1 + grp, immediate ids: a register id makes ptxas reserve all 16 hardware barriers for the CTA,
 // which would keep any other kernel's CTA (the co-scheduled NMS kernel) off the SM
+static_assert(sizeof(HeadShared) <= kHeadSharedBytes, "HeadShared outgrew its shared-memory reservation");
 __device__ __forceinline__ void epi_bar(int grp) {
     switch (grp) {
         case 0: asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory"); break;
@@ -179,7 +186,7 @@ head_kernel(const __grid_constant__ HeadMaps maps, const __grid_constant__ HeadK
     HeadShared* sh = reinterpret_cast<HeadShared*>(sbias + VD_MAX_SCALES * NPAD);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    auto gtime = []() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return (long long)t; };
+    auto gtime = []() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t) :: "memory"); return (long long)t; };
     if (EPI == EPI_FILTER && p.stamps && threadIdx.x == 0) {
         p.stamps[4096 + blockIdx.x * 4 + 0] = gtime();
         unsigned int sm; asm volatile("mov.u32 %0, %%smid;" : "=r"(sm)); p.stamps[4096 + blockIdx.x * 4 + 3] = (long long)sm;
@@ -204,7 +211,7 @@ head_kernel(const __grid_constant__ HeadMaps maps, const __grid_constant__ HeadK
         for (int i = 0; i < G; ++i) { tc::mbar_init(&sh->tmem_full[i], 1); tc::mbar_init(&sh->tmem_empty[i], 4); }
         for (int i = 0; i < kSchedSlots; ++i) { tc::mbar_init(&sh->sched_full[i], 1); tc::mbar_init(&sh->sched_empty[i], 5); }   // consumers: MMA thread + 4 epilogue warps
         for (int g = 0; g < G; ++g) {
-            sh->grp[g].cnt[0] = sh->grp[g].cnt[1] = sh->grp[g].cnt[2] = 0; sh->grp[g].cursor = 0;
+            sh->grp[g].cnt[0] = sh->grp[g].cnt[1] = sh->grp[g].cnt[2] = 0; sh->grp[g].cursor = 0; sh->grp[g].cursor2 = 0;
             for (int i = 0; i < 2 * VD_MAX_SCALES; ++i) {
                 unsigned long long hg = 0ull, hb = 0ull;
                 if (EPI == EPI_FILTER && p.hints) { hg = p.hints[2 * i]; hb = p.hints[2 * i + 1]; }
@@ -230,7 +237,7 @@ head_kernel(const __grid_constant__ HeadMaps maps, const __grid_constant__ HeadK
             const uint64_t pol_a = tc::policy_evict_first();    // activations are read exactly once
             const uint64_t pol_w = tc::policy_evict_last();     // weights are re-read by every tile
             // claims tiles (global counter: dynamic load balance, largest tiles first) and publishes them to the other roles
-            const bool dyn = p.tile_counter != nullptr && p.tile_counter[2] == kWsMagic;   // uninitialised workspace: static round-robin
+            const bool dyn = p.tile_counter != nullptr && p.tile_counter[2] == p.ws_magic;   // uninitialised workspace: static round-robin
             auto claim = [&](uint32_t i) -> int {
                 const uint32_t t = dyn ? atomicAdd(p.tile_counter, 1u) : (uint32_t)blockIdx.x + i * gridDim.x;
                 return t < (uint32_t)p.total_tiles ? (int)t : -1;
@@ -435,7 +442,34 @@ head_kernel(const __grid_constant__ HeadMaps maps, const __grid_constant__ HeadK
                 const uint32_t lcode = cellofs << 2;                // local code of (class c, anchor a) = lcode | (c << 9) | a; key low word = ~code
                 const int slot = 2 * s + ((pblk + 1) * BLOCK_M > HW ? 1 : 0);
                 const float vth = p.valid_thresh;
-                const uint32_t floor_b = vth > 0.0f ? __float_as_uint(vth) : 0u;   // lowest threshold (float bits); 0: everything
+                // Running lower bound of the frame's k-th best score: the coarse histogram counts candidates that tiles of this
+                // frame have ALREADY emitted, so the highest coarse bin whose suffix count reaches k is a score that at least
+                // k candidates of the frame attain -- nothing below it can be in the frame's top-k.  It becomes this tile's
+                // floor ("emit everything above the floor if it fits" needs no search); any stale view of the counts is safe.
+                uint32_t floor_b = vth > 0.0f ? __float_as_uint(vth) : 0u;         // lowest threshold (float bits); 0: everything
+                if (et < 64) gs->chist[et] = 0u;
+                if (p.tile_counter[2] == p.ws_magic) {                             // (uniform) the coarse histogram started this call zeroed
+                    if (et < 32) {                                                 // one warp reads it: the whole group must agree on the floor
+                        const uint32_t* ch = p.coarse + (size_t)f * 64;
+                        const uint32_t c0 = __ldcg(ch + 63 - 2 * lane), c1 = __ldcg(ch + 62 - 2 * lane);
+                        uint32_t incl = c0 + c1;
+#pragma unroll
+                        for (int o = 1; o < 32; o <<= 1) { uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+                        const uint32_t excl = incl - (c0 + c1);
+                        const unsigned hit = __ballot_sync(0xffffffffu, incl >= (uint32_t)p.k);
+                        uint32_t bound = 0u;
+                        if (hit) {
+                            const int src = __ffs(hit) - 1;
+                            const uint32_t mybin = (excl + c0 >= (uint32_t)p.k) ? (uint32_t)(63 - 2 * lane) : (uint32_t)(62 - 2 * lane);
+                            const uint32_t bin = __shfl_sync(0xffffffffu, mybin, src);
+                            bound = hist_edge(bin << 6) & 0x7fffffffu;             // score bits of the coarse bin's lower edge
+                        }
+                        if (lane == 0) gs->bound = bound;
+                    }
+                    epi_bar(grp);
+                    const uint32_t bound = gs->bound;
+                    if (bound > floor_b) floor_b = bound;
+                }
                 constexpr uint32_t kTop = 0x3f800001u;              // > 1.0: nothing scores above it
                 constexpr int CH = Cfg::CH, CPA = Cfg::CPA, CH4 = Cfg::CH4, REM = C - (CPA - 1) * CH, NCHUNK = 3 * CPA;
                 const float* cbias = scbias + s * (3 * CPA * CH4);
@@ -572,7 +606,8 @@ head_kernel(const __grid_constant__ HeadMaps maps, const __grid_constant__ HeadK
                         const uint32_t local = ~(uint32_t)v;
                         const uint32_t row = rbase + (local >> 9) * HW3 + ((local >> 2) & 127u) * 3u + (local & 3u);
                         o = (v & 0xffffffff00000000ull) | (uint32_t)(~row);
-                        if (p.dbg != 5) atomicAdd(&p.hist[(size_t)f * kHistBins + hist_bin((uint32_t)(v >> 32))], 1u);
+                        const uint32_t hb = hist_bin((uint32_t)(v >> 32));
+                        if (p.dbg != 5) { atomicAdd(&p.hist[(size_t)f * kHistBins + hb], 1u); atomicAdd(&gs->chist[hb >> 6], 1u); }
                     }
                     if (p.dbg != 6) gl[j] = o;
                 };
@@ -585,9 +620,9 @@ head_kernel(const __grid_constant__ HeadMaps maps, const __grid_constant__ HeadK
                 if (piv > kTop) piv = kTop;
                 uint32_t lo = floor_b, hi = kTop, step = band_w;
                 bool have_lo = false, have_hi = false, exact = false;
-                uint32_t list_n = 0, t_acc = 0, my_cnt = 0;
+                uint32_t list_n = 0, list_hi = 0, t_acc = 0, my_cnt = 0;
                 uint64_t piv64 = 0ull, lo64 = 0ull, hi64 = 0ull;
-                if (et == 0) gs->cursor = 0;                        // ordered before the first bump by the barrier inside epi_sum
+                if (et == 0) { gs->cursor = 0; gs->cursor2 = 0; }   // ordered before the first bump by the barrier inside epi_sum
 #pragma unroll 1
                 for (int g = 0; g < 200; ++g) {
                     if (!exact) {
@@ -606,24 +641,42 @@ head_kernel(const __grid_constant__ HeadMaps maps, const __grid_constant__ HeadK
                             sweep_fast(std::true_type{}, L + lb0);
                             if (stamp) p.stamps[it * 16 + 12] = clock64(); // stage sweep done
                             epi_bar(grp);                           // staging complete
+                            // score; split the list at the frame's hint: keys >= hint_hi go to the front, so the NMS kernel
+                            // reads only the fronts when its pivot is at or above the hint (the usual case)
                             constexpr int KPT = kListCap / kEpiThreads;
+                            const uint32_t thk = p.hint_hi[f];
                             uint64_t key[KPT];
-                            uint32_t ne = 0u;
+                            uint32_t off[KPT];                      // bit 31: front part; low bits: offset inside this warp's share of the part
+                            uint32_t ne = 0u, nh = 0u, wh = 0u, wl = 0u;
 #pragma unroll
                             for (int u = 0; u < KPT; ++u) {
                                 const uint32_t j = (uint32_t)(u * kEpiThreads + et);
-                                key[u] = 0ull;
-                                if (j < t) {
-                                    const uint64_t e = L[j];
-                                    const uint32_t code = (uint32_t)e;
-                                    const float sc = vd_score(__uint_as_float((uint32_t)(e >> 32)), cf[((code >> 2) & 127u) * 3u + (code & 3u)]);
-                                    const uint32_t kh = (sc > vth) ? (__float_as_uint(sc) | 0x80000000u) : 0u;
-                                    key[u] = kh ? (((uint64_t)kh << 32) | (uint32_t)~code) : 0ull;
-                                    ne += (kh >= ph) ? 1u : 0u;
+                                key[u] = 0ull; off[u] = 0u;
+                                if ((uint32_t)(u * kEpiThreads) < t) {      // group-uniform
+                                    const bool have = j < t;
+                                    uint32_t kh = 0u;
+                                    if (have) {
+                                        const uint64_t e = L[j];
+                                        const uint32_t code = (uint32_t)e;
+                                        const float sc = vd_score(__uint_as_float((uint32_t)(e >> 32)), cf[((code >> 2) & 127u) * 3u + (code & 3u)]);
+                                        kh = (sc > vth) ? (__float_as_uint(sc) | 0x80000000u) : 0u;
+                                        key[u] = kh ? (((uint64_t)kh << 32) | (uint32_t)~code) : 0ull;
+                                        ne += (kh >= ph) ? 1u : 0u;
+                                    }
+                                    const bool hi = have && kh != 0u && kh >= thk;
+                                    const unsigned bh = __ballot_sync(0xffffffffu, hi), bl = __ballot_sync(0xffffffffu, have && !hi);
+                                    const unsigned lt = (1u << lane) - 1u;
+                                    off[u] = hi ? (0x80000000u | (wh + (uint32_t)__popc(bh & lt))) : (wl + (uint32_t)__popc(bl & lt));
+                                    wh += (uint32_t)__popc(bh); wl += (uint32_t)__popc(bl);
+                                    nh += hi ? 1u : 0u;
                                 }
                             }
+                            uint32_t wbase = 0u;
+                            if (lane == 0) wbase = atomicAdd(&gs->cursor2, wh | (wl << 16));   // this warp's share of the front / back parts
+                            wbase = __shfl_sync(0xffffffffu, wbase, 0);
                             if (stamp) p.stamps[it * 16 + 13] = clock64(); // scored
-                            const uint32_t t2 = epi_sum(ne, gs, grp, et, sum_it);
+                            const uint32_t t2p = epi_sum(ne | (nh << 16), gs, grp, et, sum_it);
+                            const uint32_t t2 = t2p & 0xffffu, th = t2p >> 16;
                             if (p.dbg == 4) { release_tmem(); break; }
                             if (t2 >= k || piv == floor_b) {
                                 release_tmem();
@@ -631,12 +684,16 @@ head_kernel(const __grid_constant__ HeadMaps maps, const __grid_constant__ HeadK
 #pragma unroll
                                 for (int u = 0; u < KPT; ++u) {
                                     const uint32_t j = (uint32_t)(u * kEpiThreads + et);
-                                    if (j < t) flush_one(j, key[u]);
+                                    if (j < t) {
+                                        const uint32_t o = off[u] & 0x7fffffffu;
+                                        flush_one((off[u] >> 31) ? (wbase & 0xffffu) + o : th + (wbase >> 16) + o, key[u]);
+                                    }
                                 }
-                                list_n = t; t_acc = t2;
+                                list_n = t; t_acc = t2; list_hi = th;
                                 if (stamp) p.stamps[it * 16 + 14] = clock64(); // flushed
                                 break;
                             }
+                            if (et == 0) gs->cursor2 = 0;
                             // margin ate the k-th candidates (tie cluster right at the threshold): exact search just below
                             if (et == 0) gs->cursor = 0;
                             exact = true;
@@ -677,7 +734,7 @@ head_kernel(const __grid_constant__ HeadMaps maps, const __grid_constant__ HeadK
                             sweep_exact(std::true_type{}, L + pc, L + kListCap, piv64);
                             release_tmem();
                             epi_bar(grp);                           // list complete
-                            list_n = t < (uint32_t)kListCap ? t : (uint32_t)kListCap; t_acc = t;
+                            list_n = t < (uint32_t)kListCap ? t : (uint32_t)kListCap; t_acc = t; list_hi = list_n;   // no split: everything counts as front
                             for (uint32_t j = et; j < list_n; j += kEpiThreads) flush_one(j, L[j]);
                             piv = (uint32_t)(piv64 >> 32) & 0x7fffffffu;
                             break;
@@ -688,7 +745,7 @@ head_kernel(const __grid_constant__ HeadMaps maps, const __grid_constant__ HeadK
                 }
                 // ---- retarget the warm start towards the band centre
                 if (et == 0) {
-                    p.counts[li] = list_n;
+                    p.counts[li] = list_n; p.counts_hi[li] = list_hi;
                     if (piv > floor_b) {
                         const uint32_t q4 = (cap - k) / 4u, nudge = band_w >> 3;
                         uint32_t g2 = piv;
@@ -699,17 +756,19 @@ head_kernel(const __grid_constant__ HeadMaps maps, const __grid_constant__ HeadK
                     }
                 }
                 epi_bar(grp);                                       // list buffer / cursor / conf table / guess slots are reused by the next tile
+                if (et < 64) { const uint32_t cc = gs->chist[et]; if (cc) atomicAdd(&p.coarse[(size_t)f * 64 + et], cc); }
                 if (stamp) p.stamps[it * 16 + 7] = clock64();
             }
         }
     }
 
     // ---------------- teardown
+    __syncwarp();                // warps 0 / 1 ran single-lane role loops: reconverge before the aligned CTA barrier
     tc::fence_before_sync();
     __syncthreads();
     if (EPI == EPI_FILTER && p.stamps && threadIdx.x == 0) p.stamps[4096 + blockIdx.x * 4 + 2] = gtime();
     if (warp == 1) tc::tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
-    if (threadIdx.x == 0 && p.tile_counter != nullptr && p.tile_counter[2] == kWsMagic) {
+    if (threadIdx.x == 0 && p.tile_counter != nullptr && p.tile_counter[2] == p.ws_magic) {
         // last CTA out re-arms the scheduler for the next launch on this workspace
         __threadfence();
         if (atomicAdd(&p.tile_counter[1], 1u) == gridDim.x - 1u) { p.tile_counter[0] = 0u; p.tile_counter[1] = 0u; }
@@ -865,8 +924,9 @@ __device__ void nms_tail_wave(const int n, const int f, const NmsParams P, const
 // NEXT batch (256 threads, <= 64 registers, ~41 KB shared): the step pipeline overlaps the two.
 // The kernel leaves its frame's histogram zeroed for the next call (no memset node per call).
 __global__ void __maxnreg__(56)
-nms_final_hist_kernel(const uint64_t* __restrict__ lists, const uint32_t* __restrict__ counts, int n_lists,
-                      uint32_t* __restrict__ hist, unsigned int* __restrict__ ctr, NmsParams P, FusedSource src, FusedSink sink) {
+nms_final_hist_kernel(const uint64_t* __restrict__ lists, const uint32_t* __restrict__ counts, const uint32_t* __restrict__ counts_hi,
+                      uint32_t* __restrict__ hint_hi, uint32_t* __restrict__ coarse, int n_lists,
+                      uint32_t* __restrict__ hist, unsigned int* __restrict__ ctr, unsigned int ws_magic, NmsParams P, FusedSource src, FusedSink sink) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
     const int k = P.k;
@@ -880,16 +940,17 @@ nms_final_hist_kernel(const uint64_t* __restrict__ lists, const uint32_t* __rest
     int* skcls = reinterpret_cast<int*>(skarea + KMAX);
     int* scls = skcls + KMAX;
     float* sarea = reinterpret_cast<float*>(scls + k);
-    uint32_t* scount = reinterpret_cast<uint32_t*>(sarea + k);         // [256] clamped list lengths
-    WaveShared* wsh = reinterpret_cast<WaveShared*>(scount + 256);
-    lists += (size_t)f * n_lists * kListCap; counts += (size_t)f * n_lists; hist += (size_t)f * kHistBins;
+    uint32_t* scount = reinterpret_cast<uint32_t*>(sarea + k);         // [2][256] list lengths to stream / full lengths
+    WaveShared* wsh = reinterpret_cast<WaveShared*>(scount + 512);
+    lists += (size_t)f * n_lists * kListCap; counts += (size_t)f * n_lists; counts_hi += (size_t)f * n_lists; hist += (size_t)f * kHistBins;
 
     VD_STAMP(P, 0);
     if (P.dbg && tid == 0) {
-        unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t) :: "memory");
         unsigned int sm; asm volatile("mov.u32 %0, %%smid;" : "=r"(sm));
         P.dbg[8192 + f * 4 + 0] = (long long)t; P.dbg[8192 + f * 4 + 2] = (long long)sm;
     }
+    if (tid < 64) coarse[(size_t)f * 64 + tid] = 0u;
     select_scratch_init(scr);
     // ---- 1. suffix scan of the histogram; thread t owns bins [4095-16t-15, 4095-16t], highest first.
     //         The bins are zeroed behind the read: the next call's head kernel accumulates from zero.
@@ -938,7 +999,17 @@ nms_final_hist_kernel(const uint64_t* __restrict__ lists, const uint32_t* __rest
         }
         return block_sum(c, scr, it);
     };
-    for (int l = tid; l < n_lists; l += blockDim.x) { uint32_t n = counts[l]; scount[l] = n > (uint32_t)kListCap ? (uint32_t)kListCap : n; }
+    // lists are split at hint_hi: every key >= hint_hi sits in the first counts_hi entries.  A pivot at or above the
+    // hint needs only those fronts; the hint for the next call trails this frame's pivot by 16 bins (~2 % in score).
+    const uint32_t hint_used = hint_hi[f];
+    const bool fronts_only = (uint32_t)(piv >> 32) >= hint_used && cnt <= (uint32_t)kHistCap;
+    for (int l = tid; l < n_lists; l += blockDim.x) {
+        uint32_t n = counts[l]; n = n > (uint32_t)kListCap ? (uint32_t)kListCap : n;
+        uint32_t nh = counts_hi[l]; nh = nh > n ? n : nh;
+        scount[l] = fronts_only ? nh : n;
+        if (fronts_only) scount[256 + l] = n;
+    }
+    if (tid == 0) hint_hi[f] = hist_edge(bstar > 16u ? bstar - 16u : 0u);
     int sit = 0;
     uint32_t m = 0u;
     for (int attempt = 0; attempt < 2; ++attempt) {
@@ -986,6 +1057,7 @@ nms_final_hist_kernel(const uint64_t* __restrict__ lists, const uint32_t* __rest
         m = scr->out_count;
         // a clean histogram guarantees m >= k whenever a positive pivot was chosen; otherwise redo exactly
         if (m >= (uint32_t)k || piv <= 1ull || attempt == 1) break;
+        if (fronts_only) { for (int l = tid; l < n_lists; l += blockDim.x) scount[l] = scount[256 + l]; }   // the exact retry reads whole lists
     }
     VD_STAMP(P, 2);
     m = m > (uint32_t)kHistCap ? (uint32_t)kHistCap : m;
@@ -996,12 +1068,12 @@ nms_final_hist_kernel(const uint64_t* __restrict__ lists, const uint32_t* __rest
     VD_STAMP(P, 3);
     const int n = (int)(m < (uint32_t)k ? m : (uint32_t)k);
     nms_tail_wave(n, f, P, src, sink, skeys, sbox, scls, sarea, skbox, skarea, skcls, wsh);
-    if (f == 0 && tid == 0) { ctr[0] = 0u; ctr[1] = 0u; ctr[2] = kWsMagic; }   // workspace is in its between-calls state
-    if (P.dbg && tid == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); P.dbg[8192 + f * 4 + 1] = (long long)t; }
+    if (f == 0 && tid == 0) { ctr[0] = 0u; ctr[1] = 0u; ctr[2] = ws_magic; }   // workspace is in its between-calls state (for this layout)
+    if (P.dbg && tid == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t) :: "memory"); P.dbg[8192 + f * 4 + 1] = (long long)t; }
 }
 static size_t nms_hist_smem(int k, int max_out) {
     const size_t kmax = (size_t)(max_out < k ? max_out : k) + 32 + 4 * (kNmsThreads / 32);
-    return 256 + (size_t)kHistCap * 8 + (size_t)k * 16 + kmax * 24 + (size_t)k * 8 + 256 * 4 + sizeof(WaveShared) + 64;
+    return 256 + (size_t)kHistCap * 8 + (size_t)k * 16 + kmax * 24 + (size_t)k * 8 + 512 * 4 + sizeof(WaveShared) + 64;
 }
 
 // no-NMS tail (yolo3.py:525 false): rows are the plain concat; only reachable through vd_head_detections.
@@ -1013,7 +1085,7 @@ struct HeadPlan {
     HeadKernelParams kp;
     int n_pad, C;
     int merge_levels;
-    size_t off_hints, off_ctr, off_hist, off_boxes, off_lists0, off_counts0, off_listsA, off_listsB, off_countsA, off_countsB, total;
+    size_t off_hints, off_ctr, off_hist, off_boxes, off_lists0, off_counts0, off_counts_hi, off_hint_hi, off_coarse, off_listsA, off_listsB, off_countsA, off_countsB, total;
 };
 
 static int head_npad(int C) { int n = 3 * (5 + C); return (n + 15) / 16 * 16; }
@@ -1071,6 +1143,9 @@ static int make_plan(const VdHeadParams* hp, HeadPlan* pl) {
     pl->off_boxes = off; off += align_up(F * anc * 16, 256);
     pl->off_lists0 = off; off += align_up(F * tif * kListCap * 8, 256);
     pl->off_counts0 = off; off += align_up(F * tif * 4, 256);
+    pl->off_counts_hi = off; off += align_up(F * tif * 4, 256);
+    pl->off_hint_hi = off; off += align_up(F * 4, 256);
+    pl->off_coarse = off; off += align_up(F * 64 * 4, 256);
     int n1 = ceil_div(tif, kMaxLists);
     pl->off_listsA = off; off += align_up(F * n1 * kListCap * 8, 256);
     pl->off_listsB = off; off += align_up(F * n1 * kListCap * 8, 256);
@@ -1106,7 +1181,7 @@ static int launch_head_t(const HeadMaps& maps, const HeadKernelParams& kp, cudaS
     static bool configured = false;                 // once per instantiation (also keeps graph capture clean)
     if (!configured) {
         VD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-        VD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));   // same carve-out as the NMS kernel: CTAs of both can share an SM
+        if (!getenv("VD_DEBUG_NO_CARVEOUT")) VD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));   // same carve-out as the NMS kernel: CTAs of both can share an SM
         configured = true;
     }
     int grid = sm_count(); if (grid > kp.total_tiles) grid = kp.total_tiles;
@@ -1204,9 +1279,13 @@ extern "C" int vd_head_forward_stages(const VdHeadParams* hp, float* ids, float*
     kp.hints = (unsigned long long*)(ws + pl.off_hints);
     kp.hist = (uint32_t*)(ws + pl.off_hist);
     kp.tile_counter = (unsigned int*)(ws + pl.off_ctr);
+    kp.ws_magic = kWsMagic ^ (unsigned int)(pl.total * 2654435761u) ^ ((unsigned int)hp->frames << 20) ^ ((unsigned int)kp.tiles_per_frame << 8);
     kp.boxes = (float4*)(ws + pl.off_boxes);
     kp.lists = (uint64_t*)(ws + pl.off_lists0);
     kp.counts = (uint32_t*)(ws + pl.off_counts0);
+    kp.counts_hi = (uint32_t*)(ws + pl.off_counts_hi);
+    kp.hint_hi = (uint32_t*)(ws + pl.off_hint_hi);
+    kp.coarse = (uint32_t*)(ws + pl.off_coarse);
     kp.valid_thresh = hp->valid_thresh; kp.k = k; kp.cap = (k <= 448) ? 640 : kListCap;
     kp.stamps = getenv("VD_DEBUG_HEAD_STAMPS") ? (long long*)(ws + pl.off_listsA) : nullptr;   // profiling aid (unused merge area)
     if (const char* e = getenv("VD_DEBUG_SKIP_EPILOGUE")) kp.dbg = atoi(e);     // profiling aid: results are garbage
@@ -1241,10 +1320,10 @@ extern "C" int vd_head_forward_stages(const VdHeadParams* hp, float* ids, float*
     static bool configured = false;
     if (!configured) {
         VD_CUDA(cudaFuncSetAttribute(nms_final_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)nms_hist_smem(VD_MAX_TOPK, VD_MAX_TOPK)));
-        VD_CUDA(cudaFuncSetAttribute(nms_final_hist_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        if (!getenv("VD_DEBUG_NO_CARVEOUT") || atoi(getenv("VD_DEBUG_NO_CARVEOUT")) == 2) VD_CUDA(cudaFuncSetAttribute(nms_final_hist_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         configured = true;
     }
-    nms_final_hist_kernel<<<hp->frames, kNmsThreads, nms_hist_smem(k, hp->post_nms), stream>>>(kp.lists, kp.counts, kp.tiles_per_frame, kp.hist, kp.tile_counter, P, src, sink);
+    nms_final_hist_kernel<<<hp->frames, kNmsThreads, nms_hist_smem(k, hp->post_nms), stream>>>(kp.lists, kp.counts, kp.counts_hi, kp.hint_hi, kp.coarse, kp.tiles_per_frame, kp.hist, kp.tile_counter, kp.ws_magic, P, src, sink);
     VD_LAUNCH_CHECK();
     return VD_OK;
 }

@@ -163,6 +163,7 @@ temporal_conv_kernel(const __grid_constant__ TConvMaps maps, const __grid_consta
             if (lane == 0) tc::mbar_arrive(&sh->tmem_empty[buf]);
         }
     }
+    __syncwarp();                // warps 0 / 1 ran single-lane role loops: reconverge before the aligned CTA barrier
     tc::fence_before_sync();
     __syncthreads();
     if (warp == 1) tc::tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);

@@ -35,6 +35,22 @@ def timeit(fn, n=50, warm=5):
     return e0.elapsed_time(e1) / n          # ms
 
 
+def event_pairs(sessions, n, stages):
+    """Median CUDA-event time of each stage inside real calls (stages of a call run back to back, state stays steady)."""
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(len(stages) + 1)] for _ in range(n)]
+    for i in range(4):
+        sessions[i % len(sessions)].run()
+    torch.cuda.synchronize()
+    for i in range(n):
+        s = sessions[i % len(sessions)]
+        evs[i][0].record()
+        for k, st in enumerate(stages):
+            s.run(st)
+            evs[i][k + 1].record()
+    torch.cuda.synchronize()
+    return [sorted(e[k].elapsed_time(e[k + 1]) for e in evs)[n // 2] for k in range(len(stages))]
+
+
 def head_cfg(name):
     C, size, frames = bench.WORKLOADS[name]
     gen = torch.Generator(device=dev).manual_seed(1234)
@@ -43,12 +59,13 @@ def head_cfg(name):
     sessions = [head.session(bench.synth_tips(torch, gen, frames, size, dev)) for _ in range(nrot)]
     for s in sessions:
         s.capture()
+    pipe = viddet_b200.HeadPipeline(sessions, rotations=4)
     alg = bench.algorithmic_bytes_per_frame(C, size) * frames
     flops = 2.0 * 3 * (5 + C) * sum((size // st) ** 2 * c for st, c in zip(bench.STRIDES, bench.CHANNELS)) * frames
-    t_head = timeit(lambda i: sessions[i % nrot].run(_lib.VD_STAGE_HEAD))
-    t_nms = timeit(lambda i: sessions[i % nrot].run(_lib.VD_STAGE_NMS))
+    t_head, t_nms = event_pairs(sessions, 30, [_lib.VD_STAGE_HEAD, _lib.VD_STAGE_NMS])
     t_all = timeit(lambda i: sessions[i % nrot].replay())
-    for label, t in (("head_kernel", t_head), ("nms_kernel", t_nms), ("step(graph)", t_all)):
+    t_pipe = timeit(lambda i: pipe.cycle(), n=10, warm=2) / pipe.steps_per_cycle
+    for label, t in (("head_kernel (events, in real calls)", t_head), ("nms_kernel (events, in real calls)", t_nms), ("step (serial graph)", t_all), ("step (pipelined graph)", t_pipe)):
         print(json.dumps({"cfg": name, "what": label, "ms": t, "frames_per_s": frames / (t * 1e-3),
                           "alg_GBps": alg / (t * 1e-3) / 1e9, "hbm_frac": alg / (t * 1e-3) / 1e9 / PEAK_HBM,
                           "tflops": flops / (t * 1e-3) / 1e12, "tensor_frac": flops / (t * 1e-3) / 1e12 / PEAK_TC}))
@@ -72,9 +89,7 @@ def vid_temporal(windows=64, T=5, C=30, size=416, nrot=2):
     hw_c = sum((size // s) ** 2 * c for s, c in zip(bench.STRIDES, bench.CHANNELS))
     f_tconv = 2.0 * (3 * T - 2) * hw_c2 * windows
     f_pred = 2.0 * 3 * (5 + C) * hw_c * T * windows
-    t_tc = timeit(lambda i: sessions[i % nrot].run(_lib.VD_STAGE_TCONV), n=10, warm=2)
-    t_head = timeit(lambda i: sessions[i % nrot].run(_lib.VD_STAGE_HEAD), n=10, warm=2)
-    t_nms = timeit(lambda i: sessions[i % nrot].run(_lib.VD_STAGE_NMS), n=10, warm=2)
+    t_tc, t_head, t_nms = event_pairs(sessions, 10, [_lib.VD_STAGE_TCONV, _lib.VD_STAGE_HEAD, _lib.VD_STAGE_NMS])
     t_all = timeit(lambda i: sessions[i % nrot].run(), n=10, warm=2)
     print(json.dumps({"cfg": "vid416_T5_w%d" % windows, "what": "temporal_conv x3", "ms": t_tc,
                       "tflops": f_tconv / (t_tc * 1e-3) / 1e12, "tensor_frac": f_tconv / (t_tc * 1e-3) / 1e12 / PEAK_TC}))

@@ -87,10 +87,8 @@ struct HeadKernelParams {
 struct HeadMaps { CUtensorMap a[VD_MAX_SCALES]; CUtensorMap w[VD_MAX_SCALES]; };
 
 template <int EPI, int C, int NPAD> struct HeadCfg {
-    static constexpr int CPA = (C + 31) / 32;                  // TMEM read chunks per anchor (<= 32 class logits each)
+    static constexpr int CPA = (C + 15) / 16;                  // TMEM read chunks per anchor (<= 16 class logits each: 3 x 16 live registers)
     static constexpr int CH = (C + CPA - 1) / CPA;
-    // small heads (VOC: 75 columns): the whole accumulator row lives in registers, TMEM is handed back right after one load
-    static constexpr bool REGS = false && (EPI == EPI_FILTER) && (3 * (5 + C) <= 80);   // (register-resident variant spills at 128 registers: off)
     static constexpr int CH4 = (CH + 3) / 4 * 4;               // class-bias chunk padded for 128-bit shared loads
     static constexpr int CBIAS_BYTES = (EPI == EPI_FILTER) ? VD_MAX_SCALES * 3 * CPA * CH4 * 4 : 0;
     static constexpr int CONF_BYTES = (EPI == EPI_FILTER) ? kMaxEpiGroups * 3 * kEpiThreads * 4 : 0;
@@ -99,9 +97,9 @@ template <int EPI, int C, int NPAD> struct HeadCfg {
     static constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
     static constexpr int TMEM_STRIDE = NPAD <= 128 ? 128 : 256;
     // 3 groups (12 epilogue warps, 128 registers/thread) when three accumulators fit TMEM; else 2 groups
-    static constexpr int G = (EPI == EPI_FILTER && TMEM_STRIDE == 128) ? 3 : 2;
+    static constexpr int G = (EPI == EPI_FILTER && TMEM_STRIDE == 128) ? (NPAD <= 80 ? 4 : 3) : 2;   // 4 groups only where 80 registers suffice
     static constexpr int THREADS = kEpiWarp0 * 32 + G * kEpiThreads;
-    static constexpr int MAXREG = (THREADS > 320) ? 96 : 128;
+    static constexpr int MAXREG = (THREADS > 448) ? 80 : ((THREADS > 320) ? 96 : 128);
     static constexpr int LIST_BYTES = G * LIST_BUFS * kListCap * 8;
     static constexpr int EPI_BYTES = LIST_BYTES + CBIAS_BYTES + CONF_BYTES + VD_MAX_SCALES * NPAD * 4 + kHeadSharedBytes;
     // EPI_FILTER leaves ~45 KB of the SM's shared memory to a co-resident nms_final_hist_kernel CTA of the previous batch
@@ -116,7 +114,7 @@ template <int EPI, int C, int NPAD> struct HeadCfg {
 };
 
 struct EpiGroupShared {
-    uint32_t cnt[3]; uint32_t cursor; uint32_t cursor2; uint32_t bound; uint32_t pad_[2];
+    uint32_t cnt[3]; uint32_t cursor; uint32_t cursor2; uint32_t bound; uint32_t pcur[3];
     uint32_t chist[64];                    // this tile's contribution to the frame's coarse histogram
     uint64_t guess[2 * VD_MAX_SCALES];     // warm-start pivot per (scale, full / partial pixel block)
     uint64_t band[2 * VD_MAX_SCALES];      // running estimate of the accept band's key width
@@ -211,7 +209,7 @@ head_kernel(const __grid_constant__ HeadMaps maps, const __grid_constant__ HeadK
         for (int i = 0; i < G; ++i) { tc::mbar_init(&sh->tmem_full[i], 1); tc::mbar_init(&sh->tmem_empty[i], 4); }
         for (int i = 0; i < kSchedSlots; ++i) { tc::mbar_init(&sh->sched_full[i], 1); tc::mbar_init(&sh->sched_empty[i], 5); }   // consumers: MMA thread + 4 epilogue warps
         for (int g = 0; g < G; ++g) {
-            sh->grp[g].cnt[0] = sh->grp[g].cnt[1] = sh->grp[g].cnt[2] = 0; sh->grp[g].cursor = 0; sh->grp[g].cursor2 = 0;
+            sh->grp[g].cnt[0] = sh->grp[g].cnt[1] = sh->grp[g].cnt[2] = 0; sh->grp[g].cursor = 0; sh->grp[g].cursor2 = 0; sh->grp[g].pcur[0] = sh->grp[g].pcur[1] = sh->grp[g].pcur[2] = 0;
             for (int i = 0; i < 2 * VD_MAX_SCALES; ++i) {
                 unsigned long long hg = 0ull, hb = 0ull;
                 if (EPI == EPI_FILTER && p.hints) { hg = p.hints[2 * i]; hb = p.hints[2 * i + 1]; }
@@ -313,6 +311,9 @@ head_kernel(const __grid_constant__ HeadMaps maps, const __grid_constant__ HeadK
         int sum_it = 0;
         (void)gs; (void)L; (void)sum_it; (void)et;
         uint32_t it = (uint32_t)grp;
+        bool ws_ok = false;                                   // the workspace's histograms started this call zeroed (layout marker intact)
+        if constexpr (EPI == EPI_FILTER) ws_ok = p.tile_counter[2] == p.ws_magic;
+        (void)ws_ok;
         for (;; it += G) {
             const uint32_t slot = it % kSchedSlots;
             tc::mbar_wait(&sh->sched_full[slot], (it / kSchedSlots) & 1u);
@@ -329,6 +330,12 @@ head_kernel(const __grid_constant__ HeadMaps maps, const __grid_constant__ HeadK
             const float* bias = sbias + s * NPAD;
             const bool stamp = (EPI == EPI_FILTER) && p.stamps && blockIdx.x == 0 && et == 0 && it < 250u;
             if (stamp) p.stamps[it * 16 + 3] = clock64();
+            // global reads of the selection issued before the wait for the accumulator (their latency hides behind it)
+            uint32_t pf_c0 = 0u, pf_c1 = 0u, pf_hint = 0u;
+            if constexpr (EPI == EPI_FILTER) {
+                if (ws_ok && et < 32) { const uint32_t* ch = p.coarse + (size_t)f * 64; pf_c0 = __ldcg(ch + 63 - 2 * lane); pf_c1 = __ldcg(ch + 62 - 2 * lane); }
+                pf_hint = __ldg(p.hint_hi + f);
+            }
             tc::mbar_wait(&sh->tmem_full[buf], (it / (uint32_t)G) & 1u);
             tc::fence_after_sync();
             if (stamp) p.stamps[it * 16 + 4] = clock64();
@@ -362,23 +369,10 @@ head_kernel(const __grid_constant__ HeadMaps maps, const __grid_constant__ HeadK
 
             // ---- per-anchor box + objectness (yolo3.py:172-177)
             float conf[3];
-            constexpr int NACC = Cfg::REGS ? 3 * P : 1;
-            uint32_t acc[NACC];                                   // REGS: the pixel's whole accumulator row
             uint32_t rb[3][5];
-            if constexpr (Cfg::REGS) {
-                tc::tmem_ld<3 * P>(tbase, acc); tc::tmem_ld_wait();
-                tc::fence_before_sync();                           // accumulator copied out: hand TMEM back at once
-                __syncwarp();
-                if (lane == 0) tc::mbar_arrive(&sh->tmem_empty[buf]);
 #pragma unroll
-                for (int a = 0; a < 3; ++a)
-#pragma unroll
-                    for (int i = 0; i < 5; ++i) rb[a][i] = acc[a * P + i];
-            } else {
-#pragma unroll
-                for (int a = 0; a < 3; ++a) tc::tmem_ld<5>(tbase + a * P, rb[a]);
-                tc::tmem_ld_wait();
-            }
+            for (int a = 0; a < 3; ++a) tc::tmem_ld<5>(tbase + a * P, rb[a]);
+            tc::tmem_ld_wait();
 #pragma unroll
             for (int a = 0; a < 3; ++a) {
                 const uint32_t* r = rb[a];
@@ -436,7 +430,7 @@ head_kernel(const __grid_constant__ HeadMaps maps, const __grid_constant__ HeadK
                 //   sweep 2  stage P's (logit, local code) at exact list positions (predicated stores)
                 //   score    the staged entries, 128 threads striding the list (balanced), keys kept in registers
                 //   flush    keys -> global tile list (true row restored) + per-frame score histogram
-                if (p.dbg == 2) { if constexpr (!Cfg::REGS) { tc::fence_before_sync(); __syncwarp(); if (lane == 0) tc::mbar_arrive(&sh->tmem_empty[buf]); } continue; }
+                if (p.dbg == 2) { tc::fence_before_sync(); __syncwarp(); if (lane == 0) tc::mbar_arrive(&sh->tmem_empty[buf]); continue; }
                 const uint32_t k = (uint32_t)p.k, cap = (uint32_t)p.cap;
                 const uint32_t cellofs = (uint32_t)(q * 32 + lane);
                 const uint32_t lcode = cellofs << 2;                // local code of (class c, anchor a) = lcode | (c << 9) | a; key low word = ~code
@@ -448,10 +442,9 @@ head_kernel(const __grid_constant__ HeadMaps maps, const __grid_constant__ HeadK
                 // floor ("emit everything above the floor if it fits" needs no search); any stale view of the counts is safe.
                 uint32_t floor_b = vth > 0.0f ? __float_as_uint(vth) : 0u;         // lowest threshold (float bits); 0: everything
                 if (et < 64) gs->chist[et] = 0u;
-                if (p.tile_counter[2] == p.ws_magic) {                             // (uniform) the coarse histogram started this call zeroed
+                if (ws_ok) {                                                       // (uniform) the coarse histogram started this call zeroed
                     if (et < 32) {                                                 // one warp reads it: the whole group must agree on the floor
-                        const uint32_t* ch = p.coarse + (size_t)f * 64;
-                        const uint32_t c0 = __ldcg(ch + 63 - 2 * lane), c1 = __ldcg(ch + 62 - 2 * lane);
+                        const uint32_t c0 = pf_c0, c1 = pf_c1;
                         uint32_t incl = c0 + c1;
 #pragma unroll
                         for (int o = 1; o < 32; o <<= 1) { uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
@@ -494,13 +487,14 @@ head_kernel(const __grid_constant__ HeadMaps maps, const __grid_constant__ HeadK
                     const uint32_t col = tbase + (uint32_t)(a * P + 5 + cc * CH);
                     if (REM != CH && cc == CPA - 1) tc::tmem_ld<REM>(col, r); else tc::tmem_ld<CH>(col, r);
                 };
-                // fast sweep over the class logits in TMEM (next chunk's load in flight while this one is compared):
-                // STAGE = false: returns |P_thread|;  STAGE = true: stores P_thread's (logit, code) entries at wp
-                auto sweep_fast = [&](auto stage_tag, uint64_t* wp) -> uint32_t {
-                    constexpr bool STAGE = decltype(stage_tag)::value;
-                    uint32_t cnt = 0u, cnt2 = 0u;
-                    uint32_t r[2][Cfg::REGS ? 1 : CH];
-                    if constexpr (!Cfg::REGS) issue(0, r[0]);
+                // fast sweep: ONE pass over the class logits in TMEM (next chunk's load in flight while this one is compared).
+                // Per chunk a thread counts its passers, the warp scans the counts and reserves a range of the group's list
+                // with one shared-memory atomic, and the passers' (logit, code) entries are stored from the registers that
+                // still hold them.  The list is speculative: the caller accepts it iff the final cursor is inside the band.
+                const uint32_t L_s = tc::smem_u32(L);
+                auto sweep_fast = [&](uint32_t* cursor) {
+                    uint32_t r[2][CH];
+                    issue(0, r[0]);
 #pragma unroll
                     for (int j = 0; j < NCHUNK; ++j) {
                         const int a = j / CPA, cc = j - a * CPA;
@@ -509,51 +503,46 @@ head_kernel(const __grid_constant__ HeadMaps maps, const __grid_constant__ HeadK
 #pragma unroll
                         for (int i = 0; i < CH4; i += 4)
                             *reinterpret_cast<float4*>(bv + i) = *reinterpret_cast<const float4*>(cbias + (a * CPA + cc) * CH4 + i);
-                        if constexpr (!Cfg::REGS) {
-                            tc::tmem_ld_wait();
-                            if (j + 1 < NCHUNK) issue(j + 1, r[(j + 1) & 1]);
-                        }
+                        tc::tmem_ld_wait();
+                        if (j + 1 < NCHUNK) issue(j + 1, r[(j + 1) & 1]);
                         const float la = ell[a];
+                        uint32_t c0 = 0u, c1 = 0u;
 #pragma unroll
                         for (int i = 0; i < CH; ++i) {
                             if (i < n) {
-                                uint32_t raw;
-                                if constexpr (Cfg::REGS) raw = acc[a * P + 5 + cc * CH + i]; else raw = r[j & 1][i];
-                                const float x = __fadd_rn(__uint_as_float(raw), bv[i]);
-                                const bool pass = x >= la;
-                                if constexpr (!STAGE) {
-                                    if (i & 1) cnt2 += pass ? 1u : 0u; else cnt += pass ? 1u : 0u;
-                                } else {
-                                    const uint32_t code = lcode | (((uint32_t)(cc * CH + i)) << 9) | (uint32_t)a;
-                                    if (pass) *wp = ((uint64_t)__float_as_uint(x) << 32) | code;
-                                    wp += pass ? 1 : 0;
+                                bv[i] = __fadd_rn(__uint_as_float(r[j & 1][i]), bv[i]);      // the logit, kept for the stores below
+                                if (i & 1) c1 += (bv[i] >= la) ? 1u : 0u; else c0 += (bv[i] >= la) ? 1u : 0u;
+                            }
+                        }
+                        const uint32_t mine = c0 + c1;
+                        uint32_t incl = mine;
+#pragma unroll
+                        for (int o = 1; o < 32; o <<= 1) { uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+                        const uint32_t tot = __shfl_sync(0xffffffffu, incl, 31);
+                        if (tot) {                                   // warp-uniform
+                            uint32_t base = 0u;
+                            if (lane == 31) base = atomicAdd(cursor, tot);
+                            base = __shfl_sync(0xffffffffu, base, 31);
+                            uint32_t pos = base + incl - mine;
+                            if (mine) {
+#pragma unroll
+                                for (int i = 0; i < CH; ++i) {
+                                    if (i < n) {
+                                        const bool pass = (bv[i] >= la) & (pos < (uint32_t)kListCap);
+                                        const uint32_t code = lcode | (((uint32_t)(cc * CH + i)) << 9) | (uint32_t)a;
+                                        if (pass) asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(L_s + pos * 8u), "r"(code), "r"(__float_as_uint(bv[i])) : "memory");
+                                        pos += (bv[i] >= la) ? 1u : 0u;
+                                    }
                                 }
                             }
                         }
                     }
-                    return cnt + cnt2;
                 };
                 // exact sweep (rare): every candidate is scored; counts / writes the keys >= piv
                 auto sweep_exact = [&](auto emit_tag, uint64_t* wp, uint64_t* wend, const uint64_t piv) -> uint32_t {
                     constexpr bool EMIT = decltype(emit_tag)::value;
                     static_assert(2 * P + 5 + (C + 7) / 8 * 8 <= Cfg::TMEM_STRIDE, "class window leaves the TMEM buffer");
                     uint32_t cnt = 0u;
-                    if constexpr (Cfg::REGS) {
-#pragma unroll
-                        for (int a = 0; a < 3; ++a) {
-#pragma unroll
-                            for (int c = 0; c < C; ++c) {
-                                const float sc = vd_score(__fadd_rn(__uint_as_float(acc[a * P + 5 + c]), bias[a * P + 5 + c]), conf[a]);
-                                const uint32_t kh = (sc > vth) ? (__float_as_uint(sc) | 0x80000000u) : 0u;
-                                const uint64_t key = ((uint64_t)kh << 32) | (uint32_t)~(lcode | (((uint32_t)c) << 9) | (uint32_t)a);
-                                if (kh && key >= piv) {
-                                    ++cnt;
-                                    if constexpr (EMIT) { if (wp < wend) *wp++ = key; }
-                                }
-                            }
-                        }
-                        return cnt;
-                    }
 #pragma unroll 1
                     for (int a = 0; a < 3; ++a) {
                         const float ca = cf[cellofs * 3 + a];
@@ -590,7 +579,6 @@ head_kernel(const __grid_constant__ HeadMaps maps, const __grid_constant__ HeadK
                     return base + incl - mine;
                 };
                 auto release_tmem = [&]() {
-                    if constexpr (Cfg::REGS) return;            // already handed back right after the load
                     tc::fence_before_sync();
                     __syncwarp();
                     if (lane == 0) tc::mbar_arrive(&sh->tmem_empty[buf]);
@@ -622,29 +610,26 @@ head_kernel(const __grid_constant__ HeadMaps maps, const __grid_constant__ HeadK
                 bool have_lo = false, have_hi = false, exact = false;
                 uint32_t list_n = 0, list_hi = 0, t_acc = 0, my_cnt = 0;
                 uint64_t piv64 = 0ull, lo64 = 0ull, hi64 = 0ull;
-                if (et == 0) { gs->cursor = 0; gs->cursor2 = 0; }   // ordered before the first bump by the barrier inside epi_sum
 #pragma unroll 1
                 for (int g = 0; g < 200; ++g) {
                     if (!exact) {
                         set_fast(piv);
                         if (stamp) p.stamps[it * 16 + 9] = clock64();      // thresholds set
-                        my_cnt = sweep_fast(std::false_type{}, nullptr);
-                        if (stamp) p.stamps[it * 16 + 10] = clock64();     // count sweep done
-                        const uint32_t t = epi_sum(my_cnt, gs, grp, et, sum_it);
+                        uint32_t* pc = &gs->pcur[g % 3];                   // this probe's list cursor (zero on entry)
+                        if (et == 0) gs->pcur[(g + 1) % 3] = 0u;           // next probe's: last read two probes ago
+                        sweep_fast(pc);
+                        if (stamp) p.stamps[it * 16 + 10] = clock64();     // sweep done
+                        epi_bar(grp);                                      // every reservation and store of the group has landed
+                        const uint32_t t = *pc;
                         if (stamp) p.stamps[it * 16 + 5] = clock64();
                         if (p.dbg == 3) { release_tmem(); break; }
                         if (t <= cap && (t >= k || piv == floor_b)) {
-                            // ---- stage P(piv), score it, check the exact count
+                            // ---- the staged list is P(piv): score it, check the exact count
                             const uint32_t ph = (piv == floor_b) ? 1u : (piv | 0x80000000u);
-                            const uint32_t lb0 = list_base(my_cnt);
-                            if (stamp) p.stamps[it * 16 + 11] = clock64(); // positions known
-                            sweep_fast(std::true_type{}, L + lb0);
-                            if (stamp) p.stamps[it * 16 + 12] = clock64(); // stage sweep done
-                            epi_bar(grp);                           // staging complete
                             // score; split the list at the frame's hint: keys >= hint_hi go to the front, so the NMS kernel
                             // reads only the fronts when its pivot is at or above the hint (the usual case)
                             constexpr int KPT = kListCap / kEpiThreads;
-                            const uint32_t thk = p.hint_hi[f];
+                            const uint32_t thk = pf_hint;
                             uint64_t key[KPT];
                             uint32_t off[KPT];                      // bit 31: front part; low bits: offset inside this warp's share of the part
                             uint32_t ne = 0u, nh = 0u, wh = 0u, wl = 0u;
@@ -745,6 +730,7 @@ head_kernel(const __grid_constant__ HeadMaps maps, const __grid_constant__ HeadK
                 }
                 // ---- retarget the warm start towards the band centre
                 if (et == 0) {
+                    gs->pcur[0] = gs->pcur[1] = gs->pcur[2] = 0u; gs->cursor = 0u; gs->cursor2 = 0u;   // next tile starts from empty lists
                     p.counts[li] = list_n; p.counts_hi[li] = list_hi;
                     if (piv > floor_b) {
                         const uint32_t q4 = (cap - k) / 4u, nudge = band_w >> 3;

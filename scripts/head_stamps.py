@@ -10,7 +10,7 @@ dev = torch.device("cuda", 0)
 gen = torch.Generator(device=dev).manual_seed(1234)
 head = viddet_b200.YOLOV3Head(C).initialize(generator=torch.Generator().manual_seed(1234))
 ss = [head.session(bench.synth_tips(torch, gen, frames, size, dev)) for _ in range(3)]
-for i in range(9): ss[i % 3].run(_lib.VD_STAGE_HEAD)
+for i in range(9): ss[i % 3].run()          # full calls: the workspace state (bound, hints) is the steady-state one
 torch.cuda.synchronize()
 s = ss[2]
 hw = [(size // st) ** 2 for st in bench.STRIDES]
@@ -20,9 +20,9 @@ off = 256 + 256 + al(F * 4096 * 4) + al(F * anc * 16) + al(F * tif * 1024 * 8) +
 ntile = (F * tif + 147) // 148
 st = s._ws.view(torch.int64)[off // 8: off // 8 + 16 * ntile].cpu().view(ntile, 16)
 t0 = int(st[0, 0])
-order = [0, 1, 2, 3, 4, 8, 9, 10, 5, 11, 12, 13, 6, 14, 7]
-names = {0: "mma_wait", 1: "mma_go", 2: "mma_commit", 3: "epi_wait", 4: "epi_ready", 8: "box", 9: "setfast", 10: "count", 5: "sum1", 11: "scan",
-         12: "stage", 13: "scored", 6: "sum2+rel", 14: "flushed", 7: "end"}
+order = [0, 1, 2, 3, 4, 8, 9, 10, 5, 13, 6, 14, 7]
+names = {0: "mma_wait", 1: "mma_go", 2: "mma_commit", 3: "epi_wait", 4: "epi_ready", 8: "box+bound", 9: "setfast", 10: "sweep", 5: "bar", 
+         13: "scored", 6: "sum2+rel", 14: "flushed", 7: "end"}
 print("tile " + " ".join("%8s" % names[o] for o in order) + "   (us since first MMA wait; epilogue columns after epi_ready are deltas in ns)")
 for i in range(ntile):
     v = [(int(x) - t0) / 1.965e3 for x in st[i]]

@@ -565,7 +565,7 @@ class HeadPipeline:
                     with torch.cuda.stream(hs):
                         if nms_done[j] is not None:
                             hs.wait_event(nms_done[j])            # the session's buffers are free again
-                        sess.run(_lib.VD_STAGE_HEAD)
+                        sess.run(_lib.VD_STAGE_TCONV | _lib.VD_STAGE_HEAD)   # (temporal tip cell kernels, if any,) fused head kernel
                         head_done = torch.cuda.Event()
                         head_done.record(hs)
                     with torch.cuda.stream(ns):

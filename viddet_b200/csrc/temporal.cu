@@ -9,14 +9,15 @@
 // and taps that are out of range for a whole tile are skipped (13 of 15 taps do work at T=5).
 //   warp 0: TMA producer (A tile [128 rows x 64 ch] of the shifted frame + W_dt tile [NT x 64])
 //   warp 1: MMA issuer, M=128 x N=NT x K=16, accumulators double-buffered in TMEM
-//   warps 2-5: epilogue: tcgen05.ld -> folded BN -> LeakyReLU -> bf16 -> 128-bit stores
+//   warps 2-9: epilogue (two warpgroups, each takes half of the tile's columns): tcgen05.ld -> folded BN (scale/shift
+//              staged in shared memory) -> LeakyReLU -> bf16 -> 128-bit stores
 #include "tc.cuh"
 
 namespace vd {
 
 constexpr int T_BLOCK_M = 128;
 constexpr int T_BLOCK_K = 64;
-constexpr int T_THREADS = 192;
+constexpr int T_THREADS = 320;               // TMA warp, MMA warp, 8 epilogue warps
 
 struct TConvParams {
     int B, T, HW, C, rows;         // rows = T*HW
@@ -31,8 +32,9 @@ template <int NT> struct TConvCfg {
     static constexpr int B_BYTES = NT * T_BLOCK_K * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int STAGES = (200 * 1024) / STAGE_BYTES > 8 ? 8 : (200 * 1024) / STAGE_BYTES;
+    static constexpr int BN_BYTES = 2 * 1024 * 4;        // folded BN scale / shift of up to 1024 channels
     static constexpr int TMEM_COLS = 2 * NT;            // NT in {128, 256}
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2048 + 1024;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BN_BYTES + 2048 + 1024;
 };
 
 struct TShared {
@@ -47,12 +49,15 @@ temporal_conv_kernel(const __grid_constant__ TConvMaps maps, const __grid_consta
     extern __shared__ unsigned char smem_dyn[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
     unsigned char* ring = smem;
-    TShared* sh = reinterpret_cast<TShared*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+    float* sscale = reinterpret_cast<float*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);      // [C] then shift [C]
+    float* sshift = sscale + 1024;
+    TShared* sh = reinterpret_cast<TShared*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES + Cfg::BN_BYTES);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int i = threadIdx.x; i < p.C; i += T_THREADS) { sscale[i] = p.scale[i]; sshift[i] = p.shift[i]; }
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < Cfg::STAGES; ++i) { tc::mbar_init(&sh->full[i], 1); tc::mbar_init(&sh->empty[i], 1); }
-        for (int i = 0; i < 2; ++i) { tc::mbar_init(&sh->tmem_full[i], 1); tc::mbar_init(&sh->tmem_empty[i], 4); }
+        for (int i = 0; i < 2; ++i) { tc::mbar_init(&sh->tmem_full[i], 1); tc::mbar_init(&sh->tmem_empty[i], 8); }
         tc::fence_barrier_init();
         tc::prefetch_tmap(&maps.x); tc::prefetch_tmap(&maps.w);
     }
@@ -124,7 +129,9 @@ temporal_conv_kernel(const __grid_constant__ TConvMaps maps, const __grid_consta
             }
         }
     } else {
-        const int q = warp & 3;
+        const int q = warp & 3;                               // TMEM lane quarter this warp may read
+        const int half = (warp - 2) >> 2;                     // which half of the tile's columns
+        constexpr int NH = NT / 2;
         const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
         uint32_t it = 0;
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
@@ -134,28 +141,31 @@ temporal_conv_kernel(const __grid_constant__ TConvMaps maps, const __grid_consta
             const bool inb = row < p.rows;
             tc::mbar_wait(&sh->tmem_full[buf], (it >> 1) & 1u);
             tc::fence_after_sync();
-            const uint32_t tbase = tmem_base + buf * NT + lane_addr;
-            __nv_bfloat16* yrow = p.y + ((size_t)b * p.rows + (inb ? row : 0)) * p.C + (size_t)nt * NT;
-            const float* sc = p.scale + (size_t)nt * NT;
-            const float* sf = p.shift + (size_t)nt * NT;
+            const uint32_t tbase = tmem_base + buf * NT + (uint32_t)(half * NH) + lane_addr;
+            const int col0 = nt * NT + half * NH;
+            __nv_bfloat16* yrow = p.y + ((size_t)b * p.rows + (inb ? row : 0)) * p.C + col0;
+            const float* sc = sscale + col0;
+            const float* sf = sshift + col0;
 #pragma unroll 1
-            for (int n0 = 0; n0 < NT; n0 += 16) {
-                uint32_t r[16];
-                tc::tmem_ld16(tbase + n0, r); tc::tmem_ld_wait();
-                uint32_t packed[8];
+            for (int n0 = 0; n0 < NH; n0 += 32) {
+                uint32_t r[32];
+                tc::tmem_ld16(tbase + n0, r); tc::tmem_ld16(tbase + n0 + 16, r + 16); tc::tmem_ld_wait();
+                uint32_t packed[16];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    float v0 = fmaf(__uint_as_float(r[2 * i]), __ldg(sc + n0 + 2 * i), __ldg(sf + n0 + 2 * i));
-                    float v1 = fmaf(__uint_as_float(r[2 * i + 1]), __ldg(sc + n0 + 2 * i + 1), __ldg(sf + n0 + 2 * i + 1));
-                    v0 = v0 > 0.f ? v0 : v0 * p.slope;
-                    v1 = v1 > 0.f ? v1 : v1 * p.slope;
-                    __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1);
-                    packed[i] = *reinterpret_cast<uint32_t*>(&h);
+                for (int i = 0; i < 32; i += 4) {
+                    const float4 s4 = *reinterpret_cast<const float4*>(sc + n0 + i);
+                    const float4 f4 = *reinterpret_cast<const float4*>(sf + n0 + i);
+                    float v0 = fmaf(__uint_as_float(r[i]), s4.x, f4.x), v1 = fmaf(__uint_as_float(r[i + 1]), s4.y, f4.y);
+                    float v2 = fmaf(__uint_as_float(r[i + 2]), s4.z, f4.z), v3 = fmaf(__uint_as_float(r[i + 3]), s4.w, f4.w);
+                    v0 = v0 > 0.f ? v0 : v0 * p.slope; v1 = v1 > 0.f ? v1 : v1 * p.slope;
+                    v2 = v2 > 0.f ? v2 : v2 * p.slope; v3 = v3 > 0.f ? v3 : v3 * p.slope;
+                    __nv_bfloat162 h0 = __floats2bfloat162_rn(v0, v1), h1 = __floats2bfloat162_rn(v2, v3);
+                    packed[i / 2] = *reinterpret_cast<uint32_t*>(&h0); packed[i / 2 + 1] = *reinterpret_cast<uint32_t*>(&h1);
                 }
                 if (inb) {
                     uint4* dst = reinterpret_cast<uint4*>(yrow + n0);
-                    dst[0] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
-                    dst[1] = make_uint4(packed[4], packed[5], packed[6], packed[7]);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) dst[i] = make_uint4(packed[4 * i], packed[4 * i + 1], packed[4 * i + 2], packed[4 * i + 3]);
                 }
             }
             tc::fence_before_sync();
@@ -193,7 +203,7 @@ extern "C" int vd_temporal_conv(const void* x, void* y, int B, int T, int H, int
                                 float slope, void* stream_) {
     VD_CHECK_ARG(x && y && weight && scale && shift, "temporal_conv: null pointer");
     VD_CHECK_ARG(B >= 0 && T >= 1 && H > 0 && W > 0, "temporal_conv: bad shape");
-    VD_CHECK_ARG(C >= 128 && C % 128 == 0, "temporal_conv: C = %d must be a multiple of 128", C);
+    VD_CHECK_ARG(C >= 128 && C % 128 == 0 && C <= 1024, "temporal_conv: C = %d must be a multiple of 128, at most 1024", C);
     VD_CHECK_ARG(((uintptr_t)x & 15) == 0 && ((uintptr_t)y & 15) == 0 && ((uintptr_t)weight & 15) == 0, "temporal_conv: tensors must be 16-byte aligned");
     if (B == 0) return VD_OK;
     const int NT = (C % 256 == 0) ? 256 : 128;

@@ -169,6 +169,33 @@ def test_fused_valid_thresh_sweep_bit_exact(valid):
     assert torch.equal(scores.view(torch.int32), out[:, :100, 1:2].contiguous().view(torch.int32))
 
 
+@pytest.mark.parametrize("C,size,B", [(20, 416, 64), (80, 608, 8), (30, 416, 16)])
+def test_full_size_steady_state_bit_exact(C, size, B):
+    """BASELINE.json batch sizes, several consecutive calls on the same workspace: from the second call on the
+    dynamic tile scheduler, the per-frame running bound and the warm-start hints are all active.  Every call must
+    reproduce box_nms(detections()) bit-exactly, and a different batch on the same workspace must too."""
+    import viddet_b200
+    rng = np.random.RandomState(C * 7 + B)
+    ws, bs = make_pred_weights(rng, C, bias_scale=0.05)
+    head = build_head(C, ws, bs)
+    head.set_nms(nms_thresh=0.45, nms_topk=400, post_nms=100)
+    for rep in range(2):
+        tips = [cuda(t) for t in make_tips(rng, B, size=size)]
+        det = head.detections(tips)
+        out, rec = viddet_b200.box_nms(det, overlap_thresh=0.45, valid_thresh=0.01, topk=400, id_index=0, score_index=1,
+                                       coord_start=2, force_suppress=False, return_record=True)
+        del det
+        for call in range(3):
+            ids, scores, boxes, keep = head(tips, return_keep=True)
+            assert torch.equal(keep, rec[:, :100]), (rep, call)
+            assert torch.equal(scores.view(torch.int32), out[:, :100, 1:2].contiguous().view(torch.int32))
+            assert torch.equal(boxes.view(torch.int32), out[:, :100, 2:].contiguous().view(torch.int32))
+        # sortedness / validity properties of the returned rows
+        sc = scores[..., 0]
+        assert bool((sc[:, :-1] >= sc[:, 1:]).all())
+        assert bool(((keep >= 0) == (sc > 0.01)).all())
+
+
 def test_pipeline_matches_serial_calls():
     """HeadPipeline (head kernel of batch j+1 overlapped with the NMS kernel of batch j, several rotations per
     graph) must leave exactly the serial call's outputs in every session of the ring."""

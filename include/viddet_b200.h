@@ -187,6 +187,33 @@ int vd_prefetch_targets(int B, int M, int C, int orig_h, int orig_w, const int* 
                         float* objectness, float* center, float* scale, float* weight, float* cls,
                         int32_t* match_or_null, int32_t* row_or_null, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Training-side consumers of the prefetched targets.
+ *
+ * vd_target_merge -- YOLOV3DynamicTargetGeneratorSimple.hybrid_forward + YOLOV3TargetMerger.hybrid_forward
+ * (yolo_target.py:175-205, :226-281; call site yolo3.py:514).  box_preds (B,N,4) corner boxes of the
+ * train-mode decode, gt_boxes (B,M,4) padded with -1, prefetched targets obj_t (B,N,1), centers_t /
+ * scales_t / weights_t (B,N,2), clas_t (B,N,C) -- all five may be NULL (dynamic targets only).
+ * Outputs: objectness (B,N,1) [1 positive / -1 ignored / 0], center, scale, weights (B,N,2),
+ * class_targets (B,N,C), class_mask (B,N,C).
+ * ------------------------------------------------------------------------------------------ */
+int vd_target_merge(int B, int N, int M, int C, const float* box_preds, const float* gt_boxes,
+                    const float* obj_t, const float* centers_t, const float* scales_t,
+                    const float* weights_t, const float* clas_t, float ignore_iou_thresh,
+                    int label_smooth, float* objectness, float* center, float* scale, float* weights,
+                    float* class_targets, float* class_mask, void* stream);
+
+/* vd_yolo3_loss -- gluoncv.loss.YOLOV3Loss forward as called at yolo3.py:515: objness (B,N,1),
+ * box_centers / box_scales (B,N,2), cls_preds (B,N,C) raw predictions + the six merged targets
+ * -> obj_loss, center_loss, scale_loss, cls_loss, each (B).  Deterministic two-stage reduction. */
+size_t vd_yolo3_loss_workspace_bytes(int B, int N);
+int vd_yolo3_loss(int B, int N, int C, const float* objness, const float* box_centers,
+                  const float* box_scales, const float* cls_preds, const float* objness_t,
+                  const float* center_t, const float* scale_t, const float* weight_t,
+                  const float* class_t, const float* class_mask, float* obj_loss,
+                  float* center_loss, float* scale_loss, float* cls_loss, void* workspace,
+                  size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

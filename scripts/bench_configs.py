@@ -120,6 +120,31 @@ def targets(B=128, M=100, C=285, size=416, multi_hot=True):
                       "hbm_frac": alg / (t * 1e-3) / 1e9 / PEAK_HBM}))
 
 
+def train_side(B=128, M=100, C=285, size=416):
+    """8f row 1: target merger + loss forward on the cfg-5 shapes; algorithmic bytes = tensors read + written once."""
+    n_anch = 3 * sum((size // s) ** 2 for s in bench.STRIDES)
+    g = torch.Generator(device=dev).manual_seed(7)
+    box = torch.rand((B, n_anch, 4), generator=g, device=dev) * 300
+    box[..., 2:] += box[..., :2] + 8
+    gt = torch.rand((B, M, 4), generator=g, device=dev) * 300
+    gt[..., 2:] += gt[..., :2] + 8
+    obj_t = (torch.rand((B, n_anch, 1), generator=g, device=dev) > 0.995).float()
+    pre = [obj_t, torch.rand((B, n_anch, 2), generator=g, device=dev), torch.rand((B, n_anch, 2), generator=g, device=dev),
+           torch.rand((B, n_anch, 2), generator=g, device=dev), (torch.rand((B, n_anch, C), generator=g, device=dev) > 0.99).float()]
+    mg = viddet_b200.YOLOV3TargetMerger(C, 0.7)
+    t = timeit(lambda i: mg(box, gt, *pre), n=10, warm=2)
+    alg = B * n_anch * 4 * (4 + 7 + (7 + 2 * C))                  # box_preds + narrow prefetched targets read (class rows only where positive), six outputs written
+    print(json.dumps({"cfg": "merge_B%d_M%d_C%d" % (B, M, C), "what": "target_merge (incl. torch.empty + ctypes)", "ms": t,
+                      "images_per_s": B / (t * 1e-3), "alg_GBps": alg / (t * 1e-3) / 1e9, "hbm_frac": alg / (t * 1e-3) / 1e9 / PEAK_HBM}))
+    merged = mg(box, gt, *pre)
+    preds = [torch.randn((B, n_anch, w), generator=g, device=dev) for w in (1, 2, 2, C)]
+    loss = viddet_b200.YOLOV3Loss()
+    t = timeit(lambda i: loss(*preds, *merged), n=10, warm=2)
+    alg = B * n_anch * 4 * ((5 + C) + (7 + 2 * C))
+    print(json.dumps({"cfg": "loss_B%d_C%d" % (B, C), "what": "yolo3_loss forward", "ms": t, "images_per_s": B / (t * 1e-3),
+                      "alg_GBps": alg / (t * 1e-3) / 1e9, "hbm_frac": alg / (t * 1e-3) / 1e9 / PEAK_HBM}))
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["coco", "vid", "targets"]
     print(json.dumps({"peaks": {"hbm_GBps": PEAK_HBM, "bf16_tflops_sustained": PEAK_TC}}))
@@ -133,3 +158,5 @@ if __name__ == "__main__":
     if "targets" in which:
         targets()
         targets(C=20, multi_hot=False)
+    if "train" in which:
+        train_side()

@@ -65,6 +65,9 @@ SIGNATURES = {
     "vd_temporal_conv": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _f, _vp]),
     "vd_temporal_pool": (_i, [_vp, _vp, _i, _i, _i64, _i, _vp]),
     "vd_prefetch_targets": (_i, [_i, _i, _i, _i, _i, _ip, _fp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "vd_target_merge": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "vd_yolo3_loss_workspace_bytes": (_sz, [_i, _i]),
+    "vd_yolo3_loss": (_i, [_i, _i, _i] + [_vp] * 14 + [_vp, _sz, _vp]),
 }
 
 _lib = None

@@ -636,3 +636,77 @@ class YOLOV3PrefetchTargetGenerator:
         return outs + (match, row) if return_assign else outs
 
     forward = __call__
+
+
+# ------------------------------------------------------------------------------------------------
+# training: dynamic targets, target merger, loss
+# ------------------------------------------------------------------------------------------------
+class YOLOV3TargetMerger:
+    """yolo_target.py:208-281.  `__call__(box_preds, gt_boxes, obj_t, centers_t, scales_t, weights_t, clas_t)` ->
+    [objectness, center_targets, scale_targets, weights, class_targets, class_mask].  One vd_target_merge call."""
+
+    def __init__(self, num_class, ignore_iou_thresh, **kwargs):
+        self._num_class = num_class
+        self._ignore_iou_thresh = float(ignore_iou_thresh)
+        self._label_smooth = False
+
+    def _run(self, box_preds, gt_boxes, prefetched):
+        _require_cuda(box_preds, "box_preds")
+        _require_cuda(gt_boxes, "gt_boxes")
+        bp = box_preds.to(torch.float32).reshape(box_preds.shape[0], -1, 4).contiguous()
+        gt = gt_boxes.to(torch.float32).contiguous()
+        B, N = bp.shape[0], bp.shape[1]
+        M, C, dev = gt.shape[1], self._num_class, bp.device
+        pre = [None] * 5
+        if prefetched is not None:
+            shapes = [(B, N, 1), (B, N, 2), (B, N, 2), (B, N, 2), (B, N, C)]
+            pre = []
+            for t, shp in zip(prefetched, shapes):
+                _require_cuda(t, "prefetched target")
+                assert tuple(t.shape) == shp, "prefetched target shape %s != %s" % (tuple(t.shape), shp)
+                pre.append(t.to(torch.float32).contiguous())
+        outs = [torch.empty((B, N, w), device=dev) for w in (1, 2, 2, 2, C, C)]
+        check(load().vd_target_merge(B, N, M, C, ptr(bp), ptr(gt), *[ptr(t) for t in pre], self._ignore_iou_thresh,
+                                     int(self._label_smooth), *[ptr(t) for t in outs], stream_ptr()))
+        return outs
+
+    def __call__(self, box_preds, gt_boxes, obj_t, centers_t, scales_t, weights_t, clas_t):
+        return self._run(box_preds, gt_boxes, (obj_t, centers_t, scales_t, weights_t, clas_t))
+
+    forward = __call__
+
+
+class YOLOV3DynamicTargetGeneratorSimple(YOLOV3TargetMerger):
+    """yolo_target.py:151-205: targets that depend on the current predictions only (pos_iou_thresh >= 1):
+    objectness -1 where the best IoU with a ground truth exceeds ignore_iou_thresh, zeros / -1 elsewhere."""
+
+    def __call__(self, box_preds, gt_boxes):
+        return self._run(box_preds, gt_boxes, None)[:5]
+
+    forward = __call__
+
+
+class YOLOV3Loss:
+    """gluoncv.loss.YOLOV3Loss forward (constructed at yolo3.py:409, called at :515):
+    `__call__(objness, box_centers, box_scales, cls_preds, objness_t, center_t, scale_t, weight_t, class_t, class_mask)`
+    -> (obj_loss, center_loss, scale_loss, cls_loss), each (B,)."""
+
+    def __init__(self, batch_axis=0, weight=None, **kwargs):
+        assert batch_axis == 0 and weight is None
+
+    def __call__(self, objness, box_centers, box_scales, cls_preds, objness_t, center_t, scale_t, weight_t, class_t, class_mask):
+        ts = [objness, box_centers, box_scales, cls_preds, objness_t, center_t, scale_t, weight_t, class_t, class_mask]
+        for t in ts:
+            _require_cuda(t, "loss input")
+        ts = [t.to(torch.float32).contiguous() for t in ts]
+        B, N, C = cls_preds.shape[0], cls_preds.shape[1], cls_preds.shape[2]
+        for t, w in zip(ts, (1, 2, 2, C, 1, 2, 2, 2, C, C)):
+            assert t.numel() == B * N * w, "loss input has %d elements, expected %d" % (t.numel(), B * N * w)
+        dev = ts[0].device
+        outs = [torch.empty((B,), device=dev) for _ in range(4)]
+        lib = load()
+        ws = _workspace(max(lib.vd_yolo3_loss_workspace_bytes(B, N), 256), dev, owner="loss")
+        check(lib.vd_yolo3_loss(B, N, C, *[ptr(t) for t in ts], *[ptr(t) for t in outs], ptr(ws), ws.numel(), stream_ptr()))
+        return tuple(outs)
+
+    forward = __call__

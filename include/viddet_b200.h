@@ -214,6 +214,15 @@ int vd_yolo3_loss(int B, int N, int C, const float* objness, const float* box_ce
                   float* center_loss, float* scale_loss, float* cls_loss, void* workspace,
                   size_t workspace_bytes, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Post-processing of detect() on device (detect_yolo3.py:222-261): boxes clipped
+ * to [0, size], rows with id >= 0 kept in order, boxes divided by size, ids truncated.
+ * ids/scores (frames, post, 1), bboxes (frames, post, 4) -> rows (frames, post, 6)
+ * [id, score, x1, y1, x2, y2] padded with -1, counts (frames) int32.
+ * ------------------------------------------------------------------------------------------ */
+int vd_postprocess_detections(const float* ids, const float* scores, const float* bboxes, int frames,
+                              int post, float size, float* rows, int32_t* counts, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

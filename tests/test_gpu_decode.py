@@ -61,3 +61,22 @@ def test_repack_layout():
     y = viddet_b200.to_nhwc_bf16(x)
     assert y.dtype == torch.bfloat16 and y.is_contiguous(memory_format=torch.channels_last)
     torch.testing.assert_close(y.float(), x.to(torch.bfloat16).float(), rtol=0, atol=0)
+
+
+def test_postprocess_detections_bit_exact():
+    """detect()'s host loop on device (8f row 4): clip, id >= 0 compaction in order, /S, id truncation."""
+    import viddet_b200
+    from oracle import ref_post
+    rng = np.random.RandomState(2)
+    B, T, post, S = 3, 5, 100, 416
+    ids = rng.randint(-1, 20, size=(B, T, post, 1)).astype(np.float32)
+    ids[0, 0] = -1                                            # an image with no detection
+    ids[1, 2] = 7                                             # and a full one
+    scores = rng.uniform(0, 1, size=(B, T, post, 1)).astype(np.float32)
+    boxes = rng.uniform(-60, S + 60, size=(B, T, post, 4)).astype(np.float32)
+    ref_rows, ref_cnt = ref_post.postprocess(ids, scores, boxes, S)
+    rows, cnt = viddet_b200.postprocess_detections(torch.from_numpy(ids).cuda(), torch.from_numpy(scores).cuda(),
+                                                   torch.from_numpy(boxes).cuda(), S)
+    np.testing.assert_array_equal(cnt.cpu().numpy(), ref_cnt)
+    np.testing.assert_array_equal(rows.cpu().numpy(), ref_rows)
+    assert ref_cnt[0] == 0 and ref_cnt[T + 2] == post

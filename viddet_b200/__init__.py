@@ -7,7 +7,7 @@ from ._lib import VidDetError, load, SO_PATH  # noqa: F401
 from .blocks import (  # noqa: F401
     DEFAULT_ANCHORS, DEFAULT_CHANNELS, DEFAULT_STRIDES, HeadPipeline, HeadSession, TemporalPooling, TemporalTipConv, TimeDistributed,
     YOLOOutputV3, YOLOV3DynamicTargetGeneratorSimple, YOLOV3Head, YOLOV3Loss, YOLOV3PrefetchTargetGenerator, YOLOV3TargetMerger,
-    box_nms, to_nhwc_bf16,
+    box_nms, postprocess_detections, to_nhwc_bf16,
 )
 
 __version__ = "0.1.0"

@@ -710,3 +710,23 @@ class YOLOV3Loss:
         return tuple(outs)
 
     forward = __call__
+
+
+# ------------------------------------------------------------------------------------------------
+# post-processing of detect()
+# ------------------------------------------------------------------------------------------------
+def postprocess_detections(ids, scores, bboxes, size):
+    """detect_yolo3.py:222-261 on device: clip boxes to [0, size], keep rows with id >= 0 (order preserved), divide the
+    boxes by size.  ids/scores (..., post, 1), bboxes (..., post, 4) -> rows (F, post, 6) [id, score, x1, y1, x2, y2]
+    padded with -1 and counts (F,) int32, F = product of the leading dims (B, or B*T for mult_out windows)."""
+    for t in (ids, scores, bboxes):
+        _require_cuda(t, "detections")
+    post = ids.shape[-2]
+    i2 = ids.to(torch.float32).reshape(-1, post).contiguous()
+    s2 = scores.to(torch.float32).reshape(-1, post).contiguous()
+    b2 = bboxes.to(torch.float32).reshape(-1, post, 4).contiguous()
+    F = i2.shape[0]
+    rows = torch.empty((F, post, 6), device=i2.device)
+    counts = torch.empty((F,), dtype=torch.int32, device=i2.device)
+    check(load().vd_postprocess_detections(ptr(i2), ptr(s2), ptr(b2), F, post, float(size), ptr(rows), ptr(counts), stream_ptr()))
+    return rows, counts

@@ -143,3 +143,49 @@ extern "C" int vd_temporal_pool(const void* x, void* y, int B, int K, int64_t in
     VD_LAUNCH_CHECK();
     return VD_OK;
 }
+
+
+// ---------------------------------------------------------------------------------------------------------------
+// vd_postprocess_detections -- the host loop of detect() (detect_yolo3.py:222-261) on device: clip the boxes to
+// [0, S] (:226), keep the rows with id >= 0 in order (:256), normalise by S (:257), truncate the id (:258), pack
+// [id, score, x1, y1, x2, y2] and count the rows per image.  One warp per image (ballot compaction keeps the order).
+// ---------------------------------------------------------------------------------------------------------------
+namespace vd {
+__global__ void __launch_bounds__(256)
+postprocess_kernel(const float* __restrict__ ids, const float* __restrict__ scores, const float* __restrict__ bboxes,
+                   int frames, int post, float size, float* __restrict__ rows, int32_t* __restrict__ counts) {
+    const int f = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (f >= frames) return;
+    int n = 0;
+    for (int j0 = 0; j0 < post; j0 += 32) {
+        const int j = j0 + lane;
+        const float id = j < post ? ids[(size_t)f * post + j] : -1.0f;
+        const bool keep = id >= 0.0f;
+        const unsigned m = __ballot_sync(0xffffffffu, keep);
+        if (keep) {
+            const int pos = n + __popc(m & ((1u << lane) - 1u));
+            const float4 b = reinterpret_cast<const float4*>(bboxes)[(size_t)f * post + j];
+            float* o = rows + ((size_t)f * post + pos) * 6;
+            auto cl = [&](float x) { return x > size ? size : (x < 0.0f ? 0.0f : x); };     // mshadow_op::clip
+            o[0] = truncf(id); o[1] = scores[(size_t)f * post + j];
+            o[2] = __fdiv_rn(cl(b.x), size); o[3] = __fdiv_rn(cl(b.y), size);
+            o[4] = __fdiv_rn(cl(b.z), size); o[5] = __fdiv_rn(cl(b.w), size);
+        }
+        n += __popc(m);
+    }
+    for (int j = n * 6 + lane; j < post * 6; j += 32) rows[(size_t)f * post * 6 + j] = -1.0f;
+    if (lane == 0) counts[f] = n;
+}
+}  // namespace vd
+
+extern "C" int vd_postprocess_detections(const float* ids, const float* scores, const float* bboxes, int frames, int post,
+                                         float size, float* rows, int32_t* counts, void* stream_) {
+    VD_CHECK_ARG(frames >= 0 && post > 0, "postprocess: bad shape frames=%d post=%d", frames, post);
+    VD_CHECK_ARG(ids && scores && bboxes && rows && counts, "postprocess: null pointer");
+    VD_CHECK_ARG(((uintptr_t)bboxes & 15) == 0, "postprocess: bboxes must be 16-byte aligned");
+    VD_CHECK_ARG(size > 0.0f, "postprocess: image size must be positive");
+    if (frames == 0) return VD_OK;
+    vd::postprocess_kernel<<<vd::ceil_div(frames, 8), 256, 0, (cudaStream_t)stream_>>>(ids, scores, bboxes, frames, post, size, rows, counts);
+    VD_LAUNCH_CHECK();
+    return VD_OK;
+}

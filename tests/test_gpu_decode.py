@@ -80,3 +80,30 @@ def test_postprocess_detections_bit_exact():
     np.testing.assert_array_equal(cnt.cpu().numpy(), ref_cnt)
     np.testing.assert_array_equal(rows.cpu().numpy(), ref_rows)
     assert ref_cnt[0] == 0 and ref_cnt[T + 2] == post
+
+
+def test_feature_stream_from_npy_files(tmp_path):
+    """8f row 3: `<id>_F{1,2,3}.npy` (fp32 NCHW, extract_base_features.py:153-155) -> channels-last bf16 tips in the head's
+    scale order, bit-identical to converting the loaded arrays directly; short last batch; windows."""
+    import viddet_b200
+    rng = np.random.RandomState(4)
+    ids = ["clip/%06d" % i for i in range(7)]
+    (tmp_path / "clip").mkdir()
+    shapes = {"_F1.npy": (256, 8, 8), "_F2.npy": (512, 4, 4), "_F3.npy": (1024, 2, 2)}
+    data = {}
+    for fid in ids:
+        for suf, shp in shapes.items():
+            a = rng.standard_normal(shp).astype(np.float32)
+            np.save(str(tmp_path / (fid + suf)), a)
+            data[(fid, suf)] = a
+    seen = []
+    for got_ids, tips in viddet_b200.FeatureStream(str(tmp_path), ids, batch=3):
+        assert [t.shape[1] for t in tips] == [1024, 512, 256]
+        for k, suf in enumerate(("_F3.npy", "_F2.npy", "_F1.npy")):
+            ref = viddet_b200.to_nhwc_bf16(torch.from_numpy(np.stack([data[(f, suf)] for f in got_ids])).cuda())
+            assert tips[k].is_contiguous(memory_format=torch.channels_last)
+            assert torch.equal(tips[k].view(torch.int16), ref.view(torch.int16))
+        seen += got_ids
+    assert seen == ids
+    win = list(viddet_b200.FeatureStream(str(tmp_path), ids[:6], batch=1, window=3))
+    assert len(win) == 2 and tuple(win[0][1][0].shape) == (1, 3, 1024, 2, 2)

@@ -10,4 +10,6 @@ from .blocks import (  # noqa: F401
     box_nms, postprocess_detections, to_nhwc_bf16,
 )
 
+from .io import FeatureStream, feature_paths  # noqa: F401
+
 __version__ = "0.1.0"

@@ -37,7 +37,9 @@ constexpr int kEpiWarp0 = 2;                  // warp 0: TMA, warp 1: MMA, then 
 constexpr int kEpiThreads = 128;
 constexpr int A_TILE_BYTES = BLOCK_M * BLOCK_K * 2;
 
-enum { EPI_FILTER = 0, EPI_DET = 1, EPI_PRED = 2 };
+enum { EPI_FILTER = 0, EPI_DET = 1, EPI_PRED = 2, EPI_SPEC = 3 };
+constexpr int kSpecCap = 2048;                // candidates per frame the speculative path may emit
+constexpr int kSpecStage = 64;                // per-warp staging entries per tile (double-buffered); more go straight to global memory
 constexpr int kHeadSharedBytes = 2048;          // room for struct HeadShared (barriers, scheduler ring, per-group state)
 
 // Per-frame histogram of the emitted candidates' scores: 4096 bins, 512 per octave over [2^-7, 2).
@@ -76,6 +78,12 @@ struct HeadKernelParams {
     uint32_t* coarse;                    // [frames][64] the same histogram at 64 fine bins per bin: tiles read it for a running lower bound of the frame's k-th score
     unsigned int* tile_counter;          // [0] next tile, [1] finished CTAs, [2] ws_magic once the workspace is in its between-calls state; null: static round-robin
     unsigned int ws_magic;               // kWsMagic mixed with this call's workspace layout (a workspace last used with another shape is treated as uninitialised)
+    // EPI_SPEC (speculative frame-level threshold) and its exact fallback
+    uint64_t* spec_lists;                // [frames][kSpecCap] keys of the candidates >= the call's threshold
+    uint32_t* spec_cnt;                  // [frames] candidates emitted (may exceed kSpecCap = overflow); left zeroed by the NMS kernel
+    uint32_t* spec_state;                // [0] threshold (score bits) of this call, [1] accumulator for the next call's, [2] failed frames, [3] finished NMS CTAs, [4] failed frames of the last call (stats)
+    const uint32_t* frame_list;          // EPI_FILTER as the fallback: frames to process = frame_list[0 .. *frame_count)
+    const uint32_t* frame_count;
     long long* stamps;                   // profiling aid (VD_DEBUG_HEAD_STAMPS): clock64 per tile of CTA 0, [it][8]
     int dbg;                             // profiling aid (VD_DEBUG_SKIP_EPILOGUE=level): stop the epilogue early, results are garbage
     // EPI_DET
@@ -90,20 +98,20 @@ template <int EPI, int C, int NPAD> struct HeadCfg {
     static constexpr int CPA = (C + 15) / 16;                  // TMEM read chunks per anchor (<= 16 class logits each: 3 x 16 live registers)
     static constexpr int CH = (C + CPA - 1) / CPA;
     static constexpr int CH4 = (CH + 3) / 4 * 4;               // class-bias chunk padded for 128-bit shared loads
-    static constexpr int CBIAS_BYTES = (EPI == EPI_FILTER) ? VD_MAX_SCALES * 3 * CPA * CH4 * 4 : 0;
+    static constexpr int CBIAS_BYTES = (EPI == EPI_FILTER || EPI == EPI_SPEC) ? VD_MAX_SCALES * 3 * CPA * CH4 * 4 : 0;
     static constexpr int CONF_BYTES = (EPI == EPI_FILTER) ? kMaxEpiGroups * 3 * kEpiThreads * 4 : 0;
     static constexpr int LIST_BUFS = (EPI == EPI_FILTER) ? 1 : 0;
     static constexpr int B_TILE_BYTES = NPAD * BLOCK_K * 2;
     static constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
     static constexpr int TMEM_STRIDE = NPAD <= 128 ? 128 : 256;
     // 3 groups (12 epilogue warps, 128 registers/thread) when three accumulators fit TMEM; else 2 groups
-    static constexpr int G = (EPI == EPI_FILTER && TMEM_STRIDE == 128) ? (NPAD <= 80 ? 4 : 3) : 2;   // 4 groups only where 80 registers suffice
+    static constexpr int G = (EPI == EPI_FILTER && TMEM_STRIDE == 128) ? (NPAD <= 80 ? 4 : 3) : ((EPI == EPI_SPEC && TMEM_STRIDE == 128) ? 3 : 2);   // 4 groups only where 80 registers suffice
     static constexpr int THREADS = kEpiWarp0 * 32 + G * kEpiThreads;
     static constexpr int MAXREG = (THREADS > 448) ? 80 : ((THREADS > 320) ? 96 : 128);
-    static constexpr int LIST_BYTES = G * LIST_BUFS * kListCap * 8;
+    static constexpr int LIST_BYTES = (EPI == EPI_SPEC) ? G * 4 * 2 * kSpecStage * 8 : G * LIST_BUFS * kListCap * 8;
     static constexpr int EPI_BYTES = LIST_BYTES + CBIAS_BYTES + CONF_BYTES + VD_MAX_SCALES * NPAD * 4 + kHeadSharedBytes;
     // EPI_FILTER leaves ~45 KB of the SM's shared memory to a co-resident nms_final_hist_kernel CTA of the previous batch
-    static constexpr int SMEM_BUDGET = (EPI == EPI_FILTER ? 181 : 225) * 1024;
+    static constexpr int SMEM_BUDGET = ((EPI == EPI_FILTER || EPI == EPI_SPEC) ? 181 : 225) * 1024;
     static constexpr int STAGES_RAW = (SMEM_BUDGET - EPI_BYTES - 1024) / STAGE_BYTES;
     static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
     static constexpr int TMEM_COLS = (G * TMEM_STRIDE) <= 256 ? 256 : 512;
@@ -125,6 +133,7 @@ struct HeadShared {
     uint64_t full[8], empty[8], tmem_full[kMaxEpiGroups], tmem_empty[kMaxEpiGroups];
     uint64_t sched_full[kSchedSlots], sched_empty[kSchedSlots];
     int sched_tile[kSchedSlots];
+    uint32_t spec_wcnt[4 * kMaxEpiGroups];       // EPI_SPEC: staged keys of each epilogue warp's current tile
     uint32_t tmem_base, pad_;
     EpiGroupShared grp[kMaxEpiGroups];
 };
@@ -153,7 +162,17 @@ __device__ __forceinline__ uint32_t epi_sum(uint32_t v, EpiGroupShared* s, int g
     return r;
 }
 
+// fallback mode: tiles enumerate the listed frames one after another
+__device__ __forceinline__ void tile_coords_list(const HeadKernelParams& p, int tile, int& s, int& f, int& pblk) {
+    const int fi = tile / p.tiles_per_frame, t = tile - fi * p.tiles_per_frame;
+    f = (int)p.frame_list[fi];
+    s = 0;
+#pragma unroll
+    for (int i = 1; i < VD_MAX_SCALES; ++i) if (i < p.g.num_scales && t >= p.tif_base[i]) s = i;
+    pblk = t - p.tif_base[s];
+}
 __device__ __forceinline__ void tile_coords(const HeadKernelParams& p, int tile, int& s, int& f, int& pblk) {
+    if (p.frame_list) { tile_coords_list(p, tile, s, f, pblk); return; }
     int j = 0;
 #pragma unroll
     for (int i = 1; i < VD_MAX_SCALES; ++i) if (i < p.g.num_scales && tile >= p.tile_start[i]) j = i;
@@ -195,7 +214,7 @@ head_kernel(const __grid_constant__ HeadMaps maps, const __grid_constant__ HeadK
         int s = i / NPAD, n = i % NPAD;
         sbias[i] = (s < p.g.num_scales && p.bias[s] && n < p.n_valid) ? p.bias[s][n] : 0.0f;
     }
-    if constexpr (EPI == EPI_FILTER) {
+    if constexpr (EPI == EPI_FILTER || EPI == EPI_SPEC) {
         constexpr int P = 5 + C;
         for (int i = threadIdx.x; i < VD_MAX_SCALES * 3 * Cfg::CPA * Cfg::CH4; i += Cfg::THREADS) {
             const int s = i / (3 * Cfg::CPA * Cfg::CH4), r = i % (3 * Cfg::CPA * Cfg::CH4);
@@ -208,6 +227,7 @@ head_kernel(const __grid_constant__ HeadMaps maps, const __grid_constant__ HeadK
         for (int i = 0; i < Cfg::STAGES; ++i) { tc::mbar_init(&sh->full[i], 1); tc::mbar_init(&sh->empty[i], 1); }
         for (int i = 0; i < G; ++i) { tc::mbar_init(&sh->tmem_full[i], 1); tc::mbar_init(&sh->tmem_empty[i], 4); }
         for (int i = 0; i < kSchedSlots; ++i) { tc::mbar_init(&sh->sched_full[i], 1); tc::mbar_init(&sh->sched_empty[i], 5); }   // consumers: MMA thread + 4 epilogue warps
+        for (int i = 0; i < 4 * kMaxEpiGroups; ++i) sh->spec_wcnt[i] = 0u;
         for (int g = 0; g < G; ++g) {
             sh->grp[g].cnt[0] = sh->grp[g].cnt[1] = sh->grp[g].cnt[2] = 0; sh->grp[g].cursor = 0; sh->grp[g].cursor2 = 0; sh->grp[g].pcur[0] = sh->grp[g].pcur[1] = sh->grp[g].pcur[2] = 0;
             for (int i = 0; i < 2 * VD_MAX_SCALES; ++i) {
@@ -236,9 +256,10 @@ head_kernel(const __grid_constant__ HeadMaps maps, const __grid_constant__ HeadK
             const uint64_t pol_w = tc::policy_evict_last();     // weights are re-read by every tile
             // claims tiles (global counter: dynamic load balance, largest tiles first) and publishes them to the other roles
             const bool dyn = p.tile_counter != nullptr && p.tile_counter[2] == p.ws_magic;   // uninitialised workspace: static round-robin
+            const uint32_t total_tiles = p.frame_list ? *p.frame_count * (uint32_t)p.tiles_per_frame : (uint32_t)p.total_tiles;
             auto claim = [&](uint32_t i) -> int {
                 const uint32_t t = dyn ? atomicAdd(p.tile_counter, 1u) : (uint32_t)blockIdx.x + i * gridDim.x;
-                return t < (uint32_t)p.total_tiles ? (int)t : -1;
+                return t < total_tiles ? (int)t : -1;
             };
             int next = claim(0u), n_end = 0;
             for (uint32_t it = 0;; ++it) {
@@ -314,13 +335,35 @@ head_kernel(const __grid_constant__ HeadMaps maps, const __grid_constant__ HeadK
         bool ws_ok = false;                                   // the workspace's histograms started this call zeroed (layout marker intact)
         if constexpr (EPI == EPI_FILTER) ws_ok = p.tile_counter[2] == p.ws_magic;
         (void)ws_ok;
+        uint32_t spec_tb = 0u;                                // EPI_SPEC: the call's score threshold (float bits)
+        if constexpr (EPI == EPI_SPEC) {
+            const uint32_t floor_b = p.valid_thresh > 0.0f ? __float_as_uint(p.valid_thresh) : 0u;
+            const uint32_t hint = (p.tile_counter[2] == p.ws_magic) ? p.spec_state[0] : 0u;     // foreign workspace: the NMS kernel fails every frame anyway
+            spec_tb = hint > floor_b ? hint : floor_b;
+            if (spec_tb > 0x3f800001u) spec_tb = 0x3f800001u;
+        }
+        (void)spec_tb;
+        uint32_t spec_pend_base = 0u, spec_pend_n = 0u, spec_par = 0u; int spec_pend_f = 0;
+        auto spec_flush = [&]() {                             // copy the previous tile's staged keys to their reserved range
+            if constexpr (EPI == EPI_SPEC) {
+                const uint32_t n = spec_pend_n;
+                if (n) {
+                    const uint32_t base = __shfl_sync(0xffffffffu, spec_pend_base, 0);
+                    const uint64_t* src_s = slist + (size_t)((warp - kEpiWarp0) * 2 + (int)((spec_par ^ 1u) & 1u)) * kSpecStage;
+                    uint64_t* dst = p.spec_lists + (size_t)spec_pend_f * kSpecCap;
+                    for (uint32_t j = (uint32_t)lane; j < n; j += 32u) if (base + j < (uint32_t)kSpecCap) dst[base + j] = src_s[j];
+                    spec_pend_n = 0u;
+                }
+            }
+        };
+        (void)spec_pend_base; (void)spec_pend_f; (void)spec_par;
         for (;; it += G) {
             const uint32_t slot = it % kSchedSlots;
             tc::mbar_wait(&sh->sched_full[slot], (it / kSchedSlots) & 1u);
             const int tile = sh->sched_tile[slot];
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(&sh->sched_empty[slot]);
-            if (tile < 0) break;
+            if (tile < 0) { spec_flush(); break; }
             int s, f, pblk; tile_coords(p, tile, s, f, pblk);
             const uint32_t buf = (uint32_t)grp;
             const int HW = p.g.HW[s], Wd = p.g.W[s];
@@ -338,6 +381,7 @@ head_kernel(const __grid_constant__ HeadMaps maps, const __grid_constant__ HeadK
             }
             tc::mbar_wait(&sh->tmem_full[buf], (it / (uint32_t)G) & 1u);
             tc::fence_after_sync();
+            if constexpr (EPI == EPI_SPEC) spec_flush();
             if (stamp) p.stamps[it * 16 + 4] = clock64();
             const uint32_t tbase = tmem_base + buf * Cfg::TMEM_STRIDE + lane_addr;
 
@@ -379,13 +423,16 @@ head_kernel(const __grid_constant__ HeadMaps maps, const __grid_constant__ HeadK
                 float tx = __uint_as_float(r[0]) + bias[a * P + 0], ty = __uint_as_float(r[1]) + bias[a * P + 1];
                 float tw = __uint_as_float(r[2]) + bias[a * P + 2], th = __uint_as_float(r[3]) + bias[a * P + 3];
                 float to = __uint_as_float(r[4]) + bias[a * P + 4];
-                Box4 bx = vd_decode_box(tx, ty, tw, th, gx, gy, p.g.stride[s], p.g.anchors[s][2 * a], p.g.anchors[s][2 * a + 1]);
                 conf[a] = vd_sigmoid(to);
-                if constexpr (EPI == EPI_FILTER) {
+                Box4 bx;
+                if constexpr (EPI == EPI_FILTER || EPI == EPI_SPEC) {
+                    // the raw (tx,ty,tw,th) are stored; only the <= topk boxes that reach the NMS kernel are decoded there
+                    // (same vd_decode_box, same bits) instead of all 3*HW of them here
                     if (!inb) conf[a] = __uint_as_float(0x7fc00000u);   // NaN: no score of a padding pixel passes `> valid_thresh`
-                    if (inb) p.boxes[(size_t)f * p.g.anc_base[p.g.num_scales] + p.g.anc_base[s] + cell * 3 + a] =
-                        make_float4(bx.x1, bx.y1, bx.x2, bx.y2);
+                    if (inb) p.boxes[(size_t)f * p.g.anc_base[p.g.num_scales] + p.g.anc_base[s] + cell * 3 + a] = make_float4(tx, ty, tw, th);
+                    (void)bx; (void)gx; (void)gy;
                 } else {   // EPI_DET: class rows of this (cell, anchor)
+                    bx = vd_decode_box(tx, ty, tw, th, gx, gy, p.g.stride[s], p.g.anchors[s][2 * a], p.g.anchors[s][2 * a + 1]);
                     const size_t rows_scale = (size_t)HW * 3;
                     float* drow = p.det + ((size_t)f * p.det_rows_total + p.g.row_base[s] + (size_t)cell * 3 + a) * 6;
                     // 8-column windows; the last one may read up to 7 columns past 3*P, which stays inside
@@ -413,6 +460,96 @@ head_kernel(const __grid_constant__ HeadMaps maps, const __grid_constant__ HeadK
                 tc::fence_before_sync();
                 __syncwarp();
                 if (lane == 0) tc::mbar_arrive(&sh->tmem_empty[buf]);
+                continue;
+            }
+
+            if constexpr (EPI == EPI_SPEC) {
+                // ---- speculative frame-level threshold: every candidate whose score can reach the call's threshold tau
+                // (max of the valid floor and the hint left by the previous call) is scored and appended to its FRAME's
+                // list; nothing is selected per tile, no barrier, no shared-memory list.  The NMS kernel verifies per frame
+                // that the list did not overflow and holds >= k candidates at or above tau (then it contains the frame's
+                // exact top-k); frames that fail are redone by the exact EPI_FILTER path.  Same conservative logit
+                // prefilter as there: x >= logit(tau/conf) - margin  <=  score >= tau.
+                constexpr int CH = Cfg::CH, CPA = Cfg::CPA, CH4 = Cfg::CH4, REM = C - (CPA - 1) * CH;
+                const float vth = p.valid_thresh;
+                const float* cbias = scbias + s * (3 * CPA * CH4);
+                float ell[3];
+                {
+                    const float t = __fmul_rn(__uint_as_float(spec_tb), 0.999969482421875f);   // 1 - 2^-15
+#pragma unroll
+                    for (int a = 0; a < 3; ++a) {
+                        const float r = __fmul_rn(t, vd_rcp(conf[a]));
+                        const float l = __fmul_rn(__fsub_rn(vd_lg2(r), vd_lg2(__fsub_rn(1.0f, r))), 0.6931471805599453f);
+                        float e = (r < 1.0f) ? l : __uint_as_float(0x7f800000u);
+                        if (spec_tb == 0u) e = __uint_as_float(0xff800000u);
+                        if (!(conf[a] == conf[a])) e = __uint_as_float(0x7f800000u);
+                        ell[a] = e;
+                    }
+                }
+                const uint32_t HW3 = (uint32_t)HW * 3u;
+                const uint32_t row0 = (uint32_t)p.g.row_base[s] + (uint32_t)cell * 3u;       // + c*HW3 + a
+                uint64_t* fl = p.spec_lists + (size_t)f * kSpecCap;
+                uint32_t* fc = p.spec_cnt + f;
+                // Passers are staged per WARP in shared memory (no group barrier anywhere in this epilogue).  The warp's
+                // range of the frame's list is reserved with one global atomic whose result is only consumed when the
+                // NEXT tile's accumulator is ready, so its round trip hides behind that wait (deferred flush).
+                const int wq = (warp - kEpiWarp0);                                  // epilogue warp index inside the CTA
+                uint64_t* stg = slist + (size_t)(wq * 2 + (int)(spec_par & 1u)) * kSpecStage;
+                uint32_t* wc = &sh->spec_wcnt[wq];
+                uint32_t r[2][CH];
+                auto issue_a = [&](const int a, const int cc, uint32_t* dst) {
+                    const uint32_t col = tbase + (uint32_t)(a * P + 5 + cc * CH);
+                    if (REM != CH && cc == CPA - 1) tc::tmem_ld<REM>(col, dst); else tc::tmem_ld<CH>(col, dst);
+                };
+                issue_a(0, 0, r[0]);
+#pragma unroll 1
+                for (int a = 0; a < 3; ++a) {
+                    const float la = (a == 0) ? ell[0] : ((a == 1) ? ell[1] : ell[2]);
+                    const float ca = (a == 0) ? conf[0] : ((a == 1) ? conf[1] : conf[2]);
+#pragma unroll
+                    for (int cc = 0; cc < CPA; ++cc) {
+                        const int n = (REM != CH && cc == CPA - 1) ? REM : CH;
+                        float bv[CH4];
+#pragma unroll
+                        for (int i = 0; i < CH4; i += 4)
+                            *reinterpret_cast<float4*>(bv + i) = *reinterpret_cast<const float4*>(cbias + (a * CPA + cc) * CH4 + i);
+                        if ((CPA & 1) && cc == 0 && a > 0) issue_a(a, 0, r[0]);
+                        tc::tmem_ld_wait();
+                        if (cc + 1 < CPA) issue_a(a, cc + 1, r[(cc + 1) & 1]);
+                        else if (!(CPA & 1) && a + 1 < 3) issue_a(a + 1, 0, r[0]);
+                        bool any = false;
+#pragma unroll
+                        for (int i = 0; i < CH; ++i) {
+                            if (i < n) { bv[i] = __fadd_rn(__uint_as_float(r[cc & 1][i]), bv[i]); any |= bv[i] >= la; }
+                        }
+                        if (any) {                                   // rare: ~0.3 % of the candidates pass
+#pragma unroll
+                            for (int i = 0; i < CH; ++i) {
+                                if (i < n && bv[i] >= la) {
+                                    const float sc = vd_score(bv[i], ca);
+                                    if (sc > vth) {
+                                        const uint32_t kh = __float_as_uint(sc) | 0x80000000u;
+                                        const uint32_t row = row0 + (uint32_t)(cc * CH + i) * HW3 + (uint32_t)a;
+                                        const uint64_t key = ((uint64_t)kh << 32) | (uint32_t)~row;
+                                        const uint32_t sp = atomicAdd(wc, 1u);
+                                        if (sp < (uint32_t)kSpecStage) stg[sp] = key;
+                                        else { const uint32_t pos = atomicAdd(fc, 1u); if (pos < (uint32_t)kSpecCap) fl[pos] = key; }   // staging full
+                                    }
+                                }
+                            }
+                        }
+                    }
+                }
+                tc::fence_before_sync();
+                __syncwarp();
+                if (lane == 0) tc::mbar_arrive(&sh->tmem_empty[buf]);
+                // reserve this tile's range now, copy it out when the next accumulator arrives
+                uint32_t wn = *wc; wn = wn < (uint32_t)kSpecStage ? wn : (uint32_t)kSpecStage;
+                __syncwarp();
+                spec_pend_base = 0u;
+                if (lane == 0) { *wc = 0u; if (wn) spec_pend_base = atomicAdd(fc, wn); }
+                spec_pend_n = wn; spec_pend_f = f; spec_par ^= 1u;
+                __syncwarp();
                 continue;
             }
 
@@ -774,7 +911,11 @@ struct FusedSource {
         const int per = g.HW[s] * 3;
         c = rs / per;
         const int slot = rs - c * per;
-        bx = boxes[(size_t)f * g.anc_base[g.num_scales] + g.anc_base[s] + slot];
+        const float4 t = boxes[(size_t)f * g.anc_base[g.num_scales] + g.anc_base[s] + slot];     // raw (tx,ty,tw,th) of the anchor
+        const int cell = slot / 3, a = slot - cell * 3;
+        const int gy = cell / g.W[s], gx = cell - gy * g.W[s];
+        const Box4 b = vd_decode_box(t.x, t.y, t.z, t.w, (float)gx, (float)gy, g.stride[s], g.anchors[s][2 * a], g.anchors[s][2 * a + 1]);
+        bx = make_float4(b.x1, b.y1, b.x2, b.y2);
         area = __fmul_rn(__fsub_rn(bx.z, bx.x), __fsub_rn(bx.w, bx.y));
     }
 };
@@ -912,10 +1053,15 @@ __device__ void nms_tail_wave(const int n, const int f, const NmsParams P, const
 __global__ void __maxnreg__(56)
 nms_final_hist_kernel(const uint64_t* __restrict__ lists, const uint32_t* __restrict__ counts, const uint32_t* __restrict__ counts_hi,
                       uint32_t* __restrict__ hint_hi, uint32_t* __restrict__ coarse, int n_lists,
-                      uint32_t* __restrict__ hist, unsigned int* __restrict__ ctr, unsigned int ws_magic, NmsParams P, FusedSource src, FusedSink sink) {
+                      uint32_t* __restrict__ hist, unsigned int* __restrict__ ctr, unsigned int ws_magic,
+                      const uint32_t* __restrict__ frame_list, uint32_t* __restrict__ spec_state, NmsParams P, FusedSource src, FusedSink sink) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
     const int k = P.k;
+    // fallback of the speculative path: CTA i takes the i-th failed frame; every CTA joins the end-of-call bookkeeping
+    const bool active = frame_list == nullptr || blockIdx.x < spec_state[2];
+    const int f = frame_list ? (active ? (int)frame_list[blockIdx.x] : 0) : (int)blockIdx.x;
+    if (active) {
     SelectScratch* scr = reinterpret_cast<SelectScratch*>(smem_raw);
     uint32_t* sx = reinterpret_cast<uint32_t*>(smem_raw + 64);          // [40] warp sums + results
     uint64_t* skeys = reinterpret_cast<uint64_t*>(smem_raw + 256);
@@ -1054,8 +1200,111 @@ nms_final_hist_kernel(const uint64_t* __restrict__ lists, const uint32_t* __rest
     VD_STAMP(P, 3);
     const int n = (int)(m < (uint32_t)k ? m : (uint32_t)k);
     nms_tail_wave(n, f, P, src, sink, skeys, sbox, scls, sarea, skbox, skarea, skcls, wsh);
-    if (f == 0 && tid == 0) { ctr[0] = 0u; ctr[1] = 0u; ctr[2] = ws_magic; }   // workspace is in its between-calls state (for this layout)
+    if (spec_state && tid == 0) atomicMin(&spec_state[1], hist_edge(bstar > 16u ? bstar - 16u : 0u) & 0x7fffffffu);   // this frame's wish for the next call's threshold
     if (P.dbg && tid == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t) :: "memory"); P.dbg[8192 + f * 4 + 1] = (long long)t; }
+    }   // active
+    if (spec_state == nullptr) {
+        if (blockIdx.x == 0 && tid == 0) { ctr[0] = 0u; ctr[1] = 0u; ctr[2] = ws_magic; }   // workspace is in its between-calls state (for this layout)
+        return;
+    }
+    // last CTA out closes the call: next call's threshold = the lowest wish of this call's frames, counters re-armed
+    __syncthreads();
+    if (tid == 0) {
+        __threadfence();
+        if (atomicAdd(&spec_state[3], 1u) == gridDim.x - 1u) {
+            const uint32_t acc = spec_state[1];
+            if (acc != 0xffffffffu) spec_state[0] = acc;
+            spec_state[1] = 0xffffffffu; spec_state[4] = spec_state[2]; spec_state[2] = 0u; spec_state[3] = 0u;
+            ctr[0] = 0u; ctr[1] = 0u; ctr[2] = ws_magic;
+        }
+    }
+}
+
+// Speculative path, per frame: the head kernel appended every candidate that can reach the call's threshold tau to the
+// frame's list.  The list is the frame's exact top-k source iff it did not overflow and holds >= k keys at or above tau
+// (or tau is the valid floor: then it simply holds every valid candidate).  Such frames are finished here (sort, wavefront
+// NMS, outputs); the others are queued for the exact path.  256 threads, 56 registers: shares SMs with a head kernel.
+__global__ void __maxnreg__(56)
+nms_spec_kernel(const uint64_t* __restrict__ spec_lists, uint32_t* __restrict__ spec_cnt, uint32_t* __restrict__ spec_state,
+                uint32_t* __restrict__ failed, const unsigned int* __restrict__ ctr, unsigned int ws_magic, float valid_thresh,
+                NmsParams P, FusedSource src, FusedSink sink) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int f = blockIdx.x, tid = threadIdx.x;
+    const int k = P.k;
+    SelectScratch* scr = reinterpret_cast<SelectScratch*>(smem_raw);
+    uint64_t* skeys = reinterpret_cast<uint64_t*>(smem_raw + 256);
+    float4* sbox = reinterpret_cast<float4*>(skeys + kSpecCap);
+    const int KMAX = (P.max_out < k ? P.max_out : k) + 32 + 4 * (kNmsThreads / 32);
+    float4* skbox = sbox + k;
+    float* skarea = reinterpret_cast<float*>(skbox + KMAX);
+    int* skcls = reinterpret_cast<int*>(skarea + KMAX);
+    int* scls = skcls + KMAX;
+    float* sarea = reinterpret_cast<float*>(scls + k);
+    WaveShared* wsh = reinterpret_cast<WaveShared*>(sarea + k);
+    VD_STAMP(P, 0);
+    if (P.dbg && tid == 0) {
+        unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t) :: "memory");
+        unsigned int sm; asm volatile("mov.u32 %0, %%smid;" : "=r"(sm));
+        P.dbg[8192 + f * 4 + 0] = (long long)t; P.dbg[8192 + f * 4 + 2] = (long long)sm;
+    }
+    select_scratch_init(scr);
+    const bool ws_ok = ctr[2] == ws_magic;
+    const uint32_t cnt = spec_cnt[f];
+    const uint32_t floor_b = valid_thresh > 0.0f ? __float_as_uint(valid_thresh) : 0u;
+    uint32_t tb = ws_ok ? spec_state[0] : 0u;
+    tb = tb > floor_b ? tb : floor_b;
+    if (tb > 0x3f800001u) tb = 0x3f800001u;
+    __syncthreads();
+    if (tid == 0) spec_cnt[f] = 0u;                              // next call appends from zero
+    if (!ws_ok) {
+        // foreign workspace: nothing in it can be trusted -> every frame takes the exact path, which also re-initialises it
+        if (tid == 0) {
+            failed[f] = (uint32_t)f;
+            if (f == 0) { spec_state[0] = 0u; spec_state[1] = 0xffffffffu; spec_state[2] = gridDim.x; spec_state[3] = 0u; }
+        }
+        return;
+    }
+    bool ok = cnt <= (uint32_t)kSpecCap;
+    uint32_t n_ge = 0u;
+    if (ok) {
+        const uint32_t tk = tb | 0x80000000u;
+        uint32_t c = 0u;
+        for (uint32_t j = tid; j < cnt; j += blockDim.x) {
+            const uint64_t v = spec_lists[(size_t)f * kSpecCap + j];
+            skeys[j] = v;
+            c += ((uint32_t)(v >> 32) >= tk) ? 1u : 0u;
+        }
+        int it = 0;
+        n_ge = block_sum(c, scr, it);
+        ok = n_ge >= (uint32_t)k || tb == floor_b;
+    }
+    if (!ok) {
+        if (tid == 0) failed[atomicAdd(&spec_state[2], 1u)] = (uint32_t)f;
+        return;
+    }
+    VD_STAMP(P, 2);
+    const int SN = cnt <= 512u ? 512 : (cnt <= 1024u ? 1024 : 2048);
+    for (int i = (int)cnt + tid; i < SN; i += blockDim.x) skeys[i] = 0ull;
+    __syncthreads();
+    block_sort_u64_desc(skeys, SN);
+    VD_STAMP(P, 3);
+    const int n = (int)(cnt < (uint32_t)k ? cnt : (uint32_t)k);
+    // wish for the next call: the score at rank ~1.5 k of this frame, a little lower (the lowest wish of all frames wins)
+    if (tid == 0) {
+        uint32_t d = floor_b;
+        if (cnt >= (uint32_t)k) {
+            const uint32_t r = min(cnt - 1u, (uint32_t)(k + k / 2));
+            const uint32_t bits = (uint32_t)(skeys[r] >> 32) & 0x7fffffffu;
+            d = bits > floor_b + 65536u ? bits - 65536u : floor_b;          // ~0.8 % lower
+        }
+        atomicMin(&spec_state[1], d);
+    }
+    nms_tail_wave(n, f, P, src, sink, skeys, sbox, scls, sarea, skbox, skarea, skcls, wsh);
+    if (P.dbg && tid == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t) :: "memory"); P.dbg[8192 + f * 4 + 1] = (long long)t; }
+}
+static size_t nms_spec_smem(int k, int max_out) {
+    const size_t kmax = (size_t)(max_out < k ? max_out : k) + 32 + 4 * (kNmsThreads / 32);
+    return 256 + (size_t)kSpecCap * 8 + (size_t)k * 16 + kmax * 24 + (size_t)k * 8 + sizeof(WaveShared) + 64;
 }
 static size_t nms_hist_smem(int k, int max_out) {
     const size_t kmax = (size_t)(max_out < k ? max_out : k) + 32 + 4 * (kNmsThreads / 32);
@@ -1071,7 +1320,7 @@ struct HeadPlan {
     HeadKernelParams kp;
     int n_pad, C;
     int merge_levels;
-    size_t off_hints, off_ctr, off_hist, off_boxes, off_lists0, off_counts0, off_counts_hi, off_hint_hi, off_coarse, off_listsA, off_listsB, off_countsA, off_countsB, total;
+    size_t off_hints, off_ctr, off_hist, off_boxes, off_lists0, off_counts0, off_counts_hi, off_hint_hi, off_coarse, off_spec_lists, off_spec_cnt, off_spec_state, off_failed, off_listsA, off_listsB, off_countsA, off_countsB, total;
 };
 
 static int head_npad(int C) { int n = 3 * (5 + C); return (n + 15) / 16 * 16; }
@@ -1132,6 +1381,10 @@ static int make_plan(const VdHeadParams* hp, HeadPlan* pl) {
     pl->off_counts_hi = off; off += align_up(F * tif * 4, 256);
     pl->off_hint_hi = off; off += align_up(F * 4, 256);
     pl->off_coarse = off; off += align_up(F * 64 * 4, 256);
+    pl->off_spec_lists = off; off += align_up(F * kSpecCap * 8, 256);
+    pl->off_spec_cnt = off; off += align_up(F * 4, 256);
+    pl->off_spec_state = off; off += 256;
+    pl->off_failed = off; off += align_up(F * 4, 256);
     int n1 = ceil_div(tif, kMaxLists);
     pl->off_listsA = off; off += align_up(F * n1 * kListCap * 8, 256);
     pl->off_listsB = off; off += align_up(F * n1 * kListCap * 8, 256);
@@ -1231,7 +1484,7 @@ extern "C" size_t vd_head_workspace_bytes(const VdHeadParams* p) {
 extern "C" int vd_head_launch_count(const VdHeadParams* hp) {
     HeadPlan pl;
     if (make_plan(hp, &pl) != VD_OK) return -1;
-    int n = 2;                                                // fused head kernel + per-frame top-k / NMS kernel
+    int n = getenv("VD_NO_SPEC") ? 2 : 4;                         // head kernel + per-frame NMS kernel (+ the exact fallback pair, idle in the steady state)
     for (int s = 0; s < hp->num_scales; ++s) if (hp->scale[s].tconv_weight_bf16) ++n;
     return n;
 }
@@ -1272,6 +1525,11 @@ extern "C" int vd_head_forward_stages(const VdHeadParams* hp, float* ids, float*
     kp.counts_hi = (uint32_t*)(ws + pl.off_counts_hi);
     kp.hint_hi = (uint32_t*)(ws + pl.off_hint_hi);
     kp.coarse = (uint32_t*)(ws + pl.off_coarse);
+    kp.spec_lists = (uint64_t*)(ws + pl.off_spec_lists);
+    kp.spec_cnt = (uint32_t*)(ws + pl.off_spec_cnt);
+    kp.spec_state = (uint32_t*)(ws + pl.off_spec_state);
+    uint32_t* failed = (uint32_t*)(ws + pl.off_failed);
+    const bool spec = getenv("VD_NO_SPEC") == nullptr;   // speculative frame-level threshold with the exact path as fallback
     kp.valid_thresh = hp->valid_thresh; kp.k = k; kp.cap = (k <= 448) ? 640 : kListCap;
     kp.stamps = getenv("VD_DEBUG_HEAD_STAMPS") ? (long long*)(ws + pl.off_listsA) : nullptr;   // profiling aid (unused merge area)
     if (const char* e = getenv("VD_DEBUG_SKIP_EPILOGUE")) kp.dbg = atoi(e);     // profiling aid: results are garbage
@@ -1290,9 +1548,9 @@ extern "C" int vd_head_forward_stages(const VdHeadParams* hp, float* ids, float*
     rc = make_maps(hp, pl, &maps);
     if (rc) return rc;
     if (stage_mask & VD_STAGE_HEAD) {
-        // no memset: the previous call's NMS kernel left the tile counter and the histogram zeroed (kWsMagic); a workspace
-        // in any other state is detected on the device and handled exactly (static schedule, streaming selection)
-        rc = launch_head<EPI_FILTER>(maps, kp, pl.C, stream);
+        // no memset: the previous call's NMS kernels left the counters / histograms zeroed (layout marker); a workspace in
+        // any other state is detected on the device and handled exactly
+        rc = spec ? launch_head<EPI_SPEC>(maps, kp, pl.C, stream) : launch_head<EPI_FILTER>(maps, kp, pl.C, stream);
         if (rc) return rc;
     }
     if (!(stage_mask & VD_STAGE_NMS)) return VD_OK;
@@ -1306,10 +1564,33 @@ extern "C" int vd_head_forward_stages(const VdHeadParams* hp, float* ids, float*
     static bool configured = false;
     if (!configured) {
         VD_CUDA(cudaFuncSetAttribute(nms_final_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)nms_hist_smem(VD_MAX_TOPK, VD_MAX_TOPK)));
-        if (!getenv("VD_DEBUG_NO_CARVEOUT") || atoi(getenv("VD_DEBUG_NO_CARVEOUT")) == 2) VD_CUDA(cudaFuncSetAttribute(nms_final_hist_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        VD_CUDA(cudaFuncSetAttribute(nms_spec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)nms_spec_smem(VD_MAX_TOPK, VD_MAX_TOPK)));
+        if (!getenv("VD_DEBUG_NO_CARVEOUT") || atoi(getenv("VD_DEBUG_NO_CARVEOUT")) == 2) {
+            VD_CUDA(cudaFuncSetAttribute(nms_final_hist_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+            VD_CUDA(cudaFuncSetAttribute(nms_spec_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        }
         configured = true;
     }
-    nms_final_hist_kernel<<<hp->frames, kNmsThreads, nms_hist_smem(k, hp->post_nms), stream>>>(kp.lists, kp.counts, kp.counts_hi, kp.hint_hi, kp.coarse, kp.tiles_per_frame, kp.hist, kp.tile_counter, kp.ws_magic, P, src, sink);
+    if (!spec) {
+        nms_final_hist_kernel<<<hp->frames, kNmsThreads, nms_hist_smem(k, hp->post_nms), stream>>>(
+            kp.lists, kp.counts, kp.counts_hi, kp.hint_hi, kp.coarse, kp.tiles_per_frame, kp.hist, kp.tile_counter, kp.ws_magic,
+            nullptr, nullptr, P, src, sink);
+        VD_LAUNCH_CHECK();
+        return VD_OK;
+    }
+    // 1. frames whose speculative list is provably complete are finished; the others are queued in `failed`
+    nms_spec_kernel<<<hp->frames, kNmsThreads, nms_spec_smem(k, hp->post_nms), stream>>>(
+        kp.spec_lists, kp.spec_cnt, kp.spec_state, failed, kp.tile_counter, kp.ws_magic, hp->valid_thresh, P, src, sink);
+    VD_LAUNCH_CHECK();
+    // 2. exact path over the queued frames (both kernels return at once when the queue is empty -- the steady state)
+    HeadKernelParams kf = kp;
+    kf.frame_list = failed; kf.frame_count = kp.spec_state + 2;
+    kf.total_tiles = kp.tiles_per_frame * hp->frames;              // grid sizing only: the device reads the real count
+    rc = launch_head<EPI_FILTER>(maps, kf, pl.C, stream);
+    if (rc) return rc;
+    nms_final_hist_kernel<<<hp->frames, kNmsThreads, nms_hist_smem(k, hp->post_nms), stream>>>(
+        kp.lists, kp.counts, kp.counts_hi, kp.hint_hi, kp.coarse, kp.tiles_per_frame, kp.hist, kp.tile_counter, kp.ws_magic,
+        failed, kp.spec_state, P, src, sink);
     VD_LAUNCH_CHECK();
     return VD_OK;
 }

@@ -39,6 +39,10 @@ constexpr int A_TILE_BYTES = BLOCK_M * BLOCK_K * 2;
 
 enum { EPI_FILTER = 0, EPI_DET = 1, EPI_PRED = 2, EPI_SPEC = 3 };
 constexpr int kSpecCap = 2048;                // candidates per frame the speculative path may emit
+#ifndef VD_SPEC_G
+#define VD_SPEC_G 3
+#endif
+constexpr int kFallbackCtas = 8;
 constexpr int kSpecStage = 64;                // per-warp staging entries per tile (double-buffered); more go straight to global memory
 constexpr int kHeadSharedBytes = 2048;          // room for struct HeadShared (barriers, scheduler ring, per-group state)
 
@@ -105,7 +109,7 @@ template <int EPI, int C, int NPAD> struct HeadCfg {
     static constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
     static constexpr int TMEM_STRIDE = NPAD <= 128 ? 128 : 256;
     // 3 groups (12 epilogue warps, 128 registers/thread) when three accumulators fit TMEM; else 2 groups
-    static constexpr int G = (EPI == EPI_FILTER && TMEM_STRIDE == 128) ? (NPAD <= 80 ? 4 : 3) : ((EPI == EPI_SPEC && TMEM_STRIDE == 128) ? 3 : 2);   // 4 groups only where 80 registers suffice
+    static constexpr int G = (EPI == EPI_FILTER && TMEM_STRIDE == 128) ? (NPAD <= 80 ? 4 : 3) : ((EPI == EPI_SPEC && TMEM_STRIDE == 128) ? VD_SPEC_G : 2);   // 4 groups only where 80 registers suffice
     static constexpr int THREADS = kEpiWarp0 * 32 + G * kEpiThreads;
     static constexpr int MAXREG = (THREADS > 448) ? 80 : ((THREADS > 320) ? 96 : 128);
     static constexpr int LIST_BYTES = (EPI == EPI_SPEC) ? G * 4 * 2 * kSpecStage * 8 : G * LIST_BUFS * kListCap * 8;
@@ -1424,6 +1428,9 @@ static int launch_head_t(const HeadMaps& maps, const HeadKernelParams& kp, cudaS
         configured = true;
     }
     int grid = sm_count(); if (grid > kp.total_tiles) grid = kp.total_tiles;
+    // the exact fallback of the speculative path is idle in the steady state: a handful of CTAs slip in between two
+    // head kernels instead of claiming every SM's shared memory (when frames did fail, they work through them slowly)
+    if (kp.frame_list && grid > kFallbackCtas) grid = kFallbackCtas;
     if (grid < 1) return VD_OK;
     kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(maps, kp);
     VD_LAUNCH_CHECK();

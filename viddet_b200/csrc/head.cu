@@ -208,10 +208,16 @@ head_kernel(const __grid_constant__ HeadMaps maps, const __grid_constant__ HeadK
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     auto gtime = []() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t) :: "memory"); return (long long)t; };
-    if (EPI == EPI_FILTER && p.stamps && threadIdx.x == 0) {
+    if ((EPI == EPI_FILTER || EPI == EPI_SPEC) && p.stamps && p.frame_list == nullptr && threadIdx.x == 0) {
         p.stamps[4096 + blockIdx.x * 4 + 0] = gtime();
         unsigned int sm; asm volatile("mov.u32 %0, %%smid;" : "=r"(sm)); p.stamps[4096 + blockIdx.x * 4 + 3] = (long long)sm;
     }
+
+    // Programmatic dependent launch: the next kernel of the stream (the head kernel of the next batch in the pipeline)
+    // may be scheduled as soon as this grid has started, so its CTAs take over SMs one by one as ours retire and run
+    // their setup early.  Everything that could depend on an earlier kernel comes after griddepcontrol.wait.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    if constexpr (EPI != EPI_SPEC) asm volatile("griddepcontrol.wait;" ::: "memory");
 
     // ---------------- one-time setup
     for (int i = threadIdx.x; i < VD_MAX_SCALES * NPAD; i += Cfg::THREADS) {
@@ -250,7 +256,8 @@ head_kernel(const __grid_constant__ HeadMaps maps, const __grid_constant__ HeadK
     __syncthreads();
     tc::fence_after_sync();
     const uint32_t tmem_base = sh->tmem_base;
-    if (EPI == EPI_FILTER && p.stamps && threadIdx.x == 0) p.stamps[4096 + blockIdx.x * 4 + 1] = gtime();
+    if constexpr (EPI == EPI_SPEC) asm volatile("griddepcontrol.wait;" ::: "memory");      // setup (weights only) overlapped the previous kernel's tail
+    if ((EPI == EPI_FILTER || EPI == EPI_SPEC) && p.stamps && p.frame_list == nullptr && threadIdx.x == 0) p.stamps[4096 + blockIdx.x * 4 + 1] = gtime();
 
     if (warp == 0) {
         // =========================== TMA producer ===========================
@@ -893,7 +900,7 @@ head_kernel(const __grid_constant__ HeadMaps maps, const __grid_constant__ HeadK
     __syncwarp();                // warps 0 / 1 ran single-lane role loops: reconverge before the aligned CTA barrier
     tc::fence_before_sync();
     __syncthreads();
-    if (EPI == EPI_FILTER && p.stamps && threadIdx.x == 0) p.stamps[4096 + blockIdx.x * 4 + 2] = gtime();
+    if ((EPI == EPI_FILTER || EPI == EPI_SPEC) && p.stamps && p.frame_list == nullptr && threadIdx.x == 0) p.stamps[4096 + blockIdx.x * 4 + 2] = gtime();
     if (warp == 1) tc::tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
     if (threadIdx.x == 0 && p.tile_counter != nullptr && p.tile_counter[2] == p.ws_magic) {
         // last CTA out re-arms the scheduler for the next launch on this workspace
@@ -1432,7 +1439,14 @@ static int launch_head_t(const HeadMaps& maps, const HeadKernelParams& kp, cudaS
     // head kernels instead of claiming every SM's shared memory (when frames did fail, they work through them slowly)
     if (kp.frame_list && grid > kFallbackCtas) grid = kFallbackCtas;
     if (grid < 1) return VD_OK;
-    kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(maps, kp);
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)Cfg::THREADS); cfg.dynamicSmemBytes = Cfg::SMEM_BYTES; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = getenv("VD_PDL") ? 1 : 0;   // measured slower in the pipeline (43.2 vs 38.6 us/step): off unless asked for
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    VD_CUDA(cudaLaunchKernelEx(&cfg, kern, maps, kp));
     VD_LAUNCH_CHECK();
     return VD_OK;
 }

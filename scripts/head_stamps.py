@@ -16,7 +16,7 @@ s = ss[2]
 hw = [(size // st) ** 2 for st in bench.STRIDES]
 anc = 3 * sum(hw); tif = sum((h + 127) // 128 for h in hw); F = frames
 def al(x): return (x + 255) // 256 * 256
-off = 256 + 256 + al(F * 4096 * 4) + al(F * anc * 16) + al(F * tif * 1024 * 8) + al(F * tif * 4) * 2 + al(F * 4) + al(F * 256) + al(F * 2048 * 8) + al(F * 4) + 256 + al(F * 4)
+off = 256 + 256 + al(F * 4096 * 4) + al(F * anc * 16) + al(F * tif * 1024 * 8) + al(F * tif * 4) * 2 + al(F * 4) + al(F * 256) + al(F * 2048 * 8) + al(F * 4) + 256 + al(F * 4) + al(F * 4)
 ntile = (F * tif + 147) // 148
 st = s._ws.view(torch.int64)[off // 8: off // 8 + 16 * ntile].cpu().view(ntile, 16)
 t0 = int(st[0, 0])

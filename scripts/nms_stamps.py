@@ -17,7 +17,7 @@ names = ["start", "hist scan", "stream lists", "sort", "tail start", "box gather
 # offset of listsA: hints 256 + hist + boxes + lists0 + counts0 (mirrors make_plan)
 F = frames; anc = 10647; tif = 30
 def al(x): return (x + 255) // 256 * 256
-off = 256 + 256 + al(F * 4096 * 4) + al(F * anc * 16) + al(F * tif * 1024 * 8) + al(F * tif * 4) * 2 + al(F * 4) + al(F * 256) + al(F * 2048 * 8) + al(F * 4) + 256 + al(F * 4)
+off = 256 + 256 + al(F * 4096 * 4) + al(F * anc * 16) + al(F * tif * 1024 * 8) + al(F * tif * 4) * 2 + al(F * 4) + al(F * 256) + al(F * 2048 * 8) + al(F * 4) + 256 + al(F * 4) + al(F * 4)
 st = ws[off // 8: off // 8 + 10].cpu().tolist()
 print("clocks:", st)
 prev = st[0]

@@ -15,7 +15,7 @@ torch.cuda.synchronize()
 hw = [(size // st) ** 2 for st in bench.STRIDES]
 anc = 3 * sum(hw); tif = sum((h + 127) // 128 for h in hw); F = frames
 def al(x): return (x + 255) // 256 * 256
-off = (256 + 256 + al(F * 4096 * 4) + al(F * anc * 16) + al(F * tif * 1024 * 8) + al(F * tif * 4) * 2 + al(F * 4) + al(F * 256) + al(F * 2048 * 8) + al(F * 4) + 256 + al(F * 4)) // 8
+off = (256 + 256 + al(F * 4096 * 4) + al(F * anc * 16) + al(F * tif * 1024 * 8) + al(F * tif * 4) * 2 + al(F * 4) + al(F * 256) + al(F * 2048 * 8) + al(F * 4) + 256 + al(F * 4) + al(F * 4)) // 8
 # consecutive pipelined steps: absolute windows
 for i in range(2): pipe.cycle()
 torch.cuda.synchronize()

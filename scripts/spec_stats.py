@@ -24,7 +24,6 @@ for call in range(6):
     s.run(viddet_b200._lib.VD_STAGE_NMS)
     torch.cuda.synchronize()
     st = s._ws[off_state: off_state + 20].view(torch.int32).cpu().tolist()
-    tau = struct.unpack("f", struct.pack("I", st_before[0] & 0xffffffff))[0]
-    tau2 = struct.unpack("f", struct.pack("I", st[0] & 0xffffffff))[0]
-    print("call %d: tau used %.5f, emitted per frame min %d med %d max %d, failed frames %d, next tau %.5f" % (
-        call, tau, int(cnt.min()), int(cnt.median()), int(cnt.max()), st[4], tau2))
+    tau = s._ws[off_state + 256: off_state + 256 + F * 4].view(torch.float32).cpu()
+    print("call %d: emitted per frame min %d med %d max %d, failed frames %d, next tau min %.4f med %.4f max %.4f" % (
+        call, int(cnt.min()), int(cnt.median()), int(cnt.max()), st[4], float(tau.min()), float(tau.median()), float(tau.max())))

@@ -85,7 +85,8 @@ struct HeadKernelParams {
     // EPI_SPEC (speculative frame-level threshold) and its exact fallback
     uint64_t* spec_lists;                // [frames][kSpecCap] keys of the candidates >= the call's threshold
     uint32_t* spec_cnt;                  // [frames] candidates emitted (may exceed kSpecCap = overflow); left zeroed by the NMS kernel
-    uint32_t* spec_state;                // [0] threshold (score bits) of this call, [1] accumulator for the next call's, [2] failed frames, [3] finished NMS CTAs, [4] failed frames of the last call (stats)
+    uint32_t* spec_tau;                  // [frames] score threshold (float bits) each frame slot is filtered with; written by the NMS kernels for the next call (any value is valid)
+    uint32_t* spec_state;                // [2] failed frames, [3] finished NMS CTAs, [4] failed frames of the last call (stats)
     const uint32_t* frame_list;          // EPI_FILTER as the fallback: frames to process = frame_list[0 .. *frame_count)
     const uint32_t* frame_count;
     long long* stamps;                   // profiling aid (VD_DEBUG_HEAD_STAMPS): clock64 per tile of CTA 0, [it][8]
@@ -349,11 +350,14 @@ head_kernel(const __grid_constant__ HeadMaps maps, const __grid_constant__ HeadK
         uint32_t spec_tb = 0u;                                // EPI_SPEC: the call's score threshold (float bits)
         if constexpr (EPI == EPI_SPEC) {
             const uint32_t floor_b = p.valid_thresh > 0.0f ? __float_as_uint(p.valid_thresh) : 0u;
-            const uint32_t hint = (p.tile_counter[2] == p.ws_magic) ? p.spec_state[0] : 0u;     // foreign workspace: the NMS kernel fails every frame anyway
+            const uint32_t hint = 0u;                         // (per-frame thresholds are read per tile)
             spec_tb = hint > floor_b ? hint : floor_b;
             if (spec_tb > 0x3f800001u) spec_tb = 0x3f800001u;
         }
         (void)spec_tb;
+        bool spec_ws_ok = false;
+        if constexpr (EPI == EPI_SPEC) spec_ws_ok = p.tile_counter[2] == p.ws_magic;
+        (void)spec_ws_ok;
         uint32_t spec_pend_base = 0u, spec_pend_n = 0u, spec_par = 0u; int spec_pend_f = 0;
         auto spec_flush = [&]() {                             // copy the previous tile's staged keys to their reserved range
             if constexpr (EPI == EPI_SPEC) {
@@ -386,6 +390,12 @@ head_kernel(const __grid_constant__ HeadMaps maps, const __grid_constant__ HeadK
             if (stamp) p.stamps[it * 16 + 3] = clock64();
             // global reads of the selection issued before the wait for the accumulator (their latency hides behind it)
             uint32_t pf_c0 = 0u, pf_c1 = 0u, pf_hint = 0u;
+            if constexpr (EPI == EPI_SPEC) {                     // this frame slot's threshold (foreign workspace: the NMS kernel fails every frame anyway)
+                const uint32_t floor_b = p.valid_thresh > 0.0f ? __float_as_uint(p.valid_thresh) : 0u;
+                const uint32_t hint = spec_ws_ok ? __ldcg(p.spec_tau + f) : 0u;
+                spec_tb = hint > floor_b ? hint : floor_b;
+                if (spec_tb > 0x3f800001u) spec_tb = 0x3f800001u;
+            }
             if constexpr (EPI == EPI_FILTER) {
                 if (ws_ok && et < 32) { const uint32_t* ch = p.coarse + (size_t)f * 64; pf_c0 = __ldcg(ch + 63 - 2 * lane); pf_c1 = __ldcg(ch + 62 - 2 * lane); }
                 pf_hint = __ldg(p.hint_hi + f);
@@ -1065,7 +1075,7 @@ __global__ void __maxnreg__(56)
 nms_final_hist_kernel(const uint64_t* __restrict__ lists, const uint32_t* __restrict__ counts, const uint32_t* __restrict__ counts_hi,
                       uint32_t* __restrict__ hint_hi, uint32_t* __restrict__ coarse, int n_lists,
                       uint32_t* __restrict__ hist, unsigned int* __restrict__ ctr, unsigned int ws_magic,
-                      const uint32_t* __restrict__ frame_list, uint32_t* __restrict__ spec_state, NmsParams P, FusedSource src, FusedSink sink) {
+                      const uint32_t* __restrict__ frame_list, uint32_t* __restrict__ spec_state, uint32_t* __restrict__ spec_tau, NmsParams P, FusedSource src, FusedSink sink) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
     const int k = P.k;
@@ -1211,21 +1221,19 @@ nms_final_hist_kernel(const uint64_t* __restrict__ lists, const uint32_t* __rest
     VD_STAMP(P, 3);
     const int n = (int)(m < (uint32_t)k ? m : (uint32_t)k);
     nms_tail_wave(n, f, P, src, sink, skeys, sbox, scls, sarea, skbox, skarea, skcls, wsh);
-    if (spec_state && tid == 0) atomicMin(&spec_state[1], hist_edge(bstar > 16u ? bstar - 16u : 0u) & 0x7fffffffu);   // this frame's wish for the next call's threshold
+    if (spec_tau && tid == 0) spec_tau[f] = hist_edge(bstar > 16u ? bstar - 16u : 0u) & 0x7fffffffu;   // the next call's threshold for this frame slot
     if (P.dbg && tid == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t) :: "memory"); P.dbg[8192 + f * 4 + 1] = (long long)t; }
     }   // active
     if (spec_state == nullptr) {
         if (blockIdx.x == 0 && tid == 0) { ctr[0] = 0u; ctr[1] = 0u; ctr[2] = ws_magic; }   // workspace is in its between-calls state (for this layout)
         return;
     }
-    // last CTA out closes the call: next call's threshold = the lowest wish of this call's frames, counters re-armed
+    // last CTA out closes the call: counters re-armed, workspace marked as being in its between-calls state
     __syncthreads();
     if (tid == 0) {
         __threadfence();
         if (atomicAdd(&spec_state[3], 1u) == gridDim.x - 1u) {
-            const uint32_t acc = spec_state[1];
-            if (acc != 0xffffffffu) spec_state[0] = acc;
-            spec_state[1] = 0xffffffffu; spec_state[4] = spec_state[2]; spec_state[2] = 0u; spec_state[3] = 0u;
+            spec_state[4] = spec_state[2]; spec_state[2] = 0u; spec_state[3] = 0u;
             ctr[0] = 0u; ctr[1] = 0u; ctr[2] = ws_magic;
         }
     }
@@ -1236,7 +1244,7 @@ nms_final_hist_kernel(const uint64_t* __restrict__ lists, const uint32_t* __rest
 // (or tau is the valid floor: then it simply holds every valid candidate).  Such frames are finished here (sort, wavefront
 // NMS, outputs); the others are queued for the exact path.  256 threads, 56 registers: shares SMs with a head kernel.
 __global__ void __maxnreg__(56)
-nms_spec_kernel(const uint64_t* __restrict__ spec_lists, uint32_t* __restrict__ spec_cnt, uint32_t* __restrict__ spec_state,
+nms_spec_kernel(const uint64_t* __restrict__ spec_lists, uint32_t* __restrict__ spec_cnt, uint32_t* __restrict__ spec_state, uint32_t* __restrict__ spec_tau,
                 uint32_t* __restrict__ failed, const unsigned int* __restrict__ ctr, unsigned int ws_magic, float valid_thresh,
                 NmsParams P, FusedSource src, FusedSink sink) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -1262,7 +1270,7 @@ nms_spec_kernel(const uint64_t* __restrict__ spec_lists, uint32_t* __restrict__ 
     const bool ws_ok = ctr[2] == ws_magic;
     const uint32_t cnt = spec_cnt[f];
     const uint32_t floor_b = valid_thresh > 0.0f ? __float_as_uint(valid_thresh) : 0u;
-    uint32_t tb = ws_ok ? spec_state[0] : 0u;
+    uint32_t tb = ws_ok ? spec_tau[f] : 0u;
     tb = tb > floor_b ? tb : floor_b;
     if (tb > 0x3f800001u) tb = 0x3f800001u;
     __syncthreads();
@@ -1271,7 +1279,7 @@ nms_spec_kernel(const uint64_t* __restrict__ spec_lists, uint32_t* __restrict__ 
         // foreign workspace: nothing in it can be trusted -> every frame takes the exact path, which also re-initialises it
         if (tid == 0) {
             failed[f] = (uint32_t)f;
-            if (f == 0) { spec_state[0] = 0u; spec_state[1] = 0xffffffffu; spec_state[2] = gridDim.x; spec_state[3] = 0u; }
+            if (f == 0) { spec_state[2] = gridDim.x; spec_state[3] = 0u; }
         }
         return;
     }
@@ -1300,7 +1308,7 @@ nms_spec_kernel(const uint64_t* __restrict__ spec_lists, uint32_t* __restrict__ 
     block_sort_u64_desc(skeys, SN);
     VD_STAMP(P, 3);
     const int n = (int)(cnt < (uint32_t)k ? cnt : (uint32_t)k);
-    // wish for the next call: the score at rank ~1.5 k of this frame, a little lower (the lowest wish of all frames wins)
+    // the next call's threshold for this frame slot: the score at rank ~1.5 k of this frame, a little lower
     if (tid == 0) {
         uint32_t d = floor_b;
         if (cnt >= (uint32_t)k) {
@@ -1308,7 +1316,7 @@ nms_spec_kernel(const uint64_t* __restrict__ spec_lists, uint32_t* __restrict__ 
             const uint32_t bits = (uint32_t)(skeys[r] >> 32) & 0x7fffffffu;
             d = bits > floor_b + 65536u ? bits - 65536u : floor_b;          // ~0.8 % lower
         }
-        atomicMin(&spec_state[1], d);
+        spec_tau[f] = d;
     }
     nms_tail_wave(n, f, P, src, sink, skeys, sbox, scls, sarea, skbox, skarea, skcls, wsh);
     if (P.dbg && tid == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t) :: "memory"); P.dbg[8192 + f * 4 + 1] = (long long)t; }
@@ -1331,7 +1339,7 @@ struct HeadPlan {
     HeadKernelParams kp;
     int n_pad, C;
     int merge_levels;
-    size_t off_hints, off_ctr, off_hist, off_boxes, off_lists0, off_counts0, off_counts_hi, off_hint_hi, off_coarse, off_spec_lists, off_spec_cnt, off_spec_state, off_failed, off_listsA, off_listsB, off_countsA, off_countsB, total;
+    size_t off_hints, off_ctr, off_hist, off_boxes, off_lists0, off_counts0, off_counts_hi, off_hint_hi, off_coarse, off_spec_lists, off_spec_cnt, off_spec_state, off_spec_tau, off_failed, off_listsA, off_listsB, off_countsA, off_countsB, total;
 };
 
 static int head_npad(int C) { int n = 3 * (5 + C); return (n + 15) / 16 * 16; }
@@ -1395,6 +1403,7 @@ static int make_plan(const VdHeadParams* hp, HeadPlan* pl) {
     pl->off_spec_lists = off; off += align_up(F * kSpecCap * 8, 256);
     pl->off_spec_cnt = off; off += align_up(F * 4, 256);
     pl->off_spec_state = off; off += 256;
+    pl->off_spec_tau = off; off += align_up(F * 4, 256);
     pl->off_failed = off; off += align_up(F * 4, 256);
     int n1 = ceil_div(tif, kMaxLists);
     pl->off_listsA = off; off += align_up(F * n1 * kListCap * 8, 256);
@@ -1549,6 +1558,7 @@ extern "C" int vd_head_forward_stages(const VdHeadParams* hp, float* ids, float*
     kp.spec_lists = (uint64_t*)(ws + pl.off_spec_lists);
     kp.spec_cnt = (uint32_t*)(ws + pl.off_spec_cnt);
     kp.spec_state = (uint32_t*)(ws + pl.off_spec_state);
+    kp.spec_tau = (uint32_t*)(ws + pl.off_spec_tau);
     uint32_t* failed = (uint32_t*)(ws + pl.off_failed);
     const bool spec = getenv("VD_NO_SPEC") == nullptr;   // speculative frame-level threshold with the exact path as fallback
     kp.valid_thresh = hp->valid_thresh; kp.k = k; kp.cap = (k <= 448) ? 640 : kListCap;
@@ -1595,13 +1605,13 @@ extern "C" int vd_head_forward_stages(const VdHeadParams* hp, float* ids, float*
     if (!spec) {
         nms_final_hist_kernel<<<hp->frames, kNmsThreads, nms_hist_smem(k, hp->post_nms), stream>>>(
             kp.lists, kp.counts, kp.counts_hi, kp.hint_hi, kp.coarse, kp.tiles_per_frame, kp.hist, kp.tile_counter, kp.ws_magic,
-            nullptr, nullptr, P, src, sink);
+            nullptr, nullptr, nullptr, P, src, sink);
         VD_LAUNCH_CHECK();
         return VD_OK;
     }
     // 1. frames whose speculative list is provably complete are finished; the others are queued in `failed`
     nms_spec_kernel<<<hp->frames, kNmsThreads, nms_spec_smem(k, hp->post_nms), stream>>>(
-        kp.spec_lists, kp.spec_cnt, kp.spec_state, failed, kp.tile_counter, kp.ws_magic, hp->valid_thresh, P, src, sink);
+        kp.spec_lists, kp.spec_cnt, kp.spec_state, kp.spec_tau, failed, kp.tile_counter, kp.ws_magic, hp->valid_thresh, P, src, sink);
     VD_LAUNCH_CHECK();
     // 2. exact path over the queued frames (both kernels return at once when the queue is empty -- the steady state)
     HeadKernelParams kf = kp;
@@ -1611,7 +1621,7 @@ extern "C" int vd_head_forward_stages(const VdHeadParams* hp, float* ids, float*
     if (rc) return rc;
     nms_final_hist_kernel<<<hp->frames, kNmsThreads, nms_hist_smem(k, hp->post_nms), stream>>>(
         kp.lists, kp.counts, kp.counts_hi, kp.hint_hi, kp.coarse, kp.tiles_per_frame, kp.hist, kp.tile_counter, kp.ws_magic,
-        failed, kp.spec_state, P, src, sink);
+        failed, kp.spec_state, kp.spec_tau, P, src, sink);
     VD_LAUNCH_CHECK();
     return VD_OK;
 }

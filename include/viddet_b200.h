@@ -129,15 +129,21 @@ typedef struct VdHeadParams {
     VdHeadScale scale[VD_MAX_SCALES];
 } VdHeadParams;
 
-/* Workspace contract.  vd_head_forward keeps state in its workspace BETWEEN calls: warm-start hints for the
- * per-tile selection, the dynamic tile-scheduler counters, per-frame score histograms (left zeroed by the NMS
- * kernel, so no memset runs per call) and a marker that says so for the layout of the last call.  Hence:
+/* How the fused call works (and what the workspace is for).  The head kernel filters every frame with a per-frame-slot
+ * score threshold left by the previous call and appends the survivors to the frame's candidate list; the NMS kernel
+ * proves per frame that the list holds the exact top-k (no overflow, >= k candidates at or above the threshold) and
+ * finishes those frames.  Frames that cannot be proven -- all of them on a first call, a few when the data drifts --
+ * are redone in the same call by the exact path (per-tile exact top-k selection), which also leaves new thresholds.
+ * Results are therefore exact for any input; only the speed depends on the thresholds.
+ *
+ * Workspace contract.  vd_head_forward keeps state in its workspace BETWEEN calls: those thresholds, warm-start hints of
+ * the exact path, the tile-scheduler counters, per-frame histograms / counters (left zeroed by the NMS kernels, so no
+ * memset runs per call) and a marker that says so for the layout of the last call.  Hence:
  *   - pass the same buffer to consecutive calls and do not write to it in between (do not share it with
  *     vd_box_nms or other streams' calls);
  *   - a zero-filled buffer, a buffer last used with other parameters, or arbitrary foreign content are all
- *     detected on the device and handled exactly (static tile schedule, streaming selection) -- slower for
- *     that one call, never wrong;
- *   - hints only change speed, never results. */
+ *     detected on the device and handled exactly (every frame takes the exact path) -- slower for
+ *     that one call, never wrong. */
 size_t vd_head_workspace_bytes(const VdHeadParams* p);
 /* ids (frames, post_nms, 1), scores (frames, post_nms, 1), bboxes (frames, post_nms, 4) fp32;
  * keep_rows_or_null (frames, post_nms) int32 = row in the (frames, rows, 6) tensor of each output
@@ -154,6 +160,10 @@ int vd_head_forward(const VdHeadParams* p, float* ids, float* scores, float* bbo
 int vd_head_forward_stages(const VdHeadParams* p, float* ids, float* scores, float* bboxes,
                            int32_t* keep_rows_or_null, void* workspace, size_t workspace_bytes,
                            void* stream, int stage_mask);
+/* Byte offset, inside the workspace, of eight uint32 statistics of the LAST completed call: word [4] = number of frames
+ * whose speculative candidate list could not be proven complete and that were redone by the exact path (0 in the steady
+ * state; all frames on the first call).  For tests and monitoring; reading it needs a stream synchronisation. */
+size_t vd_head_stats_offset(const VdHeadParams* p);
 /* Number of kernels one vd_head_forward call launches for these parameters (-1 on bad params). */
 int vd_head_launch_count(const VdHeadParams* p);
 /* Same conv + decode, but materialises the reference's (frames, rows, 6) detection tensor

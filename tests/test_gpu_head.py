@@ -196,6 +196,52 @@ def test_full_size_steady_state_bit_exact(C, size, B):
         assert bool(((keep >= 0) == (sc > 0.01)).all())
 
 
+def test_speculative_path_and_exact_fallback_under_drift():
+    """First call: no thresholds -> every frame is redone by the exact path.  Same data again: no frame is.  Then the
+    data drifts (scores drop: too few candidates above the old thresholds; scores rise: the lists overflow; heavy ties):
+    the affected frames fall back, results stay bit-identical to box_nms(detections()), and the next call is fast again."""
+    import viddet_b200
+    rng = np.random.RandomState(21)
+    C, B, size = 20, 6, 416
+    ws, bs = make_pred_weights(rng, C, bias_scale=0.05)
+    head = build_head(C, ws, bs)
+    head.set_nms(0.45, 400, 100)
+    base = make_tips(rng, B, size=size)
+    sess = head.session([cuda(t) for t in base], return_keep=True)
+
+    def check(tips_np, expect_redone):
+        for dst, src in zip(sess.tips, tips_np):
+            dst.copy_(viddet_b200.to_nhwc_bf16(cuda(src)))
+        det = head.detections([cuda(t) for t in tips_np])
+        out, rec = viddet_b200.box_nms(det, overlap_thresh=0.45, valid_thresh=0.01, topk=400, id_index=0, score_index=1,
+                                       coord_start=2, force_suppress=False, return_record=True)
+        sess.keep.fill_(-7)
+        sess.run()
+        redone = sess.redone_frames()
+        assert torch.equal(sess.keep, rec[:, :100])
+        assert torch.equal(sess.scores.view(torch.int32), out[:, :100, 1:2].contiguous().view(torch.int32))
+        assert torch.equal(sess.bboxes.view(torch.int32), out[:, :100, 2:].contiguous().view(torch.int32))
+        if expect_redone is not None:
+            assert redone == expect_redone, (redone, expect_redone)
+        return redone
+
+    check(base, B)                                   # cold: all frames through the exact path
+    check(base, 0)                                   # thresholds in place
+    low = [bf16_round(t * 0.6) for t in base]        # scores drop
+    assert check(low, None) > 0
+    check(low, 0)
+    high = [bf16_round(t * 1.6) for t in base]       # scores rise: more than 2048 candidates above the old thresholds
+    assert check(high, None) > 0
+    check(high, 0)
+    mixed = [np.concatenate([a[:3], b[3:]]) for a, b in zip(base, high)]     # only some frames change
+    r = check(mixed, None)
+    assert 0 < r < B
+    ties = [np.full_like(t, 0.25) for t in base]     # every pixel identical: tie clusters of HW candidates
+    check(ties, None)
+    check(ties, None)
+    check(base, None)
+
+
 def test_pipeline_matches_serial_calls():
     """HeadPipeline (head kernel of batch j+1 overlapped with the NMS kernel of batch j, several rotations per
     graph) must leave exactly the serial call's outputs in every session of the ring."""

@@ -61,6 +61,7 @@ SIGNATURES = {
     "vd_head_forward": (_i, [ctypes.POINTER(VdHeadParams), _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "vd_head_forward_stages": (_i, [ctypes.POINTER(VdHeadParams), _vp, _vp, _vp, _vp, _vp, _sz, _vp, _i]),
     "vd_head_launch_count": (_i, [ctypes.POINTER(VdHeadParams)]),
+    "vd_head_stats_offset": (_sz, [ctypes.POINTER(VdHeadParams)]),
     "vd_head_detections": (_i, [ctypes.POINTER(VdHeadParams), _vp, _vp, _sz, _vp]),
     "vd_temporal_conv": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _f, _vp]),
     "vd_temporal_pool": (_i, [_vp, _vp, _i, _i, _i64, _i, _vp]),

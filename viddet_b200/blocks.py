@@ -530,6 +530,21 @@ class HeadSession:
         self._graphs[int(stage_mask)].replay()
         return self.ids, self.scores, self.bboxes
 
+    def rebind(self, tips):
+        """Point the session at other resident input tensors of the same shapes (already channels-last bf16); the workspace
+        (thresholds, hints) is kept.  Not for captured graphs: they hold the old pointers."""
+        assert len(tips) == len(self.tips)
+        for i, (t, old) in enumerate(zip(tips, self.tips)):
+            assert t.shape == old.shape and t.dtype == torch.bfloat16 and t.is_contiguous(memory_format=torch.channels_last)
+            self.params.scale[i].tip_nhwc_bf16 = t.data_ptr()
+        self.tips = list(tips)
+
+    def redone_frames(self):
+        """Frames of the last completed call that the exact path had to redo (synchronises; 0 in the steady state)."""
+        off = load().vd_head_stats_offset(ctypes.byref(self.params))
+        torch.cuda.synchronize()
+        return int(self._ws[off + 16: off + 20].view(torch.int32).item())
+
     def packed(self):
         """(frames, post_nms, 6) rows [id, score, x1, y1, x2, y2] -- the box_nms row layout."""
         return torch.cat([self.ids, self.scores, self.bboxes], dim=-1)

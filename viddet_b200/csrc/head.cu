@@ -1308,11 +1308,11 @@ nms_spec_kernel(const uint64_t* __restrict__ spec_lists, uint32_t* __restrict__ 
     block_sort_u64_desc(skeys, SN);
     VD_STAMP(P, 3);
     const int n = (int)(cnt < (uint32_t)k ? cnt : (uint32_t)k);
-    // the next call's threshold for this frame slot: the score at rank ~1.5 k of this frame, a little lower
+    // the next call's threshold for this frame slot: the score at rank ~2 k of this frame, a little lower
     if (tid == 0) {
         uint32_t d = floor_b;
         if (cnt >= (uint32_t)k) {
-            const uint32_t r = min(cnt - 1u, (uint32_t)(k + k / 2));
+            const uint32_t r = min(cnt - 1u, (uint32_t)(2 * k));            // aim at ~2k candidates: room for the next frame in this slot to differ both ways
             const uint32_t bits = (uint32_t)(skeys[r] >> 32) & 0x7fffffffu;
             d = bits > floor_b + 65536u ? bits - 65536u : floor_b;          // ~0.8 % lower
         }
@@ -1509,6 +1509,12 @@ extern "C" size_t vd_head_workspace_bytes(const VdHeadParams* p) {
     HeadPlan pl;
     if (make_plan(p, &pl) != VD_OK) return 0;
     return pl.total;
+}
+
+extern "C" size_t vd_head_stats_offset(const VdHeadParams* hp) {
+    HeadPlan pl;
+    if (make_plan(hp, &pl) != VD_OK) return 0;
+    return pl.off_spec_state;
 }
 
 extern "C" int vd_head_launch_count(const VdHeadParams* hp) {

@@ -178,6 +178,17 @@ int vd_temporal_conv(const void* x_bf16, void* y_bf16, int B, int T, int H, int 
                      const void* weight_bf16, const float* scale, const float* shift,
                      float slope, void* stream);
 
+/* Conv-BN-LeakyReLU cell of YOLODetectionBlockV3: replaces `_conv2d` (layers.py:63-70) and `_conv3d`
+ * (layers.py:73-79) as stacked at yolo3_temporal.py:198-239 -- Conv(no bias, stride 1, zero 'same' padding, kernel extents
+ * kt,kh,kw each 1 or 3) + inference BatchNorm (folded into scale/shift) + LeakyReLU(slope).  x (B,T,H,W,Cin), y (B,T,H,W,Cout)
+ * bf16 channels-last (T = 1 for 2-D convs); weight (kt*kh*kw, Cout, Cin) bf16 [tap][cout][cin], tap = (it*kh+iy)*kw+ix
+ * (cross-correlation order of the Gluon weight (Cout,Cin,kt,kh,kw)); Cin % 64 == 0, Cout % 128 == 0, Cout <= 1024. */
+int vd_conv_bn_lrelu(const void* x_bf16, void* y_bf16, int B, int T, int H, int W, int Cin, int Cout,
+                     int kt, int kh, int kw, const void* weight_bf16, const float* scale, const float* shift,
+                     float slope, void* stream);
+/* The BW x BH pixel box (BW*BH <= 128) one MMA tile of vd_conv_bn_lrelu covers on an H x W map (for roofline maths). */
+int vd_conv_tile_box(int H, int W, int* BW, int* BH);
+
 /* TemporalPooling 'direct' (layers.py:202-205): (B,K,H,W,C) bf16 -> (B,H,W,C) bf16. */
 int vd_temporal_pool(const void* x_bf16, void* y_bf16, int B, int K, int64_t inner, int mode,
                      void* stream);

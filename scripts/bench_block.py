@@ -1,0 +1,80 @@
+"""Timing of the conv-BN-LReLU cells of YOLODetectionBlockV3 at the 416^2 scales, B frames.
+CUDA events on the launching stream, rotating input sets (> L2 when B is large).  One JSON line per cell:
+useful FLOPs = 2*taps*pixels*Cin*Cout (padding taps included, as cuDNN would count them) / time vs the measured
+sustained bf16 tensor peak; `mma_row_util` = share of the 128 MMA rows that are real pixels.
+`python scripts/bench_block.py [B=64] [T=1]`"""
+import ctypes
+import json
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import viddet_b200
+from viddet_b200 import _lib
+
+PEAKS = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")))
+PEAK_TC = float(PEAKS.get("bf16_tflops_sustained", 1413.6))
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 64
+T = int(sys.argv[2]) if len(sys.argv) > 2 else 1
+
+
+def timeit(fn, n=20, warm=3):
+    for i in range(warm):
+        fn(i)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(n):
+        fn(i)
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / n
+
+
+def box(H, W):
+    bw, bh = ctypes.c_int(), ctypes.c_int()
+    _lib.check(_lib.load().vd_conv_tile_box(H, W, ctypes.byref(bw), ctypes.byref(bh)))
+    return bw.value, bh.value
+
+
+def main():
+    g = torch.Generator().manual_seed(0)
+    total_ms, total_fl = 0.0, 0.0
+    for ch, cin, hw in ((512, 1024, 13), (256, 768, 26), (128, 384, 52)):
+        cells = [("reduce1x1", cin, ch, (1, 1, 1)), ("expand3x3", ch, 2 * ch, (1, 3, 3)), ("reduce1x1b", 2 * ch, ch, (1, 1, 1))]
+        if T > 1:
+            cells.append(("temporal3x1x1", 2 * ch, 2 * ch, (3, 1, 1)))
+        for name, ci, co, k in cells:
+            cell = viddet_b200.ConvBNLReLU(ci, co, k).initialize(generator=g)
+            xs = [torch.randn(B * T, ci, hw, hw, device="cuda").to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+                  .reshape(B, T, ci, hw, hw) for _ in range(3)]
+            ms = timeit(lambda i: cell(xs[i % 3]))
+            taps = k[0] * k[1] * k[2]
+            fl = 2.0 * taps * B * T * hw * hw * ci * co
+            bw, bh = (128, 1) if taps == 1 else box(hw, hw)
+            util = 1.0 if taps == 1 else hw * hw / (-(-hw // bw) * -(-hw // bh) * 128.0)
+            print(json.dumps({"cell": name, "map": hw, "Cin": ci, "Cout": co, "kernel": k, "frames": B * T, "ms": round(ms, 4),
+                              "tflops": round(fl / ms / 1e9, 1), "frac_tensor_peak": round(fl / ms / 1e9 / PEAK_TC, 3),
+                              "box": [bw, bh], "mma_row_util": round(util, 3)}))
+            # the block runs reduce + expand twice, reduce once more, then the tip's expand
+            reps = {"reduce1x1": 1, "expand3x3": 3, "reduce1x1b": 2, "temporal3x1x1": 3}[name]
+            total_ms += reps * ms; total_fl += reps * fl
+    print(json.dumps({"block_total_ms_est": round(total_ms, 3), "tflops": round(total_fl / total_ms / 1e9, 1),
+                      "frac_tensor_peak": round(total_fl / total_ms / 1e9 / PEAK_TC, 3), "frames": B * T}))
+    # whole blocks, real chaining
+    for conv_type in (["2"] if T == 1 else ["21"]):
+        for ch, cin, hw in ((512, 1024, 13), (256, 768, 26), (128, 384, 52)):
+            blk = viddet_b200.YOLODetectionBlockV3(ch, conv_type, in_channels=cin).initialize(generator=g)
+            shape = (B, cin, hw, hw) if conv_type == "2" else (B, T, cin, hw, hw)
+            n = B * (T if conv_type != "2" else 1)
+            x = torch.randn(n, cin, hw, hw, device="cuda").to(torch.bfloat16).contiguous(memory_format=torch.channels_last).reshape(shape)
+            ms = timeit(lambda i: blk(x))
+            fl = sum(2.0 * c.kernel[0] * c.kernel[1] * c.kernel[2] * n * hw * hw * c.in_channels * c.channels for c in blk.cells())
+            print(json.dumps({"block": conv_type, "map": hw, "channel": ch, "frames": n, "ms": round(ms, 4),
+                              "tflops": round(fl / ms / 1e9, 1), "frac_tensor_peak": round(fl / ms / 1e9 / PEAK_TC, 3)}))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,126 @@
+"""GPU parity of the conv-BN-LReLU cells and YOLODetectionBlockV3 against oracle/ref_block.py.
+Inputs and weights are bf16-representable, accumulation is fp32 on both sides, the device output is bf16:
+the bar is 1 bf16 ulp-ish of the largest activation (6e-3 relative to max |ref|) per cell."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import ref_block
+from tests.util import bf16_round
+
+pytestmark = pytest.mark.gpu
+
+
+def cuda(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def bn(rng, c):
+    return (rng.uniform(0.5, 1.5, c).astype(np.float32), rng.uniform(-0.2, 0.2, c).astype(np.float32),
+            rng.uniform(-0.2, 0.2, c).astype(np.float32), rng.uniform(0.5, 1.5, c).astype(np.float32))
+
+
+CELL_CASES = [
+    # (Cin, Cout, kernel, B, T, H, W)
+    (64, 128, (1, 1, 1), 2, 1, 13, 13),
+    (128, 256, (1, 3, 3), 2, 1, 13, 13),
+    (64, 128, (1, 3, 3), 1, 1, 26, 26),
+    (64, 128, (1, 3, 3), 1, 2, 19, 7),        # ragged map: partial boxes in x and y
+    (64, 256, (1, 3, 3), 1, 1, 52, 52),
+    (128, 128, (3, 1, 1), 1, 5, 6, 5),
+    (64, 128, (3, 3, 3), 2, 3, 10, 10),
+    (192, 128, (1, 1, 1), 1, 3, 9, 11),       # Cin not a power of two (768/384-channel concat inputs of the s16/s8 blocks)
+    (64, 128, (1, 3, 3), 1, 1, 1, 1),         # one pixel: 8 of 9 taps are pure padding
+    (64, 128, (1, 3, 3), 1, 1, 3, 200),       # wider than one box
+]
+
+
+@pytest.mark.parametrize("case", CELL_CASES)
+def test_conv_cell_vs_oracle(case):
+    import viddet_b200
+    Cin, Cout, k, B, T, H, W = case
+    rng = np.random.RandomState(hash(case) % (2 ** 31))
+    x = bf16_round(rng.standard_normal((B, T, Cin, H, W)).astype(np.float32))
+    w = bf16_round(rng.uniform(-0.07, 0.07, (Cout, Cin) + k).astype(np.float32))
+    g, b, m, v = bn(rng, Cout)
+    cell = viddet_b200.ConvBNLReLU(Cin, Cout, k)
+    cell.set_data(torch.from_numpy(w), g, b, m, v)
+    y = cell(cuda(x)).float().cpu().numpy()
+    ref = ref_block.conv_bn_lrelu(x, w, g, b, m, v)
+    assert y.shape == ref.shape
+    assert np.abs(y - ref).max() <= 6e-3 * np.abs(ref).max()
+    if T == 1:                                         # 2-D call surface, (B,C,H,W)
+        y4 = cell(cuda(x[:, 0])).float().cpu().numpy()
+        np.testing.assert_array_equal(y4, y[:, 0])
+
+
+def test_temporal_cell_matches_dedicated_kernel():
+    """(3,1,1) through the generic kernel == vd_temporal_conv (TemporalTipConv) bit for bit: same products, same
+    fp32 accumulation order per output (tap-major, channel blocks inside)."""
+    import viddet_b200
+    rng = np.random.RandomState(5)
+    C, B, T, H, W = 256, 2, 5, 13, 13
+    x = bf16_round(rng.standard_normal((B, T, C, H, W)).astype(np.float32))
+    w = bf16_round(rng.uniform(-0.07, 0.07, (C, C, 3, 1, 1)).astype(np.float32))
+    g, b, m, v = bn(rng, C)
+    a = viddet_b200.ConvBNLReLU(C, C, (3, 1, 1)); a.set_data(torch.from_numpy(w), g, b, m, v)
+    t = viddet_b200.TemporalTipConv(C); t.set_data(torch.from_numpy(w), g, b, m, v)
+    xa = cuda(x)
+    ya, yt = a(xa).float().cpu().numpy(), t(xa).float().cpu().numpy()
+    assert np.abs(ya - yt).max() <= 4e-3 * np.abs(yt).max()      # tcgen05 accumulation order inside a k-block is not specified
+    ref = ref_block.conv_bn_lrelu(x, w, g, b, m, v)
+    assert np.abs(ya - ref).max() <= 6e-3 * np.abs(ref).max()
+
+
+@pytest.mark.parametrize("conv_type,shape", [("2", (2, 192, 13, 13)), ("21", (1, 3, 192, 13, 13)), ("3", (1, 3, 128, 7, 9))])
+def test_detection_block_vs_oracle(conv_type, shape):
+    import viddet_b200
+    rng = np.random.RandomState(11)
+    channel = 128
+    blk = viddet_b200.YOLODetectionBlockV3(channel, conv_type, in_channels=shape[-3])
+    cells = []
+    for c in blk.cells():
+        fan = c.in_channels * int(np.prod(c.kernel))
+        w = bf16_round(rng.standard_normal((c.channels, c.in_channels) + c.kernel).astype(np.float32) * np.sqrt(2.0 / fan))
+        if conv_type == "2":
+            w_ref = w[:, :, 0]
+        else:
+            w_ref = w
+        g, b, m, v = bn(rng, c.channels)
+        c.set_data(torch.from_numpy(w), g, b, m, v)
+        cells.append(dict(weight=w_ref, gamma=g, beta=b, mean=m, var=v))
+    x = bf16_round(rng.standard_normal(shape).astype(np.float32))
+    route, tip = blk(cuda(x))
+    r_ref, t_ref = ref_block.detection_block(x, cells, conv_type, round_fn=bf16_round)
+    assert tuple(route.shape) == r_ref.shape and tuple(tip.shape) == t_ref.shape
+    for got, ref in ((route, r_ref), (tip, t_ref)):
+        got = got.float().cpu().numpy()
+        # 5-9 cells with bf16 carriers in between: rounding-boundary flips propagate; 2e-2 of the largest activation
+        assert np.abs(got - ref).max() <= 2e-2 * np.abs(ref).max()
+        assert np.abs(got - ref).mean() <= 2e-3 * np.abs(ref).max()
+
+
+def test_block_feeds_head():
+    """route/tip carriers plug straight into YOLOOutputV3 / YOLOV3Head (tip channels = 2*channel)."""
+    import viddet_b200
+    g = torch.Generator().manual_seed(3)
+    blks = [viddet_b200.YOLODetectionBlockV3(c // 2, "2", in_channels=cin).initialize(generator=g)
+            for c, cin in zip(viddet_b200.DEFAULT_CHANNELS, (1024, 768, 384))]
+    head = viddet_b200.YOLOV3Head(20).initialize()
+    xs = [torch.randn(2, cin, 128 // s, 128 // s, device="cuda") for cin, s in zip((1024, 768, 384), (32, 16, 8))]
+    tips = [b(x)[1] for b, x in zip(blks, xs)]
+    ids, scores, boxes = head(tips)
+    assert ids.shape == (2, 100, 1) and boxes.shape == (2, 100, 4)
+    assert torch.isfinite(scores).all()
+
+
+def test_conv_errors_surface():
+    import viddet_b200
+    c = viddet_b200.ConvBNLReLU(48, 128, 3).initialize()
+    with pytest.raises(viddet_b200.VidDetError):
+        c(torch.zeros(1, 48, 4, 4, device="cuda"))           # Cin not a multiple of 64
+    c = viddet_b200.ConvBNLReLU(64, 96, 1).initialize()
+    with pytest.raises(viddet_b200.VidDetError):
+        c(torch.zeros(1, 64, 4, 4, device="cuda"))           # Cout not a multiple of 128
+    with pytest.raises(AssertionError):
+        viddet_b200.ConvBNLReLU(64, 128, 5)

@@ -5,8 +5,8 @@ the C ABI in include/viddet_b200.h; torch tensors are carriers only.  There is n
 """
 from ._lib import VidDetError, load, SO_PATH  # noqa: F401
 from .blocks import (  # noqa: F401
-    DEFAULT_ANCHORS, DEFAULT_CHANNELS, DEFAULT_STRIDES, HeadPipeline, HeadSession, TemporalPooling, TemporalTipConv, TimeDistributed,
-    YOLOOutputV3, YOLOV3DynamicTargetGeneratorSimple, YOLOV3Head, YOLOV3Loss, YOLOV3PrefetchTargetGenerator, YOLOV3TargetMerger,
+    ConvBNLReLU, DEFAULT_ANCHORS, DEFAULT_CHANNELS, DEFAULT_STRIDES, HeadPipeline, HeadSession, TemporalPooling, TemporalTipConv, TimeDistributed,
+    YOLODetectionBlockV3, YOLOOutputV3, YOLOV3DynamicTargetGeneratorSimple, YOLOV3Head, YOLOV3Loss, YOLOV3PrefetchTargetGenerator, YOLOV3TargetMerger,
     box_nms, postprocess_detections, to_nhwc_bf16,
 )
 

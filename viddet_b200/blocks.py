@@ -11,6 +11,8 @@ YOLOOutputV3                 (yolo3.py:25-199)                YOLOOutputV3
 TimeDistributed              (layers.py:208-264)              TimeDistributed
 TemporalPooling              (layers.py:161-205)              TemporalPooling
 Conv('21') temporal cell     (layers.py:82-89)                TemporalTipConv
+_conv2d / _conv3d cells      (layers.py:63-79)                ConvBNLReLU
+YOLODetectionBlockV3         (yolo3_temporal.py:184-239)      YOLODetectionBlockV3
 YOLOV3 / YOLOV3Temporal tail (yolo3.py:496,522-556;           YOLOV3Head
                               yolo3_temporal.py:468,542-555)
 YOLOV3PrefetchTargetGenerator(yolo_target.py:13-148)          YOLOV3PrefetchTargetGenerator
@@ -322,6 +324,137 @@ class TemporalTipConv:
         check(load().vd_temporal_conv(ptr(xb), ptr(y), B, T, H, W, C, ptr(self._w_taps), ptr(self._scale),
                                       ptr(self._shift), float(self.slope), stream_ptr()))
         return y.reshape(B, T, C, H, W)
+
+
+# ------------------------------------------------------------------------------------------------
+# detection block (the convs in front of the tip)
+# ------------------------------------------------------------------------------------------------
+class ConvBNLReLU:
+    """`_conv2d` (layers.py:63-70) / `_conv3d` (layers.py:73-79): Conv(no bias, stride 1, zero 'same' padding) +
+    BatchNorm(eps 1e-5, inference statistics) + LeakyReLU(0.1).  kernel = k or (kh,kw) or (kt,kh,kw), extents 1 or 3.
+    Parameters in Gluon layout: weight (Cout,Cin,kh,kw) / (Cout,Cin,kt,kh,kw), gamma, beta, running_mean, running_var."""
+
+    def __init__(self, in_channels, channel, kernel, epsilon=1e-5, slope=0.1):
+        if isinstance(kernel, int):
+            kernel = (1, kernel, kernel)
+        kernel = tuple(kernel)
+        if len(kernel) == 2:
+            kernel = (1,) + kernel
+        assert len(kernel) == 3 and all(k in (1, 3) for k in kernel), "kernel extents must be 1 or 3"
+        self.in_channels, self.channels, self.kernel = in_channels, channel, kernel
+        self.epsilon, self.slope = epsilon, slope
+        self.weight = None
+        self.gamma = torch.ones(channel, device="cuda")
+        self.beta = torch.zeros(channel, device="cuda")
+        self.running_mean = torch.zeros(channel, device="cuda")
+        self.running_var = torch.ones(channel, device="cuda")
+        self._w_taps = self._scale = self._shift = None
+
+    def initialize(self, scale=0.07, generator=None):
+        shape = (self.channels, self.in_channels) + self.kernel
+        self.set_data((torch.rand(shape, generator=generator) * 2 - 1) * scale)
+        return self
+
+    def set_data(self, weight, gamma=None, beta=None, running_mean=None, running_var=None):
+        co, ci = self.channels, self.in_channels
+        kt, kh, kw = self.kernel
+        self.weight = torch.as_tensor(weight).detach().to(torch.float32).cuda().reshape(co, ci, kt, kh, kw)
+        for name, v in (("gamma", gamma), ("beta", beta), ("running_mean", running_mean), ("running_var", running_var)):
+            if v is not None:
+                setattr(self, name, torch.as_tensor(v).detach().to(torch.float32).cuda().contiguous())
+        # [tap][cout][cin] bf16, tap = (it*kh + iy)*kw + ix; folded inference BatchNorm
+        self._w_taps = self.weight.permute(2, 3, 4, 0, 1).reshape(kt * kh * kw, co, ci).contiguous().to(torch.bfloat16)
+        self._scale = (self.gamma / torch.sqrt(self.running_var + self.epsilon)).contiguous()
+        self._shift = (self.beta - self.running_mean * self._scale).contiguous()
+
+    def __call__(self, x):
+        """x (B,Cin,H,W) or (B,T,Cin,H,W) -> same leading shape with Cout channels, bf16, channels-last per frame."""
+        _require_cuda(x, "x")
+        five = x.dim() == 5
+        if not five:
+            assert self.kernel[0] == 1, "a kernel with a temporal extent needs (B,T,C,H,W) input"
+        B, T = (x.shape[0], x.shape[1]) if five else (x.shape[0], 1)
+        C, H, W = x.shape[-3:]
+        assert C == self.in_channels, "expected %d input channels, got %d" % (self.in_channels, C)
+        assert self._w_taps is not None, "call initialize() or set_data() first"
+        xb = to_nhwc_bf16(x.reshape(B * T, C, H, W))
+        y = torch.empty((B * T, self.channels, H, W), dtype=torch.bfloat16, device=x.device, memory_format=torch.channels_last)
+        kt, kh, kw = self.kernel
+        check(load().vd_conv_bn_lrelu(ptr(xb), ptr(y), B, T, H, W, C, self.channels, kt, kh, kw, ptr(self._w_taps),
+                                      ptr(self._scale), ptr(self._shift), float(self.slope), stream_ptr()))
+        return y.reshape(B, T, self.channels, H, W) if five else y
+
+
+class _Seq:
+    def __init__(self, cells):
+        self.cells = list(cells)
+
+    def __call__(self, x):
+        for c in self.cells:
+            x = c(x)
+        return x
+
+    def __iter__(self):
+        return iter(self.cells)
+
+    def __len__(self):
+        return len(self.cells)
+
+    def __getitem__(self, i):
+        return self.cells[i]
+
+
+def _expand_cell(conv_type, in_channels, channel):
+    """The 3x3 'expand' of the block: `_conv2d(channel,3,1,1)` / `Conv('3',...)` = 3x3x3 / `Conv('21',...)` =
+    (1,3,3) in->channel then (3,1,1) channel->channel (`_conv21d` with m=channel, layers.py:82-89,154-156)."""
+    if conv_type == "2":
+        return ConvBNLReLU(in_channels, channel, (1, 3, 3))
+    if conv_type == "3":
+        return ConvBNLReLU(in_channels, channel, (3, 3, 3))
+    return _Seq([ConvBNLReLU(in_channels, channel, (1, 3, 3)), ConvBNLReLU(channel, channel, (3, 1, 1))])
+
+
+class YOLODetectionBlockV3:
+    """yolo3_temporal.py:184-239 (2-D twin in yolo3.py): body = [1x1 reduce -> channel, 3x3 expand -> 2*channel] x 2 +
+    1x1 reduce; tip = 3x3 expand.  `__call__(x)` returns (route, tip).  conv_type '2': x (B,Cin,H,W); '3' / '21':
+    x (B,T,Cin,H,W) (the reference swaps to (B,C,T,H,W) around the convs and back, :231-239 -- a no-op on the
+    channels-last carrier).  Gluon infers `in_channels` at the first call; here it is a constructor argument."""
+
+    def __init__(self, channel, conv_type="2", in_channels=None, **kwargs):
+        assert conv_type in ["2", "3", "21"]
+        assert channel % 2 == 0, "channel {} cannot be divided by 2".format(channel)
+        self._conv_type = conv_type
+        self.channel = channel
+        cin = in_channels if in_channels is not None else channel * 2
+        cells = []
+        for _ in range(2):
+            cells.append(ConvBNLReLU(cin, channel, (1, 1, 1)))
+            cells.append(_expand_cell(conv_type, channel, channel * 2))
+            cin = channel * 2
+        cells.append(ConvBNLReLU(cin, channel, (1, 1, 1)))
+        self.body = _Seq(cells)
+        self.tip = _expand_cell(conv_type, channel, channel * 2)
+
+    def cells(self):
+        """All conv-BN-LReLU cells in execution order (body then tip), composite (2+1)D cells flattened."""
+        out = []
+        for c in list(self.body) + [self.tip]:
+            out.extend(c.cells if isinstance(c, _Seq) else [c])
+        return out
+
+    def initialize(self, scale=0.07, generator=None):
+        for c in self.cells():
+            c.initialize(scale, generator)
+        return self
+
+    def __call__(self, x):
+        _require_cuda(x, "x")
+        assert x.dim() == (4 if self._conv_type == "2" else 5)
+        route = self.body(x)
+        tip = self.tip(route)
+        return route, tip
+
+    hybrid_forward = __call__
 
 
 # ------------------------------------------------------------------------------------------------

@@ -1,0 +1,283 @@
+// vd_conv_bn_lrelu -- the conv-BN-LeakyReLU cells of YOLODetectionBlockV3:
+//   _conv2d(channel, k, pad, 1)            models/definitions/layers.py:63-70   (k = 1 or 3, pad = k/2)
+//   _conv3d(channel, (kt,kh,kw), pad, 1)   models/definitions/layers.py:73-79   ((1,1,1), (1,3,3), (3,1,1), (3,3,3))
+//   = Conv(no bias, stride 1, 'same' zero padding) + BatchNorm(eps 1e-5, inference) + LeakyReLU(0.1),
+//   as stacked by YOLODetectionBlockV3 (yolo3_temporal.py:198-239; yolo3.py twin): 1x1 reduce / 3x3 expand x2,
+//   1x1 reduce (= route), 3x3 tip.
+//
+// One implicit-GEMM kernel on tcgen05 for every kernel shape: activations are channels-last bf16
+// (B, T, H, W, Cin) seen through ONE 5-D TMA map (Cin, W, H, T, B).  An M tile is a BW x BH pixel box of one frame
+// (BW*BH <= 128 rows of 64 channels, 128-byte swizzle); tap (dt,dy,dx) of the kernel is the same box fetched at
+// (x0+dx, y0+dy, t+dt): the zero padding in x, y AND t is the TMA out-of-bounds fill, so no halo copies, no im2col
+// buffer and no border branches exist.  Taps whose box is entirely outside the frame / window are skipped.
+// 1x1x1 convs flatten (B,T,H,W) into one row axis (no padding needed => full 128-row tiles).
+//   warp 0: TMA producer (A box + W_tap tile [NT x 64])          warp 1: MMA issuer (M128 x NT x K16, 2 TMEM accumulators)
+//   warps 2-9: epilogue (column halves): tcgen05.ld -> folded BN -> LeakyReLU -> bf16 -> 128-bit stores
+#include "tc.cuh"
+
+namespace vd {
+
+constexpr int C_BLOCK_M = 128;
+constexpr int C_BLOCK_K = 64;
+constexpr int C_THREADS = 320;
+
+struct ConvParams {
+    int B, T, H, W, Cin, Cout;
+    int kt, kh, kw;
+    int BW, BH;                      // pixel box of one M tile
+    int tiles_x, tiles_y, n_tiles, total_tiles;
+    const float* scale; const float* shift; float slope;
+    __nv_bfloat16* y;
+};
+struct ConvMaps { CUtensorMap x; CUtensorMap w; };
+
+template <int NT> struct ConvCfg {
+    static constexpr int A_BYTES = C_BLOCK_M * C_BLOCK_K * 2;
+    static constexpr int B_BYTES = NT * C_BLOCK_K * 2;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int STAGES = (200 * 1024) / STAGE_BYTES > 8 ? 8 : (200 * 1024) / STAGE_BYTES;
+    static constexpr int BN_BYTES = 2 * 1024 * 4;
+    static constexpr int TMEM_COLS = 2 * NT;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BN_BYTES + 2048 + 1024;
+};
+
+struct ConvShared {
+    uint64_t full[8], empty[8], tmem_full[2], tmem_empty[2];
+    uint32_t tmem_base;
+};
+
+struct ConvTile { int b, t, y0, x0, nt; };
+
+template <int NT>
+__global__ void __launch_bounds__(C_THREADS, 1)
+conv_bn_lrelu_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ ConvParams p) {
+    using Cfg = ConvCfg<NT>;
+    extern __shared__ unsigned char smem_dyn[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+    unsigned char* ring = smem;
+    float* sscale = reinterpret_cast<float*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+    float* sshift = sscale + 1024;
+    ConvShared* sh = reinterpret_cast<ConvShared*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES + Cfg::BN_BYTES);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int i = threadIdx.x; i < p.Cout; i += C_THREADS) { sscale[i] = p.scale[i]; sshift[i] = p.shift[i]; }
+    // rows of the A stages that no TMA box ever writes (BW*BH < 128) must still hold finite bf16 values: zero them once
+    for (int i = threadIdx.x; i < Cfg::STAGES * Cfg::STAGE_BYTES / 16; i += C_THREADS)
+        reinterpret_cast<uint4*>(ring)[i] = make_uint4(0, 0, 0, 0);
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < Cfg::STAGES; ++i) { tc::mbar_init(&sh->full[i], 1); tc::mbar_init(&sh->empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { tc::mbar_init(&sh->tmem_full[i], 1); tc::mbar_init(&sh->tmem_empty[i], 8); }
+        tc::fence_barrier_init();
+        tc::prefetch_tmap(&maps.x); tc::prefetch_tmap(&maps.w);
+    }
+    if (warp == 1) tc::tmem_alloc<Cfg::TMEM_COLS>(&sh->tmem_base);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy zero fill before async-proxy (TMA/UMMA) use
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem_base = sh->tmem_base;
+    const int kb_per_tap = p.Cin / C_BLOCK_K;
+    const int ntaps = p.kt * p.kh * p.kw;
+    const uint32_t a_tx_bytes = (uint32_t)(p.BW * p.BH) * C_BLOCK_K * 2;
+
+    // tile -> (window b, frame t, box origin, channel block); channel block fastest so the A boxes are re-read from L2
+    auto coords = [&](int tile) {
+        ConvTile c;
+        c.nt = tile % p.n_tiles; int r = tile / p.n_tiles;
+        c.x0 = (r % p.tiles_x) * p.BW; r /= p.tiles_x;
+        c.y0 = (r % p.tiles_y) * p.BH; r /= p.tiles_y;
+        c.t = r % p.T; c.b = r / p.T;
+        return c;
+    };
+    auto tap_offsets = [&](int tap, int& dt, int& dy, int& dx) {
+        dx = tap % p.kw - (p.kw >> 1); int r = tap / p.kw;
+        dy = r % p.kh - (p.kh >> 1); dt = r / p.kh - (p.kt >> 1);
+    };
+    auto tap_active = [&](const ConvTile& c, int dt, int dy, int dx) -> bool {   // does the shifted box touch the frame at all?
+        const int x1 = min(c.x0 + p.BW, p.W) - 1, y1 = min(c.y0 + p.BH, p.H) - 1;
+        return (c.t + dt >= 0) && (c.t + dt < p.T) && (y1 + dy >= 0) && (c.y0 + dy < p.H) && (x1 + dx >= 0) && (c.x0 + dx < p.W);
+    };
+
+    if (warp == 0) {
+        if (tc::elect_one()) {
+            int stage = 0; uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+                const ConvTile c = coords(tile);
+                for (int tap = 0; tap < ntaps; ++tap) {
+                    int dt, dy, dx; tap_offsets(tap, dt, dy, dx);
+                    if (!tap_active(c, dt, dy, dx)) continue;
+                    for (int kb = 0; kb < kb_per_tap; ++kb) {
+                        tc::mbar_wait(&sh->empty[stage], phase ^ 1u);
+                        unsigned char* a_dst = ring + stage * Cfg::STAGE_BYTES;
+                        tc::mbar_expect_tx(&sh->full[stage], a_tx_bytes + Cfg::B_BYTES);
+                        tc::tma_load_5d(a_dst, &maps.x, &sh->full[stage], kb * C_BLOCK_K, c.x0 + dx, c.y0 + dy, c.t + dt, c.b);
+                        tc::tma_load_3d(a_dst + Cfg::A_BYTES, &maps.w, &sh->full[stage], kb * C_BLOCK_K, c.nt * NT, tap);
+                        if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (tc::elect_one()) {
+            constexpr uint32_t idesc = tc::make_idesc_bf16(C_BLOCK_M, NT);
+            int stage = 0; uint32_t phase = 0; uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+                const ConvTile c = coords(tile);
+                const uint32_t buf = it & 1u;
+                tc::mbar_wait(&sh->tmem_empty[buf], ((it >> 1) & 1u) ^ 1u);
+                tc::fence_after_sync();
+                const uint32_t d_tmem = tmem_base + buf * NT;
+                uint32_t first = 1;
+                for (int tap = 0; tap < ntaps; ++tap) {
+                    int dt, dy, dx; tap_offsets(tap, dt, dy, dx);
+                    if (!tap_active(c, dt, dy, dx)) continue;
+                    for (int kb = 0; kb < kb_per_tap; ++kb) {
+                        tc::mbar_wait(&sh->full[stage], phase);
+                        tc::fence_after_sync();
+                        const uint32_t a_addr = tc::smem_u32(ring + stage * Cfg::STAGE_BYTES);
+                        const uint64_t da = tc::make_smem_desc_sw128(a_addr);
+                        const uint64_t db = tc::make_smem_desc_sw128(a_addr + Cfg::A_BYTES);
+#pragma unroll
+                        for (int k = 0; k < C_BLOCK_K / 16; ++k) {
+                            tc::umma_bf16(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, first ? 0u : 1u);
+                            first = 0;
+                        }
+                        tc::umma_commit(&sh->empty[stage]);
+                        if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
+                    }
+                }
+                tc::umma_commit(&sh->tmem_full[buf]);
+            }
+        }
+    } else {
+        const int q = warp & 3;                               // TMEM lane quarter this warp may read
+        const int half = (warp - 2) >> 2;                     // which half of the tile's columns
+        constexpr int NH = NT / 2;
+        const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+        const int r = q * 32 + lane;                          // row of the tile = pixel (r / BW, r % BW) of the box
+        const int ly = r / p.BW, lx = r - ly * p.BW;
+        uint32_t it = 0;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+            const ConvTile c = coords(tile);
+            const uint32_t buf = it & 1u;
+            const int x = c.x0 + lx, y = c.y0 + ly;
+            const bool inb = (ly < p.BH) && (x < p.W) && (y < p.H);
+            tc::mbar_wait(&sh->tmem_full[buf], (it >> 1) & 1u);
+            tc::fence_after_sync();
+            const uint32_t tbase = tmem_base + buf * NT + (uint32_t)(half * NH) + lane_addr;
+            const int col0 = c.nt * NT + half * NH;
+            const size_t pix = (((size_t)c.b * p.T + c.t) * p.H + (inb ? y : 0)) * p.W + (inb ? x : 0);
+            __nv_bfloat16* yrow = p.y + pix * p.Cout + col0;
+            const float* sc = sscale + col0;
+            const float* sf = sshift + col0;
+#pragma unroll 1
+            for (int n0 = 0; n0 < NH; n0 += 32) {
+                uint32_t v[32];
+                tc::tmem_ld16(tbase + n0, v); tc::tmem_ld16(tbase + n0 + 16, v + 16); tc::tmem_ld_wait();
+                uint32_t packed[16];
+#pragma unroll
+                for (int i = 0; i < 32; i += 4) {
+                    const float4 s4 = *reinterpret_cast<const float4*>(sc + n0 + i);
+                    const float4 f4 = *reinterpret_cast<const float4*>(sf + n0 + i);
+                    float v0 = fmaf(__uint_as_float(v[i]), s4.x, f4.x), v1 = fmaf(__uint_as_float(v[i + 1]), s4.y, f4.y);
+                    float v2 = fmaf(__uint_as_float(v[i + 2]), s4.z, f4.z), v3 = fmaf(__uint_as_float(v[i + 3]), s4.w, f4.w);
+                    v0 = v0 > 0.f ? v0 : v0 * p.slope; v1 = v1 > 0.f ? v1 : v1 * p.slope;
+                    v2 = v2 > 0.f ? v2 : v2 * p.slope; v3 = v3 > 0.f ? v3 : v3 * p.slope;
+                    __nv_bfloat162 h0 = __floats2bfloat162_rn(v0, v1), h1 = __floats2bfloat162_rn(v2, v3);
+                    packed[i / 2] = *reinterpret_cast<uint32_t*>(&h0); packed[i / 2 + 1] = *reinterpret_cast<uint32_t*>(&h1);
+                }
+                if (inb) {
+                    uint4* dst = reinterpret_cast<uint4*>(yrow + n0);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) dst[i] = make_uint4(packed[4 * i], packed[4 * i + 1], packed[4 * i + 2], packed[4 * i + 3]);
+                }
+            }
+            tc::fence_before_sync();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(&sh->tmem_empty[buf]);
+        }
+    }
+    __syncwarp();
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 1) tc::tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+}
+
+template <int NT>
+static int launch_conv(const ConvMaps& maps, const ConvParams& p, cudaStream_t stream) {
+    using Cfg = ConvCfg<NT>;
+    auto kern = conv_bn_lrelu_kernel<NT>;
+    static bool configured = false;
+    if (!configured) {
+        VD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        configured = true;
+    }
+    int grid = sm_count(); if (grid > p.total_tiles) grid = p.total_tiles;
+    kern<<<grid, C_THREADS, Cfg::SMEM_BYTES, stream>>>(maps, p);
+    VD_LAUNCH_CHECK();
+    return VD_OK;
+}
+
+// Pixel box of an M tile: the (BW, BH) with BW*BH <= 128 that wastes the fewest MMA rows over the whole frame.
+static void choose_box(int H, int W, int* BW, int* BH) {
+    double best = -1.0; *BW = 1; *BH = 1;
+    for (int bw = 1; bw <= W && bw <= C_BLOCK_M; ++bw) {
+        int bh = C_BLOCK_M / bw; if (bh > H) bh = H;
+        const double eff = (double)W * H / ((double)ceil_div(W, bw) * ceil_div(H, bh) * C_BLOCK_M);
+        if (eff > best + 1e-9 || (eff > best - 1e-9 && bw > *BW)) { best = eff; *BW = bw; *BH = bh; }
+    }
+}
+
+}  // namespace vd
+
+using namespace vd;
+
+extern "C" int vd_conv_tile_box(int H, int W, int* BW, int* BH) {
+    VD_CHECK_ARG(H > 0 && W > 0 && BW && BH, "conv_tile_box: bad arguments");
+    choose_box(H, W, BW, BH);
+    return VD_OK;
+}
+
+extern "C" int vd_conv_bn_lrelu(const void* x, void* y, int B, int T, int H, int W, int Cin, int Cout,
+                                int kt, int kh, int kw, const void* weight, const float* scale, const float* shift,
+                                float slope, void* stream_) {
+    VD_CHECK_ARG(x && y && weight && scale && shift, "conv_bn_lrelu: null pointer");
+    VD_CHECK_ARG(B >= 0 && T >= 1 && H > 0 && W > 0, "conv_bn_lrelu: bad shape");
+    VD_CHECK_ARG((kt == 1 || kt == 3) && (kh == 1 || kh == 3) && (kw == 1 || kw == 3),
+                 "conv_bn_lrelu: kernel (%d,%d,%d): every extent must be 1 or 3 ('same' padding, stride 1)", kt, kh, kw);
+    VD_CHECK_ARG(Cin >= 64 && Cin % 64 == 0, "conv_bn_lrelu: Cin = %d must be a multiple of 64", Cin);
+    VD_CHECK_ARG(Cout >= 128 && Cout % 128 == 0 && Cout <= 1024, "conv_bn_lrelu: Cout = %d must be a multiple of 128, at most 1024", Cout);
+    VD_CHECK_ARG(((uintptr_t)x & 15) == 0 && ((uintptr_t)y & 15) == 0 && ((uintptr_t)weight & 15) == 0, "conv_bn_lrelu: tensors must be 16-byte aligned");
+    if (B == 0) return VD_OK;
+    const int NT = (Cout % 256 == 0) ? 256 : 128;
+    ConvParams p;
+    p.kt = kt; p.kh = kh; p.kw = kw; p.Cin = Cin; p.Cout = Cout;
+    if (kt == 1 && kh == 1 && kw == 1) {          // pointwise: one flat row axis, full 128-row tiles
+        const long long rows = (long long)B * T * H * W;
+        VD_CHECK_ARG(rows < (1ll << 31), "conv_bn_lrelu: too many pixels");
+        p.B = 1; p.T = 1; p.H = 1; p.W = (int)rows; p.BW = C_BLOCK_M; p.BH = 1;
+    } else {
+        p.B = B; p.T = T; p.H = H; p.W = W;
+        choose_box(H, W, &p.BW, &p.BH);
+    }
+    p.tiles_x = ceil_div(p.W, p.BW); p.tiles_y = ceil_div(p.H, p.BH); p.n_tiles = Cout / NT;
+    const long long total = (long long)p.B * p.T * p.tiles_x * p.tiles_y * p.n_tiles;
+    VD_CHECK_ARG(total < (1ll << 31), "conv_bn_lrelu: too many tiles");
+    p.total_tiles = (int)total;
+    p.scale = scale; p.shift = shift; p.slope = slope; p.y = (__nv_bfloat16*)y;
+    ConvMaps maps;
+    const uint64_t e = 2;
+    uint64_t dimsX[5] = {(uint64_t)Cin, (uint64_t)p.W, (uint64_t)p.H, (uint64_t)p.T, (uint64_t)p.B};
+    uint64_t strX[4] = {Cin * e, (uint64_t)p.W * Cin * e, (uint64_t)p.H * p.W * Cin * e, (uint64_t)p.T * p.H * p.W * Cin * e};
+    uint32_t boxX[5] = {C_BLOCK_K, (uint32_t)p.BW, (uint32_t)p.BH, 1, 1};
+    int rc = encode_tmap_bf16(&maps.x, x, 5, dimsX, strX, boxX);
+    if (rc) return rc;
+    const int ntaps = kt * kh * kw;
+    uint64_t dimsW[3] = {(uint64_t)Cin, (uint64_t)Cout, (uint64_t)ntaps};
+    uint64_t strW[2] = {Cin * e, (uint64_t)Cout * Cin * e};
+    uint32_t boxW[3] = {C_BLOCK_K, (uint32_t)NT, 1};
+    rc = encode_tmap_bf16(&maps.w, weight, 3, dimsW, strW, boxW);
+    if (rc) return rc;
+    if (NT == 256) return launch_conv<256>(maps, p, (cudaStream_t)stream_);
+    return launch_conv<128>(maps, p, (cudaStream_t)stream_);
+}

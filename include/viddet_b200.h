@@ -186,8 +186,9 @@ int vd_temporal_conv(const void* x_bf16, void* y_bf16, int B, int T, int H, int 
 int vd_conv_bn_lrelu(const void* x_bf16, void* y_bf16, int B, int T, int H, int W, int Cin, int Cout,
                      int kt, int kh, int kw, const void* weight_bf16, const float* scale, const float* shift,
                      float slope, void* stream);
-/* The BW x BH pixel box (BW*BH <= 128) one MMA tile of vd_conv_bn_lrelu covers on an H x W map (for roofline maths). */
-int vd_conv_tile_box(int H, int W, int* BW, int* BH);
+/* The BW x BH x BF box of pixels x frames (BW*BH*BF <= 128) one MMA tile of vd_conv_bn_lrelu covers on F frames of an
+ * H x W map (for roofline maths; F = B*T for kernels without a temporal extent, T otherwise). */
+int vd_conv_tile_box(int H, int W, int F, int* BW, int* BH, int* BF);
 
 /* TemporalPooling 'direct' (layers.py:202-205): (B,K,H,W,C) bf16 -> (B,H,W,C) bf16. */
 int vd_temporal_pool(const void* x_bf16, void* y_bf16, int B, int K, int64_t inner, int mode,

@@ -20,7 +20,27 @@ B = int(sys.argv[1]) if len(sys.argv) > 1 else 64
 T = int(sys.argv[2]) if len(sys.argv) > 2 else 1
 
 
-def timeit(fn, n=20, warm=3):
+def timeit(fn, n=20, warm=3, reps=5):
+    """n calls captured in one CUDA graph (no host launch overhead between the kernels), replayed `reps` times."""
+    for i in range(warm):
+        fn(i)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for i in range(n):
+            fn(i)
+    g.replay()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        g.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / (n * reps)
+
+
+def timeit_eager(fn, n=20, warm=3):
     for i in range(warm):
         fn(i)
     torch.cuda.synchronize()
@@ -33,10 +53,10 @@ def timeit(fn, n=20, warm=3):
     return e0.elapsed_time(e1) / n
 
 
-def box(H, W):
-    bw, bh = ctypes.c_int(), ctypes.c_int()
-    _lib.check(_lib.load().vd_conv_tile_box(H, W, ctypes.byref(bw), ctypes.byref(bh)))
-    return bw.value, bh.value
+def box(H, W, F):
+    bw, bh, bf = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+    _lib.check(_lib.load().vd_conv_tile_box(H, W, F, ctypes.byref(bw), ctypes.byref(bh), ctypes.byref(bf)))
+    return bw.value, bh.value, bf.value
 
 
 def main():
@@ -53,11 +73,12 @@ def main():
             ms = timeit(lambda i: cell(xs[i % 3]))
             taps = k[0] * k[1] * k[2]
             fl = 2.0 * taps * B * T * hw * hw * ci * co
-            bw, bh = (128, 1) if taps == 1 else box(hw, hw)
-            util = 1.0 if taps == 1 else hw * hw / (-(-hw // bw) * -(-hw // bh) * 128.0)
+            F = B * T if k[0] == 1 else T
+            bw, bh, bf = (128, 1, 1) if taps == 1 else box(hw, hw, F)
+            util = 1.0 if taps == 1 else hw * hw * F / (-(-hw // bw) * -(-hw // bh) * -(-F // bf) * 128.0)
             print(json.dumps({"cell": name, "map": hw, "Cin": ci, "Cout": co, "kernel": k, "frames": B * T, "ms": round(ms, 4),
                               "tflops": round(fl / ms / 1e9, 1), "frac_tensor_peak": round(fl / ms / 1e9 / PEAK_TC, 3),
-                              "box": [bw, bh], "mma_row_util": round(util, 3)}))
+                              "box": [bw, bh, bf], "mma_row_util": round(util, 3)}))
             # the block runs reduce + expand twice, reduce once more, then the tip's expand
             reps = {"reduce1x1": 1, "expand3x3": 3, "reduce1x1b": 2, "temporal3x1x1": 3}[name]
             total_ms += reps * ms; total_fl += reps * fl

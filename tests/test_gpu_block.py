@@ -32,6 +32,9 @@ CELL_CASES = [
     (192, 128, (1, 1, 1), 1, 3, 9, 11),       # Cin not a power of two (768/384-channel concat inputs of the s16/s8 blocks)
     (64, 128, (1, 3, 3), 1, 1, 1, 1),         # one pixel: 8 of 9 taps are pure padding
     (64, 128, (1, 3, 3), 1, 1, 3, 200),       # wider than one box
+    (64, 128, (1, 3, 3), 11, 1, 13, 13),      # tiles span frames (13 x 1 x 9 boxes), ragged last frame group
+    (64, 128, (3, 3, 3), 2, 5, 5, 5),         # tiles span the frames of a window; temporal taps shift the frame box
+    (64, 128, (3, 1, 1), 3, 4, 4, 4),
 ]
 
 

@@ -6,10 +6,12 @@
 //   1x1 reduce (= route), 3x3 tip.
 //
 // One implicit-GEMM kernel on tcgen05 for every kernel shape: activations are channels-last bf16
-// (B, T, H, W, Cin) seen through ONE 5-D TMA map (Cin, W, H, T, B).  An M tile is a BW x BH pixel box of one frame
-// (BW*BH <= 128 rows of 64 channels, 128-byte swizzle); tap (dt,dy,dx) of the kernel is the same box fetched at
-// (x0+dx, y0+dy, t+dt): the zero padding in x, y AND t is the TMA out-of-bounds fill, so no halo copies, no im2col
-// buffer and no border branches exist.  Taps whose box is entirely outside the frame / window are skipped.
+// (B, T, H, W, Cin) seen through ONE 5-D TMA map (Cin, W, H, F1, F2) -- (F1,F2) = (T,B) when the kernel has a temporal
+// extent, (B*T,1) otherwise.  An M tile is a BW x BH x BF box of pixels x frames (BW*BH*BF <= 128 rows of 64 channels,
+// 128-byte swizzle; small maps put the same rows of several frames into one tile: 13x13 -> 13x1x9 = 117 of 128 rows);
+// tap (dt,dy,dx) of the kernel is the same box fetched at (x0+dx, y0+dy, f0+dt): the zero padding in x, y AND t is the
+// TMA out-of-bounds fill, so no halo copies, no im2col buffer and no border branches exist.  Taps whose box is entirely
+// outside the frame / window are skipped.
 // 1x1x1 convs flatten (B,T,H,W) into one row axis (no padding needed => full 128-row tiles).
 //   warp 0: TMA producer (A box + W_tap tile [NT x 64])          warp 1: MMA issuer (M128 x NT x K16, 2 TMEM accumulators)
 //   warps 2-9: epilogue (column halves): tcgen05.ld -> folded BN -> LeakyReLU -> bf16 -> 128-bit stores
@@ -22,10 +24,10 @@ constexpr int C_BLOCK_K = 64;
 constexpr int C_THREADS = 320;
 
 struct ConvParams {
-    int B, T, H, W, Cin, Cout;
+    int F2, F1, H, W, Cin, Cout;     // F1 = frame axis a tile may span (and the temporal taps shift), F2 = outer batch axis
     int kt, kh, kw;
-    int BW, BH;                      // pixel box of one M tile
-    int tiles_x, tiles_y, n_tiles, total_tiles;
+    int BW, BH, BF;                  // pixel x frame box of one M tile
+    int tiles_x, tiles_y, tiles_f, n_tiles, total_tiles;
     const float* scale; const float* shift; float slope;
     __nv_bfloat16* y;
 };
@@ -46,7 +48,7 @@ struct ConvShared {
     uint32_t tmem_base;
 };
 
-struct ConvTile { int b, t, y0, x0, nt; };
+struct ConvTile { int b, f0, y0, x0, nt; };
 
 template <int NT>
 __global__ void __launch_bounds__(C_THREADS, 1)
@@ -78,7 +80,7 @@ conv_bn_lrelu_kernel(const __grid_constant__ ConvMaps maps, const __grid_constan
     const uint32_t tmem_base = sh->tmem_base;
     const int kb_per_tap = p.Cin / C_BLOCK_K;
     const int ntaps = p.kt * p.kh * p.kw;
-    const uint32_t a_tx_bytes = (uint32_t)(p.BW * p.BH) * C_BLOCK_K * 2;
+    const uint32_t a_tx_bytes = (uint32_t)(p.BW * p.BH * p.BF) * C_BLOCK_K * 2;
 
     // tile -> (window b, frame t, box origin, channel block); channel block fastest so the A boxes are re-read from L2
     auto coords = [&](int tile) {
@@ -86,7 +88,7 @@ conv_bn_lrelu_kernel(const __grid_constant__ ConvMaps maps, const __grid_constan
         c.nt = tile % p.n_tiles; int r = tile / p.n_tiles;
         c.x0 = (r % p.tiles_x) * p.BW; r /= p.tiles_x;
         c.y0 = (r % p.tiles_y) * p.BH; r /= p.tiles_y;
-        c.t = r % p.T; c.b = r / p.T;
+        c.f0 = (r % p.tiles_f) * p.BF; c.b = r / p.tiles_f;
         return c;
     };
     auto tap_offsets = [&](int tap, int& dt, int& dy, int& dx) {
@@ -94,8 +96,8 @@ conv_bn_lrelu_kernel(const __grid_constant__ ConvMaps maps, const __grid_constan
         dy = r % p.kh - (p.kh >> 1); dt = r / p.kh - (p.kt >> 1);
     };
     auto tap_active = [&](const ConvTile& c, int dt, int dy, int dx) -> bool {   // does the shifted box touch the frame at all?
-        const int x1 = min(c.x0 + p.BW, p.W) - 1, y1 = min(c.y0 + p.BH, p.H) - 1;
-        return (c.t + dt >= 0) && (c.t + dt < p.T) && (y1 + dy >= 0) && (c.y0 + dy < p.H) && (x1 + dx >= 0) && (c.x0 + dx < p.W);
+        const int x1 = min(c.x0 + p.BW, p.W) - 1, y1 = min(c.y0 + p.BH, p.H) - 1, f1 = min(c.f0 + p.BF, p.F1) - 1;
+        return (f1 + dt >= 0) && (c.f0 + dt < p.F1) && (y1 + dy >= 0) && (c.y0 + dy < p.H) && (x1 + dx >= 0) && (c.x0 + dx < p.W);
     };
 
     if (warp == 0) {
@@ -110,7 +112,7 @@ conv_bn_lrelu_kernel(const __grid_constant__ ConvMaps maps, const __grid_constan
                         tc::mbar_wait(&sh->empty[stage], phase ^ 1u);
                         unsigned char* a_dst = ring + stage * Cfg::STAGE_BYTES;
                         tc::mbar_expect_tx(&sh->full[stage], a_tx_bytes + Cfg::B_BYTES);
-                        tc::tma_load_5d(a_dst, &maps.x, &sh->full[stage], kb * C_BLOCK_K, c.x0 + dx, c.y0 + dy, c.t + dt, c.b);
+                        tc::tma_load_5d(a_dst, &maps.x, &sh->full[stage], kb * C_BLOCK_K, c.x0 + dx, c.y0 + dy, c.f0 + dt, c.b);
                         tc::tma_load_3d(a_dst + Cfg::A_BYTES, &maps.w, &sh->full[stage], kb * C_BLOCK_K, c.nt * NT, tap);
                         if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
                     }
@@ -154,19 +156,20 @@ conv_bn_lrelu_kernel(const __grid_constant__ ConvMaps maps, const __grid_constan
         const int half = (warp - 2) >> 2;                     // which half of the tile's columns
         constexpr int NH = NT / 2;
         const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
-        const int r = q * 32 + lane;                          // row of the tile = pixel (r / BW, r % BW) of the box
-        const int ly = r / p.BW, lx = r - ly * p.BW;
+        const int r = q * 32 + lane;                          // row of the tile = (frame lf, pixel ly, lx) of the box
+        const int lx = r % p.BW, ly = (r / p.BW) % p.BH, lf = r / (p.BW * p.BH);
         uint32_t it = 0;
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
             const ConvTile c = coords(tile);
             const uint32_t buf = it & 1u;
             const int x = c.x0 + lx, y = c.y0 + ly;
-            const bool inb = (ly < p.BH) && (x < p.W) && (y < p.H);
+            const int f = c.f0 + lf;
+            const bool inb = (lf < p.BF) && (x < p.W) && (y < p.H) && (f < p.F1);
             tc::mbar_wait(&sh->tmem_full[buf], (it >> 1) & 1u);
             tc::fence_after_sync();
             const uint32_t tbase = tmem_base + buf * NT + (uint32_t)(half * NH) + lane_addr;
             const int col0 = c.nt * NT + half * NH;
-            const size_t pix = (((size_t)c.b * p.T + c.t) * p.H + (inb ? y : 0)) * p.W + (inb ? x : 0);
+            const size_t pix = inb ? (((size_t)c.b * p.F1 + f) * p.H + y) * p.W + x : 0;
             __nv_bfloat16* yrow = p.y + pix * p.Cout + col0;
             const float* sc = sscale + col0;
             const float* sf = sshift + col0;
@@ -218,23 +221,25 @@ static int launch_conv(const ConvMaps& maps, const ConvParams& p, cudaStream_t s
     return VD_OK;
 }
 
-// Pixel box of an M tile: the (BW, BH) with BW*BH <= 128 that wastes the fewest MMA rows over the whole frame.
-static void choose_box(int H, int W, int* BW, int* BH) {
-    double best = -1.0; *BW = 1; *BH = 1;
-    for (int bw = 1; bw <= W && bw <= C_BLOCK_M; ++bw) {
-        int bh = C_BLOCK_M / bw; if (bh > H) bh = H;
-        const double eff = (double)W * H / ((double)ceil_div(W, bw) * ceil_div(H, bh) * C_BLOCK_M);
-        if (eff > best + 1e-9 || (eff > best - 1e-9 && bw > *BW)) { best = eff; *BW = bw; *BH = bh; }
-    }
+// Box of an M tile: the (BW, BH, BF) with BW*BH*BF <= 128 that wastes the fewest MMA rows over all F frames
+// (ties: the widest, then tallest box = the longest contiguous runs in memory).
+static void choose_box(int H, int W, int F, int* BW, int* BH, int* BF) {
+    double best = -1.0; *BW = 1; *BH = 1; *BF = 1;
+    for (int bw = 1; bw <= W && bw <= C_BLOCK_M; ++bw)
+        for (int bh = 1; bh <= H && bw * bh <= C_BLOCK_M; ++bh) {
+            int bf = C_BLOCK_M / (bw * bh); if (bf > F) bf = F;
+            const double eff = (double)W * H * F / ((double)ceil_div(W, bw) * ceil_div(H, bh) * ceil_div(F, bf) * C_BLOCK_M);
+            if (eff > best + 1e-9 || (eff > best - 1e-9 && (bw > *BW || (bw == *BW && bh > *BH)))) { best = eff; *BW = bw; *BH = bh; *BF = bf; }
+        }
 }
 
 }  // namespace vd
 
 using namespace vd;
 
-extern "C" int vd_conv_tile_box(int H, int W, int* BW, int* BH) {
-    VD_CHECK_ARG(H > 0 && W > 0 && BW && BH, "conv_tile_box: bad arguments");
-    choose_box(H, W, BW, BH);
+extern "C" int vd_conv_tile_box(int H, int W, int F, int* BW, int* BH, int* BF) {
+    VD_CHECK_ARG(H > 0 && W > 0 && F > 0 && BW && BH && BF, "conv_tile_box: bad arguments");
+    choose_box(H, W, F, BW, BH, BF);
     return VD_OK;
 }
 
@@ -255,21 +260,23 @@ extern "C" int vd_conv_bn_lrelu(const void* x, void* y, int B, int T, int H, int
     if (kt == 1 && kh == 1 && kw == 1) {          // pointwise: one flat row axis, full 128-row tiles
         const long long rows = (long long)B * T * H * W;
         VD_CHECK_ARG(rows < (1ll << 31), "conv_bn_lrelu: too many pixels");
-        p.B = 1; p.T = 1; p.H = 1; p.W = (int)rows; p.BW = C_BLOCK_M; p.BH = 1;
+        p.F2 = 1; p.F1 = 1; p.H = 1; p.W = (int)rows; p.BW = C_BLOCK_M; p.BH = 1; p.BF = 1;
     } else {
-        p.B = B; p.T = T; p.H = H; p.W = W;
-        choose_box(H, W, &p.BW, &p.BH);
+        VD_CHECK_ARG((long long)B * T < (1ll << 31), "conv_bn_lrelu: too many frames");
+        if (kt == 1) { p.F2 = 1; p.F1 = B * T; } else { p.F2 = B; p.F1 = T; }     // frames are independent unless taps shift t
+        p.H = H; p.W = W;
+        choose_box(H, W, p.F1, &p.BW, &p.BH, &p.BF);
     }
-    p.tiles_x = ceil_div(p.W, p.BW); p.tiles_y = ceil_div(p.H, p.BH); p.n_tiles = Cout / NT;
-    const long long total = (long long)p.B * p.T * p.tiles_x * p.tiles_y * p.n_tiles;
+    p.tiles_x = ceil_div(p.W, p.BW); p.tiles_y = ceil_div(p.H, p.BH); p.tiles_f = ceil_div(p.F1, p.BF); p.n_tiles = Cout / NT;
+    const long long total = (long long)p.F2 * p.tiles_f * p.tiles_x * p.tiles_y * p.n_tiles;
     VD_CHECK_ARG(total < (1ll << 31), "conv_bn_lrelu: too many tiles");
     p.total_tiles = (int)total;
     p.scale = scale; p.shift = shift; p.slope = slope; p.y = (__nv_bfloat16*)y;
     ConvMaps maps;
     const uint64_t e = 2;
-    uint64_t dimsX[5] = {(uint64_t)Cin, (uint64_t)p.W, (uint64_t)p.H, (uint64_t)p.T, (uint64_t)p.B};
-    uint64_t strX[4] = {Cin * e, (uint64_t)p.W * Cin * e, (uint64_t)p.H * p.W * Cin * e, (uint64_t)p.T * p.H * p.W * Cin * e};
-    uint32_t boxX[5] = {C_BLOCK_K, (uint32_t)p.BW, (uint32_t)p.BH, 1, 1};
+    uint64_t dimsX[5] = {(uint64_t)Cin, (uint64_t)p.W, (uint64_t)p.H, (uint64_t)p.F1, (uint64_t)p.F2};
+    uint64_t strX[4] = {Cin * e, (uint64_t)p.W * Cin * e, (uint64_t)p.H * p.W * Cin * e, (uint64_t)p.F1 * p.H * p.W * Cin * e};
+    uint32_t boxX[5] = {C_BLOCK_K, (uint32_t)p.BW, (uint32_t)p.BH, (uint32_t)p.BF, 1};
     int rc = encode_tmap_bf16(&maps.x, x, 5, dimsX, strX, boxX);
     if (rc) return rc;
     const int ntaps = kt * kh * kw;

@@ -42,6 +42,9 @@ constexpr int kSpecCap = 2048;                // candidates per frame the specul
 #ifndef VD_SPEC_G
 #define VD_SPEC_G 3
 #endif
+#ifndef VD_SPEC_SPLIT
+#define VD_SPEC_SPLIT 2
+#endif
 constexpr int kFallbackCtas = 8;
 constexpr int kSpecStage = 64;                // per-warp staging entries per tile (double-buffered); more go straight to global memory
 constexpr int kHeadSharedBytes = 2048;          // room for struct HeadShared (barriers, scheduler ring, per-group state)
@@ -111,9 +114,12 @@ template <int EPI, int C, int NPAD> struct HeadCfg {
     static constexpr int TMEM_STRIDE = NPAD <= 128 ? 128 : 256;
     // 3 groups (12 epilogue warps, 128 registers/thread) when three accumulators fit TMEM; else 2 groups
     static constexpr int G = (EPI == EPI_FILTER && TMEM_STRIDE == 128) ? (NPAD <= 80 ? 4 : 3) : ((EPI == EPI_SPEC && TMEM_STRIDE == 128) ? VD_SPEC_G : 2);   // 4 groups only where 80 registers suffice
-    static constexpr int THREADS = kEpiWarp0 * 32 + G * kEpiThreads;
+    // wide heads (two 256-column accumulators fill TMEM): SPLIT warpgroups drain ONE accumulator together, each taking every
+    // SPLIT-th class chunk (the epilogue, not the mainloop, bounds these heads: 240 class logits per pixel at C = 80)
+    static constexpr int SPLIT = (EPI == EPI_SPEC && TMEM_STRIDE == 256) ? VD_SPEC_SPLIT : 1;
+    static constexpr int THREADS = kEpiWarp0 * 32 + G * SPLIT * kEpiThreads;
     static constexpr int MAXREG = (THREADS > 448) ? 80 : ((THREADS > 320) ? 96 : 128);
-    static constexpr int LIST_BYTES = (EPI == EPI_SPEC) ? G * 4 * 2 * kSpecStage * 8 : G * LIST_BUFS * kListCap * 8;
+    static constexpr int LIST_BYTES = (EPI == EPI_SPEC) ? G * SPLIT * 4 * 2 * kSpecStage * 8 : G * LIST_BUFS * kListCap * 8;
     static constexpr int EPI_BYTES = LIST_BYTES + CBIAS_BYTES + CONF_BYTES + VD_MAX_SCALES * NPAD * 4 + kHeadSharedBytes;
     // EPI_FILTER leaves ~45 KB of the SM's shared memory to a co-resident nms_final_hist_kernel CTA of the previous batch
     static constexpr int SMEM_BUDGET = ((EPI == EPI_FILTER || EPI == EPI_SPEC) ? 181 : 225) * 1024;
@@ -236,8 +242,8 @@ head_kernel(const __grid_constant__ HeadMaps maps, const __grid_constant__ HeadK
     }
     if (threadIdx.x == 0) {
         for (int i = 0; i < Cfg::STAGES; ++i) { tc::mbar_init(&sh->full[i], 1); tc::mbar_init(&sh->empty[i], 1); }
-        for (int i = 0; i < G; ++i) { tc::mbar_init(&sh->tmem_full[i], 1); tc::mbar_init(&sh->tmem_empty[i], 4); }
-        for (int i = 0; i < kSchedSlots; ++i) { tc::mbar_init(&sh->sched_full[i], 1); tc::mbar_init(&sh->sched_empty[i], 5); }   // consumers: MMA thread + 4 epilogue warps
+        for (int i = 0; i < G; ++i) { tc::mbar_init(&sh->tmem_full[i], 1); tc::mbar_init(&sh->tmem_empty[i], 4 * Cfg::SPLIT); }
+        for (int i = 0; i < kSchedSlots; ++i) { tc::mbar_init(&sh->sched_full[i], 1); tc::mbar_init(&sh->sched_empty[i], 1 + 4 * Cfg::SPLIT); }   // consumers: MMA thread + the epilogue warps of the tile's accumulator
         for (int i = 0; i < 4 * kMaxEpiGroups; ++i) sh->spec_wcnt[i] = 0u;
         for (int g = 0; g < G; ++g) {
             sh->grp[g].cnt[0] = sh->grp[g].cnt[1] = sh->grp[g].cnt[2] = 0; sh->grp[g].cursor = 0; sh->grp[g].cursor2 = 0; sh->grp[g].pcur[0] = sh->grp[g].pcur[1] = sh->grp[g].pcur[2] = 0;
@@ -335,8 +341,11 @@ head_kernel(const __grid_constant__ HeadMaps maps, const __grid_constant__ HeadK
         }
     } else if (warp >= kEpiWarp0) {
         // =========================== epilogue: 2 groups x 128 threads ===========================
-        const int grp = (warp - kEpiWarp0) >> 2;              // also the TMEM buffer this group drains
-        const int et = threadIdx.x - kEpiWarp0 * 32 - grp * kEpiThreads;
+        const int wgrp = (warp - kEpiWarp0) >> 2;             // warpgroup index
+        const int grp = wgrp % G;                             // the TMEM buffer this warpgroup drains (SPLIT warpgroups share one)
+        const int half = wgrp / G;                            // which share of the class chunks it takes
+        (void)half;
+        const int et = threadIdx.x - kEpiWarp0 * 32 - wgrp * kEpiThreads;
         const int q = warp & 3;                               // TMEM lane quarter this warp may read
         const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
         EpiGroupShared* gs = &sh->grp[grp];
@@ -450,7 +459,7 @@ head_kernel(const __grid_constant__ HeadMaps maps, const __grid_constant__ HeadK
                     // the raw (tx,ty,tw,th) are stored; only the <= topk boxes that reach the NMS kernel are decoded there
                     // (same vd_decode_box, same bits) instead of all 3*HW of them here
                     if (!inb) conf[a] = __uint_as_float(0x7fc00000u);   // NaN: no score of a padding pixel passes `> valid_thresh`
-                    if (inb) p.boxes[(size_t)f * p.g.anc_base[p.g.num_scales] + p.g.anc_base[s] + cell * 3 + a] = make_float4(tx, ty, tw, th);
+                    if (inb && half == 0) p.boxes[(size_t)f * p.g.anc_base[p.g.num_scales] + p.g.anc_base[s] + cell * 3 + a] = make_float4(tx, ty, tw, th);
                     (void)bx; (void)gx; (void)gy;
                 } else {   // EPI_DET: class rows of this (cell, anchor)
                     bx = vd_decode_box(tx, ty, tw, th, gx, gy, p.g.stride[s], p.g.anchors[s][2 * a], p.g.anchors[s][2 * a + 1]);
@@ -522,6 +531,57 @@ head_kernel(const __grid_constant__ HeadMaps maps, const __grid_constant__ HeadK
                     const uint32_t col = tbase + (uint32_t)(a * P + 5 + cc * CH);
                     if (REM != CH && cc == CPA - 1) tc::tmem_ld<REM>(col, dst); else tc::tmem_ld<CH>(col, dst);
                 };
+                auto emit_chunk = [&](const float* bv, const int n, const int a, const int cc, const float la, const float ca) {
+#pragma unroll
+                    for (int i = 0; i < CH; ++i) {
+                        if (i < n && bv[i] >= la) {
+                            const float sc = vd_score(bv[i], ca);
+                            if (sc > vth) {
+                                const uint32_t kh = __float_as_uint(sc) | 0x80000000u;
+                                const uint32_t row = row0 + (uint32_t)(cc * CH + i) * HW3 + (uint32_t)a;
+                                const uint64_t key = ((uint64_t)kh << 32) | (uint32_t)~row;
+                                const uint32_t sp = atomicAdd(wc, 1u);
+                                if (sp < (uint32_t)kSpecStage) stg[sp] = key;
+                                else { const uint32_t pos = atomicAdd(fc, 1u); if (pos < (uint32_t)kSpecCap) fl[pos] = key; }   // staging full
+                            }
+                        }
+                    }
+                };
+                if constexpr (Cfg::SPLIT > 1) {
+                    // flat walk over the 3*CPA class chunks, this warpgroup takes chunks half, half+SPLIT, ...; the next
+                    // chunk's TMEM read is in flight while the current one is compared
+                    constexpr int NCH = 3 * CPA;
+                    auto issue_j = [&](const int j, uint32_t* dst) {
+                        const int a = j / CPA, cc = j - a * CPA;
+                        const uint32_t col = tbase + (uint32_t)(a * P + 5 + cc * CH);
+                        if (REM != CH && cc == CPA - 1) tc::tmem_ld<REM>(col, dst); else tc::tmem_ld<CH>(col, dst);
+                    };
+                    if (half < NCH) issue_j(half, r[0]);
+                    int par = 0;
+#pragma unroll 1
+                    for (int j = half; j < NCH; j += Cfg::SPLIT, par ^= 1) {
+                        const int a = j / CPA, cc = j - a * CPA;
+                        const int n = (REM != CH && cc == CPA - 1) ? REM : CH;
+                        const float la = (a == 0) ? ell[0] : ((a == 1) ? ell[1] : ell[2]);
+                        const float ca = (a == 0) ? conf[0] : ((a == 1) ? conf[1] : conf[2]);
+                        float bv[CH4];
+#pragma unroll
+                        for (int i = 0; i < CH4; i += 4)
+                            *reinterpret_cast<float4*>(bv + i) = *reinterpret_cast<const float4*>(cbias + j * CH4 + i);
+                        tc::tmem_ld_wait();
+                        bool any = false;
+                        if (par == 0) {
+                            if (j + Cfg::SPLIT < NCH) issue_j(j + Cfg::SPLIT, r[1]);
+#pragma unroll
+                            for (int i = 0; i < CH; ++i) if (i < n) { bv[i] = __fadd_rn(__uint_as_float(r[0][i]), bv[i]); any |= bv[i] >= la; }
+                        } else {
+                            if (j + Cfg::SPLIT < NCH) issue_j(j + Cfg::SPLIT, r[0]);
+#pragma unroll
+                            for (int i = 0; i < CH; ++i) if (i < n) { bv[i] = __fadd_rn(__uint_as_float(r[1][i]), bv[i]); any |= bv[i] >= la; }
+                        }
+                        if (any) emit_chunk(bv, n, a, cc, la, ca);
+                    }
+                } else {
                 issue_a(0, 0, r[0]);
 #pragma unroll 1
                 for (int a = 0; a < 3; ++a) {
@@ -543,23 +603,9 @@ head_kernel(const __grid_constant__ HeadMaps maps, const __grid_constant__ HeadK
                         for (int i = 0; i < CH; ++i) {
                             if (i < n) { bv[i] = __fadd_rn(__uint_as_float(r[cc & 1][i]), bv[i]); any |= bv[i] >= la; }
                         }
-                        if (any) {                                   // rare: ~0.3 % of the candidates pass
-#pragma unroll
-                            for (int i = 0; i < CH; ++i) {
-                                if (i < n && bv[i] >= la) {
-                                    const float sc = vd_score(bv[i], ca);
-                                    if (sc > vth) {
-                                        const uint32_t kh = __float_as_uint(sc) | 0x80000000u;
-                                        const uint32_t row = row0 + (uint32_t)(cc * CH + i) * HW3 + (uint32_t)a;
-                                        const uint64_t key = ((uint64_t)kh << 32) | (uint32_t)~row;
-                                        const uint32_t sp = atomicAdd(wc, 1u);
-                                        if (sp < (uint32_t)kSpecStage) stg[sp] = key;
-                                        else { const uint32_t pos = atomicAdd(fc, 1u); if (pos < (uint32_t)kSpecCap) fl[pos] = key; }   // staging full
-                                    }
-                                }
-                            }
-                        }
+                        if (any) emit_chunk(bv, n, a, cc, la, ca);   // rare: ~0.3 % of the candidates pass
                     }
+                }
                 }
                 tc::fence_before_sync();
                 __syncwarp();

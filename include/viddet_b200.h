@@ -245,6 +245,17 @@ int vd_yolo3_loss(int B, int N, int C, const float* objness, const float* box_ce
 int vd_postprocess_detections(const float* ids, const float* scores, const float* bboxes, int frames,
                               int post, float size, float* rows, int32_t* counts, void* stream);
 
+/* `hierarchical_nms` of detect_yolo3.py:736-789 (with its `iou`, :712-733), applied at :898-899 to the predictions of the
+ * combined class tree.  rows (frames, post, 6) fp32 [cls, conf, x1, y1, x2, y2] with counts (frames) valid rows per image
+ * (the layout vd_postprocess_detections writes); levels (C) = dataset.get_levels() (combined.py:117-126); parent (C) = class
+ * index of the parent, -1 under ROOT (:766); branch (C, C) uint8 = dataset.on_branch(i, j) (combined.py:143-150).  arith 0:
+ * float64 arithmetic on the fp32 inputs (the reference on re-loaded predictions); 1: legacy-NumPy float32-scalar path.
+ * out_rows (frames, post, 6) padded with -1, out_counts (frames).  post <= 256. */
+int vd_hierarchical_nms(const float* rows, const int32_t* counts, int frames, int post, int num_class,
+                        const int32_t* levels, const int32_t* parent, const uint8_t* branch,
+                        double ov_thresh, double conf_thresh, int level_thresh, int arith,
+                        float* out_rows, int32_t* out_counts, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

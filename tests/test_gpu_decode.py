@@ -107,3 +107,56 @@ def test_feature_stream_from_npy_files(tmp_path):
     assert seen == ids
     win = list(viddet_b200.FeatureStream(str(tmp_path), ids[:6], batch=1, window=3))
     assert len(win) == 2 and tuple(win[0][1][0].shape) == (1, 3, 1024, 2, 2)
+
+
+# ------------------------------------------------------------------ hierarchical_nms (detect_yolo3.py:736-789)
+def _hier_cases():
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "hier_nms_golden.npz"))
+    for ci in range(int(g["n_cases"])):
+        pre = "c%d_" % ci
+        yield ci, {k[len(pre):]: g[k] for k in g.files if k.startswith(pre)}
+
+
+def test_hierarchical_nms_matches_reference_golden_bit_exact():
+    """Golden vectors = outputs of the reference's own hierarchical_nms executed on these inputs
+    (scripts/make_golden_hier_nms.py); bit-exact rows and counts."""
+    import viddet_b200
+    for ci, c in _hier_cases():
+        ov, conf, lvl = c["params"]
+        tree = viddet_b200.ClassTree(c["levels"], c["parent"], c["branch"])
+        out, cnt = viddet_b200.hierarchical_nms(torch.from_numpy(c["rows"]).cuda(), torch.from_numpy(c["counts"]).cuda(), tree,
+                                                ov_thresh=float(ov), conf_thresh=float(conf), level_thresh=int(lvl))
+        np.testing.assert_array_equal(cnt.cpu().numpy(), c["out_counts"], err_msg="case %d" % ci)
+        np.testing.assert_array_equal(out.cpu().numpy(), c["out_rows"], err_msg="case %d" % ci)
+
+
+def test_hierarchical_nms_vs_oracle_random_and_tree_builder():
+    import viddet_b200
+    from oracle import ref_post
+    rng = np.random.RandomState(77)
+    C = 60
+    names = ["n%03d" % i for i in range(C)]
+    parents = {nm: ("ROOT" if i < 4 else names[rng.randint(0, i)]) for i, nm in enumerate(names)}
+    tree = viddet_b200.ClassTree.from_parents(names, parents)
+    F, post = 37, 100
+    rows = np.full((F, post, 6), -1.0, np.float32); counts = rng.randint(0, post + 1, size=F).astype(np.int32)
+    for f in range(F):
+        n = counts[f]
+        ctr = rng.uniform(50, 350, size=(max(1, n // 5), 2))[rng.randint(0, max(1, n // 5), size=n)] + rng.normal(0, 3, size=(n, 2))
+        wh = rng.uniform(30, 120, size=(n, 2))
+        rows[f, :n] = np.concatenate([rng.randint(0, C, size=(n, 1)), rng.uniform(0, 1, size=(n, 1)), ctr - wh / 2, ctr + wh / 2], 1)
+    lv, pa, br = tree.levels.cpu().numpy(), tree.parent.cpu().numpy(), tree.branch.cpu().numpy()
+    for lvl, ov, conf in [(10, 0.5, 0.0), (2, 0.4, 0.3), (1, 0.6, 0.0)]:
+        ref, rcnt = ref_post.hierarchical_nms(rows, counts, lv, pa, br, ov, conf, lvl)
+        out, cnt = viddet_b200.hierarchical_nms(torch.from_numpy(rows).cuda(), torch.from_numpy(counts).cuda(), tree, ov, conf, lvl)
+        np.testing.assert_array_equal(cnt.cpu().numpy(), rcnt)
+        np.testing.assert_array_equal(out.cpu().numpy(), ref)
+    with pytest.raises(ValueError):
+        viddet_b200.hierarchical_nms(torch.from_numpy(rows).cuda(), torch.from_numpy(counts).cuda(), tree, level_thresh=0)
+    # chained after the device post-processing of detect()
+    ids = torch.from_numpy(rows[..., 0:1]).cuda(); sc = torch.from_numpy(rows[..., 1:2]).cuda(); bb = torch.from_numpy(rows[..., 2:]).cuda()
+    prow, pcnt = viddet_b200.postprocess_detections(ids, sc, bb, size=416)
+    out, cnt = viddet_b200.hierarchical_nms(prow, pcnt, tree)
+    ref, rcnt = ref_post.hierarchical_nms(prow.cpu().numpy(), pcnt.cpu().numpy(), lv, pa, br)
+    np.testing.assert_array_equal(out.cpu().numpy(), ref)

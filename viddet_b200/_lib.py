@@ -70,6 +70,7 @@ SIGNATURES = {
     "vd_prefetch_targets": (_i, [_i, _i, _i, _i, _i, _ip, _fp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "vd_target_merge": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "vd_postprocess_detections": (_i, [_vp, _vp, _vp, _i, _i, _f, _vp, _vp, _vp]),
+    "vd_hierarchical_nms": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, ctypes.c_double, ctypes.c_double, _i, _i, _vp, _vp, _vp]),
     "vd_yolo3_loss_workspace_bytes": (_sz, [_i, _i]),
     "vd_yolo3_loss": (_i, [_i, _i, _i] + [_vp] * 14 + [_vp, _sz, _vp]),
 }

@@ -878,3 +878,63 @@ def postprocess_detections(ids, scores, bboxes, size):
     counts = torch.empty((F,), dtype=torch.int32, device=i2.device)
     check(load().vd_postprocess_detections(ptr(i2), ptr(s2), ptr(b2), F, post, float(size), ptr(rows), ptr(counts), stream_ptr()))
     return rows, counts
+
+
+class ClassTree:
+    """The three tables `hierarchical_nms` reads from the combined dataset (detect_yolo3.py:738-746), on the device:
+    levels = dataset.get_levels() (combined.py:117-126), parent = class index of each class's parent (-1 under ROOT),
+    branch[i][j] = dataset.on_branch(i, j) (combined.py:143-150).  `from_parents(wn_classes, parents)` builds them from the
+    reference's own encoding (list of wnids + child->parent dict with 'ROOT')."""
+
+    def __init__(self, levels, parent, branch):
+        self.levels = torch.as_tensor(np.asarray(levels), dtype=torch.int32).cuda().contiguous()
+        self.parent = torch.as_tensor(np.asarray(parent), dtype=torch.int32).cuda().contiguous()
+        self.branch = torch.as_tensor(np.asarray(branch), dtype=torch.uint8).cuda().contiguous()
+        self.num_class = int(self.levels.numel())
+        assert self.parent.numel() == self.num_class and tuple(self.branch.shape) == (self.num_class, self.num_class)
+        self.min_level = int(np.asarray(levels).min()) if self.num_class else 0
+
+    @staticmethod
+    def tables(wn_classes, parents):
+        """(levels, parent, branch) numpy tables from the reference's encoding (host-side, no device needed)."""
+        idx = {c: i for i, c in enumerate(wn_classes)}
+        n = len(wn_classes)
+        parent = np.array([idx[parents[c]] if parents[c] != "ROOT" else -1 for c in wn_classes], np.int32)
+        levels = np.zeros(n, np.int32)
+        anc = []
+        for i in range(n):
+            chain, p = [i], parent[i]
+            while p >= 0:
+                chain.append(int(p)); p = parent[p]
+            levels[i] = len(chain)
+            anc.append(set(chain))
+        branch = np.zeros((n, n), np.uint8)
+        for i in range(n):
+            for j in range(n):
+                child, par = max(i, j), min(i, j)            # combined.py:147-150: the smaller index is looked up in the larger one's lineage
+                branch[i, j] = 1 if (i == j or par in anc[child]) else 0
+        return levels, parent, branch
+
+    @classmethod
+    def from_parents(cls, wn_classes, parents):
+        return cls(*cls.tables(wn_classes, parents))
+
+
+def hierarchical_nms(rows, counts, tree, ov_thresh=0.5, conf_thresh=0.0, level_thresh=10, arith="float64"):
+    """detect_yolo3.py:736-789 on the packed predictions `postprocess_detections` returns: rows (F, post, 6), counts (F,) ->
+    (rows, counts) of the merged lists.  arith 'float64' = the reference on re-loaded predictions (Python floats),
+    'legacy32' = its in-memory path under the NumPy of its era (np.float32 scalars)."""
+    _require_cuda(rows, "rows"); _require_cuda(counts, "counts")
+    assert rows.dim() == 3 and rows.shape[-1] == 6
+    level_thresh = max(0, int(level_thresh))
+    if tree.num_class and level_thresh < tree.min_level:
+        raise ValueError("'ROOT' is not in list")       # what `cls_map.index(parents[...])` raises at :766 once a lift reaches ROOT
+    F, post, _ = rows.shape
+    r = rows.to(torch.float32).contiguous()
+    c = counts.to(torch.int32).contiguous()
+    out = torch.empty_like(r)
+    ocnt = torch.empty_like(c)
+    check(load().vd_hierarchical_nms(ptr(r), ptr(c), F, post, tree.num_class, ptr(tree.levels), ptr(tree.parent), ptr(tree.branch),
+                                     float(ov_thresh), float(conf_thresh), level_thresh, {"float64": 0, "legacy32": 1}[arith],
+                                     ptr(out), ptr(ocnt), stream_ptr()))
+    return out, ocnt

@@ -189,3 +189,122 @@ extern "C" int vd_postprocess_detections(const float* ids, const float* scores, 
     VD_LAUNCH_CHECK();
     return VD_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// vd_hierarchical_nms -- detect_yolo3.py:736-789 (`hierarchical_nms`, applied to the predictions of the combined
+// class tree at :898-899) on device.  Per image: boxes sorted by class index descending (stable, :756), each lifted to
+// its ancestor at `level_thresh` (:765-766), then greedily merged into the kept list: the kept box with the largest
+// IoU above `ov_thresh` (first one on ties, :771-775) decides -- none: append; not on the same branch: append; same
+// class: max the confidences; otherwise (a descendant already stands there) drop (:777-787).  `iou` is the reference's
+// PASCAL-style one (`+ 1` extents, :712-733).  The walk over the boxes is inherently sequential; one warp per image
+// runs it, the lanes share the search over the kept list.  arith 0: float64 on the fp32 inputs (= the reference on
+// predictions re-loaded from its .txt files, Python floats; pinned by tests/golden/hier_nms_golden.npz); arith 1: the
+// legacy-NumPy in-memory path (np.float32 scalars: the six coordinate differences round to fp32, everything after the
+// first `+ 1` is float64).
+// ---------------------------------------------------------------------------------------------------------------
+namespace vd {
+constexpr int kHierMaxPost = 256;
+constexpr int kHierWarps = 4;
+
+template <int ARITH>
+__device__ __forceinline__ double hier_iou(const float4 a, const float4 b) {
+    const float x2 = fminf(a.z, b.z), x1 = fmaxf(a.x, b.x), y2 = fminf(a.w, b.w), y1 = fmaxf(a.y, b.y);
+    auto diff = [](float hi, float lo) -> double {
+        if (ARITH == 1) return (double)__fsub_rn(hi, lo);
+        return __dsub_rn((double)hi, (double)lo);
+    };
+    const double iw = __dadd_rn(diff(x2, x1), 1.0), ih = __dadd_rn(diff(y2, y1), 1.0);
+    if (!(iw > 0.0 && ih > 0.0)) return 0.0;
+    const double inter = __dmul_rn(iw, ih);
+    const double aa = __dmul_rn(__dadd_rn(diff(a.z, a.x), 1.0), __dadd_rn(diff(a.w, a.y), 1.0));
+    const double ab = __dmul_rn(__dadd_rn(diff(b.z, b.x), 1.0), __dadd_rn(diff(b.w, b.y), 1.0));
+    const double ua = __dsub_rn(__dadd_rn(aa, ab), inter);
+    return __ddiv_rn(inter, ua);
+}
+
+template <int ARITH>
+__global__ void __launch_bounds__(kHierWarps * 32)
+hier_nms_kernel(const float* __restrict__ rows, const int32_t* __restrict__ counts, int frames, int post, int C,
+                const int32_t* __restrict__ levels, const int32_t* __restrict__ parent, const uint8_t* __restrict__ branch,
+                double ov_thresh, double conf_thresh, int level_thresh, float* __restrict__ out_rows, int32_t* __restrict__ out_counts) {
+    __shared__ uint16_t s_order[kHierWarps][kHierMaxPost];
+    __shared__ int s_kcls[kHierWarps][kHierMaxPost];
+    __shared__ float s_kconf[kHierWarps][kHierMaxPost];
+    __shared__ float4 s_kbox[kHierWarps][kHierMaxPost];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int f = blockIdx.x * kHierWarps + w;
+    if (f >= frames) return;
+    const float* R = rows + (size_t)f * post * 6;
+    int n = counts[f]; n = n < 0 ? 0 : (n > post ? post : n);
+    // stable descending sort by class index: rank = #{class greater} + #{equal class, earlier row}
+    for (int i = lane; i < n; i += 32) {
+        const int ci = (int)R[i * 6];
+        int rank = 0;
+        for (int j = 0; j < n; ++j) { const int cj = (int)R[j * 6]; rank += (cj > ci || (cj == ci && j < i)) ? 1 : 0; }
+        s_order[w][rank] = (uint16_t)i;
+    }
+    __syncwarp();
+    int m = 0;
+    for (int r = 0; r < n; ++r) {
+        const int i = s_order[w][r];
+        int cls = (int)R[i * 6];
+        const float conf = R[i * 6 + 1];
+        if ((double)conf < conf_thresh) continue;
+        if (cls < 0 || cls >= C) continue;                                   // not a class of the tree (the reference would raise)
+        while (levels[cls] > level_thresh && parent[cls] >= 0) cls = parent[cls];
+        const float4 bx = make_float4(R[i * 6 + 2], R[i * 6 + 3], R[i * 6 + 4], R[i * 6 + 5]);
+        double best = 0.0; int bidx = -1;
+        for (int k = lane; k < m; k += 32) {
+            const double ov = hier_iou<ARITH>(bx, s_kbox[w][k]);
+            if (ov > ov_thresh && ov > best) { best = ov; bidx = k; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bidx, o);
+            if (oi >= 0 && (bidx < 0 || ob > best || (ob == best && oi < bidx))) { best = ob; bidx = oi; }
+        }
+        bool append = bidx < 0;
+        if (!append) {
+            const int kc = s_kcls[w][bidx];
+            if (!branch[(size_t)cls * C + kc]) append = true;
+            else if (cls == kc && lane == 0) s_kconf[w][bidx] = fmaxf(s_kconf[w][bidx], conf);
+        }
+        if (append) {
+            if (lane == 0) { s_kcls[w][m] = cls; s_kconf[w][m] = conf; s_kbox[w][m] = bx; }
+            ++m;
+        }
+        __syncwarp();
+    }
+    float* O = out_rows + (size_t)f * post * 6;
+    for (int k = lane; k < post; k += 32) {
+        float v[6] = {-1.f, -1.f, -1.f, -1.f, -1.f, -1.f};
+        if (k < m) { const float4 b = s_kbox[w][k]; v[0] = (float)s_kcls[w][k]; v[1] = s_kconf[w][k]; v[2] = b.x; v[3] = b.y; v[4] = b.z; v[5] = b.w; }
+#pragma unroll
+        for (int e = 0; e < 6; ++e) O[k * 6 + e] = v[e];
+    }
+    if (lane == 0) out_counts[f] = m;
+}
+}  // namespace vd
+
+extern "C" int vd_hierarchical_nms(const float* rows, const int32_t* counts, int frames, int post, int num_class,
+                                   const int32_t* levels, const int32_t* parent, const uint8_t* branch,
+                                   double ov_thresh, double conf_thresh, int level_thresh, int arith,
+                                   float* out_rows, int32_t* out_counts, void* stream_) {
+    VD_CHECK_ARG(frames >= 0 && post > 0 && num_class > 0, "hierarchical_nms: bad shape frames=%d post=%d classes=%d", frames, post, num_class);
+    if (post > vd::kHierMaxPost) return vd::set_error(VD_ERR_UNSUPPORTED, "hierarchical_nms: post = %d rows per image, at most %d", post, vd::kHierMaxPost);
+    VD_CHECK_ARG(rows && counts && levels && parent && branch && out_rows && out_counts, "hierarchical_nms: null pointer");
+    VD_CHECK_ARG(arith == 0 || arith == 1, "hierarchical_nms: arith must be 0 (float64) or 1 (legacy float32 scalars)");
+    VD_CHECK_ARG(rows != out_rows, "hierarchical_nms: in-place operation is not supported");
+    if (frames == 0) return VD_OK;
+    if (level_thresh < 0) level_thresh = 0;                                  // detect_yolo3.py:749
+    const int grid = vd::ceil_div(frames, vd::kHierWarps);
+    if (arith == 0)
+        vd::hier_nms_kernel<0><<<grid, vd::kHierWarps * 32, 0, (cudaStream_t)stream_>>>(rows, counts, frames, post, num_class, levels, parent, branch,
+                                                                                    ov_thresh, conf_thresh, level_thresh, out_rows, out_counts);
+    else
+        vd::hier_nms_kernel<1><<<grid, vd::kHierWarps * 32, 0, (cudaStream_t)stream_>>>(rows, counts, frames, post, num_class, levels, parent, branch,
+                                                                                    ov_thresh, conf_thresh, level_thresh, out_rows, out_counts);
+    VD_LAUNCH_CHECK();
+    return VD_OK;
+}

@@ -1,6 +1,6 @@
 """Oracle: 1x1 prediction conv + YOLOOutputV3 decode + scale concat (numpy, fp32).
 
-TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).  Parity unpinned by the reference.
+TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).  Own logic pinned against the executed reference source (tests/golden/ref_exec_golden.npz, see oracle/__init__.py); the MXNet operators it calls are restated.
 
 Follows, line by line:
   * models/definitions/yolo/yolo3.py:43-74    (constructor constants: anchors, offsets)

@@ -1,6 +1,6 @@
 """Oracle: YOLOV3DynamicTargetGeneratorSimple + YOLOV3TargetMerger + YOLOV3Loss (numpy, explicit fp32).
 
-TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).  Parity unpinned by the reference.
+TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).  Own logic pinned against the executed reference source (tests/golden/ref_exec_golden.npz, see oracle/__init__.py); the MXNet operators it calls are restated.
 
 Follows:
   * models/definitions/yolo/yolo_target.py:151-205  YOLOV3DynamicTargetGeneratorSimple.hybrid_forward

@@ -1,6 +1,7 @@
 """Oracle: the host-side post-processing loop of detect() (numpy).
 
-TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).  Parity unpinned by the reference.
+TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).  `hierarchical_nms` is pinned bit-exactly by golden vectors produced by executing
+the reference's own function (tests/golden/hier_nms_golden.npz); `postprocess` (numpy restatement of detect()'s inline loop) is unpinned.
 
 Follows detect_yolo3.py:222-261: `bboxes.clip(0, S)` (MXNet fp32 clip, :226), then per image
 `valid_pred = where(id >= 0)` (:256), `box / S` (:257, float32 array / python int -> float32), `id.astype(int)` (:258),

@@ -1,6 +1,6 @@
 """Oracle: YOLOV3PrefetchTargetGenerator (literal Python double loop on numpy, explicit dtypes).
 
-TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).  Parity unpinned by the reference.
+TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).  Own logic pinned against the executed reference source (tests/golden/ref_exec_golden.npz, see oracle/__init__.py); the MXNet operators it calls are restated.
 
 Follows models/definitions/yolo/yolo_target.py:31-148 line by line; the MXNet/GluonCV pieces it
 calls (BBoxCornerToCenter, BBoxCenterToCorner, contrib.box_iou, argmax) are restated from
@@ -29,7 +29,7 @@ def corner_to_center(boxes):
 
 
 def prefetch_targets(img_shape, xs_shapes, anchors, offsets, gt_boxes, gt_ids, gt_mixratio=None,
-                     num_class=None, return_assign=False):
+                     num_class=None, return_assign=False, promotion="legacy"):
     """yolo_target.py:31-137.
 
     img_shape: shape of `img` (only [2],[3] used, :72-73).  xs_shapes: shapes of the 3 fake feature
@@ -38,6 +38,9 @@ def prefetch_targets(img_shape, xs_shapes, anchors, offsets, gt_boxes, gt_ids, g
     padded with -1.  gt_ids (B,M,1) or multi-hot (B,M,C).  gt_mixratio (B,M,1) or None.
     Returns objectness (B,N,1), center (B,N,2), scale (B,N,2), weights (B,N,2), class (B,N,C);
     with return_assign also int32 arrays match (B,M), row (B,M) (final row index, -1 = not written).
+    promotion: 'legacy' = the NumPy < 2 scalar promotion of the reference's era (np.float32 scalar (op) python number ->
+    float64; the product behaviour); 'nep50' = NumPy >= 2 (stays fp32), used ONLY to compare bit-exactly with golden vectors
+    produced by executing the reference's own loop under the NumPy installed here (tests/golden/ref_exec_golden.npz).
     """
     gt_boxes = np.asarray(gt_boxes, dtype=f32)
     gt_ids = np.asarray(gt_ids, dtype=f32)
@@ -76,20 +79,21 @@ def prefetch_targets(img_shape, xs_shapes, anchors, offsets, gt_boxes, gt_ids, g
             height, width = int(xs_shapes[nlayer][2]), int(xs_shapes[nlayer][3])                  # :110-111
             x, y, w, h = gtx[b, m, 0], gty[b, m, 0], gtw[b, m, 0], gth[b, m, 0]                   # fp32 scalars
             # legacy promotion: np.float32 / python int -> float64
-            fx = f64(x) / orig_width * width
-            fy = f64(y) / orig_height * height
+            wide = f64 if promotion == "legacy" else f32
+            fx = wide(wide(wide(x) / wide(orig_width)) * wide(width))
+            fy = wide(wide(wide(y) / wide(orig_height)) * wide(height))
             loc_x = int(fx)                                                                       # :115
             loc_y = int(fy)                                                                       # :116
             index = _offsets[nlayer] + loc_y * width + loc_x                                      # :118
-            center_targets[b, index, match, 0] = f32(fx - loc_x)                                  # :119
-            center_targets[b, index, match, 1] = f32(fy - loc_y)                                  # :120
+            center_targets[b, index, match, 0] = f32(wide(fx - wide(loc_x)))                      # :119
+            center_targets[b, index, match, 1] = f32(wide(fy - wide(loc_y)))                      # :120
             aw, ah = all_anchors[match, 0], all_anchors[match, 1]
             # python max(gtw, 1): returns the fp32 gtw unless 1 > gtw (then the python int 1)
-            sx = f32(np.log(f32(w / aw))) if not (1 > w) else f32(np.log(f64(1) / f64(aw)))       # :121
-            sy = f32(np.log(f32(h / ah))) if not (1 > h) else f32(np.log(f64(1) / f64(ah)))       # :122
+            sx = f32(np.log(f32(w / aw))) if not (1 > w) else f32(np.log(wide(wide(1) / wide(aw))))   # :121
+            sy = f32(np.log(f32(h / ah))) if not (1 > h) else f32(np.log(wide(wide(1) / wide(ah))))   # :122
             scale_targets[b, index, match, 0] = sx
             scale_targets[b, index, match, 1] = sy
-            weights[b, index, match, :] = f32(2.0 - f64(f32(w * h)) / orig_width / orig_height)   # :123
+            weights[b, index, match, :] = f32(wide(2.0) - wide(wide(wide(f32(w * h)) / wide(orig_width)) / wide(orig_height)))   # :123
             objectness[b, index, match, 0] = gt_mixratio[b, m, 0] if gt_mixratio is not None else 1   # :124-125
             class_targets[b, index, match, :] = 0                                                 # :126
             if single:

@@ -1,0 +1,132 @@
+"""Generates tests/golden/ref_exec_golden.npz by EXECUTING the reference's own classes
+  YOLOOutputV3                          models/definitions/yolo/yolo3.py:25-199
+  YOLOV3PrefetchTargetGenerator         models/definitions/yolo/yolo_target.py:13-148
+  YOLOV3DynamicTargetGeneratorSimple    models/definitions/yolo/yolo_target.py:151-204
+  YOLOV3TargetMerger                    models/definitions/yolo/yolo_target.py:207-281
+over scripts/mx_shim.py (a numpy stand-in for the MXNet / GluonCV operators they call; MXNet itself cannot be imported here).
+The class sources are cut out of /root/reference with `ast` at run time and exec'd -- nothing is copied into the repo.
+What this pins: the reference's own logic (slicing, reshape/transposes = row order, the per-GT loop, index math, _slice,
+where-merges); what stays restated: the upstream operators inside the shim.  NumPy here is 2.x (NEP 50): np.float32 scalars
+mixed with Python numbers stay fp32, whereas the reference's era promoted them to float64 -- the target VALUES in
+this file are therefore the 'nep50' variant (<= 1 ulp from the legacy ones); assignments and class rows are identical.
+Authoring container only; the .npz travels."""
+import ast
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import mx_shim  # noqa: E402
+from mx_shim import ND, F  # noqa: E402
+
+REF = "/root/reference/models/definitions/yolo"
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "ref_exec_golden.npz")
+f32 = np.float32
+
+
+def load_classes(path, names):
+    src = open(path).read()
+    ns = mx_shim.namespace()
+    for n in ast.parse(src).body:
+        if isinstance(n, ast.ClassDef) and n.name in names:
+            exec(ast.get_source_segment(src, n), ns)
+    return [ns[n] for n in names]
+
+
+def bf16_round(x):
+    u = np.ascontiguousarray(x, f32).view(np.uint32).astype(np.uint64)
+    u = (u + 0x7FFF + ((u >> 16) & 1)) & 0xFFFF0000
+    return u.astype(np.uint32).view(f32).reshape(np.shape(x))
+
+
+ANCHORS = [[116, 90, 156, 198, 373, 326], [30, 61, 62, 45, 59, 119], [10, 13, 16, 30, 33, 23]]     # output order s32,s16,s8
+STRIDES = [32, 16, 8]
+
+
+def main():
+    (YOLOOutputV3,) = load_classes(os.path.join(REF, "yolo3.py"), ["YOLOOutputV3"])
+    Prefetch, Dynamic, Merger = load_classes(os.path.join(REF, "yolo_target.py"),
+                                             ["YOLOV3PrefetchTargetGenerator", "YOLOV3DynamicTargetGeneratorSimple", "YOLOV3TargetMerger"])
+    # the merger instantiates the dynamic generator by name
+    Merger.__init__.__globals__["YOLOV3DynamicTargetGeneratorSimple"] = Dynamic
+    rng = np.random.RandomState(20241019)
+    out = {}
+
+    # ---------------- YOLOOutputV3: inference, train-mode 7-tuple, agnostic
+    dec_cases = [(3, 0, 5, 4, 64, 2), (20, 1, 6, 6, 64, 1), (4, 2, 3, 7, 128, 2)]       # (C, scale index, H, W, Cin, B)
+    for ci, (C, si, H, W, Cin, B) in enumerate(dec_cases):
+        x = bf16_round(rng.standard_normal((B, Cin, H, W)).astype(f32))
+        n = 3 * (5 + C)
+        w = bf16_round(rng.uniform(-0.07, 0.07, (n, Cin, 1, 1)).astype(f32))
+        b = rng.uniform(-0.3, 0.3, n).astype(f32)
+        pre = "dec%d_" % ci
+        out.update({pre + "x": x, pre + "w": w, pre + "b": b, pre + "meta": np.array([C, si, H, W, Cin, B])})
+        for mode in ("infer", "train", "agnostic"):
+            blk = YOLOOutputV3(si, C, ANCHORS[si], STRIDES[si], agnostic=(mode == "agnostic"))
+            blk.prediction.weight, blk.prediction.bias = w, b
+            mx_shim.autograd.training = (mode == "train")
+            res = blk.hybrid_forward(F, ND(x), blk.anchors, blk.offsets)
+            mx_shim.autograd.training = False
+            if mode == "train":
+                for k, r in zip(("bbox", "raw_centers", "raw_scales", "objness", "class_pred", "anchors", "offsets"), res):
+                    out[pre + "train_" + k] = r.asnumpy()
+            else:
+                out[pre + mode] = res.asnumpy()
+
+    # ---------------- YOLOV3PrefetchTargetGenerator (+ merger on top of its outputs)
+    tg_cases = [(20, 2, 8, 128, False, False), (20, 3, 12, 416, False, True), (7, 2, 6, 160, True, False)]   # (C, B, M, size, multi-hot, mixup)
+    for ci, (C, B, M, size, multi, mix) in enumerate(tg_cases):
+        gt = np.full((B, M, 4), -1.0, f32)
+        ids = np.zeros((B, M, C), f32) if multi else np.full((B, M, 1), -1.0, f32)
+        for b in range(B):
+            nb = rng.randint(1, M + 1) if b else M                     # image 0 full, others ragged (-1 padding ends the loop)
+            w_ = np.exp(rng.uniform(np.log(4), np.log(size * 0.8), nb)); h_ = np.exp(rng.uniform(np.log(4), np.log(size * 0.8), nb))
+            cx = np.floor(rng.uniform(w_ / 2, size - w_ / 2)) + 0.37; cy = np.floor(rng.uniform(h_ / 2, size - h_ / 2)) + 0.61
+            gt[b, :nb] = np.stack([np.maximum(cx - w_ / 2, 0), np.maximum(cy - h_ / 2, 0),
+                                   np.minimum(cx + w_ / 2, size - 1e-3), np.minimum(cy + h_ / 2, size - 1e-3)], -1)
+            if nb >= 2:                                                # two GTs landing on the same cell + anchor: last writer wins
+                gt[b, 1] = gt[b, 0] + f32(0.25)
+            if multi:
+                for m in range(nb):
+                    ids[b, m, rng.choice(C, size=rng.randint(1, 4), replace=False)] = 1.0
+            else:
+                ids[b, :nb, 0] = rng.randint(0, C, nb)
+        mixr = rng.uniform(0.3, 1.0, (B, M, 1)).astype(f32) if mix else None
+        hw = [size // s for s in STRIDES]
+        img = ND(np.zeros((B, 3, size, size), f32))
+        xs = [ND(np.zeros((B, 1, h, h), f32)) for h in hw]
+        anchors = [ND(np.asarray(a, f32).reshape(1, 1, -1, 2)) for a in ANCHORS]
+        offsets = []
+        for h in hw:
+            gx, gy = np.meshgrid(np.arange(h), np.arange(h))
+            offsets.append(ND(np.concatenate((gx[:, :, None], gy[:, :, None]), -1).reshape(1, -1, 1, 2).astype(f32)))
+        gen = Prefetch(C)
+        res = gen.forward(img, xs, anchors, offsets, ND(gt), ND(ids), ND(mixr) if mix else None)
+        pre = "tg%d_" % ci
+        out.update({pre + "gt": gt, pre + "ids": ids, pre + "meta": np.array([C, B, M, size, int(multi), int(mix)])})
+        if mix:
+            out[pre + "mix"] = mixr
+        names = ("objectness", "center", "scale", "weights", "class")
+        for k, r in zip(names, res):
+            out[pre + k] = r.asnumpy()
+        # merger: predictions = jittered copies of a few GT boxes scattered over the anchor rows
+        N = res[0].shape[1]
+        preds = np.zeros((B, N, 4), f32)
+        xy = rng.uniform(0, size * 0.8, (B, N, 2)); wh = rng.uniform(8, size * 0.5, (B, N, 2))
+        preds[..., :2] = xy; preds[..., 2:] = xy + wh
+        for b in range(B):
+            rows = rng.choice(N, size=min(N, 40), replace=False)
+            src = gt[b, rng.randint(0, max(1, int((gt[b, :, 0] >= 0).sum())), size=len(rows))]
+            preds[b, rows] = src + rng.normal(0, 2.0, src.shape).astype(f32)
+        merged = Merger(C, 0.7)(ND(preds), ND(gt), *res)
+        out[pre + "preds"] = preds
+        for k, r in zip(names + ("class_mask",), merged):
+            out[pre + "merged_" + k] = r.asnumpy()
+    out["n_dec"] = np.array(len(dec_cases)); out["n_tg"] = np.array(len(tg_cases))
+    np.savez_compressed(OUT, **out)
+    print("wrote", OUT, os.path.getsize(OUT), "bytes")
+
+
+if __name__ == "__main__":
+    main()

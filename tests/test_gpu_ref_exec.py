@@ -1,0 +1,76 @@
+"""The CUDA path against golden vectors produced by EXECUTING the reference's own classes over a numpy stand-in for the MXNet
+operators (scripts/make_golden_ref_exec.py): YOLOOutputV3 (all three modes), YOLOV3PrefetchTargetGenerator, YOLOV3TargetMerger."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import ref_targets
+
+pytestmark = pytest.mark.gpu
+G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_exec_golden.npz"))
+ANCHORS = [[116, 90, 156, 198, 373, 326], [30, 61, 62, 45, 59, 119], [10, 13, 16, 30, 33, 23]]
+STRIDES = [32, 16, 8]
+
+
+def cuda(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def test_yolo_output_v3_vs_executed_reference():
+    """bf16-representable inputs, fp32 accumulation on both sides: 1e-5 relative (the fp32 bar of BASELINE.json), class ids
+    (= the row order of the (B, C*HW*A, 6) tensor) exact."""
+    import viddet_b200
+    for ci in range(int(G["n_dec"])):
+        pre = "dec%d_" % ci
+        C, si, H, W, Cin, B = [int(v) for v in G[pre + "meta"]]
+        x, w, b = G[pre + "x"], G[pre + "w"], G[pre + "b"]
+        for mode in ("infer", "agnostic"):
+            blk = viddet_b200.YOLOOutputV3(si, C, ANCHORS[si], STRIDES[si], agnostic=(mode == "agnostic"))
+            blk.prediction.set_data(torch.from_numpy(w), torch.from_numpy(b))
+            det = blk(cuda(x)).cpu().numpy()
+            gold = G[pre + mode]
+            assert det.shape == gold.shape
+            np.testing.assert_array_equal(det[..., 0], gold[..., 0])
+            np.testing.assert_allclose(det[..., 1], gold[..., 1], rtol=1e-5, atol=1e-6)
+            np.testing.assert_allclose(det[..., 2:], gold[..., 2:], rtol=1e-5, atol=5e-4)
+        blk = viddet_b200.YOLOOutputV3(si, C, ANCHORS[si], STRIDES[si])
+        blk.prediction.set_data(torch.from_numpy(w), torch.from_numpy(b))
+        tr = blk(cuda(x), training=True)
+        for got, k in zip(tr, ("bbox", "raw_centers", "raw_scales", "objness", "class_pred", "anchors", "offsets")):
+            gold = G[pre + "train_" + k]
+            got = got.cpu().numpy() if isinstance(got, torch.Tensor) else np.asarray(got)
+            assert got.shape == gold.shape, (k, got.shape, gold.shape)
+            np.testing.assert_allclose(got, gold, rtol=1e-5, atol=5e-4, err_msg=k)
+
+
+def test_prefetch_targets_vs_executed_reference():
+    """Assignments (which rows are written, objectness, class rows) bit-exact; regression values within ~1 ulp (the product
+    follows the NumPy < 2 scalar promotion of the reference's era, the goldens were computed under NumPy 2)."""
+    import viddet_b200
+    names = ("objectness", "center", "scale", "weights", "class")
+    for ci in range(int(G["n_tg"])):
+        pre = "tg%d_" % ci
+        C, B, M, size, multi, mix = [int(v) for v in G[pre + "meta"]]
+        img, xs, anchors, offsets = ref_targets.default_generator_inputs(size)
+        gen = viddet_b200.YOLOV3PrefetchTargetGenerator(C)
+        outs = gen((B,) + tuple(img[1:]), xs, [torch.from_numpy(a) for a in anchors], offsets, cuda(G[pre + "gt"]), cuda(G[pre + "ids"]),
+                   cuda(G[pre + "mix"]) if mix else None)
+        outs = [o.cpu().numpy() for o in outs]
+        np.testing.assert_array_equal(outs[0], G[pre + "objectness"])
+        np.testing.assert_array_equal(outs[4], G[pre + "class"])
+        for i in (1, 2, 3):
+            np.testing.assert_array_equal(outs[i] != 0, G[pre + names[i]] != 0)
+            np.testing.assert_allclose(outs[i], G[pre + names[i]], rtol=1e-6, atol=4e-6)
+
+
+def test_target_merger_vs_executed_reference_bit_exact():
+    import viddet_b200
+    names = ("objectness", "center", "scale", "weights", "class", "class_mask")
+    for ci in range(int(G["n_tg"])):
+        pre = "tg%d_" % ci
+        C = int(G[pre + "meta"][0])
+        out = viddet_b200.YOLOV3TargetMerger(C, 0.7)(cuda(G[pre + "preds"]), cuda(G[pre + "gt"]), *[cuda(G[pre + k]) for k in names[:5]])
+        for k, o in zip(names, out):
+            np.testing.assert_array_equal(o.cpu().numpy(), G[pre + "merged_" + k], err_msg="%s %s" % (pre, k))

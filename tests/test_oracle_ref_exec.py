@@ -1,0 +1,69 @@
+"""The oracle against golden vectors produced by EXECUTING the reference's own classes (YOLOOutputV3, the prefetch target
+generator, the dynamic generator + merger) over a numpy stand-in for the MXNet operators (scripts/make_golden_ref_exec.py,
+scripts/mx_shim.py).  Pins the reference's own logic -- slicing, row order, the per-GT loop, index math, _slice, merges."""
+import os
+
+import numpy as np
+
+from oracle import ref_head, ref_loss, ref_targets
+
+G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_exec_golden.npz"))
+ANCHORS = [[116, 90, 156, 198, 373, 326], [30, 61, 62, 45, 59, 119], [10, 13, 16, 30, 33, 23]]
+STRIDES = [32, 16, 8]
+
+
+def test_decode_matches_executed_reference():
+    for ci in range(int(G["n_dec"])):
+        pre = "dec%d_" % ci
+        C, si, H, W, Cin, B = [int(v) for v in G[pre + "meta"]]
+        x, w, b = G[pre + "x"], G[pre + "w"], G[pre + "b"]
+        det = ref_head.yolo_output_v3(x, w, b, ANCHORS[si], STRIDES[si], C, "infer")
+        gold = G[pre + "infer"]
+        assert det.shape == gold.shape == (B, C * H * W * 3, 6)
+        np.testing.assert_array_equal(det[..., 0], gold[..., 0])                       # class ids: the row order itself
+        np.testing.assert_allclose(det[..., 1], gold[..., 1], rtol=1e-5, atol=1e-7)    # conv summation order differs
+        np.testing.assert_allclose(det[..., 2:], gold[..., 2:], rtol=1e-5, atol=2e-4)
+        ag = ref_head.yolo_output_v3(x, w, b, ANCHORS[si], STRIDES[si], C, "agnostic")
+        np.testing.assert_allclose(ag, G[pre + "agnostic"], rtol=1e-5, atol=2e-4)
+        tr = ref_head.yolo_output_v3(x, w, b, ANCHORS[si], STRIDES[si], C, "train")
+        for got, k in zip(tr, ("bbox", "raw_centers", "raw_scales", "objness", "class_pred", "anchors", "offsets")):
+            gold = G[pre + "train_" + k]
+            assert np.shape(got) == gold.shape, k
+            np.testing.assert_allclose(got, gold, rtol=1e-5, atol=2e-4, err_msg=k)
+
+
+def _tg_inputs(pre):
+    C, B, M, size, multi, mix = [int(v) for v in G[pre + "meta"]]
+    img_shape, xs_shapes, anchors, offsets = ref_targets.default_generator_inputs(size)
+    return C, (B,) + tuple(img_shape[1:]), xs_shapes, anchors, offsets, G[pre + "gt"], G[pre + "ids"], (G[pre + "mix"] if mix else None)
+
+
+def test_prefetch_targets_match_executed_reference():
+    names = ("objectness", "center", "scale", "weights", "class")
+    for ci in range(int(G["n_tg"])):
+        pre = "tg%d_" % ci
+        C, img_shape, xs_shapes, anchors, offsets, gt, ids, mix = _tg_inputs(pre)
+        # same NumPy scalar semantics as the executed reference: bit-exact, every tensor
+        res = ref_targets.prefetch_targets(img_shape, xs_shapes, anchors, offsets, gt, ids, mix, num_class=C, promotion="nep50")
+        for k, r in zip(names, res):
+            np.testing.assert_array_equal(r, G[pre + k], err_msg="%s %s" % (pre, k))
+        # the era's promotion (what the product implements): same assignments and class rows, values within ~1 ulp
+        leg = ref_targets.prefetch_targets(img_shape, xs_shapes, anchors, offsets, gt, ids, mix, num_class=C)
+        np.testing.assert_array_equal(leg[0], G[pre + "objectness"])
+        np.testing.assert_array_equal(leg[4], G[pre + "class"])
+        for i in (1, 2, 3):
+            np.testing.assert_array_equal(leg[i] != 0, G[pre + names[i]] != 0)
+            np.testing.assert_allclose(leg[i], G[pre + names[i]], rtol=5e-7, atol=4e-6)
+        assert (G[pre + "objectness"] > 0).sum() > 0
+
+
+def test_target_merger_matches_executed_reference():
+    names = ("objectness", "center", "scale", "weights", "class", "class_mask")
+    for ci in range(int(G["n_tg"])):
+        pre = "tg%d_" % ci
+        C = int(G[pre + "meta"][0])
+        pf = [G[pre + k] for k in names[:5]]
+        res = ref_loss.target_merge(G[pre + "preds"], G[pre + "gt"], *pf, num_class=C, ignore_iou_thresh=0.7)
+        for k, r in zip(names, res):
+            np.testing.assert_array_equal(np.asarray(r, np.float32), G[pre + "merged_" + k], err_msg="%s %s" % (pre, k))
+        assert (G[pre + "merged_objectness"] < 0).sum() > 0          # some predictions are ignored (IoU > 0.7, not matched)

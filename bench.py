@@ -217,6 +217,12 @@ def main():
         return run_reference(args)
     assert args.warmup >= 3, "timing rules: at least 3 warm-up steps"
 
+    # stdout carries exactly ONE line (the JSON): libraries that print there (NCCL's version banner under NCCL_DEBUG=VERSION)
+    # are routed to stderr for the duration of the run
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+
     import torch
     import torch.distributed as dist
     import viddet_b200
@@ -233,9 +239,10 @@ def main():
     head = viddet_b200.YOLOV3Head(C).initialize(generator=cpu_gen)       # U(-0.07,0.07), bias 0 (detect_yolo3.py:885)
     head.set_nms(nms_thresh=0.45, nms_topk=400, post_nms=100)            # detect_yolo3.py:200
     # ring of NROT resident batches; the detections of the whole ring live in one tensor per field (gathered per cycle)
-    ids_all = torch.empty((NROT * frames, 100, 1), device=dev)
-    scores_all = torch.empty((NROT * frames, 100, 1), device=dev)
-    boxes_all = torch.empty((NROT * frames, 100, 4), device=dev)
+    # (one allocation, field-major, so that the gather is ONE copy + ONE collective)
+    nf = NROT * frames * 100
+    flat = torch.empty((nf * 6,), device=dev)
+    ids_all, scores_all, boxes_all = flat[:nf].view(NROT * frames, 100, 1), flat[nf:2 * nf].view(NROT * frames, 100, 1), flat[2 * nf:].view(NROT * frames, 100, 4)
     sessions = []
     for j in range(NROT):
         sl = slice(j * frames, (j + 1) * frames)
@@ -247,8 +254,8 @@ def main():
     fields = (ids_all, scores_all, boxes_all)
     if world > 1:                                        # the path's only collective: final detection gather, off the critical path
         side = torch.cuda.Stream()
-        snaps = [[torch.empty_like(t) for t in fields] for _ in range(2)]
-        gouts = [torch.empty((world,) + tuple(t.shape), device=dev) for t in fields]
+        snaps = [torch.empty_like(flat) for _ in range(2)]
+        gout = torch.empty((world * flat.numel(),), device=dev)
         gather_done = [None, None]
     state = {"c": 0}
 
@@ -259,13 +266,11 @@ def main():
         main = torch.cuda.current_stream()
         if gather_done[c] is not None:
             main.wait_event(gather_done[c])
-        for dst, src in zip(snaps[c], fields):
-            dst.copy_(src)
+        snaps[c].copy_(flat)
         ev = torch.cuda.Event(); ev.record(main)
         with torch.cuda.stream(side):
             side.wait_event(ev)
-            for g, sn in zip(gouts, snaps[c]):
-                dist.all_gather_into_tensor(g, sn)
+            dist.all_gather_into_tensor(gout, snaps[c])
             gather_done[c] = torch.cuda.Event(); gather_done[c].record(side)
 
     def run_steps(n):
@@ -399,7 +404,7 @@ def main():
             "gpu_launches": args.steps * sess.launches,                   # head kernel + NMS kernel per step
             "clocks": clocks,
         }
-        print(json.dumps(line))
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

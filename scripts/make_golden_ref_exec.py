@@ -3,6 +3,7 @@
   YOLOV3PrefetchTargetGenerator         models/definitions/yolo/yolo_target.py:13-148
   YOLOV3DynamicTargetGeneratorSimple    models/definitions/yolo/yolo_target.py:151-204
   YOLOV3TargetMerger                    models/definitions/yolo/yolo_target.py:207-281
+  TimeDistributed, TemporalPooling      models/definitions/layers.py:161-264
 over scripts/mx_shim.py (a numpy stand-in for the MXNet / GluonCV operators they call; MXNet itself cannot be imported here).
 The class sources are cut out of /root/reference with `ast` at run time and exec'd -- nothing is copied into the repo.
 What this pins: the reference's own logic (slicing, reshape/transposes = row order, the per-GT loop, index math, _slice,
@@ -123,6 +124,20 @@ def main():
         out[pre + "preds"] = preds
         for k, r in zip(names + ("class_mask",), merged):
             out[pre + "merged_" + k] = r.asnumpy()
+    # ---------------- TimeDistributed(YOLOOutputV3) on a (B,T,C,H,W) window, TemporalPooling max / mean
+    TemporalPooling, TimeDistributed = load_classes("/root/reference/models/definitions/layers.py", ["TemporalPooling", "TimeDistributed"])
+    C, si, H, W, Cin, B, T = 5, 1, 4, 5, 64, 2, 3
+    x = bf16_round(rng.standard_normal((B, T, Cin, H, W)).astype(f32))
+    n = 3 * (5 + C)
+    w = bf16_round(rng.uniform(-0.07, 0.07, (n, Cin, 1, 1)).astype(f32)); b = rng.uniform(-0.3, 0.3, n).astype(f32)
+    blk = YOLOOutputV3(si, C, ANCHORS[si], STRIDES[si])
+    blk.prediction.weight, blk.prediction.bias = w, b
+    blk_call = lambda z: blk.hybrid_forward(F, z, blk.anchors, blk.offsets)
+    td = TimeDistributed(blk_call)
+    out.update({"td_x": x, "td_w": w, "td_b": b, "td_meta": np.array([C, si, H, W, Cin, B, T]),
+                "td_out": td.hybrid_forward(F, ND(x)).asnumpy(),
+                "pool_max": TemporalPooling(T, "max").hybrid_forward(F, ND(x)).asnumpy(),
+                "pool_mean": TemporalPooling(T, "mean").hybrid_forward(F, ND(x)).asnumpy()})
     out["n_dec"] = np.array(len(dec_cases)); out["n_tg"] = np.array(len(tg_cases))
     np.savez_compressed(OUT, **out)
     print("wrote", OUT, os.path.getsize(OUT), "bytes")

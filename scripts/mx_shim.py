@@ -141,6 +141,17 @@ class F:
     stop_gradient = staticmethod(lambda x: x)
     split = staticmethod(lambda x, axis, num_outputs, squeeze_axis=False: x.split(axis, num_outputs, squeeze_axis))
 
+    max = staticmethod(lambda x, axis=None, keepdims=False: x.max(axis=axis, keepdims=keepdims))
+    mean = staticmethod(lambda x, axis=None, keepdims=False: ND(x.a.mean(axis=axis, keepdims=keepdims, dtype=f32)))
+    squeeze = staticmethod(lambda x, axis=None: x.squeeze(axis=axis))
+
+    @staticmethod
+    def reshape_like(lhs, rhs, lhs_begin=None, lhs_end=None, rhs_begin=None, rhs_end=None):
+        ls, rs = list(lhs.shape), list(rhs.shape)
+        lb, le = (0 if lhs_begin is None else lhs_begin), (len(ls) if lhs_end is None else lhs_end)
+        rb, re_ = (0 if rhs_begin is None else rhs_begin), (len(rs) if rhs_end is None else rhs_end)
+        return ND(lhs.a.reshape(ls[:lb] + rs[rb:re_] + ls[le:]))
+
     @staticmethod
     def slice_like(x, like, axes):
         sl = [slice(None)] * x.a.ndim

@@ -74,3 +74,20 @@ def test_target_merger_vs_executed_reference_bit_exact():
         out = viddet_b200.YOLOV3TargetMerger(C, 0.7)(cuda(G[pre + "preds"]), cuda(G[pre + "gt"]), *[cuda(G[pre + k]) for k in names[:5]])
         for k, o in zip(names, out):
             np.testing.assert_array_equal(o.cpu().numpy(), G[pre + "merged_" + k], err_msg="%s %s" % (pre, k))
+
+
+def test_time_distributed_and_pooling_vs_executed_reference():
+    import viddet_b200
+    C, si, H, W, Cin, B, T = [int(v) for v in G["td_meta"]]
+    blk = viddet_b200.YOLOOutputV3(si, C, ANCHORS[si], STRIDES[si])
+    blk.prediction.set_data(torch.from_numpy(G["td_w"]), torch.from_numpy(G["td_b"]))
+    out = viddet_b200.TimeDistributed(blk)(cuda(G["td_x"])).cpu().numpy()
+    assert out.shape == G["td_out"].shape
+    np.testing.assert_array_equal(out[..., 0], G["td_out"][..., 0])
+    np.testing.assert_allclose(out[..., 1], G["td_out"][..., 1], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(out[..., 2:], G["td_out"][..., 2:], rtol=1e-5, atol=5e-4)
+    # pooling runs on the bf16 carrier: the inputs are bf16-representable, max is exact, mean rounds to bf16 once
+    mx = viddet_b200.TemporalPooling(T, "max")(cuda(G["td_x"])).float().cpu().numpy()
+    np.testing.assert_array_equal(mx, G["pool_max"])
+    mean = viddet_b200.TemporalPooling(T, "mean")(cuda(G["td_x"])).float().cpu().numpy()
+    np.testing.assert_allclose(mean, G["pool_mean"], rtol=8e-3, atol=1e-3)

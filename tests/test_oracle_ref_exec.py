@@ -67,3 +67,16 @@ def test_target_merger_matches_executed_reference():
         for k, r in zip(names, res):
             np.testing.assert_array_equal(np.asarray(r, np.float32), G[pre + "merged_" + k], err_msg="%s %s" % (pre, k))
         assert (G[pre + "merged_objectness"] < 0).sum() > 0          # some predictions are ignored (IoU > 0.7, not matched)
+
+
+def test_time_distributed_and_pooling_match_executed_reference():
+    from oracle import ref_temporal
+    C, si, H, W, Cin, B, T = [int(v) for v in G["td_meta"]]
+    x = G["td_x"]
+    fn = lambda z: ref_head.yolo_output_v3(z, G["td_w"], G["td_b"], ANCHORS[si], STRIDES[si], C, "infer")
+    out = ref_temporal.time_distributed(fn, x)
+    assert out.shape == G["td_out"].shape == (B, T, C * H * W * 3, 6)
+    np.testing.assert_array_equal(out[..., 0], G["td_out"][..., 0])
+    np.testing.assert_allclose(out, G["td_out"], rtol=1e-5, atol=2e-4)
+    np.testing.assert_array_equal(ref_temporal.temporal_pooling(x, "max"), G["pool_max"])
+    np.testing.assert_allclose(ref_temporal.temporal_pooling(x, "mean"), G["pool_mean"], rtol=1e-6, atol=1e-7)

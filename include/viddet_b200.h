@@ -186,6 +186,11 @@ int vd_temporal_conv(const void* x_bf16, void* y_bf16, int B, int T, int H, int 
 int vd_conv_bn_lrelu(const void* x_bf16, void* y_bf16, int B, int T, int H, int W, int Cin, int Cout,
                      int kt, int kh, int kw, const void* weight_bf16, const float* scale, const float* shift,
                      float slope, void* stream);
+/* The glue between two detection blocks (yolo3.py:515-519): nearest x2 upsample of x (`_upsample`, layers.py:10-20), cropped
+ * to the route map (`slice_like`), channel-concatenated in front of it.  x (B,H,W,C1), route (B,H2,W2,C2), out (B,H2,W2,C1+C2)
+ * bf16 channels-last; H2 <= 2H, W2 <= 2W; C1, C2 multiples of 8. */
+int vd_upsample_concat(const void* x_bf16, const void* route_bf16, void* out_bf16, int B, int H, int W, int C1,
+                       int H2, int W2, int C2, void* stream);
 /* The BW x BH x BF box of pixels x frames (BW*BH*BF <= 128) one MMA tile of vd_conv_bn_lrelu covers on F frames of an
  * H x W map (for roofline maths; F = B*T for kernels without a temporal extent, T otherwise). */
 int vd_conv_tile_box(int H, int W, int F, int* BW, int* BH, int* BF);

@@ -66,3 +66,30 @@ def detection_block(x, cells, conv_type="2", round_fn=None):
     route = run(z, 1)
     tip = run(route, n_exp)
     return route, tip
+
+
+def upsample_concat(x, route):
+    """yolo3.py:515-519: `_upsample(x, 2)` (layers.py:10-20: repeat along W then H = nearest), `slice_like` crop to the route map,
+    concat in FRONT of the route along channels."""
+    x = np.asarray(x, f32)
+    up = x.repeat(2, axis=-1).repeat(2, axis=-2)
+    H, W = route.shape[-2:]
+    return np.concatenate([up[..., :H, :W], np.asarray(route, f32)], axis=1)
+
+
+def yolo3_neck_tips(routes, blocks, transitions, round_fn=None):
+    """YOLOV3.hybrid_forward after the stages (yolo3.py:496-521), inference: routes = stage outputs shallow -> deep; blocks[i] =
+    list of 6 cell dicts of the i-th (deep -> shallow) YOLODetectionBlockV3, transitions[i] = cell dict of `_conv2d(channel,1,0,1)`.
+    Returns the tips deep -> shallow."""
+    rf = round_fn if round_fn is not None else (lambda a: a)
+    rts = list(routes)[::-1]
+    x, tips = np.asarray(rts[0], f32), []
+    for i, cells in enumerate(blocks):
+        x, tip = detection_block(x, cells, "2", round_fn=round_fn)
+        tips.append(tip)
+        if i >= len(rts) - 1:
+            break
+        t = transitions[i]
+        x = rf(conv_bn_lrelu(x, t["weight"], t["gamma"], t["beta"], t["mean"], t["var"]))
+        x = upsample_concat(x, rts[i + 1])
+    return tips

@@ -4,6 +4,7 @@
   YOLOV3DynamicTargetGeneratorSimple    models/definitions/yolo/yolo_target.py:151-204
   YOLOV3TargetMerger                    models/definitions/yolo/yolo_target.py:207-281
   TimeDistributed, TemporalPooling      models/definitions/layers.py:161-264
+  YOLOV3 (+ YOLODetectionBlockV3, _conv2d, _upsample)   yolo3.py:202-534, layers.py:10-20,63-70  -- inference forward after the stages
 over scripts/mx_shim.py (a numpy stand-in for the MXNet / GluonCV operators they call; MXNet itself cannot be imported here).
 The class sources are cut out of /root/reference with `ast` at run time and exec'd -- nothing is copied into the repo.
 What this pins: the reference's own logic (slicing, reshape/transposes = row order, the per-GT loop, index math, _slice,
@@ -26,11 +27,12 @@ OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 
 f32 = np.float32
 
 
-def load_classes(path, names):
+def load_classes(path, names, ns=None):
+    """exec the named top-level classes / functions of a reference file into `ns` (a fresh shim namespace by default)."""
     src = open(path).read()
-    ns = mx_shim.namespace()
+    ns = mx_shim.namespace() if ns is None else ns
     for n in ast.parse(src).body:
-        if isinstance(n, ast.ClassDef) and n.name in names:
+        if isinstance(n, (ast.ClassDef, ast.FunctionDef)) and n.name in names:
             exec(ast.get_source_segment(src, n), ns)
     return [ns[n] for n in names]
 
@@ -138,6 +140,35 @@ def main():
                 "td_out": td.hybrid_forward(F, ND(x)).asnumpy(),
                 "pool_max": TemporalPooling(T, "max").hybrid_forward(F, ND(x)).asnumpy(),
                 "pool_mean": TemporalPooling(T, "mean").hybrid_forward(F, ND(x)).asnumpy()})
+    # ---------------- YOLOV3.hybrid_forward (inference) after the backbone stages: blocks, transitions, upsample + concat, outputs, NMS
+    ns = mx_shim.namespace()
+    load_classes("/root/reference/models/definitions/layers.py", ["_upsample", "_conv2d"], ns)
+    load_classes(os.path.join(REF, "yolo_target.py"), ["YOLOV3DynamicTargetGeneratorSimple", "YOLOV3TargetMerger"], ns)
+    YOLOV3, = load_classes(os.path.join(REF, "yolo3.py"), ["YOLOOutputV3", "YOLODetectionBlockV3", "YOLOV3"], ns)[2:]
+    C, B = 4, 2
+    hw = [(16, 16), (8, 8), (4, 4)]                                 # s8, s16, s32 maps of a 128 x 128 input
+    stage_ch = [64, 128, 192]
+    feats = [bf16_round(rng.standard_normal((B, c, h, w)).astype(f32)) for c, (h, w) in zip(stage_ch, hw)]
+    feats = [np.where(f > 0, f, 0.1 * f).astype(f32) for f in feats]
+    feats = [bf16_round(f) for f in feats]
+    stages = [(lambda z, f=f: ND(f)) for f in feats]               # backbone stand-ins: stage i emits the i-th pyramid level
+    mx_shim.PARAM_LOG.clear()
+    mx_shim.PARAM_RNG.seed(77)
+    net = YOLOV3(stages, [128, 128, 128], [[10, 13, 16, 30, 33, 23], [30, 61, 62, 45, 59, 119], [116, 90, 156, 198, 373, 326]],
+                 [8, 16, 32], classes=["c%d" % i for i in range(C)])
+    ids, scores, bboxes = net.hybrid_forward(F, ND(np.zeros((B, 3, 128, 128), f32)))
+    net.nms_thresh = 0                                             # yolo3.py:525: NMS skipped -> the plain concat of the decoded rows
+    rid, rsc, rbb = net.hybrid_forward(F, ND(np.zeros((B, 3, 128, 128), f32)))
+    out.update({"neck_ids": ids.asnumpy(), "neck_scores": scores.asnumpy(), "neck_bboxes": bboxes.asnumpy(),
+                "neck_det": np.concatenate([rid.asnumpy(), rsc.asnumpy(), rbb.asnumpy()], -1),
+                "neck_meta": np.array([C, B, len(mx_shim.PARAM_LOG)])})
+    for i, f in enumerate(feats):
+        out["neck_feat%d" % i] = f
+    # parameters are NOT stored (6 MB): the test replays the shim's draws from RandomState(77) (tests/util.py::replay_shim_params)
+    out["neck_param_kinds"] = np.array([0 if e[0] == "conv" else 1 for e in mx_shim.PARAM_LOG])
+    out["neck_param_shapes"] = np.array([list(e[1].shape) + [0] * (4 - e[1].ndim) for e in mx_shim.PARAM_LOG])
+    out["neck_param_bias"] = np.array([1 if (e[0] == "conv" and e[2] is not None) else 0 for e in mx_shim.PARAM_LOG])
+    out["neck_param_check"] = np.array([float(np.asarray(e[1], np.float64).sum()) for e in mx_shim.PARAM_LOG])
     out["n_dec"] = np.array(len(dec_cases)); out["n_tg"] = np.array(len(tg_cases))
     np.savez_compressed(OUT, **out)
     print("wrote", OUT, os.path.getsize(OUT), "bytes")

@@ -107,6 +107,15 @@ class ND:
 
 class _Contrib:
     @staticmethod
+    def box_nms(data, **kw):
+        """mx.nd.contrib.box_nms: delegated to the oracle's restatement (oracle/ref_nms.py) -- what the goldens pin around it
+        is the caller's wiring (concat order, parameters, slicing), not the operator."""
+        import os, sys
+        sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+        from oracle import ref_nms
+        return ND(np.asarray(ref_nms.box_nms(data.a, **kw), f32))
+
+    @staticmethod
     def box_iou(lhs, rhs, format="corner"):
         """mx.nd.contrib.box_iou, corner format: out[lhs..., rhs...] ; w,h clamped at 0 ; 0 where the union is <= 0."""
         a, b = lhs.a.reshape(-1, 4), rhs.a.reshape(-1, 4)
@@ -171,11 +180,14 @@ class autograd:
     training = False
     pause = staticmethod(contextlib.nullcontext)
     is_training = staticmethod(lambda: autograd.training)
+    is_recording = staticmethod(lambda: False)
 
 
 class _Params:
     def get_constant(self, name, value):
-        return ND(np.asarray(value, f32))
+        nd_ = ND(np.asarray(value, f32))
+        nd_._is_param = True                     # Gluon hands registered parameters to hybrid_forward as keyword arguments
+        return nd_
 
 
 class _Block:
@@ -186,7 +198,10 @@ class _Block:
         return contextlib.nullcontext()
 
     def __call__(self, *args):
-        return self.hybrid_forward(F, *args) if hasattr(self, "hybrid_forward") else self.forward(*args)
+        if hasattr(self, "hybrid_forward"):
+            params = {k: v for k, v in self.__dict__.items() if isinstance(v, ND) and getattr(v, "_is_param", False)}
+            return self.hybrid_forward(F, *args, **params)
+        return self.forward(*args)
 
 
 class gluon:
@@ -194,21 +209,99 @@ class gluon:
     HybridBlock = _Block
 
 
-class _Conv2D:
-    """nn.Conv2D(channels, kernel_size=1): fp32 1x1 convolution with a bias; weights are set by the caller."""
+PARAM_LOG = []          # parameters of every shim layer in order of first execution (the generator exports them)
+PARAM_RNG = np.random.RandomState(0)
 
-    def __init__(self, channels, kernel_size=1, padding=0, strides=1, **kw):
-        assert kernel_size == 1 and padding == 0 and strides == 1
-        self.channels, self.weight, self.bias = channels, None, None
+
+def _bf16_round(x):
+    u = np.ascontiguousarray(x, f32).view(np.uint32).astype(np.uint64)
+    u = (u + 0x7FFF + ((u >> 16) & 1)) & 0xFFFF0000
+    return u.astype(np.uint32).view(f32).reshape(np.shape(x))
+
+
+class _Conv2D:
+    """nn.Conv2D: fp32 cross-correlation, stride 1, zero padding, optional bias.  Weights: set by the caller (`weight`, `bias`)
+    or drawn at the first call (in_channels is inferred then, like Gluon's deferred init) and appended to PARAM_LOG."""
+
+    def __init__(self, channels, kernel_size=1, strides=1, padding=0, use_bias=True, in_channels=0, **kw):
+        k = kernel_size if isinstance(kernel_size, int) else kernel_size[0]
+        p_ = padding if isinstance(padding, int) else padding[0]
+        s_ = strides if isinstance(strides, int) else strides[0]
+        assert s_ == 1 and p_ == k // 2, "shim conv: stride 1, 'same' padding only"
+        self.channels, self.k, self.use_bias, self.weight, self.bias = channels, k, use_bias, None, None
 
     def __call__(self, x):
-        w = self.weight.reshape(self.channels, -1).astype(f32)
-        y = np.einsum("nk,bkhw->bnhw", w, x.a, optimize=False).astype(f32) + self.bias.astype(f32).reshape(1, -1, 1, 1)
+        cin = x.shape[1]
+        if self.weight is None:
+            fan = cin * self.k * self.k
+            self.weight = _bf16_round((PARAM_RNG.standard_normal((self.channels, cin, self.k, self.k)) * np.sqrt(2.0 / fan)).astype(f32))
+            self.bias = PARAM_RNG.uniform(-0.2, 0.2, self.channels).astype(f32) if self.use_bias else None
+            PARAM_LOG.append(("conv", self.weight, self.bias))
+        w = np.asarray(self.weight, f32).reshape(self.channels, cin, self.k, self.k)
+        B, _, H, W = x.shape
+        p_ = self.k // 2
+        xp = np.zeros((B, cin, H + 2 * p_, W + 2 * p_), f32)
+        xp[:, :, p_:p_ + H, p_:p_ + W] = x.a
+        y = np.zeros((B, self.channels, H, W), f32)
+        for j in range(self.k):
+            for i in range(self.k):
+                y += np.einsum("nk,bkhw->bnhw", w[:, :, j, i], xp[:, :, j:j + H, i:i + W], optimize=True).astype(f32)
+        if self.use_bias and self.bias is not None:
+            y = y + np.asarray(self.bias, f32).reshape(1, -1, 1, 1)
         return ND(y.astype(f32))
+
+
+class BatchNorm:
+    """Inference BatchNorm over axis 1: (x - mean) / sqrt(var + eps) * gamma + beta (fp32); statistics drawn at the first call."""
+
+    def __init__(self, epsilon=1e-5, momentum=0.9, **kw):
+        self.eps, self.p = epsilon, None
+
+    def __call__(self, x):
+        c = x.shape[1]
+        if self.p is None:
+            self.p = (PARAM_RNG.uniform(0.5, 1.5, c).astype(f32), PARAM_RNG.uniform(-0.2, 0.2, c).astype(f32),
+                      PARAM_RNG.uniform(-0.2, 0.2, c).astype(f32), PARAM_RNG.uniform(0.5, 1.5, c).astype(f32))
+            PARAM_LOG.append(("bn",) + self.p)
+        g, b, m, v = [t.reshape((1, c) + (1,) * (x.ndim - 2)) for t in self.p]
+        return ND(((x.a - m) / np.sqrt(v + f32(self.eps)) * g + b).astype(f32))
+
+
+class _LeakyReLU:
+    def __init__(self, alpha):
+        self.alpha = f32(alpha)
+
+    def __call__(self, x):
+        return ND(np.where(x.a > 0, x.a, x.a * self.alpha).astype(f32))
+
+
+class _HybridSequential:
+    def __init__(self, prefix=None, **kw):
+        self.layers = []
+
+    def add(self, *blocks):
+        self.layers.extend(blocks)
+
+    def __call__(self, x):
+        for l in self.layers:
+            x = l(x)
+        return x
+
+    def __getitem__(self, i):
+        return self.layers[i]
+
+    def __len__(self):
+        return len(self.layers)
+
+    def __iter__(self):
+        return iter(self.layers)
 
 
 class nn:
     Conv2D = _Conv2D
+    BatchNorm = BatchNorm
+    LeakyReLU = _LeakyReLU
+    HybridSequential = _HybridSequential
 
 
 # ---- gluoncv.nn.bbox (published definitions, gluon-cv 0.4/0.5)
@@ -259,5 +352,6 @@ class BBoxBatchIOU:
 def namespace():
     """Globals for exec'ing the reference classes."""
     import warnings
-    return {"np": np, "nd": F, "gluon": gluon, "nn": nn, "autograd": autograd, "warnings": warnings,
+    return {"np": np, "nd": F, "gluon": gluon, "nn": nn, "autograd": autograd, "warnings": warnings, "BatchNorm": BatchNorm,
+            "YOLOV3Loss": type("YOLOV3Loss", (), {}),
             "BBoxCornerToCenter": BBoxCornerToCenter, "BBoxCenterToCorner": BBoxCenterToCorner, "BBoxBatchIOU": BBoxBatchIOU}

@@ -91,3 +91,46 @@ def test_time_distributed_and_pooling_vs_executed_reference():
     np.testing.assert_array_equal(mx, G["pool_max"])
     mean = viddet_b200.TemporalPooling(T, "mean")(cuda(G["td_x"])).float().cpu().numpy()
     np.testing.assert_allclose(mean, G["pool_mean"], rtol=8e-3, atol=1e-3)
+
+
+def test_yolov3_neck_vs_executed_reference():
+    """YOLOV3Neck (detection blocks, transitions, upsample + concat, fused head) against the executed reference forward.  The
+    device path keeps bf16 carriers between the 19 convs, the reference fp32: compared (a) tightly against the oracle with the
+    same bf16 rounding points, (b) loosely against the fp32 golden."""
+    import viddet_b200
+    from oracle import ref_block, ref_head
+    from tests.test_oracle_ref_exec import neck_params
+    from tests.util import bf16_round
+    C, B, _ = [int(v) for v in G["neck_meta"]]
+    blocks, transitions, preds = neck_params()
+    feats = [G["neck_feat%d" % i] for i in range(3)]
+    neck = viddet_b200.YOLOV3Neck(C, channels=(128, 128, 128), stage_channels=(64, 128, 192))
+    for blk, cells in zip(neck.yolo_blocks, blocks):
+        for cell, p in zip(blk.cells(), cells):
+            cell.set_data(torch.from_numpy(p["weight"]), p["gamma"], p["beta"], p["mean"], p["var"])
+    for cell, p in zip(neck.transitions, transitions):
+        cell.set_data(torch.from_numpy(p["weight"]), p["gamma"], p["beta"], p["mean"], p["var"])
+    for o, (w, b) in zip(neck.yolo_outputs, preds):
+        o.prediction.set_data(torch.from_numpy(w), torch.from_numpy(b))
+    routes = [cuda(f) for f in feats]
+    # glue kernel alone: exact
+    up = viddet_b200.upsample_concat(cuda(feats[2]), cuda(feats[1])).float().cpu().numpy()
+    np.testing.assert_array_equal(up, ref_block.upsample_concat(feats[2], feats[1]))
+    odd = viddet_b200.upsample_concat(cuda(feats[2][:, :64, :3, :3]), cuda(feats[1][:, :, :5, :5])).float().cpu().numpy()   # cropped (slice_like)
+    np.testing.assert_array_equal(odd, ref_block.upsample_concat(feats[2][:, :64, :3, :3], feats[1][:, :, :5, :5]))
+    det = neck.detections(routes).cpu().numpy()
+    tips = ref_block.yolo3_neck_tips(feats, blocks, transitions, round_fn=bf16_round)
+    ref = ref_head.head_detections(tips, [p[0] for p in preds], [p[1] for p in preds], C)
+    assert det.shape == ref.shape == G["neck_det"].shape
+    np.testing.assert_array_equal(det[..., 0], ref[..., 0])
+    # 19 convs with bf16 carriers: a rounding-boundary flip in one layer propagates; worst element 5e-2, average 2e-3
+    assert np.abs(det[..., 1] - ref[..., 1]).max() <= 5e-2 * ref[..., 1].max()
+    assert np.abs(det[..., 1] - ref[..., 1]).mean() <= 2e-3 * ref[..., 1].max()
+    gold = G["neck_det"]
+    assert np.abs(det[..., 1] - gold[..., 1]).max() <= 8e-2 * gold[..., 1].max()
+    assert np.abs(det[..., 1] - gold[..., 1]).mean() <= 5e-3 * gold[..., 1].max()
+    ids, scores, boxes = neck(routes)
+    assert ids.shape == G["neck_ids"].shape
+    # the top detections agree with the reference's wherever the score gap exceeds the bf16 noise
+    gs, s = G["neck_scores"][..., 0], scores.cpu().numpy()[..., 0]
+    np.testing.assert_allclose(s[:, :10], gs[:, :10], rtol=5e-2)

@@ -80,3 +80,46 @@ def test_time_distributed_and_pooling_match_executed_reference():
     np.testing.assert_allclose(out, G["td_out"], rtol=1e-5, atol=2e-4)
     np.testing.assert_array_equal(ref_temporal.temporal_pooling(x, "max"), G["pool_max"])
     np.testing.assert_allclose(ref_temporal.temporal_pooling(x, "mean"), G["pool_mean"], rtol=1e-6, atol=1e-7)
+
+
+def neck_params():
+    """Layer parameters of the executed YOLOV3 in execution order -> (blocks, transitions, prediction convs)."""
+    from tests.util import replay_shim_params
+    ps = replay_shim_params(77, G["neck_param_kinds"], G["neck_param_shapes"], G["neck_param_bias"])
+    it = iter(ps)
+
+    def cell():
+        c, b = next(it), next(it)
+        assert c[0] == "conv" and b[0] == "bn" and c[2] is None
+        return dict(weight=c[1], gamma=b[1], beta=b[2], mean=b[3], var=b[4])
+    blocks, transitions, preds = [], [], []
+    for i in range(3):                       # yolo3.py:496-519: block i, output i, then transition i
+        blocks.append([cell() for _ in range(6)])
+        p = next(it)
+        assert p[0] == "conv" and p[2] is not None
+        preds.append((p[1], p[2]))
+        if i < 2:
+            transitions.append(cell())
+    assert next(it, None) is None
+    return blocks, transitions, preds
+
+
+def test_yolov3_forward_after_stages_matches_executed_reference():
+    """YOLOV3.hybrid_forward (inference) executed from the reference source: detection blocks, transitions, x2 upsample +
+    concat order, reversed routes, per-scale outputs, concat, box_nms parameters and the post_nms slice."""
+    from oracle import ref_block, ref_nms
+    C, B, _ = [int(v) for v in G["neck_meta"]]
+    blocks, transitions, preds = neck_params()
+    feats = [G["neck_feat%d" % i] for i in range(3)]
+    tips = ref_block.yolo3_neck_tips(feats, blocks, transitions)
+    assert [t.shape[1] for t in tips] == [256, 256, 256] and [t.shape[-1] for t in tips] == [4, 8, 16]
+    det = ref_head.head_detections(tips, [p[0] for p in preds], [p[1] for p in preds], C)
+    gold = G["neck_det"]
+    assert det.shape == gold.shape
+    np.testing.assert_array_equal(det[..., 0], gold[..., 0])
+    np.testing.assert_allclose(det[..., 1], gold[..., 1], rtol=2e-4, atol=1e-6)
+    np.testing.assert_allclose(det[..., 2:], gold[..., 2:], rtol=2e-4, atol=2e-3)
+    out = ref_nms.box_nms(gold, overlap_thresh=0.45, valid_thresh=0.01, topk=400, id_index=0, score_index=1, coord_start=2)[:, :100]
+    np.testing.assert_array_equal(out[..., 0:1], G["neck_ids"])
+    np.testing.assert_array_equal(out[..., 1:2], G["neck_scores"])
+    np.testing.assert_array_equal(out[..., 2:], G["neck_bboxes"])

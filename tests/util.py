@@ -75,3 +75,23 @@ def make_gt(rng, B, M, size=416, num_class=20, multi_hot=False, min_count=0):
         else:
             ids[b, :n, 0] = rng.randint(0, num_class, size=n)
     return gt, ids
+
+
+def replay_shim_params(seed, kinds, shapes, has_bias):
+    """Re-draws the layer parameters scripts/mx_shim.py drew (same RandomState stream, same expressions, same order) when the
+    reference's YOLOV3.hybrid_forward was executed for tests/golden/ref_exec_golden.npz.  Returns a list of
+    ('conv', weight, bias_or_None) / ('bn', gamma, beta, mean, var)."""
+    rng = np.random.RandomState(seed)
+    out = []
+    for kind, shp, hb in zip(kinds, shapes, has_bias):
+        if int(kind) == 0:
+            shp = tuple(int(v) for v in shp)
+            fan = shp[1] * shp[2] * shp[3]
+            w = bf16_round((rng.standard_normal(shp) * np.sqrt(2.0 / fan)).astype(np.float32))
+            b = rng.uniform(-0.2, 0.2, shp[0]).astype(np.float32) if int(hb) else None
+            out.append(("conv", w, b))
+        else:
+            c = int(shp[0])
+            out.append(("bn", rng.uniform(0.5, 1.5, c).astype(np.float32), rng.uniform(-0.2, 0.2, c).astype(np.float32),
+                        rng.uniform(-0.2, 0.2, c).astype(np.float32), rng.uniform(0.5, 1.5, c).astype(np.float32)))
+    return out

@@ -65,6 +65,7 @@ SIGNATURES = {
     "vd_head_detections": (_i, [ctypes.POINTER(VdHeadParams), _vp, _vp, _sz, _vp]),
     "vd_temporal_conv": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _f, _vp]),
     "vd_conv_bn_lrelu": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _f, _vp]),
+    "vd_upsample_concat": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "vd_conv_tile_box": (_i, [_i, _i, _i, _ip, _ip, _ip]),
     "vd_temporal_pool": (_i, [_vp, _vp, _i, _i, _i64, _i, _vp]),
     "vd_prefetch_targets": (_i, [_i, _i, _i, _i, _i, _ip, _fp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),

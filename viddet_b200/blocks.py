@@ -13,6 +13,7 @@ TemporalPooling              (layers.py:161-205)              TemporalPooling
 Conv('21') temporal cell     (layers.py:82-89)                TemporalTipConv
 _conv2d / _conv3d cells      (layers.py:63-79)                ConvBNLReLU
 YOLODetectionBlockV3         (yolo3_temporal.py:184-239)      YOLODetectionBlockV3
+YOLOV3.hybrid_forward after the stages (yolo3.py:496-534)     YOLOV3Neck, upsample_concat
 YOLOV3 / YOLOV3Temporal tail (yolo3.py:496,522-556;           YOLOV3Head
                               yolo3_temporal.py:468,542-555)
 YOLOV3PrefetchTargetGenerator(yolo_target.py:13-148)          YOLOV3PrefetchTargetGenerator
@@ -863,6 +864,74 @@ class YOLOV3Loss:
 # ------------------------------------------------------------------------------------------------
 # post-processing of detect()
 # ------------------------------------------------------------------------------------------------
+def upsample_concat(x, route):
+    """yolo3.py:515-519: concat(slice_like(_upsample(x, 2), route, axes=(2,3)), route, dim=1) on channels-last bf16 carriers."""
+    _require_cuda(x, "x"); _require_cuda(route, "route")
+    xb, rb = to_nhwc_bf16(x), to_nhwc_bf16(route)
+    B, C1, H, W = xb.shape
+    B2, C2, H2, W2 = rb.shape
+    assert B == B2, "batch mismatch"
+    out = torch.empty((B, C1 + C2, H2, W2), dtype=torch.bfloat16, device=xb.device, memory_format=torch.channels_last)
+    check(load().vd_upsample_concat(ptr(xb), ptr(rb), ptr(out), B, H, W, C1, H2, W2, C2, stream_ptr()))
+    return out
+
+
+class YOLOV3Neck:
+    """Everything `YOLOV3.hybrid_forward` does after the backbone stages (yolo3.py:496-534, inference): per scale, from deep to
+    shallow, YOLODetectionBlockV3 -> (route, tip); the tip goes to the output layer, the route through the transition
+    `_conv2d(channel, 1, 0, 1)` (yolo3.py:425-427), x2 upsample and concat in front of the next backbone route; then the fused
+    head tail (decode, concat, box_nms, slice).  `routes` = backbone stage outputs in the reference's stage order
+    (shallow -> deep: s8, s16, s32), NCHW logical layout.  Same constructor vocabulary as YOLOV3 (classes, channels in output
+    order, nms parameters); Gluon infers the input channels lazily, here `stage_channels` (shallow -> deep) states them."""
+
+    def __init__(self, classes, channels=(512, 256, 128), stage_channels=(256, 512, 1024), anchors=None, strides=None,
+                 nms_thresh=0.45, nms_topk=400, post_nms=100):
+        n = len(channels)
+        assert len(stage_channels) == n
+        self.channels = list(channels)
+        deep_first = list(stage_channels)[::-1]
+        self.yolo_blocks, self.transitions = [], []
+        for i, ch in enumerate(self.channels):
+            cin = deep_first[i] if i == 0 else self.channels[i] + deep_first[i]      # transition i-1 emits channels[i] (yolo3.py:425-427)
+            self.yolo_blocks.append(YOLODetectionBlockV3(ch, "2", in_channels=cin))
+            if i > 0:
+                self.transitions.append(ConvBNLReLU(self.channels[i - 1], ch, (1, 1, 1)))
+        self.head = YOLOV3Head(classes, anchors=anchors, strides=strides, channels=[2 * c for c in self.channels],
+                               nms_thresh=nms_thresh, nms_topk=nms_topk, post_nms=post_nms)
+        self.yolo_outputs = self.head.yolo_outputs
+
+    def initialize(self, scale=0.07, generator=None):
+        for b in self.yolo_blocks:
+            b.initialize(scale, generator)
+        for t in self.transitions:
+            t.initialize(scale, generator)
+        self.head.initialize(generator=generator)
+        return self
+
+    def set_nms(self, nms_thresh=0.45, nms_topk=400, post_nms=100):
+        self.head.set_nms(nms_thresh, nms_topk, post_nms)
+
+    def tips(self, routes):
+        """The three tips (deep -> shallow), channels-last bf16."""
+        routes = list(routes)[::-1]                                   # yolo3.py:518 `routes[::-1]`
+        x, tips = routes[0], []
+        for i, block in enumerate(self.yolo_blocks):
+            x, tip = block(x)
+            tips.append(tip)
+            if i >= len(routes) - 1:
+                break
+            x = self.transitions[i](x)
+            x = upsample_concat(x, routes[i + 1])
+        return tips
+
+    def __call__(self, routes):
+        return self.head(self.tips(routes))
+
+    def detections(self, routes):
+        """The (B, rows, 6) tensor `concat(all_detections)` holds at yolo3.py:523."""
+        return self.head.detections(self.tips(routes))
+
+
 def postprocess_detections(ids, scores, bboxes, size):
     """detect_yolo3.py:222-261 on device: clip boxes to [0, size], keep rows with id >= 0 (order preserved), divide the
     boxes by size.  ids/scores (..., post, 1), bboxes (..., post, 4) -> rows (F, post, 6) [id, score, x1, y1, x2, y2]

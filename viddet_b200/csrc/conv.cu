@@ -288,3 +288,47 @@ extern "C" int vd_conv_bn_lrelu(const void* x, void* y, int B, int T, int H, int
     if (NT == 256) return launch_conv<256>(maps, p, (cudaStream_t)stream_);
     return launch_conv<128>(maps, p, (cudaStream_t)stream_);
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// vd_upsample_concat -- the glue between two detection blocks of YOLOV3.hybrid_forward (yolo3.py:515-519):
+//   upsample = _upsample(x, stride=2)                       nearest, out[y, x] = in[y / 2, x / 2]   (layers.py:10-20)
+//   x = concat(slice_like(upsample, route_now, axes=(2,3)), route_now, dim=1)
+// on channels-last bf16: out (B, H2, W2, C1 + C2), channels [0, C1) = upsampled x cropped to (H2, W2), [C1, C1+C2) = route.
+// One 16-byte chunk (8 channels) per thread: pure HBM streaming (the upsample reads hit L2 three times out of four).
+// ---------------------------------------------------------------------------------------------------------------
+namespace vd {
+__global__ void __launch_bounds__(256)
+upsample_concat_kernel(const uint4* __restrict__ x, const uint4* __restrict__ route, uint4* __restrict__ out,
+                       long long total, int H, int W, int c1v, int H2, int W2, int c2v) {
+    const int cv = c1v + c2v;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % cv);
+        long long pix = i / cv;
+        const int xx = (int)(pix % W2); pix /= W2;
+        const int yy = (int)(pix % H2);
+        const long long b = pix / H2;
+        uint4 v;
+        if (c < c1v) v = __ldg(x + ((b * H + (yy >> 1)) * W + (xx >> 1)) * c1v + c);
+        else v = __ldg(route + ((b * H2 + yy) * W2 + xx) * c2v + (c - c1v));
+        out[i] = v;
+    }
+}
+}  // namespace vd
+
+extern "C" int vd_upsample_concat(const void* x, const void* route, void* out, int B, int H, int W, int C1,
+                                  int H2, int W2, int C2, void* stream_) {
+    VD_CHECK_ARG(x && route && out, "upsample_concat: null pointer");
+    VD_CHECK_ARG(B >= 0 && H > 0 && W > 0 && H2 > 0 && W2 > 0, "upsample_concat: bad shape");
+    VD_CHECK_ARG(H2 <= 2 * H && W2 <= 2 * W, "upsample_concat: the route map (%d x %d) is larger than the upsampled one (%d x %d)", H2, W2, 2 * H, 2 * W);
+    VD_CHECK_ARG(C1 > 0 && C2 > 0 && C1 % 8 == 0 && C2 % 8 == 0, "upsample_concat: channel counts (%d, %d) must be multiples of 8", C1, C2);
+    VD_CHECK_ARG(((uintptr_t)x & 15) == 0 && ((uintptr_t)route & 15) == 0 && ((uintptr_t)out & 15) == 0, "upsample_concat: tensors must be 16-byte aligned");
+    if (B == 0) return VD_OK;
+    const long long total = (long long)B * H2 * W2 * ((C1 + C2) / 8);
+    long long blocks = (total + 255) / 256;
+    const long long cap = (long long)sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    vd::upsample_concat_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream_>>>((const uint4*)x, (const uint4*)route, (uint4*)out, total,
+                                                                                    H, W, C1 / 8, H2, W2, C2 / 8);
+    VD_LAUNCH_CHECK();
+    return VD_OK;
+}

@@ -8,7 +8,7 @@ import ctypes
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(HERE, "libviddet_b200.so")
+SO_PATH = os.environ.get("VD_LIB") or os.path.join(HERE, "libviddet_b200.so")     # VD_LIB: tuning variants (build.py --variant)
 
 VD_MAX_SCALES = 3
 VD_MAX_TOPK = 1024

@@ -35,6 +35,29 @@ def _digest():
     return h.hexdigest()
 
 
+def build_variant(tag: str, extra_flags) -> str:
+    """Tuning aid: the same sources with extra -D flags -> viddet_b200/variants/libviddet_b200_<tag>.so (git-ignored); select it at
+    run time with VD_LIB=<path>.  The product library is always the default build()."""
+    vdir = os.path.join(HERE, "variants")
+    odir = os.path.join(OBJ, "variant_" + tag)
+    os.makedirs(vdir, exist_ok=True); os.makedirs(odir, exist_ok=True)
+    out = os.path.join(vdir, "libviddet_b200_%s.so" % tag)
+
+    def one(src):
+        obj = os.path.join(odir, src[:-3] + ".o")
+        r = subprocess.run([NVCC] + FLAGS + list(extra_flags) + ["-c", os.path.join(CSRC, src), "-o", obj], capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("nvcc failed for %s:\n%s" % (src, r.stdout + r.stderr))
+        open(os.path.join(odir, src[:-3] + ".ptxas.log"), "w").write(r.stdout + r.stderr)
+        return obj
+    with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
+        objs = list(ex.map(one, sources()))
+    r = subprocess.run([NVCC, "-shared", "-o", out] + objs + ["-lcudart"], capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("link failed:\n" + r.stdout + r.stderr)
+    return out
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(OBJ, exist_ok=True)
     stamp = os.path.join(OBJ, "digest.txt")
@@ -69,4 +92,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    if len(sys.argv) > 2 and sys.argv[1] == "--variant":
+        print(build_variant(sys.argv[2], sys.argv[3:]))
+    else:
+        print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))

@@ -122,7 +122,10 @@ template <int EPI, int C, int NPAD> struct HeadCfg {
     static constexpr int LIST_BYTES = (EPI == EPI_SPEC) ? G * SPLIT * 4 * 2 * kSpecStage * 8 : G * LIST_BUFS * kListCap * 8;
     static constexpr int EPI_BYTES = LIST_BYTES + CBIAS_BYTES + CONF_BYTES + VD_MAX_SCALES * NPAD * 4 + kHeadSharedBytes;
     // EPI_FILTER leaves ~45 KB of the SM's shared memory to a co-resident nms_final_hist_kernel CTA of the previous batch
-    static constexpr int SMEM_BUDGET = ((EPI == EPI_FILTER || EPI == EPI_SPEC) ? 181 : 225) * 1024;
+    #ifndef VD_SPEC_SMEM_KB
+#define VD_SPEC_SMEM_KB 181
+#endif
+    static constexpr int SMEM_BUDGET = ((EPI == EPI_SPEC) ? VD_SPEC_SMEM_KB : ((EPI == EPI_FILTER) ? 181 : 225)) * 1024;
     static constexpr int STAGES_RAW = (SMEM_BUDGET - EPI_BYTES - 1024) / STAGE_BYTES;
     static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
     static constexpr int TMEM_COLS = (G * TMEM_STRIDE) <= 256 ? 256 : 512;
@@ -415,7 +418,7 @@ head_kernel(const __grid_constant__ HeadMaps maps, const __grid_constant__ HeadK
             if (stamp) p.stamps[it * 16 + 4] = clock64();
             const uint32_t tbase = tmem_base + buf * Cfg::TMEM_STRIDE + lane_addr;
 
-            if constexpr (EPI == EPI_FILTER) {
+            if constexpr (EPI == EPI_FILTER || EPI == EPI_SPEC) {
                 if (p.dbg == 1) {        // debug (VD_DEBUG_SKIP_EPILOGUE=1): mainloop only, accumulators dropped
                     tc::fence_before_sync();
                     __syncwarp();
@@ -459,7 +462,7 @@ head_kernel(const __grid_constant__ HeadMaps maps, const __grid_constant__ HeadK
                     // the raw (tx,ty,tw,th) are stored; only the <= topk boxes that reach the NMS kernel are decoded there
                     // (same vd_decode_box, same bits) instead of all 3*HW of them here
                     if (!inb) conf[a] = __uint_as_float(0x7fc00000u);   // NaN: no score of a padding pixel passes `> valid_thresh`
-                    if (inb && half == 0) p.boxes[(size_t)f * p.g.anc_base[p.g.num_scales] + p.g.anc_base[s] + cell * 3 + a] = make_float4(tx, ty, tw, th);
+                    if (inb && half == 0 && p.dbg != 8) p.boxes[(size_t)f * p.g.anc_base[p.g.num_scales] + p.g.anc_base[s] + cell * 3 + a] = make_float4(tx, ty, tw, th);
                     (void)bx; (void)gx; (void)gy;
                 } else {   // EPI_DET: class rows of this (cell, anchor)
                     bx = vd_decode_box(tx, ty, tw, th, gx, gy, p.g.stride[s], p.g.anchors[s][2 * a], p.g.anchors[s][2 * a + 1]);
@@ -501,7 +504,8 @@ head_kernel(const __grid_constant__ HeadMaps maps, const __grid_constant__ HeadK
                 // exact top-k); frames that fail are redone by the exact EPI_FILTER path.  Same conservative logit
                 // prefilter as there: x >= logit(tau/conf) - margin  <=  score >= tau.
                 constexpr int CH = Cfg::CH, CPA = Cfg::CPA, CH4 = Cfg::CH4, REM = C - (CPA - 1) * CH;
-                const float vth = p.valid_thresh;
+                if (p.dbg == 7) { tc::fence_before_sync(); __syncwarp(); if (lane == 0) tc::mbar_arrive(&sh->tmem_empty[buf]); continue; }   // debug: box part only
+                const float vth = p.dbg == 9 ? 2.0f : p.valid_thresh;                 // debug 9: nothing is ever emitted
                 const float* cbias = scbias + s * (3 * CPA * CH4);
                 float ell[3];
                 {

@@ -4,7 +4,7 @@
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,memory.total --format=csv > gpurun_out/gpu_info.csv 2>&1
 files="$@"
-if [ -z "$files" ]; then files="tests/test_gpu_nms.py tests/test_gpu_decode.py tests/test_gpu_targets.py tests/test_gpu_train.py tests/test_gpu_block.py tests/test_gpu_ref_exec.py tests/test_gpu_head.py"; fi
+if [ -z "$files" ]; then files="tests/test_gpu_nms.py tests/test_gpu_decode.py tests/test_gpu_targets.py tests/test_gpu_train.py tests/test_gpu_block.py tests/test_gpu_ref_exec.py tests/test_gpu_edges.py tests/test_gpu_head.py"; fi
 rc_all=0
 for f in $files; do
   name=$(basename $f .py)

@@ -246,13 +246,13 @@ extern "C" int vd_conv_tile_box(int H, int W, int F, int* BW, int* BH, int* BF) 
 extern "C" int vd_conv_bn_lrelu(const void* x, void* y, int B, int T, int H, int W, int Cin, int Cout,
                                 int kt, int kh, int kw, const void* weight, const float* scale, const float* shift,
                                 float slope, void* stream_) {
-    VD_CHECK_ARG(x && y && weight && scale && shift, "conv_bn_lrelu: null pointer");
+    VD_CHECK_ARG(weight && scale && shift && (B == 0 || (x && y)), "conv_bn_lrelu: null pointer");
     VD_CHECK_ARG(B >= 0 && T >= 1 && H > 0 && W > 0, "conv_bn_lrelu: bad shape");
     VD_CHECK_ARG((kt == 1 || kt == 3) && (kh == 1 || kh == 3) && (kw == 1 || kw == 3),
                  "conv_bn_lrelu: kernel (%d,%d,%d): every extent must be 1 or 3 ('same' padding, stride 1)", kt, kh, kw);
     VD_CHECK_ARG(Cin >= 64 && Cin % 64 == 0, "conv_bn_lrelu: Cin = %d must be a multiple of 64", Cin);
     VD_CHECK_ARG(Cout >= 128 && Cout % 128 == 0 && Cout <= 1024, "conv_bn_lrelu: Cout = %d must be a multiple of 128, at most 1024", Cout);
-    VD_CHECK_ARG(((uintptr_t)x & 15) == 0 && ((uintptr_t)y & 15) == 0 && ((uintptr_t)weight & 15) == 0, "conv_bn_lrelu: tensors must be 16-byte aligned");
+    VD_CHECK_ARG(((uintptr_t)x & 15) == 0 && ((uintptr_t)y & 15) == 0 && ((uintptr_t)weight & 15) == 0, "conv_bn_lrelu: tensors must be 16-byte aligned");   // (an empty batch may pass null x / y)
     if (B == 0) return VD_OK;
     const int NT = (Cout % 256 == 0) ? 256 : 128;
     ConvParams p;
@@ -317,7 +317,7 @@ upsample_concat_kernel(const uint4* __restrict__ x, const uint4* __restrict__ ro
 
 extern "C" int vd_upsample_concat(const void* x, const void* route, void* out, int B, int H, int W, int C1,
                                   int H2, int W2, int C2, void* stream_) {
-    VD_CHECK_ARG(x && route && out, "upsample_concat: null pointer");
+    VD_CHECK_ARG(B == 0 || (x && route && out), "upsample_concat: null pointer");
     VD_CHECK_ARG(B >= 0 && H > 0 && W > 0 && H2 > 0 && W2 > 0, "upsample_concat: bad shape");
     VD_CHECK_ARG(H2 <= 2 * H && W2 <= 2 * W, "upsample_concat: the route map (%d x %d) is larger than the upsampled one (%d x %d)", H2, W2, 2 * H, 2 * W);
     VD_CHECK_ARG(C1 > 0 && C2 > 0 && C1 % 8 == 0 && C2 % 8 == 0, "upsample_concat: channel counts (%d, %d) must be multiples of 8", C1, C2);

@@ -103,13 +103,13 @@ extern "C" int vd_yolo_decode(const float* pred, int B, int H, int W, int num_cl
                               float* det, int64_t det_rows_total, int64_t det_row_offset,
                               float* raw_centers, float* raw_scales, float* objness, float* class_pred,
                               void* stream) {
-    VD_CHECK_ARG(pred && det && anchors_host, "yolo_decode: null pointer");
+    VD_CHECK_ARG(anchors_host && (B == 0 || (pred && det)), "yolo_decode: null pointer");
     VD_CHECK_ARG(B >= 0 && H > 0 && W > 0 && num_class > 0, "yolo_decode: bad shape");
     VD_CHECK_ARG(H <= 128 && W <= 128, "yolo_decode: feature map %dx%d exceeds alloc_size (128,128) (yolo3.py:44)", H, W);
     VD_CHECK_ARG(num_anchors >= 1 && num_anchors <= 6, "yolo_decode: num_anchors %d not in 1..6", num_anchors);
     VD_CHECK_ARG(mode >= 0 && mode <= 2, "yolo_decode: bad mode %d", mode);
     VD_CHECK_ARG(B <= 65535, "yolo_decode: batch > 65535");
-    if (mode == VD_MODE_TRAIN) VD_CHECK_ARG(raw_centers && raw_scales && objness && class_pred, "yolo_decode: train mode needs the four raw outputs");
+    if (mode == VD_MODE_TRAIN && B > 0) VD_CHECK_ARG(raw_centers && raw_scales && objness && class_pred, "yolo_decode: train mode needs the four raw outputs");
     if (B == 0) return VD_OK;
     DecodeArgs a;
     a.pred = pred; a.B = B; a.H = H; a.W = W; a.C = num_class; a.A = num_anchors; a.stride = stride; a.mode = mode;
@@ -123,7 +123,7 @@ extern "C" int vd_yolo_decode(const float* pred, int B, int H, int W, int num_cl
 }
 
 extern "C" int vd_repack_nchw_f32_to_nhwc_bf16(const float* src, void* dst, int B, int C, int H, int W, void* stream) {
-    VD_CHECK_ARG(src && dst && B >= 0 && C > 0 && H > 0 && W > 0, "repack: bad argument");
+    VD_CHECK_ARG((B == 0 || (src && dst)) && B >= 0 && C > 0 && H > 0 && W > 0, "repack: bad argument");
     VD_CHECK_ARG(B <= 65535, "repack: batch > 65535");
     if (B == 0) return VD_OK;
     int HW = H * W;
@@ -134,7 +134,7 @@ extern "C" int vd_repack_nchw_f32_to_nhwc_bf16(const float* src, void* dst, int 
 }
 
 extern "C" int vd_temporal_pool(const void* x, void* y, int B, int K, int64_t inner, int mode, void* stream) {
-    VD_CHECK_ARG(x && y && B >= 0 && K >= 1 && inner > 0, "temporal_pool: bad argument");
+    VD_CHECK_ARG((B == 0 || (x && y)) && B >= 0 && K >= 1 && inner > 0, "temporal_pool: bad argument");
     VD_CHECK_ARG(mode == VD_JOIN_MAX || mode == VD_JOIN_MEAN, "temporal_pool: mode must be VD_JOIN_MAX or VD_JOIN_MEAN");
     VD_CHECK_ARG(B <= 65535, "temporal_pool: batch > 65535");
     if (B == 0) return VD_OK;
@@ -181,7 +181,7 @@ postprocess_kernel(const float* __restrict__ ids, const float* __restrict__ scor
 extern "C" int vd_postprocess_detections(const float* ids, const float* scores, const float* bboxes, int frames, int post,
                                          float size, float* rows, int32_t* counts, void* stream_) {
     VD_CHECK_ARG(frames >= 0 && post > 0, "postprocess: bad shape frames=%d post=%d", frames, post);
-    VD_CHECK_ARG(ids && scores && bboxes && rows && counts, "postprocess: null pointer");
+    VD_CHECK_ARG(frames == 0 || (ids && scores && bboxes && rows && counts), "postprocess: null pointer");
     VD_CHECK_ARG(((uintptr_t)bboxes & 15) == 0, "postprocess: bboxes must be 16-byte aligned");
     VD_CHECK_ARG(size > 0.0f, "postprocess: image size must be positive");
     if (frames == 0) return VD_OK;
@@ -293,9 +293,9 @@ extern "C" int vd_hierarchical_nms(const float* rows, const int32_t* counts, int
                                    float* out_rows, int32_t* out_counts, void* stream_) {
     VD_CHECK_ARG(frames >= 0 && post > 0 && num_class > 0, "hierarchical_nms: bad shape frames=%d post=%d classes=%d", frames, post, num_class);
     if (post > vd::kHierMaxPost) return vd::set_error(VD_ERR_UNSUPPORTED, "hierarchical_nms: post = %d rows per image, at most %d", post, vd::kHierMaxPost);
-    VD_CHECK_ARG(rows && counts && levels && parent && branch && out_rows && out_counts, "hierarchical_nms: null pointer");
+    VD_CHECK_ARG(levels && parent && branch && (frames == 0 || (rows && counts && out_rows && out_counts)), "hierarchical_nms: null pointer");
     VD_CHECK_ARG(arith == 0 || arith == 1, "hierarchical_nms: arith must be 0 (float64) or 1 (legacy float32 scalars)");
-    VD_CHECK_ARG(rows != out_rows, "hierarchical_nms: in-place operation is not supported");
+    VD_CHECK_ARG(frames == 0 || rows != out_rows, "hierarchical_nms: in-place operation is not supported");
     if (frames == 0) return VD_OK;
     if (level_thresh < 0) level_thresh = 0;                                  // detect_yolo3.py:749
     const int grid = vd::ceil_div(frames, vd::kHierWarps);

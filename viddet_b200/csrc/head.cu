@@ -1416,7 +1416,7 @@ static int make_plan(const VdHeadParams* hp, HeadPlan* pl) {
         const VdHeadScale& sc = hp->scale[s];
         VD_CHECK_ARG(sc.H > 0 && sc.W > 0 && sc.H <= 128 && sc.W <= 128, "head: scale %d feature map %dx%d (alloc_size is 128x128, yolo3.py:44)", s, sc.H, sc.W);
         VD_CHECK_ARG(sc.Cin > 0 && sc.Cin % BLOCK_K == 0, "head: scale %d Cin %d must be a multiple of %d", s, sc.Cin, BLOCK_K);
-        VD_CHECK_ARG(sc.tip_nhwc_bf16 && sc.weight_bf16, "head: scale %d null tip/weight", s);
+        VD_CHECK_ARG((sc.tip_nhwc_bf16 || hp->frames == 0) && sc.weight_bf16, "head: scale %d null tip/weight", s);     // an empty batch has no tip storage
         VD_CHECK_ARG(((uintptr_t)sc.tip_nhwc_bf16 & 15) == 0 && ((uintptr_t)sc.weight_bf16 & 15) == 0, "head: scale %d tensors must be 16-byte aligned", s);
         k.g.H[s] = sc.H; k.g.W[s] = sc.W; k.g.HW[s] = sc.H * sc.W;
         k.g.stride[s] = sc.stride;
@@ -1588,14 +1588,14 @@ extern "C" int vd_head_forward_stages(const VdHeadParams* hp, float* ids, float*
     HeadPlan pl;
     int rc = make_plan(hp, &pl);
     if (rc) return rc;
-    VD_CHECK_ARG(ids && scores && bboxes, "head_forward: null output");
+    VD_CHECK_ARG(hp->frames == 0 || (ids && scores && bboxes), "head_forward: null output");
     VD_CHECK_ARG(hp->nms_thresh > 0.f && hp->nms_thresh < 1.f,
                  "head_forward: nms_thresh %g disables NMS (yolo3.py:525); use vd_head_detections for the raw rows", hp->nms_thresh);
     VD_CHECK_ARG(hp->post_nms > 0, "head_forward: post_nms must be > 0 (use vd_head_detections + vd_box_nms for the unsliced output)");
     const long long rows = pl.kp.g.row_base[hp->num_scales];
     long long k64 = (hp->nms_topk > 0 && hp->nms_topk < rows) ? hp->nms_topk : rows;
     if (k64 > VD_MAX_TOPK) return set_error(VD_ERR_UNSUPPORTED, "head_forward: nms_topk %lld > VD_MAX_TOPK %d", k64, VD_MAX_TOPK);
-    if (!workspace || workspace_bytes < pl.total) return set_error(VD_ERR_WORKSPACE, "head_forward: workspace %zu < required %zu", workspace_bytes, pl.total);
+    if (hp->frames > 0 && (!workspace || workspace_bytes < pl.total)) return set_error(VD_ERR_WORKSPACE, "head_forward: workspace %zu < required %zu", workspace_bytes, pl.total);
     VD_CHECK_ARG(((uintptr_t)bboxes & 15) == 0, "head_forward: bboxes must be 16-byte aligned");
     if (hp->frames == 0) return VD_OK;
     const int k = (int)k64;
@@ -1688,7 +1688,7 @@ extern "C" int vd_head_detections(const VdHeadParams* hp, float* det, void* work
     HeadPlan pl;
     int rc = make_plan(hp, &pl);
     if (rc) return rc;
-    VD_CHECK_ARG(det, "head_detections: null output");
+    VD_CHECK_ARG(hp->frames == 0 || det, "head_detections: null output");
     VD_CHECK_ARG(((uintptr_t)det & 7) == 0, "head_detections: det must be 8-byte aligned");
     if (hp->frames == 0) return VD_OK;
     HeadKernelParams& kp = pl.kp;
@@ -1711,7 +1711,7 @@ extern "C" int vd_head_detections(const VdHeadParams* hp, float* det, void* work
 
 extern "C" int vd_pred_conv(const void* x, int B, int H, int W, int Cin, int K_frames, int join,
                             const void* weight, const float* bias, int N, float* pred, void* stream_) {
-    VD_CHECK_ARG(x && weight && pred, "pred_conv: null pointer");
+    VD_CHECK_ARG(weight && (B == 0 || (x && pred)), "pred_conv: null pointer");
     VD_CHECK_ARG(B >= 0 && B <= 65535 && H > 0 && W > 0 && N > 0, "pred_conv: bad shape");
     VD_CHECK_ARG(Cin > 0 && Cin % BLOCK_K == 0, "pred_conv: Cin %d must be a multiple of %d", Cin, BLOCK_K);
     VD_CHECK_ARG(join == VD_JOIN_NONE || join == VD_JOIN_CAT, "pred_conv: join %d must be pre-reduced (vd_temporal_pool)", join);

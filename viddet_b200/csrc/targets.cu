@@ -158,10 +158,10 @@ extern "C" int vd_prefetch_targets(int B, int M, int C, int orig_h, int orig_w, 
     cudaStream_t stream = (cudaStream_t)stream_;
     VD_CHECK_ARG(B >= 0 && M >= 0 && C > 0 && orig_h > 0 && orig_w > 0, "prefetch_targets: bad shape");
     VD_CHECK_ARG(hw_host && anchors_host, "prefetch_targets: null hw/anchors");
-    VD_CHECK_ARG(objectness && center && scale && weight && cls, "prefetch_targets: null output");
+    VD_CHECK_ARG(B == 0 || (objectness && center && scale && weight && cls), "prefetch_targets: null output");
     VD_CHECK_ARG(ids_width == 1 || ids_width == C, "prefetch_targets: gt_ids last dim must be 1 or num_class (%d), got %d", C, ids_width);
     VD_CHECK_ARG(M <= kTgtMaxM, "prefetch_targets: M %d > %d", M, kTgtMaxM);
-    VD_CHECK_ARG(M == 0 || (gt_boxes && gt_ids), "prefetch_targets: null gt tensors");
+    VD_CHECK_ARG(B == 0 || M == 0 || (gt_boxes && gt_ids), "prefetch_targets: null gt tensors");
     VD_CHECK_ARG(((uintptr_t)gt_boxes & 15) == 0, "prefetch_targets: gt_boxes must be 16-byte aligned");
     if (B == 0) return VD_OK;
     TargetArgs a;

@@ -201,7 +201,7 @@ using namespace vd;
 extern "C" int vd_temporal_conv(const void* x, void* y, int B, int T, int H, int W, int C,
                                 const void* weight, const float* scale, const float* shift,
                                 float slope, void* stream_) {
-    VD_CHECK_ARG(x && y && weight && scale && shift, "temporal_conv: null pointer");
+    VD_CHECK_ARG(weight && scale && shift && (B == 0 || (x && y)), "temporal_conv: null pointer");
     VD_CHECK_ARG(B >= 0 && T >= 1 && H > 0 && W > 0, "temporal_conv: bad shape");
     VD_CHECK_ARG(C >= 128 && C % 128 == 0 && C <= 1024, "temporal_conv: C = %d must be a multiple of 128, at most 1024", C);
     VD_CHECK_ARG(((uintptr_t)x & 15) == 0 && ((uintptr_t)y & 15) == 0 && ((uintptr_t)weight & 15) == 0, "temporal_conv: tensors must be 16-byte aligned");

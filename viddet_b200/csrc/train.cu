@@ -182,7 +182,7 @@ extern "C" int vd_target_merge(int B, int N, int M, int C, const float* box_pred
                                float* class_mask, void* stream_) {
     VD_CHECK_ARG(B >= 0 && N > 0 && M >= 1 && C >= 1, "target_merge: bad shape B=%d N=%d M=%d C=%d", B, N, M, C);
     VD_CHECK_ARG(M <= kTrainMaxM, "target_merge: M = %d ground-truth boxes per image > %d", M, kTrainMaxM);
-    VD_CHECK_ARG(box_preds && gt_boxes && objectness && center && scale && weights && class_targets && class_mask, "target_merge: null pointer");
+    VD_CHECK_ARG(B == 0 || (box_preds && gt_boxes && objectness && center && scale && weights && class_targets && class_mask), "target_merge: null pointer");
     const bool have = obj_t != nullptr;
     VD_CHECK_ARG(!have || (centers_t && scales_t && weights_t && clas_t), "target_merge: prefetched targets must be given together");
     VD_CHECK_ARG((((uintptr_t)box_preds | (uintptr_t)gt_boxes) & 15) == 0, "target_merge: box tensors must be 16-byte aligned");

@@ -16,6 +16,9 @@ from viddet_b200 import _lib
 
 PEAKS = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")))
 PEAK_TC = float(PEAKS.get("bf16_tflops_sustained", 1413.6))
+NECK = "neck" in sys.argv
+if NECK:
+    sys.argv.remove("neck")
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 64
 T = int(sys.argv[2]) if len(sys.argv) > 2 else 1
 
@@ -97,5 +100,29 @@ def main():
                               "tflops": round(fl / ms / 1e9, 1), "frac_tensor_peak": round(fl / ms / 1e9 / PEAK_TC, 3)}))
 
 
+def neck():
+    """Backbone routes -> detections (YOLOV3.hybrid_forward after the stages) at VOC-416: 19 conv cells + 2 glue kernels + fused head."""
+    g = torch.Generator().manual_seed(1)
+    nk = viddet_b200.YOLOV3Neck(20).initialize(generator=g)
+    routes = [torch.randn(B, c, 416 // s, 416 // s, device="cuda").to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+              for c, s in zip((256, 512, 1024), (8, 16, 32))]
+    for _ in range(3):
+        nk(routes)                                   # steady state of the head's speculative thresholds
+    ms = timeit(lambda i: nk(routes), n=5, warm=2)
+    cells = [c for b in nk.yolo_blocks for c in b.cells()] + list(nk.transitions)
+    hw = {1024: 13, 768: 26, 384: 52}
+    fl = 0.0
+    for blk, h in zip(nk.yolo_blocks, (13, 26, 52)):
+        fl += sum(2.0 * c.kernel[0] * c.kernel[1] * c.kernel[2] * B * h * h * c.in_channels * c.channels for c in blk.cells())
+    fl += 2.0 * B * (13 * 13 * 512 * 256 + 26 * 26 * 256 * 128)                       # transitions
+    fl += 2.0 * B * 75 * (13 * 13 * 1024 + 26 * 26 * 512 + 52 * 52 * 256)             # prediction convs
+    print(json.dumps({"neck": "routes -> detections", "frames": B, "ms": round(ms, 4), "frames_per_s": round(B / ms * 1e3, 1),
+                      "tflops": round(fl / ms / 1e9, 1), "frac_tensor_peak": round(fl / ms / 1e9 / PEAK_TC, 3),
+                      "gflop_per_frame": round(fl / B / 1e9, 2)}))
+
+
 if __name__ == "__main__":
-    main()
+    if NECK:
+        neck()
+    else:
+        main()

@@ -9,19 +9,21 @@
 //   contrib.box_nms + slice + split              yolo3.py:526-534     -> candidate lists -> nms_final
 //   late 'cat' temporal join                     yolo3.py:1134-1136   -> K loop over the K frames
 //
-// Kernel head_kernel<EPI, C>: persistent (one CTA per SM), 192 threads:
-//   warp 0      TMA producer: A tile [128 px x 64 ch] (4-D map: Cin, HW, K, frames; out-of-range
-//               pixels zero-filled) + W tile [NPAD x 64 ch] per stage, mbarrier ring
-//   warp 1      MMA issuer: tcgen05.mma.cta_group::1.kind::f16 M=128 N=NPAD K=16, fp32 accumulators
-//               double-buffered in TMEM, tcgen05.commit -> empty/full barriers
-//   warps 2-5   epilogue: tcgen05.ld of the pixel's logits, decode, then
-//        EPI_FILTER  per-anchor boxes -> box array; class scores -> 32-bit orderable keys in
-//                    registers; streaming exact selection of the tile's top-k (pivot search on
-//                    (score,row) keys, warm-started from the previous tile) -> <=cap candidates
-//                    per tile in the tile's list
+// Kernel head_kernel<EPI, C, NPAD>: persistent (one CTA per SM), 64 + G*SPLIT*128 threads:
+//   warp 0      claims tiles from a global counter (dynamic, largest tiles first) and issues TMA: A tile [128 px x 64 ch]
+//               (4-D map: Cin, HW, K, frames; out-of-range pixels zero-filled) + W tile [NPAD x 64 ch] per stage, mbarrier ring
+//   warp 1      MMA issuer: tcgen05.mma.cta_group::1.kind::f16 M=128 N=NPAD K=16, fp32 accumulators in G TMEM buffers,
+//               tcgen05.commit -> empty/full barriers
+//   warps 2..   epilogue warpgroups (one TMEM lane = one pixel): tcgen05.ld of the pixel's logits, decode, then
+//        EPI_SPEC    (steady state) every candidate that can reach its frame slot's threshold tau (left by the previous call's
+//                    NMS kernel) is scored and appended to the FRAME's list: one compare per class logit, per-warp staging,
+//                    deferred flush, no barriers; nms_spec_kernel verifies each frame (list complete <=> no overflow and
+//                    >= k keys >= tau) and finishes it; frames that fail are redone by the exact pair below, on the device
+//        EPI_FILTER  (exact path: fallback + first call) per-tile exact top-k superset by a pivot search on the logit
+//                    prefilter, frame-level running bound from a coarse histogram -> per-tile lists -> nms_final_hist_kernel
 //        EPI_DET     materialise the reference's (frames, rows, 6) detection rows
 //        EPI_PRED    write the conv output (B, N, H, W) fp32
-// Tiles are ordered scale-major (s32 first: most bytes per tile) and dealt round-robin.
+//   Wide heads (NPAD > 128: two 256-column accumulators) put SPLIT = 2 warpgroups on one accumulator (class chunks interleaved).
 #include <stdlib.h>
 #include <type_traits>
 #include "tc.cuh"

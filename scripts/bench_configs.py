@@ -96,10 +96,15 @@ def vid_temporal(windows=64, T=5, C=30, size=416, nrot=2):
     print(json.dumps({"cfg": "vid416_T5_w%d" % windows, "what": "head_kernel", "ms": t_head,
                       "alg_GBps": hw_c * 2 * T * windows / (t_head * 1e-3) / 1e9}))
     print(json.dumps({"cfg": "vid416_T5_w%d" % windows, "what": "nms_kernel", "ms": t_nms}))
-    print(json.dumps({"cfg": "vid416_T5_w%d" % windows, "what": "step", "ms": t_all, "windows_per_s": windows / (t_all * 1e-3),
-                      "frames_per_s": windows * T / (t_all * 1e-3),
-                      "tflops": (f_tconv + f_pred) / (t_all * 1e-3) / 1e12,
-                      "tensor_frac": (f_tconv + f_pred) / (t_all * 1e-3) / 1e12 / PEAK_TC}))
+    for s_ in sessions:
+        s_.capture()
+    pipe = viddet_b200.HeadPipeline(sessions, rotations=4)
+    t_pipe = timeit(lambda i: pipe.cycle(), n=6, warm=2) / pipe.steps_per_cycle
+    for label, t in (("step", t_all), ("step (pipelined graph: NMS of batch j under the tip cells of batch j+1)", t_pipe)):
+        print(json.dumps({"cfg": "vid416_T5_w%d" % windows, "what": label, "ms": t, "windows_per_s": windows / (t * 1e-3),
+                          "frames_per_s": windows * T / (t * 1e-3),
+                          "tflops": (f_tconv + f_pred) / (t * 1e-3) / 1e12,
+                          "tensor_frac": (f_tconv + f_pred) / (t * 1e-3) / 1e12 / PEAK_TC}))
 
 
 def targets(B=128, M=100, C=285, size=416, multi_hot=True):
@@ -146,7 +151,7 @@ def train_side(B=128, M=100, C=285, size=416):
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["coco", "vid", "targets"]
+    which = sys.argv[1:] or ["coco", "vid", "targets"]      # also: "voc", "vidt" (temporal only)
     print(json.dumps({"peaks": {"hbm_GBps": PEAK_HBM, "bf16_tflops_sustained": PEAK_TC}}))
     if "voc" in which:
         head_cfg("voc416_b64")
@@ -154,6 +159,8 @@ if __name__ == "__main__":
         head_cfg("coco608_b64")
     if "vid" in which:
         head_cfg("vid416_b64")
+        vid_temporal()
+    if "vidt" in which:
         vid_temporal()
     if "targets" in which:
         targets()

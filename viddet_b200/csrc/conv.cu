@@ -15,6 +15,9 @@
 // 1x1x1 convs flatten (B,T,H,W) into one row axis (no padding needed => full 128-row tiles).
 //   warp 0: TMA producer (A box + W_tap tile [NT x 64])          warp 1: MMA issuer (M128 x NT x K16, 2 TMEM accumulators)
 //   warps 2-9: epilogue (column halves): tcgen05.ld -> folded BN -> LeakyReLU -> bf16 -> 128-bit stores
+// 256-wide channel blocks run on CTA PAIRS (conv_bn_lrelu_pair_kernel below: tcgen05 cta_group::2, M256 x N256 MMAs, each CTA
+// stages only half of the weight tile); 128-wide ones on the single-CTA kernel.
+#include <stdlib.h>
 #include "tc.cuh"
 
 namespace vd {
@@ -221,6 +224,216 @@ static int launch_conv(const ConvMaps& maps, const ConvParams& p, cudaStream_t s
     return VD_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// CTA-pair variant (tcgen05 cta_group::2): two CTAs of a cluster (one TPC) work on two M tiles x the same 256 output
+// channels with ONE M256 x N256 x K16 MMA stream issued by the leader.  Each CTA stages its own A box (128 rows) and only
+// HALF of the weight tile (128 of the 256 rows), so the operand bytes a CTA pulls from L2 per k-block drop from 48 KB to
+// 32 KB -- the 1-CTA kernel is bound by exactly that traffic.  Protocol (every barrier lives at the same offset in both CTAs):
+//   producer (warp 0, both CTAs)   waits its own empty[s], TMA-loads its A box + its half of W into its own shared memory; the
+//                                  loads of both CTAs report their bytes to the LEADER's full[s] (cp.async.bulk.tensor.cta_group::2)
+//   MMA      (warp 1, leader CTA)  waits full[s], issues the cta_group::2 MMAs, commit (multicast) -> empty[s] of
+//                                  both CTAs; after the tile's last k-block commit (multicast) -> tmem_full[buf] of both CTAs
+//   epilogue (warps 2-9, both)     drains its own CTA's accumulator (its M tile), arrives on the LEADER's tmem_empty[buf]
+// ---------------------------------------------------------------------------------------------------------------
+struct Conv2Shared {
+    uint64_t full[8], empty[8], peer_full[8], tmem_full[2], tmem_empty[2];
+    uint32_t tmem_base;
+};
+template <int NT> struct Conv2Cfg {
+    static constexpr int A_BYTES = C_BLOCK_M * C_BLOCK_K * 2;
+    static constexpr int B_BYTES = (NT / 2) * C_BLOCK_K * 2;          // this CTA's half of the weight tile
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int STAGES = (200 * 1024) / STAGE_BYTES > 8 ? 8 : (200 * 1024) / STAGE_BYTES;
+    static constexpr int BN_BYTES = 2 * 1024 * 4;
+    static constexpr int TMEM_COLS = 2 * NT;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BN_BYTES + 2048 + 1024;
+};
+
+template <int NT>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(C_THREADS, 1)
+conv_bn_lrelu_pair_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ ConvParams p) {
+    using Cfg = Conv2Cfg<NT>;
+    extern __shared__ unsigned char smem_dyn[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+    unsigned char* ring = smem;
+    float* sscale = reinterpret_cast<float*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+    float* sshift = sscale + 1024;
+    Conv2Shared* sh = reinterpret_cast<Conv2Shared*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES + Cfg::BN_BYTES);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = tc::cluster_ctarank();
+    const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+    for (int i = threadIdx.x; i < p.Cout; i += C_THREADS) { sscale[i] = p.scale[i]; sshift[i] = p.shift[i]; }
+    for (int i = threadIdx.x; i < Cfg::STAGES * Cfg::STAGE_BYTES / 16; i += C_THREADS)
+        reinterpret_cast<uint4*>(ring)[i] = make_uint4(0, 0, 0, 0);
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < Cfg::STAGES; ++i) { tc::mbar_init(&sh->full[i], 1); tc::mbar_init(&sh->empty[i], 1); tc::mbar_init(&sh->peer_full[i], 1); }
+        for (int i = 0; i < 2; ++i) { tc::mbar_init(&sh->tmem_full[i], 1); tc::mbar_init(&sh->tmem_empty[i], 16); }   // 8 epilogue warps x 2 CTAs
+        tc::fence_barrier_init();
+        tc::prefetch_tmap(&maps.x); tc::prefetch_tmap(&maps.w);
+    }
+    if (warp == 1) tc::tmem_alloc_2cta<Cfg::TMEM_COLS>(&sh->tmem_base);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::cluster_sync_all();                 // the peer's barriers are initialised before anything signals them
+    tc::fence_after_sync();
+    const uint32_t tmem_base = sh->tmem_base;
+    const int kb_per_tap = p.Cin / C_BLOCK_K;
+    const int ntaps = p.kt * p.kh * p.kw;
+    const uint32_t a_tx_bytes = (uint32_t)(p.BW * p.BH * p.BF) * C_BLOCK_K * 2;
+    const int m_tiles = p.F2 * p.tiles_f * p.tiles_y * p.tiles_x;
+    const int m_pairs = (m_tiles + 1) >> 1;
+    const int total_pairs = m_pairs * p.n_tiles;
+
+    // pair -> (M tile of CTA r, channel block); a pair index past the last M tile yields b >= F2: an all-padding tile
+    auto coords = [&](int pair, uint32_t r) {
+        ConvTile c;
+        c.nt = pair % p.n_tiles;
+        int m = (pair / p.n_tiles) * 2 + (int)r;
+        c.x0 = (m % p.tiles_x) * p.BW; m /= p.tiles_x;
+        c.y0 = (m % p.tiles_y) * p.BH; m /= p.tiles_y;
+        c.f0 = (m % p.tiles_f) * p.BF; c.b = m / p.tiles_f;
+        return c;
+    };
+    auto tap_offsets = [&](int tap, int& dt, int& dy, int& dx) {
+        dx = tap % p.kw - (p.kw >> 1); int r = tap / p.kw;
+        dy = r % p.kh - (p.kh >> 1); dt = r / p.kh - (p.kt >> 1);
+    };
+    auto tap_active1 = [&](const ConvTile& c, int dt, int dy, int dx) -> bool {
+        const int x1 = min(c.x0 + p.BW, p.W) - 1, y1 = min(c.y0 + p.BH, p.H) - 1, f1 = min(c.f0 + p.BF, p.F1) - 1;
+        return (c.b < p.F2) && (f1 + dt >= 0) && (c.f0 + dt < p.F1) && (y1 + dy >= 0) && (c.y0 + dy < p.H) && (x1 + dx >= 0) && (c.x0 + dx < p.W);
+    };
+    // both CTAs walk the same k-loop: a tap is skipped only if it is pure padding for BOTH M tiles of the pair
+    auto tap_active = [&](int pair, int tap) -> bool {
+        int dt, dy, dx; tap_offsets(tap, dt, dy, dx);
+        return tap_active1(coords(pair, 0), dt, dy, dx) || tap_active1(coords(pair, 1), dt, dy, dx);
+    };
+
+    if (warp == 0) {
+        if (tc::elect_one()) {
+            int stage = 0; uint32_t phase = 0;
+            for (int pair = cluster_id; pair < total_pairs; pair += num_clusters) {
+                const ConvTile c = coords(pair, rank);
+                for (int tap = 0; tap < ntaps; ++tap) {
+                    if (!tap_active(pair, tap)) continue;
+                    int dt, dy, dx; tap_offsets(tap, dt, dy, dx);
+                    for (int kb = 0; kb < kb_per_tap; ++kb) {
+                        tc::mbar_wait_cluster(&sh->empty[stage], phase ^ 1u);
+                        unsigned char* a_dst = ring + stage * Cfg::STAGE_BYTES;
+                        // both CTAs' loads report to the LEADER's full[stage]; the leader expects the bytes of the pair
+                        if (rank == 0) tc::mbar_expect_tx(&sh->full[stage], 2u * (a_tx_bytes + Cfg::B_BYTES));
+                        const uint32_t bar = tc::mapa_u32(&sh->full[stage], 0u);
+                        tc::tma_load_5d_pair(a_dst, &maps.x, bar, kb * C_BLOCK_K, c.x0 + dx, c.y0 + dy, c.f0 + dt, c.b);
+                        tc::tma_load_3d_pair(a_dst + Cfg::A_BYTES, &maps.w, bar, kb * C_BLOCK_K, c.nt * NT + (int)rank * (NT / 2), tap);
+                        if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (tc::elect_one()) {
+            int stage = 0; uint32_t phase = 0; uint32_t it = 0;
+            if (rank == 0) {
+                constexpr uint32_t idesc = tc::make_idesc_bf16(2 * C_BLOCK_M, NT);
+                for (int pair = cluster_id; pair < total_pairs; pair += num_clusters, ++it) {
+                    const uint32_t buf = it & 1u;
+                    tc::mbar_wait_cluster(&sh->tmem_empty[buf], ((it >> 1) & 1u) ^ 1u);
+                    tc::fence_after_sync();
+                    const uint32_t d_tmem = tmem_base + buf * NT;
+                    uint32_t first = 1;
+                    for (int tap = 0; tap < ntaps; ++tap) {
+                        if (!tap_active(pair, tap)) continue;
+                        for (int kb = 0; kb < kb_per_tap; ++kb) {
+                            tc::mbar_wait_cluster(&sh->full[stage], phase);
+                            tc::fence_after_sync();
+                            const uint32_t a_addr = tc::smem_u32(ring + stage * Cfg::STAGE_BYTES);
+                            const uint64_t da = tc::make_smem_desc_sw128(a_addr);
+                            const uint64_t db = tc::make_smem_desc_sw128(a_addr + Cfg::A_BYTES);
+#pragma unroll
+                            for (int k = 0; k < C_BLOCK_K / 16; ++k) {
+                                tc::umma_bf16_2cta(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, first ? 0u : 1u);
+                                first = 0;
+                            }
+                            tc::umma_commit_2cta(&sh->empty[stage]);
+                            if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
+                        }
+                    }
+                    tc::umma_commit_2cta(&sh->tmem_full[buf]);
+                }
+            }
+        }
+    } else {
+        const int q = warp & 3;
+        const int half = (warp - 2) >> 2;
+        constexpr int NH = NT / 2;
+        const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+        const int r = q * 32 + lane;
+        const int lx = r % p.BW, ly = (r / p.BW) % p.BH, lf = r / (p.BW * p.BH);
+        uint32_t it = 0;
+        for (int pair = cluster_id; pair < total_pairs; pair += num_clusters, ++it) {
+            const ConvTile c = coords(pair, rank);
+            const uint32_t buf = it & 1u;
+            const int x = c.x0 + lx, y = c.y0 + ly, f = c.f0 + lf;
+            const bool inb = (lf < p.BF) && (x < p.W) && (y < p.H) && (f < p.F1) && (c.b < p.F2);
+            tc::mbar_wait_cluster(&sh->tmem_full[buf], (it >> 1) & 1u);
+            tc::fence_after_sync();
+            const uint32_t tbase = tmem_base + buf * NT + (uint32_t)(half * NH) + lane_addr;
+            const int col0 = c.nt * NT + half * NH;
+            const size_t pix = inb ? (((size_t)c.b * p.F1 + f) * p.H + y) * p.W + x : 0;
+            __nv_bfloat16* yrow = p.y + pix * p.Cout + col0;
+            const float* sc = sscale + col0;
+            const float* sf = sshift + col0;
+#pragma unroll 1
+            for (int n0 = 0; n0 < NH; n0 += 32) {
+                uint32_t v[32];
+                tc::tmem_ld16(tbase + n0, v); tc::tmem_ld16(tbase + n0 + 16, v + 16); tc::tmem_ld_wait();
+                uint32_t packed[16];
+#pragma unroll
+                for (int i = 0; i < 32; i += 4) {
+                    const float4 s4 = *reinterpret_cast<const float4*>(sc + n0 + i);
+                    const float4 f4 = *reinterpret_cast<const float4*>(sf + n0 + i);
+                    float v0 = fmaf(__uint_as_float(v[i]), s4.x, f4.x), v1 = fmaf(__uint_as_float(v[i + 1]), s4.y, f4.y);
+                    float v2 = fmaf(__uint_as_float(v[i + 2]), s4.z, f4.z), v3 = fmaf(__uint_as_float(v[i + 3]), s4.w, f4.w);
+                    v0 = v0 > 0.f ? v0 : v0 * p.slope; v1 = v1 > 0.f ? v1 : v1 * p.slope;
+                    v2 = v2 > 0.f ? v2 : v2 * p.slope; v3 = v3 > 0.f ? v3 : v3 * p.slope;
+                    __nv_bfloat162 h0 = __floats2bfloat162_rn(v0, v1), h1 = __floats2bfloat162_rn(v2, v3);
+                    packed[i / 2] = *reinterpret_cast<uint32_t*>(&h0); packed[i / 2 + 1] = *reinterpret_cast<uint32_t*>(&h1);
+                }
+                if (inb) {
+                    uint4* dst = reinterpret_cast<uint4*>(yrow + n0);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) dst[i] = make_uint4(packed[4 * i], packed[4 * i + 1], packed[4 * i + 2], packed[4 * i + 3]);
+                }
+            }
+            tc::fence_before_sync();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive_cluster(&sh->tmem_empty[buf], 0u);
+        }
+    }
+    __syncwarp();
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::cluster_sync_all();                 // neither CTA may exit (or free TMEM) while its peer can still touch it
+    if (warp == 1) tc::tmem_dealloc_2cta<Cfg::TMEM_COLS>(tmem_base);
+}
+
+static int launch_conv_pair(const ConvMaps& maps, const ConvParams& p, cudaStream_t stream) {
+    using Cfg = Conv2Cfg<256>;
+    auto kern = conv_bn_lrelu_pair_kernel<256>;
+    static bool configured = false;
+    if (!configured) {
+        VD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        configured = true;
+    }
+    const long long m_tiles = (long long)p.F2 * p.tiles_f * p.tiles_y * p.tiles_x;
+    const long long pairs = (m_tiles + 1) / 2 * p.n_tiles;
+    long long clusters = sm_count() / 2; if (clusters > pairs) clusters = pairs;
+    kern<<<(unsigned)(2 * clusters), C_THREADS, Cfg::SMEM_BYTES, stream>>>(maps, p);
+    VD_LAUNCH_CHECK();
+    return VD_OK;
+}
+
 // Box of an M tile: the (BW, BH, BF) with BW*BH*BF <= 128 that wastes the fewest MMA rows over all F frames
 // (ties: the widest, then tallest box = the longest contiguous runs in memory).
 static void choose_box(int H, int W, int F, int* BW, int* BH, int* BF) {
@@ -282,9 +495,13 @@ extern "C" int vd_conv_bn_lrelu(const void* x, void* y, int B, int T, int H, int
     const int ntaps = kt * kh * kw;
     uint64_t dimsW[3] = {(uint64_t)Cin, (uint64_t)Cout, (uint64_t)ntaps};
     uint64_t strW[2] = {Cin * e, (uint64_t)Cout * Cin * e};
-    uint32_t boxW[3] = {C_BLOCK_K, (uint32_t)NT, 1};
+    // CTA pairs (cta_group::2) for 256-wide channel blocks; VD_CONV_PAIR=0 keeps the 1-CTA kernel
+    static const bool pair_ok = []() { const char* e = getenv("VD_CONV_PAIR"); return e ? atoi(e) != 0 : true; }();
+    const bool pair = pair_ok && NT == 256 && (long long)p.F2 * p.tiles_f * p.tiles_y * p.tiles_x >= 2;
+    uint32_t boxW[3] = {C_BLOCK_K, (uint32_t)(pair ? NT / 2 : NT), 1};
     rc = encode_tmap_bf16(&maps.w, weight, 3, dimsW, strW, boxW);
     if (rc) return rc;
+    if (pair) return launch_conv_pair(maps, p, (cudaStream_t)stream_);
     if (NT == 256) return launch_conv<256>(maps, p, (cudaStream_t)stream_);
     return launch_conv<128>(maps, p, (cudaStream_t)stream_);
 }

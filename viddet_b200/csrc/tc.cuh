@@ -155,6 +155,72 @@ __device__ __forceinline__ void tmem_ld(uint32_t taddr, uint32_t* r) {
     else { tmem_ld1(taddr, r); }
 }
 
+// ------------------------------------------------------------------ CTA pair (cta_group::2) / cluster helpers
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the same barrier (same shared-memory offset) of CTA `cta` of the cluster
+__device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t cta) {
+    asm volatile("{\n\t.reg .b32 ra;\n\tmapa.shared::cluster.u32 ra, %0, %1;\n\t"
+                 "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}" ::"r"(smem_u32(bar)), "r"(cta) : "memory");
+}
+// wait on a local barrier whose arrivals come from the peer CTA (cluster-scope acquire); bounded like mbar_wait
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    uint32_t done = 0;
+    for (uint32_t spin = 0; !done; ++spin) {
+        asm volatile(
+            "{\n\t.reg .pred P;\n\t"
+            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, P;\n\t}"
+            : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+        if (!done && spin > (1u << 24)) {
+            printf("viddet_b200: cluster mbarrier wait timed out (block %d thread %d bar %u parity %u)\n",
+                   (int)blockIdx.x, (int)threadIdx.x, addr, parity);
+            __trap();
+        }
+    }
+}
+// shared::cluster address of the same shared-memory offset in CTA `cta` of the cluster
+__device__ __forceinline__ uint32_t mapa_u32(const void* p, uint32_t cta) {
+    uint32_t r; asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(p)), "r"(cta)); return r;
+}
+// TMA loads of a CTA pair: the data lands in THIS CTA's shared memory, the transaction bytes are reported to a barrier that may
+// live in the peer CTA (`bar_cluster_addr` = mapa of the leader's barrier)
+__device__ __forceinline__ void tma_load_5d_pair(void* smem_dst, const CUtensorMap* m, uint32_t bar_cluster_addr, int c0, int c1, int c2, int c3, int c4) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_pair(void* smem_dst, const CUtensorMap* m, uint32_t bar_cluster_addr, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+template <uint32_t kCols>
+__device__ __forceinline__ void tmem_alloc_2cta(uint32_t* smem_slot) {      // one full warp in EACH CTA of the pair
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_slot)), "n"(kCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+template <uint32_t kCols>
+__device__ __forceinline__ void tmem_dealloc_2cta(uint32_t taddr) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(kCols) : "memory");
+}
+// D[tmem of both CTAs] (+)= A[smem of both CTAs: 128 rows each] * B[smem of both CTAs: N/2 rows each]^T; issued by ONE thread of the leader CTA
+__device__ __forceinline__ void umma_bf16_2cta(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+// arrives on the barrier at this offset in BOTH CTAs once all previously issued MMAs of the pair have completed
+__device__ __forceinline__ void umma_commit_2cta(uint64_t* bar) {
+    const uint16_t mask = 3;
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"(mask) : "memory");
+}
+
 // ------------------------------------------------------------------ descriptors
 // Shared-memory matrix descriptor, K-major operand tile stored as rows of 64 bf16 (128 bytes)
 // with the 128-byte swizzle (what a TMA box {64, rows} with CU_TENSOR_MAP_SWIZZLE_128B writes):

@@ -11,6 +11,7 @@
 //   warp 1: MMA issuer, M=128 x N=NT x K=16, accumulators double-buffered in TMEM
 //   warps 2-9: epilogue (two warpgroups, each takes half of the tile's columns): tcgen05.ld -> folded BN (scale/shift
 //              staged in shared memory) -> LeakyReLU -> bf16 -> 128-bit stores
+#include <stdlib.h>
 #include "tc.cuh"
 
 namespace vd {
@@ -179,6 +180,190 @@ temporal_conv_kernel(const __grid_constant__ TConvMaps maps, const __grid_consta
     if (warp == 1) tc::tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// CTA-pair variant for 256-wide channel blocks (tcgen05 cta_group::2; same protocol as conv_bn_lrelu_pair_kernel in
+// conv.cu): the two CTAs of a cluster take two consecutive 128-row tiles of the flattened (window, T*HW) row axis and the same
+// 256 output channels; ONE M256 x N256 x K16 MMA stream is issued by the leader; each CTA stages its own A tile and HALF of
+// the tap's weight tile, both CTAs' TMA loads report their bytes to the leader's full barrier, commits are multicast.
+// ---------------------------------------------------------------------------------------------------------------
+struct T2Shared {
+    uint64_t full[8], empty[8], tmem_full[2], tmem_empty[2];
+    uint32_t tmem_base;
+};
+struct T2Cfg {
+    static constexpr int NT = 256;
+    static constexpr int A_BYTES = T_BLOCK_M * T_BLOCK_K * 2;
+    static constexpr int B_BYTES = (NT / 2) * T_BLOCK_K * 2;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int STAGES = (200 * 1024) / STAGE_BYTES > 8 ? 8 : (200 * 1024) / STAGE_BYTES;
+    static constexpr int BN_BYTES = 2 * 1024 * 4;
+    static constexpr int TMEM_COLS = 2 * NT;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BN_BYTES + 2048 + 1024;
+};
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(T_THREADS, 1)
+temporal_conv_pair_kernel(const __grid_constant__ TConvMaps maps, const __grid_constant__ TConvParams p) {
+    using Cfg = T2Cfg;
+    constexpr int NT = Cfg::NT;
+    extern __shared__ unsigned char smem_dyn[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+    unsigned char* ring = smem;
+    float* sscale = reinterpret_cast<float*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+    float* sshift = sscale + 1024;
+    T2Shared* sh = reinterpret_cast<T2Shared*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES + Cfg::BN_BYTES);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = tc::cluster_ctarank();
+    const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+    for (int i = threadIdx.x; i < p.C; i += T_THREADS) { sscale[i] = p.scale[i]; sshift[i] = p.shift[i]; }
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < Cfg::STAGES; ++i) { tc::mbar_init(&sh->full[i], 1); tc::mbar_init(&sh->empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { tc::mbar_init(&sh->tmem_full[i], 1); tc::mbar_init(&sh->tmem_empty[i], 16); }
+        tc::fence_barrier_init();
+        tc::prefetch_tmap(&maps.x); tc::prefetch_tmap(&maps.w);
+    }
+    if (warp == 1) tc::tmem_alloc_2cta<Cfg::TMEM_COLS>(&sh->tmem_base);
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::cluster_sync_all();
+    tc::fence_after_sync();
+    const uint32_t tmem_base = sh->tmem_base;
+    const int kb_per_tap = p.C / T_BLOCK_K;
+    const int m_total = p.B * p.m_tiles;                       // 128-row tiles over all windows
+    const int total_pairs = ((m_total + 1) >> 1) * p.n_tiles;
+
+    // pair -> (window b, row block mt) of CTA r, channel block nt; past the last tile: b == B (pure padding, nothing stored)
+    auto coords = [&](int pair, uint32_t r, int& b, int& mt, int& nt) {
+        nt = pair % p.n_tiles;
+        const int m = (pair / p.n_tiles) * 2 + (int)r;
+        mt = m % p.m_tiles; b = m / p.m_tiles;
+    };
+    auto tap_active1 = [&](int b, int mt, int dt) -> bool {
+        const int r0 = mt * T_BLOCK_M;
+        int r1 = r0 + T_BLOCK_M - 1; if (r1 > p.rows - 1) r1 = p.rows - 1;
+        return (b < p.B) && (r1 + dt * p.HW >= 0) && (r0 + dt * p.HW <= p.rows - 1);
+    };
+    auto tap_active = [&](int pair, int dt) -> bool {          // skipped only if pure padding for BOTH tiles of the pair
+        int b0, m0, n0, b1, m1, n1; coords(pair, 0, b0, m0, n0); coords(pair, 1, b1, m1, n1);
+        return tap_active1(b0, m0, dt) || tap_active1(b1, m1, dt);
+    };
+
+    if (warp == 0) {
+        if (tc::elect_one()) {
+            int stage = 0; uint32_t phase = 0;
+            for (int pair = cluster_id; pair < total_pairs; pair += num_clusters) {
+                int b, mt, nt; coords(pair, rank, b, mt, nt);
+                for (int tap = 0; tap < 3; ++tap) {
+                    const int dt = tap - 1;
+                    if (!tap_active(pair, dt)) continue;
+                    for (int kb = 0; kb < kb_per_tap; ++kb) {
+                        tc::mbar_wait_cluster(&sh->empty[stage], phase ^ 1u);
+                        unsigned char* a_dst = ring + stage * Cfg::STAGE_BYTES;
+                        if (rank == 0) tc::mbar_expect_tx(&sh->full[stage], 2u * Cfg::STAGE_BYTES);
+                        const uint32_t bar = tc::mapa_u32(&sh->full[stage], 0u);
+                        tc::tma_load_3d_pair(a_dst, &maps.x, bar, kb * T_BLOCK_K, mt * T_BLOCK_M + dt * p.HW, b);
+                        tc::tma_load_3d_pair(a_dst + Cfg::A_BYTES, &maps.w, bar, kb * T_BLOCK_K, nt * NT + (int)rank * (NT / 2), tap);
+                        if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (rank == 0 && tc::elect_one()) {
+            constexpr uint32_t idesc = tc::make_idesc_bf16(2 * T_BLOCK_M, NT);
+            int stage = 0; uint32_t phase = 0; uint32_t it = 0;
+            for (int pair = cluster_id; pair < total_pairs; pair += num_clusters, ++it) {
+                const uint32_t buf = it & 1u;
+                tc::mbar_wait_cluster(&sh->tmem_empty[buf], ((it >> 1) & 1u) ^ 1u);
+                tc::fence_after_sync();
+                const uint32_t d_tmem = tmem_base + buf * NT;
+                uint32_t first = 1;
+                for (int tap = 0; tap < 3; ++tap) {
+                    if (!tap_active(pair, tap - 1)) continue;
+                    for (int kb = 0; kb < kb_per_tap; ++kb) {
+                        tc::mbar_wait_cluster(&sh->full[stage], phase);
+                        tc::fence_after_sync();
+                        const uint32_t a_addr = tc::smem_u32(ring + stage * Cfg::STAGE_BYTES);
+                        const uint64_t da = tc::make_smem_desc_sw128(a_addr);
+                        const uint64_t db = tc::make_smem_desc_sw128(a_addr + Cfg::A_BYTES);
+#pragma unroll
+                        for (int k = 0; k < T_BLOCK_K / 16; ++k) {
+                            tc::umma_bf16_2cta(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, first ? 0u : 1u);
+                            first = 0;
+                        }
+                        tc::umma_commit_2cta(&sh->empty[stage]);
+                        if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
+                    }
+                }
+                tc::umma_commit_2cta(&sh->tmem_full[buf]);
+            }
+        }
+    } else {
+        const int q = warp & 3;
+        const int half = (warp - 2) >> 2;
+        constexpr int NH = NT / 2;
+        const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+        uint32_t it = 0;
+        for (int pair = cluster_id; pair < total_pairs; pair += num_clusters, ++it) {
+            int b, mt, nt; coords(pair, rank, b, mt, nt);
+            const uint32_t buf = it & 1u;
+            const int row = mt * T_BLOCK_M + q * 32 + lane;
+            const bool inb = row < p.rows && b < p.B;
+            tc::mbar_wait_cluster(&sh->tmem_full[buf], (it >> 1) & 1u);
+            tc::fence_after_sync();
+            const uint32_t tbase = tmem_base + buf * NT + (uint32_t)(half * NH) + lane_addr;
+            const int col0 = nt * NT + half * NH;
+            __nv_bfloat16* yrow = p.y + (inb ? ((size_t)b * p.rows + row) * p.C : 0) + col0;
+            const float* sc = sscale + col0;
+            const float* sf = sshift + col0;
+#pragma unroll 1
+            for (int n0 = 0; n0 < NH; n0 += 32) {
+                uint32_t r[32];
+                tc::tmem_ld16(tbase + n0, r); tc::tmem_ld16(tbase + n0 + 16, r + 16); tc::tmem_ld_wait();
+                uint32_t packed[16];
+#pragma unroll
+                for (int i = 0; i < 32; i += 4) {
+                    const float4 s4 = *reinterpret_cast<const float4*>(sc + n0 + i);
+                    const float4 f4 = *reinterpret_cast<const float4*>(sf + n0 + i);
+                    float v0 = fmaf(__uint_as_float(r[i]), s4.x, f4.x), v1 = fmaf(__uint_as_float(r[i + 1]), s4.y, f4.y);
+                    float v2 = fmaf(__uint_as_float(r[i + 2]), s4.z, f4.z), v3 = fmaf(__uint_as_float(r[i + 3]), s4.w, f4.w);
+                    v0 = v0 > 0.f ? v0 : v0 * p.slope; v1 = v1 > 0.f ? v1 : v1 * p.slope;
+                    v2 = v2 > 0.f ? v2 : v2 * p.slope; v3 = v3 > 0.f ? v3 : v3 * p.slope;
+                    __nv_bfloat162 h0 = __floats2bfloat162_rn(v0, v1), h1 = __floats2bfloat162_rn(v2, v3);
+                    packed[i / 2] = *reinterpret_cast<uint32_t*>(&h0); packed[i / 2 + 1] = *reinterpret_cast<uint32_t*>(&h1);
+                }
+                if (inb) {
+                    uint4* dst = reinterpret_cast<uint4*>(yrow + n0);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) dst[i] = make_uint4(packed[4 * i], packed[4 * i + 1], packed[4 * i + 2], packed[4 * i + 3]);
+                }
+            }
+            tc::fence_before_sync();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive_cluster(&sh->tmem_empty[buf], 0u);
+        }
+    }
+    __syncwarp();
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::cluster_sync_all();
+    if (warp == 1) tc::tmem_dealloc_2cta<Cfg::TMEM_COLS>(tmem_base);
+}
+
+static int launch_tconv_pair(const TConvMaps& maps, const TConvParams& p, cudaStream_t stream) {
+    auto kern = temporal_conv_pair_kernel;
+    static bool configured = false;
+    if (!configured) {
+        VD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, T2Cfg::SMEM_BYTES));
+        configured = true;
+    }
+    const long long pairs = ((long long)p.B * p.m_tiles + 1) / 2 * p.n_tiles;
+    long long clusters = sm_count() / 2; if (clusters > pairs) clusters = pairs;
+    kern<<<(unsigned)(2 * clusters), T_THREADS, T2Cfg::SMEM_BYTES, stream>>>(maps, p);
+    VD_LAUNCH_CHECK();
+    return VD_OK;
+}
+
 template <int NT>
 static int launch_tconv(const TConvMaps& maps, const TConvParams& p, cudaStream_t stream) {
     using Cfg = TConvCfg<NT>;
@@ -222,9 +407,12 @@ extern "C" int vd_temporal_conv(const void* x, void* y, int B, int T, int H, int
     if (rc) return rc;
     uint64_t dimsW[3] = {(uint64_t)C, (uint64_t)C, 3};
     uint64_t strW[2] = {(uint64_t)C * 2, (uint64_t)C * C * 2};
-    uint32_t boxW[3] = {T_BLOCK_K, (uint32_t)NT, 1};
+    static const bool pair_ok = []() { const char* e = getenv("VD_CONV_PAIR"); return e ? atoi(e) != 0 : true; }();   // CTA pairs (cta_group::2) for 256-wide channel blocks
+    const bool pair = pair_ok && NT == 256 && (long long)B * p.m_tiles >= 2;
+    uint32_t boxW[3] = {T_BLOCK_K, (uint32_t)(pair ? NT / 2 : NT), 1};
     rc = encode_tmap_bf16(&maps.w, weight, 3, dimsW, strW, boxW);
     if (rc) return rc;
+    if (pair) return launch_tconv_pair(maps, p, (cudaStream_t)stream_);
     if (NT == 256) return launch_tconv<256>(maps, p, (cudaStream_t)stream_);
     return launch_tconv<128>(maps, p, (cudaStream_t)stream_);
 }

@@ -219,6 +219,8 @@ head_kernel(const __grid_constant__ HeadMaps maps, const __grid_constant__ HeadK
     HeadShared* sh = reinterpret_cast<HeadShared*>(sbias + VD_MAX_SCALES * NPAD);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // the exact fallback of the speculative path with no failed frame (the steady state): nothing to set up, nothing to claim
+    if constexpr (EPI == EPI_FILTER) { if (p.frame_list != nullptr && *p.frame_count == 0u) return; }
     auto gtime = []() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t) :: "memory"); return (long long)t; };
     if ((EPI == EPI_FILTER || EPI == EPI_SPEC) && p.stamps && p.frame_list == nullptr && threadIdx.x == 0) {
         p.stamps[4096 + blockIdx.x * 4 + 0] = gtime();
@@ -404,11 +406,16 @@ head_kernel(const __grid_constant__ HeadMaps maps, const __grid_constant__ HeadK
             if (stamp) p.stamps[it * 16 + 3] = clock64();
             // global reads of the selection issued before the wait for the accumulator (their latency hides behind it)
             uint32_t pf_c0 = 0u, pf_c1 = 0u, pf_hint = 0u;
-            if constexpr (EPI == EPI_SPEC) {                     // this frame slot's threshold (foreign workspace: the NMS kernel fails every frame anyway)
+            if constexpr (EPI == EPI_SPEC) {                     // this frame slot's threshold
                 const uint32_t floor_b = p.valid_thresh > 0.0f ? __float_as_uint(p.valid_thresh) : 0u;
                 const uint32_t hint = spec_ws_ok ? __ldcg(p.spec_tau + f) : 0u;
                 spec_tb = hint > floor_b ? hint : floor_b;
                 if (spec_tb > 0x3f800001u) spec_tb = 0x3f800001u;
+                // Nothing is emitted (threshold above every score) on a foreign workspace: the NMS kernel fails every frame
+                // anyway, and with tau = the valid floor this was 8 ms of atomics for 64 dense frames.  (Also reading the frame's
+                // running count here, to stop emitting once its list has overflowed, costs 2 us per step: the word is under
+                // atomic traffic from every CTA.)
+                if (!spec_ws_ok) spec_tb = 0x3f800001u;
             }
             if constexpr (EPI == EPI_FILTER) {
                 if (ws_ok && et < 32) { const uint32_t* ch = p.coarse + (size_t)f * 64; pf_c0 = __ldcg(ch + 63 - 2 * lane); pf_c1 = __ldcg(ch + 62 - 2 * lane); }
@@ -519,6 +526,7 @@ head_kernel(const __grid_constant__ HeadMaps maps, const __grid_constant__ HeadK
                         float e = (r < 1.0f) ? l : __uint_as_float(0x7f800000u);
                         if (spec_tb == 0u) e = __uint_as_float(0xff800000u);
                         if (!(conf[a] == conf[a])) e = __uint_as_float(0x7f800000u);
+                        if (spec_tb >= 0x3f800001u) e = __uint_as_float(0x7f800000u);      // "emit nothing" (see above): conf may exceed tau/1 only by rounding
                         ell[a] = e;
                     }
                 }

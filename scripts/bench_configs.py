@@ -51,10 +51,17 @@ def event_pairs(sessions, n, stages):
     return [sorted(e[k].elapsed_time(e[k + 1]) for e in evs)[n // 2] for k in range(len(stages))]
 
 
-def head_cfg(name):
+def head_cfg(name, obj_bias=None):
+    """obj_bias: the 'trained-like' secondary variant of SURVEY 8(d): objectness bias (e.g. -5) => sparse candidates."""
     C, size, frames = bench.WORKLOADS[name]
     gen = torch.Generator(device=dev).manual_seed(1234)
     head = viddet_b200.YOLOV3Head(C).initialize(generator=torch.Generator().manual_seed(1234))
+    if obj_bias is not None:
+        for o in head.yolo_outputs:
+            bias = o.prediction.bias.clone()
+            bias.view(3, 5 + C)[:, 4] = obj_bias
+            o.prediction.set_data(o.prediction.weight, bias)
+        name = "%s_objbias%g" % (name, obj_bias)
     nrot = 3
     sessions = [head.session(bench.synth_tips(torch, gen, frames, size, dev)) for _ in range(nrot)]
     for s in sessions:
@@ -155,6 +162,8 @@ if __name__ == "__main__":
     print(json.dumps({"peaks": {"hbm_GBps": PEAK_HBM, "bf16_tflops_sustained": PEAK_TC}}))
     if "voc" in which:
         head_cfg("voc416_b64")
+    if "voc_trained" in which:
+        head_cfg("voc416_b64", obj_bias=-5.0)
     if "coco" in which:
         head_cfg("coco608_b64")
     if "vid" in which:

@@ -234,13 +234,19 @@ head_kernel(const __grid_constant__ HeadMaps maps, const __grid_constant__ HeadK
     if constexpr (EPI != EPI_SPEC) asm volatile("griddepcontrol.wait;" ::: "memory");
 
     // ---------------- one-time setup
-    for (int i = threadIdx.x; i < VD_MAX_SCALES * NPAD; i += Cfg::THREADS) {
+    // EPI_SPEC: the producer warp does not stage biases and does not wait for the rest of the CTA: it initialises the barriers,
+    // signals the named barrier (bar.arrive, non-blocking) and starts claiming tiles / issuing TMA at once, so the first loads'
+    // latency overlaps the bias staging and the TMEM allocation of the other warps (kEarly).
+    constexpr bool kEarly = (EPI == EPI_SPEC);
+    const int st0 = kEarly ? (int)threadIdx.x - 32 : (int)threadIdx.x;        // staging index of this thread (warp 0 excluded when early)
+    constexpr int kStageThreads = kEarly ? Cfg::THREADS - 32 : Cfg::THREADS;
+    for (int i = st0; i >= 0 && i < VD_MAX_SCALES * NPAD; i += kStageThreads) {
         int s = i / NPAD, n = i % NPAD;
         sbias[i] = (s < p.g.num_scales && p.bias[s] && n < p.n_valid) ? p.bias[s][n] : 0.0f;
     }
     if constexpr (EPI == EPI_FILTER || EPI == EPI_SPEC) {
         constexpr int P = 5 + C;
-        for (int i = threadIdx.x; i < VD_MAX_SCALES * 3 * Cfg::CPA * Cfg::CH4; i += Cfg::THREADS) {
+        for (int i = st0; i >= 0 && i < VD_MAX_SCALES * 3 * Cfg::CPA * Cfg::CH4; i += kStageThreads) {
             const int s = i / (3 * Cfg::CPA * Cfg::CH4), r = i % (3 * Cfg::CPA * Cfg::CH4);
             const int a = r / (Cfg::CPA * Cfg::CH4), cc = (r / Cfg::CH4) % Cfg::CPA, ci = r % Cfg::CH4;
             const int c = cc * Cfg::CH + ci;
@@ -267,6 +273,10 @@ head_kernel(const __grid_constant__ HeadMaps maps, const __grid_constant__ HeadK
     }
     if (warp == 1) tc::tmem_alloc<Cfg::TMEM_COLS>(&sh->tmem_base);
     tc::fence_before_sync();
+    if constexpr (kEarly) {
+        if (warp == 0) { __syncwarp(); asm volatile("bar.arrive 1, %0;" ::"n"(Cfg::THREADS) : "memory"); }
+        else asm volatile("bar.sync 1, %0;" ::"n"(Cfg::THREADS) : "memory");
+    } else
     __syncthreads();
     tc::fence_after_sync();
     const uint32_t tmem_base = sh->tmem_base;
@@ -364,12 +374,6 @@ head_kernel(const __grid_constant__ HeadMaps maps, const __grid_constant__ HeadK
         if constexpr (EPI == EPI_FILTER) ws_ok = p.tile_counter[2] == p.ws_magic;
         (void)ws_ok;
         uint32_t spec_tb = 0u;                                // EPI_SPEC: the call's score threshold (float bits)
-        if constexpr (EPI == EPI_SPEC) {
-            const uint32_t floor_b = p.valid_thresh > 0.0f ? __float_as_uint(p.valid_thresh) : 0u;
-            const uint32_t hint = 0u;                         // (per-frame thresholds are read per tile)
-            spec_tb = hint > floor_b ? hint : floor_b;
-            if (spec_tb > 0x3f800001u) spec_tb = 0x3f800001u;
-        }
         (void)spec_tb;
         bool spec_ws_ok = false;
         if constexpr (EPI == EPI_SPEC) spec_ws_ok = p.tile_counter[2] == p.ws_magic;

@@ -47,15 +47,33 @@ def measured_peaks():
     return 6650.0, "fallback"
 
 
+_NVML_POLL = r"""
+import sys, time, signal
+import pynvml as nv
+nv.nvmlInit()
+h = nv.nvmlDeviceGetHandleByIndex(int(sys.argv[1]))
+print("max %d" % nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM), flush=True)
+run = [True]
+signal.signal(signal.SIGTERM, lambda *a: run.__setitem__(0, False))
+out = []
+while run[0]:
+    try:
+        out.append("%.6f %d %d" % (time.monotonic(), nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM), nv.nvmlDeviceGetCurrentClocksEventReasons(h)))
+    except Exception:
+        pass
+    time.sleep(0.002)
+print("\n".join(out), flush=True)
+"""
+
+
 class NvmlSampler:
-    """SM clock + clock-event (throttle) reasons polled through NVML every ~2 ms DURING the timed region (the timed region of
-    the default run lasts ~10-100 ms: nvidia-smi's 100 ms loop would see none of it).  Same fields as the recipe's clocks line."""
+    """SM clock + clock-event (throttle) reasons polled through NVML every ~2 ms by a SEPARATE PROCESS (a thread of this one is
+    starved by the launch loop holding the GIL), time-stamped with CLOCK_MONOTONIC; `stop(t0, t1)` keeps the samples taken
+    inside the timed region [t0, t1].  Same fields as the recipe's clocks line."""
 
     def __init__(self, index):
         import pynvml
-        self.nv = pynvml
-        pynvml.nvmlInit()
-        # NVML enumerates physical devices: honour CUDA_VISIBLE_DEVICES when it is a plain index list
+        pynvml.nvmlInit()                      # fail here (-> nvidia-smi fallback) rather than in the child
         vis = os.environ.get("CUDA_VISIBLE_DEVICES")
         phys = index
         if vis:
@@ -63,36 +81,46 @@ class NvmlSampler:
                 phys = int(vis.split(",")[index])
             except (ValueError, IndexError):
                 phys = index
-        self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
-        self.sm, self.reasons, self.stop_flag = [], 0, False
-        self.max_sm = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
-        self.lines = self.sm          # len() = samples so far
+        self.phys, self.proc, self.lines = phys, None, []
 
     def start(self):
-        self.thread = threading.Thread(target=self._poll, daemon=True)
-        self.thread.start()
+        self.proc = subprocess.Popen([sys.executable, "-c", _NVML_POLL, str(self.phys)], stdout=subprocess.PIPE,
+                                     stderr=subprocess.DEVNULL, text=True)
+        self.max_line = self.proc.stdout.readline()          # the child is up and polling once this arrives
         return self
 
-    def _poll(self):
-        nv = self.nv
-        while not self.stop_flag:
-            try:
-                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
-                self.reasons |= int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
-            except Exception:
-                pass
-            time.sleep(0.002)
-
-    def stop(self):
-        self.stop_flag = True
-        self.thread.join(timeout=1)
-        nv = self.nv
+    def stop(self, t0=None, t1=None):
+        import pynvml as nv
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill(); out = ""
         names = [("hw_slowdown", nv.nvmlClocksEventReasonHwSlowdown), ("hw_thermal_slowdown", nv.nvmlClocksEventReasonHwThermalSlowdown),
                  ("sw_thermal_slowdown", nv.nvmlClocksEventReasonSwThermalSlowdown), ("sw_power_cap", nv.nvmlClocksEventReasonSwPowerCap),
                  ("hw_power_brake", nv.nvmlClocksEventReasonHwPowerBrakeSlowdown)]
-        sm = sorted(self.sm)
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.max_sm, "samples": len(sm),
-                "reasons": [n for n, bit in names if self.reasons & bit], "source": "nvml, 2 ms period"}
+        sm, reasons, total, allp = [], 0, 0, []
+        for ln in out.splitlines():
+            f = ln.split()
+            if len(f) != 3:
+                continue
+            total += 1
+            t = float(f[0])
+            allp.append((t, float(f[1]), int(f[2])))
+            if (t0 is None or t >= t0) and (t1 is None or t <= t1):
+                sm.append(float(f[1])); reasons |= int(f[2])
+        nearest = False
+        if not sm and allp and t0 is not None:      # timed region shorter than the polling period: the sample closest to it
+            mid = 0.5 * (t0 + t1)
+            t, c, r = min(allp, key=lambda x: abs(x[0] - mid))
+            sm, reasons, nearest = [c], r, True
+        sm.sort()
+        try:
+            mx = float(self.max_line.split()[1])
+        except Exception:
+            mx = None
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "samples": len(sm), "samples_total": total,
+                "reasons": [n for n, bit in names if reasons & bit], "source": "nvml, 2 ms period, separate process, " + ("sample nearest to the (sub-period) timed region" if nearest else "samples inside the timed region")}
 
 
 class ClockSampler:
@@ -118,7 +146,7 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -291,19 +319,21 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = make_sampler(local).start() if rank == 0 else None       # polling (and NVML's lazy init) is warm before the timed region
     run_steps(max(args.warmup, spc))
     barrier()
-    sampler = make_sampler(local).start() if rank == 0 else None
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    t_mono0 = time.monotonic()
     e0.record()
     run_steps(args.steps)
     if world > 1:
         torch.cuda.current_stream().wait_stream(side)     # the last gather is part of the job
     e1.record()
     barrier()
+    t_mono1 = time.monotonic()
     ms = e0.elapsed_time(e1)
-    clocks = sampler.stop() if sampler else None
+    clocks = sampler.stop(t_mono0, t_mono1) if sampler else None
     if world > 1:
         t = torch.tensor([ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

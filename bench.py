@@ -363,20 +363,36 @@ def main():
 
     # ---- end to end through the public API with HOST buffers (pinned), H2D + D2H inside the timed region
     host_sets = [[t.cpu().pin_memory() for t in s.tips] for s in sessions[:2]]
-    host_out = torch.empty((frames, 100, 6), dtype=torch.float32).pin_memory()
+    host_outs = [torch.empty((frames, 100, 6), dtype=torch.float32).pin_memory() for _ in range(2)]
     h2d = sum(t.numel() * t.element_size() for t in host_sets[0])
-    d2h = host_out.numel() * 4
+    d2h = host_outs[0].numel() * 4
     sess = sessions[0]
+    copy_stream = torch.cuda.Stream()
+    h2d_done = [torch.cuda.Event() for _ in range(2)]
+    compute_done = [torch.cuda.Event() for _ in range(2)]
+    for ev in compute_done:
+        ev.record()
 
     gather_one = torch.empty((world * frames, 100, 6), device=dev) if world > 1 else None
 
     def e2e_step(i):
-        for dst, src in zip(sess.tips, host_sets[i % 2]):
-            dst.copy_(src, non_blocking=True)
-        sess.replay()
-        host_out.copy_(sess.packed(), non_blocking=True)
+        """Two device input buffers: the H2D copy of step i+1 (copy stream) runs under the head of step i (main stream); every
+        step's inputs cross PCIe and its (64,100,6) result is read back, both inside the timed region."""
+        j = i % 2
+        s_ = sessions[j]
+        main = torch.cuda.current_stream()
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(compute_done[j])              # the buffer's previous step has consumed it
+            for dst, src in zip(s_.tips, host_sets[j]):
+                dst.copy_(src, non_blocking=True)
+            h2d_done[j].record(copy_stream)
+        main.wait_event(h2d_done[j])
+        s_.replay()
+        packed = s_.packed()
+        host_outs[j].copy_(packed, non_blocking=True)
+        compute_done[j].record(main)
         if world > 1:
-            dist.all_gather_into_tensor(gather_one, sess.packed())
+            dist.all_gather_into_tensor(gather_one, packed)
 
     e2e_steps = max(5, min(args.steps, 30))
     for i in range(3):
@@ -430,7 +446,7 @@ def main():
                          "path_frac": (alg_bytes * world * args.steps / (ms * 1e-3) / 1e9 / world) / peak},
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": e2e_steps, "note": "pinned host bf16 NHWC tips -> H2D -> fused head -> D2H of (64,100,6)"},
+                    "steps": e2e_steps, "note": "pinned host bf16 NHWC tips -> H2D (copy stream, double-buffered under the previous step's compute) -> fused head -> D2H of (64,100,6); PCIe-bound (measured H2D ceiling 55.2 GB/s)"},
             "gpu_launches": args.steps * sess.launches,                   # head kernel + NMS kernel per step
             "clocks": clocks,
         }

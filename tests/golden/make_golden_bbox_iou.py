@@ -8,7 +8,7 @@ import sys
 import numpy as np
 
 REF = "/root/reference/utils/bbox.py"
-OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "bbox_iou_golden.npz")
+OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "bbox_iou_golden.npz")
 
 
 def main():

@@ -9,7 +9,7 @@ import os
 import numpy as np
 
 REF = "/root/reference"
-OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "hier_nms_golden.npz")
+OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "hier_nms_golden.npz")
 
 
 def cut(path, names, cls=None):

@@ -5,7 +5,7 @@
   YOLOV3TargetMerger                    models/definitions/yolo/yolo_target.py:207-281
   TimeDistributed, TemporalPooling      models/definitions/layers.py:161-264
   YOLOV3 (+ YOLODetectionBlockV3, _conv2d, _upsample)   yolo3.py:202-534, layers.py:10-20,63-70  -- inference forward after the stages
-over scripts/mx_shim.py (a numpy stand-in for the MXNet / GluonCV operators they call; MXNet itself cannot be imported here).
+over tests/golden/mx_shim.py (a numpy stand-in for the MXNet / GluonCV operators they call; MXNet itself cannot be imported here).
 The class sources are cut out of /root/reference with `ast` at run time and exec'd -- nothing is copied into the repo.
 What this pins: the reference's own logic (slicing, reshape/transposes = row order, the per-GT loop, index math, _slice,
 where-merges); what stays restated: the upstream operators inside the shim.  NumPy here is 2.x (NEP 50): np.float32 scalars
@@ -23,7 +23,7 @@ import mx_shim  # noqa: E402
 from mx_shim import ND, F  # noqa: E402
 
 REF = "/root/reference/models/definitions/yolo"
-OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "ref_exec_golden.npz")
+OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "ref_exec_golden.npz")
 f32 = np.float32
 
 

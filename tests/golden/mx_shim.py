@@ -1,6 +1,6 @@
 """A numpy-backed stand-in for the handful of MXNet / Gluon / GluonCV names the reference's hot-path classes touch, so that
 their OWN Python (cut out of /root/reference with `ast`, never copied) can be executed here to generate golden vectors
-(scripts/make_golden_ref_exec.py).  TEST INFRASTRUCTURE ONLY.  The operators below restate the published MXNet semantics
+(tests/golden/make_golden_ref_exec.py).  TEST INFRASTRUCTURE ONLY.  The operators below restate the published MXNet semantics
 (fp32 everywhere, reshape codes 0/-1/-2/-3, float 0/1 comparison results, first-max argmax returned as fp32, corner-format
 box_iou); what the goldens pin is the reference's own logic on top of them: slicing, row order, the target loop, index math."""
 import contextlib
@@ -111,7 +111,7 @@ class _Contrib:
         """mx.nd.contrib.box_nms: delegated to the oracle's restatement (oracle/ref_nms.py) -- what the goldens pin around it
         is the caller's wiring (concat order, parameters, slicing), not the operator."""
         import os, sys
-        sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+        sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
         from oracle import ref_nms
         return ND(np.asarray(ref_nms.box_nms(data.a, **kw), f32))
 

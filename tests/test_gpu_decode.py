@@ -120,7 +120,7 @@ def _hier_cases():
 
 def test_hierarchical_nms_matches_reference_golden_bit_exact():
     """Golden vectors = outputs of the reference's own hierarchical_nms executed on these inputs
-    (scripts/make_golden_hier_nms.py); bit-exact rows and counts."""
+    (tests/golden/make_golden_hier_nms.py); bit-exact rows and counts."""
     import viddet_b200
     for ci, c in _hier_cases():
         ov, conf, lvl = c["params"]

@@ -1,5 +1,5 @@
 """The CUDA path against golden vectors produced by EXECUTING the reference's own classes over a numpy stand-in for the MXNet
-operators (scripts/make_golden_ref_exec.py): YOLOOutputV3 (all three modes), YOLOV3PrefetchTargetGenerator, YOLOV3TargetMerger."""
+operators (tests/golden/make_golden_ref_exec.py): YOLOOutputV3 (all three modes), YOLOV3PrefetchTargetGenerator, YOLOV3TargetMerger."""
 import os
 
 import numpy as np

@@ -1,5 +1,5 @@
 """Oracle vs golden vectors produced by the reference's own importable helper
-(utils/bbox.py::bbox_iou, see scripts/make_golden_bbox_iou.py)."""
+(utils/bbox.py::bbox_iou, see tests/golden/make_golden_bbox_iou.py)."""
 import os
 
 import numpy as np

@@ -1,5 +1,5 @@
 """oracle/ref_post.py::hierarchical_nms against golden vectors produced by EXECUTING the reference's own
-hierarchical_nms / iou / CombinedDetection tree methods (scripts/make_golden_hier_nms.py): this row's parity is pinned."""
+hierarchical_nms / iou / CombinedDetection tree methods (tests/golden/make_golden_hier_nms.py): this row's parity is pinned."""
 import os
 
 import numpy as np

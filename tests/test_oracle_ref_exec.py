@@ -1,6 +1,6 @@
 """The oracle against golden vectors produced by EXECUTING the reference's own classes (YOLOOutputV3, the prefetch target
-generator, the dynamic generator + merger) over a numpy stand-in for the MXNet operators (scripts/make_golden_ref_exec.py,
-scripts/mx_shim.py).  Pins the reference's own logic -- slicing, row order, the per-GT loop, index math, _slice, merges."""
+generator, the dynamic generator + merger) over a numpy stand-in for the MXNet operators (tests/golden/make_golden_ref_exec.py,
+tests/golden/mx_shim.py).  Pins the reference's own logic -- slicing, row order, the per-GT loop, index math, _slice, merges."""
 import os
 
 import numpy as np

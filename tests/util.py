@@ -78,7 +78,7 @@ def make_gt(rng, B, M, size=416, num_class=20, multi_hot=False, min_count=0):
 
 
 def replay_shim_params(seed, kinds, shapes, has_bias):
-    """Re-draws the layer parameters scripts/mx_shim.py drew (same RandomState stream, same expressions, same order) when the
+    """Re-draws the layer parameters tests/golden/mx_shim.py drew (same RandomState stream, same expressions, same order) when the
     reference's YOLOV3.hybrid_forward was executed for tests/golden/ref_exec_golden.npz.  Returns a list of
     ('conv', weight, bias_or_None) / ('bn', gamma, beta, mean, var)."""
     rng = np.random.RandomState(seed)

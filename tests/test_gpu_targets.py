@@ -94,3 +94,30 @@ def test_config5_shapes_properties():
             np.testing.assert_array_equal(cls[b, r], ids[b, m])
     # oracle parity on a 2-image slice of the same batch
     compare(gt[:2], ids[:2], None, C)
+
+
+def test_full_size_cfg5_batch_independence_and_properties():
+    """BASELINE configs[4] at full size (B=128, M<=100, C=285 multi-hot): the oracle's Python loop is too slow for all 128 images,
+    so (a) four images are checked bit-exactly against the oracle run on them alone (images are independent), (b) the whole
+    batch through size-independent properties of the generator."""
+    rng = np.random.RandomState(2024)
+    C, B, M, size = 285, 128, 100, 416
+    gt, ids = make_gt(rng, B, M, size=size, num_class=C, multi_hot=True)
+    got = run_gpu(gt, ids, None, C, size)
+    obj, ctr, scl, wgt, cls, match, row = got
+    img, xs, anchors, offsets = ref_targets.default_generator_inputs(size)
+    for b in (0, 1, 63, 127):
+        ref = ref_targets.prefetch_targets(img, xs, anchors, offsets, gt[b:b + 1], ids[b:b + 1], None, num_class=C, return_assign=True)
+        np.testing.assert_array_equal(match[b], ref[5][0]); np.testing.assert_array_equal(row[b], ref[6][0])
+        np.testing.assert_array_equal(obj[b], ref[0][0]); np.testing.assert_array_equal(cls[b], ref[4][0])
+        for g, r in ((ctr[b], ref[1][0]), (scl[b], ref[2][0]), (wgt[b], ref[3][0])):
+            np.testing.assert_allclose(g, r, rtol=1e-6, atol=1e-6)
+    valid = (gt >= 0).all(-1)
+    assert ((row >= 0) == valid).all()                                   # every valid GT is assigned, no padded one is
+    pos = obj[..., 0] == 1
+    for b in range(B):
+        assert pos[b].sum() == len(set(row[b][row[b] >= 0].tolist()))    # one positive row per distinct assignment (last writer wins)
+    assert set(np.unique(obj).tolist()) <= {0.0, 1.0}
+    assert (cls[pos] >= 0).all() and (cls[pos].sum(-1) >= 1).all()       # positives carry their multi-hot row
+    assert (cls[~pos] == -1).all() and (ctr[~pos] == 0).all() and (wgt[~pos] == 0).all()
+    assert ((ctr[pos] >= 0) & (ctr[pos] < 1)).all() and ((wgt[pos] > 0) & (wgt[pos] <= 2)).all()

@@ -115,7 +115,7 @@ template <int EPI, int C, int NPAD> struct HeadCfg {
     static constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
     static constexpr int TMEM_STRIDE = NPAD <= 128 ? 128 : 256;
     // 3 groups (12 epilogue warps, 128 registers/thread) when three accumulators fit TMEM; else 2 groups
-    static constexpr int G = (EPI == EPI_FILTER && TMEM_STRIDE == 128) ? (NPAD <= 80 ? 4 : 3) : ((EPI == EPI_SPEC && TMEM_STRIDE == 128) ? VD_SPEC_G : 2);   // 4 groups only where 80 registers suffice
+    static constexpr int G = (EPI == EPI_FILTER && TMEM_STRIDE == 128) ? (NPAD <= 80 ? 4 : 3) : ((EPI == EPI_SPEC && TMEM_STRIDE == 128) ? (NPAD <= 96 ? VD_SPEC_G : 2) : 2);   // 4 groups only where 80 registers suffice; EPI_SPEC: 3 groups up to 96 columns, 2 (128 registers) above (measured: VOC 39.0 / 44.2 / 39.6 us with 3 / 2 / 4 groups, VID 47.4 / 46.3 / 51.8)
     // wide heads (two 256-column accumulators fill TMEM): SPLIT warpgroups drain ONE accumulator together, each taking every
     // SPLIT-th class chunk (the epilogue, not the mainloop, bounds these heads: 240 class logits per pixel at C = 80)
     static constexpr int SPLIT = (EPI == EPI_SPEC && TMEM_STRIDE == 256) ? VD_SPEC_SPLIT : 1;

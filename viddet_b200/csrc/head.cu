@@ -47,7 +47,10 @@ constexpr int kSpecCap = 2048;                // candidates per frame the specul
 #ifndef VD_SPEC_SPLIT
 #define VD_SPEC_SPLIT 2
 #endif
-constexpr int kFallbackCtas = 8;
+#ifndef VD_FALLBACK_CTAS
+#define VD_FALLBACK_CTAS 8
+#endif
+constexpr int kFallbackCtas = VD_FALLBACK_CTAS;
 constexpr int kSpecStage = 64;                // per-warp staging entries per tile (double-buffered); more go straight to global memory
 constexpr int kHeadSharedBytes = 2048;          // room for struct HeadShared (barriers, scheduler ring, per-group state)
 

@@ -69,27 +69,30 @@ def detection_block(x, cells, conv_type="2", round_fn=None):
 
 
 def upsample_concat(x, route):
-    """yolo3.py:515-519: `_upsample(x, 2)` (layers.py:10-20: repeat along W then H = nearest), `slice_like` crop to the route map,
-    concat in FRONT of the route along channels."""
+    """yolo3.py:515-519 / yolo3_temporal.py:502-506: `_upsample(x, 2)` (layers.py:10-20: repeat along W then H = nearest), `slice_like`
+    crop to the route map, concat in FRONT of the route along channels (axis -3: works for (B,C,H,W) and (B,T,C,H,W))."""
     x = np.asarray(x, f32)
     up = x.repeat(2, axis=-1).repeat(2, axis=-2)
     H, W = route.shape[-2:]
-    return np.concatenate([up[..., :H, :W], np.asarray(route, f32)], axis=1)
+    return np.concatenate([up[..., :H, :W], np.asarray(route, f32)], axis=-3)
 
 
-def yolo3_neck_tips(routes, blocks, transitions, round_fn=None):
-    """YOLOV3.hybrid_forward after the stages (yolo3.py:496-521), inference: routes = stage outputs shallow -> deep; blocks[i] =
-    list of 6 cell dicts of the i-th (deep -> shallow) YOLODetectionBlockV3, transitions[i] = cell dict of `_conv2d(channel,1,0,1)`.
-    Returns the tips deep -> shallow."""
+def yolo3_neck_tips(routes, blocks, transitions, round_fn=None, conv_type="2"):
+    """YOLOV3.hybrid_forward after the stages (yolo3.py:496-521) and its temporal twin (yolo3_temporal.py:448-506, t_out): routes =
+    stage outputs shallow -> deep, (B,C,H,W) or (B,T,C,H,W); blocks[i] = cell dicts of the i-th (deep -> shallow)
+    YOLODetectionBlockV3 (6 for conv_type '2'/'3', 9 for '21'), transitions[i] = cell dict of `_conv2d(channel,1,0,1)` (applied per
+    frame through TimeDistributed in the temporal net, :495-497).  Returns the tips deep -> shallow."""
     rf = round_fn if round_fn is not None else (lambda a: a)
     rts = list(routes)[::-1]
     x, tips = np.asarray(rts[0], f32), []
     for i, cells in enumerate(blocks):
-        x, tip = detection_block(x, cells, "2", round_fn=round_fn)
+        x, tip = detection_block(x, cells, conv_type, round_fn=round_fn)
         tips.append(tip)
         if i >= len(rts) - 1:
             break
         t = transitions[i]
-        x = rf(conv_bn_lrelu(x, t["weight"], t["gamma"], t["beta"], t["mean"], t["var"]))
-        x = upsample_concat(x, rts[i + 1])
+        lead = x.shape[:-3]
+        x4 = x.reshape((-1,) + x.shape[-3:])                                 # TimeDistributed 'reshape1'
+        x4 = rf(conv_bn_lrelu(x4, t["weight"], t["gamma"], t["beta"], t["mean"], t["var"]))
+        x = upsample_concat(x4.reshape(lead + x4.shape[1:]), rts[i + 1])
     return tips

@@ -5,6 +5,8 @@
   YOLOV3TargetMerger                    models/definitions/yolo/yolo_target.py:207-281
   TimeDistributed, TemporalPooling      models/definitions/layers.py:161-264
   YOLOV3 (+ YOLODetectionBlockV3, _conv2d, _upsample)   yolo3.py:202-534, layers.py:10-20,63-70  -- inference forward after the stages
+  YOLOV3Temporal (+ its YOLODetectionBlockV3 / YOLOOutputV3, Conv, _conv3d, _conv21d)   yolo3_temporal.py:25-555, layers.py:73-158
+                                                        -- t=5, t_out=True, conv type 21, inference forward after the stages
 over tests/golden/mx_shim.py (a numpy stand-in for the MXNet / GluonCV operators they call; MXNet itself cannot be imported here).
 The class sources are cut out of /root/reference with `ast` at run time and exec'd -- nothing is copied into the repo.
 What this pins: the reference's own logic (slicing, reshape/transposes = row order, the per-GT loop, index math, _slice,
@@ -169,6 +171,34 @@ def main():
     out["neck_param_shapes"] = np.array([list(e[1].shape) + [0] * (4 - e[1].ndim) for e in mx_shim.PARAM_LOG])
     out["neck_param_bias"] = np.array([1 if (e[0] == "conv" and e[2] is not None) else 0 for e in mx_shim.PARAM_LOG])
     out["neck_param_check"] = np.array([float(np.asarray(e[1], np.float64).sum()) for e in mx_shim.PARAM_LOG])
+    # ---------------- YOLOV3Temporal.hybrid_forward (inference), t=5, t_out=True, conv type 21: TimeDistributed stages / outputs /
+    # transitions, (2+1)D detection blocks with swapaxes around the 3-D convs, 5-D upsample + concat, 4-D box_nms and slice
+    ns = mx_shim.namespace()
+    load_classes("/root/reference/models/definitions/layers.py", ["_upsample", "_conv2d", "_conv3d", "_conv21d", "Conv", "TimeDistributed"], ns)
+    load_classes(os.path.join(REF, "yolo_target.py"), ["YOLOV3DynamicTargetGeneratorSimple", "YOLOV3TargetMerger"], ns)
+    YOLOV3Temporal, = load_classes(os.path.join(REF, "yolo3_temporal.py"), ["YOLOOutputV3", "YOLODetectionBlockV3", "YOLOV3Temporal"], ns)[2:]
+    C, B, T = 3, 1, 5
+    hw = [(8, 8), (4, 4), (2, 2)]
+    stage_ch = [64, 128, 192]
+    tfeats = [np.where((f := rng.standard_normal((B, T, c, h, w)).astype(f32)) > 0, f, 0.1 * f).astype(f32) for c, (h, w) in zip(stage_ch, hw)]
+    tfeats = [bf16_round(f) for f in tfeats]
+    tstages = [(lambda z, f=f: ND(f.reshape((-1,) + f.shape[2:]))) for f in tfeats]      # called through TimeDistributed: (B*T, C, H, W)
+    mx_shim.PARAM_LOG.clear()
+    mx_shim.PARAM_RNG.seed(78)
+    tnet = YOLOV3Temporal(tstages, [128, 128, 128], [[10, 13, 16, 30, 33, 23], [30, 61, 62, 45, 59, 119], [116, 90, 156, 198, 373, 326]],
+                          [8, 16, 32], classes=["c%d" % i for i in range(C)], t=5, t_out=True, conv=21)
+    tids, tscores, tbboxes = tnet.hybrid_forward(F, ND(np.zeros((B, T, 3, 64, 64), f32)))
+    tnet.nms_thresh = 0
+    rid, rsc, rbb = tnet.hybrid_forward(F, ND(np.zeros((B, T, 3, 64, 64), f32)))
+    out.update({"tneck_ids": tids.asnumpy(), "tneck_scores": tscores.asnumpy(), "tneck_bboxes": tbboxes.asnumpy(),
+                "tneck_det": np.concatenate([rid.asnumpy(), rsc.asnumpy(), rbb.asnumpy()], -1),
+                "tneck_meta": np.array([C, B, T, len(mx_shim.PARAM_LOG)])})
+    for i, f in enumerate(tfeats):
+        out["tneck_feat%d" % i] = f
+    out["tneck_param_kinds"] = np.array([0 if e[0] == "conv" else 1 for e in mx_shim.PARAM_LOG])
+    out["tneck_param_shapes"] = np.array([list(e[1].shape) + [0] * (5 - e[1].ndim) for e in mx_shim.PARAM_LOG])
+    out["tneck_param_bias"] = np.array([1 if (e[0] == "conv" and e[2] is not None) else 0 for e in mx_shim.PARAM_LOG])
+    out["tneck_param_check"] = np.array([float(np.asarray(e[1], np.float64).sum()) for e in mx_shim.PARAM_LOG])
     out["n_dec"] = np.array(len(dec_cases)); out["n_tg"] = np.array(len(tg_cases))
     np.savez_compressed(OUT, **out)
     print("wrote", OUT, os.path.getsize(OUT), "bytes")

@@ -73,6 +73,9 @@ class ND:
     def squeeze(self, axis=None):
         return ND(np.squeeze(self.a, axis=axis))
 
+    def swapaxes(self, a1, a2):
+        return ND(np.ascontiguousarray(np.swapaxes(self.a, a1, a2)))
+
     def argmax(self, axis):
         return ND(np.argmax(self.a, axis=axis).astype(f32))          # first maximum; MXNet returns fp32 indices
 
@@ -153,6 +156,10 @@ class F:
     max = staticmethod(lambda x, axis=None, keepdims=False: x.max(axis=axis, keepdims=keepdims))
     mean = staticmethod(lambda x, axis=None, keepdims=False: ND(x.a.mean(axis=axis, keepdims=keepdims, dtype=f32)))
     squeeze = staticmethod(lambda x, axis=None: x.squeeze(axis=axis))
+    swapaxes = staticmethod(lambda x, dim1=0, dim2=0: x.swapaxes(dim1, dim2))
+    repeat = staticmethod(lambda x, repeats=1, axis=None: x.repeat(repeats, axis=axis))
+    expand_dims = staticmethod(lambda x, axis: x.expand_dims(axis))
+    slice_axis = staticmethod(lambda x, axis, begin, end: x.slice_axis(axis, begin, end))
 
     @staticmethod
     def reshape_like(lhs, rhs, lhs_begin=None, lhs_end=None, rhs_begin=None, rhs_end=None):
@@ -251,6 +258,36 @@ class _Conv2D:
         return ND(y.astype(f32))
 
 
+class _Conv3D:
+    """nn.Conv3D on (B, C, T, H, W): fp32 cross-correlation, stride 1, zero 'same' padding, no bias; kernel extents 1 or 3.
+    Weights (Co, Ci, kt, kh, kw) drawn at the first call and logged like _Conv2D."""
+
+    def __init__(self, channels, kernel_size=1, strides=1, padding=0, use_bias=True, groups=1, **kw):
+        k = (kernel_size,) * 3 if isinstance(kernel_size, int) else tuple(kernel_size)
+        p_ = (padding,) * 3 if isinstance(padding, int) else tuple(padding)
+        s_ = (strides,) * 3 if isinstance(strides, int) else tuple(strides)
+        assert s_ == (1, 1, 1) and p_ == tuple(e // 2 for e in k) and not use_bias and groups == 1, "shim conv3d: stride 1, 'same', no bias"
+        self.channels, self.k, self.weight = channels, k, None
+
+    def __call__(self, x):
+        cin = x.shape[1]
+        kt, kh, kw = self.k
+        if self.weight is None:
+            fan = cin * kt * kh * kw
+            self.weight = _bf16_round((PARAM_RNG.standard_normal((self.channels, cin, kt, kh, kw)) * np.sqrt(2.0 / fan)).astype(f32))
+            PARAM_LOG.append(("conv", self.weight, None))
+        B, _, T, H, W = x.shape
+        pt, ph, pw = kt // 2, kh // 2, kw // 2
+        xp = np.zeros((B, cin, T + 2 * pt, H + 2 * ph, W + 2 * pw), f32)
+        xp[:, :, pt:pt + T, ph:ph + H, pw:pw + W] = x.a
+        y = np.zeros((B, self.channels, T, H, W), f32)
+        for i in range(kt):
+            for j in range(kh):
+                for k in range(kw):
+                    y += np.einsum("nk,bkthw->bnthw", self.weight[:, :, i, j, k], xp[:, :, i:i + T, j:j + H, k:k + W], optimize=True).astype(f32)
+        return ND(y.astype(f32))
+
+
 class BatchNorm:
     """Inference BatchNorm over axis 1: (x - mean) / sqrt(var + eps) * gamma + beta (fp32); statistics drawn at the first call."""
 
@@ -299,6 +336,7 @@ class _HybridSequential:
 
 class nn:
     Conv2D = _Conv2D
+    Conv3D = _Conv3D
     BatchNorm = BatchNorm
     LeakyReLU = _LeakyReLU
     HybridSequential = _HybridSequential
@@ -352,6 +390,7 @@ class BBoxBatchIOU:
 def namespace():
     """Globals for exec'ing the reference classes."""
     import warnings
-    return {"np": np, "nd": F, "gluon": gluon, "nn": nn, "autograd": autograd, "warnings": warnings, "BatchNorm": BatchNorm,
+    import math
+    return {"np": np, "math": math, "nd": F, "gluon": gluon, "nn": nn, "autograd": autograd, "warnings": warnings, "BatchNorm": BatchNorm,
             "YOLOV3Loss": type("YOLOV3Loss", (), {}),
             "BBoxCornerToCenter": BBoxCornerToCenter, "BBoxCenterToCorner": BBoxCenterToCorner, "BBoxBatchIOU": BBoxBatchIOU}

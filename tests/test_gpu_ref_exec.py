@@ -134,3 +134,40 @@ def test_yolov3_neck_vs_executed_reference():
     # the top detections agree with the reference's wherever the score gap exceeds the bf16 noise
     gs, s = G["neck_scores"][..., 0], scores.cpu().numpy()[..., 0]
     np.testing.assert_allclose(s[:, :10], gs[:, :10], rtol=5e-2)
+
+
+def test_yolov3_temporal_neck_vs_executed_reference():
+    """YOLOV3Neck(conv_type='21') on (B,T,C,H,W) routes against the executed YOLOV3Temporal forward (t=5, t_out): (2+1)D blocks,
+    per-frame transitions and output layers, 5-D upsample + concat, (B,T,100,.) detections."""
+    import viddet_b200
+    from oracle import ref_block, ref_head
+    from tests.test_oracle_ref_exec import tneck_params
+    from tests.util import bf16_round
+    C, B, T, _ = [int(v) for v in G["tneck_meta"]]
+    blocks, transitions, preds = tneck_params()
+    feats = [G["tneck_feat%d" % i] for i in range(3)]
+    neck = viddet_b200.YOLOV3Neck(C, channels=(128, 128, 128), stage_channels=(64, 128, 192), conv_type="21")
+    for blk, cells in zip(neck.yolo_blocks, blocks):
+        assert len(blk.cells()) == len(cells) == 9
+        for cell, p in zip(blk.cells(), cells):
+            cell.set_data(torch.from_numpy(p["weight"]), p["gamma"], p["beta"], p["mean"], p["var"])
+    for cell, p in zip(neck.transitions, transitions):
+        cell.set_data(torch.from_numpy(p["weight"]), p["gamma"], p["beta"], p["mean"], p["var"])
+    for o, (w, b) in zip(neck.yolo_outputs, preds):
+        o.prediction.set_data(torch.from_numpy(w), torch.from_numpy(b))
+    routes = [cuda(f) for f in feats]
+    det = neck.detections(routes).cpu().numpy()
+    tips = ref_block.yolo3_neck_tips(feats, blocks, transitions, round_fn=bf16_round, conv_type="21")
+    ref = ref_head.head_detections([t.reshape((B * T,) + t.shape[2:]) for t in tips], [p[0] for p in preds], [p[1] for p in preds], C)
+    ref = ref.reshape(B, T, -1, 6)
+    gold = G["tneck_det"]
+    assert det.shape == ref.shape == gold.shape
+    np.testing.assert_array_equal(det[..., 0], ref[..., 0])
+    assert np.abs(det[..., 1] - ref[..., 1]).max() <= 5e-2 * ref[..., 1].max()          # 28 convs with bf16 carriers
+    assert np.abs(det[..., 1] - ref[..., 1]).mean() <= 3e-3 * ref[..., 1].max()
+    assert np.abs(det[..., 1] - gold[..., 1]).max() <= 1e-1 * gold[..., 1].max()
+    assert np.abs(det[..., 1] - gold[..., 1]).mean() <= 6e-3 * gold[..., 1].max()
+    ids, scores, boxes = neck(routes)
+    assert tuple(ids.shape) == G["tneck_ids"].shape == (B, T, 100, 1)
+    gs, s = G["tneck_scores"][..., 0], scores.cpu().numpy()[..., 0]
+    np.testing.assert_allclose(s[..., :5], gs[..., :5], rtol=8e-2)

@@ -123,3 +123,48 @@ def test_yolov3_forward_after_stages_matches_executed_reference():
     np.testing.assert_array_equal(out[..., 0:1], G["neck_ids"])
     np.testing.assert_array_equal(out[..., 1:2], G["neck_scores"])
     np.testing.assert_array_equal(out[..., 2:], G["neck_bboxes"])
+
+
+def tneck_params():
+    from tests.util import replay_shim_params
+    ps = replay_shim_params(78, G["tneck_param_kinds"], G["tneck_param_shapes"], G["tneck_param_bias"])
+    chk = np.array([float(np.asarray(p[1], np.float64).sum()) for p in ps])
+    np.testing.assert_array_equal(chk, G["tneck_param_check"])
+    it = iter(ps)
+
+    def cell():
+        c, b = next(it), next(it)
+        assert c[0] == "conv" and b[0] == "bn" and c[2] is None
+        return dict(weight=c[1], gamma=b[1], beta=b[2], mean=b[3], var=b[4])
+    blocks, transitions, preds = [], [], []
+    for i in range(3):                       # yolo3_temporal.py:448-497: (2+1)D block i (9 cells), output i, then transition i
+        blocks.append([cell() for _ in range(9)])
+        p = next(it)
+        assert p[0] == "conv" and p[2] is not None
+        preds.append((p[1], p[2]))
+        if i < 2:
+            transitions.append(cell())
+    assert next(it, None) is None
+    return blocks, transitions, preds
+
+
+def test_yolov3_temporal_forward_matches_executed_reference():
+    """YOLOV3Temporal.hybrid_forward (t=5, t_out, conv type 21) executed from the reference source: TimeDistributed stages / output
+    layers / transitions, (2+1)D detection blocks (swapaxes around the 3-D convs), 5-D upsample + concat, box_nms over (B,T,rows,6)."""
+    from oracle import ref_block, ref_nms, ref_temporal
+    C, B, T, _ = [int(v) for v in G["tneck_meta"]]
+    blocks, transitions, preds = tneck_params()
+    feats = [G["tneck_feat%d" % i] for i in range(3)]
+    tips = ref_block.yolo3_neck_tips(feats, blocks, transitions, conv_type="21")
+    assert [t.shape for t in tips] == [(B, T, 256, 2, 2), (B, T, 256, 4, 4), (B, T, 256, 8, 8)]
+    head = lambda *frames: ref_head.head_detections(list(frames), [p[0] for p in preds], [p[1] for p in preds], C)
+    det = head(*[t.reshape((B * T,) + t.shape[2:]) for t in tips]).reshape(B, T, -1, 6)        # TimeDistributed(output), concat dim -2
+    gold = G["tneck_det"]
+    assert det.shape == gold.shape
+    np.testing.assert_array_equal(det[..., 0], gold[..., 0])
+    np.testing.assert_allclose(det[..., 1], gold[..., 1], rtol=3e-4, atol=1e-6)
+    np.testing.assert_allclose(det[..., 2:], gold[..., 2:], rtol=3e-4, atol=3e-3)
+    out = ref_nms.box_nms(gold, overlap_thresh=0.45, valid_thresh=0.01, topk=400, id_index=0, score_index=1, coord_start=2)[..., :100, :]
+    np.testing.assert_array_equal(out[..., 0:1], G["tneck_ids"])
+    np.testing.assert_array_equal(out[..., 1:2], G["tneck_scores"])
+    np.testing.assert_array_equal(out[..., 2:], G["tneck_bboxes"])

@@ -85,8 +85,8 @@ def replay_shim_params(seed, kinds, shapes, has_bias):
     out = []
     for kind, shp, hb in zip(kinds, shapes, has_bias):
         if int(kind) == 0:
-            shp = tuple(int(v) for v in shp)
-            fan = shp[1] * shp[2] * shp[3]
+            shp = tuple(int(v) for v in shp if int(v) > 0)        # (Co, Ci, kh, kw) or (Co, Ci, kt, kh, kw); zero-padded in the file
+            fan = int(np.prod(shp[1:]))
             w = bf16_round((rng.standard_normal(shp) * np.sqrt(2.0 / fan)).astype(np.float32))
             b = rng.uniform(-0.2, 0.2, shp[0]).astype(np.float32) if int(hb) else None
             out.append(("conv", w, b))

@@ -865,8 +865,13 @@ class YOLOV3Loss:
 # post-processing of detect()
 # ------------------------------------------------------------------------------------------------
 def upsample_concat(x, route):
-    """yolo3.py:515-519: concat(slice_like(_upsample(x, 2), route, axes=(2,3)), route, dim=1) on channels-last bf16 carriers."""
+    """yolo3.py:515-519 / yolo3_temporal.py:500-506: concat(slice_like(_upsample(x, 2), route, axes=(-2,-1)), route, dim=-3) on
+    channels-last bf16 carriers; (B,C,H,W) or (B,T,C,H,W) (frames are independent)."""
     _require_cuda(x, "x"); _require_cuda(route, "route")
+    if x.dim() == 5:
+        B_, T_ = x.shape[0], x.shape[1]
+        out = upsample_concat(x.reshape((B_ * T_,) + tuple(x.shape[2:])), route.reshape((B_ * T_,) + tuple(route.shape[2:])))
+        return out.reshape((B_, T_) + tuple(out.shape[1:]))
     xb, rb = to_nhwc_bf16(x), to_nhwc_bf16(route)
     B, C1, H, W = xb.shape
     B2, C2, H2, W2 = rb.shape
@@ -885,7 +890,12 @@ class YOLOV3Neck:
     order, nms parameters); Gluon infers the input channels lazily, here `stage_channels` (shallow -> deep) states them."""
 
     def __init__(self, classes, channels=(512, 256, 128), stage_channels=(256, 512, 1024), anchors=None, strides=None,
-                 nms_thresh=0.45, nms_topk=400, post_nms=100):
+                 nms_thresh=0.45, nms_topk=400, post_nms=100, conv_type="2"):
+        """conv_type '2': YOLOV3 (routes (B,C,H,W)); '3' / '21': YOLOV3Temporal with t_out (yolo3_temporal.py:448-555): routes
+        (B,T,C,H,W), 3-D / (2+1)D detection blocks, transitions and output layers applied per frame (TimeDistributed), detections
+        (B,T,post,.)."""
+        assert conv_type in ("2", "3", "21")
+        self._conv_type = conv_type
         n = len(channels)
         assert len(stage_channels) == n
         self.channels = list(channels)
@@ -893,7 +903,7 @@ class YOLOV3Neck:
         self.yolo_blocks, self.transitions = [], []
         for i, ch in enumerate(self.channels):
             cin = deep_first[i] if i == 0 else self.channels[i] + deep_first[i]      # transition i-1 emits channels[i] (yolo3.py:425-427)
-            self.yolo_blocks.append(YOLODetectionBlockV3(ch, "2", in_channels=cin))
+            self.yolo_blocks.append(YOLODetectionBlockV3(ch, conv_type, in_channels=cin))
             if i > 0:
                 self.transitions.append(ConvBNLReLU(self.channels[i - 1], ch, (1, 1, 1)))
         self.head = YOLOV3Head(classes, anchors=anchors, strides=strides, channels=[2 * c for c in self.channels],
@@ -920,7 +930,12 @@ class YOLOV3Neck:
             tips.append(tip)
             if i >= len(routes) - 1:
                 break
-            x = self.transitions[i](x)
+            if x.dim() == 5:                                           # TimeDistributed(self.transitions[i]) (yolo3_temporal.py:495-497)
+                B_, T_ = x.shape[0], x.shape[1]
+                x = self.transitions[i](x.reshape((B_ * T_,) + tuple(x.shape[2:])))
+                x = x.reshape((B_, T_) + tuple(x.shape[1:]))
+            else:
+                x = self.transitions[i](x)
             x = upsample_concat(x, routes[i + 1])
         return tips
 

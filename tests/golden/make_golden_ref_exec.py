@@ -161,6 +161,16 @@ def main():
     ids, scores, bboxes = net.hybrid_forward(F, ND(np.zeros((B, 3, 128, 128), f32)))
     net.nms_thresh = 0                                             # yolo3.py:525: NMS skipped -> the plain concat of the decoded rows
     rid, rsc, rbb = net.hybrid_forward(F, ND(np.zeros((B, 3, 128, 128), f32)))
+    # the training-mode branch without a recorded loss (yolo3.py:498-509,532-535): raw predictions concatenated over the scales
+    net.nms_thresh = 0.45
+    mx_shim.autograd.training = True
+    raw = net.hybrid_forward(F, ND(np.zeros((B, 3, 128, 128), f32)))
+    mx_shim.autograd.training = False
+    for k, r in zip(("box_preds", None, None, None, "box_centers", "box_scales", "objness", "class_pred"), raw):
+        if k is not None:
+            out["neck_train_" + k] = r.asnumpy()
+    out["neck_train_fmap_shapes"] = np.array([m.shape for m in raw[3]])
+    out["neck_train_offsets_sizes"] = np.array([m.size for m in raw[2]])
     out.update({"neck_ids": ids.asnumpy(), "neck_scores": scores.asnumpy(), "neck_bboxes": bboxes.asnumpy(),
                 "neck_det": np.concatenate([rid.asnumpy(), rsc.asnumpy(), rbb.asnumpy()], -1),
                 "neck_meta": np.array([C, B, len(mx_shim.PARAM_LOG)])})

@@ -171,3 +171,42 @@ def test_yolov3_temporal_neck_vs_executed_reference():
     assert tuple(ids.shape) == G["tneck_ids"].shape == (B, T, 100, 1)
     gs, s = G["tneck_scores"][..., 0], scores.cpu().numpy()[..., 0]
     np.testing.assert_allclose(s[..., :5], gs[..., :5], rtol=8e-2)
+
+
+def test_training_branch_on_device_vs_executed_reference():
+    """YOLOV3Head.train_outputs (the raw-prediction tuple of yolo3.py:532-535) against the executed training branch, and
+    train_forward (target merger + loss on those predictions) against the oracle's loss on the same tensors."""
+    import viddet_b200
+    from oracle import ref_block, ref_loss, ref_targets
+    from tests.test_oracle_ref_exec import neck_params, train_outputs_oracle
+    from tests.util import bf16_round
+    C, B, _ = [int(v) for v in G["neck_meta"]]
+    blocks, transitions, preds = neck_params()
+    feats = [G["neck_feat%d" % i] for i in range(3)]
+    tips_ref = [bf16_round(t) for t in ref_block.yolo3_neck_tips(feats, blocks, transitions)]      # same tips for both sides
+    head = viddet_b200.YOLOV3Head(C, channels=[256, 256, 256])
+    for o, (w, b) in zip(head.yolo_outputs, preds):
+        o.prediction.set_data(torch.from_numpy(w), torch.from_numpy(b))
+    tips = [cuda(t) for t in tips_ref]
+    out = head.train_outputs(tips)
+    ref = train_outputs_oracle(tips_ref, preds, C)
+    for g, r, k in zip((out[0], out[4], out[5], out[6], out[7]), ref, ("box_preds", "box_centers", "box_scales", "objness", "class_pred")):
+        g = g.cpu().numpy()
+        assert g.shape == r.shape == G["neck_train_" + k].shape, k
+        np.testing.assert_allclose(g, r, rtol=1e-3, atol=1e-2, err_msg=k)            # bf16 conv operands, fp32 accumulate
+    assert [tuple(m.shape) for m in out[3]] == [tuple(s_) for s_ in G["neck_train_fmap_shapes"]]
+    assert [int(o.numel()) for o in out[2]] == [int(v) for v in G["neck_train_offsets_sizes"]]
+    # recorded branch: targets for a few boxes -> merger -> loss, device vs oracle on the device's own predictions
+    rng = np.random.RandomState(9)
+    gt = np.full((B, 6, 4), -1.0, np.float32); ids = np.full((B, 6, 1), -1.0, np.float32)
+    for b in range(B):
+        xy = rng.uniform(5, 70, (4, 2)); wh = rng.uniform(10, 50, (4, 2))
+        gt[b, :4] = np.concatenate([xy, xy + wh], 1); ids[b, :4, 0] = rng.randint(0, C, 4)
+    img, xs, anchors, offsets = ref_targets.default_generator_inputs(128)
+    pf = ref_targets.prefetch_targets((B,) + tuple(img[1:]), xs, anchors, offsets, gt, ids, None, num_class=C)
+    losses = head.train_forward(tips, cuda(gt), *[cuda(t) for t in pf])
+    o_np = [t.cpu().numpy() for t in (out[6], out[4], out[5], out[7])]
+    merged = ref_loss.target_merge(out[0].cpu().numpy(), gt, *pf, num_class=C, ignore_iou_thresh=0.7)
+    ref_l = ref_loss.yolo3_loss(*o_np, *merged)
+    for l, r in zip(losses, ref_l):
+        np.testing.assert_allclose(l.cpu().numpy(), r, rtol=1e-4, atol=1e-6)

@@ -168,3 +168,25 @@ def test_yolov3_temporal_forward_matches_executed_reference():
     np.testing.assert_array_equal(out[..., 0:1], G["tneck_ids"])
     np.testing.assert_array_equal(out[..., 1:2], G["tneck_scores"])
     np.testing.assert_array_equal(out[..., 2:], G["tneck_bboxes"])
+
+
+def train_outputs_oracle(tips, preds, C):
+    """yolo3.py:498-509,532-535 on oracle pieces: per-scale train-mode 7-tuples, reshape((0,-3,-1)), concat over the scales."""
+    outs = [ref_head.yolo_output_v3(t, w, b, ANCHORS[i], STRIDES[i], C, "train") for i, (t, (w, b)) in enumerate(zip(tips, preds))]
+    B = tips[0].shape[0]
+    cat = lambda j, last: np.concatenate([np.asarray(o[j]).reshape(B, -1, last) for o in outs], axis=1)
+    return cat(0, 4), cat(1, 2), cat(2, 2), cat(3, 1), cat(4, C)
+
+
+def test_training_branch_raw_predictions_match_executed_reference():
+    from oracle import ref_block
+    C, B, _ = [int(v) for v in G["neck_meta"]]
+    blocks, transitions, preds = neck_params()
+    feats = [G["neck_feat%d" % i] for i in range(3)]
+    tips = ref_block.yolo3_neck_tips(feats, blocks, transitions)
+    got = train_outputs_oracle(tips, preds, C)
+    for g, k in zip(got, ("box_preds", "box_centers", "box_scales", "objness", "class_pred")):
+        gold = G["neck_train_" + k]
+        assert g.shape == gold.shape, k
+        np.testing.assert_allclose(g, gold, rtol=3e-4, atol=3e-3, err_msg=k)
+    np.testing.assert_array_equal(G["neck_train_fmap_shapes"], [[1, 1, 4, 4], [1, 1, 8, 8], [1, 1, 16, 16]])

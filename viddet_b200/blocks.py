@@ -601,6 +601,30 @@ class YOLOV3Head:
         per-call Python work (and can be captured into a CUDA graph)."""
         return HeadSession(self, tips, return_keep, out)
 
+    def train_outputs(self, tips):
+        """The training-mode branch of YOLOV3.hybrid_forward without a recorded loss (yolo3.py:498-509,532-535): per scale the
+        output layer's 7-tuple, the raw parts flattened with reshape((0,-3,-1)) and concatenated over the scales (deep -> shallow).
+        Returns (box_preds (B,N,4), all_anchors, all_offsets, all_feat_maps [(1,1,H,W) fake maps], box_centers (B,N,2),
+        box_scales (B,N,2), objness (B,N,1), class_pred (B,N,C)), N = 3*sum(HW) -- the row order of the prefetched targets."""
+        dets, centers, scales, objs, clss, ancs, offs, fmaps = [], [], [], [], [], [], [], []
+        for t, o in zip(tips, self.yolo_outputs):
+            _require_cuda(t, "tip")
+            bbox, rc, rs, ob, cp, an, of = o(t, training=True)
+            B = bbox.shape[0]
+            dets.append(bbox); centers.append(rc.reshape(B, -1, 2)); scales.append(rs.reshape(B, -1, 2))
+            objs.append(ob.reshape(B, -1, 1)); clss.append(cp.reshape(B, -1, cp.shape[-1]))
+            ancs.append(an); offs.append(of)
+            fmaps.append(torch.zeros((1, 1, t.shape[-2], t.shape[-1]), device=bbox.device))
+        cat = lambda xs: torch.cat(xs, dim=1)
+        return cat(dets), ancs, offs, fmaps, cat(centers), cat(scales), cat(objs), cat(clss)
+
+    def train_forward(self, tips, gt_boxes, obj_t, centers_t, scales_t, weights_t, clas_t, ignore_iou_thresh=0.7):
+        """The recorded training branch (yolo3.py:510-516): losses = YOLOV3Loss(preds + YOLOV3TargetMerger(box_preds, gt, prefetched
+        targets)) -> (obj_loss, center_loss, scale_loss, cls_loss), forward values, all on the device."""
+        box_preds, _, _, _, centers, scales, objness, cls_pred = self.train_outputs(tips)
+        merged = YOLOV3TargetMerger(self._num_class, ignore_iou_thresh)(box_preds, gt_boxes, obj_t, centers_t, scales_t, weights_t, clas_t)
+        return YOLOV3Loss()(objness, centers, scales, cls_pred, *merged)
+
     def detections(self, tips):
         """The concatenated (B[,T], rows, 6) tensor of yolo3.py:523 (before NMS)."""
         p, flat, scratch, lead = self._prepare(tips)

@@ -467,7 +467,10 @@ extern "C" int vd_conv_bn_lrelu(const void* x, void* y, int B, int T, int H, int
     VD_CHECK_ARG(Cout >= 128 && Cout % 128 == 0 && Cout <= 1024, "conv_bn_lrelu: Cout = %d must be a multiple of 128, at most 1024", Cout);
     VD_CHECK_ARG(((uintptr_t)x & 15) == 0 && ((uintptr_t)y & 15) == 0 && ((uintptr_t)weight & 15) == 0, "conv_bn_lrelu: tensors must be 16-byte aligned");   // (an empty batch may pass null x / y)
     if (B == 0) return VD_OK;
-    const int NT = (Cout % 256 == 0) ? 256 : 128;
+    int NT = (Cout % 256 == 0) ? 256 : 128;
+    // pointwise cells are short (85-1352 M tiles, K <= 1024): 128-wide channel blocks balance the 148 SMs better than 256-wide
+    // pairs (same-box A/B: 22.0 -> 20.3 us at s32, 25.6 -> 21.9 us at s16); VD_CONV_1X1_NT256=1 restores the wide tiles
+    if (kt == 1 && kh == 1 && kw == 1 && !getenv("VD_CONV_1X1_NT256")) NT = 128;
     ConvParams p;
     p.kt = kt; p.kh = kh; p.kw = kw; p.Cin = Cin; p.Cout = Cout;
     if (kt == 1 && kh == 1 && kw == 1) {          // pointwise: one flat row axis, full 128-row tiles

@@ -1000,6 +1000,11 @@ class ClassTree:
         self.branch = torch.as_tensor(np.asarray(branch), dtype=torch.uint8).cuda().contiguous()
         self.num_class = int(self.levels.numel())
         assert self.parent.numel() == self.num_class and tuple(self.branch.shape) == (self.num_class, self.num_class)
+        par = np.asarray(parent).astype(np.int64)
+        if ((par >= self.num_class) | (par < -1)).any():            # the device walks parent[] without bounds checks
+            raise ValueError("ClassTree: parent indices must be in [-1, num_class)")
+        if (par == np.arange(self.num_class)).any():
+            raise ValueError("ClassTree: a class cannot be its own parent")
         self.min_level = int(np.asarray(levels).min()) if self.num_class else 0
 
     @staticmethod

@@ -251,7 +251,7 @@ hier_nms_kernel(const float* __restrict__ rows, const int32_t* __restrict__ coun
         const float conf = R[i * 6 + 1];
         if ((double)conf < conf_thresh) continue;
         if (cls < 0 || cls >= C) continue;                                   // not a class of the tree (the reference would raise)
-        while (levels[cls] > level_thresh && parent[cls] >= 0) cls = parent[cls];
+        for (int hop = 0; hop < C && levels[cls] > level_thresh && parent[cls] >= 0; ++hop) cls = parent[cls];   // bounded: inconsistent tables must not hang the GPU
         const float4 bx = make_float4(R[i * 6 + 2], R[i * 6 + 3], R[i * 6 + 4], R[i * 6 + 5]);
         double best = 0.0; int bidx = -1;
         for (int k = lane; k < m; k += 32) {

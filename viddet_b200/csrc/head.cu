@@ -130,7 +130,10 @@ template <int EPI, int C, int NPAD> struct HeadCfg {
     #ifndef VD_SPEC_SMEM_KB
 #define VD_SPEC_SMEM_KB 181
 #endif
-    static constexpr int SMEM_BUDGET = ((EPI == EPI_SPEC) ? VD_SPEC_SMEM_KB : ((EPI == EPI_FILTER) ? 181 : 225)) * 1024;
+#ifndef VD_SPEC_SMEM_KB_WIDE
+#define VD_SPEC_SMEM_KB_WIDE VD_SPEC_SMEM_KB
+#endif
+    static constexpr int SMEM_BUDGET = ((EPI == EPI_SPEC) ? (TMEM_STRIDE == 256 ? VD_SPEC_SMEM_KB_WIDE : VD_SPEC_SMEM_KB) : ((EPI == EPI_FILTER) ? 181 : 225)) * 1024;
     static constexpr int STAGES_RAW = (SMEM_BUDGET - EPI_BYTES - 1024) / STAGE_BYTES;
     static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
     static constexpr int TMEM_COLS = (G * TMEM_STRIDE) <= 256 ? 256 : 512;

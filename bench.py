@@ -206,7 +206,7 @@ def run_reference(args):
     ws, bs = make_pred_weights(rng, C)
     threads = os.cpu_count() or 1
     for _ in range(max(args.warmup, 1)):
-        cpu_baseline.head_forward_cpu([t[:2] for t in tips], ws, bs, C, threads=threads)
+        cpu_baseline.head_forward_cpu(tips, ws, bs, C, threads=threads)           # warm-up at the timed shape (oneDNN primitive creation)
     t0 = time.perf_counter()
     for _ in range(args.steps):
         cpu_baseline.head_forward_cpu(tips, ws, bs, C, threads=threads)
@@ -428,7 +428,7 @@ def main():
         threads = os.cpu_count() or 1
         ctips = make_tips(rng, args.cpu_frames, size=size)
         cws, cbs = make_pred_weights(rng, C)
-        cpu_baseline.head_forward_cpu([t[:2] for t in ctips], cws, cbs, C, threads=threads)
+        cpu_baseline.head_forward_cpu(ctips, cws, cbs, C, threads=threads)      # untimed warm-up at the timed shape (oneDNN primitive creation)
         reps = 12                                     # ~8-10 s of CPU work on the box's host cores
         fps, secs, nfr = cpu_baseline.time_head_cpu(ctips, cws, cbs, C, repeats=reps, threads=threads)
         cpu = {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port",

@@ -429,7 +429,7 @@ def main():
         ctips = make_tips(rng, args.cpu_frames, size=size)
         cws, cbs = make_pred_weights(rng, C)
         cpu_baseline.head_forward_cpu(ctips, cws, cbs, C, threads=threads)      # untimed warm-up at the timed shape (oneDNN primitive creation)
-        reps = 12                                     # ~8-10 s of CPU work on the box's host cores
+        reps = 24                                     # ~10 s of CPU work on the box's host cores
         fps, secs, nfr = cpu_baseline.time_head_cpu(ctips, cws, cbs, C, repeats=reps, threads=threads)
         cpu = {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port",
                "sample": "%d passes over %d synthetic %s frames (%.1f s); torch/oneDNN conv + numpy decode + C box_nms"

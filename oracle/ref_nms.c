@@ -6,7 +6,9 @@
  * its published algorithm.  The reference's call sites are
  *   models/definitions/yolo/yolo3.py:526-528 (x5) and yolo3_temporal.py:545-547   (box_nms)
  *   models/definitions/yolo/yolo_target.py:92                                     (box_iou)
- * Pinned by: the two upstream operator-doc examples (tests/test_oracle_kat.py).
+ * Pinned by: the two upstream operator-doc examples (tests/test_oracle_kat.py); every assumption about the upstream operator is
+ * listed with its known-answer test in oracle/ASSUMPTIONS.md; cross-checked on tie-free inputs against an independent
+ * implementation (torchvision.ops.nms per class, tests/test_oracle_crosscheck.py).
  *
  * Build:  make -C oracle        (gcc -O2 -ffp-contract=off; fp32 op order is part of the spec)
  */
@@ -37,6 +39,15 @@ static float intersect_1d(const float* a, const float* b, int encode) {
     right = a2 < b2 ? a2 : b2;
     w = right - left;
     return w > 0 ? w : 0;
+}
+
+/* BoxArea(): width * height, 0 when either extent is negative (upstream clamps degenerate boxes; oracle/ASSUMPTIONS.md A3).
+ * encode 0: (x1,y1,x2,y2); 1: (x,y,w,h). */
+static float box_area(const float* bx, int encode) {
+    float w = encode == 0 ? bx[2] - bx[0] : bx[2];
+    float h = encode == 0 ? bx[3] - bx[1] : bx[3];
+    if (w < 0 || h < 0) return 0.0f;
+    return w * h;
 }
 
 /* data (num_batch, num_elem, width) fp32 -> out same shape, record (num_batch, num_elem) int32
@@ -79,7 +90,7 @@ int ref_box_nms(const float* data, int64_t num_batch, int64_t num_elem, int widt
         /* 4. areas */
         for (r = 0; r < n; ++r) {
             const float* bx = in + (int64_t)keys[r].idx * width + coord_start;
-            area[r] = (in_format == 0) ? (bx[2] - bx[0]) * (bx[3] - bx[1]) : bx[2] * bx[3];
+            area[r] = box_area(bx, in_format);
             dead[r] = 0;
         }
         /* 5. greedy suppression in rank order */
@@ -126,10 +137,10 @@ int ref_box_iou(const float* lhs, int64_t n, const float* rhs, int64_t m, float*
     int64_t i, j;
     for (i = 0; i < n; ++i) {
         const float* a = lhs + 4 * i;
-        float al = (a[2] - a[0]) * (a[3] - a[1]);
+        float al = box_area(a, 0);
         for (j = 0; j < m; ++j) {
             const float* b = rhs + 4 * j;
-            float ar = (b[2] - b[0]) * (b[3] - b[1]);
+            float ar = box_area(b, 0);
             float inter = intersect_1d(a, b, 0) * intersect_1d(a + 1, b + 1, 0);
             out[i * m + j] = (inter <= 0) ? 0.0f : inter / (al + ar - inter);
         }

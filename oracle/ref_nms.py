@@ -118,7 +118,10 @@ def box_nms_py(data, overlap_thresh=0.5, valid_thresh=0.0, topk=-1, coord_start=
         order = sorted(valid, key=lambda i: -float(d[i, score_index]))   # python sort is stable
         order = order[:k_eff]
         box = d[:, coord_start:coord_start + 4]
-        area = {i: f32(f32(box[i, 2] - box[i, 0]) * f32(box[i, 3] - box[i, 1])) for i in order}
+        def _area(i):          # BoxArea(): 0 for a negative extent (oracle/ASSUMPTIONS.md A3)
+            w, h = f32(box[i, 2] - box[i, 0]), f32(box[i, 3] - box[i, 1])
+            return f32(0) if (w < 0 or h < 0) else f32(w * h)
+        area = {i: _area(i) for i in order}
         dead = set()
         for ri, r in enumerate(order):
             if r in dead:

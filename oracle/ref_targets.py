@@ -107,7 +107,12 @@ def prefetch_targets(img_shape, xs_shapes, anchors, offsets, gt_boxes, gt_ids, g
             row_base = sum((_offsets[i + 1] - _offsets[i]) *
                            (int(num_anchors[i]) - (0 if i == 0 else int(num_anchors[i - 1])))
                            for i in range(nlayer))
-            assign_row[b, m] = row_base + (index - _offsets[nlayer]) * a_cnt + (match - a_begin)
+            # a cell index past the matched layer's own map (loc_y >= height: centre on / below the bottom border) was written
+            # into another layer's rows, in anchor columns `_slice` (:139-148) drops: not visible in the outputs -> row -1
+            if _offsets[nlayer] <= index < _offsets[nlayer + 1]:
+                assign_row[b, m] = row_base + (index - _offsets[nlayer]) * a_cnt + (match - a_begin)
+            else:
+                assign_match[b, m] = -1
 
     outs = tuple(_slice(t, num_anchors, num_offsets)
                  for t in (objectness, center_targets, scale_targets, weights, class_targets))  # :132-136

@@ -30,6 +30,15 @@ def test_doc_examples():
         check(x, overlap_thresh=0.1, coord_start=2, score_index=1, id_index=0, force_suppress=force)
 
 
+def test_upstream_assumption_kats():
+    """oracle/ASSUMPTIONS.md A1-A10 on the CUDA operator: hand-derived keep records, and bit-equality with the oracle."""
+    from tests.kat_nms import case_arrays
+    for name, d, kw, rec in case_arrays():
+        o, r = run(d, **kw)
+        np.testing.assert_array_equal(r, rec, err_msg=name)
+        check(d, **kw)
+
+
 @pytest.mark.parametrize("N,topk", [(37, -1), (300, 100), (1000, 400), (5000, 400), (40000, 400), (20000, 1024), (600, 512)])
 @pytest.mark.parametrize("force", [False, True])
 def test_random_parity(N, topk, force):

@@ -65,6 +65,17 @@ def test_break_on_invalid_and_empty():
     assert (got[6][0, 3:] == -1).all() and (got[6][1] == -1).all() and np.count_nonzero(got[0][1]) == 0
 
 
+def test_centre_on_bottom_border_is_sliced_away():
+    """gy == orig_h with a layer-0 / layer-1 match: the reference's write lands in columns `_slice` drops (yolo_target.py:139-148)."""
+    gt = np.full((2, 4, 4), -1, np.float32); ids = np.zeros((2, 4, 1), np.float32)
+    gt[0, 0] = [100, 371, 220, 461]      # layer 0 (13x13), cy = 416 -> loc_y = 13
+    gt[0, 1] = [100, 120, 220, 300]
+    gt[1, 0] = [180, 386, 240, 446]      # w=60,h=60 -> layer 1 (26x26), cy = 416 -> loc_y = 26
+    gt[1, 1] = [10, 10, 40, 50]
+    got, ref = compare(gt, ids, None, 20)
+    assert got[6][0, 0] == -1 and got[6][1, 0] == -1 and np.count_nonzero(got[0]) == 2
+
+
 def test_small_boxes_float64_path():
     gt = np.full((1, 4, 4), -1, np.float32); ids = np.zeros((1, 4, 1), np.float32)
     gt[0, 0] = [50, 60, 50.5, 60.25]

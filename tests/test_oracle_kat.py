@@ -74,6 +74,30 @@ def test_nms_class_aware_vs_force_and_all_filtered_and_4d():
     np.testing.assert_array_equal(rec4[0], [[0, 1], [1, 0]])
 
 
+def test_upstream_assumption_kats():
+    """oracle/ASSUMPTIONS.md: every assumption about the upstream operator, hand-derived expected keep records."""
+    from tests.kat_nms import case_arrays, expected_output
+    for name, d, kw, rec in case_arrays():
+        out, got = ref_nms.box_nms(d, return_record=True, **kw)
+        np.testing.assert_array_equal(got, rec, err_msg=name)
+        if kw.get("in_format", "corner") == kw.get("out_format", "corner"):
+            np.testing.assert_array_equal(out, expected_output(d, kw, rec), err_msg=name)
+        if kw.get("in_format", "corner") == "corner":               # the numpy twin restates the corner format only
+            kw2 = {k: v for k, v in kw.items() if k not in ("in_format", "out_format")}
+            _, got2 = ref_nms.box_nms_py(d, **kw2)
+            np.testing.assert_array_equal(got2, rec, err_msg=name + " (numpy twin)")
+
+
+def test_box_area_clamp_value():
+    """A3: the area of an inverted box is 0, not the (positive) product of its two negative extents.  B = [4,0,14,10] (area 100)
+    overlaps the inverted row A' = [10,10,0,0] nowhere (Intersect clamps), but overlaps C = [0,0,10,10] with inter 60:
+    IoU(C,B) = 60 / (100 + 100 - 60) = 0.4286.  box_iou of the inverted box with anything is exactly 0 (A11)."""
+    iou = ref_nms.box_iou(np.array([[10, 10, 0, 0]], f32), np.array([[0, 0, 10, 10], [2, 2, 8, 8]], f32))
+    np.testing.assert_array_equal(iou, [[0, 0]])
+    iou = ref_nms.box_iou(np.array([[0, 0, 10, 10]], f32), np.array([[4, 0, 14, 10]], f32))
+    np.testing.assert_allclose(iou, [[60 / 140]], rtol=1e-6)
+
+
 @pytest.mark.parametrize("seed", [0, 1, 2])
 @pytest.mark.parametrize("force", [False, True])
 def test_c_oracle_matches_python_restatement(seed, force):
@@ -218,6 +242,19 @@ def test_targets_small_box_float64_log_path():
     aw, ah = 10, 13
     assert match[0, 0] == 6
     np.testing.assert_allclose(scl[0, row[0, 0]], [np.log(1 / aw), np.log(1 / ah)], rtol=1e-6)
+
+
+def test_targets_centre_on_bottom_border_is_sliced_away():
+    """A GT whose centre row maps to loc_y == H of its layer (gy == orig_h) is written at cell index >= HW, i.e. into the NEXT
+    layer's rows of the (B, sum HW, 9, .) scratch but in its own anchor columns, which `_slice` drops (yolo_target.py:139-148):
+    no visible positive.  (the device once wrote a bogus positive into the next scale.)"""
+    gt = np.full((1, 3, 4), -1, f32); ids = np.zeros((1, 3, 1), f32)
+    gt[0, 0] = [100, 371, 220, 461]          # w=120,h=90 -> anchor (116,90) = index 0 -> layer 0; cy = 416 -> loc_y = 13
+    gt[0, 1] = [100, 120, 220, 300]          # an ordinary GT after it is still processed (no break: the box is valid)
+    obj, ctr, scl, wgt, cls, match, row = _gen(gt, ids)
+    assert row[0, 0] == -1 and match[0, 0] == -1 and row[0, 1] >= 0
+    assert np.count_nonzero(obj) == 1 and obj[0, row[0, 1], 0] == 1
+    assert (np.delete(cls[0], row[0, 1], axis=0) == -1).all()
 
 
 # ------------------------------------------------------------------ temporal (A.5)

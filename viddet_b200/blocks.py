@@ -66,9 +66,11 @@ _WS_CACHE = {}
 
 
 def _workspace(nbytes, device, owner="nms"):
-    """Cached scratch buffer per (device, owner).  The fused head keeps state in its workspace between calls
-    (tile-scheduler counters, histograms left zeroed, warm-start hints), so it never shares a buffer with box_nms."""
-    key = (device.index if device.index is not None else torch.cuda.current_device(), owner)
+    """Cached scratch buffer per (device, owner, current stream).  The fused head keeps state in its workspace between
+    calls (tile-scheduler counters, histograms left zeroed, thresholds), so it never shares a buffer with box_nms, with
+    another head instance (`owner` carries the instance id) or with a call enqueued on another stream."""
+    key = (device.index if device.index is not None else torch.cuda.current_device(), owner,
+           torch.cuda.current_stream(device).cuda_stream)
     buf = _WS_CACHE.get(key)
     if buf is None or buf.numel() < nbytes:
         buf = torch.zeros(int(nbytes * 1.25) + 1024, dtype=torch.uint8, device=device)
@@ -479,6 +481,13 @@ class YOLOV3Head:
         self._num_class = len(self.classes)
         anchors = DEFAULT_ANCHORS if anchors is None else anchors
         strides = DEFAULT_STRIDES if strides is None else strides
+        # ORDER CONTRACT: anchors / strides / channels are given in OUTPUT order (deep -> shallow: s32, s16, s8), i.e. what
+        # YOLOV3.__init__ holds AFTER its `anchors[::-1]`, `strides[::-1]` (yolo3.py:416-417).  wrappers.py:80-84 lists them
+        # shallow -> deep (s8, s16, s32): reverse such lists before passing them here -- checked, not silently mis-paired.
+        if list(strides) != sorted(strides, reverse=True):
+            raise ValueError("YOLOV3Head: strides must be in output order (deep -> shallow, e.g. [32, 16, 8]); the reference's "
+                             "constructor lists (s8, s16, s32) are reversed at yolo3.py:416-417 -- pass anchors[::-1], strides[::-1]")
+        assert len(anchors) == len(strides), "one anchor list per stride"
         self.channels = DEFAULT_CHANNELS if channels is None else list(channels)
         assert temporal in (None, "conv21", "cat", "max", "mean")
         self.temporal, self.k = temporal, k
@@ -490,6 +499,7 @@ class YOLOV3Head:
         self.tip_convs = [TemporalTipConv(c) for c in self.channels] if temporal == "conv21" else None
         self.pool = TemporalPooling(k, temporal) if temporal in ("max", "mean") else None
         self._keep = None
+        self._ws_cache = {}
 
     def initialize(self, generator=None):
         mult = self.k if self.temporal == "cat" else 1
@@ -511,6 +521,17 @@ class YOLOV3Head:
             o.reset_class(classes, reuse_weights)
 
     # -- helpers ---------------------------------------------------------------------------------
+    def _ws(self, nbytes, device, tag):
+        """The fused call keeps state in its workspace between calls (include/viddet_b200.h "Workspace contract"): one
+        buffer per (head instance, device, stream, entry point), owned by the instance (freed with it)."""
+        key = (device.index if device.index is not None else torch.cuda.current_device(), tag,
+               torch.cuda.current_stream(device).cuda_stream)
+        buf = self._ws_cache.get(key)
+        if buf is None or buf.numel() < nbytes:
+            buf = torch.zeros(int(nbytes * 1.25) + 1024, dtype=torch.uint8, device=device)
+            self._ws_cache[key] = buf
+        return buf
+
     def _params(self, tips, scratch):
         """Build VdHeadParams for already-channels-last tips [(frames,C,H,W) or (B,K,C,H,W)-flattened]."""
         p = VdHeadParams()
@@ -587,7 +608,7 @@ class YOLOV3Head:
         bboxes = torch.empty((F, post, 4), device=dev)
         keep = torch.empty((F, post), dtype=torch.int32, device=dev) if return_keep else None
         lib = load()
-        ws = _workspace(lib.vd_head_workspace_bytes(ctypes.byref(p)), dev, owner="head")
+        ws = self._ws(lib.vd_head_workspace_bytes(ctypes.byref(p)), dev, "head")
         check(lib.vd_head_forward(ctypes.byref(p), ptr(ids), ptr(scores), ptr(bboxes), ptr(keep), ptr(ws), ws.numel(),
                                   stream_ptr()))
         if lead is not None:
@@ -632,7 +653,7 @@ class YOLOV3Head:
         rows = sum(self._num_class * int(p.scale[i].H) * int(p.scale[i].W) * 3 for i in range(p.num_scales))
         det = torch.empty((p.frames, rows, 6), device=dev)
         lib = load()
-        ws = _workspace(max(lib.vd_head_workspace_bytes(ctypes.byref(p)), 256), dev, owner="det")
+        ws = self._ws(max(lib.vd_head_workspace_bytes(ctypes.byref(p)), 256), dev, "det")
         check(lib.vd_head_detections(ctypes.byref(p), ptr(det), ptr(ws), ws.numel(), stream_ptr()))
         if lead is not None:
             det = det.reshape(lead + (rows, 6))
@@ -915,7 +936,9 @@ class YOLOV3Neck:
 
     def __init__(self, classes, channels=(512, 256, 128), stage_channels=(256, 512, 1024), anchors=None, strides=None,
                  nms_thresh=0.45, nms_topk=400, post_nms=100, conv_type="2"):
-        """conv_type '2': YOLOV3 (routes (B,C,H,W)); '3' / '21': YOLOV3Temporal with t_out (yolo3_temporal.py:448-555): routes
+        """anchors / strides: OUTPUT order (deep -> shallow), i.e. the reference's lists after yolo3.py:416-417 reversed them
+        (YOLOV3Head checks that strides descend); channels: as the reference passes them (deep -> shallow already, wrappers.py:91-107).
+        conv_type '2': YOLOV3 (routes (B,C,H,W)); '3' / '21': YOLOV3Temporal with t_out (yolo3_temporal.py:448-555): routes
         (B,T,C,H,W), 3-D / (2+1)D detection blocks, transitions and output layers applied per frame (TimeDistributed), detections
         (B,T,post,.)."""
         assert conv_type in ("2", "3", "21")

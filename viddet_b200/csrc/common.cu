@@ -1,6 +1,9 @@
 // Error plumbing + device queries for the C ABI.
 #include "common.cuh"
 #include <stdarg.h>
+#include <mutex>
+#include <set>
+#include <utility>
 
 namespace vd {
 
@@ -15,16 +18,32 @@ int set_error(int code, const char* fmt, ...) {
     return code;
 }
 
+static std::mutex g_cfg_mutex;      // guards the per-device caches below (one process may drive several devices / threads)
+
 int sm_count() {
     static int cached[64] = {0};
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    std::lock_guard<std::mutex> lock(g_cfg_mutex);
     if (!cached[dev]) {
         int n = 0;
         if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
         cached[dev] = n;
     }
     return cached[dev];
+}
+
+// Function attributes are per (device, function): set them once for each pair (not once per process), under a lock.
+int configure_kernel(const void* func, int dyn_smem_bytes, bool max_shared_carveout) {
+    int dev = 0;
+    VD_CUDA(cudaGetDevice(&dev));
+    static std::set<std::pair<int, const void*>> done;
+    std::lock_guard<std::mutex> lock(g_cfg_mutex);
+    if (done.count(std::make_pair(dev, func))) return VD_OK;
+    if (dyn_smem_bytes > 0) VD_CUDA(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_smem_bytes));
+    if (max_shared_carveout) VD_CUDA(cudaFuncSetAttribute(func, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    done.insert(std::make_pair(dev, func));
+    return VD_OK;
 }
 
 }  // namespace vd

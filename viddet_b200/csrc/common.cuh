@@ -28,7 +28,9 @@ static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
-int sm_count();   // of the current device (cached)
+int sm_count();   // of the current device (cached per device)
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize[, carve-out]) once per (current device, kernel); thread-safe
+int configure_kernel(const void* func, int dyn_smem_bytes, bool max_shared_carveout);
 
 // ---------------------------------------------------------------------------------------------
 // 64-bit selection key: (orderable(score) << 32) | ~row.  Larger key == earlier in MXNet's

@@ -213,11 +213,7 @@ template <int NT>
 static int launch_conv(const ConvMaps& maps, const ConvParams& p, cudaStream_t stream) {
     using Cfg = ConvCfg<NT>;
     auto kern = conv_bn_lrelu_kernel<NT>;
-    static bool configured = false;
-    if (!configured) {
-        VD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-        configured = true;
-    }
+    { int rc_ = configure_kernel((const void*)kern, Cfg::SMEM_BYTES, false); if (rc_) return rc_; }
     int grid = sm_count(); if (grid > p.total_tiles) grid = p.total_tiles;
     kern<<<grid, C_THREADS, Cfg::SMEM_BYTES, stream>>>(maps, p);
     VD_LAUNCH_CHECK();
@@ -421,11 +417,7 @@ conv_bn_lrelu_pair_kernel(const __grid_constant__ ConvMaps maps, const __grid_co
 static int launch_conv_pair(const ConvMaps& maps, const ConvParams& p, cudaStream_t stream) {
     using Cfg = Conv2Cfg<256>;
     auto kern = conv_bn_lrelu_pair_kernel<256>;
-    static bool configured = false;
-    if (!configured) {
-        VD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-        configured = true;
-    }
+    { int rc_ = configure_kernel((const void*)kern, Cfg::SMEM_BYTES, false); if (rc_) return rc_; }
     const long long m_tiles = (long long)p.F2 * p.tiles_f * p.tiles_y * p.tiles_x;
     const long long pairs = (m_tiles + 1) / 2 * p.n_tiles;
     long long clusters = sm_count() / 2; if (clusters > pairs) clusters = pairs;

@@ -1007,7 +1007,7 @@ struct FusedSource {
         const int gy = cell / g.W[s], gx = cell - gy * g.W[s];
         const Box4 b = vd_decode_box(t.x, t.y, t.z, t.w, (float)gx, (float)gy, g.stride[s], g.anchors[s][2 * a], g.anchors[s][2 * a + 1]);
         bx = make_float4(b.x1, b.y1, b.x2, b.y2);
-        area = __fmul_rn(__fsub_rn(bx.z, bx.x), __fsub_rn(bx.w, bx.y));
+        area = vd_box_area(__fsub_rn(bx.z, bx.x), __fsub_rn(bx.w, bx.y));
     }
 };
 struct FusedSink {
@@ -1507,12 +1507,8 @@ template <int EPI, int C, int NPAD>
 static int launch_head_t(const HeadMaps& maps, const HeadKernelParams& kp, cudaStream_t stream) {
     using Cfg = HeadCfg<EPI, C, NPAD>;
     auto kern = head_kernel<EPI, C, NPAD>;
-    static bool configured = false;                 // once per instantiation (also keeps graph capture clean)
-    if (!configured) {
-        VD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-        if (!getenv("VD_DEBUG_NO_CARVEOUT")) VD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));   // same carve-out as the NMS kernel: CTAs of both can share an SM
-        configured = true;
-    }
+    // once per (device, instantiation) (also keeps graph capture clean); same carve-out as the NMS kernel: CTAs of both can share an SM
+    { int rc_ = configure_kernel((const void*)kern, Cfg::SMEM_BYTES, !getenv("VD_DEBUG_NO_CARVEOUT")); if (rc_) return rc_; }
     int grid = sm_count(); if (grid > kp.total_tiles) grid = kp.total_tiles;
     // the exact fallback of the speculative path is idle in the steady state: a handful of CTAs slip in between two
     // head kernels instead of claiming every SM's shared memory (when frames did fail, they work through them slowly)
@@ -1668,15 +1664,12 @@ extern "C" int vd_head_forward_stages(const VdHeadParams* hp, float* ids, float*
     P.dbg = (getenv("VD_DEBUG_NMS_STAMPS") || getenv("VD_DEBUG_HEAD_STAMPS")) ? (long long*)(ws + pl.off_listsA) : nullptr;   // profiling aid (unused merge area)
     FusedSource src{kp.g, kp.boxes};
     FusedSink sink{ids, scores, bboxes, keep_rows_or_null, hp->post_nms};
-    static bool configured = false;
-    if (!configured) {
-        VD_CUDA(cudaFuncSetAttribute(nms_final_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)nms_hist_smem(VD_MAX_TOPK, VD_MAX_TOPK)));
-        VD_CUDA(cudaFuncSetAttribute(nms_spec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)nms_spec_smem(VD_MAX_TOPK, VD_MAX_TOPK)));
-        if (!getenv("VD_DEBUG_NO_CARVEOUT") || atoi(getenv("VD_DEBUG_NO_CARVEOUT")) == 2) {
-            VD_CUDA(cudaFuncSetAttribute(nms_final_hist_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-            VD_CUDA(cudaFuncSetAttribute(nms_spec_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-        }
-        configured = true;
+    {
+        const bool carve = !getenv("VD_DEBUG_NO_CARVEOUT") || atoi(getenv("VD_DEBUG_NO_CARVEOUT")) == 2;
+        rc = configure_kernel((const void*)nms_final_hist_kernel, (int)nms_hist_smem(VD_MAX_TOPK, VD_MAX_TOPK), carve);
+        if (rc) return rc;
+        rc = configure_kernel((const void*)nms_spec_kernel, (int)nms_spec_smem(VD_MAX_TOPK, VD_MAX_TOPK), carve);
+        if (rc) return rc;
     }
     if (!spec) {
         nms_final_hist_kernel<<<hp->frames, kNmsThreads, nms_hist_smem(k, hp->post_nms), stream>>>(

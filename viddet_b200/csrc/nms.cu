@@ -76,11 +76,11 @@ struct CompatSource {
         float v0 = p[a.coord_start], v1 = p[a.coord_start + 1], v2 = p[a.coord_start + 2], v3 = p[a.coord_start + 3];
         if (a.in_format == 0) {
             bx = make_float4(v0, v1, v2, v3);
-            area = __fmul_rn(__fsub_rn(v2, v0), __fsub_rn(v3, v1));
+            area = vd_box_area(__fsub_rn(v2, v0), __fsub_rn(v3, v1));
         } else {                                   // center: MXNet Intersect(): a1 -/+ a2/2
             float hw = __fdiv_rn(v2, 2.0f), hh = __fdiv_rn(v3, 2.0f);
             bx = make_float4(__fsub_rn(v0, hw), __fsub_rn(v1, hh), __fadd_rn(v0, hw), __fadd_rn(v1, hh));
-            area = __fmul_rn(v2, v3);
+            area = vd_box_area(v2, v3);
         }
         c = a.id_index >= 0 ? (int)p[a.id_index] : 0;
     }
@@ -196,11 +196,7 @@ extern "C" int vd_box_nms(const float* data, int64_t num_batch, int64_t num_elem
     P.overlap_thresh = overlap_thresh; P.k = k; P.sortn = nms_sortn(k);
     P.class_aware = (!force_suppress && id_index >= 0) ? 1 : 0; P.max_out = k; P.dbg = nullptr;
     size_t smem = nms_final_smem(k);
-    static bool configured = false;
-    if (!configured) {
-        VD_CUDA(cudaFuncSetAttribute(nms_final_compat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)nms_final_smem(VD_MAX_TOPK)));
-        configured = true;
-    }
+    { int rc_ = configure_kernel((const void*)nms_final_compat_kernel, (int)nms_final_smem(VD_MAX_TOPK), false); if (rc_) return rc_; }
     nms_final_compat_kernel<<<(unsigned)num_batch, kFinalThreads, smem, stream>>>(lists, counts, n_lists, P, a);
     VD_LAUNCH_CHECK();
     return VD_OK;

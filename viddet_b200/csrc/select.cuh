@@ -147,6 +147,9 @@ __device__ __forceinline__ float vd_intersect_1d(float a1, float a2, float b1, f
     float w = __fsub_rn(right, left);
     return w > 0.0f ? w : 0.0f;
 }
+// MXNet BoxArea(): width * height, 0 when either extent is negative (oracle/ASSUMPTIONS.md A3)
+__device__ __forceinline__ float vd_box_area(float w, float h) { return (w < 0.0f || h < 0.0f) ? 0.0f : __fmul_rn(w, h); }
+
 __device__ __forceinline__ bool vd_iou_gt(float4 r, float area_r, float4 p, float area_p, float thresh) {
     float inter = __fmul_rn(vd_intersect_1d(r.x, r.z, p.x, p.z), vd_intersect_1d(r.y, r.w, p.y, p.w));
     if (inter == 0.0f && thresh >= 0.0f) return false;     // 0/u is 0, -0 or NaN: never > thresh >= 0

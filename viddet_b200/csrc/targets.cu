@@ -97,7 +97,10 @@ targets_scatter_kernel(TargetArgs a) {
             int loc_x = (int)fx, loc_y = (int)fy;                   // trunc toward 0
             int cell = loc_y * W + loc_x;
             row = 3 * a.cell_off[layer] + cell * 3 + (match - 3 * layer);
-            if (row < 0 || row >= a.N) row = -1;                    // undefined in the reference (A.4)
+            // A cell index past the matched layer's map (centre on / beyond the bottom border: loc_y >= H) lands in another
+            // layer's rows of the reference's (B, sum HW, 9, .) scratch, in columns `_slice` discards (yolo_target.py:139-148):
+            // nothing visible is written.  (loc_x >= W with the cell still inside the layer IS visible there and is kept.)
+            if (cell < 0 || cell >= H * W || row < 0 || row >= a.N) row = -1;
             s_row[m] = row; s_match[m] = (unsigned char)match;
         } else { s_row[m] = -1; s_match[m] = 0; }
         s_own[m] = 0;

@@ -352,11 +352,7 @@ temporal_conv_pair_kernel(const __grid_constant__ TConvMaps maps, const __grid_c
 
 static int launch_tconv_pair(const TConvMaps& maps, const TConvParams& p, cudaStream_t stream) {
     auto kern = temporal_conv_pair_kernel;
-    static bool configured = false;
-    if (!configured) {
-        VD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, T2Cfg::SMEM_BYTES));
-        configured = true;
-    }
+    { int rc_ = configure_kernel((const void*)kern, T2Cfg::SMEM_BYTES, false); if (rc_) return rc_; }
     const long long pairs = ((long long)p.B * p.m_tiles + 1) / 2 * p.n_tiles;
     long long clusters = sm_count() / 2; if (clusters > pairs) clusters = pairs;
     kern<<<(unsigned)(2 * clusters), T_THREADS, T2Cfg::SMEM_BYTES, stream>>>(maps, p);
@@ -368,11 +364,7 @@ template <int NT>
 static int launch_tconv(const TConvMaps& maps, const TConvParams& p, cudaStream_t stream) {
     using Cfg = TConvCfg<NT>;
     auto kern = temporal_conv_kernel<NT>;
-    static bool configured = false;
-    if (!configured) {
-        VD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-        configured = true;
-    }
+    { int rc_ = configure_kernel((const void*)kern, Cfg::SMEM_BYTES, false); if (rc_) return rc_; }
     int grid = sm_count(); if (grid > p.total_tiles) grid = p.total_tiles;
     kern<<<grid, T_THREADS, Cfg::SMEM_BYTES, stream>>>(maps, p);
     VD_LAUNCH_CHECK();

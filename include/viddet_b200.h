@@ -96,6 +96,26 @@ int vd_pred_conv(const void* x_nhwc_bf16, int B, int H, int W, int Cin, int K_fr
                  float* pred_nchw, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * fp32-parity mode (VD_PREC_FP32_SPLIT).  The reference head is fp32 end to end (yolo3.py:62,157).  The tensor cores take
+ * bf16 operands, so an fp32 value v is carried as two bf16 planes hi = bf16(v), lo = bf16(v - hi) (16 mantissa bits,
+ * residual <= 2^-18 |v|) and the conv accumulates  hi*W_hi + lo*W_hi + hi*W_lo  in fp32 (the lo*lo term, 2^-18 relative, is
+ * dropped): decoded scores / boxes land within 1e-5 relative of the fp32 reference instead of 1e-3 (tests/test_gpu_fp32.py).
+ * Carriers in this mode:  activations (B, 2, H, W, Cin) bf16 = [hi plane, lo plane] per frame, channels-last;
+ *                         weights     (N_out, 2, Cin) bf16  = [hi row, lo row] per output channel.
+ * The mode reads 4 bytes per activation element (what an fp32 carrier costs) and issues 3x the MMAs; the VOC / VID heads stay
+ * HBM-bound.  Not combinable with VD_JOIN_CAT or the temporal tip cell (VD_ERR_UNSUPPORTED).
+ * ------------------------------------------------------------------------------------------ */
+#define VD_PREC_BF16        0   /* bf16 operands, fp32 accumulate (1e-3 relative vs the fp32 reference)          */
+#define VD_PREC_FP32_SPLIT  1   /* hi/lo bf16 planes, 3 products, fp32 accumulate (1e-5 relative)                */
+/* (B, C, H, W) fp32 -> (B, 2, H, W, C) bf16 hi/lo planes (the activation carrier of VD_PREC_FP32_SPLIT). */
+int vd_repack_nchw_f32_to_nhwc_split(const float* src, void* dst_bf16, int B, int C, int H, int W, void* stream);
+/* (rows, cols) fp32 -> (rows, 2, cols) bf16 hi/lo rows (the weight carrier of VD_PREC_FP32_SPLIT). */
+int vd_split_f32_rows(const float* src, void* dst_bf16, int64_t rows, int64_t cols, void* stream);
+/* vd_pred_conv with a precision selector: VD_PREC_FP32_SPLIT takes the split carriers described above. */
+int vd_pred_conv_ex(const void* x, int B, int H, int W, int Cin, int K_frames, int join, int precision,
+                    const void* weight, const float* bias_or_null, int N, float* pred_nchw, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Fused detector tail -- replaces, for one forward call of YOLOV3 / YOLOV3T / YOLOV3Temporal in
  * inference mode: the three YOLOOutputV3 blocks (yolo3.py:496 -> :132-199), the scale concat
  * (:523), box_nms (:526-528), the post_nms slice (:529-530) and the id/score/bbox split
@@ -126,6 +146,8 @@ typedef struct VdHeadParams {
     float valid_thresh;          /* 0.01 at yolo3.py:527                                        */
     int nms_topk;                /* 400 (detect_yolo3.py:200)                                   */
     int post_nms;                /* 100 (yolo3.py:395)                                          */
+    int precision;               /* VD_PREC_BF16 (0) or VD_PREC_FP32_SPLIT: tips (frames,2,H,W,Cin), weights (N_out,2,Cin) */
+    int reserved0;               /* must be 0                                                    */
     VdHeadScale scale[VD_MAX_SCALES];
 } VdHeadParams;
 
@@ -144,6 +166,9 @@ typedef struct VdHeadParams {
  *   - a zero-filled buffer, a buffer last used with other parameters, or arbitrary foreign content are all
  *     detected on the device and handled exactly (every frame takes the exact path) -- slower for
  *     that one call, never wrong. */
+/* sizeof of the ABI structs as the library was compiled (which: 0 VdHeadScale, 1 VdHeadParams; 0 for anything else):
+ * lets a binding check its own struct mirror. */
+size_t vd_sizeof(int which);
 size_t vd_head_workspace_bytes(const VdHeadParams* p);
 /* ids (frames, post_nms, 1), scores (frames, post_nms, 1), bboxes (frames, post_nms, 4) fp32;
  * keep_rows_or_null (frames, post_nms) int32 = row in the (frames, rows, 6) tensor of each output

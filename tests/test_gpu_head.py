@@ -9,7 +9,7 @@ import pytest
 import torch
 
 from oracle import ref_head, ref_nms, ref_temporal
-from tests.util import ANCHORS, CHANNELS, STRIDES, bf16_round, make_pred_weights, make_tips
+from tests.util import ANCHORS, CHANNELS, STRIDES, bf16_round, keep_agreement, make_pred_weights, make_tips, rel_err
 
 pytestmark = pytest.mark.gpu
 
@@ -285,7 +285,8 @@ def test_workspace_in_foreign_state_is_exact():
     out, rec = viddet_b200.box_nms(det, overlap_thresh=0.45, valid_thresh=0.01, topk=400, id_index=0, score_index=1,
                                    coord_start=2, force_suppress=False, return_record=True)
     head(tips)                                              # make sure the cached workspace exists
-    for buf in blocks._WS_CACHE.values():
+    assert head._ws_cache, "the head keeps its own workspace(s)"
+    for buf in head._ws_cache.values():
         buf.copy_(torch.randint(0, 256, buf.shape, dtype=torch.uint8, device=buf.device))
     for _ in range(3):
         ids, scores, boxes, keep = head(tips, return_keep=True)
@@ -359,9 +360,25 @@ def test_temporal_head_conv21_vs_oracle():
     mid = [bf16_round(ref_temporal.temporal_conv_bn_lrelu(t, w, ones(c), zeros(c), zeros(c), ones(c)))
            for t, w, c in zip(tips5, tw, CHANNELS)]
     ref = ref_head.head_detections([m.reshape((B * T,) + m.shape[2:]) for m in mid], ws, bs, C).reshape(det.shape)
-    np.testing.assert_allclose(det[..., 1], ref[..., 1], rtol=3e-2)      # bf16 intermediate between the two convs
-    ids, scores, boxes = head(t5)
+    # The tip travels between the two convs as bf16 on both sides.  The device and the oracle accumulate the tip cell in a
+    # different order, so a tip element that sits within ~1e-6 of a bf16 rounding boundary can round the other way (one
+    # bf16 ulp = 2^-8 relative on that element); through the 1x1 conv (K = 256..1024 terms) that moves a logit by ~1e-5.
+    # Measured on B200 (printed below, recorded in DESIGN.md): scores within 3e-4 relative, boxes within 3e-4 of the image.
+    es = rel_err(det[..., 1], ref[..., 1], 1e-3)
+    eb = float(np.abs(det[..., 2:].astype(np.float64) - ref[..., 2:]).max() / 160.0)
+    print("temporal conv21 head (cfg 4 shape, C=30, T=5): score rel err %.2e, box err %.2e of the image size" % (es, eb))
+    assert es <= 1e-3 and eb <= 1e-3                                      # north star: 1e-3 relative for the bf16 conv
+    head.set_nms(0.45, 400, 100)
+    ids, scores, boxes, keep = head(t5, return_keep=True)
     assert ids.shape == (B, T, 100, 1)
+    # keep rows of the temporal head vs the oracle chain (box_nms over (B,T,rows,6), yolo3_temporal.py:545-547)
+    out, rec = ref_nms.box_nms(ref, overlap_thresh=0.45, valid_thresh=0.01, topk=400, id_index=0, score_index=1, coord_start=2,
+                               return_record=True)
+    frac, n_tie = keep_agreement(keep.reshape(B * T, 100).cpu().numpy(), rec.reshape(B * T, -1), ref.reshape(B * T, -1, 6), tol=2e-3)
+    print("temporal conv21 head: %.2f%% identical keep positions, %d near-tie swaps" % (100 * frac, n_tie))
+    assert frac >= 0.97
+    same = keep.reshape(B * T, 100).cpu().numpy() == rec.reshape(B * T, -1)[:, :100]
+    np.testing.assert_allclose(scores.reshape(B * T, 100).cpu().numpy()[same], out.reshape(B * T, -1, 6)[:, :100, 1][same], rtol=1e-3)
 
 
 def test_errors_surface():

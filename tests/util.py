@@ -95,3 +95,26 @@ def replay_shim_params(seed, kinds, shapes, has_bias):
             out.append(("bn", rng.uniform(0.5, 1.5, c).astype(np.float32), rng.uniform(-0.2, 0.2, c).astype(np.float32),
                         rng.uniform(-0.2, 0.2, c).astype(np.float32), rng.uniform(0.5, 1.5, c).astype(np.float32)))
     return out
+
+
+def keep_agreement(keep_dev, rec_ref, det_ref, tol):
+    """Compare the device's NMS keep rows (frames, post) with the oracle's record (frames, >= post) position by position.
+    A mismatch is accepted only as a near-tie: the row the device kept at that position must have an ORACLE score within `tol`
+    (relative) of the oracle's own pick there (two candidates whose scores differ by less than the arithmetic noise may swap
+    ranks).  Returns (fraction of identical positions, number of near-tie positions); raises on any other mismatch."""
+    post = keep_dev.shape[1]
+    same = keep_dev == rec_ref[:, :post]
+    n_tie = 0
+    for f, i in zip(*np.nonzero(~same)):
+        rd, rr = int(keep_dev[f, i]), int(rec_ref[f, i])
+        assert rd >= 0 and rr >= 0, "frame %d pos %d: device kept row %d, oracle row %d" % (f, i, rd, rr)
+        sd, sr = float(det_ref[f, rd, 1]), float(det_ref[f, rr, 1])
+        assert abs(sd - sr) <= tol * abs(sr), "frame %d pos %d: rows %d / %d differ by more than a near-tie (%.9g vs %.9g)" % (f, i, rd, rr, sd, sr)
+        n_tie += 1
+    return float(same.mean()), n_tie
+
+
+def rel_err(got, ref, floor):
+    """max |got - ref| / max(|ref|, floor) over all elements."""
+    got = np.asarray(got, np.float64); ref = np.asarray(ref, np.float64)
+    return float((np.abs(got - ref) / np.maximum(np.abs(ref), floor)).max())

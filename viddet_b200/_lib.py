@@ -15,6 +15,7 @@ VD_MAX_TOPK = 1024
 VD_MODE_INFER, VD_MODE_TRAIN, VD_MODE_AGNOSTIC = 0, 1, 2
 VD_JOIN_NONE, VD_JOIN_CAT, VD_JOIN_MAX, VD_JOIN_MEAN = 0, 1, 2, 3
 VD_STAGE_TCONV, VD_STAGE_HEAD, VD_STAGE_NMS, VD_STAGE_ALL = 1, 2, 4, 7
+VD_PREC_BF16, VD_PREC_FP32_SPLIT = 0, 1
 ERR_NAMES = {-1: "VD_ERR_INVALID_ARG", -2: "VD_ERR_UNSUPPORTED", -3: "VD_ERR_WORKSPACE", -4: "VD_ERR_CUDA"}
 
 
@@ -40,6 +41,7 @@ class VdHeadParams(ctypes.Structure):
         ("T", ctypes.c_int), ("K_frames", ctypes.c_int), ("join", ctypes.c_int),
         ("nms_thresh", ctypes.c_float), ("valid_thresh", ctypes.c_float),
         ("nms_topk", ctypes.c_int), ("post_nms", ctypes.c_int),
+        ("precision", ctypes.c_int), ("reserved0", ctypes.c_int),
         ("scale", VdHeadScale * VD_MAX_SCALES),
     ]
 
@@ -57,6 +59,10 @@ SIGNATURES = {
     "vd_yolo_decode": (_i, [_vp, _i, _i, _i, _i, _i, _fp, _f, _i, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp]),
     "vd_repack_nchw_f32_to_nhwc_bf16": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "vd_pred_conv": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp]),
+    "vd_pred_conv_ex": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp]),
+    "vd_repack_nchw_f32_to_nhwc_split": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
+    "vd_split_f32_rows": (_i, [_vp, _vp, _i64, _i64, _vp]),
+    "vd_sizeof": (_sz, [_i]),
     "vd_head_workspace_bytes": (_sz, [ctypes.POINTER(VdHeadParams)]),
     "vd_head_forward": (_i, [ctypes.POINTER(VdHeadParams), _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "vd_head_forward_stages": (_i, [ctypes.POINTER(VdHeadParams), _vp, _vp, _vp, _vp, _vp, _sz, _vp, _i]),
@@ -90,6 +96,9 @@ def load():
             fn = getattr(lib, name)          # AttributeError if a declared symbol is not exported
             fn.restype = res
             fn.argtypes = args
+        if lib.vd_sizeof(0) != ctypes.sizeof(VdHeadScale) or lib.vd_sizeof(1) != ctypes.sizeof(VdHeadParams):
+            raise VidDetError(-1, "struct mirror out of date: library VdHeadScale/VdHeadParams = %d/%d bytes, ctypes %d/%d"
+                              % (lib.vd_sizeof(0), lib.vd_sizeof(1), ctypes.sizeof(VdHeadScale), ctypes.sizeof(VdHeadParams)))
         _lib = lib
     return _lib
 

@@ -59,6 +59,39 @@ def to_nhwc_bf16(x: torch.Tensor) -> torch.Tensor:
     return x.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
 
 
+class SplitF32:
+    """fp32 feature map carried for the tensor cores as two bf16 planes (VD_PREC_FP32_SPLIT, include/viddet_b200.h):
+    `data` (B, 2, H, W, C) bf16 = [hi, lo] with hi = bf16(v), lo = bf16(v - hi); `shape` is the logical (B, C, H, W)."""
+
+    def __init__(self, data, shape):
+        self.data, self.shape = data, tuple(shape)
+
+    @property
+    def device(self):
+        return self.data.device
+
+
+def to_nhwc_split(x) -> SplitF32:
+    """(B,C,H,W) fp32 NCHW (the reference's layout and dtype) -> SplitF32 through the repack kernel."""
+    if isinstance(x, SplitF32):
+        return x
+    _require_cuda(x, "x")
+    assert x.dim() == 4, "expected (B,C,H,W)"
+    x = x.to(torch.float32).contiguous()
+    B, C, H, W = x.shape
+    out = torch.empty((B, 2, H, W, C), dtype=torch.bfloat16, device=x.device)
+    check(load().vd_repack_nchw_f32_to_nhwc_split(ptr(x), ptr(out), B, C, H, W, stream_ptr()))
+    return SplitF32(out, (B, C, H, W))
+
+
+def _precision_code(precision):
+    if precision in ("bf16", None, _lib.VD_PREC_BF16):
+        return _lib.VD_PREC_BF16
+    if precision in ("fp32", "f32", "float32", _lib.VD_PREC_FP32_SPLIT) and precision is not True:
+        return _lib.VD_PREC_FP32_SPLIT
+    raise ValueError("precision must be 'bf16' or 'fp32', got %r" % (precision,))
+
+
 # ------------------------------------------------------------------------------------------------
 # box_nms
 # ------------------------------------------------------------------------------------------------
@@ -126,10 +159,22 @@ class _Conv1x1:
         self.bias = (torch.zeros(n, device="cuda") if bias is None
                      else torch.as_tensor(bias).detach().to(torch.float32).cuda().contiguous())
         self._w_bf16 = self.weight.reshape(n, -1).to(torch.bfloat16).contiguous()
+        self._w_split = None
 
     @property
     def weight_bf16(self):
         return self._w_bf16
+
+    @property
+    def weight_split(self):
+        """(N, 2, Cin) bf16 hi / lo rows of the fp32 master weight (VD_PREC_FP32_SPLIT carrier), built on first use."""
+        if self._w_split is None:
+            n = self.weight.shape[0]
+            w2 = self.weight.reshape(n, -1).contiguous()
+            out = torch.empty((n, 2, w2.shape[1]), dtype=torch.bfloat16, device=w2.device)
+            check(load().vd_split_f32_rows(ptr(w2), ptr(out), n, w2.shape[1], stream_ptr()))
+            self._w_split = out
+        return self._w_split
 
 
 class YOLOOutputV3:
@@ -145,7 +190,8 @@ class YOLOOutputV3:
     """
 
     def __init__(self, index, num_class, anchors, stride, alloc_size=(128, 128), k=None, rnn_shape=None,
-                 k_join_type="max", agnostic=False, in_channels=None):
+                 k_join_type="max", agnostic=False, in_channels=None, precision="bf16"):
+        self._precision = _precision_code(precision)     # 'fp32': hi/lo split operands, 1e-5 vs the fp32 reference (fp32 NCHW inputs)
         if k is not None and rnn_shape is not None:
             raise NotImplementedError("ConvRNN prediction (yolo3.py:58-60) is outside the hot path")
         anchors = np.array(anchors).astype("float32")
@@ -199,14 +245,19 @@ class YOLOOutputV3:
     # -- forward ---------------------------------------------------------------------------------
     def predict(self, x):
         """The prediction conv alone: (B,Cin,H,W) -> pred (B, A*(5+C), H, W) fp32 (yolo3.py:157)."""
-        xb = to_nhwc_bf16(x)
+        split = self._precision == _lib.VD_PREC_FP32_SPLIT
+        xb = to_nhwc_split(x) if split else to_nhwc_bf16(x)
         B, Cin, H, W = xb.shape
         n = self._num_pred * self._num_anchors
         if self.prediction.weight is None or self.prediction.weight.shape[1] != Cin:
             raise _lib.VidDetError(-1, "YOLOOutputV3: prediction weights not set for Cin=%d" % Cin)
         pred = torch.empty((B, n, H, W), dtype=torch.float32, device=xb.device)
-        check(load().vd_pred_conv(ptr(xb), B, H, W, Cin, 1, _lib.VD_JOIN_NONE, ptr(self.prediction.weight_bf16),
-                                  ptr(self.prediction.bias), n, ptr(pred), stream_ptr()))
+        if split:
+            check(load().vd_pred_conv_ex(ptr(xb.data), B, H, W, Cin, 1, _lib.VD_JOIN_NONE, _lib.VD_PREC_FP32_SPLIT,
+                                         ptr(self.prediction.weight_split), ptr(self.prediction.bias), n, ptr(pred), stream_ptr()))
+        else:
+            check(load().vd_pred_conv(ptr(xb), B, H, W, Cin, 1, _lib.VD_JOIN_NONE, ptr(self.prediction.weight_bf16),
+                                      ptr(self.prediction.bias), n, ptr(pred), stream_ptr()))
         return pred
 
     def decode(self, pred, training=False, out=None, rows_total=None, row_offset=0):
@@ -476,7 +527,13 @@ class YOLOV3Head:
     """
 
     def __init__(self, classes, anchors=None, strides=None, channels=None, nms_thresh=0.45, nms_topk=400,
-                 post_nms=100, temporal=None, k=1, agnostic=False):
+                 post_nms=100, temporal=None, k=1, agnostic=False, precision="bf16"):
+        """precision 'bf16' (default): bf16 operands, fp32 accumulate -- 1e-3 relative vs the fp32 reference.
+        precision 'fp32': fp32 NCHW tips are split into hi/lo bf16 planes, three products per term -- 1e-5 relative
+        (VD_PREC_FP32_SPLIT; plain per-frame heads only)."""
+        self._precision = _precision_code(precision)
+        if self._precision != _lib.VD_PREC_BF16 and temporal is not None:
+            raise NotImplementedError("precision='fp32' is available for the per-frame head (temporal=None)")
         self.classes = list(classes) if not isinstance(classes, int) else list(range(classes))
         self._num_class = len(self.classes)
         anchors = DEFAULT_ANCHORS if anchors is None else anchors
@@ -495,7 +552,7 @@ class YOLOV3Head:
         self.valid_thresh = 0.01                      # hard-coded at yolo3.py:527
         if agnostic:
             raise NotImplementedError("agnostic detector tail: use YOLOOutputV3(agnostic=True) + box_nms")
-        self.yolo_outputs = [YOLOOutputV3(i, self._num_class, a, s) for i, (a, s) in enumerate(zip(anchors, strides))]
+        self.yolo_outputs = [YOLOOutputV3(i, self._num_class, a, s, precision=precision) for i, (a, s) in enumerate(zip(anchors, strides))]
         self.tip_convs = [TemporalTipConv(c) for c in self.channels] if temporal == "conv21" else None
         self.pool = TemporalPooling(k, temporal) if temporal in ("max", "mean") else None
         self._keep = None
@@ -541,6 +598,8 @@ class YOLOV3Head:
         p.K_frames, p.join = 1, _lib.VD_JOIN_NONE
         p.nms_thresh, p.valid_thresh = float(self.nms_thresh), float(self.valid_thresh)
         p.nms_topk, p.post_nms = int(self.nms_topk), int(self.post_nms)
+        p.precision = self._precision
+        split = self._precision == _lib.VD_PREC_FP32_SPLIT
         frames = None
         for i, (t, o) in enumerate(zip(tips, self.yolo_outputs)):
             F, C, H, W = t.shape
@@ -551,8 +610,8 @@ class YOLOV3Head:
                 F = F // self.k
             frames = F if frames is None else frames
             assert frames == F, "all scales must carry the same number of frames"
-            s.tip_nhwc_bf16 = t.data_ptr()
-            s.weight_bf16 = o.prediction.weight_bf16.data_ptr()
+            s.tip_nhwc_bf16 = t.data.data_ptr() if split else t.data_ptr()
+            s.weight_bf16 = (o.prediction.weight_split if split else o.prediction.weight_bf16).data_ptr()
             s.bias = o.prediction.bias.data_ptr()
             s.H, s.W, s.Cin = H, W, C
             s.stride = float(o._stride)
@@ -570,12 +629,17 @@ class YOLOV3Head:
     def _prepare(self, tips):
         lead = None
         flat = []
+        split = self._precision == _lib.VD_PREC_FP32_SPLIT
         for t in tips:
+            if isinstance(t, SplitF32):
+                assert split, "SplitF32 tips need precision='fp32'"
+                flat.append(t)
+                continue
             _require_cuda(t, "tip")
             if t.dim() == 5:
                 lead = (t.shape[0], t.shape[1])
                 t = t.reshape((t.shape[0] * t.shape[1],) + tuple(t.shape[2:]))
-            flat.append(to_nhwc_bf16(t))
+            flat.append(to_nhwc_split(t) if split else to_nhwc_bf16(t))
         T = 1
         if self.temporal in ("max", "mean"):
             assert lead is not None, "temporal pooling needs (B,K,C,H,W) tips"

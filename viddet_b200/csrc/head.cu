@@ -73,6 +73,7 @@ __host__ __device__ __forceinline__ uint32_t hist_edge(uint32_t bin) {   // smal
 struct HeadKernelParams {
     HeadGeom g;
     int frames, K_frames;
+    int split;                           // fp32-parity mode: K_frames = 3 virtual planes (A_hi W_hi + A_lo W_hi + A_hi W_lo), operands stored as hi/lo bf16 planes
     int cin[VD_MAX_SCALES];
     int pb[VD_MAX_SCALES];               // pixel blocks per frame
     int tile_start[VD_MAX_SCALES + 1];   // cumulative tile index per processing slot
@@ -320,8 +321,11 @@ head_kernel(const __grid_constant__ HeadMaps maps, const __grid_constant__ HeadK
                     unsigned char* a_dst = ring + stage * Cfg::STAGE_BYTES;
                     unsigned char* b_dst = a_dst + A_TILE_BYTES;
                     tc::mbar_expect_tx(&sh->full[stage], Cfg::STAGE_BYTES);
-                    tc::tma_load_4d_hint(a_dst, &maps.a[s], &sh->full[stage], c0, pblk * BLOCK_M, kf, f, pol_a);
-                    tc::tma_load_2d_hint(b_dst, &maps.w[s], &sh->full[stage], kf * p.cin[s] + c0, 0, pol_w);
+                    // fp32-parity mode: plane kf of the K loop pairs (A_hi, W_hi), (A_lo, W_hi), (A_hi, W_lo) -- the a_lo * w_lo term (2^-18 relative) is dropped
+                    const int a_pl = p.split ? (kf == 1 ? 1 : 0) : kf;
+                    const int w_pl = p.split ? (kf == 2 ? 1 : 0) : kf;
+                    tc::tma_load_4d_hint(a_dst, &maps.a[s], &sh->full[stage], c0, pblk * BLOCK_M, a_pl, f, pol_a);
+                    tc::tma_load_2d_hint(b_dst, &maps.w[s], &sh->full[stage], w_pl * p.cin[s] + c0, 0, pol_w);
                     c0 += BLOCK_K; if (c0 == p.cin[s]) { c0 = 0; ++kf; }
                     if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
                 }
@@ -1429,8 +1433,15 @@ static int make_plan(const VdHeadParams* hp, HeadPlan* pl) {
     k.frames = hp->frames; k.n_pad = npad; k.n_valid = 3 * (5 + C);
     const int join = hp->join;
     VD_CHECK_ARG(join == VD_JOIN_NONE || join == VD_JOIN_CAT, "head: join %d must be pre-reduced (use vd_temporal_pool for max/mean)", join);
+    VD_CHECK_ARG(hp->precision == VD_PREC_BF16 || hp->precision == VD_PREC_FP32_SPLIT, "head: precision %d", hp->precision);
     k.K_frames = (join == VD_JOIN_CAT) ? hp->K_frames : 1;
     VD_CHECK_ARG(k.K_frames >= 1, "head: K_frames %d", k.K_frames);
+    if (hp->precision == VD_PREC_FP32_SPLIT) {
+        if (join != VD_JOIN_NONE) return set_error(VD_ERR_UNSUPPORTED, "head: VD_PREC_FP32_SPLIT with a late cat join is not supported");
+        for (int s = 0; s < hp->num_scales; ++s)
+            if (hp->scale[s].tconv_weight_bf16) return set_error(VD_ERR_UNSUPPORTED, "head: VD_PREC_FP32_SPLIT with the fused temporal tip cell is not supported");
+        k.split = 1; k.K_frames = 3;
+    }
     int rows = 0, anc = 0, tif = 0;
     for (int s = 0; s < hp->num_scales; ++s) {
         const VdHeadScale& sc = hp->scale[s];
@@ -1487,7 +1498,7 @@ static int make_plan(const VdHeadParams* hp, HeadPlan* pl) {
 static int make_maps(const VdHeadParams* hp, const HeadPlan& pl, HeadMaps* maps) {
     for (int s = 0; s < hp->num_scales; ++s) {
         const VdHeadScale& sc = hp->scale[s];
-        const uint64_t HW = (uint64_t)sc.H * sc.W, Cin = sc.Cin, K = pl.kp.K_frames;
+        const uint64_t HW = (uint64_t)sc.H * sc.W, Cin = sc.Cin, K = pl.kp.split ? 2 : pl.kp.K_frames;   // split: (frames, 2, H, W, Cin) hi / lo planes
         const void* aptr = (sc.tconv_weight_bf16 && sc.tconv_out_nhwc_bf16) ? sc.tconv_out_nhwc_bf16 : sc.tip_nhwc_bf16;
         uint64_t dimsA[4] = {Cin, HW, K, (uint64_t)(hp->frames > 0 ? hp->frames : 1)};
         uint64_t strA[3] = {Cin * 2, HW * Cin * 2, K * HW * Cin * 2};
@@ -1570,6 +1581,10 @@ static int launch_pred(const HeadMaps& maps, const HeadKernelParams& kp, cudaStr
 }  // namespace vd
 
 using namespace vd;
+
+extern "C" size_t vd_sizeof(int which) {
+    return which == 0 ? sizeof(VdHeadScale) : (which == 1 ? sizeof(VdHeadParams) : 0);
+}
 
 extern "C" size_t vd_head_workspace_bytes(const VdHeadParams* p) {
     HeadPlan pl;
@@ -1724,13 +1739,21 @@ extern "C" int vd_head_detections(const VdHeadParams* hp, float* det, void* work
 
 extern "C" int vd_pred_conv(const void* x, int B, int H, int W, int Cin, int K_frames, int join,
                             const void* weight, const float* bias, int N, float* pred, void* stream_) {
+    return vd_pred_conv_ex(x, B, H, W, Cin, K_frames, join, VD_PREC_BF16, weight, bias, N, pred, stream_);
+}
+
+extern "C" int vd_pred_conv_ex(const void* x, int B, int H, int W, int Cin, int K_frames, int join, int precision,
+                               const void* weight, const float* bias, int N, float* pred, void* stream_) {
     VD_CHECK_ARG(weight && (B == 0 || (x && pred)), "pred_conv: null pointer");
+    VD_CHECK_ARG(precision == VD_PREC_BF16 || precision == VD_PREC_FP32_SPLIT, "pred_conv: precision %d", precision);
+    const bool split = precision == VD_PREC_FP32_SPLIT;
+    if (split && join != VD_JOIN_NONE) return set_error(VD_ERR_UNSUPPORTED, "pred_conv: VD_PREC_FP32_SPLIT with a late cat join is not supported");
     VD_CHECK_ARG(B >= 0 && B <= 65535 && H > 0 && W > 0 && N > 0, "pred_conv: bad shape");
     VD_CHECK_ARG(Cin > 0 && Cin % BLOCK_K == 0, "pred_conv: Cin %d must be a multiple of %d", Cin, BLOCK_K);
     VD_CHECK_ARG(join == VD_JOIN_NONE || join == VD_JOIN_CAT, "pred_conv: join %d must be pre-reduced (vd_temporal_pool)", join);
     VD_CHECK_ARG(((uintptr_t)x & 15) == 0 && ((uintptr_t)weight & 15) == 0, "pred_conv: tensors must be 16-byte aligned");
     if (B == 0) return VD_OK;
-    const int K = (join == VD_JOIN_CAT) ? K_frames : 1;
+    const int K = split ? 2 : ((join == VD_JOIN_CAT) ? K_frames : 1);      // planes per frame in memory (split: hi / lo)
     VD_CHECK_ARG(K >= 1, "pred_conv: K_frames %d", K_frames);
     const uint64_t HW = (uint64_t)H * W;
     for (int n0 = 0; n0 < N; n0 += 256) {            // output-channel slices of <= 256 rows of W
@@ -1738,7 +1761,7 @@ extern "C" int vd_pred_conv(const void* x, int B, int H, int W, int Cin, int K_f
         HeadKernelParams kp; memset(&kp, 0, sizeof(kp));
         kp.g.num_scales = 1; kp.g.num_class = 1; kp.g.A = 3;
         kp.g.H[0] = H; kp.g.W[0] = W; kp.g.HW[0] = (int)HW; kp.g.stride[0] = 1.f;
-        kp.frames = B; kp.K_frames = K; kp.cin[0] = Cin;
+        kp.frames = B; kp.K_frames = split ? 3 : K; kp.split = split ? 1 : 0; kp.cin[0] = Cin;
         kp.pb[0] = ceil_div((int)HW, BLOCK_M);
         kp.tile_start[0] = 0; kp.tile_start[1] = kp.pb[0] * B; kp.order[0] = 0;
         kp.tiles_per_frame = kp.pb[0]; kp.total_tiles = kp.pb[0] * B;

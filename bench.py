@@ -6,7 +6,9 @@
 
 A step = one pass of the hot path (fused tcgen05 pred-conv + YOLOOutputV3 decode + exact top-k +
 class-aware NMS) over one 64-frame batch of synthetic VOC-416 tip features resident in HBM
-(configs[1] of BASELINE.json).  Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement".
+(configs[1] of BASELINE.json).  Every step reads a DIFFERENT resident batch (pool of 32) than the one
+its speculative thresholds were learned from.  Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement".
+Other workloads (--workload): coco608_b64, vid416_b64, vid416_t5_w64 (temporal head, cfg 4), targets_c285_b128 (cfg 5).
 """
 from __future__ import annotations
 
@@ -24,14 +26,18 @@ if ROOT not in sys.path:
 
 METRIC = "head+decode+NMS frames/s at 416^2"
 WORKLOADS = {
-    # name: (classes, input size, frames per step per GPU)
-    "voc416_b64": (20, 416, 64),
-    "coco608_b64": (80, 608, 64),
-    "vid416_b64": (30, 416, 64),
+    # name: (classes, input size, frames per step per GPU)                     BASELINE.json configs[]
+    "voc416_b64": (20, 416, 64),       # [1] the configuration the metric is quoted on (default)
+    "coco608_b64": (80, 608, 64),      # [2]
+    "vid416_b64": (30, 416, 64),       #     per-frame head of the VID model
+    "vid416_t5_w64": (30, 416, 320),   # [3] temporal head: 64 windows of T=5 frames per step (clips sharded by rank)
+    "targets_c285_b128": (285, 416, 128),   # [4] YOLOV3PrefetchTargetGenerator, images sharded by rank, no collective
 }
+TEMPORAL_T = 5
 CHANNELS = [1024, 512, 256]
 STRIDES = [32, 16, 8]
-NROT = 4          # distinct resident input sets cycled through, so no step re-reads a cached batch
+NRING = 4         # sessions (workspace + outputs) in flight
+GRAPH_STEPS = 64  # steps per pipeline graph in long runs (a run of <= 96 steps is ONE graph of exactly that many steps)
 
 
 def algorithmic_bytes_per_frame(C, size, elem=2):
@@ -180,67 +186,274 @@ def make_sampler(index):
         return ClockSampler(index)
 
 
-def synth_tips(torch, gen, frames, size, device):
-    """leaky_relu(N(0,1), 0.1) tips (what a conv-BN-LReLU tip emits under identity BN), bf16 NHWC."""
+def measured_tensor_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d.get("bf16_tflops_sustained", 1413.6)), "measured (sustained)"
+    return 1413.6, "fallback"
+
+
+def synth_tips(torch, gen, frames, size, device, T=None):
+    """leaky_relu(N(0,1), 0.1) tips (what a conv-BN-LReLU tip emits under identity BN), bf16 NHWC; T: (frames//T, T, C, H, W)."""
     tips = []
     for c, s in zip(CHANNELS, STRIDES):
         h = size // s
         x = torch.randn((frames, c, h, h), generator=gen, device=device, dtype=torch.float32)
         x = torch.where(x > 0, x, 0.1 * x).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
-        tips.append(x)
+        tips.append(x if T is None else x.reshape(frames // T, T, c, h, h))
     return tips
 
 
+def synth_video_pool(torch, gen, n, frames, size, device, rho=0.95):
+    """'Video-like' pool: batch t+1 = perturbed batch t (AR(1) latent, correlation rho per step), slot by slot."""
+    pool, z = [], None
+    for _ in range(n):
+        tips, zs = [], []
+        for k, (c, s) in enumerate(zip(CHANNELS, STRIDES)):
+            h = size // s
+            e = torch.randn((frames, c, h, h), generator=gen, device=device, dtype=torch.float32)
+            zz = e if z is None else rho * z[k] + (1.0 - rho * rho) ** 0.5 * e
+            zs.append(zz)
+            tips.append(torch.where(zz > 0, zz, 0.1 * zz).to(torch.bfloat16).contiguous(memory_format=torch.channels_last))
+        z = zs
+        pool.append(tips)
+    return pool
+
+
+def pin_to_gpu_numa(index):
+    """Bind this process to the CPUs next to its GPU before any pinned host buffer is allocated (NUMA-local staging)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        phys = int(vis.split(",")[index]) if vis else index
+        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(phys))
+        return True
+    except Exception:
+        return False
+
+
+def base_config(workload):
+    """The keys BOTH arms (--impl ours / reference) emit, identically, so that the driver can match the configurations."""
+    C, size, frames = WORKLOADS[workload]
+    return {"workload": workload, "classes": C, "input": size, "frames_per_step_per_gpu": frames}
+
+
+def workload_metric(workload):
+    if workload.startswith("targets"):
+        return "YOLOv3 target generation images/s (C=285, B=128, M<=100)", "images/s"
+    if workload == "vid416_t5_w64":
+        return "temporal head+decode+NMS frames/s at 416^2 (T=5 windows)", "frames/s"
+    return METRIC, "frames/s"
+
+
 def run_reference(args):
-    """CPU restatement of the MXNet head (MXNet itself is not installable here), all host threads."""
+    """CPU restatement of the MXNet path (MXNet itself is not installable here), all host threads, rank 0 only."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     import numpy as np
-    from oracle import cpu_baseline
-    from tests.util import make_pred_weights, make_tips
     C, size, frames = WORKLOADS[args.workload]
-    sample = args.cpu_frames                     # bounded sample of the 64-frame batch per step
-    rng = np.random.RandomState(1234)
-    tips = make_tips(rng, sample, size=size)
-    ws, bs = make_pred_weights(rng, C)
+    metric, unit = workload_metric(args.workload)
     threads = os.cpu_count() or 1
+    rng = np.random.RandomState(1234)
+    if args.workload.startswith("targets"):
+        from oracle import ref_targets
+        from tests.util import make_gt
+        sample = min(args.cpu_frames, 8)                     # the reference's per-sample Python loop (yolo_target.py:104-130)
+        gt, ids = make_gt(rng, sample, 100, size=size, num_class=C, multi_hot=True)
+        img, xs, anchors, offsets = ref_targets.default_generator_inputs(size)
+        fn = lambda: ref_targets.prefetch_targets(img, xs, anchors, offsets, gt, ids, None, num_class=C)
+        note = "literal numpy restatement of YOLOV3PrefetchTargetGenerator.forward (what a DataLoader worker runs), 1 thread"
+        threads = 1
+    elif args.workload == "vid416_t5_w64":
+        from oracle import cpu_baseline
+        sample = max(TEMPORAL_T, (min(args.cpu_frames, 10) // TEMPORAL_T) * TEMPORAL_T)
+        fn_data = cpu_baseline.make_temporal_sample(rng, sample // TEMPORAL_T, TEMPORAL_T, C, size)
+        fn = lambda: cpu_baseline.temporal_head_forward_cpu(*fn_data, num_class=C, threads=threads)
+        note = "CPU restatement: torch/oneDNN conv3d (3,1,1)+BN+LReLU + conv + numpy decode + C box_nms"
+    else:
+        from oracle import cpu_baseline
+        from tests.util import make_pred_weights, make_tips
+        sample = args.cpu_frames                             # bounded sample of the batch per step
+        tips = make_tips(rng, sample, size=size)
+        ws, bs = make_pred_weights(rng, C)
+        fn = lambda: cpu_baseline.head_forward_cpu(tips, ws, bs, C, threads=threads)
+        note = "CPU restatement of the MXNet path (MXNet unavailable): torch/oneDNN conv + numpy decode + C box_nms"
     for _ in range(max(args.warmup, 1)):
-        cpu_baseline.head_forward_cpu(tips, ws, bs, C, threads=threads)           # warm-up at the timed shape (oneDNN primitive creation)
+        fn()                                                 # warm-up at the timed shape (oneDNN primitive creation)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        cpu_baseline.head_forward_cpu(tips, ws, bs, C, threads=threads)
+        fn()
     dt = time.perf_counter() - t0
     fps = sample * args.steps / dt
     line = {
-        "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
+        "impl": "reference", "metric": metric, "value": fps, "unit": unit, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": args.workload, "classes": C, "input": size, "frames_per_step": sample,
-                   "note": "CPU restatement of the MXNet path (MXNet unavailable): torch/oneDNN conv + numpy decode + C box_nms"},
-        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port",
-                         "sample": "%d steps x %d frames of the %s batch" % (args.steps, sample, args.workload)},
-        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "config": base_config(args.workload),
+        "details": {"sample_per_step": sample, "note": note},
+        "cpu_baseline": {"value": fps, "unit": unit, "cores": threads, "kind": "port",
+                         "sample": "%d steps x %d units of the %s batch" % (args.steps, sample, args.workload)},
+        "e2e": {"value": fps, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line))
     return 0
 
 
+class StepRunner:
+    """n steps of the pipelined head = GRAPH_STEPS-step graphs + ONE graph for the remainder; a run of <= 96 steps is a single
+    graph of exactly that many steps, so every timed step is a steady-state pipelined step (no serial remainder)."""
+
+    def __init__(self, vd, sessions, pool):
+        self.vd, self.sessions, self.pool, self.graphs = vd, sessions, pool, {}
+
+    def graph(self, n):
+        if n not in self.graphs:
+            self.graphs[n] = self.vd.HeadPipeline(self.sessions, steps=n, inputs=self.pool)
+        return self.graphs[n]
+
+    def plan(self, n):
+        if n <= 96:
+            return [n]
+        q, r = divmod(n, GRAPH_STEPS)
+        return [GRAPH_STEPS] * q + ([r] if r else [])
+
+    def prepare(self, n):
+        for k in set(self.plan(n)):
+            self.graph(k)
+
+    def run(self, n):
+        for k in self.plan(n):
+            self.graph(k).cycle()
+
+
+def bench_targets(args, torch, dist, vd, rank, world, local, dev, json_fd):
+    """cfg 5: one step = YOLOV3PrefetchTargetGenerator over 128 images (C=285 multi-hot, <= 100 GTs); images shard by rank, no
+    collective.  HBM-write-bound: 12 435 696 B per image (the five target tensors in their final layout)."""
+    import numpy as np
+    from tests.util import ANCHORS, make_gt
+    C, size, B = WORKLOADS[args.workload]
+    rng = np.random.RandomState(1234 + rank)
+    hs = [size // s for s in STRIDES]
+    xs = [(B, 1, h, h) for h in hs]
+    anchors = [np.asarray(a, np.float32).reshape(1, 1, 3, 2) for a in ANCHORS]
+    offsets = [np.zeros((1, h * h, 1, 2), np.float32) for h in hs]
+    img = (B, 3, size, size)
+    n_anch = 3 * sum(h * h for h in hs)
+    alg = n_anch * (7 + C) * 4 * B
+    sets = []
+    for _ in range(2):
+        gt, ids = make_gt(rng, B, 100, size=size, num_class=C, multi_hot=True)
+        sets.append((torch.from_numpy(gt).to(dev), torch.from_numpy(ids).to(dev)))
+    gen = vd.YOLOV3PrefetchTargetGenerator(C)
+    outs = [gen.alloc_outputs(B, n_anch, dev) for _ in range(2)]          # 1.59 GB per set: every step writes past the L2
+    graphs = []
+    for j in range(2):
+        gen.run_into(img, xs, anchors, offsets, sets[j][0], sets[j][1], None, outs[j])
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            gen.run_into(img, xs, anchors, offsets, sets[j][0], sets[j][1], None, outs[j])
+        graphs.append(g)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = make_sampler(local).start() if rank == 0 else None
+    for i in range(args.warmup):
+        graphs[i % 2].replay()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.monotonic()
+    e0.record()
+    for i in range(args.steps):
+        graphs[i % 2].replay()
+    e1.record()
+    barrier()
+    t1 = time.monotonic()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop(t0, t1) if sampler else None
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = world * B * args.steps / (ms * 1e-3)
+    # e2e: GT boxes / ids from pinned host memory every step, objectness column read back (the loss consumes the rest on device)
+    hgt = [(a.cpu().pin_memory(), b.cpu().pin_memory()) for a, b in sets]
+    hobj = torch.empty((B, n_anch, 1)).pin_memory()
+    h2d = sum(t.numel() * t.element_size() for t in hgt[0]); d2h = hobj.numel() * 4
+    ne = max(5, min(args.steps, 30))
+
+    def e2e_step(i):
+        j = i % 2
+        sets[j][0].copy_(hgt[j][0], non_blocking=True); sets[j][1].copy_(hgt[j][1], non_blocking=True)
+        graphs[j].replay()
+        hobj.copy_(outs[j][0], non_blocking=True)
+    for i in range(3):
+        e2e_step(i)
+    barrier()
+    x0, x1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    x0.record()
+    for i in range(ne):
+        e2e_step(i)
+    x1.record()
+    barrier()
+    ems = x0.elapsed_time(x1)
+    if world > 1:
+        t = torch.tensor([ems], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ems = float(t.item())
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import ref_targets
+        gt, ids = make_gt(np.random.RandomState(1234), 8, 100, size=size, num_class=C, multi_hot=True)
+        im, x_, an, of = ref_targets.default_generator_inputs(size)
+        t_0 = time.perf_counter(); reps = 0
+        while time.perf_counter() - t_0 < 10.0:
+            ref_targets.prefetch_targets(im, x_, an, of, gt, ids, None, num_class=C); reps += 1
+        secs = time.perf_counter() - t_0
+        cpu = {"value": 8 * reps / secs, "unit": "images/s", "cores": 1, "kind": "port",
+               "sample": "%d passes over 8 images (%.1f s): literal numpy restatement of the per-GT Python loop" % (reps, secs)}
+    peak, peak_kind = measured_peaks()
+    kms = ms / args.steps
+    if rank == 0:
+        metric, unit = workload_metric(args.workload)
+        line = {"metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": kms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": base_config(args.workload),
+                "details": {"gt": "count ~U{0..100}, 1-5 hot classes per GT", "l2": "outputs %.0f MB/step, 2 rotating output sets" % (alg / 1e6),
+                            "sharding": "images split by rank, no collective" if world > 1 else "single GPU"},
+                "roofline": {"bound": "hbm", "kernel": "targets_fill_kernel + targets_scatter_kernel (one step)", "achieved": alg / (kms * 1e-3) / 1e9,
+                             "peak": peak, "peak_kind": peak_kind, "unit": "GB/s", "frac": alg / (kms * 1e-3) / 1e9 / peak, "traffic": None,
+                             "algorithmic_bytes_per_launch": alg, "kernel_ms": kms},
+                "cpu_baseline": cpu,
+                "e2e": {"value": world * B * ne / (ems * 1e-3), "unit": unit, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": ne},
+                "gpu_launches": args.steps * 2, "clocks": clocks}
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=2000)
-    ap.add_argument("--warmup", type=int, default=32)
+    ap.add_argument("--steps", type=int, default=2048)
+    ap.add_argument("--warmup", type=int, default=64)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="voc416_b64", choices=sorted(WORKLOADS))
     ap.add_argument("--cpu-frames", type=int, default=64, help="frames per CPU-baseline step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-pipeline", action="store_true", help="serial step graphs instead of the overlapped pipeline")
-    ap.add_argument("--rotations", type=int, default=4, help="ring rotations captured per pipeline graph")
+    ap.add_argument("--data", default="iid", choices=["iid", "video", "same"],
+                    help="iid: pool of distinct iid batches (default); video: batch t+1 = perturbed batch t; same: each session replays its own batch (r1 behaviour)")
+    ap.add_argument("--pool", type=int, default=0, help="distinct resident input batches (default 32; 8 for the temporal workload)")
+    ap.add_argument("--gather", default="peer", choices=["peer", "nccl"], help="multi-GPU detection gather: fused into the NMS sink over NVLink (peer) or staged NCCL all_gather")
     args = ap.parse_args()
     if args.impl == "reference":
-        if args.steps == 2000 and args.warmup == 32:       # defaults sized for the GPU arm
+        if args.steps == 2048 and args.warmup == 64:       # defaults sized for the GPU arm
             args.steps, args.warmup = 3, 1
         return run_reference(args)
     args.warmup = max(args.warmup, 3)               # timing rules: at least 3 warm-up steps (the line reports what was run)
@@ -260,27 +473,51 @@ def main():
     assert torch.cuda.is_available(), "bench.py (impl=ours) needs a B200; there is no CPU fallback"
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = pin_to_gpu_numa(local)
+    if args.workload.startswith("targets"):
+        rc = bench_targets(args, torch, dist, viddet_b200, rank, world, local, dev, json_fd)
+        if world > 1:
+            dist.barrier(); dist.destroy_process_group()
+        return rc
     C, size, frames = WORKLOADS[args.workload]
+    temporal = args.workload == "vid416_t5_w64"
+    T = TEMPORAL_T if temporal else None
+    npool = args.pool or (8 if temporal else 32)
+    if args.data == "same":
+        npool = NRING
 
     gen = torch.Generator(device=dev).manual_seed(1234 + rank)
     cpu_gen = torch.Generator().manual_seed(1234)
-    head = viddet_b200.YOLOV3Head(C).initialize(generator=cpu_gen)       # U(-0.07,0.07), bias 0 (detect_yolo3.py:885)
+    head = viddet_b200.YOLOV3Head(C, temporal="conv21" if temporal else None).initialize(generator=cpu_gen)   # U(-0.07,0.07), bias 0 (detect_yolo3.py:885)
     head.set_nms(nms_thresh=0.45, nms_topk=400, post_nms=100)            # detect_yolo3.py:200
-    # ring of NROT resident batches; the detections of the whole ring live in one tensor per field (gathered per cycle)
-    # (one allocation, field-major, so that the gather is ONE copy + ONE collective)
-    nf = NROT * frames * 100
-    flat = torch.empty((nf * 6,), device=dev)
-    ids_all, scores_all, boxes_all = flat[:nf].view(NROT * frames, 100, 1), flat[nf:2 * nf].view(NROT * frames, 100, 1), flat[2 * nf:].view(NROT * frames, 100, 4)
+    # resident input pool (clips / frames of this rank) + ring of NRING sessions (workspace + outputs)
+    if args.data == "video":
+        assert not temporal
+        pool = synth_video_pool(torch, gen, npool, frames, size, dev)
+    else:
+        pool = [synth_tips(torch, gen, frames, size, dev, T) for _ in range(npool)]
+    nf = NRING * frames * 100
+    peer, gather_kind = None, "single GPU"
+    if world > 1 and args.gather == "peer":
+        try:
+            peer = vdist.PeerGather(nf * 6)
+            gather_kind = "fused: the NMS kernel's sink stores each result row into every peer's gather buffer over NVLink (CUDA IPC mapped), no collective in the step"
+        except Exception as e:                          # noqa: BLE001 -- any failure of the IPC setup falls back to the NCCL gather
+            sys.stderr.write("PeerGather unavailable (%s): falling back to the staged NCCL gather\n" % (e,))
+            peer = None
+    flat = peer.slot[:nf * 6] if peer is not None else torch.empty((nf * 6,), device=dev)
+    ids_all, scores_all, boxes_all = flat[:nf].view(NRING * frames, 100, 1), flat[nf:2 * nf].view(NRING * frames, 100, 1), flat[2 * nf:].view(NRING * frames, 100, 4)
     sessions = []
-    for j in range(NROT):
+    for j in range(NRING):
         sl = slice(j * frames, (j + 1) * frames)
-        s = head.session(synth_tips(torch, gen, frames, size, dev), out=(ids_all[sl], scores_all[sl], boxes_all[sl]))
-        s.capture()
+        s = head.session(pool[j % npool], out=(ids_all[sl], scores_all[sl], boxes_all[sl]), mirrors=peer.deltas if peer is not None else None)
         sessions.append(s)
-    pipe = None if args.no_pipeline else viddet_b200.HeadPipeline(sessions, rotations=args.rotations)
-    spc = pipe.steps_per_cycle if pipe else 1
-    fields = (ids_all, scores_all, boxes_all)
-    if world > 1:                                        # the path's only collective: final detection gather, off the critical path
+    pool_flat = [[t.reshape((-1,) + tuple(t.shape[-3:])) if t.dim() == 5 else t for t in p] for p in pool]
+    pool_flat = [[viddet_b200.to_nhwc_bf16(t) for t in p] for p in pool_flat]
+    runner = StepRunner(viddet_b200, sessions, None if args.data == "same" else pool_flat)
+    nccl_gather = world > 1 and peer is None
+    if nccl_gather:                                      # fallback: staged all_gather of the ring per graph, off the critical path
+        gather_kind = "NCCL all_gather_into_tensor of the ring's detections per graph on a side stream (staged snapshot)"
         side = torch.cuda.Stream()
         snaps = [torch.empty_like(flat) for _ in range(2)]
         gout = torch.empty((world * flat.numel(),), device=dev)
@@ -288,7 +525,6 @@ def main():
     state = {"c": 0}
 
     def gather_ring():
-        """all_gather of the ring's detections on a side stream (double-buffered snapshot), overlapped with the next cycle."""
         c = state["c"] % 2
         state["c"] += 1
         main = torch.cuda.current_stream()
@@ -302,120 +538,177 @@ def main():
             gather_done[c] = torch.cuda.Event(); gather_done[c].record(side)
 
     def run_steps(n):
-        """n steps = n batches; whole cycles go through the overlapped pipeline, the remainder through the serial graphs."""
-        i = 0
-        while pipe is not None and n - i >= spc:
-            pipe.cycle(); i += spc
-            if world > 1:
-                gather_ring()
-        while i < n:
-            sessions[i % NROT].replay(); i += 1
-            if world > 1 and (i % NROT == 0 or i == n):
-                gather_ring()
+        if not nccl_gather:
+            runner.run(n)
+            return
+        for k in runner.plan(n):
+            runner.graph(k).cycle()
+            gather_ring()
 
     def barrier():
-        if world > 1:
+        if nccl_gather:
             torch.cuda.current_stream().wait_stream(side)
+        if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
     sampler = make_sampler(local).start() if rank == 0 else None       # polling (and NVML's lazy init) is warm before the timed region
-    run_steps(max(args.warmup, spc))
+    runner.prepare(args.steps)
+    runner.prepare(max(args.warmup, 2 * NRING))
+    run_steps(max(args.warmup, 2 * NRING))
     barrier()
+    st0 = [s.stats() for s in sessions]
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     t_mono0 = time.monotonic()
     e0.record()
     run_steps(args.steps)
-    if world > 1:
+    if nccl_gather:
         torch.cuda.current_stream().wait_stream(side)     # the last gather is part of the job
     e1.record()
     barrier()
     t_mono1 = time.monotonic()
     ms = e0.elapsed_time(e1)
     clocks = sampler.stop(t_mono0, t_mono1) if sampler else None
+    st1 = [s.stats() for s in sessions]
+    redone = sum(((b[0] - a[0]) & 0xffffffff) for a, b in zip(st0, st1))
+    calls = sum(((b[1] - a[1]) & 0xffffffff) for a, b in zip(st0, st1))
     if world > 1:
         t = torch.tensor([ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
     value = world * frames * args.steps / (ms * 1e-3)
+    gather_verified = None
+    if peer is not None:                                  # outside the timed region: every rank's slot of MY buffer == what that rank holds
+        ref_g = torch.empty((world, peer.slot_floats), device=dev)
+        dist.all_gather_into_tensor(ref_g.view(-1), peer.slot.contiguous())
+        gather_verified = bool(torch.equal(ref_g.view(torch.int32), peer.gathered.view(torch.int32)))
 
-    # ---- dominant kernel (fused head kernel) timed inside real steps: CUDA events around the kernel on the launching
-    #      stream, each followed by its NMS kernel so the workspace state (histograms, hints) is the steady-state one
+    # ---- dominant kernel timed inside real steps: CUDA events around the kernel on the launching stream, each followed by
+    #      its NMS kernel so the workspace state is the steady-state one
     ksteps = max(20, min(args.steps, 100))
-    pairs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(ksteps)]
+    stages = ([_lib.VD_STAGE_TCONV] if temporal else []) + [_lib.VD_STAGE_HEAD, _lib.VD_STAGE_NMS]
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(len(stages) + 1)] for _ in range(ksteps)]
     for i in range(4):
-        sessions[i % NROT].run()
+        sessions[i % NRING].run()
     torch.cuda.synchronize()
     for i in range(ksteps):
-        a, b, c = pairs[i]
-        a.record(); sessions[i % NROT].run(_lib.VD_STAGE_HEAD); b.record(); sessions[i % NROT].run(_lib.VD_STAGE_NMS); c.record()
+        evs[i][0].record()
+        for k, stg in enumerate(stages):
+            sessions[i % NRING].run(stg)
+            evs[i][k + 1].record()
     torch.cuda.synchronize()
-    head_ms = sorted(a.elapsed_time(b) for a, b, c in pairs)[ksteps // 2]
-    nms_ms = sorted(b.elapsed_time(c) for a, b, c in pairs)[ksteps // 2]
+    med = [sorted(e[k].elapsed_time(e[k + 1]) for e in evs)[ksteps // 2] for k in range(len(stages))]
+    head_ms, nms_ms = med[-2], med[-1]
+    tconv_ms = med[0] if temporal else None
     peak, peak_kind = measured_peaks()
     alg_bytes = algorithmic_bytes_per_frame(C, size) * frames
-    # Two upper bounds of the head kernel's launch duration, both from CUDA events on its launching stream: (a) events around
-    # one direct launch inside a real call (includes the launch latency of an eager launch, ~3 us); (b) the step period of the
-    # timed region itself -- in the pipeline graph the main stream runs exactly one head kernel per step, back to back, so no
-    # head kernel can last longer than a step.  The tighter bound is used (ncu: 38.7 us per launch, profiles/).
-    head_ms_events = head_ms
-    if pipe is not None and world == 1:
-        head_ms = min(head_ms, ms / args.steps)
-    achieved = alg_bytes / (head_ms * 1e-3) / 1e9
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "traffic_head_kernel_%s.json" % args.workload)
-    if os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get("traffic_bytes_per_launch")
+    step_ms = ms / args.steps
+    if temporal:
+        # cfg 4 is tensor-bound: 2*13*sum HW*C^2 (13 non-zero taps of a k=3 zero-padded conv over T=5) + pred conv, per window
+        windows = frames // TEMPORAL_T
+        hw_c2 = sum((size // s) ** 2 * c * c for s, c in zip(STRIDES, CHANNELS))
+        hw_c = sum((size // s) ** 2 * c for s, c in zip(STRIDES, CHANNELS))
+        f_tconv = 2.0 * (3 * TEMPORAL_T - 2) * hw_c2 * windows
+        f_all = f_tconv + 2.0 * 3 * (5 + C) * hw_c * TEMPORAL_T * windows
+        tpeak, tkind = measured_tensor_peak()
+        roof = {"bound": "tensor", "kernel": "temporal_conv_pair_kernel x3 scales (tcgen05 cta_group::2 implicit GEMM, tip cell of layers.py:82-89)",
+                "achieved": f_tconv / (tconv_ms * 1e-3) / 1e12, "peak": tpeak, "peak_kind": tkind, "unit": "TFLOP/s",
+                "frac": f_tconv / (tconv_ms * 1e-3) / 1e12 / tpeak, "traffic": None, "algorithmic_flops_per_launch": f_tconv,
+                "kernel_ms": tconv_ms, "head_kernel_ms": head_ms, "nms_kernel_ms": nms_ms,
+                "path_frac": f_all / (step_ms * 1e-3) / 1e12 / tpeak, "path_flops_per_step": f_all}
+    else:
+        # Two upper bounds of the head kernel's launch duration, both from CUDA events on its launching stream: (a) events
+        # around one direct launch inside a real call (includes ~3 us of eager-launch latency); (b) the step period of the
+        # timed region -- the pipeline graph runs exactly one head kernel per step, back to back, so no head kernel can last
+        # longer than a step.  The tighter bound is used.
+        head_ms_events = head_ms
+        if world == 1:
+            head_ms = min(head_ms, step_ms)
+        achieved = alg_bytes / (head_ms * 1e-3) / 1e9
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "traffic_head_kernel_%s.json" % args.workload)
+        if os.path.exists(tpath):
+            traffic = json.load(open(tpath)).get("traffic_bytes_per_launch")
+        roof = {"bound": "hbm", "kernel": "head_kernel<EPI_SPEC> (tcgen05 pred conv + decode + speculative candidate filter; exact EPI_FILTER fallback idle in the steady state)",
+                "achieved": achieved, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": traffic, "algorithmic_bytes_per_launch": alg_bytes,
+                "kernel_ms": head_ms, "kernel_ms_events_around_one_eager_launch": head_ms_events,
+                "kernel_ms_note": "min(events around one eager launch in a real call, step period of the pipelined timed region: one head kernel per step on the main stream)",
+                "nms_kernel_ms": nms_ms, "path_frac": alg_bytes / (step_ms * 1e-3) / 1e9 / peak}
 
-    # ---- end to end through the public API with HOST buffers (pinned), H2D + D2H inside the timed region
-    host_sets = [[t.cpu().pin_memory() for t in s.tips] for s in sessions[:2]]
+    # ---- worst case of the speculative path: EVERY frame fails its proof (thresholds learned on data scaled the other way),
+    #      so the exact pair redoes the whole batch inside the call
+    allfail = None
+    if not temporal:
+        hi = [(t.float() * 1.6).to(torch.bfloat16).contiguous(memory_format=torch.channels_last) for t in pool_flat[0]]
+        lo = [(t.float() * 0.5).to(torch.bfloat16).contiguous(memory_format=torch.channels_last) for t in pool_flat[0]]
+        s0 = sessions[0]
+        a0 = s0.stats()
+        tms = []
+        for i in range(6):
+            s0.rebind(hi if i % 2 == 0 else lo)
+            x0, x1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            x0.record(); s0.run(); x1.record()
+            torch.cuda.synchronize()
+            tms.append(x0.elapsed_time(x1))
+        a1 = s0.stats()
+        allfail = {"step_ms": sorted(tms)[len(tms) // 2], "frames_redone_per_step": ((a1[0] - a0[0]) & 0xffffffff) / 6.0}
+        del hi, lo
+        s0.rebind(pool_flat[0]); s0.run(); s0.run()
+
+    # ---- end to end through the public API with HOST buffers (pinned, NUMA-local), H2D + D2H inside the timed region
+    esess = sessions[:2]
+    for j, s_ in enumerate(esess):
+        s_.rebind([t.clone() for t in pool_flat[j]])          # private device input buffers for the e2e leg
+    host_sets = [[t.cpu().pin_memory() for t in pool_flat[j]] for j in range(4)]
     host_outs = [torch.empty((frames, 100, 6), dtype=torch.float32).pin_memory() for _ in range(2)]
     h2d = sum(t.numel() * t.element_size() for t in host_sets[0])
     d2h = host_outs[0].numel() * 4
-    sess = sessions[0]
     copy_stream = torch.cuda.Stream()
     h2d_done = [torch.cuda.Event() for _ in range(2)]
     compute_done = [torch.cuda.Event() for _ in range(2)]
     for ev in compute_done:
         ev.record()
 
-    gather_one = torch.empty((world * frames, 100, 6), device=dev) if world > 1 else None
-
-    def e2e_step(i):
+    def e2e_step(i, compute=True):
         """Two device input buffers: the H2D copy of step i+1 (copy stream) runs under the head of step i (main stream); every
-        step's inputs cross PCIe and its (64,100,6) result is read back, both inside the timed region."""
+        step's inputs cross PCIe from a different host batch and its (frames,100,6) result is read back, inside the timed region.
+        (Multi-GPU: the detection gather is the NMS kernel's mirrored stores; nothing else crosses ranks.)"""
         j = i % 2
-        s_ = sessions[j]
+        s_ = esess[j]
         main = torch.cuda.current_stream()
         with torch.cuda.stream(copy_stream):
             copy_stream.wait_event(compute_done[j])              # the buffer's previous step has consumed it
-            for dst, src in zip(s_.tips, host_sets[j]):
+            for dst, src in zip(s_.tips, host_sets[i % 4]):
                 dst.copy_(src, non_blocking=True)
             h2d_done[j].record(copy_stream)
         main.wait_event(h2d_done[j])
-        s_.replay()
-        packed = s_.packed()
-        host_outs[j].copy_(packed, non_blocking=True)
+        if compute:
+            s_.run()
+            host_outs[j].copy_(s_.packed(), non_blocking=True)
         compute_done[j].record(main)
+
+    def timed(fn, n):
+        for i in range(3):
+            fn(i)
+        barrier()
+        x0, x1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        x0.record()
+        for i in range(n):
+            fn(i)
+        x1.record()
+        barrier()
+        t_ms = x0.elapsed_time(x1)
         if world > 1:
-            dist.all_gather_into_tensor(gather_one, packed)
+            t = torch.tensor([t_ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            t_ms = float(t.item())
+        return t_ms
 
     e2e_steps = max(5, min(args.steps, 30))
-    for i in range(3):
-        e2e_step(i)
-    barrier()
-    x0, x1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    x0.record()
-    for i in range(e2e_steps):
-        e2e_step(i)
-    x1.record()
-    barrier()
-    e2e_ms = x0.elapsed_time(x1)
-    if world > 1:
-        t = torch.tensor([e2e_ms], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_ms = float(t.item())
+    e2e_ms = timed(e2e_step, e2e_steps)
+    copy_ms = timed(lambda i: e2e_step(i, compute=False), e2e_steps)      # the same H2D traffic alone: the link's ceiling for this rank count
     e2e_value = world * frames * e2e_steps / (e2e_ms * 1e-3)
 
     # ---- CPU baseline beside it (rank 0, N = 1 only): the oracle restatement on a bounded sample
@@ -423,45 +716,55 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         import numpy as np
         from oracle import cpu_baseline
-        from tests.util import make_pred_weights, make_tips
-        rng = np.random.RandomState(1234)
         threads = os.cpu_count() or 1
-        ctips = make_tips(rng, args.cpu_frames, size=size)
-        cws, cbs = make_pred_weights(rng, C)
-        cpu_baseline.head_forward_cpu(ctips, cws, cbs, C, threads=threads)      # untimed warm-up at the timed shape (oneDNN primitive creation)
-        reps = 24                                     # ~10 s of CPU work on the box's host cores
-        fps, secs, nfr = cpu_baseline.time_head_cpu(ctips, cws, cbs, C, repeats=reps, threads=threads)
-        cpu = {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port",
-               "sample": "%d passes over %d synthetic %s frames (%.1f s); torch/oneDNN conv + numpy decode + C box_nms"
-                         % (reps, args.cpu_frames, args.workload, secs)}
+        rng = np.random.RandomState(1234)
+        if temporal:
+            data = cpu_baseline.make_temporal_sample(rng, 2, TEMPORAL_T, C, size)
+            fn = lambda: cpu_baseline.temporal_head_forward_cpu(*data, num_class=C, threads=threads)
+            nfr, what = 2 * TEMPORAL_T, "torch/oneDNN conv3d (3,1,1)+BN+LReLU + conv + numpy decode + C box_nms"
+        else:
+            from tests.util import make_pred_weights, make_tips
+            ctips = make_tips(rng, args.cpu_frames, size=size)
+            cws, cbs = make_pred_weights(rng, C)
+            fn = lambda: cpu_baseline.head_forward_cpu(ctips, cws, cbs, C, threads=threads)
+            nfr, what = args.cpu_frames, "torch/oneDNN conv + numpy decode + C box_nms"
+        fn()                                          # untimed warm-up at the timed shape (oneDNN primitive creation)
+        t_0 = time.perf_counter(); reps = 0
+        while time.perf_counter() - t_0 < 10.0:       # ~10 s of CPU work on the box's host cores
+            fn(); reps += 1
+        secs = time.perf_counter() - t_0
+        cpu = {"value": nfr * reps / secs, "unit": "frames/s", "cores": threads, "kind": "port",
+               "sample": "%d passes over %d synthetic %s frames (%.1f s); %s" % (reps, nfr, args.workload, secs, what)}
 
     if rank == 0:
+        metric, unit = workload_metric(args.workload)
         line = {
-            "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": args.workload, "classes": C, "input": size, "frames_per_step_per_gpu": frames,
-                       "carrier": "bf16 channels-last tips, bf16 weights, fp32 accumulate/decode/NMS",
-                       "nms": {"thresh": 0.45, "valid": 0.01, "topk": 400, "post": 100},
-                       "l2": "inputs %.0f MB/step > 126 MB L2; %d rotating resident input sets" % (alg_bytes / 1e6, NROT),
-                       "launch": ("cuda graph per %d steps: head kernel of batch j+1 overlapped with the top-k/NMS kernel of batch j" % spc) if pipe else "cuda graph per step (serial)",
-                       "sharding": "frames split by rank, all_gather of the detections per cycle on a side stream" if world > 1 else "single GPU"},
-            "roofline": {"bound": "hbm", "kernel": "head_kernel<EPI_SPEC> (tcgen05 pred conv + decode + speculative candidate filter; exact EPI_FILTER fallback idle in the steady state)",
-                         "achieved": achieved, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": traffic, "algorithmic_bytes_per_launch": alg_bytes,
-                         "kernel_ms": head_ms, "kernel_ms_events_around_one_eager_launch": head_ms_events,
-                         "kernel_ms_note": "min(events around one eager launch in a real call, step period of the pipelined timed region: one head kernel per step on the main stream)",
-                         "nms_kernel_ms": nms_ms,
-                         "path_frac": (alg_bytes * world * args.steps / (ms * 1e-3) / 1e9 / world) / peak},
+            "config": base_config(args.workload),
+            "details": {"carrier": "bf16 channels-last tips, bf16 weights, fp32 accumulate/decode/NMS",
+                        "nms": {"thresh": 0.45, "valid": 0.01, "topk": 400, "post": 100},
+                        "l2": "inputs %.0f MB/step > 126 MB L2; pool of %d distinct resident batches, %s" % (alg_bytes / 1e6, npool, {"iid": "iid", "video": "video-like (AR(1), rho 0.95 per step)", "same": "each session replays its own batch"}[args.data]),
+                        "launch": "cuda graphs of %s steps: head kernel of batch j+1 overlapped with the top-k/NMS kernel of batch j" % "+".join(str(k) for k in sorted(set(runner.plan(args.steps)), reverse=True)),
+                        "speculation": {"thresholds_learned_on": "a different batch than the one filtered" if args.data != "same" else "the same batch (r1 behaviour)",
+                                        "frames_redone_per_step": redone / max(calls, 1), "steps_counted": calls,
+                                        "all_frames_fail_worst_case": allfail},
+                        "sharding": ("%s split by rank; gather = %s" % ("clips" if temporal else "frames", gather_kind)) if world > 1 else "single GPU",
+                        "gather_verified": gather_verified, "numa_pinned": numa},
+            "roofline": roof,
             "cpu_baseline": cpu,
-            "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": e2e_steps, "note": "pinned host bf16 NHWC tips -> H2D (copy stream, double-buffered under the previous step's compute) -> fused head -> D2H of (64,100,6); PCIe-bound (measured H2D ceiling 55.2 GB/s)"},
-            "gpu_launches": args.steps * sess.launches,                   # head kernel + NMS kernel per step
+            "e2e": {"value": e2e_value, "unit": unit, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "steps": e2e_steps, "h2d_only_gbs_per_rank": h2d * e2e_steps / (copy_ms * 1e-3) / 1e9,
+                    "note": "pinned host bf16 NHWC tips (4 host batches, NUMA-local) -> H2D (copy stream, double-buffered under the previous step's compute) -> fused head -> D2H of (frames,100,6); PCIe-bound: h2d_only_gbs_per_rank is the same traffic with no compute"},
+            "gpu_launches": args.steps * sessions[0].launches,
             "clocks": clocks,
         }
         os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.barrier()
+        if peer is not None:
+            peer.close()
         dist.destroy_process_group()
     return 0
 

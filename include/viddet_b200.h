@@ -35,6 +35,7 @@ extern "C" {
 
 #define VD_MAX_SCALES 3
 #define VD_MAX_TOPK   1024      /* largest nms_topk the device NMS handles */
+#define VD_MAX_MIRRORS 7        /* peer copies of the fused head's outputs (8 GPUs of one box) */
 
 /* YOLOOutputV3 decode modes (yolo3.py:179-199) */
 #define VD_MODE_INFER    0      /* (B, C*HW*A, 6) rows [id, score, x1, y1, x2, y2]            */
@@ -149,6 +150,12 @@ typedef struct VdHeadParams {
     int precision;               /* VD_PREC_BF16 (0) or VD_PREC_FP32_SPLIT: tips (frames,2,H,W,Cin), weights (N_out,2,Cin) */
     int reserved0;               /* must be 0                                                    */
     VdHeadScale scale[VD_MAX_SCALES];
+    /* Output mirrors (multi-GPU detection gather): every ids / scores / bboxes element vd_head_forward stores at
+     * address a is also stored at a + mirror_delta[i] (bytes, multiples of 16), i < n_mirrors.  The targets are the same slot of
+     * the gather buffers of the peer GPUs, mapped into this process (vd_ipc_open); 0 mirrors = local outputs only. */
+    int n_mirrors;
+    int reserved1;               /* must be 0                                                    */
+    long long mirror_delta[VD_MAX_MIRRORS];
 } VdHeadParams;
 
 /* How the fused call works (and what the workspace is for).  The head kernel filters every frame with a per-frame-slot
@@ -185,9 +192,10 @@ int vd_head_forward(const VdHeadParams* p, float* ids, float* scores, float* bbo
 int vd_head_forward_stages(const VdHeadParams* p, float* ids, float* scores, float* bboxes,
                            int32_t* keep_rows_or_null, void* workspace, size_t workspace_bytes,
                            void* stream, int stage_mask);
-/* Byte offset, inside the workspace, of eight uint32 statistics of the LAST completed call: word [4] = number of frames
+/* Byte offset, inside the workspace, of eight uint32 statistics: word [4] = number of frames of the LAST completed call
  * whose speculative candidate list could not be proven complete and that were redone by the exact path (0 in the steady
- * state; all frames on the first call).  For tests and monitoring; reading it needs a stream synchronisation. */
+ * state; all frames on the first call); word [5] = running total of such frames and word [6] = running total of completed
+ * calls on this workspace (both wrap; take differences).  For tests and monitoring; reading needs a stream synchronisation. */
 size_t vd_head_stats_offset(const VdHeadParams* p);
 /* Number of kernels one vd_head_forward call launches for these parameters (-1 on bad params). */
 int vd_head_launch_count(const VdHeadParams* p);
@@ -195,6 +203,17 @@ int vd_head_launch_count(const VdHeadParams* p);
  * (what `concat(all_detections)` holds at yolo3.py:523) instead of running NMS. */
 int vd_head_detections(const VdHeadParams* p, float* det, void* workspace, size_t workspace_bytes,
                        void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Peer-mapped buffers for the output mirrors above (one process per GPU on one NVLink / NVSwitch box; detect_yolo3.py:211-213
+ * shards the batch over the GPUs, the results meet on the host -- here in every rank's gather buffer).  vd_ipc_alloc:
+ * cudaMalloc'ed zero-filled device buffer + its 64-byte CUDA IPC handle (exchange it through torch.distributed); vd_ipc_open
+ * maps a peer's buffer (peer access enabled lazily); vd_ipc_close unmaps it, vd_ipc_free releases an own buffer.
+ * ------------------------------------------------------------------------------------------ */
+int vd_ipc_alloc(size_t bytes, void** dev_ptr_out, unsigned char handle_out[64]);
+int vd_ipc_open(const unsigned char handle[64], void** dev_ptr_out);
+int vd_ipc_close(void* dev_ptr);
+int vd_ipc_free(void* dev_ptr);
 
 /* Temporal tip cell alone: Conv3D((3,1,1), pad (1,0,0), no bias) + BN + LeakyReLU(0.1)
  * (layers.py:82-89).  x, y: (B, T, H, W, C) bf16 channels-last; weight (3, C, C) bf16

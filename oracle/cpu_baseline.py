@@ -59,3 +59,32 @@ def time_head_cpu(tips, ws, bs, num_class, repeats=1, threads=None):
         head_forward_cpu(tips, ws, bs, num_class, threads=threads)
     dt = time.perf_counter() - t0
     return frames * repeats / dt, dt, frames * repeats
+
+
+# ------------------------------------------------------------------------------------------------
+# temporal head (BASELINE configs[3]): Conv3D((3,1,1)) + BN + LeakyReLU tip cell per scale
+# (layers.py:82-89), then the per-frame head over B*T frames (TimeDistributed, yolo3_temporal.py:468,542-555)
+# ------------------------------------------------------------------------------------------------
+def make_temporal_sample(rng, windows, T, num_class, size=416):
+    """(tips5, tip-cell weights, pred weights, pred biases) for `temporal_head_forward_cpu`."""
+    from tests.util import CHANNELS, make_pred_weights, make_tips
+    tips5 = make_tips(rng, windows, size=size, T=T)
+    tw = [rng.uniform(-0.07, 0.07, (c, c, 3, 1, 1)).astype(np.float32) for c in CHANNELS]
+    ws, bs = make_pred_weights(rng, num_class)
+    return tips5, tw, ws, bs
+
+
+def temporal_head_forward_cpu(tips5, tw, ws, bs, num_class, threads=None):
+    import torch
+    threads = threads or os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    mids = []
+    with torch.no_grad():
+        for x, w in zip(tips5, tw):
+            B, T, C, H, W = x.shape
+            xt = torch.from_numpy(x).permute(0, 2, 1, 3, 4)                       # swapaxes to (B,C,T,H,W), yolo3_temporal.py:231
+            y = torch.nn.functional.conv3d(xt, torch.from_numpy(w), padding=(1, 0, 0))
+            y = y / float(np.sqrt(1.0 + 1e-5))                                   # identity BatchNorm (eps 1e-5)
+            y = torch.nn.functional.leaky_relu(y, 0.1)
+            mids.append(y.permute(0, 2, 1, 3, 4).reshape(B * T, C, H, W).contiguous().numpy())
+    return head_forward_cpu(mids, ws, bs, num_class, threads=threads)

@@ -55,3 +55,17 @@ def test_shard_range_covers_everything():
             sizes = [e - b for b, e in spans]
             assert max(sizes) - min(sizes) <= 1
     assert vdist.shard_clips([10, 20, 30, 40, 50], 1, 2) == [1, 3]
+
+
+def test_mirror_layout_addresses():
+    """Host-side address arithmetic of the fused detection gather (PeerGather): rank r's slot sits at r * slot_bytes in every
+    buffer; the deltas lead from the own slot to the same slot of every peer buffer, in rank order without the own rank."""
+    bases = [0x10000000, 0x7f0000000000, 0x20000100]
+    for rank in range(3):
+        own, deltas = vdist.mirror_layout(3, rank, 4096, bases)
+        assert own == bases[rank] + rank * 4096
+        peers = [p for p in range(3) if p != rank]
+        assert [own + d for d in deltas] == [bases[p] + rank * 4096 for p in peers]
+    import pytest
+    with pytest.raises(AssertionError):
+        vdist.mirror_layout(2, 0, 4096, [0x1000, 0x2004])        # misaligned peer buffer

@@ -98,9 +98,10 @@ def test_detection_block_vs_oracle(conv_type, shape):
     assert tuple(route.shape) == r_ref.shape and tuple(tip.shape) == t_ref.shape
     for got, ref in ((route, r_ref), (tip, t_ref)):
         got = got.float().cpu().numpy()
-        # 5-9 cells with bf16 carriers in between: rounding-boundary flips propagate; 2e-2 of the largest activation
-        assert np.abs(got - ref).max() <= 2e-2 * np.abs(ref).max()
-        assert np.abs(got - ref).mean() <= 2e-3 * np.abs(ref).max()
+        # 5-9 cells with bf16 carriers in between: rounding-boundary flips propagate; worst element and 99.9th percentile
+        from tests.util import err_profile
+        mx, p999, _ = err_profile(got, ref, "detection block '%s' vs oracle" % conv_type)
+        assert mx <= 2e-2 and p999 <= 1e-2
 
 
 def test_block_feeds_head():

@@ -392,3 +392,107 @@ def test_errors_surface():
     tips = [torch.zeros(1, c, 4, 4, device="cuda") for c in CHANNELS]
     with pytest.raises(viddet_b200.VidDetError):
         h17(tips)                                    # no fused instantiation for 17 classes
+
+
+def _ar1_batches(rng, n, B, size, rho):
+    """'Video-like' sequence: batch t+1 = perturbed batch t (AR(1) latent per element, correlation rho), leaky-relu tips."""
+    z, out = None, []
+    for _ in range(n):
+        e = [rng.standard_normal((B, c, size // s, size // s)).astype(np.float32) for c, s in zip(CHANNELS, STRIDES)]
+        z = e if z is None else [rho * a + np.sqrt(1 - rho * rho) * b for a, b in zip(z, e)]
+        out.append([bf16_round(np.where(a > 0, a, 0.1 * a).astype(np.float32)) for a in z])
+    return out
+
+
+@pytest.mark.parametrize("kind", ["iid", "video"])
+def test_speculative_path_on_unseen_batches_bit_exact(kind):
+    """The speculative thresholds of a session are always learned on the PREVIOUS batch.  50 distinct consecutive batches
+    (iid, and a video-like sequence where batch t+1 is a perturbation of batch t) through ONE session: every call must
+    reproduce box_nms(detections()) bit for bit, whether its frames were proven by the speculative kernel or redone by the
+    exact pair; the redo rate is reported (iid / slowly varying data: only the cold first call redoes frames)."""
+    import viddet_b200
+    rng = np.random.RandomState(31)
+    C, B, size, n = 20, 4, 416, 50
+    ws, bs = make_pred_weights(rng, C, bias_scale=0.05)
+    head = build_head(C, ws, bs)
+    head.set_nms(0.45, 400, 100)
+    if kind == "iid":
+        batches = [make_tips(rng, B, size=size) for _ in range(n)]
+    else:
+        batches = _ar1_batches(rng, n, B, size, rho=0.9)
+    sess = head.session([cuda(t) for t in batches[0]], return_keep=True)
+    redone_after_first = 0
+    for i, tips in enumerate(batches):
+        tt = [viddet_b200.to_nhwc_bf16(cuda(t)) for t in tips]
+        sess.rebind(tt)
+        det = head.detections(tt)
+        out, rec = viddet_b200.box_nms(det, overlap_thresh=0.45, valid_thresh=0.01, topk=400, id_index=0, score_index=1,
+                                       coord_start=2, force_suppress=False, return_record=True)
+        sess.keep.fill_(-7)
+        sess.run()
+        r = sess.redone_frames()
+        assert torch.equal(sess.keep, rec[:, :100]), (kind, i)
+        assert torch.equal(sess.scores.view(torch.int32), out[:, :100, 1:2].contiguous().view(torch.int32)), (kind, i)
+        assert torch.equal(sess.bboxes.view(torch.int32), out[:, :100, 2:].contiguous().view(torch.int32)), (kind, i)
+        if i == 0:
+            assert r == B                                  # cold workspace: everything through the exact path
+        else:
+            redone_after_first += r
+    total, calls = sess.stats()
+    assert calls >= n and total >= B
+    rate = redone_after_first / float(B * (n - 1))
+    print("speculative path, %s batches: %.2f%% of the frames after the first call were redone by the exact path" % (kind, 100 * rate))
+    assert rate <= 0.05
+
+
+def test_pipeline_with_fresh_inputs_matches_direct_calls():
+    """HeadPipeline(inputs=...): step i reads input set i % len(inputs) with session i % len(sessions)'s workspace / outputs
+    (bench.py's default mode).  After one graph replay every session holds the result of the LAST input it processed."""
+    import viddet_b200
+    rng = np.random.RandomState(13)
+    C, B, size = 20, 3, 320
+    ws, bs = make_pred_weights(rng, C, bias_scale=0.1)
+    head = build_head(C, ws, bs)
+    head.set_nms(0.45, 400, 100)
+    pool = [[viddet_b200.to_nhwc_bf16(cuda(t)) for t in make_tips(rng, B, size=size)] for _ in range(5)]
+    ref = [[t.clone() for t in head(p, return_keep=True)] for p in pool]
+    sessions = [head.session(pool[j], return_keep=True) for j in range(2)]
+    steps = 7
+    pipe = viddet_b200.HeadPipeline(sessions, steps=steps, inputs=pool)
+    for s in sessions:
+        s.keep.fill_(-7); s.scores.fill_(-7.0)
+    for _ in range(2):
+        pipe.cycle()
+    torch.cuda.synchronize()
+    for j, s in enumerate(sessions):
+        last = max(i for i in range(steps) if i % 2 == j) % len(pool)
+        ids, scores, boxes, keep = ref[last]
+        assert torch.equal(s.keep, keep), j
+        assert torch.equal(s.scores.view(torch.int32), scores.view(torch.int32))
+        assert torch.equal(s.bboxes.view(torch.int32), boxes.view(torch.int32))
+
+
+def test_output_mirrors_store_every_result_twice():
+    """VdHeadParams::mirror_delta: every ids / scores / bboxes element is also stored at address + delta (the peers' gather
+    buffers in the multi-GPU job; here a second buffer on the same device)."""
+    import viddet_b200
+    rng = np.random.RandomState(17)
+    C, B, size = 20, 3, 320
+    ws, bs = make_pred_weights(rng, C, bias_scale=0.1)
+    head = build_head(C, ws, bs)
+    head.set_nms(0.45, 400, 100)
+    tips = [cuda(t) for t in make_tips(rng, B, size=size)]
+    n = B * 100
+    buf = torch.full((3, 6 * n), -9.0, device="cuda")          # own buffer + two "peers"
+    own = buf[0]
+    out = (own[:n].view(B, 100, 1), own[n:2 * n].view(B, 100, 1), own[2 * n:].view(B, 100, 4))
+    deltas = [buf[1].data_ptr() - own.data_ptr(), buf[2].data_ptr() - own.data_ptr()]
+    sess = head.session(tips, out=out, mirrors=deltas)
+    for _ in range(2):                                          # exact path (cold) and speculative path
+        buf.fill_(-9.0)
+        sess.run()
+        torch.cuda.synchronize()
+        ids, scores, boxes = head(tips)
+        assert torch.equal(out[1].view(torch.int32), scores.view(torch.int32))
+        assert torch.equal(buf[1].view(torch.int32), buf[0].view(torch.int32))
+        assert torch.equal(buf[2].view(torch.int32), buf[0].view(torch.int32))

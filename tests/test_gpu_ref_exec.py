@@ -123,12 +123,14 @@ def test_yolov3_neck_vs_executed_reference():
     ref = ref_head.head_detections(tips, [p[0] for p in preds], [p[1] for p in preds], C)
     assert det.shape == ref.shape == G["neck_det"].shape
     np.testing.assert_array_equal(det[..., 0], ref[..., 0])
-    # 19 convs with bf16 carriers: a rounding-boundary flip in one layer propagates; worst element 5e-2, average 2e-3
-    assert np.abs(det[..., 1] - ref[..., 1]).max() <= 5e-2 * ref[..., 1].max()
-    assert np.abs(det[..., 1] - ref[..., 1]).mean() <= 2e-3 * ref[..., 1].max()
+    # 19 convs with bf16 carriers: a rounding-boundary flip in one layer propagates.  Bounds on the WORST element and on the
+    # 99.9th percentile (a mean would hide outliers), measured on B200 and printed by err_profile.
+    from tests.util import err_profile
+    mx, p999, _ = err_profile(det[..., 1], ref[..., 1], "neck scores vs oracle with the same bf16 rounding points")
+    assert mx <= 5e-2 and p999 <= 2e-2
     gold = G["neck_det"]
-    assert np.abs(det[..., 1] - gold[..., 1]).max() <= 8e-2 * gold[..., 1].max()
-    assert np.abs(det[..., 1] - gold[..., 1]).mean() <= 5e-3 * gold[..., 1].max()
+    mx, p999, _ = err_profile(det[..., 1], gold[..., 1], "neck scores vs the executed fp32 reference")
+    assert mx <= 8e-2 and p999 <= 4e-2
     ids, scores, boxes = neck(routes)
     assert ids.shape == G["neck_ids"].shape
     # the top detections agree with the reference's wherever the score gap exceeds the bf16 noise
@@ -163,10 +165,11 @@ def test_yolov3_temporal_neck_vs_executed_reference():
     gold = G["tneck_det"]
     assert det.shape == ref.shape == gold.shape
     np.testing.assert_array_equal(det[..., 0], ref[..., 0])
-    assert np.abs(det[..., 1] - ref[..., 1]).max() <= 5e-2 * ref[..., 1].max()          # 28 convs with bf16 carriers
-    assert np.abs(det[..., 1] - ref[..., 1]).mean() <= 3e-3 * ref[..., 1].max()
-    assert np.abs(det[..., 1] - gold[..., 1]).max() <= 1e-1 * gold[..., 1].max()
-    assert np.abs(det[..., 1] - gold[..., 1]).mean() <= 6e-3 * gold[..., 1].max()
+    from tests.util import err_profile
+    mx, p999, _ = err_profile(det[..., 1], ref[..., 1], "temporal neck scores vs oracle with the same bf16 rounding points")   # 28 convs with bf16 carriers
+    assert mx <= 5e-2 and p999 <= 2e-2
+    mx, p999, _ = err_profile(det[..., 1], gold[..., 1], "temporal neck scores vs the executed fp32 reference")
+    assert mx <= 1e-1 and p999 <= 5e-2
     ids, scores, boxes = neck(routes)
     assert tuple(ids.shape) == G["tneck_ids"].shape == (B, T, 100, 1)
     gs, s = G["tneck_scores"][..., 0], scores.cpu().numpy()[..., 0]

@@ -118,3 +118,11 @@ def rel_err(got, ref, floor):
     """max |got - ref| / max(|ref|, floor) over all elements."""
     got = np.asarray(got, np.float64); ref = np.asarray(ref, np.float64)
     return float((np.abs(got - ref) / np.maximum(np.abs(ref), floor)).max())
+
+
+def err_profile(got, ref, what):
+    """(max, 99.9th percentile, mean) of |got - ref| relative to the largest |ref|; printed so the bounds below stay measured."""
+    e = np.abs(np.asarray(got, np.float64) - np.asarray(ref, np.float64)).ravel() / float(np.abs(ref).max())
+    mx, p999, mean = float(e.max()), float(np.quantile(e, 0.999)), float(e.mean())
+    print("%s: max %.2e, p99.9 %.2e, mean %.2e of max|ref|" % (what, mx, p999, mean))
+    return mx, p999, mean

@@ -12,6 +12,7 @@ SO_PATH = os.environ.get("VD_LIB") or os.path.join(HERE, "libviddet_b200.so")   
 
 VD_MAX_SCALES = 3
 VD_MAX_TOPK = 1024
+VD_MAX_MIRRORS = 7
 VD_MODE_INFER, VD_MODE_TRAIN, VD_MODE_AGNOSTIC = 0, 1, 2
 VD_JOIN_NONE, VD_JOIN_CAT, VD_JOIN_MAX, VD_JOIN_MEAN = 0, 1, 2, 3
 VD_STAGE_TCONV, VD_STAGE_HEAD, VD_STAGE_NMS, VD_STAGE_ALL = 1, 2, 4, 7
@@ -43,6 +44,8 @@ class VdHeadParams(ctypes.Structure):
         ("nms_topk", ctypes.c_int), ("post_nms", ctypes.c_int),
         ("precision", ctypes.c_int), ("reserved0", ctypes.c_int),
         ("scale", VdHeadScale * VD_MAX_SCALES),
+        ("n_mirrors", ctypes.c_int), ("reserved1", ctypes.c_int),
+        ("mirror_delta", ctypes.c_longlong * VD_MAX_MIRRORS),
     ]
 
 
@@ -69,6 +72,10 @@ SIGNATURES = {
     "vd_head_launch_count": (_i, [ctypes.POINTER(VdHeadParams)]),
     "vd_head_stats_offset": (_sz, [ctypes.POINTER(VdHeadParams)]),
     "vd_head_detections": (_i, [ctypes.POINTER(VdHeadParams), _vp, _vp, _sz, _vp]),
+    "vd_ipc_alloc": (_i, [_sz, ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_ubyte)]),
+    "vd_ipc_open": (_i, [ctypes.POINTER(ctypes.c_ubyte), ctypes.POINTER(ctypes.c_void_p)]),
+    "vd_ipc_close": (_i, [_vp]),
+    "vd_ipc_free": (_i, [_vp]),
     "vd_temporal_conv": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _f, _vp]),
     "vd_conv_bn_lrelu": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _f, _vp]),
     "vd_upsample_concat": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),

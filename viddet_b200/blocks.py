@@ -681,10 +681,11 @@ class YOLOV3Head:
                 keep = keep.reshape(lead + (post,))
         return (ids, scores, bboxes, keep) if return_keep else (ids, scores, bboxes)
 
-    def session(self, tips, return_keep=False, out=None):
+    def session(self, tips, return_keep=False, out=None, mirrors=None):
         """Bind tips/outputs/workspace once; the returned HeadSession re-enqueues the same call with no
-        per-call Python work (and can be captured into a CUDA graph)."""
-        return HeadSession(self, tips, return_keep, out)
+        per-call Python work (and can be captured into a CUDA graph).  mirrors: byte deltas to the same output slot in the
+        peer GPUs' gather buffers (viddet_b200.dist.PeerGather.deltas) -- the NMS kernel then stores every result there too."""
+        return HeadSession(self, tips, return_keep, out, mirrors)
 
     def train_outputs(self, tips):
         """The training-mode branch of YOLOV3.hybrid_forward without a recorded loss (yolo3.py:498-509,532-535): per scale the
@@ -730,11 +731,17 @@ class HeadSession:
     workspace.  `run()` enqueues the kernels on the current stream; `capture()` records them into a
     CUDA graph whose `replay()` is a single launch."""
 
-    def __init__(self, head, tips, return_keep=False, out=None):
+    def __init__(self, head, tips, return_keep=False, out=None, mirrors=None):
         if not (0 < head.nms_thresh < 1) or head.post_nms <= 0:
             raise _lib.VidDetError(-1, "HeadSession needs NMS and post_nms enabled")
         self.head = head
         self.params, self.tips, self._scratch, self.lead = head._prepare(tips)
+        if mirrors:
+            assert out is not None, "output mirrors need caller-owned outputs inside the gather buffer"
+            assert len(mirrors) <= _lib.VD_MAX_MIRRORS
+            self.params.n_mirrors = len(mirrors)
+            for i, d in enumerate(mirrors):
+                self.params.mirror_delta[i] = int(d)
         dev = self.tips[0].device
         F, post = self.params.frames, head.post_nms
         if out is not None:                           # caller-owned output buffers (e.g. slices of one tensor per ring)
@@ -781,6 +788,14 @@ class HeadSession:
             assert t.shape == old.shape and t.dtype == torch.bfloat16 and t.is_contiguous(memory_format=torch.channels_last)
             self.params.scale[i].tip_nhwc_bf16 = t.data_ptr()
         self.tips = list(tips)
+        return self
+
+    def stats(self):
+        """(frames redone by the exact path, completed calls) -- running totals of this workspace (synchronises)."""
+        off = load().vd_head_stats_offset(ctypes.byref(self.params))
+        torch.cuda.synchronize()
+        w = self._ws[off + 20: off + 28].view(torch.int32).tolist()
+        return int(w[0]) & 0xffffffff, int(w[1]) & 0xffffffff
 
     def redone_frames(self):
         """Frames of the last completed call that the exact path had to redo (synchronises; 0 in the steady state)."""
@@ -804,9 +819,15 @@ class HeadPipeline:
     waits for its previous NMS kernel.  `cycle()` = rotations * len(sessions) steps; every batch is complete
     when the graph has finished."""
 
-    def __init__(self, sessions, rotations=2):
+    def __init__(self, sessions, rotations=2, steps=None, inputs=None):
+        """steps: batches per graph (default rotations * len(sessions); any count >= 1: step i runs on session i % len).
+        inputs: optional list of resident input sets (each a list of channels-last bf16 tips of the sessions' shapes); step i
+        then reads inputs[i % len(inputs)] while using session i % len(sessions)'s workspace and outputs -- every threshold the
+        speculative filter uses was learned from a DIFFERENT batch than the one it filters (fresh data every step)."""
         assert len(sessions) >= 2 and rotations >= 1
         self.sessions = list(sessions)
+        steps = rotations * len(self.sessions) if steps is None else int(steps)
+        assert steps >= 1
         self._streams = [torch.cuda.Stream() for _ in range(2)]
         for s in self.sessions:                       # initialise workspaces (scheduler state, warm-start hints)
             s.run()
@@ -818,23 +839,26 @@ class HeadPipeline:
             hs.wait_stream(main)
             ns.wait_stream(main)
             nms_done = [None] * len(self.sessions)
-            for r in range(rotations):
-                for j, sess in enumerate(self.sessions):
-                    with torch.cuda.stream(hs):
-                        if nms_done[j] is not None:
-                            hs.wait_event(nms_done[j])            # the session's buffers are free again
-                        sess.run(_lib.VD_STAGE_TCONV | _lib.VD_STAGE_HEAD)   # (temporal tip cell kernels, if any,) fused head kernel
-                        head_done = torch.cuda.Event()
-                        head_done.record(hs)
-                    with torch.cuda.stream(ns):
-                        ns.wait_event(head_done)
-                        sess.run(_lib.VD_STAGE_NMS)
-                        nms_done[j] = torch.cuda.Event()
-                        nms_done[j].record(ns)
+            for i in range(steps):
+                j = i % len(self.sessions)
+                sess = self.sessions[j]
+                if inputs is not None:
+                    sess.rebind(inputs[i % len(inputs)])            # the captured nodes keep this step's pointers
+                with torch.cuda.stream(hs):
+                    if nms_done[j] is not None:
+                        hs.wait_event(nms_done[j])            # the session's buffers are free again
+                    sess.run(_lib.VD_STAGE_TCONV | _lib.VD_STAGE_HEAD)   # (temporal tip cell kernels, if any,) fused head kernel
+                    head_done = torch.cuda.Event()
+                    head_done.record(hs)
+                with torch.cuda.stream(ns):
+                    ns.wait_event(head_done)
+                    sess.run(_lib.VD_STAGE_NMS)
+                    nms_done[j] = torch.cuda.Event()
+                    nms_done[j].record(ns)
             main.wait_stream(hs)
             main.wait_stream(ns)
         self._graph = g
-        self.steps_per_cycle = rotations * len(self.sessions)
+        self.steps_per_cycle = steps
         self.launches_per_step = 2
 
     def cycle(self):
@@ -856,7 +880,15 @@ class YOLOV3PrefetchTargetGenerator:
     def __init__(self, num_class, **kwargs):
         self._num_class = num_class
 
-    def __call__(self, img, xs, anchors, offsets, gt_boxes, gt_ids, gt_mixratio=None, return_assign=False):
+    def alloc_outputs(self, B, N, device):
+        """The five target tensors (objectness, center, scale, weights, class) for `run_into` (static buffers, e.g. for CUDA graphs)."""
+        return tuple(torch.empty((B, N, w), device=device) for w in (1, 2, 2, 2, self._num_class))
+
+    def run_into(self, img, xs, anchors, offsets, gt_boxes, gt_ids, gt_mixratio, outs):
+        """`__call__` writing into caller-owned outputs (from alloc_outputs); returns them."""
+        return self.__call__(img, xs, anchors, offsets, gt_boxes, gt_ids, gt_mixratio, out=outs)
+
+    def __call__(self, img, xs, anchors, offsets, gt_boxes, gt_ids, gt_mixratio=None, return_assign=False, out=None):
         assert isinstance(anchors, (list, tuple)) and isinstance(offsets, (list, tuple)) and isinstance(xs, (list, tuple))
         assert len(xs) == len(anchors) == len(offsets) == 3
         _require_cuda(gt_boxes, "gt_boxes")
@@ -878,11 +910,12 @@ class YOLOV3PrefetchTargetGenerator:
         C = self._num_class
         N = 3 * sum(hw[2 * i] * hw[2 * i + 1] for i in range(3))
         dev = gb.device
-        obj = torch.empty((B, N, 1), device=dev)
-        ctr = torch.empty((B, N, 2), device=dev)
-        scl = torch.empty((B, N, 2), device=dev)
-        wgt = torch.empty((B, N, 2), device=dev)
-        cls = torch.empty((B, N, C), device=dev)
+        if out is not None:
+            obj, ctr, scl, wgt, cls = out
+            for t, w in zip(out, (1, 2, 2, 2, C)):
+                assert tuple(t.shape) == (B, N, w) and t.is_contiguous() and t.dtype == torch.float32 and t.is_cuda
+        else:
+            obj, ctr, scl, wgt, cls = self.alloc_outputs(B, N, dev)
         match = torch.empty((B, M), dtype=torch.int32, device=dev) if return_assign else None
         row = torch.empty((B, M), dtype=torch.int32, device=dev) if return_assign else None
         hw_c = (ctypes.c_int * 6)(*hw)

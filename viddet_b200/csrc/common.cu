@@ -49,6 +49,30 @@ int configure_kernel(const void* func, int dyn_smem_bytes, bool max_shared_carve
 }  // namespace vd
 
 extern "C" int vd_version(void) { return 100; }
+
+// ---- peer-mapped buffers (CUDA IPC) for the fused head's output mirrors
+static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle is 64 bytes");
+extern "C" int vd_ipc_alloc(size_t bytes, void** dev_ptr_out, unsigned char handle_out[64]) {
+    VD_CHECK_ARG(bytes > 0 && dev_ptr_out && handle_out, "ipc_alloc: bad argument");
+    void* p = nullptr;
+    VD_CUDA(cudaMalloc(&p, bytes));
+    cudaError_t e = cudaMemset(p, 0, bytes);
+    cudaIpcMemHandle_t h;
+    if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) { cudaFree(p); return vd::set_error(VD_ERR_CUDA, "ipc_alloc: %s", cudaGetErrorString(e)); }
+    memcpy(handle_out, &h, 64);
+    *dev_ptr_out = p;
+    return VD_OK;
+}
+extern "C" int vd_ipc_open(const unsigned char handle[64], void** dev_ptr_out) {
+    VD_CHECK_ARG(handle && dev_ptr_out, "ipc_open: bad argument");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    VD_CUDA(cudaIpcOpenMemHandle(dev_ptr_out, h, cudaIpcMemLazyEnablePeerAccess));
+    return VD_OK;
+}
+extern "C" int vd_ipc_close(void* dev_ptr) { if (dev_ptr) VD_CUDA(cudaIpcCloseMemHandle(dev_ptr)); return VD_OK; }
+extern "C" int vd_ipc_free(void* dev_ptr) { if (dev_ptr) VD_CUDA(cudaFree(dev_ptr)); return VD_OK; }
 extern "C" const char* vd_last_error(void) { return vd::last_error_buf(); }
 
 extern "C" int vd_device_info(int device, int* sm_count, int* cc_major, int* cc_minor) {

@@ -48,7 +48,7 @@ constexpr int kSpecCap = 2048;                // candidates per frame the specul
 #define VD_SPEC_SPLIT 2
 #endif
 #ifndef VD_FALLBACK_CTAS
-#define VD_FALLBACK_CTAS 8
+#define VD_FALLBACK_CTAS 32      // CTAs of the exact fallback head kernel (idle in the steady state; measured r1: 2 / 8 / 32 CTAs -> 39.1 / 39.1 / 39.3 us per step, all-frames-failed call 2.5 / 0.98 / 0.51 ms)
 #endif
 constexpr int kFallbackCtas = VD_FALLBACK_CTAS;
 constexpr int kSpecStage = 64;                // per-warp staging entries per tile (double-buffered); more go straight to global memory
@@ -1014,20 +1014,29 @@ struct FusedSource {
         area = vd_box_area(__fsub_rn(bx.z, bx.x), __fsub_rn(bx.w, bx.y));
     }
 };
+// The sink of the fused path.  Output mirrors (VdHeadParams::n_mirrors): every ids / scores / bboxes element stored at address a
+// is also stored at a + mirror[i] -- the same slot of the detection gather buffer of peer GPU i, mapped into this process over
+// NVLink (CUDA IPC): the final detection gather of the multi-GPU job happens inside the NMS kernel, with no staging copy and
+// no collective on the data path (2.4 KB per frame and peer).
 struct FusedSink {
     float* ids; float* scores; float* bboxes; int32_t* keep; int post;
+    int n_mirror; long long mirror[VD_MAX_MIRRORS];
+    template <class T> __device__ __forceinline__ void put(T* p, const T v) const {
+        *p = v;
+        for (int i = 0; i < n_mirror; ++i) *reinterpret_cast<T*>(reinterpret_cast<char*>(p) + mirror[i]) = v;
+    }
     __device__ __forceinline__ void emit(int f, int pos, uint32_t row, float score, float4 bx, int c) const {
         size_t o = (size_t)f * post + pos;
-        ids[o] = __fadd_rn(__fmul_rn(score, 0.0f), (float)c);
-        scores[o] = score;
-        reinterpret_cast<float4*>(bboxes)[o] = bx;
+        put(ids + o, __fadd_rn(__fmul_rn(score, 0.0f), (float)c));
+        put(scores + o, score);
+        put(reinterpret_cast<float4*>(bboxes) + o, bx);
         if (keep) keep[o] = (int32_t)row;
     }
     __device__ __forceinline__ void finish(int f, int kept) const {
         for (int pos = kept + threadIdx.x; pos < post; pos += blockDim.x) {
             size_t o = (size_t)f * post + pos;
-            ids[o] = -1.0f; scores[o] = -1.0f;
-            reinterpret_cast<float4*>(bboxes)[o] = make_float4(-1.f, -1.f, -1.f, -1.f);
+            put(ids + o, -1.0f); put(scores + o, -1.0f);
+            put(reinterpret_cast<float4*>(bboxes) + o, make_float4(-1.f, -1.f, -1.f, -1.f));
             if (keep) keep[o] = -1;
         }
     }
@@ -1307,7 +1316,8 @@ nms_final_hist_kernel(const uint64_t* __restrict__ lists, const uint32_t* __rest
     if (tid == 0) {
         __threadfence();
         if (atomicAdd(&spec_state[3], 1u) == gridDim.x - 1u) {
-            spec_state[4] = spec_state[2]; spec_state[2] = 0u; spec_state[3] = 0u;
+            spec_state[4] = spec_state[2]; spec_state[5] += spec_state[2]; spec_state[6] += 1u;     // last call / running totals (frames redone, calls)
+            spec_state[2] = 0u; spec_state[3] = 0u;
             ctr[0] = 0u; ctr[1] = 0u; ctr[2] = ws_magic;
         }
     }
@@ -1678,7 +1688,14 @@ extern "C" int vd_head_forward_stages(const VdHeadParams* hp, float* ids, float*
     P.max_out = hp->post_nms;
     P.dbg = (getenv("VD_DEBUG_NMS_STAMPS") || getenv("VD_DEBUG_HEAD_STAMPS")) ? (long long*)(ws + pl.off_listsA) : nullptr;   // profiling aid (unused merge area)
     FusedSource src{kp.g, kp.boxes};
-    FusedSink sink{ids, scores, bboxes, keep_rows_or_null, hp->post_nms};
+    FusedSink sink;
+    sink.ids = ids; sink.scores = scores; sink.bboxes = bboxes; sink.keep = keep_rows_or_null; sink.post = hp->post_nms;
+    VD_CHECK_ARG(hp->n_mirrors >= 0 && hp->n_mirrors <= VD_MAX_MIRRORS, "head_forward: n_mirrors %d", hp->n_mirrors);
+    sink.n_mirror = hp->n_mirrors;
+    for (int i = 0; i < VD_MAX_MIRRORS; ++i) {
+        sink.mirror[i] = i < hp->n_mirrors ? hp->mirror_delta[i] : 0;
+        VD_CHECK_ARG((sink.mirror[i] & 15) == 0, "head_forward: mirror_delta[%d] must be a multiple of 16 bytes", i);
+    }
     {
         const bool carve = !getenv("VD_DEBUG_NO_CARVEOUT") || atoi(getenv("VD_DEBUG_NO_CARVEOUT")) == 2;
         rc = configure_kernel((const void*)nms_final_hist_kernel, (int)nms_hist_smem(VD_MAX_TOPK, VD_MAX_TOPK), carve);

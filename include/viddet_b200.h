@@ -97,21 +97,24 @@ int vd_pred_conv(const void* x_nhwc_bf16, int B, int H, int W, int Cin, int K_fr
                  float* pred_nchw, void* stream);
 
 /* ------------------------------------------------------------------------------------------
- * fp32-parity mode (VD_PREC_FP32_SPLIT).  The reference head is fp32 end to end (yolo3.py:62,157).  The tensor cores take
- * bf16 operands, so an fp32 value v is carried as two bf16 planes hi = bf16(v), lo = bf16(v - hi) (16 mantissa bits,
- * residual <= 2^-18 |v|) and the conv accumulates  hi*W_hi + lo*W_hi + hi*W_lo  in fp32 (the lo*lo term, 2^-18 relative, is
- * dropped): decoded scores / boxes land within 1e-5 relative of the fp32 reference instead of 1e-3 (tests/test_gpu_fp32.py).
- * Carriers in this mode:  activations (B, 2, H, W, Cin) bf16 = [hi plane, lo plane] per frame, channels-last;
- *                         weights     (N_out, 2, Cin) bf16  = [hi row, lo row] per output channel.
- * The mode reads 4 bytes per activation element (what an fp32 carrier costs) and issues 3x the MMAs; the VOC / VID heads stay
- * HBM-bound.  Not combinable with VD_JOIN_CAT or the temporal tip cell (VD_ERR_UNSUPPORTED).
+ * fp32-parity modes.  The reference head is fp32 end to end (yolo3.py:62,157).  The tensor cores take bf16 operands, so an
+ * fp32 value v is carried as P bf16 planes p0 = bf16(v), p1 = bf16(v - p0), p2 = bf16(v - p0 - p1) (8 mantissa bits each:
+ * P = 3 holds all 24 bits of v) and the conv accumulates plane products in fp32:
+ *   VD_PREC_FP32_SPLIT (P = 3): a0 w0 + a1 w0 + a0 w1 + a1 w1 + a2 w0 + a0 w2  (dropped terms <= 2^-27 relative) -- decoded
+ *       scores / boxes within 1e-5 relative of the fp32 reference (tests/test_gpu_fp32.py), 6 bytes per element, 6x the MMAs;
+ *   VD_PREC_BF16X2     (P = 2): a0 w0 + a1 w0 + a0 w1  (residual ~ 2^-18 relative) -- within 1e-4, 4 bytes per element, 3x MMAs.
+ * Carriers:  activations (P, B, H, W, Cin) bf16, plane-major (every plane is an ordinary channels-last tensor);
+ *            weights     (N_out, P, Cin) bf16 (the planes of one output channel side by side).
+ * Not combinable with VD_JOIN_CAT; the temporal tip cell has its own entry (vd_temporal_conv_ex) whose split output feeds
+ * the head (VD_ERR_UNSUPPORTED otherwise).
  * ------------------------------------------------------------------------------------------ */
-#define VD_PREC_BF16        0   /* bf16 operands, fp32 accumulate (1e-3 relative vs the fp32 reference)          */
-#define VD_PREC_FP32_SPLIT  1   /* hi/lo bf16 planes, 3 products, fp32 accumulate (1e-5 relative)                */
-/* (B, C, H, W) fp32 -> (B, 2, H, W, C) bf16 hi/lo planes (the activation carrier of VD_PREC_FP32_SPLIT). */
-int vd_repack_nchw_f32_to_nhwc_split(const float* src, void* dst_bf16, int B, int C, int H, int W, void* stream);
-/* (rows, cols) fp32 -> (rows, 2, cols) bf16 hi/lo rows (the weight carrier of VD_PREC_FP32_SPLIT). */
-int vd_split_f32_rows(const float* src, void* dst_bf16, int64_t rows, int64_t cols, void* stream);
+#define VD_PREC_BF16        0   /* bf16 operands, fp32 accumulate (1e-3 relative vs the fp32 reference on bf16-representable inputs) */
+#define VD_PREC_FP32_SPLIT  1   /* 3 bf16 planes, 6 products, fp32 accumulate (1e-5 relative)                    */
+#define VD_PREC_BF16X2      2   /* 2 bf16 planes, 3 products (1e-4 relative)                                     */
+/* (B, C, H, W) fp32 -> (planes, B, H, W, C) bf16 planes, planes = 2 or 3 (the activation carrier of the modes above). */
+int vd_repack_nchw_f32_to_nhwc_split(const float* src, void* dst_bf16, int B, int C, int H, int W, int planes, void* stream);
+/* (rows, cols) fp32 -> (rows, planes, cols) bf16 (the weight carrier of the modes above). */
+int vd_split_f32_rows(const float* src, void* dst_bf16, int64_t rows, int64_t cols, int planes, void* stream);
 /* vd_pred_conv with a precision selector: VD_PREC_FP32_SPLIT takes the split carriers described above. */
 int vd_pred_conv_ex(const void* x, int B, int H, int W, int Cin, int K_frames, int join, int precision,
                     const void* weight, const float* bias_or_null, int N, float* pred_nchw, void* stream);
@@ -147,7 +150,7 @@ typedef struct VdHeadParams {
     float valid_thresh;          /* 0.01 at yolo3.py:527                                        */
     int nms_topk;                /* 400 (detect_yolo3.py:200)                                   */
     int post_nms;                /* 100 (yolo3.py:395)                                          */
-    int precision;               /* VD_PREC_BF16 (0) or VD_PREC_FP32_SPLIT: tips (frames,2,H,W,Cin), weights (N_out,2,Cin) */
+    int precision;               /* VD_PREC_BF16 (0), or an fp32-parity mode: tips (P,frames,H,W,Cin), weights (N_out,P,Cin) */
     int reserved0;               /* must be 0                                                    */
     VdHeadScale scale[VD_MAX_SCALES];
     /* Output mirrors (multi-GPU detection gather): every ids / scores / bboxes element vd_head_forward stores at
@@ -221,6 +224,12 @@ int vd_ipc_free(void* dev_ptr);
 int vd_temporal_conv(const void* x_bf16, void* y_bf16, int B, int T, int H, int W, int C,
                      const void* weight_bf16, const float* scale, const float* shift,
                      float slope, void* stream);
+/* The same cell in an fp32-parity mode (see VD_PREC_* above): x, y (P, B, T, H, W, C) bf16 plane-major, weight (P, 3, C, C) bf16
+ * [plane][tap][cout][cin]; the fp32 result of BN + LeakyReLU is written as P planes, ready for vd_head_forward with the same
+ * precision.  VD_PREC_BF16 is vd_temporal_conv. */
+int vd_temporal_conv_ex(const void* x_bf16, void* y_bf16, int B, int T, int H, int W, int C,
+                        const void* weight_bf16, const float* scale, const float* shift,
+                        float slope, int precision, void* stream);
 
 /* Conv-BN-LeakyReLU cell of YOLODetectionBlockV3: replaces `_conv2d` (layers.py:63-70) and `_conv3d`
  * (layers.py:73-79) as stacked at yolo3_temporal.py:198-239 -- Conv(no bias, stride 1, zero 'same' padding, kernel extents

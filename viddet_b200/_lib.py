@@ -16,7 +16,8 @@ VD_MAX_MIRRORS = 7
 VD_MODE_INFER, VD_MODE_TRAIN, VD_MODE_AGNOSTIC = 0, 1, 2
 VD_JOIN_NONE, VD_JOIN_CAT, VD_JOIN_MAX, VD_JOIN_MEAN = 0, 1, 2, 3
 VD_STAGE_TCONV, VD_STAGE_HEAD, VD_STAGE_NMS, VD_STAGE_ALL = 1, 2, 4, 7
-VD_PREC_BF16, VD_PREC_FP32_SPLIT = 0, 1
+VD_PREC_BF16, VD_PREC_FP32_SPLIT, VD_PREC_BF16X2 = 0, 1, 2
+PLANES = {VD_PREC_BF16: 1, VD_PREC_FP32_SPLIT: 3, VD_PREC_BF16X2: 2}
 ERR_NAMES = {-1: "VD_ERR_INVALID_ARG", -2: "VD_ERR_UNSUPPORTED", -3: "VD_ERR_WORKSPACE", -4: "VD_ERR_CUDA"}
 
 
@@ -63,8 +64,8 @@ SIGNATURES = {
     "vd_repack_nchw_f32_to_nhwc_bf16": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "vd_pred_conv": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp]),
     "vd_pred_conv_ex": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp]),
-    "vd_repack_nchw_f32_to_nhwc_split": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
-    "vd_split_f32_rows": (_i, [_vp, _vp, _i64, _i64, _vp]),
+    "vd_repack_nchw_f32_to_nhwc_split": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "vd_split_f32_rows": (_i, [_vp, _vp, _i64, _i64, _i, _vp]),
     "vd_sizeof": (_sz, [_i]),
     "vd_head_workspace_bytes": (_sz, [ctypes.POINTER(VdHeadParams)]),
     "vd_head_forward": (_i, [ctypes.POINTER(VdHeadParams), _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
@@ -77,6 +78,7 @@ SIGNATURES = {
     "vd_ipc_close": (_i, [_vp]),
     "vd_ipc_free": (_i, [_vp]),
     "vd_temporal_conv": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _f, _vp]),
+    "vd_temporal_conv_ex": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _f, _i, _vp]),
     "vd_conv_bn_lrelu": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _f, _vp]),
     "vd_upsample_concat": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "vd_conv_tile_box": (_i, [_i, _i, _i, _ip, _ip, _ip]),

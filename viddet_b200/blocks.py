@@ -60,36 +60,41 @@ def to_nhwc_bf16(x: torch.Tensor) -> torch.Tensor:
 
 
 class SplitF32:
-    """fp32 feature map carried for the tensor cores as two bf16 planes (VD_PREC_FP32_SPLIT, include/viddet_b200.h):
-    `data` (B, 2, H, W, C) bf16 = [hi, lo] with hi = bf16(v), lo = bf16(v - hi); `shape` is the logical (B, C, H, W)."""
+    """fp32 feature map carried for the tensor cores as P bf16 planes (fp32-parity modes, include/viddet_b200.h):
+    `data` (P, B, H, W, C) bf16, plane-major, p0 = bf16(v), p1 = bf16(v - p0), p2 = bf16(v - p0 - p1); `shape` is the
+    logical (B, C, H, W)."""
 
     def __init__(self, data, shape):
         self.data, self.shape = data, tuple(shape)
+        self.planes = int(data.shape[0])
 
     @property
     def device(self):
         return self.data.device
 
 
-def to_nhwc_split(x) -> SplitF32:
+def to_nhwc_split(x, planes=3) -> SplitF32:
     """(B,C,H,W) fp32 NCHW (the reference's layout and dtype) -> SplitF32 through the repack kernel."""
     if isinstance(x, SplitF32):
+        assert x.planes == planes, "carrier has %d planes, the call needs %d" % (x.planes, planes)
         return x
     _require_cuda(x, "x")
     assert x.dim() == 4, "expected (B,C,H,W)"
     x = x.to(torch.float32).contiguous()
     B, C, H, W = x.shape
-    out = torch.empty((B, 2, H, W, C), dtype=torch.bfloat16, device=x.device)
-    check(load().vd_repack_nchw_f32_to_nhwc_split(ptr(x), ptr(out), B, C, H, W, stream_ptr()))
+    out = torch.empty((planes, B, H, W, C), dtype=torch.bfloat16, device=x.device)
+    check(load().vd_repack_nchw_f32_to_nhwc_split(ptr(x), ptr(out), B, C, H, W, planes, stream_ptr()))
     return SplitF32(out, (B, C, H, W))
 
 
 def _precision_code(precision):
-    if precision in ("bf16", None, _lib.VD_PREC_BF16):
+    if precision is None or precision == "bf16" or (precision == _lib.VD_PREC_BF16 and precision is not False):
         return _lib.VD_PREC_BF16
-    if precision in ("fp32", "f32", "float32", _lib.VD_PREC_FP32_SPLIT) and precision is not True:
+    if precision in ("fp32", "f32", "float32") or (precision == _lib.VD_PREC_FP32_SPLIT and precision is not True):
         return _lib.VD_PREC_FP32_SPLIT
-    raise ValueError("precision must be 'bf16' or 'fp32', got %r" % (precision,))
+    if precision == "bf16x2" or precision == _lib.VD_PREC_BF16X2:
+        return _lib.VD_PREC_BF16X2
+    raise ValueError("precision must be 'bf16', 'bf16x2' or 'fp32', got %r" % (precision,))
 
 
 # ------------------------------------------------------------------------------------------------
@@ -159,22 +164,21 @@ class _Conv1x1:
         self.bias = (torch.zeros(n, device="cuda") if bias is None
                      else torch.as_tensor(bias).detach().to(torch.float32).cuda().contiguous())
         self._w_bf16 = self.weight.reshape(n, -1).to(torch.bfloat16).contiguous()
-        self._w_split = None
+        self._w_split = {}
 
     @property
     def weight_bf16(self):
         return self._w_bf16
 
-    @property
-    def weight_split(self):
-        """(N, 2, Cin) bf16 hi / lo rows of the fp32 master weight (VD_PREC_FP32_SPLIT carrier), built on first use."""
-        if self._w_split is None:
+    def weight_split(self, planes):
+        """(N, planes, Cin) bf16 planes of the fp32 master weight (carrier of the fp32-parity modes), built on first use."""
+        if planes not in self._w_split:
             n = self.weight.shape[0]
             w2 = self.weight.reshape(n, -1).contiguous()
-            out = torch.empty((n, 2, w2.shape[1]), dtype=torch.bfloat16, device=w2.device)
-            check(load().vd_split_f32_rows(ptr(w2), ptr(out), n, w2.shape[1], stream_ptr()))
-            self._w_split = out
-        return self._w_split
+            out = torch.empty((n, planes, w2.shape[1]), dtype=torch.bfloat16, device=w2.device)
+            check(load().vd_split_f32_rows(ptr(w2), ptr(out), n, w2.shape[1], planes, stream_ptr()))
+            self._w_split[planes] = out
+        return self._w_split[planes]
 
 
 class YOLOOutputV3:
@@ -245,16 +249,17 @@ class YOLOOutputV3:
     # -- forward ---------------------------------------------------------------------------------
     def predict(self, x):
         """The prediction conv alone: (B,Cin,H,W) -> pred (B, A*(5+C), H, W) fp32 (yolo3.py:157)."""
-        split = self._precision == _lib.VD_PREC_FP32_SPLIT
-        xb = to_nhwc_split(x) if split else to_nhwc_bf16(x)
+        planes = _lib.PLANES[self._precision]
+        split = planes > 1
+        xb = to_nhwc_split(x, planes) if split else to_nhwc_bf16(x)
         B, Cin, H, W = xb.shape
         n = self._num_pred * self._num_anchors
         if self.prediction.weight is None or self.prediction.weight.shape[1] != Cin:
             raise _lib.VidDetError(-1, "YOLOOutputV3: prediction weights not set for Cin=%d" % Cin)
         pred = torch.empty((B, n, H, W), dtype=torch.float32, device=xb.device)
         if split:
-            check(load().vd_pred_conv_ex(ptr(xb.data), B, H, W, Cin, 1, _lib.VD_JOIN_NONE, _lib.VD_PREC_FP32_SPLIT,
-                                         ptr(self.prediction.weight_split), ptr(self.prediction.bias), n, ptr(pred), stream_ptr()))
+            check(load().vd_pred_conv_ex(ptr(xb.data), B, H, W, Cin, 1, _lib.VD_JOIN_NONE, self._precision,
+                                         ptr(self.prediction.weight_split(planes)), ptr(self.prediction.bias), n, ptr(pred), stream_ptr()))
         else:
             check(load().vd_pred_conv(ptr(xb), B, H, W, Cin, 1, _lib.VD_JOIN_NONE, ptr(self.prediction.weight_bf16),
                                       ptr(self.prediction.bias), n, ptr(pred), stream_ptr()))
@@ -342,10 +347,12 @@ class TemporalTipConv:
     """The temporal cell of Conv('21', C, 3, 1, 1) (layers.py:82-89 second `_conv3d`):
     Conv3D(C, (3,1,1), pad (1,0,0), no bias) + BatchNorm(eps=1e-5) + LeakyReLU(0.1) on (B,T,C,H,W)."""
 
-    def __init__(self, channels, epsilon=1e-5, slope=0.1):
+    def __init__(self, channels, epsilon=1e-5, slope=0.1, precision="bf16"):
         self.channels = channels
         self.epsilon = epsilon
         self.slope = slope
+        self._precision = _precision_code(precision)   # fp32-parity modes: split carriers in and out (vd_temporal_conv_ex)
+        self._w_split = {}
         self.weight = None                 # (Cout, Cin, 3, 1, 1) fp32, Gluon Conv3D layout
         self.gamma = torch.ones(channels, device="cuda")
         self.beta = torch.zeros(channels, device="cuda")
@@ -366,13 +373,38 @@ class TemporalTipConv:
                 setattr(self, name, torch.as_tensor(v).detach().to(torch.float32).cuda().contiguous())
         # [tap][cout][cin] bf16 + folded inference BatchNorm
         self._w_taps = self.weight.permute(2, 0, 1).contiguous().to(torch.bfloat16)
+        self._w_split = {}
         self._scale = (self.gamma / torch.sqrt(self.running_var + self.epsilon)).contiguous()
         self._shift = (self.beta - self.running_mean * self._scale).contiguous()
 
+    def weight_split(self, planes):
+        """(planes, 3, Cout, Cin) bf16 planes of the fp32 weight, [plane][tap][cout][cin] (vd_temporal_conv_ex)."""
+        if planes not in self._w_split:
+            c = self.channels
+            taps = self.weight.permute(2, 0, 1).contiguous().reshape(3 * c, c)          # fp32 [tap][cout][cin]
+            rows = torch.empty((3 * c, planes, c), dtype=torch.bfloat16, device=taps.device)
+            check(load().vd_split_f32_rows(ptr(taps), ptr(rows), 3 * c, c, planes, stream_ptr()))
+            self._w_split[planes] = rows.permute(1, 0, 2).contiguous().reshape(planes, 3, c, c)
+        return self._w_split[planes]
+
+    def split_forward(self, xs, B, T):
+        """fp32-parity mode: xs = SplitF32 of the (B*T, C, H, W) window frames -> SplitF32 of the cell's fp32 output."""
+        planes = _lib.PLANES[self._precision]
+        assert planes > 1 and xs.planes == planes
+        F, C, H, W = xs.shape
+        assert F == B * T and C == self.channels
+        y = torch.empty_like(xs.data)
+        check(load().vd_temporal_conv_ex(ptr(xs.data), ptr(y), B, T, H, W, C, ptr(self.weight_split(planes)), ptr(self._scale),
+                                         ptr(self._shift), float(self.slope), self._precision, stream_ptr()))
+        return SplitF32(y, xs.shape)
+
     def __call__(self, x):
-        """x (B,T,C,H,W) -> (B,T,C,H,W) bf16 (channels-last per frame)."""
+        """x (B,T,C,H,W) -> (B,T,C,H,W) bf16 (channels-last per frame); in an fp32-parity mode: fp32 (B,T,C,H,W) in, SplitF32 of
+        the (B*T,C,H,W) output frames out."""
         _require_cuda(x, "x")
         B, T, C, H, W = x.shape
+        if self._precision != _lib.VD_PREC_BF16:
+            return self.split_forward(to_nhwc_split(x.reshape(B * T, C, H, W), _lib.PLANES[self._precision]), B, T)
         xb = to_nhwc_bf16(x.reshape(B * T, C, H, W))
         y = torch.empty((B * T, C, H, W), dtype=torch.bfloat16, device=x.device, memory_format=torch.channels_last)
         check(load().vd_temporal_conv(ptr(xb), ptr(y), B, T, H, W, C, ptr(self._w_taps), ptr(self._scale),
@@ -528,12 +560,12 @@ class YOLOV3Head:
 
     def __init__(self, classes, anchors=None, strides=None, channels=None, nms_thresh=0.45, nms_topk=400,
                  post_nms=100, temporal=None, k=1, agnostic=False, precision="bf16"):
-        """precision 'bf16' (default): bf16 operands, fp32 accumulate -- 1e-3 relative vs the fp32 reference.
-        precision 'fp32': fp32 NCHW tips are split into hi/lo bf16 planes, three products per term -- 1e-5 relative
-        (VD_PREC_FP32_SPLIT; plain per-frame heads only)."""
+        """precision 'bf16' (default): bf16 operands, fp32 accumulate -- 1e-3 relative vs the fp32 reference on bf16-representable
+        inputs.  precision 'fp32': fp32 NCHW tips / weights are split into three bf16 planes, six plane products -- 1e-5
+        relative (VD_PREC_FP32_SPLIT); 'bf16x2': two planes, three products -- 1e-4 (VD_PREC_BF16X2).  Per-frame heads only."""
         self._precision = _precision_code(precision)
-        if self._precision != _lib.VD_PREC_BF16 and temporal is not None:
-            raise NotImplementedError("precision='fp32' is available for the per-frame head (temporal=None)")
+        if self._precision != _lib.VD_PREC_BF16 and temporal not in (None, "conv21"):
+            raise NotImplementedError("the fp32-parity modes cover the per-frame head and the 'conv21' temporal head")
         self.classes = list(classes) if not isinstance(classes, int) else list(range(classes))
         self._num_class = len(self.classes)
         anchors = DEFAULT_ANCHORS if anchors is None else anchors
@@ -553,7 +585,7 @@ class YOLOV3Head:
         if agnostic:
             raise NotImplementedError("agnostic detector tail: use YOLOOutputV3(agnostic=True) + box_nms")
         self.yolo_outputs = [YOLOOutputV3(i, self._num_class, a, s, precision=precision) for i, (a, s) in enumerate(zip(anchors, strides))]
-        self.tip_convs = [TemporalTipConv(c) for c in self.channels] if temporal == "conv21" else None
+        self.tip_convs = [TemporalTipConv(c, precision=precision) for c in self.channels] if temporal == "conv21" else None
         self.pool = TemporalPooling(k, temporal) if temporal in ("max", "mean") else None
         self._keep = None
         self._ws_cache = {}
@@ -599,7 +631,8 @@ class YOLOV3Head:
         p.nms_thresh, p.valid_thresh = float(self.nms_thresh), float(self.valid_thresh)
         p.nms_topk, p.post_nms = int(self.nms_topk), int(self.post_nms)
         p.precision = self._precision
-        split = self._precision == _lib.VD_PREC_FP32_SPLIT
+        planes = _lib.PLANES[self._precision]
+        split = planes > 1
         frames = None
         for i, (t, o) in enumerate(zip(tips, self.yolo_outputs)):
             F, C, H, W = t.shape
@@ -611,13 +644,13 @@ class YOLOV3Head:
             frames = F if frames is None else frames
             assert frames == F, "all scales must carry the same number of frames"
             s.tip_nhwc_bf16 = t.data.data_ptr() if split else t.data_ptr()
-            s.weight_bf16 = (o.prediction.weight_split if split else o.prediction.weight_bf16).data_ptr()
+            s.weight_bf16 = (o.prediction.weight_split(planes) if split else o.prediction.weight_bf16).data_ptr()
             s.bias = o.prediction.bias.data_ptr()
             s.H, s.W, s.Cin = H, W, C
             s.stride = float(o._stride)
             for j in range(6):
                 s.anchors[j] = float(o._anchors_np[j])
-            if self.tip_convs is not None:
+            if self.tip_convs is not None and not split:
                 tc = self.tip_convs[i]
                 s.tconv_weight_bf16 = tc._w_taps.data_ptr()
                 s.tconv_scale = tc._scale.data_ptr()
@@ -629,17 +662,18 @@ class YOLOV3Head:
     def _prepare(self, tips):
         lead = None
         flat = []
-        split = self._precision == _lib.VD_PREC_FP32_SPLIT
+        planes = _lib.PLANES[self._precision]
+        split = planes > 1
         for t in tips:
             if isinstance(t, SplitF32):
-                assert split, "SplitF32 tips need precision='fp32'"
+                assert split and t.planes == planes, "SplitF32 tips need a matching fp32-parity precision"
                 flat.append(t)
                 continue
             _require_cuda(t, "tip")
             if t.dim() == 5:
                 lead = (t.shape[0], t.shape[1])
                 t = t.reshape((t.shape[0] * t.shape[1],) + tuple(t.shape[2:]))
-            flat.append(to_nhwc_split(t) if split else to_nhwc_bf16(t))
+            flat.append(to_nhwc_split(t, planes) if split else to_nhwc_bf16(t))
         T = 1
         if self.temporal in ("max", "mean"):
             assert lead is not None, "temporal pooling needs (B,K,C,H,W) tips"
@@ -651,7 +685,10 @@ class YOLOV3Head:
         elif self.temporal == "conv21":
             assert lead is not None, "the temporal tip cell needs (B,T,C,H,W) tips"
             T = lead[1]
-        scratch = [torch.empty_like(f) for f in flat] if self.tip_convs is not None else None
+            if split:      # parity modes: the tip cells run here (split carriers in and out), the fused call then sees a plain per-frame head
+                flat = [tc.split_forward(f, lead[0], T) for tc, f in zip(self.tip_convs, flat)]
+                T = 1
+        scratch = [torch.empty_like(f) for f in flat] if (self.tip_convs is not None and not split) else None
         p = self._params(flat, scratch)
         p.T = T
         return p, flat, scratch, lead

@@ -78,14 +78,22 @@ repack_nchw_to_nhwc_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __
     }
 }
 
-// (B, C, H, W) fp32 -> (B, 2, H, W, C) bf16 hi / lo planes: hi = bf16(v), lo = bf16(v - hi)  (VD_PREC_FP32_SPLIT carrier)
+// fp32 -> bf16 planes: p0 = bf16(v), p1 = bf16(v - p0), p2 = bf16(v - p0 - p1); the subtractions are exact in fp32
+__device__ __forceinline__ void split_planes(float v, int planes, __nv_bfloat16* out /*[3]*/) {
+    out[0] = __float2bfloat16_rn(v);
+    const float r1 = __fsub_rn(v, __bfloat162float(out[0]));
+    out[1] = __float2bfloat16_rn(r1);
+    out[2] = planes > 2 ? __float2bfloat16_rn(__fsub_rn(r1, __bfloat162float(out[1]))) : __float2bfloat16_rn(0.0f);
+}
+// (B, C, H, W) fp32 -> (planes, B, H, W, C) bf16 planes (carrier of the fp32-parity modes)
 __global__ void __launch_bounds__(256)
-repack_nchw_to_nhwc_split_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int C, int HW) {
+repack_nchw_to_nhwc_split_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int C, int HW, int planes) {
     __shared__ float tile[32][33];
     const int b = blockIdx.z, c0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const float* s = src + (size_t)b * C * HW;
-    __nv_bfloat16* d = dst + (size_t)b * 2 * HW * C;
+    __nv_bfloat16* d = dst + (size_t)b * HW * C;
+    const size_t plane = (size_t)gridDim.z * HW * C;
     for (int i = ty; i < 32; i += 8) {
         int c = c0 + i, p = p0 + tx;
         tile[i][tx] = (c < C && p < HW) ? s[(size_t)c * HW + p] : 0.0f;
@@ -94,22 +102,20 @@ repack_nchw_to_nhwc_split_kernel(const float* __restrict__ src, __nv_bfloat16* _
     for (int i = ty; i < 32; i += 8) {
         int p = p0 + i, c = c0 + tx;
         if (p < HW && c < C) {
-            const float v = tile[tx][i];
-            const __nv_bfloat16 hi = __float2bfloat16_rn(v);
-            d[(size_t)p * C + c] = hi;
-            d[(size_t)HW * C + (size_t)p * C + c] = __float2bfloat16_rn(__fsub_rn(v, __bfloat162float(hi)));
+            __nv_bfloat16 pl[3];
+            split_planes(tile[tx][i], planes, pl);
+            for (int q = 0; q < planes; ++q) d[q * plane + (size_t)p * C + c] = pl[q];
         }
     }
 }
 __global__ void __launch_bounds__(256)
-split_rows_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int64_t rows, int64_t cols) {
+split_rows_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int64_t rows, int64_t cols, int planes) {
     const int64_t n = rows * cols;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t r = i / cols, c = i - r * cols;
-        const float v = src[i];
-        const __nv_bfloat16 hi = __float2bfloat16_rn(v);
-        dst[(r * 2) * cols + c] = hi;
-        dst[(r * 2 + 1) * cols + c] = __float2bfloat16_rn(__fsub_rn(v, __bfloat162float(hi)));
+        __nv_bfloat16 pl[3];
+        split_planes(src[i], planes, pl);
+        for (int q = 0; q < planes; ++q) dst[(r * planes + q) * cols + c] = pl[q];
     }
 }
 
@@ -168,23 +174,23 @@ extern "C" int vd_repack_nchw_f32_to_nhwc_bf16(const float* src, void* dst, int 
     return VD_OK;
 }
 
-extern "C" int vd_repack_nchw_f32_to_nhwc_split(const float* src, void* dst, int B, int C, int H, int W, void* stream) {
-    VD_CHECK_ARG((B == 0 || (src && dst)) && B >= 0 && C > 0 && H > 0 && W > 0, "repack_split: bad argument");
+extern "C" int vd_repack_nchw_f32_to_nhwc_split(const float* src, void* dst, int B, int C, int H, int W, int planes, void* stream) {
+    VD_CHECK_ARG((B == 0 || (src && dst)) && B >= 0 && C > 0 && H > 0 && W > 0 && (planes == 2 || planes == 3), "repack_split: bad argument");
     VD_CHECK_ARG(B <= 65535, "repack_split: batch > 65535");
     if (B == 0) return VD_OK;
     int HW = H * W;
     dim3 grid(ceil_div(HW, 32), ceil_div(C, 32), B);
-    repack_nchw_to_nhwc_split_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(src, (__nv_bfloat16*)dst, C, HW);
+    repack_nchw_to_nhwc_split_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(src, (__nv_bfloat16*)dst, C, HW, planes);
     VD_LAUNCH_CHECK();
     return VD_OK;
 }
 
-extern "C" int vd_split_f32_rows(const float* src, void* dst, int64_t rows, int64_t cols, void* stream) {
-    VD_CHECK_ARG(rows >= 0 && cols > 0 && (rows == 0 || (src && dst)), "split_rows: bad argument");
+extern "C" int vd_split_f32_rows(const float* src, void* dst, int64_t rows, int64_t cols, int planes, void* stream) {
+    VD_CHECK_ARG(rows >= 0 && cols > 0 && (rows == 0 || (src && dst)) && (planes == 2 || planes == 3), "split_rows: bad argument");
     if (rows == 0) return VD_OK;
     int64_t blocks = ceil_div64(rows * cols, 256); const int64_t cap = (int64_t)sm_count() * 16;
     if (blocks > cap) blocks = cap;
-    split_rows_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(src, (__nv_bfloat16*)dst, rows, cols);
+    split_rows_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(src, (__nv_bfloat16*)dst, rows, cols, planes);
     VD_LAUNCH_CHECK();
     return VD_OK;
 }

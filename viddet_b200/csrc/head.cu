@@ -73,7 +73,8 @@ __host__ __device__ __forceinline__ uint32_t hist_edge(uint32_t bin) {   // smal
 struct HeadKernelParams {
     HeadGeom g;
     int frames, K_frames;
-    int split;                           // fp32-parity mode: K_frames = 3 virtual planes (A_hi W_hi + A_lo W_hi + A_hi W_lo), operands stored as hi/lo bf16 planes
+    int split;                           // fp32-parity modes: operand planes in memory (0: off; 3: hi/mid/lo; 2: hi/lo); K_frames = number of plane products
+    signed char a_pl[8], w_pl[8];        // plane of A / of W that product kf of the K loop multiplies
     int cin[VD_MAX_SCALES];
     int pb[VD_MAX_SCALES];               // pixel blocks per frame
     int tile_start[VD_MAX_SCALES + 1];   // cumulative tile index per processing slot
@@ -321,9 +322,9 @@ head_kernel(const __grid_constant__ HeadMaps maps, const __grid_constant__ HeadK
                     unsigned char* a_dst = ring + stage * Cfg::STAGE_BYTES;
                     unsigned char* b_dst = a_dst + A_TILE_BYTES;
                     tc::mbar_expect_tx(&sh->full[stage], Cfg::STAGE_BYTES);
-                    // fp32-parity mode: plane kf of the K loop pairs (A_hi, W_hi), (A_lo, W_hi), (A_hi, W_lo) -- the a_lo * w_lo term (2^-18 relative) is dropped
-                    const int a_pl = p.split ? (kf == 1 ? 1 : 0) : kf;
-                    const int w_pl = p.split ? (kf == 2 ? 1 : 0) : kf;
+                    // fp32-parity modes: product kf of the K loop pairs plane a_pl[kf] of A with plane w_pl[kf] of W (split_products())
+                    const int a_pl = p.split ? (int)p.a_pl[kf & 7] : kf;
+                    const int w_pl = p.split ? (int)p.w_pl[kf & 7] : kf;
                     tc::tma_load_4d_hint(a_dst, &maps.a[s], &sh->full[stage], c0, pblk * BLOCK_M, a_pl, f, pol_a);
                     tc::tma_load_2d_hint(b_dst, &maps.w[s], &sh->full[stage], w_pl * p.cin[s] + c0, 0, pol_w);
                     c0 += BLOCK_K; if (c0 == p.cin[s]) { c0 = 0; ++kf; }
@@ -1428,6 +1429,18 @@ struct HeadPlan {
 
 static int head_npad(int C) { int n = 3 * (5 + C); return (n + 15) / 16 * 16; }
 
+// Plane products of the fp32-parity modes, largest terms first.  v = p0 + p1 (+ p2) with |p1| <= 2^-9 |v|, |p2| <= 2^-18 |v|.
+//   3 planes (VD_PREC_FP32_SPLIT):  p0 w0 + p1 w0 + p0 w1 + p1 w1 + p2 w0 + p0 w2   (dropped terms <= 2^-27 relative)
+//   2 planes (VD_PREC_BF16X2):      p0 w0 + p1 w0 + p0 w1                           (dropped / residual terms ~ 2^-18 relative)
+static int split_products(int precision, HeadKernelParams* k) {
+    static const signed char a3[6] = {0, 1, 0, 1, 2, 0}, w3[6] = {0, 0, 1, 1, 0, 2};
+    const int n = precision == VD_PREC_FP32_SPLIT ? 6 : 3;
+    k->split = precision == VD_PREC_FP32_SPLIT ? 3 : 2;
+    k->K_frames = n;
+    for (int i = 0; i < 8; ++i) { k->a_pl[i] = i < n ? a3[i] : 0; k->w_pl[i] = i < n ? w3[i] : 0; }
+    return n;
+}
+
 static int make_plan(const VdHeadParams* hp, HeadPlan* pl) {
     VD_CHECK_ARG(hp, "head: null params");
     VD_CHECK_ARG(hp->num_scales >= 1 && hp->num_scales <= VD_MAX_SCALES, "head: num_scales %d", hp->num_scales);
@@ -1443,14 +1456,14 @@ static int make_plan(const VdHeadParams* hp, HeadPlan* pl) {
     k.frames = hp->frames; k.n_pad = npad; k.n_valid = 3 * (5 + C);
     const int join = hp->join;
     VD_CHECK_ARG(join == VD_JOIN_NONE || join == VD_JOIN_CAT, "head: join %d must be pre-reduced (use vd_temporal_pool for max/mean)", join);
-    VD_CHECK_ARG(hp->precision == VD_PREC_BF16 || hp->precision == VD_PREC_FP32_SPLIT, "head: precision %d", hp->precision);
+    VD_CHECK_ARG(hp->precision == VD_PREC_BF16 || hp->precision == VD_PREC_FP32_SPLIT || hp->precision == VD_PREC_BF16X2, "head: precision %d", hp->precision);
     k.K_frames = (join == VD_JOIN_CAT) ? hp->K_frames : 1;
     VD_CHECK_ARG(k.K_frames >= 1, "head: K_frames %d", k.K_frames);
-    if (hp->precision == VD_PREC_FP32_SPLIT) {
-        if (join != VD_JOIN_NONE) return set_error(VD_ERR_UNSUPPORTED, "head: VD_PREC_FP32_SPLIT with a late cat join is not supported");
+    if (hp->precision != VD_PREC_BF16) {
+        if (join != VD_JOIN_NONE) return set_error(VD_ERR_UNSUPPORTED, "head: the fp32-parity modes are not combinable with a late cat join");
         for (int s = 0; s < hp->num_scales; ++s)
-            if (hp->scale[s].tconv_weight_bf16) return set_error(VD_ERR_UNSUPPORTED, "head: VD_PREC_FP32_SPLIT with the fused temporal tip cell is not supported");
-        k.split = 1; k.K_frames = 3;
+            if (hp->scale[s].tconv_weight_bf16) return set_error(VD_ERR_UNSUPPORTED, "head: the fp32-parity modes are not combinable with the fused temporal tip cell (run vd_temporal_conv_ex first)");
+        split_products(hp->precision, &k);
     }
     int rows = 0, anc = 0, tif = 0;
     for (int s = 0; s < hp->num_scales; ++s) {
@@ -1508,10 +1521,12 @@ static int make_plan(const VdHeadParams* hp, HeadPlan* pl) {
 static int make_maps(const VdHeadParams* hp, const HeadPlan& pl, HeadMaps* maps) {
     for (int s = 0; s < hp->num_scales; ++s) {
         const VdHeadScale& sc = hp->scale[s];
-        const uint64_t HW = (uint64_t)sc.H * sc.W, Cin = sc.Cin, K = pl.kp.split ? 2 : pl.kp.K_frames;   // split: (frames, 2, H, W, Cin) hi / lo planes
+        const uint64_t HW = (uint64_t)sc.H * sc.W, Cin = sc.Cin, K = pl.kp.split ? pl.kp.split : pl.kp.K_frames;
+        const uint64_t F = (uint64_t)(hp->frames > 0 ? hp->frames : 1);
         const void* aptr = (sc.tconv_weight_bf16 && sc.tconv_out_nhwc_bf16) ? sc.tconv_out_nhwc_bf16 : sc.tip_nhwc_bf16;
-        uint64_t dimsA[4] = {Cin, HW, K, (uint64_t)(hp->frames > 0 ? hp->frames : 1)};
+        uint64_t dimsA[4] = {Cin, HW, K, F};
         uint64_t strA[3] = {Cin * 2, HW * Cin * 2, K * HW * Cin * 2};
+        if (pl.kp.split) { strA[1] = F * HW * Cin * 2; strA[2] = HW * Cin * 2; }     // plane-major carrier (planes, frames, H, W, Cin): every plane is an ordinary NHWC tensor
         uint32_t boxA[4] = {BLOCK_K, BLOCK_M, 1, 1};
         int rc = encode_tmap_bf16(&maps->a[s], aptr, 4, dimsA, strA, boxA);
         if (rc) return rc;
@@ -1762,15 +1777,16 @@ extern "C" int vd_pred_conv(const void* x, int B, int H, int W, int Cin, int K_f
 extern "C" int vd_pred_conv_ex(const void* x, int B, int H, int W, int Cin, int K_frames, int join, int precision,
                                const void* weight, const float* bias, int N, float* pred, void* stream_) {
     VD_CHECK_ARG(weight && (B == 0 || (x && pred)), "pred_conv: null pointer");
-    VD_CHECK_ARG(precision == VD_PREC_BF16 || precision == VD_PREC_FP32_SPLIT, "pred_conv: precision %d", precision);
-    const bool split = precision == VD_PREC_FP32_SPLIT;
-    if (split && join != VD_JOIN_NONE) return set_error(VD_ERR_UNSUPPORTED, "pred_conv: VD_PREC_FP32_SPLIT with a late cat join is not supported");
+    VD_CHECK_ARG(precision == VD_PREC_BF16 || precision == VD_PREC_FP32_SPLIT || precision == VD_PREC_BF16X2, "pred_conv: precision %d", precision);
+    const bool split = precision != VD_PREC_BF16;
+    const int planes = precision == VD_PREC_FP32_SPLIT ? 3 : 2;
+    if (split && join != VD_JOIN_NONE) return set_error(VD_ERR_UNSUPPORTED, "pred_conv: the fp32-parity modes are not combinable with a late cat join");
     VD_CHECK_ARG(B >= 0 && B <= 65535 && H > 0 && W > 0 && N > 0, "pred_conv: bad shape");
     VD_CHECK_ARG(Cin > 0 && Cin % BLOCK_K == 0, "pred_conv: Cin %d must be a multiple of %d", Cin, BLOCK_K);
     VD_CHECK_ARG(join == VD_JOIN_NONE || join == VD_JOIN_CAT, "pred_conv: join %d must be pre-reduced (vd_temporal_pool)", join);
     VD_CHECK_ARG(((uintptr_t)x & 15) == 0 && ((uintptr_t)weight & 15) == 0, "pred_conv: tensors must be 16-byte aligned");
     if (B == 0) return VD_OK;
-    const int K = split ? 2 : ((join == VD_JOIN_CAT) ? K_frames : 1);      // planes per frame in memory (split: hi / lo)
+    const int K = split ? planes : ((join == VD_JOIN_CAT) ? K_frames : 1);      // operand planes / joined frames in memory
     VD_CHECK_ARG(K >= 1, "pred_conv: K_frames %d", K_frames);
     const uint64_t HW = (uint64_t)H * W;
     for (int n0 = 0; n0 < N; n0 += 256) {            // output-channel slices of <= 256 rows of W
@@ -1778,7 +1794,8 @@ extern "C" int vd_pred_conv_ex(const void* x, int B, int H, int W, int Cin, int 
         HeadKernelParams kp; memset(&kp, 0, sizeof(kp));
         kp.g.num_scales = 1; kp.g.num_class = 1; kp.g.A = 3;
         kp.g.H[0] = H; kp.g.W[0] = W; kp.g.HW[0] = (int)HW; kp.g.stride[0] = 1.f;
-        kp.frames = B; kp.K_frames = split ? 3 : K; kp.split = split ? 1 : 0; kp.cin[0] = Cin;
+        kp.frames = B; kp.K_frames = K; kp.cin[0] = Cin;
+        if (split) split_products(precision, &kp);
         kp.pb[0] = ceil_div((int)HW, BLOCK_M);
         kp.tile_start[0] = 0; kp.tile_start[1] = kp.pb[0] * B; kp.order[0] = 0;
         kp.tiles_per_frame = kp.pb[0]; kp.total_tiles = kp.pb[0] * B;
@@ -1788,6 +1805,7 @@ extern "C" int vd_pred_conv_ex(const void* x, int B, int H, int W, int Cin, int 
         HeadMaps maps;
         uint64_t dimsA[4] = {(uint64_t)Cin, HW, (uint64_t)K, (uint64_t)B};
         uint64_t strA[3] = {(uint64_t)Cin * 2, HW * Cin * 2, (uint64_t)K * HW * Cin * 2};
+        if (split) { strA[1] = (uint64_t)B * HW * Cin * 2; strA[2] = HW * Cin * 2; }      // plane-major (planes, B, H, W, Cin)
         uint32_t boxA[4] = {BLOCK_K, BLOCK_M, 1, 1};
         int rc = encode_tmap_bf16(&maps.a[0], x, 4, dimsA, strA, boxA);
         if (rc) return rc;

@@ -25,6 +25,11 @@ struct TConvParams {
     int m_tiles, n_tiles, total_tiles;
     const float* scale; const float* shift; float slope;
     __nv_bfloat16* y;
+    // fp32-parity modes (vd_temporal_conv_ex): x (planes, B, T*HW, C), w (planes, 3, Cout, Cin), y (planes, B, T*HW, C); the
+    // K loop of a tap runs n_prod plane products (a_pl[i], w_pl[i]); planes == 1: the plain bf16 cell
+    int planes, n_prod;
+    signed char a_pl[8], w_pl[8];
+    long long y_plane_stride;      // elements between output planes
 };
 struct TConvMaps { CUtensorMap x; CUtensorMap w; };
 
@@ -87,13 +92,16 @@ temporal_conv_kernel(const __grid_constant__ TConvMaps maps, const __grid_consta
                 for (int tap = 0; tap < 3; ++tap) {
                     const int dt = tap - 1;
                     if (!tap_active(mt, dt)) continue;
-                    for (int kb = 0; kb < kb_per_tap; ++kb) {
-                        tc::mbar_wait(&sh->empty[stage], phase ^ 1u);
-                        unsigned char* a_dst = ring + stage * Cfg::STAGE_BYTES;
-                        tc::mbar_expect_tx(&sh->full[stage], Cfg::STAGE_BYTES);
-                        tc::tma_load_3d(a_dst, &maps.x, &sh->full[stage], kb * T_BLOCK_K, mt * T_BLOCK_M + dt * p.HW, b);
-                        tc::tma_load_3d(a_dst + Cfg::A_BYTES, &maps.w, &sh->full[stage], kb * T_BLOCK_K, nt * NT, tap);
-                        if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
+                    for (int pr = 0; pr < p.n_prod; ++pr) {
+                        const int xb = b + (int)p.a_pl[pr] * p.B, wt = tap + 3 * (int)p.w_pl[pr];     // plane-major operands
+                        for (int kb = 0; kb < kb_per_tap; ++kb) {
+                            tc::mbar_wait(&sh->empty[stage], phase ^ 1u);
+                            unsigned char* a_dst = ring + stage * Cfg::STAGE_BYTES;
+                            tc::mbar_expect_tx(&sh->full[stage], Cfg::STAGE_BYTES);
+                            tc::tma_load_3d(a_dst, &maps.x, &sh->full[stage], kb * T_BLOCK_K, mt * T_BLOCK_M + dt * p.HW, xb);
+                            tc::tma_load_3d(a_dst + Cfg::A_BYTES, &maps.w, &sh->full[stage], kb * T_BLOCK_K, nt * NT, wt);
+                            if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
+                        }
                     }
                 }
             }
@@ -111,7 +119,7 @@ temporal_conv_kernel(const __grid_constant__ TConvMaps maps, const __grid_consta
                 uint32_t first = 1;
                 for (int tap = 0; tap < 3; ++tap) {
                     if (!tap_active(mt, tap - 1)) continue;
-                    for (int kb = 0; kb < kb_per_tap; ++kb) {
+                    for (int kb = 0; kb < kb_per_tap * p.n_prod; ++kb) {          // all plane products of the tap accumulate into the same tile
                         tc::mbar_wait(&sh->full[stage], phase);
                         tc::fence_after_sync();
                         const uint32_t a_addr = tc::smem_u32(ring + stage * Cfg::STAGE_BYTES);
@@ -152,21 +160,39 @@ temporal_conv_kernel(const __grid_constant__ TConvMaps maps, const __grid_consta
                 uint32_t r[32];
                 tc::tmem_ld16(tbase + n0, r); tc::tmem_ld16(tbase + n0 + 16, r + 16); tc::tmem_ld_wait();
                 uint32_t packed[16];
+#pragma unroll 1
+                for (int pl = 0; pl < p.planes; ++pl) {            // plane pl of the fp32 result: bf16(v - planes before it) (exact subtractions)
 #pragma unroll
-                for (int i = 0; i < 32; i += 4) {
-                    const float4 s4 = *reinterpret_cast<const float4*>(sc + n0 + i);
-                    const float4 f4 = *reinterpret_cast<const float4*>(sf + n0 + i);
-                    float v0 = fmaf(__uint_as_float(r[i]), s4.x, f4.x), v1 = fmaf(__uint_as_float(r[i + 1]), s4.y, f4.y);
-                    float v2 = fmaf(__uint_as_float(r[i + 2]), s4.z, f4.z), v3 = fmaf(__uint_as_float(r[i + 3]), s4.w, f4.w);
-                    v0 = v0 > 0.f ? v0 : v0 * p.slope; v1 = v1 > 0.f ? v1 : v1 * p.slope;
-                    v2 = v2 > 0.f ? v2 : v2 * p.slope; v3 = v3 > 0.f ? v3 : v3 * p.slope;
-                    __nv_bfloat162 h0 = __floats2bfloat162_rn(v0, v1), h1 = __floats2bfloat162_rn(v2, v3);
-                    packed[i / 2] = *reinterpret_cast<uint32_t*>(&h0); packed[i / 2 + 1] = *reinterpret_cast<uint32_t*>(&h1);
-                }
-                if (inb) {
-                    uint4* dst = reinterpret_cast<uint4*>(yrow + n0);
+                    for (int i = 0; i < 32; i += 4) {
+                        float v[4];
+                        if (pl == 0) {
+                            const float4 s4 = *reinterpret_cast<const float4*>(sc + n0 + i);
+                            const float4 f4 = *reinterpret_cast<const float4*>(sf + n0 + i);
+                            if (p.planes == 1) {                   // the plain bf16 cell keeps its historical arithmetic (fused multiply-add)
+                                v[0] = fmaf(__uint_as_float(r[i]), s4.x, f4.x); v[1] = fmaf(__uint_as_float(r[i + 1]), s4.y, f4.y);
+                                v[2] = fmaf(__uint_as_float(r[i + 2]), s4.z, f4.z); v[3] = fmaf(__uint_as_float(r[i + 3]), s4.w, f4.w);
+                            } else {                               // parity modes: the reference's two roundings, (y * scale) + shift
+                                v[0] = __fadd_rn(__fmul_rn(__uint_as_float(r[i]), s4.x), f4.x); v[1] = __fadd_rn(__fmul_rn(__uint_as_float(r[i + 1]), s4.y), f4.y);
+                                v[2] = __fadd_rn(__fmul_rn(__uint_as_float(r[i + 2]), s4.z), f4.z); v[3] = __fadd_rn(__fmul_rn(__uint_as_float(r[i + 3]), s4.w), f4.w);
+                            }
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) dst[i] = make_uint4(packed[4 * i], packed[4 * i + 1], packed[4 * i + 2], packed[4 * i + 3]);
+                            for (int u = 0; u < 4; ++u) v[u] = v[u] > 0.f ? v[u] : v[u] * p.slope;
+                        } else {
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) v[u] = __uint_as_float(r[i + u]);      // residual left by the previous plane
+                        }
+                        __nv_bfloat162 h0 = __floats2bfloat162_rn(v[0], v[1]), h1 = __floats2bfloat162_rn(v[2], v[3]);
+                        packed[i / 2] = *reinterpret_cast<uint32_t*>(&h0); packed[i / 2 + 1] = *reinterpret_cast<uint32_t*>(&h1);
+                        if (p.planes > 1) {
+                            r[i] = __float_as_uint(__fsub_rn(v[0], __low2float(h0))); r[i + 1] = __float_as_uint(__fsub_rn(v[1], __high2float(h0)));
+                            r[i + 2] = __float_as_uint(__fsub_rn(v[2], __low2float(h1))); r[i + 3] = __float_as_uint(__fsub_rn(v[3], __high2float(h1)));
+                        }
+                    }
+                    if (inb) {
+                        uint4* dst = reinterpret_cast<uint4*>(yrow + (size_t)pl * p.y_plane_stride + n0);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) dst[i] = make_uint4(packed[4 * i], packed[4 * i + 1], packed[4 * i + 2], packed[4 * i + 3]);
+                    }
                 }
             }
             tc::fence_before_sync();
@@ -378,29 +404,44 @@ using namespace vd;
 extern "C" int vd_temporal_conv(const void* x, void* y, int B, int T, int H, int W, int C,
                                 const void* weight, const float* scale, const float* shift,
                                 float slope, void* stream_) {
+    return vd_temporal_conv_ex(x, y, B, T, H, W, C, weight, scale, shift, slope, VD_PREC_BF16, stream_);
+}
+
+extern "C" int vd_temporal_conv_ex(const void* x, void* y, int B, int T, int H, int W, int C,
+                                   const void* weight, const float* scale, const float* shift,
+                                   float slope, int precision, void* stream_) {
     VD_CHECK_ARG(weight && scale && shift && (B == 0 || (x && y)), "temporal_conv: null pointer");
     VD_CHECK_ARG(B >= 0 && T >= 1 && H > 0 && W > 0, "temporal_conv: bad shape");
     VD_CHECK_ARG(C >= 128 && C % 128 == 0 && C <= 1024, "temporal_conv: C = %d must be a multiple of 128, at most 1024", C);
     VD_CHECK_ARG(((uintptr_t)x & 15) == 0 && ((uintptr_t)y & 15) == 0 && ((uintptr_t)weight & 15) == 0, "temporal_conv: tensors must be 16-byte aligned");
+    VD_CHECK_ARG(precision == VD_PREC_BF16 || precision == VD_PREC_FP32_SPLIT || precision == VD_PREC_BF16X2, "temporal_conv: precision %d", precision);
     if (B == 0) return VD_OK;
+    const int planes = precision == VD_PREC_FP32_SPLIT ? 3 : (precision == VD_PREC_BF16X2 ? 2 : 1);
     const int NT = (C % 256 == 0) ? 256 : 128;
     TConvParams p;
+    memset(&p, 0, sizeof(p));
     p.B = B; p.T = T; p.HW = H * W; p.C = C; p.rows = T * H * W;
     p.m_tiles = ceil_div(p.rows, T_BLOCK_M); p.n_tiles = C / NT;
     long long total = (long long)B * p.m_tiles * p.n_tiles;
     VD_CHECK_ARG(total < (1ll << 31), "temporal_conv: too many tiles");
     p.total_tiles = (int)total;
     p.scale = scale; p.shift = shift; p.slope = slope; p.y = (__nv_bfloat16*)y;
+    p.planes = planes; p.n_prod = 1; p.y_plane_stride = (long long)B * p.rows * C;
+    if (planes > 1) {                      // same plane products as the head kernel (head.cu split_products)
+        static const signed char a3[6] = {0, 1, 0, 1, 2, 0}, w3[6] = {0, 0, 1, 1, 0, 2};
+        p.n_prod = planes == 3 ? 6 : 3;
+        for (int i = 0; i < p.n_prod; ++i) { p.a_pl[i] = a3[i]; p.w_pl[i] = w3[i]; }
+    }
     TConvMaps maps;
-    uint64_t dimsX[3] = {(uint64_t)C, (uint64_t)p.rows, (uint64_t)B};
+    uint64_t dimsX[3] = {(uint64_t)C, (uint64_t)p.rows, (uint64_t)B * planes};
     uint64_t strX[2] = {(uint64_t)C * 2, (uint64_t)p.rows * C * 2};
     uint32_t boxX[3] = {T_BLOCK_K, T_BLOCK_M, 1};
     int rc = encode_tmap_bf16(&maps.x, x, 3, dimsX, strX, boxX);
     if (rc) return rc;
-    uint64_t dimsW[3] = {(uint64_t)C, (uint64_t)C, 3};
+    uint64_t dimsW[3] = {(uint64_t)C, (uint64_t)C, (uint64_t)3 * planes};
     uint64_t strW[2] = {(uint64_t)C * 2, (uint64_t)C * C * 2};
     static const bool pair_ok = []() { const char* e = getenv("VD_CONV_PAIR"); return e ? atoi(e) != 0 : true; }();   // CTA pairs (cta_group::2) for 256-wide channel blocks
-    const bool pair = pair_ok && NT == 256 && (long long)B * p.m_tiles >= 2;
+    const bool pair = pair_ok && planes == 1 && NT == 256 && (long long)B * p.m_tiles >= 2;      // the parity modes run on the 1-CTA kernel
     uint32_t boxW[3] = {T_BLOCK_K, (uint32_t)(pair ? NT / 2 : NT), 1};
     rc = encode_tmap_bf16(&maps.w, weight, 3, dimsW, strW, boxW);
     if (rc) return rc;

@@ -36,8 +36,9 @@ WORKLOADS = {
 TEMPORAL_T = 5
 CHANNELS = [1024, 512, 256]
 STRIDES = [32, 16, 8]
-NRING = 4         # sessions (workspace + outputs) in flight
+NRING = 3         # sessions (workspace + outputs) in flight
 GRAPH_STEPS = 64  # steps per pipeline graph in long runs (a run of <= 96 steps is ONE graph of exactly that many steps)
+GROUP = 4         # batches (steps) one persistent head-kernel launch covers: the launch / prologue / tail of the kernel is paid once per GROUP steps
 
 
 def algorithmic_bytes_per_frame(C, size, elem=2):
@@ -194,31 +195,36 @@ def measured_tensor_peak():
     return 1413.6, "fallback"
 
 
-def synth_tips(torch, gen, frames, size, device, T=None):
-    """leaky_relu(N(0,1), 0.1) tips (what a conv-BN-LReLU tip emits under identity BN), bf16 NHWC; T: (frames//T, T, C, H, W)."""
+def synth_tips(torch, gen, frames, size, device, T=None, out=None):
+    """leaky_relu(N(0,1), 0.1) tips (what a conv-BN-LReLU tip emits under identity BN), bf16 NHWC; T: (frames//T, T, C, H, W).
+    out: write into these (frames, C, H, W) channels-last bf16 views instead of allocating."""
     tips = []
-    for c, s in zip(CHANNELS, STRIDES):
+    for k, (c, s) in enumerate(zip(CHANNELS, STRIDES)):
         h = size // s
         x = torch.randn((frames, c, h, h), generator=gen, device=device, dtype=torch.float32)
-        x = torch.where(x > 0, x, 0.1 * x).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+        x = torch.where(x > 0, x, 0.1 * x)
+        if out is not None:
+            out[k].copy_(x)
+            x = out[k]
+        else:
+            x = x.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
         tips.append(x if T is None else x.reshape(frames // T, T, c, h, h))
     return tips
 
 
-def synth_video_pool(torch, gen, n, frames, size, device, rho=0.95):
-    """'Video-like' pool: batch t+1 = perturbed batch t (AR(1) latent, correlation rho per step), slot by slot."""
-    pool, z = [], None
-    for _ in range(n):
-        tips, zs = [], []
+def synth_video_pool(torch, gen, n, frames, size, device, outs, rho=0.95):
+    """'Video-like' pool: batch t+1 = perturbed batch t (AR(1) latent, correlation rho per step), slot by slot; batch i is
+    written into outs[i] (channels-last bf16 views)."""
+    z = None
+    for i in range(n):
+        zs = []
         for k, (c, s) in enumerate(zip(CHANNELS, STRIDES)):
             h = size // s
             e = torch.randn((frames, c, h, h), generator=gen, device=device, dtype=torch.float32)
             zz = e if z is None else rho * z[k] + (1.0 - rho * rho) ** 0.5 * e
             zs.append(zz)
-            tips.append(torch.where(zz > 0, zz, 0.1 * zz).to(torch.bfloat16).contiguous(memory_format=torch.channels_last))
+            outs[i][k].copy_(torch.where(zz > 0, zz, 0.1 * zz))
         z = zs
-        pool.append(tips)
-    return pool
 
 
 def pin_to_gpu_numa(index):
@@ -304,22 +310,27 @@ def run_reference(args):
 
 
 class StepRunner:
-    """n steps of the pipelined head = GRAPH_STEPS-step graphs + ONE graph for the remainder; a run of <= 96 steps is a single
-    graph of exactly that many steps, so every timed step is a steady-state pipelined step (no serial remainder)."""
+    """n steps (batches) of the pipelined head.  One persistent head-kernel launch covers `group` consecutive batches of the resident
+    pool (they are contiguous in memory: one TMA map), its top-k / NMS kernel runs under the next launch's head kernel.  Launches
+    are replayed from CUDA graphs of GRAPH_STEPS steps + ONE graph for the remainder; a run of <= 96 steps is a single graph of
+    exactly that many steps, so every timed step is a steady-state step."""
 
-    def __init__(self, vd, sessions, pool):
-        self.vd, self.sessions, self.pool, self.graphs = vd, sessions, pool, {}
+    def __init__(self, vd, sessions, group_inputs, group):
+        self.vd, self.sessions, self.inputs, self.group, self.graphs = vd, sessions, group_inputs, group, {}
 
     def graph(self, n):
+        assert n % self.group == 0
         if n not in self.graphs:
-            self.graphs[n] = self.vd.HeadPipeline(self.sessions, steps=n, inputs=self.pool)
+            self.graphs[n] = self.vd.HeadPipeline(self.sessions, steps=n // self.group, inputs=self.inputs)
         return self.graphs[n]
 
     def plan(self, n):
+        assert n % self.group == 0, "steps must be a multiple of the launch group"
         if n <= 96:
             return [n]
-        q, r = divmod(n, GRAPH_STEPS)
-        return [GRAPH_STEPS] * q + ([r] if r else [])
+        gs = (GRAPH_STEPS // self.group) * self.group
+        q, r = divmod(n, gs)
+        return [gs] * q + ([r] if r else [])
 
     def prepare(self, n):
         for k in set(self.plan(n)):
@@ -450,6 +461,7 @@ def main():
     ap.add_argument("--data", default="iid", choices=["iid", "video", "same"],
                     help="iid: pool of distinct iid batches (default); video: batch t+1 = perturbed batch t; same: each session replays its own batch (r1 behaviour)")
     ap.add_argument("--pool", type=int, default=0, help="distinct resident input batches (default 32; 8 for the temporal workload)")
+    ap.add_argument("--group", type=int, default=0, help="steps (batches) per persistent head-kernel launch (default %d; 1 for the temporal workload)" % GROUP)
     ap.add_argument("--gather", default="peer", choices=["peer", "nccl"], help="multi-GPU detection gather: fused into the NMS sink over NVLink (peer) or staged NCCL all_gather")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -482,39 +494,52 @@ def main():
     C, size, frames = WORKLOADS[args.workload]
     temporal = args.workload == "vid416_t5_w64"
     T = TEMPORAL_T if temporal else None
+    group = max(1, args.group if args.group else (1 if temporal else GROUP))
+    while args.steps % group:                            # the largest launch group <= --group that divides the step count
+        group -= 1
     npool = args.pool or (8 if temporal else 32)
-    if args.data == "same":
-        npool = NRING
+    npool = max(group * NRING, (npool // group) * group)
+    gframes = group * frames                             # frames one launch covers
 
     gen = torch.Generator(device=dev).manual_seed(1234 + rank)
     cpu_gen = torch.Generator().manual_seed(1234)
     head = viddet_b200.YOLOV3Head(C, temporal="conv21" if temporal else None).initialize(generator=cpu_gen)   # U(-0.07,0.07), bias 0 (detect_yolo3.py:885)
     head.set_nms(nms_thresh=0.45, nms_topk=400, post_nms=100)            # detect_yolo3.py:200
-    # resident input pool (clips / frames of this rank) + ring of NRING sessions (workspace + outputs)
+    # resident input pool: npool distinct batches (clips / frames of this rank), contiguous per scale, so that `group` consecutive
+    # batches are one (group*frames, H, W, C) tensor; ring of NRING sessions (workspace + outputs), each covering one launch group
+    big = [torch.empty((npool * frames, c, size // s_, size // s_), dtype=torch.bfloat16, device=dev, memory_format=torch.channels_last)
+           for c, s_ in zip(CHANNELS, STRIDES)]
+    batch_view = lambda i: [b_[i * frames:(i + 1) * frames] for b_ in big]
     if args.data == "video":
         assert not temporal
-        pool = synth_video_pool(torch, gen, npool, frames, size, dev)
+        synth_video_pool(torch, gen, npool, frames, size, dev, [batch_view(i) for i in range(npool)])
     else:
-        pool = [synth_tips(torch, gen, frames, size, dev, T) for _ in range(npool)]
-    nf = NRING * frames * 100
+        for i in range(npool):
+            synth_tips(torch, gen, frames, size, dev, out=batch_view(i))
+    as_windows = (lambda ts: [t.reshape((t.shape[0] // T, T) + tuple(t.shape[1:])) for t in ts]) if temporal else (lambda ts: ts)
+    group_inputs = [[b_[g * gframes:(g + 1) * gframes] for b_ in big] for g in range(npool // group)]
+    nf = NRING * gframes * 100
     peer, gather_kind = None, "single GPU"
     if world > 1 and args.gather == "peer":
         try:
             peer = vdist.PeerGather(nf * 6)
             gather_kind = "fused: the NMS kernel's sink stores each result row into every peer's gather buffer over NVLink (CUDA IPC mapped), no collective in the step"
-        except Exception as e:                          # noqa: BLE001 -- any failure of the IPC setup falls back to the NCCL gather
+        except Exception as e:                          # noqa: BLE001 -- any failure of the IPC setup falls back to the NCCL gather (agreed across ranks inside PeerGather)
             sys.stderr.write("PeerGather unavailable (%s): falling back to the staged NCCL gather\n" % (e,))
             peer = None
     flat = peer.slot[:nf * 6] if peer is not None else torch.empty((nf * 6,), device=dev)
-    ids_all, scores_all, boxes_all = flat[:nf].view(NRING * frames, 100, 1), flat[nf:2 * nf].view(NRING * frames, 100, 1), flat[2 * nf:].view(NRING * frames, 100, 4)
+    ids_all, scores_all, boxes_all = flat[:nf].view(NRING * gframes, 100, 1), flat[nf:2 * nf].view(NRING * gframes, 100, 1), flat[2 * nf:].view(NRING * gframes, 100, 4)
     sessions = []
     for j in range(NRING):
-        sl = slice(j * frames, (j + 1) * frames)
-        s = head.session(pool[j % npool], out=(ids_all[sl], scores_all[sl], boxes_all[sl]), mirrors=peer.deltas if peer is not None else None)
+        sl = slice(j * gframes, (j + 1) * gframes)
+        s = head.session(as_windows(group_inputs[j]), out=(ids_all[sl], scores_all[sl], boxes_all[sl]), mirrors=peer.deltas if peer is not None else None)
         sessions.append(s)
-    pool_flat = [[t.reshape((-1,) + tuple(t.shape[-3:])) if t.dim() == 5 else t for t in p] for p in pool]
-    pool_flat = [[viddet_b200.to_nhwc_bf16(t) for t in p] for p in pool_flat]
-    runner = StepRunner(viddet_b200, sessions, None if args.data == "same" else pool_flat)
+    if args.data == "same":                               # r1 behaviour: every session keeps replaying its own inputs
+        group_inputs_run = None
+    else:
+        group_inputs_run = group_inputs
+    runner = StepRunner(viddet_b200, sessions, group_inputs_run, group)
+    pool_flat = [batch_view(i) for i in range(npool)]
     nccl_gather = world > 1 and peer is None
     if nccl_gather:                                      # fallback: staged all_gather of the ring per graph, off the critical path
         gather_kind = "NCCL all_gather_into_tensor of the ring's detections per graph on a side stream (staged snapshot)"
@@ -553,9 +578,13 @@ def main():
         torch.cuda.synchronize()
 
     sampler = make_sampler(local).start() if rank == 0 else None       # polling (and NVML's lazy init) is warm before the timed region
+    # warm-up: at least --warmup steps, at least two turns of the ring (thresholds in every workspace), and every graph of the
+    # timed region replayed once (the first replay of a CUDA graph pays its upload)
     runner.prepare(args.steps)
-    runner.prepare(max(args.warmup, 2 * NRING))
-    run_steps(max(args.warmup, 2 * NRING))
+    wsteps = -(-max(args.warmup, 2 * NRING * group) // group) * group
+    run_steps(wsteps)
+    for k in set(runner.plan(args.steps)):
+        runner.graph(k).cycle(); wsteps += k
     barrier()
     st0 = [s.stats() for s in sessions]
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -590,9 +619,10 @@ def main():
     stages = ([_lib.VD_STAGE_TCONV] if temporal else []) + [_lib.VD_STAGE_HEAD, _lib.VD_STAGE_NMS]
     evs = [[torch.cuda.Event(enable_timing=True) for _ in range(len(stages) + 1)] for _ in range(ksteps)]
     for i in range(4):
-        sessions[i % NRING].run()
+        sessions[i % NRING].rebind(group_inputs[i % len(group_inputs)]).run()
     torch.cuda.synchronize()
     for i in range(ksteps):
+        sessions[i % NRING].rebind(group_inputs[(i + 1) % len(group_inputs)])
         evs[i][0].record()
         for k, stg in enumerate(stages):
             sessions[i % NRING].run(stg)
@@ -602,7 +632,8 @@ def main():
     head_ms, nms_ms = med[-2], med[-1]
     tconv_ms = med[0] if temporal else None
     peak, peak_kind = measured_peaks()
-    alg_bytes = algorithmic_bytes_per_frame(C, size) * frames
+    alg_bytes = algorithmic_bytes_per_frame(C, size) * frames          # per step (one batch)
+    launch_bytes = alg_bytes * group                                     # per head-kernel launch
     step_ms = ms / args.steps
     if temporal:
         # cfg 4 is tensor-bound: 2*13*sum HW*C^2 (13 non-zero taps of a k=3 zero-padded conv over T=5) + pred conv, per window
@@ -624,26 +655,30 @@ def main():
         # longer than a step.  The tighter bound is used.
         head_ms_events = head_ms
         if world == 1:
-            head_ms = min(head_ms, step_ms)
-        achieved = alg_bytes / (head_ms * 1e-3) / 1e9
+            head_ms = min(head_ms, step_ms * group)
+        achieved = launch_bytes / (head_ms * 1e-3) / 1e9
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "traffic_head_kernel_%s.json" % args.workload)
         if os.path.exists(tpath):
             traffic = json.load(open(tpath)).get("traffic_bytes_per_launch")
         roof = {"bound": "hbm", "kernel": "head_kernel<EPI_SPEC> (tcgen05 pred conv + decode + speculative candidate filter; exact EPI_FILTER fallback idle in the steady state)",
                 "achieved": achieved, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": traffic, "algorithmic_bytes_per_launch": alg_bytes,
+                "frac": achieved / peak, "traffic": (traffic * group if traffic else None), "algorithmic_bytes_per_launch": launch_bytes, "steps_per_launch": group,
                 "kernel_ms": head_ms, "kernel_ms_events_around_one_eager_launch": head_ms_events,
-                "kernel_ms_note": "min(events around one eager launch in a real call, step period of the pipelined timed region: one head kernel per step on the main stream)",
+                "kernel_ms_note": "min(events around one eager launch in a real call, launch period of the pipelined timed region: one head kernel per launch group on the main stream, back to back)",
                 "nms_kernel_ms": nms_ms, "path_frac": alg_bytes / (step_ms * 1e-3) / 1e9 / peak}
 
     # ---- worst case of the speculative path: EVERY frame fails its proof (thresholds learned on data scaled the other way),
     #      so the exact pair redoes the whole batch inside the call
     allfail = None
+    one = [head.session(as_windows([t.clone() for t in pool_flat[j]])) for j in range(2)]       # single-batch sessions (own input buffers) for the legs below
+    for s_ in one:
+        s_.run(); s_.run()
     if not temporal:
         hi = [(t.float() * 1.6).to(torch.bfloat16).contiguous(memory_format=torch.channels_last) for t in pool_flat[0]]
         lo = [(t.float() * 0.5).to(torch.bfloat16).contiguous(memory_format=torch.channels_last) for t in pool_flat[0]]
-        s0 = sessions[0]
+        s0 = one[0]
+        keep0 = s0.tips
         a0 = s0.stats()
         tms = []
         for i in range(6):
@@ -655,12 +690,10 @@ def main():
         a1 = s0.stats()
         allfail = {"step_ms": sorted(tms)[len(tms) // 2], "frames_redone_per_step": ((a1[0] - a0[0]) & 0xffffffff) / 6.0}
         del hi, lo
-        s0.rebind(pool_flat[0]); s0.run(); s0.run()
+        s0.rebind(keep0); s0.run(); s0.run()
 
     # ---- end to end through the public API with HOST buffers (pinned, NUMA-local), H2D + D2H inside the timed region
-    esess = sessions[:2]
-    for j, s_ in enumerate(esess):
-        s_.rebind([t.clone() for t in pool_flat[j]])          # private device input buffers for the e2e leg
+    esess = one
     host_sets = [[t.cpu().pin_memory() for t in pool_flat[j]] for j in range(4)]
     host_outs = [torch.empty((frames, 100, 6), dtype=torch.float32).pin_memory() for _ in range(2)]
     h2d = sum(t.numel() * t.element_size() for t in host_sets[0])
@@ -746,9 +779,10 @@ def main():
             "details": {"carrier": "bf16 channels-last tips, bf16 weights, fp32 accumulate/decode/NMS",
                         "nms": {"thresh": 0.45, "valid": 0.01, "topk": 400, "post": 100},
                         "l2": "inputs %.0f MB/step > 126 MB L2; pool of %d distinct resident batches, %s" % (alg_bytes / 1e6, npool, {"iid": "iid", "video": "video-like (AR(1), rho 0.95 per step)", "same": "each session replays its own batch"}[args.data]),
-                        "launch": "cuda graphs of %s steps: head kernel of batch j+1 overlapped with the top-k/NMS kernel of batch j" % "+".join(str(k) for k in sorted(set(runner.plan(args.steps)), reverse=True)),
+                        "launch": "cuda graphs of %s steps; one persistent head-kernel launch per %d steps (batches contiguous in the pool), its top-k/NMS kernel runs under the next launch's head kernel" % ("+".join(str(k) for k in sorted(set(runner.plan(args.steps)), reverse=True)), group),
+                        "warmup_steps_run": wsteps,
                         "speculation": {"thresholds_learned_on": "a different batch than the one filtered" if args.data != "same" else "the same batch (r1 behaviour)",
-                                        "frames_redone_per_step": redone / max(calls, 1), "steps_counted": calls,
+                                        "frames_redone_per_step": redone / max(calls * group, 1), "steps_counted": calls * group,
                                         "all_frames_fail_worst_case": allfail},
                         "sharding": ("%s split by rank; gather = %s" % ("clips" if temporal else "frames", gather_kind)) if world > 1 else "single GPU",
                         "gather_verified": gather_verified, "numa_pinned": numa},
@@ -757,7 +791,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": unit, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps, "h2d_only_gbs_per_rank": h2d * e2e_steps / (copy_ms * 1e-3) / 1e9,
                     "note": "pinned host bf16 NHWC tips (4 host batches, NUMA-local) -> H2D (copy stream, double-buffered under the previous step's compute) -> fused head -> D2H of (frames,100,6); PCIe-bound: h2d_only_gbs_per_rank is the same traffic with no compute"},
-            "gpu_launches": args.steps * sessions[0].launches,
+            "gpu_launches": (args.steps // group) * sessions[0].launches,
             "clocks": clocks,
         }
         os.write(json_fd, (json.dumps(line) + "\n").encode())

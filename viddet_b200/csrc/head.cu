@@ -74,7 +74,7 @@ struct HeadKernelParams {
     HeadGeom g;
     int frames, K_frames;
     int split;                           // fp32-parity modes: operand planes in memory (0: off; 3: hi/mid/lo; 2: hi/lo); K_frames = number of plane products
-    signed char a_pl[8], w_pl[8];        // plane of A / of W that product kf of the K loop multiplies
+    signed char a_pl[8], w_pl[8];        // plane of A / of W that product kf of the K loop multiplies (smallest products first, p0 w0 last)
     int cin[VD_MAX_SCALES];
     int pb[VD_MAX_SCALES];               // pixel blocks per frame
     int tile_start[VD_MAX_SCALES + 1];   // cumulative tile index per processing slot
@@ -82,6 +82,9 @@ struct HeadKernelParams {
     int tif_base[VD_MAX_SCALES];         // tile-in-frame index of the scale's first pixel block
     int tiles_per_frame, total_tiles, n_pad;
     int n_valid;                         // prediction channels actually present (<= n_pad)
+    // class windows (any num_class on the compiled shapes): this launch covers classes [c_off, c_off + c_valid) of c_total; the
+    // kernel's own class index c (0 .. C-1 of its template shape) is class c_off + c of the head; c >= c_valid are padding
+    int c_off, c_valid, n_pass, pass;
     const float* bias[VD_MAX_SCALES];
     // EPI_FILTER
     float4* boxes; uint64_t* lists; uint32_t* counts; float valid_thresh; int k, cap;
@@ -279,7 +282,7 @@ head_kernel(const __grid_constant__ HeadMaps maps, const __grid_constant__ HeadK
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < p.g.num_scales; ++s) { tc::prefetch_tmap(&maps.a[s]); tc::prefetch_tmap(&maps.w[s]); }
     }
-    if (warp == 1) tc::tmem_alloc<Cfg::TMEM_COLS>(&sh->tmem_base);
+    if (warp == 1) { if (p.split) tc::tmem_alloc<512>(&sh->tmem_base); else tc::tmem_alloc<Cfg::TMEM_COLS>(&sh->tmem_base); }   // parity modes: all of TMEM for partial accumulators
     tc::fence_before_sync();
     if constexpr (kEarly) {
         if (warp == 0) { __syncwarp(); asm volatile("bar.arrive 1, %0;" ::"n"(Cfg::THREADS) : "memory"); }
@@ -351,6 +354,35 @@ head_kernel(const __grid_constant__ HeadMaps maps, const __grid_constant__ HeadK
                 tc::fence_after_sync();
                 if (p.stamps && blockIdx.x == 0 && it < 250u) p.stamps[it * 16 + 1] = clock64();
                 const uint32_t d_tmem = tmem_base + buf * Cfg::TMEM_STRIDE;
+                if (p.split) {
+                    // fp32-parity modes: partial accumulators (see split_products): 0 = all low-order products, 1.. = K-ranges of p0 w0;
+                    // the tile owns every TMEM buffer, so it starts only when the previous tile's epilogue has drained (tiles serialise;
+                    // the operand ring keeps streaming meanwhile)
+                    if (it > 0u) { const uint32_t j = it - 1u; tc::mbar_wait(&sh->tmem_empty[j % (uint32_t)G], (j / (uint32_t)G) & 1u); tc::fence_after_sync(); }
+                    constexpr int NB = 512 / Cfg::TMEM_STRIDE;
+                    const int kbpf = p.cin[s] / BLOCK_K;
+                    const int parts = (NB - 1) < kbpf ? (NB - 1) : kbpf;
+                    uint32_t used = 0u;
+                    int kf = 0, kbi = 0;
+                    for (int kb = 0; kb < nkb; ++kb) {
+                        const int acc = (kf + 1 < p.K_frames) ? 0 : 1 + (kbi * parts) / kbpf;
+                        const uint32_t d_acc = tmem_base + (uint32_t)acc * Cfg::TMEM_STRIDE;
+                        tc::mbar_wait(&sh->full[stage], phase);
+                        tc::fence_after_sync();
+                        const uint32_t a_addr = tc::smem_u32(ring + stage * Cfg::STAGE_BYTES);
+                        const uint64_t da = tc::make_smem_desc_sw128(a_addr);
+                        const uint64_t db = tc::make_smem_desc_sw128(a_addr + A_TILE_BYTES);
+#pragma unroll
+                        for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+                            tc::umma_bf16(d_acc, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (uint32_t)(k != 0 || ((used >> acc) & 1u)));
+                        used |= 1u << acc;
+                        tc::umma_commit(&sh->empty[stage]);
+                        if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
+                        if (++kbi == kbpf) { kbi = 0; ++kf; }
+                    }
+                    tc::umma_commit(&sh->tmem_full[buf]);
+                    continue;
+                }
                 for (int kb = 0; kb < nkb; ++kb) {
                     tc::mbar_wait(&sh->full[stage], phase);
                     tc::fence_after_sync();
@@ -441,6 +473,35 @@ head_kernel(const __grid_constant__ HeadMaps maps, const __grid_constant__ HeadK
             if constexpr (EPI == EPI_SPEC) spec_flush();
             if (stamp) p.stamps[it * 16 + 4] = clock64();
             const uint32_t tbase = tmem_base + buf * Cfg::TMEM_STRIDE + lane_addr;
+            if (p.split) {
+                // fp32-parity modes: fold the partial accumulators into this tile's buffer, fp32 round-to-nearest adds (K-ranges of
+                // p0 w0 first, the low-order products last), then run the ordinary epilogue on the sum.  A thread touches only its own
+                // TMEM lane; with SPLIT warpgroups on one buffer each folds every SPLIT-th 16-column chunk, then they meet.
+                constexpr int NB = 512 / Cfg::TMEM_STRIDE;
+                const int kbpf = p.cin[s] / BLOCK_K;
+                const int parts = (NB - 1) < kbpf ? (NB - 1) : kbpf;
+                const uint32_t t0 = tmem_base + lane_addr;
+#pragma unroll 1
+                for (int c0 = 0; c0 < NPAD; c0 += 16) {
+                    if (Cfg::SPLIT > 1 && ((c0 >> 4) % Cfg::SPLIT) != half) continue;
+                    uint32_t acc[16], r[16];
+                    tc::tmem_ld16(t0 + (uint32_t)(Cfg::TMEM_STRIDE + c0), acc); tc::tmem_ld_wait();
+                    for (int j = 2; j <= parts; ++j) {
+                        tc::tmem_ld16(t0 + (uint32_t)(j * Cfg::TMEM_STRIDE + c0), r); tc::tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) acc[i] = __float_as_uint(__fadd_rn(__uint_as_float(acc[i]), __uint_as_float(r[i])));
+                    }
+                    tc::tmem_ld16(t0 + (uint32_t)c0, r); tc::tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) acc[i] = __float_as_uint(__fadd_rn(__uint_as_float(acc[i]), __uint_as_float(r[i])));
+                    tc::tmem_st16(tbase + (uint32_t)c0, acc);
+                }
+                tc::tmem_st_wait();
+                if constexpr (Cfg::SPLIT > 1) {
+                    if (grp == 0) asm volatile("bar.sync 5, %0;" ::"n"(Cfg::SPLIT * kEpiThreads) : "memory");
+                    else asm volatile("bar.sync 6, %0;" ::"n"(Cfg::SPLIT * kEpiThreads) : "memory");
+                }
+            }
 
             if constexpr (EPI == EPI_FILTER || EPI == EPI_SPEC) {
                 if (p.dbg == 1) {        // debug (VD_DEBUG_SKIP_EPILOGUE=1): mainloop only, accumulators dropped
@@ -486,7 +547,7 @@ head_kernel(const __grid_constant__ HeadMaps maps, const __grid_constant__ HeadK
                     // the raw (tx,ty,tw,th) are stored; only the <= topk boxes that reach the NMS kernel are decoded there
                     // (same vd_decode_box, same bits) instead of all 3*HW of them here
                     if (!inb) conf[a] = __uint_as_float(0x7fc00000u);   // NaN: no score of a padding pixel passes `> valid_thresh`
-                    if (inb && half == 0 && p.dbg != 8) p.boxes[(size_t)f * p.g.anc_base[p.g.num_scales] + p.g.anc_base[s] + cell * 3 + a] = make_float4(tx, ty, tw, th);
+                    if (inb && half == 0 && p.pass == 0 && p.dbg != 8) p.boxes[(size_t)f * p.g.anc_base[p.g.num_scales] + p.g.anc_base[s] + cell * 3 + a] = make_float4(tx, ty, tw, th);
                     (void)bx; (void)gx; (void)gy;
                 } else {   // EPI_DET: class rows of this (cell, anchor)
                     bx = vd_decode_box(tx, ty, tw, th, gx, gy, p.g.stride[s], p.g.anchors[s][2 * a], p.g.anchors[s][2 * a + 1]);
@@ -502,10 +563,10 @@ head_kernel(const __grid_constant__ HeadMaps maps, const __grid_constant__ HeadK
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
                             const int c = c0 + i;
-                            if (c < C && inb) {
+                            if (c < C && c < p.c_valid && inb) {
                                 float sc = vd_score(__uint_as_float(rc[i]) + bias[a * P + 5 + c], conf[a]);
-                                float2* o = reinterpret_cast<float2*>(drow + (size_t)c * rows_scale * 6);
-                                o[0] = make_float2(__fadd_rn(__fmul_rn(sc, 0.0f), (float)c), sc);
+                                float2* o = reinterpret_cast<float2*>(drow + (size_t)(p.c_off + c) * rows_scale * 6);
+                                o[0] = make_float2(__fadd_rn(__fmul_rn(sc, 0.0f), (float)(p.c_off + c)), sc);
                                 o[1] = make_float2(bx.x1, bx.y1);
                                 o[2] = make_float2(bx.x2, bx.y2);
                             }
@@ -546,7 +607,8 @@ head_kernel(const __grid_constant__ HeadMaps maps, const __grid_constant__ HeadK
                     }
                 }
                 const uint32_t HW3 = (uint32_t)HW * 3u;
-                const uint32_t row0 = (uint32_t)p.g.row_base[s] + (uint32_t)cell * 3u;       // + c*HW3 + a
+                const uint32_t row0 = (uint32_t)p.g.row_base[s] + (uint32_t)cell * 3u + (uint32_t)p.c_off * HW3;       // + c*HW3 + a
+                const int cval = p.c_valid;
                 uint64_t* fl = p.spec_lists + (size_t)f * kSpecCap;
                 uint32_t* fc = p.spec_cnt + f;
                 // Passers are staged per WARP in shared memory (no group barrier anywhere in this epilogue).  The warp's
@@ -563,7 +625,7 @@ head_kernel(const __grid_constant__ HeadMaps maps, const __grid_constant__ HeadK
                 auto emit_chunk = [&](const float* bv, const int n, const int a, const int cc, const float la, const float ca) {
 #pragma unroll
                     for (int i = 0; i < CH; ++i) {
-                        if (i < n && bv[i] >= la) {
+                        if (i < n && bv[i] >= la && cc * CH + i < cval) {
                             const float sc = vd_score(bv[i], ca);
                             if (sc > vth) {
                                 const uint32_t kh = __float_as_uint(sc) | 0x80000000u;
@@ -788,7 +850,7 @@ head_kernel(const __grid_constant__ HeadMaps maps, const __grid_constant__ HeadK
                                 const int c = c0 + i;
                                 if (c < C) {
                                     const float sc = vd_score(__fadd_rn(__uint_as_float(rc[i]), bias[a * P + 5 + c]), ca);
-                                    const uint32_t kh = (sc > vth) ? (__float_as_uint(sc) | 0x80000000u) : 0u;
+                                    const uint32_t kh = (sc > vth && c < p.c_valid) ? (__float_as_uint(sc) | 0x80000000u) : 0u;
                                     const uint64_t key = ((uint64_t)kh << 32) | (uint32_t)~(lcode | (((uint32_t)c) << 9) | (uint32_t)a);
                                     if (kh && key >= piv) {
                                         ++cnt;
@@ -817,10 +879,10 @@ head_kernel(const __grid_constant__ HeadMaps maps, const __grid_constant__ HeadK
                     if (lane == 0) tc::mbar_arrive(&sh->tmem_empty[buf]);
                 };
                 // global tile list + histogram
-                const size_t li = (size_t)f * p.tiles_per_frame + p.tif_base[s] + pblk;
+                const size_t li = ((size_t)f * p.n_pass + p.pass) * p.tiles_per_frame + p.tif_base[s] + pblk;
                 uint64_t* gl = p.lists + li * kListCap;
                 const uint32_t HW3 = (uint32_t)HW * 3u;
-                const uint32_t rbase = (uint32_t)p.g.row_base[s] + (uint32_t)(pblk * BLOCK_M) * 3u;
+                const uint32_t rbase = (uint32_t)p.g.row_base[s] + (uint32_t)(pblk * BLOCK_M) * 3u + (uint32_t)p.c_off * HW3;
                 auto flush_one = [&](const uint32_t j, const uint64_t v) {     // v: (key_hi, ~local code) or 0
                     uint64_t o = 0ull;
                     if (v != 0ull) {
@@ -877,7 +939,7 @@ head_kernel(const __grid_constant__ HeadMaps maps, const __grid_constant__ HeadK
                                         const uint64_t e = L[j];
                                         const uint32_t code = (uint32_t)e;
                                         const float sc = vd_score(__uint_as_float((uint32_t)(e >> 32)), cf[((code >> 2) & 127u) * 3u + (code & 3u)]);
-                                        kh = (sc > vth) ? (__float_as_uint(sc) | 0x80000000u) : 0u;
+                                        kh = (sc > vth && (int)(code >> 9) < p.c_valid) ? (__float_as_uint(sc) | 0x80000000u) : 0u;
                                         key[u] = kh ? (((uint64_t)kh << 32) | (uint32_t)~code) : 0ull;
                                         ne += (kh >= ph) ? 1u : 0u;
                                     }
@@ -986,7 +1048,7 @@ head_kernel(const __grid_constant__ HeadMaps maps, const __grid_constant__ HeadK
     tc::fence_before_sync();
     __syncthreads();
     if ((EPI == EPI_FILTER || EPI == EPI_SPEC) && p.stamps && p.frame_list == nullptr && threadIdx.x == 0) p.stamps[4096 + blockIdx.x * 4 + 2] = gtime();
-    if (warp == 1) tc::tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+    if (warp == 1) { if (p.split) tc::tmem_dealloc<512>(tmem_base); else tc::tmem_dealloc<Cfg::TMEM_COLS>(tmem_base); }
     if (threadIdx.x == 0 && p.tile_counter != nullptr && p.tile_counter[2] == p.ws_magic) {
         // last CTA out re-arms the scheduler for the next launch on this workspace
         __threadfence();
@@ -1052,6 +1114,7 @@ struct FusedSink {
 //       straight to the output and appended to the kept list
 // Semantics = nms_core.cuh::nms_tail (rank order, IoU > thresh, same class, first max_out survivors), same IoU arithmetic.
 constexpr int kNmsThreads = 256;
+constexpr int kMaxFrameLists = 512;          // per-tile candidate lists of one frame the exact NMS kernel can walk (pixel blocks x class windows)
 struct WaveShared { uint32_t kept_total; uint32_t sup; uint32_t diag[32]; };
 template <class Source, class Sink>
 __device__ void nms_tail_wave(const int n, const int f, const NmsParams P, const Source& src, const Sink& sink,
@@ -1177,8 +1240,8 @@ nms_final_hist_kernel(const uint64_t* __restrict__ lists, const uint32_t* __rest
     int* skcls = reinterpret_cast<int*>(skarea + KMAX);
     int* scls = skcls + KMAX;
     float* sarea = reinterpret_cast<float*>(scls + k);
-    uint32_t* scount = reinterpret_cast<uint32_t*>(sarea + k);         // [2][256] list lengths to stream / full lengths
-    WaveShared* wsh = reinterpret_cast<WaveShared*>(scount + 512);
+    uint32_t* scount = reinterpret_cast<uint32_t*>(sarea + k);         // [2][kMaxFrameLists] list lengths to stream / full lengths
+    WaveShared* wsh = reinterpret_cast<WaveShared*>(scount + 2 * kMaxFrameLists);
     lists += (size_t)f * n_lists * kListCap; counts += (size_t)f * n_lists; counts_hi += (size_t)f * n_lists; hist += (size_t)f * kHistBins;
 
     VD_STAMP(P, 0);
@@ -1244,7 +1307,7 @@ nms_final_hist_kernel(const uint64_t* __restrict__ lists, const uint32_t* __rest
         uint32_t n = counts[l]; n = n > (uint32_t)kListCap ? (uint32_t)kListCap : n;
         uint32_t nh = counts_hi[l]; nh = nh > n ? n : nh;
         scount[l] = fronts_only ? nh : n;
-        if (fronts_only) scount[256 + l] = n;
+        if (fronts_only) scount[kMaxFrameLists + l] = n;
     }
     if (tid == 0) hint_hi[f] = hist_edge(bstar > 16u ? bstar - 16u : 0u);
     int sit = 0;
@@ -1294,7 +1357,7 @@ nms_final_hist_kernel(const uint64_t* __restrict__ lists, const uint32_t* __rest
         m = scr->out_count;
         // a clean histogram guarantees m >= k whenever a positive pivot was chosen; otherwise redo exactly
         if (m >= (uint32_t)k || piv <= 1ull || attempt == 1) break;
-        if (fronts_only) { for (int l = tid; l < n_lists; l += blockDim.x) scount[l] = scount[256 + l]; }   // the exact retry reads whole lists
+        if (fronts_only) { for (int l = tid; l < n_lists; l += blockDim.x) scount[l] = scount[kMaxFrameLists + l]; }   // the exact retry reads whole lists
     }
     VD_STAMP(P, 2);
     m = m > (uint32_t)kHistCap ? (uint32_t)kHistCap : m;
@@ -1412,7 +1475,7 @@ static size_t nms_spec_smem(int k, int max_out) {
 }
 static size_t nms_hist_smem(int k, int max_out) {
     const size_t kmax = (size_t)(max_out < k ? max_out : k) + 32 + 4 * (kNmsThreads / 32);
-    return 256 + (size_t)kHistCap * 8 + (size_t)k * 16 + kmax * 24 + (size_t)k * 8 + 512 * 4 + sizeof(WaveShared) + 64;
+    return 256 + (size_t)kHistCap * 8 + (size_t)k * 16 + kmax * 24 + (size_t)k * 8 + 2 * kMaxFrameLists * 4 + sizeof(WaveShared) + 64;
 }
 
 // no-NMS tail (yolo3.py:525 false): rows are the plain concat; only reachable through vd_head_detections.
@@ -1422,22 +1485,32 @@ static size_t nms_hist_smem(int k, int max_out) {
 // ----------------------------------------------------------------------------------------------
 struct HeadPlan {
     HeadKernelParams kp;
-    int n_pad, C;
+    int n_pad, C;                  // C: class count of the compiled kernel shape that runs (== num_class when that is compiled)
+    int C_total, n_pass;           // the head's num_class; class windows of C classes each
+    bool repack;                   // weights / biases are re-laid out per window into the workspace (off_wrepack)
+    size_t off_wrepack, wrepack_bytes, wrepack_w_bytes[VD_MAX_SCALES], wrepack_stride[VD_MAX_SCALES];
     int merge_levels;
     size_t off_hints, off_ctr, off_hist, off_boxes, off_lists0, off_counts0, off_counts_hi, off_hint_hi, off_coarse, off_spec_lists, off_spec_cnt, off_spec_state, off_spec_tau, off_failed, off_listsA, off_listsB, off_countsA, off_countsB, total;
 };
 
 static int head_npad(int C) { int n = 3 * (5 + C); return (n + 15) / 16 * 16; }
 
-// Plane products of the fp32-parity modes, largest terms first.  v = p0 + p1 (+ p2) with |p1| <= 2^-9 |v|, |p2| <= 2^-18 |v|.
-//   3 planes (VD_PREC_FP32_SPLIT):  p0 w0 + p1 w0 + p0 w1 + p1 w1 + p2 w0 + p0 w2   (dropped terms <= 2^-27 relative)
-//   2 planes (VD_PREC_BF16X2):      p0 w0 + p1 w0 + p0 w1                           (dropped / residual terms ~ 2^-18 relative)
+// Plane products of the fp32-parity modes.  v = p0 + p1 (+ p2) with |p1| <= 2^-9 |v|, |p2| <= 2^-18 |v|.
+//   3 planes (VD_PREC_FP32_SPLIT):  p0 w2 + p2 w0 + p1 w1 + p0 w1 + p1 w0 + p0 w0   (dropped terms <= 2^-27 relative)
+//   2 planes (VD_PREC_BF16X2):      p0 w1 + p1 w0 + p0 w0                           (dropped / residual terms ~ 2^-18 relative)
+// The tensor core's fp32 accumulator truncates on every accumulate (measured: the error of a K-term bf16 dot product grows
+// LINEARLY, ~2.3e-8 of max|y| per MMA, tests/test_gpu_head.py prints it).  So in these modes (a) the low-order products are
+// summed in their own accumulator (their truncation errors scale with their own 2^-9 / 2^-18 magnitude), (b) the p0 w0 chain
+// is cut into up to 3 K-ranges with separate accumulators, and (c) the epilogue adds the partial accumulators in fp32
+// round-to-nearest before decoding (fold, see head_kernel).  The last product listed here is p0 w0.
 static int split_products(int precision, HeadKernelParams* k) {
-    static const signed char a3[6] = {0, 1, 0, 1, 2, 0}, w3[6] = {0, 0, 1, 1, 0, 2};
-    const int n = precision == VD_PREC_FP32_SPLIT ? 6 : 3;
-    k->split = precision == VD_PREC_FP32_SPLIT ? 3 : 2;
+    static const signed char a3[6] = {0, 2, 1, 0, 1, 0}, w3[6] = {2, 0, 1, 1, 0, 0};
+    static const signed char a2[3] = {0, 1, 0}, w2[3] = {1, 0, 0};
+    const bool three = precision == VD_PREC_FP32_SPLIT;
+    const int n = three ? 6 : 3;
+    k->split = three ? 3 : 2;
     k->K_frames = n;
-    for (int i = 0; i < 8; ++i) { k->a_pl[i] = i < n ? a3[i] : 0; k->w_pl[i] = i < n ? w3[i] : 0; }
+    for (int i = 0; i < 8; ++i) { k->a_pl[i] = i < n ? (three ? a3[i] : a2[i]) : 0; k->w_pl[i] = i < n ? (three ? w3[i] : w2[i]) : 0; }
     return n;
 }
 
@@ -1446,14 +1519,25 @@ static int make_plan(const VdHeadParams* hp, HeadPlan* pl) {
     VD_CHECK_ARG(hp->num_scales >= 1 && hp->num_scales <= VD_MAX_SCALES, "head: num_scales %d", hp->num_scales);
     VD_CHECK_ARG(hp->num_class >= 1, "head: num_class %d", hp->num_class);
     VD_CHECK_ARG(hp->frames >= 0 && hp->frames <= 65535, "head: frames %d out of range", hp->frames);
-    const int C = hp->num_class;
+    // Any num_class runs on the compiled kernel shapes (C in 1-5, 20, 30, 80): a class count in between is padded up to the next
+    // shape, a larger one is cut into windows of 80 classes (one head-kernel launch per window, all appending to the same
+    // per-frame candidate lists).  The prediction weights / biases of a window are re-laid out into the workspace first
+    // (repack_pred_weights_kernel): box + objectness rows of each anchor, then the window's class rows, padding rows zero.
+    const int C_total = hp->num_class;
+    int C = C_total, n_pass = 1;
+    bool repack = false;
+    if (!(C_total <= 5 || C_total == 20 || C_total == 30 || C_total == 80)) {
+        repack = true;
+        C = C_total < 20 ? 20 : (C_total < 30 ? 30 : 80);
+        n_pass = ceil_div(C_total, C);
+    }
     const int npad = head_npad(C);
-    if (npad > 256) return set_error(VD_ERR_UNSUPPORTED, "head: 3*(5+%d) = %d prediction channels > 256 not supported by the fused kernel yet", C, 3 * (5 + C));
     memset(pl, 0, sizeof(*pl));
     HeadKernelParams& k = pl->kp;
-    pl->n_pad = npad; pl->C = C;
-    k.g.num_scales = hp->num_scales; k.g.num_class = C; k.g.A = 3;
+    pl->n_pad = npad; pl->C = C; pl->C_total = C_total; pl->n_pass = n_pass; pl->repack = repack;
+    k.g.num_scales = hp->num_scales; k.g.num_class = C_total; k.g.A = 3;
     k.frames = hp->frames; k.n_pad = npad; k.n_valid = 3 * (5 + C);
+    k.c_off = 0; k.c_valid = C_total < C ? C_total : C; k.n_pass = n_pass; k.pass = 0;
     const int join = hp->join;
     VD_CHECK_ARG(join == VD_JOIN_NONE || join == VD_JOIN_CAT, "head: join %d must be pre-reduced (use vd_temporal_pool for max/mean)", join);
     VD_CHECK_ARG(hp->precision == VD_PREC_BF16 || hp->precision == VD_PREC_FP32_SPLIT || hp->precision == VD_PREC_BF16X2, "head: precision %d", hp->precision);
@@ -1476,7 +1560,7 @@ static int make_plan(const VdHeadParams* hp, HeadPlan* pl) {
         k.g.stride[s] = sc.stride;
         for (int i = 0; i < 6; ++i) k.g.anchors[s][i] = sc.anchors[i];
         k.g.row_base[s] = rows; k.g.anc_base[s] = anc;
-        rows += C * k.g.HW[s] * 3; anc += k.g.HW[s] * 3;
+        rows += C_total * k.g.HW[s] * 3; anc += k.g.HW[s] * 3;
         k.cin[s] = sc.Cin; k.bias[s] = sc.bias;
         k.pb[s] = ceil_div(k.g.HW[s], BLOCK_M);
         k.tif_base[s] = tif; tif += k.pb[s];
@@ -1491,7 +1575,7 @@ static int make_plan(const VdHeadParams* hp, HeadPlan* pl) {
     for (int j = hp->num_scales; j < VD_MAX_SCALES; ++j) k.order[j] = 0;
     for (int s = hp->num_scales; s <= VD_MAX_SCALES; ++s) { k.g.row_base[s] = rows; k.g.anc_base[s] = anc; k.tile_start[s] = tiles; }
     k.tiles_per_frame = tif; k.total_tiles = tiles;
-    if (tif > 256) return set_error(VD_ERR_UNSUPPORTED, "head: %d pixel blocks per frame > 256", tif);
+    if (tif * n_pass > kMaxFrameLists) return set_error(VD_ERR_UNSUPPORTED, "head: %d pixel blocks x %d class windows per frame > %d", tif, n_pass, kMaxFrameLists);
     // workspace
     size_t off = 0;
     const size_t F = (size_t)(hp->frames > 0 ? hp->frames : 1);
@@ -1499,9 +1583,9 @@ static int make_plan(const VdHeadParams* hp, HeadPlan* pl) {
     pl->off_ctr = off; off += 256;                      // dynamic tile counter; zeroed together with the histogram that follows it
     pl->off_hist = off; off += align_up(F * kHistBins * 4, 256);
     pl->off_boxes = off; off += align_up(F * anc * 16, 256);
-    pl->off_lists0 = off; off += align_up(F * tif * kListCap * 8, 256);
-    pl->off_counts0 = off; off += align_up(F * tif * 4, 256);
-    pl->off_counts_hi = off; off += align_up(F * tif * 4, 256);
+    pl->off_lists0 = off; off += align_up(F * tif * n_pass * kListCap * 8, 256);
+    pl->off_counts0 = off; off += align_up(F * tif * n_pass * 4, 256);
+    pl->off_counts_hi = off; off += align_up(F * tif * n_pass * 4, 256);
     pl->off_hint_hi = off; off += align_up(F * 4, 256);
     pl->off_coarse = off; off += align_up(F * 64 * 4, 256);
     pl->off_spec_lists = off; off += align_up(F * kSpecCap * 8, 256);
@@ -1514,11 +1598,74 @@ static int make_plan(const VdHeadParams* hp, HeadPlan* pl) {
     pl->off_listsB = off; off += align_up(F * n1 * kListCap * 8, 256);
     pl->off_countsA = off; off += align_up(F * n1 * 4, 256);
     pl->off_countsB = off; off += align_up(F * n1 * 4, 256);
+    pl->off_wrepack = off;
+    if (repack) {
+        const int planes = hp->precision == VD_PREC_FP32_SPLIT ? 3 : (hp->precision == VD_PREC_BF16X2 ? 2 : 1);
+        for (int s = 0; s < hp->num_scales; ++s) {
+            const size_t row_elems = (size_t)hp->scale[s].Cin * (planes > 1 ? planes : k.K_frames);
+            pl->wrepack_w_bytes[s] = align_up((size_t)npad * row_elems * 2, 256);
+            pl->wrepack_stride[s] = pl->wrepack_w_bytes[s] + align_up((size_t)npad * 4, 256);     // weights then biases of one window
+            off += pl->wrepack_stride[s] * n_pass;
+        }
+    }
+    pl->wrepack_bytes = off - pl->off_wrepack;
     pl->total = off;
     return VD_OK;
 }
 
-static int make_maps(const VdHeadParams* hp, const HeadPlan& pl, HeadMaps* maps) {
+// Weights / biases of class window `pass` in the layout of the compiled shape (C_T classes): row a*(5+C_T)+p <- source row
+// a*(5+C_total)+p for the box / objectness part (p < 5), a*(5+C_total)+5+c_off+(p-5) for the window's classes; padding rows zero.
+__global__ void __launch_bounds__(256)
+repack_pred_weights_kernel(const uint4* __restrict__ w, const float* __restrict__ bias, uint4* __restrict__ w_out, float* __restrict__ b_out,
+                           int C_total, int C_T, int c_off, int npad, int row_vec /* 16-byte vectors per row */) {
+    const int n = blockIdx.x;                  // output row
+    const int P_T = 5 + C_T, P_S = 5 + C_total;
+    const int a = n / P_T, pp = n - a * P_T;
+    int src = -1;
+    if (a < 3) {
+        if (pp < 5) src = a * P_S + pp;
+        else { const int c = c_off + pp - 5; if (c < C_total) src = a * P_S + 5 + c; }
+    }
+    for (int j = threadIdx.x; j < row_vec; j += blockDim.x)
+        w_out[(size_t)n * row_vec + j] = src >= 0 ? w[(size_t)src * row_vec + j] : make_uint4(0u, 0u, 0u, 0u);
+    if (threadIdx.x == 0) b_out[n] = (src >= 0 && bias) ? bias[src] : 0.0f;
+    (void)npad;
+}
+
+// Runs the repack for every (scale, window) and returns, through wptr / bptr, where window `pass` of scale s lives.
+static int repack_windows(const VdHeadParams* hp, const HeadPlan& pl, unsigned char* ws, cudaStream_t stream) {
+    if (!pl.repack) return VD_OK;
+    size_t off = pl.off_wrepack;
+    const int planes = hp->precision == VD_PREC_FP32_SPLIT ? 3 : (hp->precision == VD_PREC_BF16X2 ? 2 : 1);
+    for (int s = 0; s < hp->num_scales; ++s) {
+        const VdHeadScale& sc = hp->scale[s];
+        const size_t row_elems = (size_t)sc.Cin * (planes > 1 ? planes : pl.kp.K_frames);
+        for (int ps = 0; ps < pl.n_pass; ++ps) {
+            unsigned char* base = ws + off + (size_t)ps * pl.wrepack_stride[s];
+            repack_pred_weights_kernel<<<pl.n_pad, 256, 0, stream>>>((const uint4*)sc.weight_bf16, sc.bias, (uint4*)base, (float*)(base + pl.wrepack_w_bytes[s]),
+                                                                      pl.C_total, pl.C, ps * pl.C, pl.n_pad, (int)(row_elems / 8));
+            VD_LAUNCH_CHECK();
+        }
+        off += pl.wrepack_stride[s] * pl.n_pass;
+    }
+    return VD_OK;
+}
+// Kernel parameters / weight pointers of class window `pass`.
+static void window_params(const VdHeadParams* hp, const HeadPlan& pl, unsigned char* ws, int pass, HeadKernelParams* kp, const void* wptr[VD_MAX_SCALES]) {
+    kp->pass = pass; kp->n_pass = pl.n_pass; kp->c_off = pass * pl.C;
+    const int left = pl.C_total - kp->c_off;
+    kp->c_valid = left < pl.C ? left : pl.C;
+    size_t off = pl.off_wrepack;
+    for (int s = 0; s < hp->num_scales; ++s) {
+        if (pl.repack) {
+            unsigned char* base = ws + off + (size_t)pass * pl.wrepack_stride[s];
+            wptr[s] = base; kp->bias[s] = (const float*)(base + pl.wrepack_w_bytes[s]);
+            off += pl.wrepack_stride[s] * pl.n_pass;
+        } else { wptr[s] = hp->scale[s].weight_bf16; kp->bias[s] = hp->scale[s].bias; }
+    }
+}
+
+static int make_maps(const VdHeadParams* hp, const HeadPlan& pl, HeadMaps* maps, const void* const* wptr = nullptr) {
     for (int s = 0; s < hp->num_scales; ++s) {
         const VdHeadScale& sc = hp->scale[s];
         const uint64_t HW = (uint64_t)sc.H * sc.W, Cin = sc.Cin, K = pl.kp.split ? pl.kp.split : pl.kp.K_frames;
@@ -1533,7 +1680,7 @@ static int make_maps(const VdHeadParams* hp, const HeadPlan& pl, HeadMaps* maps)
         uint64_t dimsW[2] = {Cin * K, (uint64_t)3 * (5 + pl.C)};
         uint64_t strW[1] = {Cin * K * 2};
         uint32_t boxW[2] = {BLOCK_K, (uint32_t)pl.n_pad};
-        rc = encode_tmap_bf16(&maps->w[s], sc.weight_bf16, 2, dimsW, strW, boxW);
+        rc = encode_tmap_bf16(&maps->w[s], wptr ? wptr[s] : sc.weight_bf16, 2, dimsW, strW, boxW);
         if (rc) return rc;
     }
     return VD_OK;
@@ -1575,8 +1722,7 @@ static int launch_head(const HeadMaps& maps, const HeadKernelParams& kp, int C, 
         case 5:  return launch_head_t<EPI, 5, 32>(maps, kp, stream);
         default: break;
     }
-    return set_error(VD_ERR_UNSUPPORTED, "head: num_class %d has no compiled fused instantiation (have 1-5, 20, 30, 80); "
-                     "use vd_pred_conv + vd_yolo_decode + vd_box_nms", C);
+    return set_error(VD_ERR_UNSUPPORTED, "head: internal error, no kernel shape for %d classes", C);
 }
 
 // EPI_PRED only depends on the padded width
@@ -1626,8 +1772,9 @@ extern "C" size_t vd_head_stats_offset(const VdHeadParams* hp) {
 extern "C" int vd_head_launch_count(const VdHeadParams* hp) {
     HeadPlan pl;
     if (make_plan(hp, &pl) != VD_OK) return -1;
-    int n = getenv("VD_NO_SPEC") ? 2 : 4;                         // head kernel + per-frame NMS kernel (+ the exact fallback pair, idle in the steady state)
+    int n = getenv("VD_NO_SPEC") ? 1 + pl.n_pass : 2 + 2 * pl.n_pass;   // head kernel per class window + per-frame NMS kernel (+ the exact fallback pair, idle in the steady state)
     for (int s = 0; s < hp->num_scales; ++s) if (hp->scale[s].tconv_weight_bf16) ++n;
+    if (pl.repack) n += hp->num_scales * pl.n_pass;               // weight re-layout per (scale, window)
     return n;
 }
 
@@ -1687,14 +1834,20 @@ extern "C" int vd_head_forward_stages(const VdHeadParams* hp, float* ids, float*
             if (rc) return rc;
         }
     }
+    const void* wptr[VD_MAX_SCALES];
     HeadMaps maps;
-    rc = make_maps(hp, pl, &maps);
-    if (rc) return rc;
     if (stage_mask & VD_STAGE_HEAD) {
         // no memset: the previous call's NMS kernels left the counters / histograms zeroed (layout marker); a workspace in
         // any other state is detected on the device and handled exactly
-        rc = spec ? launch_head<EPI_SPEC>(maps, kp, pl.C, stream) : launch_head<EPI_FILTER>(maps, kp, pl.C, stream);
+        rc = repack_windows(hp, pl, ws, stream);
         if (rc) return rc;
+        for (int ps = 0; ps < pl.n_pass; ++ps) {       // one launch per class window (1 unless num_class > 80), all appending to the frames' lists
+            window_params(hp, pl, ws, ps, &kp, wptr);
+            rc = make_maps(hp, pl, &maps, wptr);
+            if (rc) return rc;
+            rc = spec ? launch_head<EPI_SPEC>(maps, kp, pl.C, stream) : launch_head<EPI_FILTER>(maps, kp, pl.C, stream);
+            if (rc) return rc;
+        }
     }
     if (!(stage_mask & VD_STAGE_NMS)) return VD_OK;
 
@@ -1720,7 +1873,7 @@ extern "C" int vd_head_forward_stages(const VdHeadParams* hp, float* ids, float*
     }
     if (!spec) {
         nms_final_hist_kernel<<<hp->frames, kNmsThreads, nms_hist_smem(k, hp->post_nms), stream>>>(
-            kp.lists, kp.counts, kp.counts_hi, kp.hint_hi, kp.coarse, kp.tiles_per_frame, kp.hist, kp.tile_counter, kp.ws_magic,
+            kp.lists, kp.counts, kp.counts_hi, kp.hint_hi, kp.coarse, kp.tiles_per_frame * pl.n_pass, kp.hist, kp.tile_counter, kp.ws_magic,
             nullptr, nullptr, nullptr, P, src, sink);
         VD_LAUNCH_CHECK();
         return VD_OK;
@@ -1730,13 +1883,18 @@ extern "C" int vd_head_forward_stages(const VdHeadParams* hp, float* ids, float*
         kp.spec_lists, kp.spec_cnt, kp.spec_state, kp.spec_tau, failed, kp.tile_counter, kp.ws_magic, hp->valid_thresh, P, src, sink);
     VD_LAUNCH_CHECK();
     // 2. exact path over the queued frames (both kernels return at once when the queue is empty -- the steady state)
-    HeadKernelParams kf = kp;
-    kf.frame_list = failed; kf.frame_count = kp.spec_state + 2;
-    kf.total_tiles = kp.tiles_per_frame * hp->frames;              // grid sizing only: the device reads the real count
-    rc = launch_head<EPI_FILTER>(maps, kf, pl.C, stream);
-    if (rc) return rc;
+    for (int ps = 0; ps < pl.n_pass; ++ps) {
+        HeadKernelParams kf = kp;
+        window_params(hp, pl, ws, ps, &kf, wptr);
+        rc = make_maps(hp, pl, &maps, wptr);
+        if (rc) return rc;
+        kf.frame_list = failed; kf.frame_count = kp.spec_state + 2;
+        kf.total_tiles = kp.tiles_per_frame * hp->frames;              // grid sizing only: the device reads the real count
+        rc = launch_head<EPI_FILTER>(maps, kf, pl.C, stream);
+        if (rc) return rc;
+    }
     nms_final_hist_kernel<<<hp->frames, kNmsThreads, nms_hist_smem(k, hp->post_nms), stream>>>(
-        kp.lists, kp.counts, kp.counts_hi, kp.hint_hi, kp.coarse, kp.tiles_per_frame, kp.hist, kp.tile_counter, kp.ws_magic,
+        kp.lists, kp.counts, kp.counts_hi, kp.hint_hi, kp.coarse, kp.tiles_per_frame * pl.n_pass, kp.hist, kp.tile_counter, kp.ws_magic,
         failed, kp.spec_state, kp.spec_tau, P, src, sink);
     VD_LAUNCH_CHECK();
     return VD_OK;
@@ -1744,7 +1902,6 @@ extern "C" int vd_head_forward_stages(const VdHeadParams* hp, float* ids, float*
 
 extern "C" int vd_head_detections(const VdHeadParams* hp, float* det, void* workspace, size_t workspace_bytes, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
-    (void)workspace; (void)workspace_bytes;
     HeadPlan pl;
     int rc = make_plan(hp, &pl);
     if (rc) return rc;
@@ -1763,10 +1920,21 @@ extern "C" int vd_head_detections(const VdHeadParams* hp, float* det, void* work
             if (rc) return rc;
         }
     }
-    HeadMaps maps;
-    rc = make_maps(hp, pl, &maps);
+    if (pl.repack && (!workspace || workspace_bytes < pl.total))
+        return set_error(VD_ERR_WORKSPACE, "head_detections: workspace %zu < required %zu (class windows need the weight re-layout area)", workspace_bytes, pl.total);
+    unsigned char* ws = (unsigned char*)workspace;
+    rc = repack_windows(hp, pl, ws, stream);
     if (rc) return rc;
-    return launch_head<EPI_DET>(maps, kp, pl.C, stream);
+    const void* wptr[VD_MAX_SCALES];
+    HeadMaps maps;
+    for (int ps = 0; ps < pl.n_pass; ++ps) {
+        window_params(hp, pl, ws, ps, &kp, wptr);
+        rc = make_maps(hp, pl, &maps, wptr);
+        if (rc) return rc;
+        rc = launch_head<EPI_DET>(maps, kp, pl.C, stream);
+        if (rc) return rc;
+    }
+    return VD_OK;
 }
 
 extern "C" int vd_pred_conv(const void* x, int B, int H, int W, int Cin, int K_frames, int join,

@@ -89,18 +89,25 @@ temporal_conv_kernel(const __grid_constant__ TConvMaps maps, const __grid_consta
             int stage = 0; uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
                 int b, mt, nt; coords(tile, b, mt, nt);
-                for (int tap = 0; tap < 3; ++tap) {
-                    const int dt = tap - 1;
-                    if (!tap_active(mt, dt)) continue;
-                    for (int pr = 0; pr < p.n_prod; ++pr) {
-                        const int xb = b + (int)p.a_pl[pr] * p.B, wt = tap + 3 * (int)p.w_pl[pr];     // plane-major operands
-                        for (int kb = 0; kb < kb_per_tap; ++kb) {
-                            tc::mbar_wait(&sh->empty[stage], phase ^ 1u);
-                            unsigned char* a_dst = ring + stage * Cfg::STAGE_BYTES;
-                            tc::mbar_expect_tx(&sh->full[stage], Cfg::STAGE_BYTES);
-                            tc::tma_load_3d(a_dst, &maps.x, &sh->full[stage], kb * T_BLOCK_K, mt * T_BLOCK_M + dt * p.HW, xb);
-                            tc::tma_load_3d(a_dst + Cfg::A_BYTES, &maps.w, &sh->full[stage], kb * T_BLOCK_K, nt * NT, wt);
-                            if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
+                // item order (shared with the MMA role): plain cell: tap -> k-block.  Parity modes: first every low-order plane product
+                // (tap -> product -> k-block), then the p0 w0 product (tap -> k-block), see the MMA role for the chunking.
+                const int phases = p.planes > 1 ? 2 : 1;
+                for (int ph = 0; ph < phases; ++ph) {
+                    const int pr0 = (p.planes > 1 && ph == 1) ? p.n_prod - 1 : 0;
+                    const int pr1 = (p.planes > 1 && ph == 0) ? p.n_prod - 1 : p.n_prod;
+                    for (int tap = 0; tap < 3; ++tap) {
+                        const int dt = tap - 1;
+                        if (!tap_active(mt, dt)) continue;
+                        for (int pr = pr0; pr < pr1; ++pr) {
+                            const int xb = b + (int)p.a_pl[pr] * p.B, wt = tap + 3 * (int)p.w_pl[pr];     // plane-major operands
+                            for (int kb = 0; kb < kb_per_tap; ++kb) {
+                                tc::mbar_wait(&sh->empty[stage], phase ^ 1u);
+                                unsigned char* a_dst = ring + stage * Cfg::STAGE_BYTES;
+                                tc::mbar_expect_tx(&sh->full[stage], Cfg::STAGE_BYTES);
+                                tc::tma_load_3d(a_dst, &maps.x, &sh->full[stage], kb * T_BLOCK_K, mt * T_BLOCK_M + dt * p.HW, xb);
+                                tc::tma_load_3d(a_dst + Cfg::A_BYTES, &maps.w, &sh->full[stage], kb * T_BLOCK_K, nt * NT, wt);
+                                if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
+                            }
                         }
                     }
                 }
@@ -109,17 +116,28 @@ temporal_conv_kernel(const __grid_constant__ TConvMaps maps, const __grid_consta
     } else if (warp == 1) {
         if (tc::elect_one()) {
             constexpr uint32_t idesc = tc::make_idesc_bf16(T_BLOCK_M, NT);
-            int stage = 0; uint32_t phase = 0; uint32_t it = 0;
-            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+            int stage = 0; uint32_t phase = 0; uint32_t it = 0;      // `it` counts accumulator hand-overs (chunks): one per tile in the plain cell
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
                 int b, mt, nt; coords(tile, b, mt, nt);
-                const uint32_t buf = it & 1u;
-                tc::mbar_wait(&sh->tmem_empty[buf], ((it >> 1) & 1u) ^ 1u);
-                tc::fence_after_sync();
-                const uint32_t d_tmem = tmem_base + buf * NT;
-                uint32_t first = 1;
-                for (int tap = 0; tap < 3; ++tap) {
-                    if (!tap_active(mt, tap - 1)) continue;
-                    for (int kb = 0; kb < kb_per_tap * p.n_prod; ++kb) {          // all plane products of the tap accumulate into the same tile
+                int n_act = 0;
+                for (int tap = 0; tap < 3; ++tap) n_act += tap_active(mt, tap - 1) ? 1 : 0;
+                // chunks of k-blocks that accumulate into one TMEM buffer before the epilogue takes it.  Plain cell: the whole tile.
+                // Parity modes: chunk 0 = every low-order plane product (their truncation errors scale with their 2^-9 / 2^-18
+                // magnitude), then the p0 w0 product in chunks of 4 k-blocks = 16 accumulates; the epilogue adds the chunks in
+                // registers with round-to-nearest (the tensor core's fp32 accumulator truncates: error grows linearly with the chain).
+                int lows = p.planes > 1 ? n_act * (p.n_prod - 1) * kb_per_tap : 0;
+                int his = n_act * kb_per_tap;
+                while (lows > 0 || his > 0) {
+                    int n_items;
+                    if (lows > 0) { n_items = lows; lows = 0; }
+                    else if (p.planes > 1) { n_items = his < 4 ? his : 4; his -= n_items; }
+                    else { n_items = his; his = 0; }
+                    const uint32_t buf = it & 1u;
+                    tc::mbar_wait(&sh->tmem_empty[buf], ((it >> 1) & 1u) ^ 1u);
+                    tc::fence_after_sync();
+                    const uint32_t d_tmem = tmem_base + buf * NT;
+                    uint32_t first = 1;
+                    for (int kb = 0; kb < n_items; ++kb) {
                         tc::mbar_wait(&sh->full[stage], phase);
                         tc::fence_after_sync();
                         const uint32_t a_addr = tc::smem_u32(ring + stage * Cfg::STAGE_BYTES);
@@ -133,8 +151,9 @@ temporal_conv_kernel(const __grid_constant__ TConvMaps maps, const __grid_consta
                         tc::umma_commit(&sh->empty[stage]);
                         if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
                     }
+                    tc::umma_commit(&sh->tmem_full[buf]);
+                    ++it;
                 }
-                tc::umma_commit(&sh->tmem_full[buf]);
             }
         }
     } else {
@@ -143,7 +162,62 @@ temporal_conv_kernel(const __grid_constant__ TConvMaps maps, const __grid_consta
         constexpr int NH = NT / 2;
         const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
         uint32_t it = 0;
-        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+        if constexpr (NT == 128) {
+            if (p.planes > 1) {
+                // parity modes (always on 128-wide channel blocks): add the tile's chunks in registers, then BN + LeakyReLU and the plane split
+                for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+                    int b, mt, nt; coords(tile, b, mt, nt);
+                    const int row = mt * T_BLOCK_M + q * 32 + lane;
+                    const bool inb = row < p.rows;
+                    int n_act = 0;
+                    for (int tap = 0; tap < 3; ++tap) n_act += tap_active(mt, tap - 1) ? 1 : 0;
+                    const int n_chunks = 1 + (n_act * kb_per_tap + 3) / 4;
+                    float sum[NH];
+#pragma unroll
+                    for (int i = 0; i < NH; ++i) sum[i] = 0.0f;
+                    for (int c = 0; c < n_chunks; ++c, ++it) {
+                        const uint32_t buf = it & 1u;
+                        tc::mbar_wait(&sh->tmem_full[buf], (it >> 1) & 1u);
+                        tc::fence_after_sync();
+                        const uint32_t tb = tmem_base + buf * NT + (uint32_t)(half * NH) + lane_addr;
+#pragma unroll
+                        for (int n0 = 0; n0 < NH; n0 += 32) {
+                            uint32_t r[32];
+                            tc::tmem_ld16(tb + n0, r); tc::tmem_ld16(tb + n0 + 16, r + 16); tc::tmem_ld_wait();
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) sum[n0 + i] = __fadd_rn(sum[n0 + i], __uint_as_float(r[i]));
+                        }
+                        tc::fence_before_sync();
+                        __syncwarp();
+                        if (lane == 0) tc::mbar_arrive(&sh->tmem_empty[buf]);
+                    }
+                    const int col0 = nt * NT + half * NH;
+                    __nv_bfloat16* yrow = p.y + ((size_t)b * p.rows + (inb ? row : 0)) * p.C + col0;
+#pragma unroll
+                    for (int i = 0; i < NH; ++i) {        // the reference's BatchNorm roundings: (y * scale) + shift, then LeakyReLU
+                        float v = __fadd_rn(__fmul_rn(sum[i], sscale[col0 + i]), sshift[col0 + i]);
+                        sum[i] = v > 0.f ? v : v * p.slope;
+                    }
+#pragma unroll 1
+                    for (int pl = 0; pl < p.planes; ++pl) {
+#pragma unroll
+                        for (int n0 = 0; n0 < NH; n0 += 8) {
+                            uint32_t packed[4];
+#pragma unroll
+                            for (int i = 0; i < 8; i += 2) {
+                                __nv_bfloat162 h = __floats2bfloat162_rn(sum[n0 + i], sum[n0 + i + 1]);
+                                packed[i / 2] = *reinterpret_cast<uint32_t*>(&h);
+                                sum[n0 + i] = __fsub_rn(sum[n0 + i], __low2float(h));             // exact: what the next plane carries
+                                sum[n0 + i + 1] = __fsub_rn(sum[n0 + i + 1], __high2float(h));
+                            }
+                            if (inb) *reinterpret_cast<uint4*>(yrow + (size_t)pl * p.y_plane_stride + n0) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+                        }
+                    }
+                }
+                it = 0xffffffffu;      // nothing left for the plain loop below
+            }
+        }
+        for (int tile = blockIdx.x; tile < p.total_tiles && it != 0xffffffffu; tile += gridDim.x, ++it) {
             int b, mt, nt; coords(tile, b, mt, nt);
             const uint32_t buf = it & 1u;
             const int row = mt * T_BLOCK_M + q * 32 + lane;
@@ -160,39 +234,21 @@ temporal_conv_kernel(const __grid_constant__ TConvMaps maps, const __grid_consta
                 uint32_t r[32];
                 tc::tmem_ld16(tbase + n0, r); tc::tmem_ld16(tbase + n0 + 16, r + 16); tc::tmem_ld_wait();
                 uint32_t packed[16];
-#pragma unroll 1
-                for (int pl = 0; pl < p.planes; ++pl) {            // plane pl of the fp32 result: bf16(v - planes before it) (exact subtractions)
 #pragma unroll
-                    for (int i = 0; i < 32; i += 4) {
-                        float v[4];
-                        if (pl == 0) {
-                            const float4 s4 = *reinterpret_cast<const float4*>(sc + n0 + i);
-                            const float4 f4 = *reinterpret_cast<const float4*>(sf + n0 + i);
-                            if (p.planes == 1) {                   // the plain bf16 cell keeps its historical arithmetic (fused multiply-add)
-                                v[0] = fmaf(__uint_as_float(r[i]), s4.x, f4.x); v[1] = fmaf(__uint_as_float(r[i + 1]), s4.y, f4.y);
-                                v[2] = fmaf(__uint_as_float(r[i + 2]), s4.z, f4.z); v[3] = fmaf(__uint_as_float(r[i + 3]), s4.w, f4.w);
-                            } else {                               // parity modes: the reference's two roundings, (y * scale) + shift
-                                v[0] = __fadd_rn(__fmul_rn(__uint_as_float(r[i]), s4.x), f4.x); v[1] = __fadd_rn(__fmul_rn(__uint_as_float(r[i + 1]), s4.y), f4.y);
-                                v[2] = __fadd_rn(__fmul_rn(__uint_as_float(r[i + 2]), s4.z), f4.z); v[3] = __fadd_rn(__fmul_rn(__uint_as_float(r[i + 3]), s4.w), f4.w);
-                            }
+                for (int i = 0; i < 32; i += 4) {
+                    const float4 s4 = *reinterpret_cast<const float4*>(sc + n0 + i);
+                    const float4 f4 = *reinterpret_cast<const float4*>(sf + n0 + i);
+                    float v0 = fmaf(__uint_as_float(r[i]), s4.x, f4.x), v1 = fmaf(__uint_as_float(r[i + 1]), s4.y, f4.y);
+                    float v2 = fmaf(__uint_as_float(r[i + 2]), s4.z, f4.z), v3 = fmaf(__uint_as_float(r[i + 3]), s4.w, f4.w);
+                    v0 = v0 > 0.f ? v0 : v0 * p.slope; v1 = v1 > 0.f ? v1 : v1 * p.slope;
+                    v2 = v2 > 0.f ? v2 : v2 * p.slope; v3 = v3 > 0.f ? v3 : v3 * p.slope;
+                    __nv_bfloat162 h0 = __floats2bfloat162_rn(v0, v1), h1 = __floats2bfloat162_rn(v2, v3);
+                    packed[i / 2] = *reinterpret_cast<uint32_t*>(&h0); packed[i / 2 + 1] = *reinterpret_cast<uint32_t*>(&h1);
+                }
+                if (inb) {
+                    uint4* dst = reinterpret_cast<uint4*>(yrow + n0);
 #pragma unroll
-                            for (int u = 0; u < 4; ++u) v[u] = v[u] > 0.f ? v[u] : v[u] * p.slope;
-                        } else {
-#pragma unroll
-                            for (int u = 0; u < 4; ++u) v[u] = __uint_as_float(r[i + u]);      // residual left by the previous plane
-                        }
-                        __nv_bfloat162 h0 = __floats2bfloat162_rn(v[0], v[1]), h1 = __floats2bfloat162_rn(v[2], v[3]);
-                        packed[i / 2] = *reinterpret_cast<uint32_t*>(&h0); packed[i / 2 + 1] = *reinterpret_cast<uint32_t*>(&h1);
-                        if (p.planes > 1) {
-                            r[i] = __float_as_uint(__fsub_rn(v[0], __low2float(h0))); r[i + 1] = __float_as_uint(__fsub_rn(v[1], __high2float(h0)));
-                            r[i + 2] = __float_as_uint(__fsub_rn(v[2], __low2float(h1))); r[i + 3] = __float_as_uint(__fsub_rn(v[3], __high2float(h1)));
-                        }
-                    }
-                    if (inb) {
-                        uint4* dst = reinterpret_cast<uint4*>(yrow + (size_t)pl * p.y_plane_stride + n0);
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) dst[i] = make_uint4(packed[4 * i], packed[4 * i + 1], packed[4 * i + 2], packed[4 * i + 3]);
-                    }
+                    for (int i = 0; i < 4; ++i) dst[i] = make_uint4(packed[4 * i], packed[4 * i + 1], packed[4 * i + 2], packed[4 * i + 3]);
                 }
             }
             tc::fence_before_sync();
@@ -417,7 +473,7 @@ extern "C" int vd_temporal_conv_ex(const void* x, void* y, int B, int T, int H, 
     VD_CHECK_ARG(precision == VD_PREC_BF16 || precision == VD_PREC_FP32_SPLIT || precision == VD_PREC_BF16X2, "temporal_conv: precision %d", precision);
     if (B == 0) return VD_OK;
     const int planes = precision == VD_PREC_FP32_SPLIT ? 3 : (precision == VD_PREC_BF16X2 ? 2 : 1);
-    const int NT = (C % 256 == 0) ? 256 : 128;
+    const int NT = (C % 256 == 0 && planes == 1) ? 256 : 128;      // the parity modes sum their chunks in registers: 128-wide channel blocks
     TConvParams p;
     memset(&p, 0, sizeof(p));
     p.B = B; p.T = T; p.HW = H * W; p.C = C; p.rows = T * H * W;
@@ -427,10 +483,11 @@ extern "C" int vd_temporal_conv_ex(const void* x, void* y, int B, int T, int H, 
     p.total_tiles = (int)total;
     p.scale = scale; p.shift = shift; p.slope = slope; p.y = (__nv_bfloat16*)y;
     p.planes = planes; p.n_prod = 1; p.y_plane_stride = (long long)B * p.rows * C;
-    if (planes > 1) {                      // same plane products as the head kernel (head.cu split_products)
-        static const signed char a3[6] = {0, 1, 0, 1, 2, 0}, w3[6] = {0, 0, 1, 1, 0, 2};
+    if (planes > 1) {                      // same plane products as the head kernel (head.cu split_products): low-order first, p0 w0 last
+        static const signed char a3[6] = {0, 2, 1, 0, 1, 0}, w3[6] = {2, 0, 1, 1, 0, 0};
+        static const signed char a2[3] = {0, 1, 0}, w2[3] = {1, 0, 0};
         p.n_prod = planes == 3 ? 6 : 3;
-        for (int i = 0; i < p.n_prod; ++i) { p.a_pl[i] = a3[i]; p.w_pl[i] = w3[i]; }
+        for (int i = 0; i < p.n_prod; ++i) { p.a_pl[i] = planes == 3 ? a3[i] : a2[i]; p.w_pl[i] = planes == 3 ? w3[i] : w2[i]; }
     }
     TConvMaps maps;
     uint64_t dimsX[3] = {(uint64_t)C, (uint64_t)p.rows, (uint64_t)B * planes};

@@ -398,8 +398,8 @@ def test_errors_surface():
         head(bad)                                    # Cin not a multiple of 64
     h17 = viddet_b200.YOLOV3Head(17).initialize()
     tips = [torch.zeros(1, c, 4, 4, device="cuda") for c in CHANNELS]
-    with pytest.raises(viddet_b200.VidDetError):
-        h17(tips)                                    # no fused instantiation for 17 classes
+    ids, scores, boxes = h17(tips)                   # any class count runs fused (class windows on the compiled shapes)
+    assert ids.shape == (1, 100, 1)
 
 
 def _ar1_batches(rng, n, B, size, rho):
@@ -504,3 +504,73 @@ def test_output_mirrors_store_every_result_twice():
         assert torch.equal(out[1].view(torch.int32), scores.view(torch.int32))
         assert torch.equal(buf[1].view(torch.int32), buf[0].view(torch.int32))
         assert torch.equal(buf[2].view(torch.int32), buf[0].view(torch.int32))
+
+
+@pytest.mark.parametrize("C,size,B", [(7, 224, 3), (17, 320, 2), (23, 224, 2), (81, 160, 2), (200, 160, 2), (285, 224, 2)])
+def test_arbitrary_class_counts_fused_bit_exact(C, size, B):
+    """YOLOOutputV3 takes any num_class (yolo3.py:43-62): YouTube-BB has 23, ImageNet-DET 200, the reference's combined tree 285
+    (datasets/combined.py:16).  Class counts without a compiled kernel shape run on the next shape with padding classes masked
+    (C <= 80) or as windows of 80 classes appending to the same per-frame lists (C > 80).  Checked like the compiled shapes:
+    detections() == per-scale predict (sliced GEMM) + decode (standalone kernel), head() == box_nms(detections()) bit for bit,
+    on the cold (exact) and the steady (speculative) path."""
+    import viddet_b200
+    rng = np.random.RandomState(C + size)
+    tips = make_tips(rng, B, size=size)
+    ws, bs = make_pred_weights(rng, C, bias_scale=0.2)
+    head = build_head(C, ws, bs)
+    head.set_nms(nms_thresh=0.45, nms_topk=400, post_nms=100)
+    tt = [cuda(t) for t in tips]
+    det = head.detections(tt)
+    parts = [o(t) for o, t in zip(head.yolo_outputs, tt)]
+    compat = torch.cat(parts, dim=1)
+    assert torch.equal(det.view(torch.int32), compat.view(torch.int32))
+    out, rec = viddet_b200.box_nms(det, overlap_thresh=0.45, valid_thresh=0.01, topk=400, id_index=0, score_index=1,
+                                   coord_start=2, force_suppress=False, return_record=True)
+    for call in range(3):
+        ids, scores, boxes, keep = head(tt, return_keep=True)
+        assert torch.equal(keep, rec[:, :100]), call
+        assert torch.equal(ids.view(torch.int32), out[:, :100, 0:1].contiguous().view(torch.int32))
+        assert torch.equal(scores.view(torch.int32), out[:, :100, 1:2].contiguous().view(torch.int32))
+        assert torch.equal(boxes.view(torch.int32), out[:, :100, 2:].contiguous().view(torch.int32))
+    assert int(ids.max().item()) <= C - 1
+
+
+@pytest.mark.parametrize("C", [7, 285])
+def test_arbitrary_class_counts_vs_oracle(C):
+    """The same heads against the CPU oracle chain (decode ids exact, scores 1e-3, keep rows up to near-ties)."""
+    rng = np.random.RandomState(C)
+    B, size = 2, 160
+    tips = make_tips(rng, B, size=size)
+    ws, bs = make_pred_weights(rng, C, bias_scale=0.2)
+    head = build_head(C, ws, bs)
+    tt = [cuda(t) for t in tips]
+    det = head.detections(tt).cpu().numpy()
+    ref = ref_head.head_detections(tips, ws, bs, C)
+    np.testing.assert_array_equal(det[..., 0], ref[..., 0])
+    np.testing.assert_allclose(det[..., 1], ref[..., 1], rtol=1e-3)
+    ids, scores, boxes, keep = [t.cpu().numpy() for t in head(tt, return_keep=True)]
+    out, rec = ref_nms.box_nms(ref, overlap_thresh=0.45, valid_thresh=0.01, topk=400, id_index=0, score_index=1, coord_start=2,
+                               return_record=True)
+    frac, n_tie = keep_agreement(keep, rec, ref, tol=1e-4)
+    assert frac >= 0.97, frac
+
+
+def test_arbitrary_class_counts_valid_thresh_below_zero_and_heavy_ties():
+    """Padding classes must never surface: with valid_thresh < 0 every REAL candidate is valid (score 0 included), and constant
+    feature maps tie whole scales; both through a padded shape (C = 7 on the 20-class kernel) and windows (C = 90)."""
+    import viddet_b200
+    for C in (7, 90):
+        rng = np.random.RandomState(C)
+        tips = [np.full_like(t, 0.5) for t in make_tips(rng, 2, size=160)]
+        ws, bs = make_pred_weights(rng, C, bias_scale=0.3)
+        head = build_head(C, ws, bs)
+        head.valid_thresh = -1.0
+        head.set_nms(0.45, 400, 100)
+        tt = [cuda(t) for t in tips]
+        det = head.detections(tt)
+        out, rec = viddet_b200.box_nms(det, overlap_thresh=0.45, valid_thresh=-1.0, topk=400, id_index=0, score_index=1,
+                                       coord_start=2, force_suppress=False, return_record=True)
+        for call in range(2):
+            ids, scores, boxes, keep = head(tt, return_keep=True)
+            assert torch.equal(keep, rec[:, :100]), (C, call)
+            assert torch.equal(scores.view(torch.int32), out[:, :100, 1:2].contiguous().view(torch.int32))

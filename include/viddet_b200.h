@@ -138,6 +138,9 @@ typedef struct VdHeadScale {
     const float* tconv_scale;       /* (Cin) folded BN scale  gamma/sqrt(var+eps)                */
     const float* tconv_shift;       /* (Cin) folded BN shift  beta - mean*scale                  */
     void* tconv_out_nhwc_bf16;      /* (frames, H, W, Cin) bf16 scratch for the cell's output    */
+    int tip_window_stride_frames;   /* temporal cell input: 0 / T = materialised windows (B,T,H,W,Cin); 1 = windows sliding over a
+                                       resident clip, tip points at window 0's first frame (see vd_temporal_conv_ex) */
+    int reserved;                   /* must be 0                                                 */
 } VdHeadScale;
 
 typedef struct VdHeadParams {
@@ -226,10 +229,15 @@ int vd_temporal_conv(const void* x_bf16, void* y_bf16, int B, int T, int H, int 
                      float slope, void* stream);
 /* The same cell in an fp32-parity mode (see VD_PREC_* above): x, y (P, B, T, H, W, C) bf16 plane-major, weight (P, 3, C, C) bf16
  * [plane][tap][cout][cin]; the fp32 result of BN + LeakyReLU is written as P planes, ready for vd_head_forward with the same
- * precision.  VD_PREC_BF16 is vd_temporal_conv. */
+ * precision.  VD_PREC_BF16 is vd_temporal_conv.
+ * window_stride_frames: frames between the starts of consecutive windows inside x (0 or T: windows materialised back to back,
+ * x = (B, T, H, W, C)).  1 = windows sliding frame by frame over a RESIDENT clip: x points at the first frame of window 0 inside
+ * a (L, H, W, C) clip, window b covers clip frames [b, b + T) -- what datasets/imgnetvid.py:480-506 builds for consecutive
+ * centres away from the clip's ends (the clamped windows at the ends repeat frames and must be materialised).  The cell's zero
+ * padding stays local to each window.  bf16 mode only. */
 int vd_temporal_conv_ex(const void* x_bf16, void* y_bf16, int B, int T, int H, int W, int C,
                         const void* weight_bf16, const float* scale, const float* shift,
-                        float slope, int precision, void* stream);
+                        float slope, int precision, int window_stride_frames, void* stream);
 
 /* Conv-BN-LeakyReLU cell of YOLODetectionBlockV3: replaces `_conv2d` (layers.py:63-70) and `_conv3d`
  * (layers.py:73-79) as stacked at yolo3_temporal.py:198-239 -- Conv(no bias, stride 1, zero 'same' padding, kernel extents

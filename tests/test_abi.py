@@ -34,8 +34,8 @@ def test_load_and_version():
 
 def test_struct_layout_matches_header():
     # VdHeadScale: 3 ptr + 3 int + float + 6 float + 4 ptr ; natural alignment.  VdHeadParams: 12 x 4-byte scalars + 3 scales
-    assert ctypes.sizeof(_lib.VdHeadScale) == 96
-    assert ctypes.sizeof(_lib.VdHeadParams) == 48 + 3 * 96 + 8 + 7 * 8
+    assert ctypes.sizeof(_lib.VdHeadScale) == 104
+    assert ctypes.sizeof(_lib.VdHeadParams) == 48 + 3 * 104 + 8 + 7 * 8
     lib = viddet_b200.load()                         # the library's own sizeof of the compiled header
     assert lib.vd_sizeof(0) == ctypes.sizeof(_lib.VdHeadScale) and lib.vd_sizeof(1) == ctypes.sizeof(_lib.VdHeadParams)
 

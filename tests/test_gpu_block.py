@@ -101,7 +101,7 @@ def test_detection_block_vs_oracle(conv_type, shape):
         # 5-9 cells with bf16 carriers in between: rounding-boundary flips propagate; worst element and 99.9th percentile
         from tests.util import err_profile
         mx, p999, _ = err_profile(got, ref, "detection block '%s' vs oracle" % conv_type)
-        assert mx <= 2e-2 and p999 <= 1e-2
+        assert mx <= 8e-3 and p999 <= 6e-3                # measured on B200: max <= 4.6e-3, p99.9 <= 4.0e-3 over the three conv types
 
 
 def test_block_feeds_head():

@@ -127,10 +127,10 @@ def test_yolov3_neck_vs_executed_reference():
     # 99.9th percentile (a mean would hide outliers), measured on B200 and printed by err_profile.
     from tests.util import err_profile
     mx, p999, _ = err_profile(det[..., 1], ref[..., 1], "neck scores vs oracle with the same bf16 rounding points")
-    assert mx <= 5e-2 and p999 <= 2e-2
+    assert mx <= 4e-2 and p999 <= 2.5e-2                  # measured on B200: max 2.5e-2, p99.9 1.6e-2
     gold = G["neck_det"]
     mx, p999, _ = err_profile(det[..., 1], gold[..., 1], "neck scores vs the executed fp32 reference")
-    assert mx <= 8e-2 and p999 <= 4e-2
+    assert mx <= 3e-2 and p999 <= 2.5e-2                  # measured: max 1.9e-2, p99.9 1.5e-2
     ids, scores, boxes = neck(routes)
     assert ids.shape == G["neck_ids"].shape
     # the top detections agree with the reference's wherever the score gap exceeds the bf16 noise
@@ -167,9 +167,9 @@ def test_yolov3_temporal_neck_vs_executed_reference():
     np.testing.assert_array_equal(det[..., 0], ref[..., 0])
     from tests.util import err_profile
     mx, p999, _ = err_profile(det[..., 1], ref[..., 1], "temporal neck scores vs oracle with the same bf16 rounding points")   # 28 convs with bf16 carriers
-    assert mx <= 5e-2 and p999 <= 2e-2
+    assert mx <= 3e-2 and p999 <= 2.5e-2                  # measured on B200: max 1.8e-2, p99.9 1.6e-2
     mx, p999, _ = err_profile(det[..., 1], gold[..., 1], "temporal neck scores vs the executed fp32 reference")
-    assert mx <= 1e-1 and p999 <= 5e-2
+    assert mx <= 2.5e-2 and p999 <= 2e-2                  # measured: max 1.3e-2, p99.9 1.1e-2
     ids, scores, boxes = neck(routes)
     assert tuple(ids.shape) == G["tneck_ids"].shape == (B, T, 100, 1)
     gs, s = G["tneck_scores"][..., 0], scores.cpu().numpy()[..., 0]

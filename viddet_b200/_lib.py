@@ -34,6 +34,7 @@ class VdHeadScale(ctypes.Structure):
         ("stride", ctypes.c_float), ("anchors", ctypes.c_float * 6),
         ("tconv_weight_bf16", ctypes.c_void_p), ("tconv_scale", ctypes.c_void_p),
         ("tconv_shift", ctypes.c_void_p), ("tconv_out_nhwc_bf16", ctypes.c_void_p),
+        ("tip_window_stride_frames", ctypes.c_int), ("reserved", ctypes.c_int),
     ]
 
 
@@ -78,7 +79,7 @@ SIGNATURES = {
     "vd_ipc_close": (_i, [_vp]),
     "vd_ipc_free": (_i, [_vp]),
     "vd_temporal_conv": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _f, _vp]),
-    "vd_temporal_conv_ex": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _f, _i, _vp]),
+    "vd_temporal_conv_ex": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _f, _i, _i, _vp]),
     "vd_conv_bn_lrelu": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _f, _vp]),
     "vd_upsample_concat": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "vd_conv_tile_box": (_i, [_i, _i, _i, _ip, _ip, _ip]),

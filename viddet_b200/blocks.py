@@ -87,6 +87,55 @@ def to_nhwc_split(x, planes=3) -> SplitF32:
     return SplitF32(out, (B, C, H, W))
 
 
+def window_frame_indices(num_frames, centre, window_size, window_step=1):
+    """Frame indices of the temporal window around frame `centre` of a clip of `num_frames` frames, exactly as the reference's
+    dataset builds it (datasets/imgnetvid.py:480-506): floor(window_size / 2) frames back and forward at `window_step`, indices
+    clamped to the clip (the first / last frame is repeated at the clip's ends), an even window drops its last frame."""
+    half = int(window_size / 2.0)
+    win = [max(0, centre - back) for back in range(half * window_step, window_step - 1, -window_step)]
+    win.append(centre)
+    for fwd in range(window_step, half * window_step + 1, window_step):
+        if len(win) == window_size:
+            break
+        win.append(min(num_frames - 1, centre + fwd))
+    return win
+
+
+class ClipWindows:
+    """`count` windows of `T` consecutive frames sliding frame by frame over a RESIDENT clip (one scale's features of a whole
+    clip, (L, C, H, W) channels-last bf16): window b = clip frames [start + b, start + b + T).  That is what
+    window_frame_indices gives for consecutive centres start + T//2 + b away from the clip's ends (window_step 1); the temporal
+    head reads the windows straight out of the clip through one overlapping TMA map (vd_temporal_conv_ex, window stride 1) --
+    no frame is copied, every frame is fetched from HBM once instead of T times.  The clamped windows at a clip's two ends repeat
+    frames: build those with `materialise_windows`."""
+
+    def __init__(self, clip, start, count, T):
+        clip = to_nhwc_bf16(clip)
+        L, C, H, W = clip.shape
+        assert 0 <= start and count >= 0 and start + count + T - 1 <= L, "windows leave the clip"
+        self.clip, self.start, self.count, self.T = clip, int(start), int(count), int(T)
+        self.shape = (self.count * self.T, C, H, W)          # frames the head sees
+        self.device = clip.device
+
+    def data_ptr(self):
+        return self.clip[self.start:].data_ptr()
+
+    def materialise(self):
+        """The same windows as an ordinary (count, T, C, H, W) tensor (T-fold copy; for tests and the parity modes)."""
+        idx = torch.arange(self.count, device=self.device)[:, None] + torch.arange(self.T, device=self.device)[None, :] + self.start
+        return self.clip[idx.reshape(-1)].reshape((self.count, self.T) + tuple(self.clip.shape[1:]))
+
+
+def materialise_windows(clip, centres, window_size, window_step=1):
+    """(len(centres), T, C, H, W) windows gathered out of a resident clip with the reference's clamping (window_frame_indices):
+    the general path -- any centres, any step, the clip's ends."""
+    clip = to_nhwc_bf16(clip)
+    idx = [window_frame_indices(clip.shape[0], int(c), window_size, window_step) for c in centres]
+    T = len(idx[0])
+    flat = torch.as_tensor(idx, device=clip.device).reshape(-1)
+    return clip[flat].reshape((len(idx), T) + tuple(clip.shape[1:]))
+
+
 def _precision_code(precision):
     if precision is None or precision == "bf16" or (precision == _lib.VD_PREC_BF16 and precision is not False):
         return _lib.VD_PREC_BF16
@@ -395,7 +444,7 @@ class TemporalTipConv:
         assert F == B * T and C == self.channels
         y = torch.empty_like(xs.data)
         check(load().vd_temporal_conv_ex(ptr(xs.data), ptr(y), B, T, H, W, C, ptr(self.weight_split(planes)), ptr(self._scale),
-                                         ptr(self._shift), float(self.slope), self._precision, stream_ptr()))
+                                         ptr(self._shift), float(self.slope), self._precision, 0, stream_ptr()))
         return SplitF32(y, xs.shape)
 
     def __call__(self, x):
@@ -644,6 +693,7 @@ class YOLOV3Head:
             frames = F if frames is None else frames
             assert frames == F, "all scales must carry the same number of frames"
             s.tip_nhwc_bf16 = t.data.data_ptr() if split else t.data_ptr()
+            s.tip_window_stride_frames = 1 if isinstance(t, ClipWindows) else 0
             s.weight_bf16 = (o.prediction.weight_split(planes) if split else o.prediction.weight_bf16).data_ptr()
             s.bias = o.prediction.bias.data_ptr()
             s.H, s.W, s.Cin = H, W, C
@@ -665,6 +715,12 @@ class YOLOV3Head:
         planes = _lib.PLANES[self._precision]
         split = planes > 1
         for t in tips:
+            if isinstance(t, ClipWindows):
+                if self.temporal != "conv21" or split:
+                    raise _lib.VidDetError(-1, "ClipWindows feed the bf16 temporal ('conv21') head; use .materialise() elsewhere")
+                lead = (t.count, t.T)
+                flat.append(t)
+                continue
             if isinstance(t, SplitF32):
                 assert split and t.planes == planes, "SplitF32 tips need a matching fp32-parity precision"
                 flat.append(t)
@@ -688,7 +744,9 @@ class YOLOV3Head:
             if split:      # parity modes: the tip cells run here (split carriers in and out), the fused call then sees a plain per-frame head
                 flat = [tc.split_forward(f, lead[0], T) for tc, f in zip(self.tip_convs, flat)]
                 T = 1
-        scratch = [torch.empty_like(f) for f in flat] if (self.tip_convs is not None and not split) else None
+        scratch = None
+        if self.tip_convs is not None and not split:
+            scratch = [torch.empty(tuple(f.shape), dtype=torch.bfloat16, device=f.device, memory_format=torch.channels_last) for f in flat]
         p = self._params(flat, scratch)
         p.T = T
         return p, flat, scratch, lead
@@ -822,7 +880,9 @@ class HeadSession:
         (thresholds, hints) is kept.  Not for captured graphs: they hold the old pointers."""
         assert len(tips) == len(self.tips)
         for i, (t, old) in enumerate(zip(tips, self.tips)):
-            assert t.shape == old.shape and t.dtype == torch.bfloat16 and t.is_contiguous(memory_format=torch.channels_last)
+            assert tuple(t.shape) == tuple(old.shape) and type(t) is type(old)
+            if not isinstance(t, ClipWindows):
+                assert t.dtype == torch.bfloat16 and t.is_contiguous(memory_format=torch.channels_last)
             self.params.scale[i].tip_nhwc_bf16 = t.data_ptr()
         self.tips = list(tips)
         return self

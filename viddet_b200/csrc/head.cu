@@ -1829,8 +1829,8 @@ extern "C" int vd_head_forward_stages(const VdHeadParams* hp, float* ids, float*
         if (sc.tconv_weight_bf16 && (stage_mask & VD_STAGE_TCONV)) {
             VD_CHECK_ARG(sc.tconv_out_nhwc_bf16 && sc.tconv_scale && sc.tconv_shift, "head_forward: scale %d temporal cell needs out/scale/shift", s);
             VD_CHECK_ARG(hp->T >= 1 && hp->frames % hp->T == 0, "head_forward: frames %d not a multiple of T %d", hp->frames, hp->T);
-            rc = vd_temporal_conv(sc.tip_nhwc_bf16, sc.tconv_out_nhwc_bf16, hp->frames / hp->T, hp->T, sc.H, sc.W, sc.Cin,
-                                  sc.tconv_weight_bf16, sc.tconv_scale, sc.tconv_shift, 0.1f, stream_);
+            rc = vd_temporal_conv_ex(sc.tip_nhwc_bf16, sc.tconv_out_nhwc_bf16, hp->frames / hp->T, hp->T, sc.H, sc.W, sc.Cin,
+                                     sc.tconv_weight_bf16, sc.tconv_scale, sc.tconv_shift, 0.1f, VD_PREC_BF16, sc.tip_window_stride_frames, stream_);
             if (rc) return rc;
         }
     }
@@ -1915,8 +1915,8 @@ extern "C" int vd_head_detections(const VdHeadParams* hp, float* det, void* work
         if (sc.tconv_weight_bf16) {
             VD_CHECK_ARG(sc.tconv_out_nhwc_bf16 && sc.tconv_scale && sc.tconv_shift, "head_detections: scale %d temporal cell needs out/scale/shift", s);
             VD_CHECK_ARG(hp->T >= 1 && hp->frames % hp->T == 0, "head_detections: frames %d not a multiple of T %d", hp->frames, hp->T);
-            rc = vd_temporal_conv(sc.tip_nhwc_bf16, sc.tconv_out_nhwc_bf16, hp->frames / hp->T, hp->T, sc.H, sc.W, sc.Cin,
-                                  sc.tconv_weight_bf16, sc.tconv_scale, sc.tconv_shift, 0.1f, stream_);
+            rc = vd_temporal_conv_ex(sc.tip_nhwc_bf16, sc.tconv_out_nhwc_bf16, hp->frames / hp->T, hp->T, sc.H, sc.W, sc.Cin,
+                                     sc.tconv_weight_bf16, sc.tconv_scale, sc.tconv_shift, 0.1f, VD_PREC_BF16, sc.tip_window_stride_frames, stream_);
             if (rc) return rc;
         }
     }

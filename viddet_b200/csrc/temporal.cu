@@ -460,12 +460,12 @@ using namespace vd;
 extern "C" int vd_temporal_conv(const void* x, void* y, int B, int T, int H, int W, int C,
                                 const void* weight, const float* scale, const float* shift,
                                 float slope, void* stream_) {
-    return vd_temporal_conv_ex(x, y, B, T, H, W, C, weight, scale, shift, slope, VD_PREC_BF16, stream_);
+    return vd_temporal_conv_ex(x, y, B, T, H, W, C, weight, scale, shift, slope, VD_PREC_BF16, 0, stream_);
 }
 
 extern "C" int vd_temporal_conv_ex(const void* x, void* y, int B, int T, int H, int W, int C,
                                    const void* weight, const float* scale, const float* shift,
-                                   float slope, int precision, void* stream_) {
+                                   float slope, int precision, int window_stride_frames, void* stream_) {
     VD_CHECK_ARG(weight && scale && shift && (B == 0 || (x && y)), "temporal_conv: null pointer");
     VD_CHECK_ARG(B >= 0 && T >= 1 && H > 0 && W > 0, "temporal_conv: bad shape");
     VD_CHECK_ARG(C >= 128 && C % 128 == 0 && C <= 1024, "temporal_conv: C = %d must be a multiple of 128, at most 1024", C);
@@ -473,6 +473,12 @@ extern "C" int vd_temporal_conv_ex(const void* x, void* y, int B, int T, int H, 
     VD_CHECK_ARG(precision == VD_PREC_BF16 || precision == VD_PREC_FP32_SPLIT || precision == VD_PREC_BF16X2, "temporal_conv: precision %d", precision);
     if (B == 0) return VD_OK;
     const int planes = precision == VD_PREC_FP32_SPLIT ? 3 : (precision == VD_PREC_BF16X2 ? 2 : 1);
+    // Windows sliding over a resident clip: window b starts window_stride_frames frames after window b-1 in x (0 = T: windows
+    // materialised back to back).  The 3-D map (C, T*HW, B) then has OVERLAPPING windows along its last dimension; its middle
+    // extent stays T*HW, so the taps that leave a window still read as zeros (TMA out-of-bounds fill) although the clip holds
+    // real frames there -- the window-local zero padding of the Conv3D is kept without copying a single frame.
+    const int wstride = window_stride_frames > 0 ? window_stride_frames : T;
+    VD_CHECK_ARG(planes == 1 || wstride == T, "temporal_conv: the fp32-parity modes take materialised windows (window_stride_frames = T)");
     const int NT = (C % 256 == 0 && planes == 1) ? 256 : 128;      // the parity modes sum their chunks in registers: 128-wide channel blocks
     TConvParams p;
     memset(&p, 0, sizeof(p));
@@ -491,7 +497,7 @@ extern "C" int vd_temporal_conv_ex(const void* x, void* y, int B, int T, int H, 
     }
     TConvMaps maps;
     uint64_t dimsX[3] = {(uint64_t)C, (uint64_t)p.rows, (uint64_t)B * planes};
-    uint64_t strX[2] = {(uint64_t)C * 2, (uint64_t)p.rows * C * 2};
+    uint64_t strX[2] = {(uint64_t)C * 2, (uint64_t)wstride * H * W * C * 2};
     uint32_t boxX[3] = {T_BLOCK_K, T_BLOCK_M, 1};
     int rc = encode_tmap_bf16(&maps.x, x, 3, dimsX, strX, boxX);
     if (rc) return rc;

@@ -507,17 +507,28 @@ def main():
     head.set_nms(nms_thresh=0.45, nms_topk=400, post_nms=100)            # detect_yolo3.py:200
     # resident input pool: npool distinct batches (clips / frames of this rank), contiguous per scale, so that `group` consecutive
     # batches are one (group*frames, H, W, C) tensor; ring of NRING sessions (workspace + outputs), each covering one launch group
-    big = [torch.empty((npool * frames, c, size // s_, size // s_), dtype=torch.bfloat16, device=dev, memory_format=torch.channels_last)
+    # Temporal workload (cfg 4): the pool is a RESIDENT CLIP of this rank (npool * 64 + 4 frames per scale); a step = 64 windows of
+    # T = 5 frames sliding frame by frame over it (centres 2 + 64 i ...), read through ClipWindows -- no window is materialised,
+    # every clip frame is fetched once per step instead of five times (datasets/imgnetvid.py:480-506; clamped end windows excluded).
+    in_frames = frames // T if temporal else frames      # NEW input frames per step
+    halo = T - 1 if temporal else 0
+    big = [torch.empty((npool * in_frames + halo, c, size // s_, size // s_), dtype=torch.bfloat16, device=dev, memory_format=torch.channels_last)
            for c, s_ in zip(CHANNELS, STRIDES)]
-    batch_view = lambda i: [b_[i * frames:(i + 1) * frames] for b_ in big]
+    batch_view = lambda i: [b_[i * in_frames:(i + 1) * in_frames + halo] for b_ in big]      # the frames step i reads
     if args.data == "video":
         assert not temporal
         synth_video_pool(torch, gen, npool, frames, size, dev, [batch_view(i) for i in range(npool)])
     else:
         for i in range(npool):
-            synth_tips(torch, gen, frames, size, dev, out=batch_view(i))
-    as_windows = (lambda ts: [t.reshape((t.shape[0] // T, T) + tuple(t.shape[1:])) for t in ts]) if temporal else (lambda ts: ts)
-    group_inputs = [[b_[g * gframes:(g + 1) * gframes] for b_ in big] for g in range(npool // group)]
+            synth_tips(torch, gen, in_frames, size, dev, out=[b_[i * in_frames:(i + 1) * in_frames] for b_ in big])
+        if halo:
+            synth_tips(torch, gen, halo, size, dev, out=[b_[npool * in_frames:] for b_ in big])
+    if temporal:
+        windows_of = lambda ts, start=0, count=in_frames * group: [viddet_b200.ClipWindows(t, start, count, T) for t in ts]
+        group_inputs = [windows_of(big, g * group * in_frames) for g in range(npool // group)]
+    else:
+        windows_of = lambda ts, start=0, count=0: ts
+        group_inputs = [[b_[g * gframes:(g + 1) * gframes] for b_ in big] for g in range(npool // group)]
     nf = NRING * gframes * 100
     peer, gather_kind = None, "single GPU"
     if world > 1 and args.gather == "peer":
@@ -532,7 +543,7 @@ def main():
     sessions = []
     for j in range(NRING):
         sl = slice(j * gframes, (j + 1) * gframes)
-        s = head.session(as_windows(group_inputs[j]), out=(ids_all[sl], scores_all[sl], boxes_all[sl]), mirrors=peer.deltas if peer is not None else None)
+        s = head.session(group_inputs[j], out=(ids_all[sl], scores_all[sl], boxes_all[sl]), mirrors=peer.deltas if peer is not None else None)
         sessions.append(s)
     if args.data == "same":                               # r1 behaviour: every session keeps replaying its own inputs
         group_inputs_run = None
@@ -671,7 +682,8 @@ def main():
     # ---- worst case of the speculative path: EVERY frame fails its proof (thresholds learned on data scaled the other way),
     #      so the exact pair redoes the whole batch inside the call
     allfail = None
-    one = [head.session(as_windows([t.clone() for t in pool_flat[j]])) for j in range(2)]       # single-batch sessions (own input buffers) for the legs below
+    one_bufs = [[t.clone() for t in pool_flat[j]] for j in range(2)]                              # single-step sessions with their own input buffers for the legs below
+    one = [head.session(windows_of(one_bufs[j], 0, in_frames)) for j in range(2)]
     for s_ in one:
         s_.run(); s_.run()
     if not temporal:
@@ -713,7 +725,7 @@ def main():
         main = torch.cuda.current_stream()
         with torch.cuda.stream(copy_stream):
             copy_stream.wait_event(compute_done[j])              # the buffer's previous step has consumed it
-            for dst, src in zip(s_.tips, host_sets[i % 4]):
+            for dst, src in zip(one_bufs[j], host_sets[i % 4]):
                 dst.copy_(src, non_blocking=True)
             h2d_done[j].record(copy_stream)
         main.wait_event(h2d_done[j])
@@ -790,7 +802,7 @@ def main():
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": unit, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps, "h2d_only_gbs_per_rank": h2d * e2e_steps / (copy_ms * 1e-3) / 1e9,
-                    "note": "pinned host bf16 NHWC tips (4 host batches, NUMA-local) -> H2D (copy stream, double-buffered under the previous step's compute) -> fused head -> D2H of (frames,100,6); PCIe-bound: h2d_only_gbs_per_rank is the same traffic with no compute"},
+                    "note": "pinned host bf16 NHWC tips (4 host batches, NUMA-local) -> H2D (copy stream, double-buffered under the previous step's compute) -> fused head -> D2H of (frames,100,6); PCIe-bound: h2d_only_gbs_per_rank is the same traffic with no compute" + ("; temporal: each step uploads its 64 new clip frames + 4 halo frames ONCE, the 5-frame windows are formed on the device" if temporal else "")},
             "gpu_launches": (args.steps // group) * sessions[0].launches,
             "clocks": clocks,
         }

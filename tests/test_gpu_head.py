@@ -574,3 +574,43 @@ def test_arbitrary_class_counts_valid_thresh_below_zero_and_heavy_ties():
             ids, scores, boxes, keep = head(tt, return_keep=True)
             assert torch.equal(keep, rec[:, :100]), (C, call)
             assert torch.equal(scores.view(torch.int32), out[:, :100, 1:2].contiguous().view(torch.int32))
+
+
+def test_clip_windows_equal_materialised_windows_bit_exact():
+    """Temporal head on windows sliding over a RESIDENT clip (ClipWindows: one overlapping TMA map, no copies) == the same head on
+    the materialised (B,T,C,H,W) windows, bit for bit; the clamped windows at the clip's ends (datasets/imgnetvid.py:480-506) go
+    through materialise_windows and are checked against a literal gather with the reference's index rule."""
+    import viddet_b200
+    rng = np.random.RandomState(12)
+    C, L, T, size = 30, 14, 5, 160
+    clips = [cuda(t) for t in make_tips(rng, L, size=size)]                     # one clip: (L, C_s, H_s, W_s) per scale
+    ws, bs = make_pred_weights(rng, C)
+    head = build_head(C, ws, bs, temporal="conv21")
+    for tc_, ch in zip(head.tip_convs, CHANNELS):
+        tc_.set_data(torch.from_numpy(bf16_round(rng.uniform(-0.05, 0.05, (ch, ch, 3, 1, 1)).astype(np.float32))))
+    head.set_nms(0.45, 400, 100)
+    start, count = 1, 8                                                         # centres 3 .. 10: windows [1,6) .. [8,13)
+    cw = [viddet_b200.ClipWindows(c, start, count, T) for c in clips]
+    ids, scores, boxes, keep = head(cw, return_keep=True)
+    assert ids.shape == (count, T, 100, 1)
+    mat = [w.materialise() for w in cw]
+    for b in range(count):                                                      # materialise() == the reference's window rule away from the ends
+        assert viddet_b200.window_frame_indices(L, start + 2 + b, T) == list(range(start + b, start + b + T))
+    ids2, scores2, boxes2, keep2 = head(mat, return_keep=True)
+    assert torch.equal(keep, keep2)
+    assert torch.equal(scores.view(torch.int32), scores2.view(torch.int32))
+    assert torch.equal(boxes.view(torch.int32), boxes2.view(torch.int32))
+    det = head.detections(cw)
+    det2 = head.detections(mat)
+    assert torch.equal(det.view(torch.int32), det2.view(torch.int32))
+    # the clip's ends: clamped windows repeat the first / last frame
+    centres = [0, 1, L - 2, L - 1]
+    ends = [viddet_b200.materialise_windows(c, centres, T) for c in clips]
+    assert tuple(ends[0].shape[:2]) == (4, T)
+    idx = [viddet_b200.window_frame_indices(L, c, T) for c in centres]
+    assert idx[0] == [0, 0, 0, 1, 2] and idx[-1] == [L - 3, L - 2, L - 1, L - 1, L - 1]
+    for e, c in zip(ends, clips):
+        ref = torch.stack([torch.stack([c[i] for i in w]) for w in idx])
+        assert torch.equal(e, ref)
+    ids3, _, _ = head(ends)
+    assert ids3.shape == (4, T, 100, 1)

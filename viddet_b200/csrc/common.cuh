@@ -24,6 +24,18 @@ int set_error(int code, const char* fmt, ...);
                              cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
 #define VD_LAUNCH_CHECK()  VD_CUDA(cudaGetLastError())
 
+// Device-side index checks of the global-memory stores / gathers of the hot kernels.  compute-sanitizer is closed on this pool
+// (it left GPUs needing a reset), so the memory-safety evidence is a build variant with these checks compiled in
+// (`python -m viddet_b200.build --variant bounds -DVD_BOUNDS_CHECK`, VD_LIB=... pytest -m gpu; profiles/r02_bounds_check.txt): a
+// violated check prints its location and traps, which fails the test with a CUDA error.  Compiled out of the product build.
+#ifdef VD_BOUNDS_CHECK
+#define VD_DEV_CHECK(cond)                                                                                          \
+    do { if (!(cond)) { printf("viddet_b200 bounds check failed: %s (%s:%d) block %d thread %d\n", #cond, __FILE__, __LINE__, \
+                               (int)blockIdx.x, (int)threadIdx.x); __trap(); } } while (0)
+#else
+#define VD_DEV_CHECK(cond) do { } while (0)
+#endif
+
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }

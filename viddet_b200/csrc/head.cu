@@ -429,6 +429,7 @@ head_kernel(const __grid_constant__ HeadMaps maps, const __grid_constant__ HeadK
                     const uint32_t base = __shfl_sync(0xffffffffu, spec_pend_base, 0);
                     const uint64_t* src_s = slist + (size_t)((warp - kEpiWarp0) * 2 + (int)((spec_par ^ 1u) & 1u)) * kSpecStage;
                     uint64_t* dst = p.spec_lists + (size_t)spec_pend_f * kSpecCap;
+                    VD_DEV_CHECK(spec_pend_f >= 0 && spec_pend_f < p.frames && n <= (uint32_t)kSpecStage);
                     for (uint32_t j = (uint32_t)lane; j < n; j += 32u) if (base + j < (uint32_t)kSpecCap) dst[base + j] = src_s[j];
                     spec_pend_n = 0u;
                 }
@@ -547,6 +548,7 @@ head_kernel(const __grid_constant__ HeadMaps maps, const __grid_constant__ HeadK
                     // the raw (tx,ty,tw,th) are stored; only the <= topk boxes that reach the NMS kernel are decoded there
                     // (same vd_decode_box, same bits) instead of all 3*HW of them here
                     if (!inb) conf[a] = __uint_as_float(0x7fc00000u);   // NaN: no score of a padding pixel passes `> valid_thresh`
+                    VD_DEV_CHECK(f >= 0 && f < p.frames && s >= 0 && s < p.g.num_scales && (!inb || p.g.anc_base[s] + cell * 3 + a < p.g.anc_base[p.g.num_scales]));
                     if (inb && half == 0 && p.pass == 0 && p.dbg != 8) p.boxes[(size_t)f * p.g.anc_base[p.g.num_scales] + p.g.anc_base[s] + cell * 3 + a] = make_float4(tx, ty, tw, th);
                     (void)bx; (void)gx; (void)gy;
                 } else {   // EPI_DET: class rows of this (cell, anchor)
@@ -630,6 +632,7 @@ head_kernel(const __grid_constant__ HeadMaps maps, const __grid_constant__ HeadK
                             if (sc > vth) {
                                 const uint32_t kh = __float_as_uint(sc) | 0x80000000u;
                                 const uint32_t row = row0 + (uint32_t)(cc * CH + i) * HW3 + (uint32_t)a;
+                                VD_DEV_CHECK(row < (uint32_t)p.g.row_base[p.g.num_scales] && inb);
                                 const uint64_t key = ((uint64_t)kh << 32) | (uint32_t)~row;
                                 const uint32_t sp = atomicAdd(wc, 1u);
                                 if (sp < (uint32_t)kSpecStage) stg[sp] = key;
@@ -890,6 +893,7 @@ head_kernel(const __grid_constant__ HeadMaps maps, const __grid_constant__ HeadK
                         const uint32_t row = rbase + (local >> 9) * HW3 + ((local >> 2) & 127u) * 3u + (local & 3u);
                         o = (v & 0xffffffff00000000ull) | (uint32_t)(~row);
                         const uint32_t hb = hist_bin((uint32_t)(v >> 32));
+                        VD_DEV_CHECK(hb < (uint32_t)kHistBins && row < (uint32_t)p.g.row_base[p.g.num_scales] && j < (uint32_t)kListCap);
                         if (p.dbg != 5) { atomicAdd(&p.hist[(size_t)f * kHistBins + hb], 1u); atomicAdd(&gs->chist[hb >> 6], 1u); }
                     }
                     if (p.dbg != 6) gl[j] = o;
@@ -1026,6 +1030,7 @@ head_kernel(const __grid_constant__ HeadMaps maps, const __grid_constant__ HeadK
                 // ---- retarget the warm start towards the band centre
                 if (et == 0) {
                     gs->pcur[0] = gs->pcur[1] = gs->pcur[2] = 0u; gs->cursor = 0u; gs->cursor2 = 0u;   // next tile starts from empty lists
+                    VD_DEV_CHECK(li < (size_t)p.frames * p.n_pass * p.tiles_per_frame && list_n <= (uint32_t)kListCap && list_hi <= list_n);
                     p.counts[li] = list_n; p.counts_hi[li] = list_hi;
                     if (piv > floor_b) {
                         const uint32_t q4 = (cap - k) / 4u, nudge = band_w >> 3;
@@ -1069,6 +1074,7 @@ struct FusedSource {
         const int per = g.HW[s] * 3;
         c = rs / per;
         const int slot = rs - c * per;
+        VD_DEV_CHECK((int)row < g.row_base[g.num_scales] && rs >= 0 && c < g.num_class && slot < per);
         const float4 t = boxes[(size_t)f * g.anc_base[g.num_scales] + g.anc_base[s] + slot];     // raw (tx,ty,tw,th) of the anchor
         const int cell = slot / 3, a = slot - cell * 3;
         const int gy = cell / g.W[s], gx = cell - gy * g.W[s];
@@ -1090,6 +1096,7 @@ struct FusedSink {
     }
     __device__ __forceinline__ void emit(int f, int pos, uint32_t row, float score, float4 bx, int c) const {
         size_t o = (size_t)f * post + pos;
+        VD_DEV_CHECK(pos >= 0 && pos < post && f >= 0);
         put(ids + o, __fadd_rn(__fmul_rn(score, 0.0f), (float)c));
         put(scores + o, score);
         put(reinterpret_cast<float4*>(bboxes) + o, bx);
@@ -1196,6 +1203,7 @@ __device__ void nms_tail_wave(const int n, const int f, const NmsParams P, const
             const uint32_t slot = kept_total + (uint32_t)__popc(alive & ((1u << lane) - 1u));
             if ((alive >> lane) & 1u) {
                 if (slot < (uint32_t)P.max_out) sink.emit(f, (int)slot, key_row(skeys[pm]), key_score(skeys[pm]), bm, cm);
+                VD_DEV_CHECK(slot < (uint32_t)((P.max_out < P.k ? P.max_out : P.k) + 32));
                 skbox[slot] = bm; skarea[slot] = am_; skcls[slot] = cm;
             }
             // pad the list to the test loop's stride with entries that match no class
@@ -1446,7 +1454,7 @@ nms_spec_kernel(const uint64_t* __restrict__ spec_lists, uint32_t* __restrict__ 
         ok = n_ge >= (uint32_t)k || tb == floor_b;
     }
     if (!ok) {
-        if (tid == 0) failed[atomicAdd(&spec_state[2], 1u)] = (uint32_t)f;
+        if (tid == 0) { const uint32_t slot_ = atomicAdd(&spec_state[2], 1u); VD_DEV_CHECK(slot_ < gridDim.x); failed[slot_] = (uint32_t)f; }
         return;
     }
     VD_STAMP(P, 2);

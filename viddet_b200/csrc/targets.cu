@@ -123,6 +123,7 @@ targets_scatter_kernel(TargetArgs a) {
         double fx = (double)gx / (double)a.orig_w * (double)a.W[layer];
         double fy = (double)gy / (double)a.orig_h * (double)a.H[layer];
         size_t o = (size_t)b * a.N + row;
+        VD_DEV_CHECK(row >= 0 && row < a.N && match >= 0 && match < 9);
         a.ctr[o * 2] = (float)(fx - (double)(int)fx);
         a.ctr[o * 2 + 1] = (float)(fy - (double)(int)fy);
         // np.log(max(gtw, 1) / anchor): fp32 path when gtw >= 1, float64 path when 1 > gtw

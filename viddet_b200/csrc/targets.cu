@@ -10,12 +10,49 @@
 //                           of SURVEY.md A.3), fp64 cell index (A.4), `break` at the first invalid
 //                           GT, last-writer-wins de-duplication, then the <= M owner rows are
 //                           written (class row replaced, not OR-ed).
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace vd {
 
 struct FillSeg { float* p; size_t n; float v; };
 struct FillArgs { FillSeg seg[5]; };
+
+// Background fill through the TMA bulk-copy engine: every CTA keeps one 32 KB shared-memory tile of its segment's value and
+// streams it to consecutive 32 KB chunks of the output with cp.async.bulk (shared -> global), one elected thread issuing, up to
+// kFillInFlight copies in flight -- a handful of instructions per 32 KB instead of 2048 128-bit stores.  The source tile is never
+// modified, so groups are only drained before the CTA exits.
+constexpr int kFillTileBytes = 32 * 1024;
+constexpr int kFillInFlight = 8;
+__global__ void __launch_bounds__(256)
+targets_fill_bulk_kernel(FillArgs a) {
+    __shared__ __align__(128) float tile[kFillTileBytes / 4];
+    const FillSeg s = a.seg[blockIdx.y];
+    for (int i = threadIdx.x; i < kFillTileBytes / 4; i += blockDim.x) tile[i] = s.v;
+    // unaligned head / tail elements (outputs of torch allocations are 256-byte aligned: normally none)
+    size_t head = ((16 - ((uintptr_t)s.p & 15)) & 15) / 4; if (head > s.n) head = s.n;
+    const size_t body = (s.n - head) / 4 * 4;                      // floats in whole 16-byte units
+    if (blockIdx.x == 0) {
+        for (size_t j = threadIdx.x; j < head; j += blockDim.x) s.p[j] = s.v;
+        for (size_t j = head + body + threadIdx.x; j < s.n; j += blockDim.x) s.p[j] = s.v;
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    // generic-proxy writes of the tile -> visible to the bulk-copy engine
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const size_t bytes = body * 4;
+        const size_t n_chunks = (bytes + kFillTileBytes - 1) / kFillTileBytes;
+        unsigned char* base = reinterpret_cast<unsigned char*>(s.p + head);
+        const uint32_t src = (uint32_t)__cvta_generic_to_shared(tile);
+        for (size_t c = blockIdx.x; c < n_chunks; c += gridDim.x) {
+            const size_t off = c * kFillTileBytes;
+            const uint32_t nb = (uint32_t)((bytes - off) < (size_t)kFillTileBytes ? (bytes - off) : (size_t)kFillTileBytes);
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(base + off), "r"(src), "r"(nb) : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(kFillInFlight - 1) : "memory");
+        }
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }
+}
 
 __global__ void __launch_bounds__(256)
 targets_fill_kernel(FillArgs a) {
@@ -45,7 +82,7 @@ struct TargetArgs {
     int N;                             // 3 * sum HW
 };
 
-constexpr int kTgtThreads = 128;
+constexpr int kTgtThreads = 256;
 constexpr int kTgtMaxM = 1024;
 
 __global__ void __launch_bounds__(kTgtThreads)
@@ -53,7 +90,8 @@ targets_scatter_kernel(TargetArgs a) {
     __shared__ int s_row[kTgtMaxM];
     __shared__ unsigned char s_match[kTgtMaxM];
     __shared__ unsigned char s_own[kTgtMaxM];
-    __shared__ int s_nv;
+    __shared__ unsigned short s_list[kTgtMaxM];
+    __shared__ int s_nv, s_cnt;
     const int b = blockIdx.x, tid = threadIdx.x;
     if (tid == 0) s_nv = a.M;
     __syncthreads();
@@ -134,19 +172,43 @@ targets_scatter_kernel(TargetArgs a) {
         a.obj[o] = a.mix ? a.mix[(size_t)b * a.M + m] : 1.0f;
     }
     __syncthreads();
-    // class rows of the owners, whole CTA per row (coalesced)
-    for (int m = 0; m < nv; ++m) {
-        int row = s_row[m];
-        if (row < 0 || !s_own[m]) continue;
-        float* crow = a.cls + ((size_t)b * a.N + row) * a.C;
-        if (a.ids_width == 1) {
-            int id = (int)a.gt_ids[(size_t)b * a.M + m];
-            if (id < 0) id += a.C;                                  // numpy negative index
-            for (int c = tid; c < a.C; c += kTgtThreads) crow[c] = (c == id) ? 1.0f : 0.0f;
-        } else {
-            const float* g = a.gt_ids + ((size_t)b * a.M + m) * a.C;
-            for (int c = tid; c < a.C; c += kTgtThreads) crow[c] = g[c];
+    // class rows of the owners.  (r1: the whole CTA walked the owners one after another, a dependent global load per row: 100 rows
+    // x ~1 us = a third of the step at C = 285.)  Now the owners are compacted and the (owner, 128-class chunk) items are spread
+    // over the warps, two items (8 independent coalesced loads per lane) in flight per warp.
+    if (tid == 0) {
+        int n = 0;
+        for (int m = 0; m < nv; ++m) if (s_row[m] >= 0 && s_own[m]) s_list[n++] = (unsigned short)m;
+        s_cnt = n;
+    }
+    __syncthreads();
+    const int warp = tid >> 5, lane = tid & 31, nw = kTgtThreads >> 5;
+    const int nchunk = (a.C + 127) >> 7, items = s_cnt * nchunk;
+    for (int it0 = warp * 2; it0 < items; it0 += nw * 2) {
+        float v[2][4]; float* dst[2]; int c0[2]; bool on[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int item = it0 + u;
+            on[u] = item < items;
+            const int i = on[u] ? item / nchunk : 0, j = on[u] ? item - i * nchunk : 0;
+            const int m = (int)s_list[i];
+            c0[u] = j * 128 + lane;
+            dst[u] = a.cls + ((size_t)b * a.N + s_row[m]) * a.C;
+            if (a.ids_width == 1) {
+                int id = (int)a.gt_ids[(size_t)b * a.M + m];
+                if (id < 0) id += a.C;                              // numpy negative index
+#pragma unroll
+                for (int q = 0; q < 4; ++q) v[u][q] = (c0[u] + 32 * q == id) ? 1.0f : 0.0f;
+            } else {
+                const float* g = a.gt_ids + ((size_t)b * a.M + m) * a.C;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) v[u][q] = (on[u] && c0[u] + 32 * q < a.C) ? __ldg(g + c0[u] + 32 * q) : 0.0f;
+            }
         }
+#pragma unroll
+        for (int u = 0; u < 2; ++u)
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                if (on[u] && c0[u] + 32 * q < a.C) dst[u][c0[u] + 32 * q] = v[u][q];
     }
 }
 
@@ -189,8 +251,14 @@ extern "C" int vd_prefetch_targets(int B, int M, int C, int orig_h, int orig_w, 
     f.seg[2] = {center, bn * 2, 0.0f};
     f.seg[3] = {scale, bn * 2, 0.0f};
     f.seg[4] = {weight, bn * 2, 0.0f};
-    int blocks = sm_count() * 8;
-    targets_fill_kernel<<<dim3(blocks, 5), 256, 0, stream>>>(f);
+    static const int fill_mode = []() { const char* e = getenv("VD_TARGETS_FILL"); return e ? atoi(e) : 1; }();   // 1: TMA bulk stores (default), 0: per-thread 128-bit streaming stores
+    if (fill_mode == 1) {
+        // the class tensor is ~98 % of the bytes: give every SM several CTAs there (6 x 32 KB tiles fit an SM), one wave on the small segments
+        targets_fill_bulk_kernel<<<dim3(sm_count() * 4, 5), 256, 0, stream>>>(f);
+    } else {
+        int blocks = sm_count() * 8;
+        targets_fill_kernel<<<dim3(blocks, 5), 256, 0, stream>>>(f);
+    }
     VD_LAUNCH_CHECK();
     if (M > 0) {
         targets_scatter_kernel<<<B, kTgtThreads, 0, stream>>>(a);

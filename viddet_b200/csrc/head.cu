@@ -40,7 +40,10 @@ constexpr int kEpiThreads = 128;
 constexpr int A_TILE_BYTES = BLOCK_M * BLOCK_K * 2;
 
 enum { EPI_FILTER = 0, EPI_DET = 1, EPI_PRED = 2, EPI_SPEC = 3 };
-constexpr int kSpecCap = 2048;                // candidates per frame the speculative path may emit
+#ifndef VD_SPEC_CAP
+#define VD_SPEC_CAP 1024      // r02: 1024 keys (8 KB of the NMS CTA's shared memory instead of 16) let the head kernel take 200 KB = 7 ring stages while
+#endif                        // the NMS CTA of the previous launch still shares the SM: 33.5 -> 32.5 us per step; 2048 + 181 KB was r01's choice
+constexpr int kSpecCap = VD_SPEC_CAP;         // candidates per frame the speculative path may emit (multiple of 512)
 #ifndef VD_SPEC_G
 #define VD_SPEC_G 3
 #endif
@@ -133,7 +136,7 @@ template <int EPI, int C, int NPAD> struct HeadCfg {
     static constexpr int EPI_BYTES = LIST_BYTES + CBIAS_BYTES + CONF_BYTES + VD_MAX_SCALES * NPAD * 4 + kHeadSharedBytes;
     // EPI_FILTER leaves ~45 KB of the SM's shared memory to a co-resident nms_final_hist_kernel CTA of the previous batch
     #ifndef VD_SPEC_SMEM_KB
-#define VD_SPEC_SMEM_KB 181
+#define VD_SPEC_SMEM_KB 200
 #endif
 #ifndef VD_SPEC_SMEM_KB_WIDE
 #define VD_SPEC_SMEM_KB_WIDE VD_SPEC_SMEM_KB
@@ -1458,6 +1461,7 @@ nms_spec_kernel(const uint64_t* __restrict__ spec_lists, uint32_t* __restrict__ 
         return;
     }
     VD_STAMP(P, 2);
+    static_assert(kSpecCap == 1024 || kSpecCap == 2048, "kSpecCap");
     const int SN = cnt <= 512u ? 512 : (cnt <= 1024u ? 1024 : 2048);
     for (int i = (int)cnt + tid; i < SN; i += blockDim.x) skeys[i] = 0ull;
     __syncthreads();
@@ -1468,7 +1472,8 @@ nms_spec_kernel(const uint64_t* __restrict__ spec_lists, uint32_t* __restrict__ 
     if (tid == 0) {
         uint32_t d = floor_b;
         if (cnt >= (uint32_t)k) {
-            const uint32_t r = min(cnt - 1u, (uint32_t)(2 * k));            // aim at ~2k candidates: room for the next frame in this slot to differ both ways
+            // aim at ~2k candidates (1.5k when the list holds <= 1024): room for the next frame in this slot to differ both ways
+            const uint32_t r = min(cnt - 1u, (uint32_t)(kSpecCap >= 2048 ? 2 * k : (3 * k) / 2));
             const uint32_t bits = (uint32_t)(skeys[r] >> 32) & 0x7fffffffu;
             d = bits > floor_b + 65536u ? bits - 65536u : floor_b;          // ~0.8 % lower
         }

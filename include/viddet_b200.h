@@ -58,7 +58,8 @@ int vd_device_info(int device, int* sm_count, int* cc_major, int* cc_minor);
  * yolo3_temporal.py:545-547.  data/out: (num_batch, num_elem, width) fp32 (leading dims
  * flattened by the caller); record_or_null: (num_batch, num_elem) int32 = MXNet's hidden second
  * output (original row of each kept element, -1 elsewhere).  in/out_format: 0 corner, 1 center.
- * topk <= 0 means num_elem; min(topk, num_elem) must be <= VD_MAX_TOPK.
+ * topk <= 0 means num_elem (MXNet's default -1).  Up to VD_MAX_TOPK candidates per image run in shared memory (the reference's call
+ * sites: topk = 400); more take the general path (global-memory sort + workspace-resident NMS, O(n * kept) like the operator itself).
  * ------------------------------------------------------------------------------------------ */
 size_t vd_box_nms_workspace_bytes(int64_t num_batch, int64_t num_elem, int width, int topk);
 int vd_box_nms(const float* data, int64_t num_batch, int64_t num_elem, int width,

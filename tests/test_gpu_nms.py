@@ -103,10 +103,22 @@ def test_full_size_voc_rows_properties():
         assert (np.diff(kept[b, :n[b], 1]) <= 0).all()                                  # sorted by score
 
 
+@pytest.mark.parametrize("N,topk,B", [(1500, -1, 2), (3000, -1, 3), (5000, 2000, 2), (2049, 0, 1), (9000, 4096, 1)])
+@pytest.mark.parametrize("force", [False, True])
+def test_more_than_max_topk_candidates(N, topk, B, force):
+    """MXNet's default topk = -1 (or a large explicit topk) on inputs longer than VD_MAX_TOPK rows: the general path (global
+    bitonic sort + workspace-resident wavefront NMS) must give the oracle's rows and records bit for bit, ties included."""
+    rng = np.random.RandomState(N + (topk if topk > 0 else 7) + force)
+    d = random_dets(rng, B, N, num_class=5, tie_frac=0.2)
+    check(d, overlap_thresh=0.45, valid_thresh=0.01, topk=topk, id_index=0, score_index=1, coord_start=2, force_suppress=force)
+    if not force:
+        check(d, overlap_thresh=0.45, valid_thresh=0.01, topk=topk, id_index=0, background_id=2)
+        check(d, overlap_thresh=0.6, valid_thresh=-1.0, topk=topk, id_index=-1)                    # no id column, everything valid
+        d[..., 1] = 0.25                                                                            # all scores tie: order = row index
+        check(d, overlap_thresh=0.45, valid_thresh=0.01, topk=topk, id_index=0)
+
+
 def test_errors():
     import viddet_b200
-    d = torch.zeros((1, 5000, 6), device="cuda")
-    with pytest.raises(viddet_b200.VidDetError):
-        viddet_b200.box_nms(d, topk=-1)                 # k = 5000 > VD_MAX_TOPK
     with pytest.raises(viddet_b200.VidDetError):
         viddet_b200.box_nms(torch.zeros((1, 10, 6)))    # CPU tensor: no fallback

@@ -293,6 +293,113 @@ __device__ void nms_final_body(const uint64_t* __restrict__ lists, const uint32_
 }
 
 
+// Steps 3-6 of the per-image NMS as used by the fused head (head.cu) and by box_nms with more than VD_MAX_TOPK candidates (nms.cu): class-aware greedy NMS as a WAVEFRONT over 32-rank chunks, with no
+// n x n matrix and no class sort.  Only KEPT boxes ever suppress and the scan stops once max_out boxes are kept, so a
+// chunk's members are tested just in time against the (< max_out + 32) boxes kept so far:
+//   round c, test phase (all warps):  lane = member of chunk c; warp w tests it against kept boxes w, w+8, ... and
+//       against rows 4w..4w+3 of the chunk itself (one ballot per row = the chunk's 32x32 "diagonal" block)
+//   round c, resolve phase (warp 0):  greedy rank-order resolution of the chunk in registers, survivors are emitted
+//       straight to the output and appended to the kept list
+// Semantics = nms_core.cuh::nms_tail (rank order, IoU > thresh, same class, first max_out survivors), same IoU arithmetic.
+constexpr int kNmsThreads = 256;
+struct WaveShared { uint32_t kept_total; uint32_t sup; uint32_t diag[32]; };
+template <class Source, class Sink>
+__device__ void nms_tail_wave(const int n, const int f, const NmsParams P, const Source& src, const Sink& sink,
+                              const uint64_t* skeys, float4* sbox, int* scls, float* sarea,
+                              float4* skbox, float* skarea, int* skcls, WaveShared* wsh) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    const int NB = (n + 31) >> 5;
+    const float thr = P.overlap_thresh;
+    VD_STAMP(P, 4);
+    for (int r = tid; r < n; r += blockDim.x) {
+        float4 bx; int c; float ar;
+        src.load(f, key_row(skeys[r]), key_score(skeys[r]), bx, c, ar);
+        sbox[r] = bx; scls[r] = c; sarea[r] = ar;
+    }
+    if (tid == 0) { wsh->kept_total = 0u; wsh->sup = 0u; }
+    __syncthreads();
+    VD_STAMP(P, 5);
+    uint32_t kept_total = 0u;
+    for (int c = 0; c < NB; ++c) {
+        // ---- test phase
+        const int pm = 32 * c + lane;
+        const bool valid = pm < n;
+        float4 bm = make_float4(0.f, 0.f, 0.f, 0.f); float am_ = 0.f; int cm = -2;
+        if (valid) { bm = sbox[pm]; am_ = sarea[pm]; cm = scls[pm]; }
+        {
+            bool sup = false;
+            for (uint32_t i0 = (uint32_t)warp; i0 < kept_total; i0 += 4u * (uint32_t)nwarps) {     // kept list is padded with never-matching entries
+                bool sp[4], am[4]; bool any_amb = false;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const uint32_t i = i0 + (uint32_t)(u * nwarps);
+                    sp[u] = vd_iou_gt_fast(skbox[i], skarea[i], bm, am_, thr, am[u]);
+                    const bool same = skcls[i] == cm;
+                    sp[u] &= same; am[u] &= same; any_amb |= am[u];
+                }
+                if (__builtin_expect(any_amb, 0)) {
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) { const uint32_t i = i0 + (uint32_t)(u * nwarps); if (am[u]) sp[u] = vd_iou_gt(skbox[i], skarea[i], bm, am_, thr); }
+                }
+                sup |= sp[0] | sp[1] | sp[2] | sp[3];
+            }
+            const unsigned sw = __ballot_sync(0xffffffffu, sup);
+            if (lane == 0 && sw) atomicOr(&wsh->sup, sw);
+            // rows 4w .. 4w+3 of the chunk's own block (row = earlier rank, lane = later rank)
+            bool sp[4], am[4]; bool any_amb = false;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int rr = 4 * warp + u, pr = min(32 * c + rr, n - 1);
+                sp[u] = vd_iou_gt_fast(sbox[pr], sarea[pr], bm, am_, thr, am[u]);
+                const bool rel = (lane > rr) & (scls[pr] == cm) & (32 * c + rr < n);
+                sp[u] &= rel; am[u] &= rel; any_amb |= am[u];
+            }
+            if (__builtin_expect(any_amb, 0)) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) { const int pr = min(32 * c + 4 * warp + u, n - 1); if (am[u]) sp[u] = vd_iou_gt(sbox[pr], sarea[pr], bm, am_, thr); }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const unsigned bal = __ballot_sync(0xffffffffu, sp[u]);
+                if (lane == 0) wsh->diag[4 * warp + u] = bal;
+            }
+        }
+        __syncthreads();
+        // ---- resolve phase
+        if (warp == 0) {
+            uint32_t cur = wsh->sup | (valid ? 0u : 0u);
+            cur |= ~__ballot_sync(0xffffffffu, valid);                 // ranks past n never survive
+            const uint32_t diag = wsh->diag[lane];
+#pragma unroll
+            for (int j0 = 0; j0 < 32; j0 += 8) {
+                uint32_t d[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) d[j] = __shfl_sync(0xffffffffu, diag, j0 + j);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) if (!((cur >> (j0 + j)) & 1u)) cur |= d[j];
+            }
+            const uint32_t alive = ~cur;
+            const uint32_t cnt = (uint32_t)__popc(alive);
+            const uint32_t slot = kept_total + (uint32_t)__popc(alive & ((1u << lane) - 1u));
+            if ((alive >> lane) & 1u) {
+                if (slot < (uint32_t)P.max_out) sink.emit(f, (int)slot, key_row(skeys[pm]), key_score(skeys[pm]), bm, cm);
+                VD_DEV_CHECK(slot < (uint32_t)((P.max_out < P.k ? P.max_out : P.k) + 32));
+                skbox[slot] = bm; skarea[slot] = am_; skcls[slot] = cm;
+            }
+            // pad the list to the test loop's stride with entries that match no class
+            const uint32_t padded = (kept_total + cnt + 4u * (uint32_t)nwarps);
+            for (uint32_t i = kept_total + cnt + (uint32_t)lane; i < padded; i += 32u) skcls[i] = -3;
+            if (lane == 0) { wsh->kept_total = kept_total + cnt; wsh->sup = 0u; }
+        }
+        __syncthreads();
+        kept_total = wsh->kept_total;
+        if (kept_total >= (uint32_t)P.max_out) break;
+    }
+    VD_STAMP(P, 8);
+    sink.finish(f, (int)kept_total < P.max_out ? (int)kept_total : P.max_out);
+    VD_STAMP(P, 9);
+}
+
 // Intermediate level: merge <= 8 lists into one list holding a superset (<= kListCap) of their
 // joint top-k.  grid (n_groups, num_batch).
 static __global__ void __launch_bounds__(kFinalThreads, 1)

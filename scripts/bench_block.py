@@ -116,9 +116,16 @@ def neck():
         fl += sum(2.0 * c.kernel[0] * c.kernel[1] * c.kernel[2] * B * h * h * c.in_channels * c.channels for c in blk.cells())
     fl += 2.0 * B * (13 * 13 * 512 * 256 + 26 * 26 * 256 * 128)                       # transitions
     fl += 2.0 * B * 75 * (13 * 13 * 1024 + 26 * 26 * 512 + 52 * 52 * 256)             # prediction convs
-    print(json.dumps({"neck": "routes -> detections", "frames": B, "ms": round(ms, 4), "frames_per_s": round(B / ms * 1e3, 1),
+    print(json.dumps({"neck": "routes -> detections (20 calls captured into one graph by the benchmark)", "frames": B, "ms": round(ms, 4), "frames_per_s": round(B / ms * 1e3, 1),
                       "tflops": round(fl / ms / 1e9, 1), "frac_tensor_peak": round(fl / ms / 1e9 / PEAK_TC, 3),
                       "gflop_per_frame": round(fl / B / 1e9, 2)}))
+    sess = nk.session(routes)                        # the same forward as ONE CUDA graph
+    ms = timeit_eager(lambda i: sess.replay(), n=20, warm=3)
+    ms_eager = timeit_eager(lambda i: nk(routes), n=20, warm=3)
+    print(json.dumps({"neck": "routes -> detections (product API called eagerly: 22 launches + per-call torch.empty, host-bound)", "frames": B, "ms": round(ms_eager, 4),
+                      "frames_per_s": round(B / ms_eager * 1e3, 1)}))
+    print(json.dumps({"neck": "routes -> detections (NeckSession: one CUDA graph)", "frames": B, "ms": round(ms, 4), "frames_per_s": round(B / ms * 1e3, 1),
+                      "tflops": round(fl / ms / 1e9, 1), "frac_tensor_peak": round(fl / ms / 1e9 / PEAK_TC, 3)}))
 
 
 if __name__ == "__main__":

@@ -128,3 +128,28 @@ def test_conv_errors_surface():
         c(torch.zeros(1, 64, 4, 4, device="cuda"))           # Cout not a multiple of 128
     with pytest.raises(AssertionError):
         viddet_b200.ConvBNLReLU(64, 128, 5)
+
+
+def test_neck_session_graph_equals_eager():
+    """YOLOV3Neck.session(): the whole forward after the backbone stages as ONE CUDA graph; replays reproduce the eager call bit
+    for bit (also after refilling the static inputs), and the head's thresholds survive between replays (no frame redone)."""
+    import viddet_b200
+    g = torch.Generator().manual_seed(5)
+    nk = viddet_b200.YOLOV3Neck(20, channels=(128, 128, 128), stage_channels=(64, 128, 192)).initialize(generator=g)
+    mk = lambda seed: [torch.randn(3, c, 128 // s, 128 // s, device="cuda", generator=torch.Generator(device="cuda").manual_seed(seed + s))
+                       .to(torch.bfloat16).contiguous(memory_format=torch.channels_last) for c, s in zip((64, 128, 192), (8, 16, 32))]
+    r0, r1 = mk(1), mk(2)
+    e0 = [t.clone() for t in nk(r0)]
+    e1 = [t.clone() for t in nk(r1)]
+    sess = nk.session(r0)
+    for rep in range(2):
+        out = sess.replay()
+        torch.cuda.synchronize()
+        for a, b in zip(out, e0):
+            assert torch.equal(a.view(torch.int32), b.view(torch.int32))
+    for dst, src in zip(sess.routes, r1):
+        dst.copy_(src)
+    out = sess.replay()
+    torch.cuda.synchronize()
+    for a, b in zip(out, e1):
+        assert torch.equal(a.view(torch.int32), b.view(torch.int32))

@@ -614,3 +614,35 @@ def test_clip_windows_equal_materialised_windows_bit_exact():
         assert torch.equal(e, ref)
     ids3, _, _ = head(ends)
     assert ids3.shape == (4, T, 100, 1)
+
+
+def test_grouped_launch_equals_separate_batches():
+    """bench.py hands ONE head-kernel launch several consecutive batches of the resident pool (frames = group x batch: the
+    kernel's launch / prologue / tail is paid once per group).  The grouped call must return exactly what the batches return
+    one by one, cold and steady, and through the pipeline graph with rotating inputs."""
+    import viddet_b200
+    rng = np.random.RandomState(23)
+    C, B, G, size = 20, 6, 4, 320
+    ws, bs = make_pred_weights(rng, C, bias_scale=0.1)
+    head = build_head(C, ws, bs)
+    head.set_nms(0.45, 400, 100)
+    big = [viddet_b200.to_nhwc_bf16(cuda(t)) for t in make_tips(rng, 3 * G * B, size=size)]      # pool of 3 groups, contiguous per scale
+    singles = [[t[i * B:(i + 1) * B] for t in big] for i in range(3 * G)]
+    ref = [[x.clone() for x in head(s, return_keep=True)] for s in singles]
+    groups = [[t[g * G * B:(g + 1) * G * B] for t in big] for g in range(3)]
+    for g, tips in enumerate(groups):
+        for call in range(2):
+            ids, scores, boxes, keep = head(tips, return_keep=True)
+            for i in range(G):
+                r = ref[g * G + i]
+                sl = slice(i * B, (i + 1) * B)
+                assert torch.equal(keep[sl], r[3]), (g, call, i)
+                assert torch.equal(scores[sl].view(torch.int32), r[1].view(torch.int32))
+                assert torch.equal(boxes[sl].view(torch.int32), r[2].view(torch.int32))
+    sessions = [head.session(groups[j], return_keep=True) for j in range(2)]
+    pipe = viddet_b200.HeadPipeline(sessions, steps=3, inputs=groups)              # step i: group i, session i % 2
+    pipe.cycle(); pipe.cycle()
+    torch.cuda.synchronize()
+    for j, g in ((0, 2), (1, 1)):                                                   # last group each session processed
+        for i in range(G):
+            assert torch.equal(sessions[j].keep[i * B:(i + 1) * B], ref[g * G + i][3]), (j, i)

@@ -5,7 +5,7 @@ the C ABI in include/viddet_b200.h; torch tensors are carriers only.  There is n
 """
 from ._lib import VidDetError, load, SO_PATH  # noqa: F401
 from .blocks import (  # noqa: F401
-    ClassTree, ConvBNLReLU, DEFAULT_ANCHORS, DEFAULT_CHANNELS, DEFAULT_STRIDES, HeadPipeline, HeadSession, TemporalPooling, TemporalTipConv, TimeDistributed,
+    ClassTree, ConvBNLReLU, DEFAULT_ANCHORS, DEFAULT_CHANNELS, DEFAULT_STRIDES, HeadPipeline, HeadSession, NeckSession, TemporalPooling, TemporalTipConv, TimeDistributed,
     YOLODetectionBlockV3, YOLOOutputV3, YOLOV3DynamicTargetGeneratorSimple, YOLOV3Head, YOLOV3Loss, YOLOV3Neck, YOLOV3PrefetchTargetGenerator, YOLOV3TargetMerger,
     ClipWindows, SplitF32, materialise_windows, window_frame_indices, box_nms, hierarchical_nms, postprocess_detections, to_nhwc_bf16, to_nhwc_split, upsample_concat,
 )

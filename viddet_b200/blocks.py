@@ -1187,6 +1187,43 @@ class YOLOV3Neck:
         """The (B, rows, 6) tensor `concat(all_detections)` holds at yolo3.py:523."""
         return self.head.detections(self.tips(routes))
 
+    def session(self, routes):
+        """Bind routes once and record the whole forward (19-28 conv cells, the glue kernels, the fused head) into ONE CUDA graph:
+        `NeckSession.replay()` is a single launch with no per-call Python, allocation or tensor-map work."""
+        return NeckSession(self, routes)
+
+
+class NeckSession:
+    """A YOLOV3Neck forward with static inputs (`routes`: refill with copy_), static outputs (`ids`, `scores`, `bboxes`) and
+    every intermediate activation owned by the graph's memory pool.  The warm-up and the capture run on the same private stream,
+    so the head's workspace (its thresholds live there between replays) is the one created during the warm-up, not a buffer the
+    graph would re-zero."""
+
+    def __init__(self, neck, routes):
+        self.neck = neck
+        self.routes = []
+        for r in routes:
+            _require_cuda(r, "route")
+            if r.dim() == 4:
+                self.routes.append(to_nhwc_bf16(r).clone(memory_format=torch.preserve_format))
+            else:                                           # (B,T,C,H,W): channels-last per frame
+                B, T = r.shape[0], r.shape[1]
+                f = to_nhwc_bf16(r.reshape((B * T,) + tuple(r.shape[2:]))).clone(memory_format=torch.preserve_format)
+                self.routes.append(f.reshape((B, T) + tuple(f.shape[1:])))
+        self._stream = torch.cuda.Stream()
+        self._stream.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(self._stream):
+            for _ in range(2):                              # function attributes, workspace, thresholds
+                neck(self.routes)
+        self._stream.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph, stream=self._stream):
+            self.ids, self.scores, self.bboxes = neck(self.routes)
+
+    def replay(self):
+        self.graph.replay()
+        return self.ids, self.scores, self.bboxes
+
 
 def postprocess_detections(ids, scores, bboxes, size):
     """detect_yolo3.py:222-261 on device: clip boxes to [0, size], keep rows with id >= 0 (order preserved), divide the

@@ -204,6 +204,8 @@ int vd_head_forward_stages(const VdHeadParams* p, float* ids, float* scores, flo
  * state; all frames on the first call); word [5] = running total of such frames and word [6] = running total of completed
  * calls on this workspace (both wrap; take differences).  For tests and monitoring; reading needs a stream synchronisation. */
 size_t vd_head_stats_offset(const VdHeadParams* p);
+/* Byte offset of the profiling-stamp area inside the workspace (VD_DEBUG_HEAD_STAMPS=1: per-tile clock64 of CTA 0; scripts/spec_stamps.py). */
+size_t vd_head_debug_offset(const VdHeadParams* p);
 /* Number of kernels one vd_head_forward call launches for these parameters (-1 on bad params). */
 int vd_head_launch_count(const VdHeadParams* p);
 /* Same conv + decode, but materialises the reference's (frames, rows, 6) detection tensor

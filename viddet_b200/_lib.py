@@ -73,6 +73,7 @@ SIGNATURES = {
     "vd_head_forward_stages": (_i, [ctypes.POINTER(VdHeadParams), _vp, _vp, _vp, _vp, _vp, _sz, _vp, _i]),
     "vd_head_launch_count": (_i, [ctypes.POINTER(VdHeadParams)]),
     "vd_head_stats_offset": (_sz, [ctypes.POINTER(VdHeadParams)]),
+    "vd_head_debug_offset": (_sz, [ctypes.POINTER(VdHeadParams)]),
     "vd_head_detections": (_i, [ctypes.POINTER(VdHeadParams), _vp, _vp, _sz, _vp]),
     "vd_ipc_alloc": (_i, [_sz, ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_ubyte)]),
     "vd_ipc_open": (_i, [ctypes.POINTER(ctypes.c_ubyte), ctypes.POINTER(ctypes.c_void_p)]),

@@ -131,7 +131,11 @@ template <int EPI, int C, int NPAD> struct HeadCfg {
     // SPLIT-th class chunk (the epilogue, not the mainloop, bounds these heads: 240 class logits per pixel at C = 80)
     static constexpr int SPLIT = (EPI == EPI_SPEC && TMEM_STRIDE == 256) ? VD_SPEC_SPLIT : 1;
     static constexpr int THREADS = kEpiWarp0 * 32 + G * SPLIT * kEpiThreads;
+#ifdef VD_SPEC_MAXREG
+    static constexpr int MAXREG = (EPI == EPI_SPEC) ? VD_SPEC_MAXREG : ((THREADS > 448) ? 80 : ((THREADS > 320) ? 96 : 128));   // tuning knob
+#else
     static constexpr int MAXREG = (THREADS > 448) ? 80 : ((THREADS > 320) ? 96 : 128);
+#endif
     static constexpr int LIST_BYTES = (EPI == EPI_SPEC) ? G * SPLIT * 4 * 2 * kSpecStage * 8 : G * LIST_BUFS * kListCap * 8;
     static constexpr int EPI_BYTES = LIST_BYTES + CBIAS_BYTES + CONF_BYTES + VD_MAX_SCALES * NPAD * 4 + kHeadSharedBytes;
     // EPI_FILTER leaves ~45 KB of the SM's shared memory to a co-resident nms_final_hist_kernel CTA of the previous batch
@@ -453,7 +457,7 @@ head_kernel(const __grid_constant__ HeadMaps maps, const __grid_constant__ HeadK
             const bool inb = cell < HW;
             const float gx = (float)(cell % Wd), gy = (float)(cell / Wd);
             const float* bias = sbias + s * NPAD;
-            const bool stamp = (EPI == EPI_FILTER) && p.stamps && blockIdx.x == 0 && et == 0 && it < 250u;
+            const bool stamp = (EPI == EPI_FILTER || EPI == EPI_SPEC) && p.stamps && blockIdx.x == 0 && et == 0 && it < 250u;
             if (stamp) p.stamps[it * 16 + 3] = clock64();
             // global reads of the selection issued before the wait for the accumulator (their latency hides behind it)
             uint32_t pf_c0 = 0u, pf_c1 = 0u, pf_hint = 0u;
@@ -594,6 +598,7 @@ head_kernel(const __grid_constant__ HeadMaps maps, const __grid_constant__ HeadK
                 // exact top-k); frames that fail are redone by the exact EPI_FILTER path.  Same conservative logit
                 // prefilter as there: x >= logit(tau/conf) - margin  <=  score >= tau.
                 constexpr int CH = Cfg::CH, CPA = Cfg::CPA, CH4 = Cfg::CH4, REM = C - (CPA - 1) * CH;
+                if (stamp) p.stamps[it * 16 + 8] = clock64();          // box part done
                 if (p.dbg == 7) { tc::fence_before_sync(); __syncwarp(); if (lane == 0) tc::mbar_arrive(&sh->tmem_empty[buf]); continue; }   // debug: box part only
                 const float vth = p.dbg == 9 ? 2.0f : p.valid_thresh;                 // debug 9: nothing is ever emitted
                 const float* cbias = scbias + s * (3 * CPA * CH4);
@@ -704,6 +709,7 @@ head_kernel(const __grid_constant__ HeadMaps maps, const __grid_constant__ HeadK
                     }
                 }
                 }
+                if (stamp) p.stamps[it * 16 + 10] = clock64();         // class loop done
                 tc::fence_before_sync();
                 __syncwarp();
                 if (lane == 0) tc::mbar_arrive(&sh->tmem_empty[buf]);
@@ -714,6 +720,7 @@ head_kernel(const __grid_constant__ HeadMaps maps, const __grid_constant__ HeadK
                 if (lane == 0) { *wc = 0u; if (wn) spec_pend_base = atomicAdd(fc, wn); }
                 spec_pend_n = wn; spec_pend_f = f; spec_par ^= 1u;
                 __syncwarp();
+                if (stamp) p.stamps[it * 16 + 7] = clock64();
                 continue;
             }
 
@@ -1668,6 +1675,12 @@ extern "C" size_t vd_head_workspace_bytes(const VdHeadParams* p) {
     HeadPlan pl;
     if (make_plan(p, &pl) != VD_OK) return 0;
     return pl.total;
+}
+
+extern "C" size_t vd_head_debug_offset(const VdHeadParams* hp) {
+    HeadPlan pl;
+    if (make_plan(hp, &pl) != VD_OK) return 0;
+    return pl.off_listsA;
 }
 
 extern "C" size_t vd_head_stats_offset(const VdHeadParams* hp) {

@@ -228,6 +228,19 @@ def synth_video_pool(torch, gen, n, frames, size, device, outs, rho=0.95):
         z = zs
 
 
+_FULL_AFFINITY = os.sched_getaffinity(0) if hasattr(os, "sched_getaffinity") else None
+
+
+def unpin():
+    """Give the process its original CPU set back (the CPU baseline leg uses every host core the box offers)."""
+    if _FULL_AFFINITY is not None:
+        try:
+            os.sched_setaffinity(0, _FULL_AFFINITY)
+        except OSError:
+            pass
+    return len(_FULL_AFFINITY) if _FULL_AFFINITY is not None else (os.cpu_count() or 1)
+
+
 def pin_to_gpu_numa(index):
     """Bind this process to the CPUs next to its GPU before any pinned host buffer is allocated (NUMA-local staging)."""
     try:
@@ -773,7 +786,7 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         import numpy as np
         from oracle import cpu_baseline
-        threads = os.cpu_count() or 1
+        threads = unpin()
         rng = np.random.RandomState(1234)
         if temporal:
             data = cpu_baseline.make_temporal_sample(rng, 2, TEMPORAL_T, C, size)

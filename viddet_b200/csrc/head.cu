@@ -1374,7 +1374,10 @@ nms_spec_kernel(const uint64_t* __restrict__ spec_lists, uint32_t* __restrict__ 
         uint32_t d = floor_b;
         if (cnt >= (uint32_t)k) {
             // aim at ~2k candidates (1.5k when the list holds <= 1024): room for the next frame in this slot to differ both ways
-            const uint32_t r = min(cnt - 1u, (uint32_t)(kSpecCap >= 2048 ? 2 * k : (3 * k) / 2));
+#ifndef VD_SPEC_TARGET_PCT
+#define VD_SPEC_TARGET_PCT (kSpecCap >= 2048 ? 200 : 150)
+#endif
+            const uint32_t r = min(cnt - 1u, (uint32_t)((VD_SPEC_TARGET_PCT * k) / 100));
             const uint32_t bits = (uint32_t)(skeys[r] >> 32) & 0x7fffffffu;
             d = bits > floor_b + 65536u ? bits - 65536u : floor_b;          // ~0.8 % lower
         }

@@ -88,6 +88,7 @@ struct HeadKernelParams {
     // class windows (any num_class on the compiled shapes): this launch covers classes [c_off, c_off + c_valid) of c_total; the
     // kernel's own class index c (0 .. C-1 of its template shape) is class c_off + c of the head; c >= c_valid are padding
     int c_off, c_valid, n_pass, pass;
+    int prefetch;                        // tiles the producer claims ahead and prefetches into L2 (0: off)
     const float* bias[VD_MAX_SCALES];
     // EPI_FILTER
     float4* boxes; uint64_t* lists; uint32_t* counts; float valid_thresh; int k, cap;
@@ -314,12 +315,33 @@ head_kernel(const __grid_constant__ HeadMaps maps, const __grid_constant__ HeadK
                 const uint32_t t = dyn ? atomicAdd(p.tile_counter, 1u) : (uint32_t)blockIdx.x + i * gridDim.x;
                 return t < total_tiles ? (int)t : -1;
             };
-            int next = claim(0u), n_end = 0;
+            // Tiles are claimed D + 1 ahead; the activations of the farthest one are prefetched into L2 (cp.async.bulk.prefetch.tensor):
+            // the shared-memory ring bounds the bytes in flight per SM (7 x 16 KB), the L2 prefetch of whole tiles lifts that bound
+            // without shared memory.  D = 0: claim one ahead, no prefetch (r01 behaviour).
+            const int D = (p.prefetch > 0 && !p.split) ? (p.prefetch < 3 ? p.prefetch : 3) : 0;
+            auto prefetch_tile = [&](int t) {
+                if (t < 0) return;
+                int s2, f2, pb2; tile_coords(p, t, s2, f2, pb2);
+                for (int kf2 = 0; kf2 < p.K_frames; ++kf2)
+                    for (int c2 = 0; c2 < p.cin[s2]; c2 += BLOCK_K) tc::tma_prefetch_4d(&maps.a[s2], c2, pb2 * BLOCK_M, kf2, f2);
+            };
+            uint32_t nclaim = 0u;
+            const int QN = D > 1 ? D : 1;                           // tiles held at the top of an iteration: q[0] = the next to run
+            int q[4] = {-1, -1, -1, -1};
+            for (int i = 0; i < QN; ++i) {
+                q[i] = (i == 0 || q[i - 1] >= 0) ? claim(nclaim++) : -1;
+                if (D > 0 && i > 0) prefetch_tile(q[i]);
+            }
+            int n_end = 0;
             for (uint32_t it = 0;; ++it) {
                 const uint32_t slot = it % kSchedSlots;
                 tc::mbar_wait(&sh->sched_empty[slot], ((it / kSchedSlots) & 1u) ^ 1u);
-                const int tile = next;
-                if (tile >= 0) next = claim(it + 1u);               // in flight while this tile's loads are issued
+                const int tile = q[0];
+                if (tile >= 0) {                                    // shift the queue; the new claim is in flight while this tile's loads are issued
+                    for (int i = 0; i + 1 < QN; ++i) q[i] = q[i + 1];
+                    q[QN - 1] = claim(nclaim++);
+                    if (D > 0) prefetch_tile(q[QN - 1]);
+                }
                 sh->sched_tile[slot] = tile;
                 tc::mbar_arrive(&sh->sched_full[slot]);
                 if (tile < 0) { if (++n_end == G) break; continue; }   // one terminator per epilogue group
@@ -1744,6 +1766,7 @@ extern "C" int vd_head_forward_stages(const VdHeadParams* hp, float* ids, float*
     uint32_t* failed = (uint32_t*)(ws + pl.off_failed);
     const bool spec = getenv("VD_NO_SPEC") == nullptr;   // speculative frame-level threshold with the exact path as fallback
     kp.valid_thresh = hp->valid_thresh; kp.k = k; kp.cap = (k <= 448) ? 640 : kListCap;
+    { const char* e = getenv("VD_HEAD_PREFETCH"); kp.prefetch = e ? atoi(e) : 0; }
     kp.stamps = getenv("VD_DEBUG_HEAD_STAMPS") ? (long long*)(ws + pl.off_listsA) : nullptr;   // profiling aid (unused merge area)
     if (const char* e = getenv("VD_DEBUG_SKIP_EPILOGUE")) kp.dbg = atoi(e);     // profiling aid: results are garbage
 

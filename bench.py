@@ -627,10 +627,12 @@ def main():
     st1 = [s.stats() for s in sessions]
     redone = sum(((b[0] - a[0]) & 0xffffffff) for a, b in zip(st0, st1))
     calls = sum(((b[1] - a[1]) & 0xffffffff) for a, b in zip(st0, st1))
+    ms_per_rank = [ms]
     if world > 1:
-        t = torch.tensor([ms], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
+        allms = torch.zeros((world,), device=dev)
+        dist.all_gather_into_tensor(allms, torch.tensor([ms], device=dev))
+        ms_per_rank = [float(v) for v in allms.tolist()]
+        ms = max(ms_per_rank)                              # the job's time = the slowest rank's
     value = world * frames * args.steps / (ms * 1e-3)
     gather_verified = None
     if peer is not None:                                  # outside the timed region: every rank's slot of MY buffer == what that rank holds
@@ -822,7 +824,8 @@ def main():
                                         "frames_redone_per_step": redone / max(calls * group, 1), "steps_counted": calls * group,
                                         "all_frames_fail_worst_case": allfail},
                         "sharding": ("%s split by rank; gather = %s" % ("clips" if temporal else "frames", gather_kind)) if world > 1 else "single GPU",
-                        "gather_verified": gather_verified, "numa_pinned": numa},
+                        "gather_verified": gather_verified, "numa_pinned": numa,
+                        "timed_region_ms_per_rank": [round(v, 4) for v in ms_per_rank]},
             "roofline": roof,
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": unit, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

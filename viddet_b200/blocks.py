@@ -916,7 +916,7 @@ class HeadPipeline:
     waits for its previous NMS kernel.  `cycle()` = rotations * len(sessions) steps; every batch is complete
     when the graph has finished."""
 
-    def __init__(self, sessions, rotations=2, steps=None, inputs=None):
+    def __init__(self, sessions, rotations=2, steps=None, inputs=None, overlap_head=False):
         """steps: batches per graph (default rotations * len(sessions); any count >= 1: step i runs on session i % len).
         inputs: optional list of resident input sets (each a list of channels-last bf16 tips of the sessions' shapes); step i
         then reads inputs[i % len(inputs)] while using session i % len(sessions)'s workspace and outputs -- every threshold the
@@ -925,26 +925,40 @@ class HeadPipeline:
         self.sessions = list(sessions)
         steps = rotations * len(self.sessions) if steps is None else int(steps)
         assert steps >= 1
-        self._streams = [torch.cuda.Stream() for _ in range(2)]
+        # overlap_head (temporal heads): the tip-cell kernels get their own stream, so the HBM-bound head kernel of step i runs beside
+        # the tensor-bound tip kernels of step i + 1 (on the SMs the partition leaves it, see VdHeadParams.head_ctas / tconv_ctas)
+        self._streams = [torch.cuda.Stream() for _ in range(3 if overlap_head else 2)]
         for s in self.sessions:                       # initialise workspaces (scheduler state, warm-start hints)
             s.run()
         torch.cuda.synchronize()
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
             main = torch.cuda.current_stream()
-            hs, ns = self._streams
-            hs.wait_stream(main)
-            ns.wait_stream(main)
+            hs, ns = self._streams[:2]
+            ts = self._streams[2] if overlap_head else None
+            for st in self._streams:
+                st.wait_stream(main)
             nms_done = [None] * len(self.sessions)
             for i in range(steps):
                 j = i % len(self.sessions)
                 sess = self.sessions[j]
                 if inputs is not None:
                     sess.rebind(inputs[i % len(inputs)])            # the captured nodes keep this step's pointers
+                if ts is not None:
+                    with torch.cuda.stream(ts):
+                        if nms_done[j] is not None:
+                            ts.wait_event(nms_done[j])        # the session's buffers (tip scratch, workspace) are free again
+                        sess.run(_lib.VD_STAGE_TCONV)
+                        tip_done = torch.cuda.Event()
+                        tip_done.record(ts)
                 with torch.cuda.stream(hs):
-                    if nms_done[j] is not None:
-                        hs.wait_event(nms_done[j])            # the session's buffers are free again
-                    sess.run(_lib.VD_STAGE_TCONV | _lib.VD_STAGE_HEAD)   # (temporal tip cell kernels, if any,) fused head kernel
+                    if ts is not None:
+                        hs.wait_event(tip_done)
+                        sess.run(_lib.VD_STAGE_HEAD)
+                    else:
+                        if nms_done[j] is not None:
+                            hs.wait_event(nms_done[j])            # the session's buffers are free again
+                        sess.run(_lib.VD_STAGE_TCONV | _lib.VD_STAGE_HEAD)   # (temporal tip cell kernels, if any,) fused head kernel
                     head_done = torch.cuda.Event()
                     head_done.record(hs)
                 with torch.cuda.stream(ns):
@@ -952,8 +966,8 @@ class HeadPipeline:
                     sess.run(_lib.VD_STAGE_NMS)
                     nms_done[j] = torch.cuda.Event()
                     nms_done[j].record(ns)
-            main.wait_stream(hs)
-            main.wait_stream(ns)
+            for st in self._streams:
+                main.wait_stream(st)
         self._graph = g
         self.steps_per_cycle = steps
         self.launches_per_step = 2

@@ -89,6 +89,7 @@ struct HeadKernelParams {
     // kernel's own class index c (0 .. C-1 of its template shape) is class c_off + c of the head; c >= c_valid are padding
     int c_off, c_valid, n_pass, pass;
     int prefetch;                        // tiles the producer claims ahead and prefetches into L2 (0: off)
+    int head_ctas;                       // > 0: CTAs of the speculative head kernel (SM partition beside the tip-cell kernels); 0: one per SM
     const float* bias[VD_MAX_SCALES];
     // EPI_FILTER
     float4* boxes; uint64_t* lists; uint32_t* counts; float valid_thresh; int k, cap;
@@ -1652,14 +1653,24 @@ static int launch_head_t(const HeadMaps& maps, const HeadKernelParams& kp, cudaS
     // the exact fallback of the speculative path is idle in the steady state: a handful of CTAs slip in between two
     // head kernels instead of claiming every SM's shared memory (when frames did fail, they work through them slowly)
     if (kp.frame_list && grid > kFallbackCtas) grid = kFallbackCtas;
+    // SM partition (temporal head): the head kernel of step i runs on `head_ctas` SMs beside the tip-cell kernels of step i + 1
+    // (tensor-bound, on the other SMs); launched as 2-CTA clusters so that its CTAs fill whole TPCs and leave the others to the
+    // tip kernels' CTA pairs
+    int cluster = 1;
+    if (EPI == EPI_SPEC && !kp.frame_list && kp.head_ctas >= 2 && kp.head_ctas < grid) { grid = kp.head_ctas & ~1; cluster = 2; }
     if (grid < 1) return VD_OK;
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)Cfg::THREADS); cfg.dynamicSmemBytes = Cfg::SMEM_BYTES; cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = getenv("VD_PDL") ? 1 : 0;   // measured slower in the pipeline (43.2 vs 38.6 us/step): off unless asked for
     cfg.attrs = attr; cfg.numAttrs = 1;
+    if (cluster > 1) {
+        attr[1].id = cudaLaunchAttributeClusterDimension;
+        attr[1].val.clusterDim.x = (unsigned)cluster; attr[1].val.clusterDim.y = 1; attr[1].val.clusterDim.z = 1;
+        cfg.numAttrs = 2;
+    }
     VD_CUDA(cudaLaunchKernelEx(&cfg, kern, maps, kp));
     VD_LAUNCH_CHECK();
     return VD_OK;
@@ -1784,6 +1795,7 @@ extern "C" int vd_head_forward_stages(const VdHeadParams* hp, float* ids, float*
     const bool spec = getenv("VD_NO_SPEC") == nullptr;   // speculative frame-level threshold with the exact path as fallback
     kp.valid_thresh = hp->valid_thresh; kp.k = k; kp.cap = (k <= 448) ? 640 : kListCap;
     { const char* e = getenv("VD_HEAD_PREFETCH"); kp.prefetch = e ? atoi(e) : 0; }
+    { const char* e = getenv("VD_HEAD_CTAS"); kp.head_ctas = e ? atoi(e) : 0; }
     kp.stamps = getenv("VD_DEBUG_HEAD_STAMPS") ? (long long*)(ws + pl.off_listsA) : nullptr;   // profiling aid (unused merge area)
     if (const char* e = getenv("VD_DEBUG_SKIP_EPILOGUE")) kp.dbg = atoi(e);     // profiling aid: results are garbage
 

@@ -30,8 +30,9 @@ struct TConvParams {
     int planes, n_prod;
     signed char a_pl[8], w_pl[8];
     long long y_plane_stride;      // elements between output planes
+    int dbg;                       // profiling aid (VD_TCONV_DBG=1): the epilogue releases its accumulator without BN / stores, results are garbage
 };
-struct TConvMaps { CUtensorMap x; CUtensorMap w; };
+struct TConvMaps { CUtensorMap x; CUtensorMap w; CUtensorMap y; };      // y: output map of the pair kernel's TMA-store epilogue, box {64 ch, 128 rows, 1}
 
 template <int NT> struct TConvCfg {
     static constexpr int A_BYTES = T_BLOCK_M * T_BLOCK_K * 2;
@@ -272,16 +273,30 @@ struct T2Shared {
     uint64_t full[8], empty[8], tmem_full[2], tmem_empty[2];
     uint32_t tmem_base;
 };
+#ifndef VD_TCONV_OUT_BUFS
+#define VD_TCONV_OUT_BUFS 2
+#endif
 struct T2Cfg {
     static constexpr int NT = 256;
     static constexpr int A_BYTES = T_BLOCK_M * T_BLOCK_K * 2;
     static constexpr int B_BYTES = (NT / 2) * T_BLOCK_K * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int STAGES = (200 * 1024) / STAGE_BYTES > 8 ? 8 : (200 * 1024) / STAGE_BYTES;
+    // output staging of the TMA-store epilogue: per column half (4 epilogue warps) OUT_BUFS tiles of [128 rows x 64 ch] bf16 in the
+    // 128-byte-swizzled layout of a TMA box
+    static constexpr int OUT_BUFS = VD_TCONV_OUT_BUFS;
+    static constexpr int OUT_TILE_BYTES = T_BLOCK_M * 64 * 2;
+    static constexpr int OUT_BYTES = 2 * OUT_BUFS * OUT_TILE_BYTES;
+    static constexpr int STAGES = (212 * 1024 - OUT_BYTES) / STAGE_BYTES > 8 ? 8 : (212 * 1024 - OUT_BYTES) / STAGE_BYTES;
     static constexpr int BN_BYTES = 2 * 1024 * 4;
     static constexpr int TMEM_COLS = 2 * NT;
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BN_BYTES + 2048 + 1024;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + OUT_BYTES + BN_BYTES + 2048 + 1024;
+    static_assert(OUT_BUFS == 1 || OUT_BUFS == 2, "OUT_BUFS");
+    static_assert(SMEM_BYTES <= 227 * 1024 && STAGES >= 3, "shared memory");
 };
+// named barrier of one column half's 4 epilogue warps (immediate ids, like head.cu)
+__device__ __forceinline__ void t2_half_bar(int half) {
+    if (half == 0) asm volatile("bar.sync 1, 128;" ::: "memory"); else asm volatile("bar.sync 2, 128;" ::: "memory");
+}
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(T_THREADS, 1)
 temporal_conv_pair_kernel(const __grid_constant__ TConvMaps maps, const __grid_constant__ TConvParams p) {
@@ -290,9 +305,10 @@ temporal_conv_pair_kernel(const __grid_constant__ TConvMaps maps, const __grid_c
     extern __shared__ unsigned char smem_dyn[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
     unsigned char* ring = smem;
-    float* sscale = reinterpret_cast<float*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+    unsigned char* outb = smem + Cfg::STAGES * Cfg::STAGE_BYTES;                 // [half][OUT_BUFS][128 rows x 128 B], 1024-byte aligned
+    float* sscale = reinterpret_cast<float*>(outb + Cfg::OUT_BYTES);
     float* sshift = sscale + 1024;
-    T2Shared* sh = reinterpret_cast<T2Shared*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES + Cfg::BN_BYTES);
+    T2Shared* sh = reinterpret_cast<T2Shared*>(outb + Cfg::OUT_BYTES + Cfg::BN_BYTES);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = tc::cluster_ctarank();
     const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
@@ -302,7 +318,7 @@ temporal_conv_pair_kernel(const __grid_constant__ TConvMaps maps, const __grid_c
         for (int i = 0; i < Cfg::STAGES; ++i) { tc::mbar_init(&sh->full[i], 1); tc::mbar_init(&sh->empty[i], 1); }
         for (int i = 0; i < 2; ++i) { tc::mbar_init(&sh->tmem_full[i], 1); tc::mbar_init(&sh->tmem_empty[i], 16); }
         tc::fence_barrier_init();
-        tc::prefetch_tmap(&maps.x); tc::prefetch_tmap(&maps.w);
+        tc::prefetch_tmap(&maps.x); tc::prefetch_tmap(&maps.w); tc::prefetch_tmap(&maps.y);
     }
     if (warp == 1) tc::tmem_alloc_2cta<Cfg::TMEM_COLS>(&sh->tmem_base);
     tc::fence_before_sync();
@@ -381,32 +397,47 @@ temporal_conv_pair_kernel(const __grid_constant__ TConvMaps maps, const __grid_c
             }
         }
     } else {
+        // Epilogue: 8 warps; warp (q, half) owns TMEM lanes q*32.. (rows) and 128 of the tile's 256 columns, in two passes of 64.
+        // Per pass: tcgen05.ld -> folded BN -> LeakyReLU -> bf16 -> st.shared into the half's staging tile (swizzled like a TMA box:
+        // conflict-free 128-bit stores) -> fence.proxy.async + named barrier of the half -> ONE thread issues a TMA store of the
+        // [128 rows x 64 ch] box (rows past the window's end are clipped by the map).  The direct per-thread global stores this replaces
+        // (32 rows x 16 B per instruction) kept the LSU busy for ~4 k cycles per tile: s8 ran at 0.31 ms against 0.20 ms of mainloop.
         const int q = warp & 3;
         const int half = (warp - 2) >> 2;
         constexpr int NH = NT / 2;
         const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
-        uint32_t it = 0;
+        const bool issuer = (q == 0 && lane == 0);
+        const int trow = q * 32 + lane;                                       // row inside the tile
+        unsigned char* obase = outb + half * Cfg::OUT_BUFS * Cfg::OUT_TILE_BYTES;
+        const uint32_t orow = tc::smem_u32(obase) + (uint32_t)trow * 128u;
+        const uint32_t sw = (uint32_t)(trow & 7);
+        uint32_t it = 0, ob = 0;
         for (int pair = cluster_id; pair < total_pairs; pair += num_clusters, ++it) {
             int b, mt, nt; coords(pair, rank, b, mt, nt);
             const uint32_t buf = it & 1u;
-            const int row = mt * T_BLOCK_M + q * 32 + lane;
-            const bool inb = row < p.rows && b < p.B;
             tc::mbar_wait_cluster(&sh->tmem_full[buf], (it >> 1) & 1u);
             tc::fence_after_sync();
             const uint32_t tbase = tmem_base + buf * NT + (uint32_t)(half * NH) + lane_addr;
             const int col0 = nt * NT + half * NH;
-            __nv_bfloat16* yrow = p.y + (inb ? ((size_t)b * p.rows + row) * p.C : 0) + col0;
-            const float* sc = sscale + col0;
-            const float* sf = sshift + col0;
 #pragma unroll 1
-            for (int n0 = 0; n0 < NH; n0 += 32) {
-                uint32_t r[32];
-                tc::tmem_ld16(tbase + n0, r); tc::tmem_ld16(tbase + n0 + 16, r + 16); tc::tmem_ld_wait();
-                uint32_t packed[16];
+            for (int pass = 0; pass < 2; ++pass, ++ob) {
+                uint32_t r[64];
+                const uint32_t ta = tbase + (uint32_t)(pass * 64);
+                tc::tmem_ld16(ta, r); tc::tmem_ld16(ta + 16, r + 16); tc::tmem_ld16(ta + 32, r + 32); tc::tmem_ld16(ta + 48, r + 48);
+                tc::tmem_ld_wait();
+                if (pass == 1) {                                              // this warp has read its share of the accumulator
+                    tc::fence_before_sync();
+                    __syncwarp();
+                    if (lane == 0) tc::mbar_arrive_cluster(&sh->tmem_empty[buf], 0u);
+                }
+                if (p.dbg & 1) continue;
+                const float* sc = sscale + col0 + pass * 64;
+                const float* sf = sshift + col0 + pass * 64;
+                uint32_t packed[32];
 #pragma unroll
-                for (int i = 0; i < 32; i += 4) {
-                    const float4 s4 = *reinterpret_cast<const float4*>(sc + n0 + i);
-                    const float4 f4 = *reinterpret_cast<const float4*>(sf + n0 + i);
+                for (int i = 0; i < 64; i += 4) {
+                    const float4 s4 = *reinterpret_cast<const float4*>(sc + i);
+                    const float4 f4 = *reinterpret_cast<const float4*>(sf + i);
                     float v0 = fmaf(__uint_as_float(r[i]), s4.x, f4.x), v1 = fmaf(__uint_as_float(r[i + 1]), s4.y, f4.y);
                     float v2 = fmaf(__uint_as_float(r[i + 2]), s4.z, f4.z), v3 = fmaf(__uint_as_float(r[i + 3]), s4.w, f4.w);
                     v0 = v0 > 0.f ? v0 : v0 * p.slope; v1 = v1 > 0.f ? v1 : v1 * p.slope;
@@ -414,16 +445,30 @@ temporal_conv_pair_kernel(const __grid_constant__ TConvMaps maps, const __grid_c
                     __nv_bfloat162 h0 = __floats2bfloat162_rn(v0, v1), h1 = __floats2bfloat162_rn(v2, v3);
                     packed[i / 2] = *reinterpret_cast<uint32_t*>(&h0); packed[i / 2 + 1] = *reinterpret_cast<uint32_t*>(&h1);
                 }
-                if (inb) {
-                    uint4* dst = reinterpret_cast<uint4*>(yrow + n0);
+                const uint32_t slot = Cfg::OUT_BUFS == 2 ? (ob & 1u) : 0u;
+                if (Cfg::OUT_BUFS == 1) {                                     // single staging tile: wait until the previous store has read it
+                    if (issuer) tc::tma_store_wait_read<0>();
+                    __syncwarp();
+                    t2_half_bar(half);
+                }
+                const uint32_t dst = orow + slot * (uint32_t)Cfg::OUT_TILE_BYTES;
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) dst[i] = make_uint4(packed[4 * i], packed[4 * i + 1], packed[4 * i + 2], packed[4 * i + 3]);
+                for (int j = 0; j < 8; ++j)
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + (((uint32_t)j ^ sw) << 4)),
+                                 "r"(packed[4 * j]), "r"(packed[4 * j + 1]), "r"(packed[4 * j + 2]), "r"(packed[4 * j + 3]) : "memory");
+                tc::fence_proxy_async_smem();
+                // two staging tiles: the store issued one pass ago must have read its tile before anyone passes this barrier, because
+                // the NEXT pass overwrites that tile
+                if (Cfg::OUT_BUFS == 2 && issuer) tc::tma_store_wait_read<0>();
+                __syncwarp();
+                t2_half_bar(half);
+                if (issuer && b < p.B) {
+                    tc::tma_store_3d(&maps.y, obase + slot * Cfg::OUT_TILE_BYTES, col0 + pass * 64, mt * T_BLOCK_M, b);
+                    tc::tma_store_commit();
                 }
             }
-            tc::fence_before_sync();
-            __syncwarp();
-            if (lane == 0) tc::mbar_arrive_cluster(&sh->tmem_empty[buf], 0u);
         }
+        if (issuer) tc::tma_store_wait<0>();
     }
     __syncwarp();
     tc::fence_before_sync();
@@ -436,7 +481,9 @@ static int launch_tconv_pair(const TConvMaps& maps, const TConvParams& p, cudaSt
     auto kern = temporal_conv_pair_kernel;
     { int rc_ = configure_kernel((const void*)kern, T2Cfg::SMEM_BYTES, false); if (rc_) return rc_; }
     const long long pairs = ((long long)p.B * p.m_tiles + 1) / 2 * p.n_tiles;
-    long long clusters = sm_count() / 2; if (clusters > pairs) clusters = pairs;
+    long long clusters = sm_count() / 2;
+    { static const int cap = []() { const char* e = getenv("VD_TCONV_CTAS"); return e ? atoi(e) : 0; }(); if (cap >= 2 && cap / 2 < clusters) clusters = cap / 2; }   // SM partition: leave SMs to a concurrent head kernel
+    if (clusters > pairs) clusters = pairs;
     kern<<<(unsigned)(2 * clusters), T_THREADS, T2Cfg::SMEM_BYTES, stream>>>(maps, p);
     VD_LAUNCH_CHECK();
     return VD_OK;
@@ -489,6 +536,7 @@ extern "C" int vd_temporal_conv_ex(const void* x, void* y, int B, int T, int H, 
     p.total_tiles = (int)total;
     p.scale = scale; p.shift = shift; p.slope = slope; p.y = (__nv_bfloat16*)y;
     p.planes = planes; p.n_prod = 1; p.y_plane_stride = (long long)B * p.rows * C;
+    { static const int dbg = []() { const char* e = getenv("VD_TCONV_DBG"); return e ? atoi(e) : 0; }(); p.dbg = dbg; }
     if (planes > 1) {                      // same plane products as the head kernel (head.cu split_products): low-order first, p0 w0 last
         static const signed char a3[6] = {0, 2, 1, 0, 1, 0}, w3[6] = {2, 0, 1, 1, 0, 0};
         static const signed char a2[3] = {0, 1, 0}, w2[3] = {1, 0, 0};
@@ -508,7 +556,15 @@ extern "C" int vd_temporal_conv_ex(const void* x, void* y, int B, int T, int H, 
     uint32_t boxW[3] = {T_BLOCK_K, (uint32_t)(pair ? NT / 2 : NT), 1};
     rc = encode_tmap_bf16(&maps.w, weight, 3, dimsW, strW, boxW);
     if (rc) return rc;
-    if (pair) return launch_tconv_pair(maps, p, (cudaStream_t)stream_);
+    if (pair) {
+        uint64_t dimsY[3] = {(uint64_t)C, (uint64_t)p.rows, (uint64_t)B};
+        uint64_t strY[2] = {(uint64_t)C * 2, (uint64_t)p.rows * C * 2};
+        uint32_t boxY[3] = {64, T_BLOCK_M, 1};
+        rc = encode_tmap_bf16(&maps.y, y, 3, dimsY, strY, boxY);
+        if (rc) return rc;
+        return launch_tconv_pair(maps, p, (cudaStream_t)stream_);
+    }
+    maps.y = maps.x;      // unused by the 1-CTA kernels
     if (NT == 256) return launch_tconv<256>(maps, p, (cudaStream_t)stream_);
     return launch_tconv<128>(maps, p, (cudaStream_t)stream_);
 }

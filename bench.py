@@ -329,14 +329,13 @@ class StepRunner:
     are replayed from CUDA graphs of GRAPH_STEPS steps + ONE graph for the remainder; a run of <= 96 steps is a single graph of
     exactly that many steps, so every timed step is a steady-state step."""
 
-    def __init__(self, vd, sessions, group_inputs, group, overlap_head=False):
+    def __init__(self, vd, sessions, group_inputs, group):
         self.vd, self.sessions, self.inputs, self.group, self.graphs = vd, sessions, group_inputs, group, {}
-        self.overlap_head = overlap_head
 
     def graph(self, n):
         assert n % self.group == 0
         if n not in self.graphs:
-            self.graphs[n] = self.vd.HeadPipeline(self.sessions, steps=n // self.group, inputs=self.inputs, overlap_head=self.overlap_head)
+            self.graphs[n] = self.vd.HeadPipeline(self.sessions, steps=n // self.group, inputs=self.inputs)
         return self.graphs[n]
 
     def plan(self, n):
@@ -477,7 +476,6 @@ def main():
                     help="iid: pool of distinct iid batches (default); video: batch t+1 = perturbed batch t; same: each session replays its own batch (r1 behaviour)")
     ap.add_argument("--pool", type=int, default=0, help="distinct resident input batches (default 32; 8 for the temporal workload)")
     ap.add_argument("--group", type=int, default=0, help="steps (batches) per persistent head-kernel launch (default %d; 1 for the temporal workload)" % GROUP)
-    ap.add_argument("--overlap-head", type=int, default=-1, help="temporal workload: head kernel of step i beside the tip-cell kernels of step i+1 on an SM partition (1/0; default: on for the temporal workload)")
     ap.add_argument("--preroll-ms", type=float, default=-1.0, help="device-side pre-roll in front of the timed region (a spin kernel enqueued before the start event, so the timed launches are already queued when the clock starts); default 0.3")
     ap.add_argument("--idle-ms", type=float, default=0.0, help="experiment: host sleep between the barrier and the timed region")
     ap.add_argument("--gather", default="peer", choices=["peer", "nccl"], help="multi-GPU detection gather: fused into the NMS sink over NVLink (peer) or staged NCCL all_gather")
@@ -567,8 +565,7 @@ def main():
         group_inputs_run = None
     else:
         group_inputs_run = group_inputs
-    overlap_head = temporal and args.overlap_head != 0 and bool(os.environ.get("VD_HEAD_CTAS"))
-    runner = StepRunner(viddet_b200, sessions, group_inputs_run, group, overlap_head=overlap_head)
+    runner = StepRunner(viddet_b200, sessions, group_inputs_run, group)
     pool_flat = [batch_view(i) for i in range(npool)]
     nccl_gather = world > 1 and peer is None
     if nccl_gather:                                      # fallback: staged all_gather of the ring per graph, off the critical path
@@ -681,11 +678,20 @@ def main():
         f_tconv = 2.0 * (3 * TEMPORAL_T - 2) * hw_c2 * windows
         f_all = f_tconv + 2.0 * 3 * (5 + C) * hw_c * TEMPORAL_T * windows
         tpeak, tkind = measured_tensor_peak()
-        roof = {"bound": "tensor", "kernel": "temporal_conv_pair_kernel x3 scales (tcgen05 cta_group::2 implicit GEMM, tip cell of layers.py:82-89)",
-                "achieved": f_tconv / (tconv_ms * 1e-3) / 1e12, "peak": tpeak, "peak_kind": tkind, "unit": "TFLOP/s",
-                "frac": f_tconv / (tconv_ms * 1e-3) / 1e12 / tpeak, "traffic": None, "algorithmic_flops_per_launch": f_tconv,
-                "kernel_ms": tconv_ms, "head_kernel_ms": head_ms, "nms_kernel_ms": nms_ms,
-                "path_frac": f_all / (step_ms * 1e-3) / 1e12 / tpeak, "path_flops_per_step": f_all}
+        if sessions[0].fused_tip:
+            # tip cell + prediction conv + decode + candidate filter as ONE kernel per scale (csrc/tfused.cuh): the dominant kernels
+            # carry both GEMMs; the tip never goes to HBM
+            roof = {"bound": "tensor", "kernel": "temporal_head_fused_kernel x3 scales (tcgen05 cta_group::2: tip-cell implicit GEMM -> BN/LReLU/bf16 tile in shared memory -> prediction GEMM -> decode + candidate filter; layers.py:82-89 + yolo3.py:157-199)",
+                    "achieved": f_all / (head_ms * 1e-3) / 1e12, "peak": tpeak, "peak_kind": tkind, "unit": "TFLOP/s",
+                    "frac": f_all / (head_ms * 1e-3) / 1e12 / tpeak, "traffic": None, "algorithmic_flops_per_launch": f_all,
+                    "kernel_ms": head_ms, "head_kernel_ms": None, "nms_kernel_ms": nms_ms,
+                    "path_frac": f_all / (step_ms * 1e-3) / 1e12 / tpeak, "path_flops_per_step": f_all}
+        else:
+            roof = {"bound": "tensor", "kernel": "temporal_conv_pair_kernel x3 scales (tcgen05 cta_group::2 implicit GEMM, tip cell of layers.py:82-89)",
+                    "achieved": f_tconv / (tconv_ms * 1e-3) / 1e12, "peak": tpeak, "peak_kind": tkind, "unit": "TFLOP/s",
+                    "frac": f_tconv / (tconv_ms * 1e-3) / 1e12 / tpeak, "traffic": None, "algorithmic_flops_per_launch": f_tconv,
+                    "kernel_ms": tconv_ms, "head_kernel_ms": head_ms, "nms_kernel_ms": nms_ms,
+                    "path_frac": f_all / (step_ms * 1e-3) / 1e12 / tpeak, "path_flops_per_step": f_all}
     else:
         # Two upper bounds of the head kernel's launch duration, both from CUDA events on its launching stream: (a) events
         # around one direct launch inside a real call (includes ~3 us of eager-launch latency); (b) the step period of the

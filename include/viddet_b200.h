@@ -144,6 +144,9 @@ typedef struct VdHeadScale {
     int reserved;                   /* must be 0                                                 */
 } VdHeadScale;
 
+/* VdHeadParams.flags */
+#define VD_HEAD_NO_FUSED_TIP 1  /* temporal heads: run the tip cell and the head as separate kernels (vd_temporal_conv -> head kernel) even
+                                 * where the fused kernel applies (bf16, num_class 20 / 30, Cin % 256 == 0); results are bit-identical */
 typedef struct VdHeadParams {
     int num_scales;              /* 3, output order s32, s16, s8 (yolo3.py:416-417)             */
     int num_class;
@@ -155,7 +158,7 @@ typedef struct VdHeadParams {
     int nms_topk;                /* 400 (detect_yolo3.py:200)                                   */
     int post_nms;                /* 100 (yolo3.py:395)                                          */
     int precision;               /* VD_PREC_BF16 (0), or an fp32-parity mode: tips (P,frames,H,W,Cin), weights (N_out,P,Cin) */
-    int reserved0;               /* must be 0                                                    */
+    int flags;                   /* 0, or VD_HEAD_* bits below                                   */
     VdHeadScale scale[VD_MAX_SCALES];
     /* Output mirrors (multi-GPU detection gather): every ids / scores / bboxes element vd_head_forward stores at
      * address a is also stored at a + mirror_delta[i] (bytes, multiples of 16), i < n_mirrors.  The targets are the same slot of
@@ -208,6 +211,9 @@ size_t vd_head_stats_offset(const VdHeadParams* p);
 size_t vd_head_debug_offset(const VdHeadParams* p);
 /* Number of kernels one vd_head_forward call launches for these parameters (-1 on bad params). */
 int vd_head_launch_count(const VdHeadParams* p);
+/* 1 if vd_head_forward runs the temporal tip cell and the head as ONE kernel per scale for these parameters (the tip tile stays in
+ * shared memory between the two GEMMs: yolo3_temporal.py:226-227 + yolo3.py:157-199 fused), 0 if as separate kernels, -1 on bad params. */
+int vd_head_fused_tip(const VdHeadParams* p);
 /* Same conv + decode, but materialises the reference's (frames, rows, 6) detection tensor
  * (what `concat(all_detections)` holds at yolo3.py:523) instead of running NMS. */
 int vd_head_detections(const VdHeadParams* p, float* det, void* workspace, size_t workspace_bytes,

@@ -16,13 +16,16 @@ for C, hw in ((1024, 13), (512, 26), (256, 52)):
         check(load().vd_temporal_conv(ptr(xs[i % 2]), ptr(y), B, T, hw, hw, C, ptr(cell._w_taps), ptr(cell._scale), ptr(cell._shift), 0.1, stream_ptr()))
     for i in range(3): run(i)
     torch.cuda.synchronize()
-    n = 20
+    n = int(os.environ.get("TC_N", 20))
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(n): run(i)
-    e1.record(); torch.cuda.synchronize()
+    e1.record()
+    torch.cuda._sleep(2_000_000)            # clock probe: a spin of 2 M SM cycles right behind the loop -> SM MHz while the loop's power state still holds
+    e2 = torch.cuda.Event(enable_timing=True); e2.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / n
+    mhz = 2_000_000 / (e1.elapsed_time(e2) * 1e3)
     fl = 2.0 * 13 * hw * hw * C * C * B
     tot += ms
-    print(json.dumps({"C": C, "hw": hw, "ms": round(ms, 4), "tflops": round(fl / ms / 1e9, 1), "dbg": os.environ.get("VD_TCONV_DBG"), "ctas": os.environ.get("VD_TCONV_CTAS")}))
+    print(json.dumps({"C": C, "hw": hw, "ms": round(ms, 4), "tflops": round(fl / ms / 1e9, 1), "sm_mhz_after": round(mhz), "dbg": os.environ.get("VD_TCONV_DBG"), "ctas": os.environ.get("VD_TCONV_CTAS")}))
 print(json.dumps({"total_ms": round(tot, 4)}))

@@ -331,7 +331,8 @@ def test_time_distributed_head_and_late_joins():
 def test_temporal_tip_conv_vs_oracle():
     import viddet_b200
     rng = np.random.RandomState(4)
-    for (Cc, H, Wd, B, T) in [(256, 13, 13, 2, 5), (512, 6, 5, 1, 5), (128, 20, 20, 2, 3)]:
+    # (512, 13, 13, 3, 5): 21 row tiles -> clusters of 4 CTAs with 3 padding tiles in the last item (one pair all padding); (256, 26, 26, 1, 5): 27 tiles
+    for (Cc, H, Wd, B, T) in [(256, 13, 13, 2, 5), (512, 6, 5, 1, 5), (128, 20, 20, 2, 3), (512, 13, 13, 3, 5), (256, 26, 26, 1, 5)]:
         x = bf16_round(rng.standard_normal((B, T, Cc, H, Wd)).astype(np.float32))
         w = bf16_round(rng.uniform(-0.07, 0.07, (Cc, Cc, 3, 1, 1)).astype(np.float32))
         gamma = rng.uniform(0.5, 1.5, Cc).astype(np.float32); beta = rng.uniform(-0.2, 0.2, Cc).astype(np.float32)
@@ -574,6 +575,54 @@ def test_arbitrary_class_counts_valid_thresh_below_zero_and_heavy_ties():
             ids, scores, boxes, keep = head(tt, return_keep=True)
             assert torch.equal(keep, rec[:, :100]), (C, call)
             assert torch.equal(scores.view(torch.int32), out[:, :100, 1:2].contiguous().view(torch.int32))
+
+
+@pytest.mark.parametrize("C", [30, 20])
+def test_fused_tip_head_equals_separate_kernels_bit_exact(C):
+    """cfg 4 in ONE kernel per scale (tip cell -> BN/LReLU/bf16 tile in shared memory -> prediction GEMM -> decode + candidate
+    filter, csrc/tfused.cuh) == the separate kernels (vd_temporal_conv -> head kernel), bit for bit: keep rows, ids, scores, boxes,
+    on the cold call (every frame redone by the exact path, which recomputes the tip) and on steady calls with new inputs (no
+    frame redone: the fused kernel's candidate lists are the ones that reach NMS).  Shapes: 3 windows (odd tile counts -> a
+    padding tile), materialised windows and windows over a resident clip."""
+    import viddet_b200
+    rng = np.random.RandomState(21 + C)
+    B, T, size = 3, 5, 160
+    ws, bs = make_pred_weights(rng, C, bias_scale=0.1)
+    heads = [build_head(C, ws, bs, temporal="conv21", fuse_tip=f) for f in (True, False)]
+    for ch_i, ch in enumerate(CHANNELS):
+        w = torch.from_numpy(bf16_round(rng.uniform(-0.05, 0.05, (ch, ch, 3, 1, 1)).astype(np.float32)))
+        g, b_, m, v = (rng.uniform(0.5, 1.5, ch).astype(np.float32), rng.uniform(-0.2, 0.2, ch).astype(np.float32),
+                       rng.uniform(-0.2, 0.2, ch).astype(np.float32), rng.uniform(0.5, 1.5, ch).astype(np.float32))
+        for h in heads:
+            h.tip_convs[ch_i].set_data(w, g, b_, m, v)
+    for h in heads:
+        h.set_nms(0.45, 400, 100)
+    batches = [[cuda(t) for t in make_tips(rng, B, size=size, T=T)] for _ in range(3)]
+    sess = [h.session([t.clone() for t in batches[0]], return_keep=True) for h in heads]
+    for call, batch in enumerate(batches + [batches[1]]):
+        for s_ in sess:
+            for dst, src in zip(s_.tips, batch):
+                dst.copy_(src.reshape(dst.shape))
+            s_.run()
+        torch.cuda.synchronize()
+        f_, u_ = sess
+        assert torch.equal(f_.keep, u_.keep), (C, call)
+        assert torch.equal(f_.ids.view(torch.int32), u_.ids.view(torch.int32)), (C, call)
+        assert torch.equal(f_.scores.view(torch.int32), u_.scores.view(torch.int32)), (C, call)
+        assert torch.equal(f_.bboxes.view(torch.int32), u_.bboxes.view(torch.int32)), (C, call)
+        assert int((f_.keep >= 0).sum()) > 0
+        if call >= 1:       # steady calls: the same (few) frames fail their proof on both paths; the others are the fused kernel's own lists
+            assert f_.redone_frames() == u_.redone_frames() and f_.redone_frames() <= B * T // 3, (C, call, f_.redone_frames(), u_.redone_frames())
+    # windows sliding over a resident clip
+    L = 12
+    clips = [cuda(t) for t in make_tips(rng, L, size=size)]
+    cw = [viddet_b200.ClipWindows(c, 1, 7, T) for c in clips]
+    outs = []
+    for h in heads:
+        h(cw, return_keep=True)                                                     # cold call: thresholds
+        outs.append(h(cw, return_keep=True))
+    for a, b2 in zip(outs[0], outs[1]):
+        assert torch.equal(a.view(torch.int32), b2.view(torch.int32))
 
 
 def test_clip_windows_equal_materialised_windows_bit_exact():

@@ -16,6 +16,7 @@ VD_MAX_MIRRORS = 7
 VD_MODE_INFER, VD_MODE_TRAIN, VD_MODE_AGNOSTIC = 0, 1, 2
 VD_JOIN_NONE, VD_JOIN_CAT, VD_JOIN_MAX, VD_JOIN_MEAN = 0, 1, 2, 3
 VD_STAGE_TCONV, VD_STAGE_HEAD, VD_STAGE_NMS, VD_STAGE_ALL = 1, 2, 4, 7
+VD_HEAD_NO_FUSED_TIP = 1          # VdHeadParams.flags
 VD_PREC_BF16, VD_PREC_FP32_SPLIT, VD_PREC_BF16X2 = 0, 1, 2
 PLANES = {VD_PREC_BF16: 1, VD_PREC_FP32_SPLIT: 3, VD_PREC_BF16X2: 2}
 ERR_NAMES = {-1: "VD_ERR_INVALID_ARG", -2: "VD_ERR_UNSUPPORTED", -3: "VD_ERR_WORKSPACE", -4: "VD_ERR_CUDA"}
@@ -44,7 +45,7 @@ class VdHeadParams(ctypes.Structure):
         ("T", ctypes.c_int), ("K_frames", ctypes.c_int), ("join", ctypes.c_int),
         ("nms_thresh", ctypes.c_float), ("valid_thresh", ctypes.c_float),
         ("nms_topk", ctypes.c_int), ("post_nms", ctypes.c_int),
-        ("precision", ctypes.c_int), ("reserved0", ctypes.c_int),
+        ("precision", ctypes.c_int), ("flags", ctypes.c_int),
         ("scale", VdHeadScale * VD_MAX_SCALES),
         ("n_mirrors", ctypes.c_int), ("reserved1", ctypes.c_int),
         ("mirror_delta", ctypes.c_longlong * VD_MAX_MIRRORS),
@@ -72,6 +73,7 @@ SIGNATURES = {
     "vd_head_forward": (_i, [ctypes.POINTER(VdHeadParams), _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "vd_head_forward_stages": (_i, [ctypes.POINTER(VdHeadParams), _vp, _vp, _vp, _vp, _vp, _sz, _vp, _i]),
     "vd_head_launch_count": (_i, [ctypes.POINTER(VdHeadParams)]),
+    "vd_head_fused_tip": (_i, [ctypes.POINTER(VdHeadParams)]),
     "vd_head_stats_offset": (_sz, [ctypes.POINTER(VdHeadParams)]),
     "vd_head_debug_offset": (_sz, [ctypes.POINTER(VdHeadParams)]),
     "vd_head_detections": (_i, [ctypes.POINTER(VdHeadParams), _vp, _vp, _sz, _vp]),

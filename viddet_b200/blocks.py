@@ -608,11 +608,12 @@ class YOLOV3Head:
     """
 
     def __init__(self, classes, anchors=None, strides=None, channels=None, nms_thresh=0.45, nms_topk=400,
-                 post_nms=100, temporal=None, k=1, agnostic=False, precision="bf16"):
+                 post_nms=100, temporal=None, k=1, agnostic=False, precision="bf16", fuse_tip=True):
         """precision 'bf16' (default): bf16 operands, fp32 accumulate -- 1e-3 relative vs the fp32 reference on bf16-representable
         inputs.  precision 'fp32': fp32 NCHW tips / weights are split into three bf16 planes, six plane products -- 1e-5
         relative (VD_PREC_FP32_SPLIT); 'bf16x2': two planes, three products -- 1e-4 (VD_PREC_BF16X2).  Per-frame heads only."""
         self._precision = _precision_code(precision)
+        self.fuse_tip = bool(fuse_tip)     # temporal='conv21': tip cell + head in one kernel per scale where it applies (bit-identical; False = separate kernels)
         if self._precision != _lib.VD_PREC_BF16 and temporal not in (None, "conv21"):
             raise NotImplementedError("the fp32-parity modes cover the per-frame head and the 'conv21' temporal head")
         self.classes = list(classes) if not isinstance(classes, int) else list(range(classes))
@@ -680,6 +681,7 @@ class YOLOV3Head:
         p.nms_thresh, p.valid_thresh = float(self.nms_thresh), float(self.valid_thresh)
         p.nms_topk, p.post_nms = int(self.nms_topk), int(self.post_nms)
         p.precision = self._precision
+        p.flags = 0 if self.fuse_tip else _lib.VD_HEAD_NO_FUSED_TIP
         planes = _lib.PLANES[self._precision]
         split = planes > 1
         frames = None
@@ -851,6 +853,7 @@ class HeadSession:
         lib = load()
         self._ws = torch.zeros(lib.vd_head_workspace_bytes(ctypes.byref(self.params)) + 256, dtype=torch.uint8, device=dev)
         self.launches = lib.vd_head_launch_count(ctypes.byref(self.params))
+        self.fused_tip = lib.vd_head_fused_tip(ctypes.byref(self.params)) == 1      # temporal tip cell + head as one kernel per scale
         self.graph = None
         self._graphs = {}
 
@@ -916,7 +919,7 @@ class HeadPipeline:
     waits for its previous NMS kernel.  `cycle()` = rotations * len(sessions) steps; every batch is complete
     when the graph has finished."""
 
-    def __init__(self, sessions, rotations=2, steps=None, inputs=None, overlap_head=False):
+    def __init__(self, sessions, rotations=2, steps=None, inputs=None):
         """steps: batches per graph (default rotations * len(sessions); any count >= 1: step i runs on session i % len).
         inputs: optional list of resident input sets (each a list of channels-last bf16 tips of the sessions' shapes); step i
         then reads inputs[i % len(inputs)] while using session i % len(sessions)'s workspace and outputs -- every threshold the
@@ -925,40 +928,26 @@ class HeadPipeline:
         self.sessions = list(sessions)
         steps = rotations * len(self.sessions) if steps is None else int(steps)
         assert steps >= 1
-        # overlap_head (temporal heads): the tip-cell kernels get their own stream, so the HBM-bound head kernel of step i runs beside
-        # the tensor-bound tip kernels of step i + 1 (on the SMs the partition leaves it, see VdHeadParams.head_ctas / tconv_ctas)
-        self._streams = [torch.cuda.Stream() for _ in range(3 if overlap_head else 2)]
+        self._streams = [torch.cuda.Stream() for _ in range(2)]
         for s in self.sessions:                       # initialise workspaces (scheduler state, warm-start hints)
             s.run()
         torch.cuda.synchronize()
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
             main = torch.cuda.current_stream()
-            hs, ns = self._streams[:2]
-            ts = self._streams[2] if overlap_head else None
-            for st in self._streams:
-                st.wait_stream(main)
+            hs, ns = self._streams
+            hs.wait_stream(main)
+            ns.wait_stream(main)
             nms_done = [None] * len(self.sessions)
             for i in range(steps):
                 j = i % len(self.sessions)
                 sess = self.sessions[j]
                 if inputs is not None:
                     sess.rebind(inputs[i % len(inputs)])            # the captured nodes keep this step's pointers
-                if ts is not None:
-                    with torch.cuda.stream(ts):
-                        if nms_done[j] is not None:
-                            ts.wait_event(nms_done[j])        # the session's buffers (tip scratch, workspace) are free again
-                        sess.run(_lib.VD_STAGE_TCONV)
-                        tip_done = torch.cuda.Event()
-                        tip_done.record(ts)
                 with torch.cuda.stream(hs):
-                    if ts is not None:
-                        hs.wait_event(tip_done)
-                        sess.run(_lib.VD_STAGE_HEAD)
-                    else:
-                        if nms_done[j] is not None:
-                            hs.wait_event(nms_done[j])            # the session's buffers are free again
-                        sess.run(_lib.VD_STAGE_TCONV | _lib.VD_STAGE_HEAD)   # (temporal tip cell kernels, if any,) fused head kernel
+                    if nms_done[j] is not None:
+                        hs.wait_event(nms_done[j])            # the session's buffers are free again
+                    sess.run(_lib.VD_STAGE_TCONV | _lib.VD_STAGE_HEAD)   # (temporal tip cell kernels, if any,) fused head kernel
                     head_done = torch.cuda.Event()
                     head_done.record(hs)
                 with torch.cuda.stream(ns):
@@ -966,8 +955,8 @@ class HeadPipeline:
                     sess.run(_lib.VD_STAGE_NMS)
                     nms_done[j] = torch.cuda.Event()
                     nms_done[j].record(ns)
-            for st in self._streams:
-                main.wait_stream(st)
+            main.wait_stream(hs)
+            main.wait_stream(ns)
         self._graph = g
         self.steps_per_cycle = steps
         self.launches_per_step = 2

@@ -43,6 +43,10 @@ static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b;
 int sm_count();   // of the current device (cached per device)
 // cudaFuncSetAttribute(MaxDynamicSharedMemorySize[, carve-out]) once per (current device, kernel); thread-safe
 int configure_kernel(const void* func, int dyn_smem_bytes, bool max_shared_carveout);
+// vd_temporal_conv_ex with a device-side condition: cond != nullptr -> the kernels return at once when *cond == 0; with frame_list the
+// CTA-pair kernel computes only the windows of frames frame_list[0 .. *cond)
+int temporal_conv_impl(const void* x, void* y, int B, int T, int H, int W, int C, const void* weight, const float* scale, const float* shift,
+                       float slope, int precision, int window_stride_frames, const unsigned int* cond, const unsigned int* frame_list, void* stream);
 
 // ---------------------------------------------------------------------------------------------
 // 64-bit selection key: (orderable(score) << 32) | ~row.  Larger key == earlier in MXNet's

@@ -89,7 +89,6 @@ struct HeadKernelParams {
     // kernel's own class index c (0 .. C-1 of its template shape) is class c_off + c of the head; c >= c_valid are padding
     int c_off, c_valid, n_pass, pass;
     int prefetch;                        // tiles the producer claims ahead and prefetches into L2 (0: off)
-    int head_ctas;                       // > 0: CTAs of the speculative head kernel (SM partition beside the tip-cell kernels); 0: one per SM
     const float* bias[VD_MAX_SCALES];
     // EPI_FILTER
     float4* boxes; uint64_t* lists; uint32_t* counts; float valid_thresh; int k, cap;
@@ -1450,6 +1449,10 @@ struct HeadPlan {
     size_t off_hints, off_ctr, off_hist, off_boxes, off_lists0, off_counts0, off_counts_hi, off_hint_hi, off_coarse, off_spec_lists, off_spec_cnt, off_spec_state, off_spec_tau, off_failed, off_listsA, off_listsB, off_countsA, off_countsB, total;
 };
 
+}  // namespace vd
+#include "tfused.cuh"
+namespace vd {
+
 static int head_npad(int C) { int n = 3 * (5 + C); return (n + 15) / 16 * 16; }
 
 // Plane products of the fp32-parity modes.  v = p0 + p1 (+ p2) with |p1| <= 2^-9 |v|, |p2| <= 2^-18 |v|.
@@ -1653,24 +1656,14 @@ static int launch_head_t(const HeadMaps& maps, const HeadKernelParams& kp, cudaS
     // the exact fallback of the speculative path is idle in the steady state: a handful of CTAs slip in between two
     // head kernels instead of claiming every SM's shared memory (when frames did fail, they work through them slowly)
     if (kp.frame_list && grid > kFallbackCtas) grid = kFallbackCtas;
-    // SM partition (temporal head): the head kernel of step i runs on `head_ctas` SMs beside the tip-cell kernels of step i + 1
-    // (tensor-bound, on the other SMs); launched as 2-CTA clusters so that its CTAs fill whole TPCs and leave the others to the
-    // tip kernels' CTA pairs
-    int cluster = 1;
-    if (EPI == EPI_SPEC && !kp.frame_list && kp.head_ctas >= 2 && kp.head_ctas < grid) { grid = kp.head_ctas & ~1; cluster = 2; }
     if (grid < 1) return VD_OK;
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)Cfg::THREADS); cfg.dynamicSmemBytes = Cfg::SMEM_BYTES; cfg.stream = stream;
-    cudaLaunchAttribute attr[2];
+    cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = getenv("VD_PDL") ? 1 : 0;   // measured slower in the pipeline (43.2 vs 38.6 us/step): off unless asked for
     cfg.attrs = attr; cfg.numAttrs = 1;
-    if (cluster > 1) {
-        attr[1].id = cudaLaunchAttributeClusterDimension;
-        attr[1].val.clusterDim.x = (unsigned)cluster; attr[1].val.clusterDim.y = 1; attr[1].val.clusterDim.z = 1;
-        cfg.numAttrs = 2;
-    }
     VD_CUDA(cudaLaunchKernelEx(&cfg, kern, maps, kp));
     VD_LAUNCH_CHECK();
     return VD_OK;
@@ -1716,6 +1709,61 @@ static int launch_pred(const HeadMaps& maps, const HeadKernelParams& kp, cudaStr
     return set_error(VD_ERR_INVALID_ARG, "pred_conv: bad padded width %d", kp.n_pad);
 }
 
+// The fused tip-cell + head kernel (tfused.cuh) replaces the temporal_conv + head_kernel<EPI_SPEC> launches where it applies.
+static bool tfused_applicable(const VdHeadParams* hp, const HeadPlan& pl, bool spec) {
+    static const bool on = []() { const char* e = getenv("VD_TFUSED"); return e ? atoi(e) != 0 : true; }();
+    if (!on || !spec || (hp->flags & VD_HEAD_NO_FUSED_TIP)) return false;
+    if (pl.n_pass != 1 || pl.repack || hp->precision != VD_PREC_BF16 || hp->join != VD_JOIN_NONE || pl.kp.K_frames != 1) return false;
+    if (!tfused_supported(pl.C) || hp->T < 1 || hp->frames <= 0 || hp->frames % hp->T) return false;
+    for (int s = 0; s < hp->num_scales; ++s) {
+        const VdHeadScale& sc = hp->scale[s];
+        if (!sc.tconv_weight_bf16 || !sc.tconv_scale || !sc.tconv_shift || !sc.tconv_out_nhwc_bf16) return false;
+        if (sc.Cin % F_NT || sc.Cin > 1024) return false;
+        if ((long long)(hp->frames / hp->T) * ceil_div(hp->T * sc.H * sc.W, F_BLOCK_M) < 2) return false;
+    }
+    return true;
+}
+
+static int run_tfused(const VdHeadParams* hp, const HeadPlan& pl, const HeadKernelParams& kp, cudaStream_t stream) {
+    const char* e_dbg = getenv("VD_TFUSED_DBG");            // profiling aids (results are garbage): bit 0 = no decode / filter epilogue;
+    const char* e_scl = getenv("VD_TFUSED_SCALES");         // bit mask of the scales to launch
+    const int dbg = e_dbg ? atoi(e_dbg) : 0, scl = e_scl ? atoi(e_scl) : 7;
+    for (int s = 0; s < hp->num_scales; ++s) {
+        const VdHeadScale& sc = hp->scale[s];
+        if (!((scl >> s) & 1)) continue;
+        FusedParams fp;
+        memset(&fp, 0, sizeof(fp));
+        fp.B = hp->frames / hp->T; fp.T = hp->T; fp.HW = sc.H * sc.W; fp.Cin = sc.Cin; fp.rows = hp->T * sc.H * sc.W;
+        fp.m_tiles = ceil_div(fp.rows, F_BLOCK_M); fp.n_chunks = sc.Cin / F_NT;
+        fp.scale = sc.tconv_scale; fp.shift = sc.tconv_shift; fp.slope = 0.1f;
+        fp.s = s; fp.g = kp.g; fp.bias = kp.bias[s]; fp.c_valid = kp.c_valid; fp.valid_thresh = hp->valid_thresh;
+        fp.boxes = kp.boxes; fp.spec_lists = kp.spec_lists; fp.spec_cnt = kp.spec_cnt; fp.spec_tau = kp.spec_tau;
+        fp.tile_counter = kp.tile_counter; fp.ws_magic = kp.ws_magic; fp.frames = hp->frames; fp.dbg = dbg;
+        fp.stamps = kp.stamps;
+        FusedMaps maps;
+        const uint64_t Cin = (uint64_t)sc.Cin, HW = (uint64_t)sc.H * sc.W;
+        const int wstride = sc.tip_window_stride_frames > 0 ? sc.tip_window_stride_frames : hp->T;
+        uint64_t dimsX[3] = {Cin, (uint64_t)fp.rows, (uint64_t)fp.B};
+        uint64_t strX[2] = {Cin * 2, (uint64_t)wstride * HW * Cin * 2};
+        uint32_t boxX[3] = {F_BLOCK_K, F_BLOCK_M, 1};
+        int rc = encode_tmap_bf16(&maps.x, sc.tip_nhwc_bf16, 3, dimsX, strX, boxX);
+        if (rc) return rc;
+        uint64_t dimsW[3] = {Cin, Cin, 3};
+        uint64_t strW[2] = {Cin * 2, Cin * Cin * 2};
+        uint32_t boxW[3] = {F_BLOCK_K, F_NT / 2, 1};
+        rc = encode_tmap_bf16(&maps.w, sc.tconv_weight_bf16, 3, dimsW, strW, boxW);
+        if (rc) return rc;
+        uint64_t dimsP[2] = {Cin, (uint64_t)3 * (5 + pl.C)};
+        uint64_t strP[1] = {Cin * 2};
+        uint32_t boxP[2] = {F_BLOCK_K, (uint32_t)(pl.n_pad / 2)};
+        rc = encode_tmap_bf16(&maps.wp, sc.weight_bf16, 2, dimsP, strP, boxP);
+        if (rc) return rc;
+        rc = launch_tfused(maps, fp, pl.C, stream);
+        if (rc) return rc;
+    }
+    return VD_OK;
+}
+
 }  // namespace vd
 
 using namespace vd;
@@ -1747,8 +1795,15 @@ extern "C" int vd_head_launch_count(const VdHeadParams* hp) {
     if (make_plan(hp, &pl) != VD_OK) return -1;
     int n = getenv("VD_NO_SPEC") ? 1 + pl.n_pass : 2 + 2 * pl.n_pass;   // head kernel per class window + per-frame NMS kernel (+ the exact fallback pair, idle in the steady state)
     for (int s = 0; s < hp->num_scales; ++s) if (hp->scale[s].tconv_weight_bf16) ++n;
+    if (tfused_applicable(hp, pl, getenv("VD_NO_SPEC") == nullptr)) n += hp->num_scales - 1;     // fused: one kernel per scale instead of ONE head kernel; the tip cells (counted above) become the conditional launches of the exact path
     if (pl.repack) n += hp->num_scales * pl.n_pass;               // weight re-layout per (scale, window)
     return n;
+}
+
+extern "C" int vd_head_fused_tip(const VdHeadParams* hp) {
+    HeadPlan pl;
+    if (make_plan(hp, &pl) != VD_OK) return -1;
+    return tfused_applicable(hp, pl, getenv("VD_NO_SPEC") == nullptr) ? 1 : 0;
 }
 
 extern "C" int vd_head_forward(const VdHeadParams* hp, float* ids, float* scores, float* bboxes,
@@ -1795,13 +1850,13 @@ extern "C" int vd_head_forward_stages(const VdHeadParams* hp, float* ids, float*
     const bool spec = getenv("VD_NO_SPEC") == nullptr;   // speculative frame-level threshold with the exact path as fallback
     kp.valid_thresh = hp->valid_thresh; kp.k = k; kp.cap = (k <= 448) ? 640 : kListCap;
     { const char* e = getenv("VD_HEAD_PREFETCH"); kp.prefetch = e ? atoi(e) : 0; }
-    { const char* e = getenv("VD_HEAD_CTAS"); kp.head_ctas = e ? atoi(e) : 0; }
-    kp.stamps = getenv("VD_DEBUG_HEAD_STAMPS") ? (long long*)(ws + pl.off_listsA) : nullptr;   // profiling aid (unused merge area)
+    kp.stamps = (getenv("VD_DEBUG_HEAD_STAMPS") || getenv("VD_TFUSED_STAMPS")) ? (long long*)(ws + pl.off_listsA) : nullptr;   // profiling aid (unused merge area)
     if (const char* e = getenv("VD_DEBUG_SKIP_EPILOGUE")) kp.dbg = atoi(e);     // profiling aid: results are garbage
 
+    const bool fused_tip = tfused_applicable(hp, pl, spec);      // tip cell + head in one kernel per scale (tfused.cuh): the TCONV stage is empty
     for (int s = 0; s < hp->num_scales; ++s) {      // optional temporal tip cell in front (layers.py:82-89)
         const VdHeadScale& sc = hp->scale[s];
-        if (sc.tconv_weight_bf16 && (stage_mask & VD_STAGE_TCONV)) {
+        if (sc.tconv_weight_bf16 && (stage_mask & VD_STAGE_TCONV) && !fused_tip) {
             VD_CHECK_ARG(sc.tconv_out_nhwc_bf16 && sc.tconv_scale && sc.tconv_shift, "head_forward: scale %d temporal cell needs out/scale/shift", s);
             VD_CHECK_ARG(hp->T >= 1 && hp->frames % hp->T == 0, "head_forward: frames %d not a multiple of T %d", hp->frames, hp->T);
             rc = vd_temporal_conv_ex(sc.tip_nhwc_bf16, sc.tconv_out_nhwc_bf16, hp->frames / hp->T, hp->T, sc.H, sc.W, sc.Cin,
@@ -1816,7 +1871,12 @@ extern "C" int vd_head_forward_stages(const VdHeadParams* hp, float* ids, float*
         // any other state is detected on the device and handled exactly
         rc = repack_windows(hp, pl, ws, stream);
         if (rc) return rc;
-        for (int ps = 0; ps < pl.n_pass; ++ps) {       // one launch per class window (1 unless num_class > 80), all appending to the frames' lists
+        if (fused_tip) {
+            window_params(hp, pl, ws, 0, &kp, wptr);
+            rc = run_tfused(hp, pl, kp, stream);
+            if (rc) return rc;
+        }
+        for (int ps = 0; ps < pl.n_pass && !fused_tip; ++ps) {       // one launch per class window (1 unless num_class > 80), all appending to the frames' lists
             window_params(hp, pl, ws, ps, &kp, wptr);
             rc = make_maps(hp, pl, &maps, wptr);
             if (rc) return rc;
@@ -1858,6 +1918,15 @@ extern "C" int vd_head_forward_stages(const VdHeadParams* hp, float* ids, float*
         kp.spec_lists, kp.spec_cnt, kp.spec_state, kp.spec_tau, failed, kp.tile_counter, kp.ws_magic, hp->valid_thresh, P, src, sink);
     VD_LAUNCH_CHECK();
     // 2. exact path over the queued frames (both kernels return at once when the queue is empty -- the steady state)
+    if (fused_tip) {
+        // the fused kernel kept the tip on chip: the exact path reads it from memory, so the tip cells run first -- only if a frame failed
+        for (int s = 0; s < hp->num_scales; ++s) {
+            const VdHeadScale& sc = hp->scale[s];
+            rc = temporal_conv_impl(sc.tip_nhwc_bf16, sc.tconv_out_nhwc_bf16, hp->frames / hp->T, hp->T, sc.H, sc.W, sc.Cin, sc.tconv_weight_bf16,
+                                    sc.tconv_scale, sc.tconv_shift, 0.1f, VD_PREC_BF16, sc.tip_window_stride_frames, kp.spec_state + 2, failed, stream_);
+            if (rc) return rc;
+        }
+    }
     for (int ps = 0; ps < pl.n_pass; ++ps) {
         HeadKernelParams kf = kp;
         window_params(hp, pl, ws, ps, &kf, wptr);

@@ -194,10 +194,13 @@ __device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile
 __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
-// arrive on the same barrier (same shared-memory offset) of CTA `cta` of the cluster
+// arrive on the same barrier (same shared-memory offset) of CTA `cta` of the cluster.  Default semantics (.release.cta): what the
+// arrivals hand over is ordered by its own fence (tcgen05.fence::before_thread_sync for TMEM reads, fence.proxy.async for staged
+// shared-memory tiles).  The .release.cluster form compiles to MEMBAR.ALL.GPU -- measured: ~3 k cycles per arrive, it made the
+// epilogue of the CTA-pair kernels (not their mainloop) the bottleneck.
 __device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t cta) {
     asm volatile("{\n\t.reg .b32 ra;\n\tmapa.shared::cluster.u32 ra, %0, %1;\n\t"
-                 "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}" ::"r"(smem_u32(bar)), "r"(cta) : "memory");
+                 "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}" ::"r"(smem_u32(bar)), "r"(cta) : "memory");
 }
 // wait on a local barrier whose arrivals come from the peer CTA (cluster-scope acquire); bounded like mbar_wait
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
@@ -226,6 +229,11 @@ __device__ __forceinline__ void tma_load_5d_pair(void* smem_dst, const CUtensorM
     asm volatile(
         "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
         ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorMap* m, uint32_t bar_cluster_addr, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr), "r"(c0), "r"(c1) : "memory");
 }
 __device__ __forceinline__ void tma_load_3d_pair(void* smem_dst, const CUtensorMap* m, uint32_t bar_cluster_addr, int c0, int c1, int c2) {
     asm volatile(

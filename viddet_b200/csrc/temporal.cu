@@ -30,6 +30,10 @@ struct TConvParams {
     int planes, n_prod;
     signed char a_pl[8], w_pl[8];
     long long y_plane_stride;      // elements between output planes
+    int prefetch;                  // pair kernel: L2 prefetch of the next item's activation boxes (VD_TCONV_PREFETCH, default on)
+    const unsigned int* frame_list; // pair kernel, with cond: only the windows of the listed frames (frame_list[0 .. *cond)) are computed -- the exact
+                                   // fallback of the fused temporal head needs the tip of the frames it redoes, nothing else
+    const unsigned int* cond;      // non-null: the launch does nothing when *cond == 0 (the fused head's exact fallback recomputes the tip only when frames failed)
     int dbg;                       // profiling aid (VD_TCONV_DBG=1): the epilogue releases its accumulator without BN / stores, results are garbage
 };
 struct TConvMaps { CUtensorMap x; CUtensorMap w; CUtensorMap y; };      // y: output map of the pair kernel's TMA-store epilogue, box {64 ch, 128 rows, 1}
@@ -53,6 +57,7 @@ template <int NT>
 __global__ void __launch_bounds__(T_THREADS, 1)
 temporal_conv_kernel(const __grid_constant__ TConvMaps maps, const __grid_constant__ TConvParams p) {
     using Cfg = TConvCfg<NT>;
+    if (p.cond && *p.cond == 0u) return;
     extern __shared__ unsigned char smem_dyn[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
     unsigned char* ring = smem;
@@ -302,6 +307,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(T_THREADS, 1)
 temporal_conv_pair_kernel(const __grid_constant__ TConvMaps maps, const __grid_constant__ TConvParams p) {
     using Cfg = T2Cfg;
     constexpr int NT = Cfg::NT;
+    if (p.cond && *p.cond == 0u) return;                         // both CTAs of the pair read the same word
     extern __shared__ unsigned char smem_dyn[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
     unsigned char* ring = smem;
@@ -328,11 +334,20 @@ temporal_conv_pair_kernel(const __grid_constant__ TConvMaps maps, const __grid_c
     const uint32_t tmem_base = sh->tmem_base;
     const int kb_per_tap = p.C / T_BLOCK_K;
     const int m_total = p.B * p.m_tiles;                       // 128-row tiles over all windows
-    const int total_pairs = ((m_total + 1) >> 1) * p.n_tiles;
+    const int pairs_per_win = (p.m_tiles + 1) >> 1;
+    const int n_listed = p.frame_list ? (int)*p.cond : 0;      // list mode: windows of the listed frames only (pairs do not straddle windows)
+    const int total_pairs = p.frame_list ? n_listed * pairs_per_win * p.n_tiles : ((m_total + 1) >> 1) * p.n_tiles;
 
     // pair -> (window b, row block mt) of CTA r, channel block nt; past the last tile: b == B (pure padding, nothing stored)
     auto coords = [&](int pair, uint32_t r, int& b, int& mt, int& nt) {
         nt = pair % p.n_tiles;
+        if (p.frame_list) {
+            const int qq = pair / p.n_tiles, wi = qq / pairs_per_win;
+            mt = (qq - wi * pairs_per_win) * 2 + (int)r;
+            b = mt < p.m_tiles ? (int)(p.frame_list[wi] / (unsigned)p.T) : p.B;
+            if (mt >= p.m_tiles) mt = 0;
+            return;
+        }
         const int m = (pair / p.n_tiles) * 2 + (int)r;
         mt = m % p.m_tiles; b = m / p.m_tiles;
     };
@@ -351,6 +366,10 @@ temporal_conv_pair_kernel(const __grid_constant__ TConvMaps maps, const __grid_c
             int stage = 0; uint32_t phase = 0;
             for (int pair = cluster_id; pair < total_pairs; pair += num_clusters) {
                 int b, mt, nt; coords(pair, rank, b, mt, nt);
+                // L2 prefetch of the NEXT item's activation boxes, one per k-block of this item: the shared-memory ring (4-5 stages =
+                // ~1 us of MMA work) covers an L2 hit but not a first touch that goes to HBM under load
+                int b2 = p.B, mt2 = 0, nt2 = 0;
+                if (p.prefetch && pair + num_clusters < total_pairs) coords(pair + num_clusters, rank, b2, mt2, nt2);
                 for (int tap = 0; tap < 3; ++tap) {
                     const int dt = tap - 1;
                     if (!tap_active(pair, dt)) continue;
@@ -359,6 +378,7 @@ temporal_conv_pair_kernel(const __grid_constant__ TConvMaps maps, const __grid_c
                         unsigned char* a_dst = ring + stage * Cfg::STAGE_BYTES;
                         if (rank == 0) tc::mbar_expect_tx(&sh->full[stage], 2u * Cfg::STAGE_BYTES);
                         const uint32_t bar = tc::mapa_u32(&sh->full[stage], 0u);
+                        if (b2 < p.B) tc::tma_prefetch_3d(&maps.x, kb * T_BLOCK_K, mt2 * T_BLOCK_M + dt * p.HW, b2);
                         tc::tma_load_3d_pair(a_dst, &maps.x, bar, kb * T_BLOCK_K, mt * T_BLOCK_M + dt * p.HW, b);
                         tc::tma_load_3d_pair(a_dst + Cfg::A_BYTES, &maps.w, bar, kb * T_BLOCK_K, nt * NT + (int)rank * (NT / 2), tap);
                         if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
@@ -482,7 +502,7 @@ static int launch_tconv_pair(const TConvMaps& maps, const TConvParams& p, cudaSt
     { int rc_ = configure_kernel((const void*)kern, T2Cfg::SMEM_BYTES, false); if (rc_) return rc_; }
     const long long pairs = ((long long)p.B * p.m_tiles + 1) / 2 * p.n_tiles;
     long long clusters = sm_count() / 2;
-    { static const int cap = []() { const char* e = getenv("VD_TCONV_CTAS"); return e ? atoi(e) : 0; }(); if (cap >= 2 && cap / 2 < clusters) clusters = cap / 2; }   // SM partition: leave SMs to a concurrent head kernel
+    if (p.frame_list && clusters > 16) clusters = 16;      // exact-fallback launch (idle in the steady state): a handful of CTAs, like the fallback head kernel
     if (clusters > pairs) clusters = pairs;
     kern<<<(unsigned)(2 * clusters), T_THREADS, T2Cfg::SMEM_BYTES, stream>>>(maps, p);
     VD_LAUNCH_CHECK();
@@ -513,6 +533,12 @@ extern "C" int vd_temporal_conv(const void* x, void* y, int B, int T, int H, int
 extern "C" int vd_temporal_conv_ex(const void* x, void* y, int B, int T, int H, int W, int C,
                                    const void* weight, const float* scale, const float* shift,
                                    float slope, int precision, int window_stride_frames, void* stream_) {
+    return vd::temporal_conv_impl(x, y, B, T, H, W, C, weight, scale, shift, slope, precision, window_stride_frames, nullptr, nullptr, stream_);
+}
+
+int vd::temporal_conv_impl(const void* x, void* y, int B, int T, int H, int W, int C,
+                           const void* weight, const float* scale, const float* shift,
+                           float slope, int precision, int window_stride_frames, const unsigned int* cond, const unsigned int* frame_list, void* stream_) {
     VD_CHECK_ARG(weight && scale && shift && (B == 0 || (x && y)), "temporal_conv: null pointer");
     VD_CHECK_ARG(B >= 0 && T >= 1 && H > 0 && W > 0, "temporal_conv: bad shape");
     VD_CHECK_ARG(C >= 128 && C % 128 == 0 && C <= 1024, "temporal_conv: C = %d must be a multiple of 128, at most 1024", C);
@@ -534,9 +560,10 @@ extern "C" int vd_temporal_conv_ex(const void* x, void* y, int B, int T, int H, 
     long long total = (long long)B * p.m_tiles * p.n_tiles;
     VD_CHECK_ARG(total < (1ll << 31), "temporal_conv: too many tiles");
     p.total_tiles = (int)total;
-    p.scale = scale; p.shift = shift; p.slope = slope; p.y = (__nv_bfloat16*)y;
+    p.scale = scale; p.shift = shift; p.slope = slope; p.y = (__nv_bfloat16*)y; p.cond = cond; p.frame_list = frame_list;
     p.planes = planes; p.n_prod = 1; p.y_plane_stride = (long long)B * p.rows * C;
     { static const int dbg = []() { const char* e = getenv("VD_TCONV_DBG"); return e ? atoi(e) : 0; }(); p.dbg = dbg; }
+    { static const int pf = []() { const char* e = getenv("VD_TCONV_PREFETCH"); return e ? atoi(e) : 1; }(); p.prefetch = pf; }
     if (planes > 1) {                      // same plane products as the head kernel (head.cu split_products): low-order first, p0 w0 last
         static const signed char a3[6] = {0, 2, 1, 0, 1, 0}, w3[6] = {2, 0, 1, 1, 0, 0};
         static const signed char a2[3] = {0, 1, 0}, w2[3] = {1, 0, 0};
@@ -556,6 +583,7 @@ extern "C" int vd_temporal_conv_ex(const void* x, void* y, int B, int T, int H, 
     uint32_t boxW[3] = {T_BLOCK_K, (uint32_t)(pair ? NT / 2 : NT), 1};
     rc = encode_tmap_bf16(&maps.w, weight, 3, dimsW, strW, boxW);
     if (rc) return rc;
+    if (!pair) p.frame_list = nullptr;                     // the 1-CTA kernels recompute every window (still only when *cond != 0)
     if (pair) {
         uint64_t dimsY[3] = {(uint64_t)C, (uint64_t)p.rows, (uint64_t)B};
         uint64_t strY[2] = {(uint64_t)C * 2, (uint64_t)p.rows * C * 2};

@@ -1,0 +1,461 @@
+// temporal_head_fused_kernel -- cfg 4 in ONE kernel per scale (SURVEY section 7, K4 -> K1):
+//   temporal (3,1,1) tip cell (Conv3D + BN + LeakyReLU, layers.py:82-89; yolo3_temporal.py:226-227)
+//   -> 1x1 prediction conv (yolo3.py:62,157) -> YOLOOutputV3 decode (yolo3.py:158-199) -> speculative candidate filter
+// The tip tile never leaves the SM: the tip GEMM's accumulator (TMEM) goes through BN / LeakyReLU / bf16 rounding into shared
+// memory in the K-major 128-byte-swizzled layout of a UMMA A operand, and the prediction GEMM multiplies it from there.
+// Included by head.cu (uses HeadGeom / kSpecCap and the decode math of common.cuh); results are bit-identical to the unfused
+// chain temporal_conv_pair_kernel -> head_kernel<EPI_SPEC> (same bf16 tip bits, same K order of the prediction GEMM).
+//
+// CTA pair (tcgen05 cta_group::2), persistent; an item = two consecutive 128-row tiles of the flattened (window, T*HW) row axis,
+// all channel chunks of 256:
+//   warp 0 (both CTAs)   TMA producer: per k-block its own A tile [128 rows x 64 ch] of the shifted frame + half of the tap's weight
+//                        tile [128 x 64]; per chunk its half of the prediction weights [NPAD/2 x 256 ch]
+//   warp 1 (leader CTA)  MMA issuer: tip GEMM M256 x N256 x K(3 taps x Cin) into TMEM cols [0,256) (single buffer), then the
+//                        prediction GEMM M256 x NPAD x K256 from the staged tip chunk into one of two prediction accumulators
+//                        (TMEM cols [256,384) / [384,512)): accumulates over the chunks
+//   warps 2-9            per chunk: tcgen05.ld -> BN -> LeakyReLU -> bf16 -> st.shared (swizzled) -> fence.proxy.async -> arrive;
+//                        after an item's last chunk: decode + candidate filter on the prediction accumulator (the EPI_SPEC epilogue of
+//                        head_kernel; a tile spans up to two frames here, so frame / cell are per lane and candidates go to their
+//                        frame's list with one atomic each -- ~0.3 % of the class logits pass)
+// The tip accumulator is single-buffered: these kernels are bound by the L2 -> SM operand traffic, not by the tensor pipe (measured:
+// same time at 1.9 and 1.5 GHz SM clock), so the pipe has slack and the operand ring keeps filling while an accumulator drains.
+#pragma once
+
+namespace vd {
+
+constexpr int F_THREADS = 320;
+constexpr int F_BLOCK_M = 128;
+constexpr int F_BLOCK_K = 64;
+constexpr int F_NT = 256;                    // tip channels per chunk = K of one prediction-GEMM step
+
+struct FusedParams {
+    int B, T, HW, Cin, rows;                 // windows, frames per window, pixels per frame, channels, rows = T*HW
+    int m_tiles, n_chunks;                   // 128-row tiles per window, Cin / 256
+    const float* scale; const float* shift; float slope;      // folded BN of the tip cell
+    int s;                                   // scale index in g
+    HeadGeom g;
+    const float* bias;                       // prediction bias of this scale (3*(5+C)) or null
+    int c_valid;                             // classes actually present (<= C)
+    float valid_thresh;
+    float4* boxes; uint64_t* spec_lists; uint32_t* spec_cnt; const uint32_t* spec_tau;
+    const unsigned int* tile_counter; unsigned int ws_magic;
+    int frames;
+    int dbg;                                 // profiling aid (VD_TFUSED_DBG): 1 = skip the decode / filter epilogue
+    long long* stamps;                       // profiling aid (VD_TFUSED_STAMPS): clock64 per chunk of cluster 0's leader CTA, [chunk][16]
+};
+struct FusedMaps { CUtensorMap x, w, wp; };
+
+template <int C, int NPAD> struct FusedCfg {
+    static constexpr int A_BYTES = F_BLOCK_M * F_BLOCK_K * 2;
+    static constexpr int B_BYTES = (F_NT / 2) * F_BLOCK_K * 2;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int STAGES = 4;
+    static constexpr int STG_TILE = F_BLOCK_M * F_BLOCK_K * 2;            // one k-block of the staged tip chunk
+    static constexpr int STG_BYTES = (F_NT / F_BLOCK_K) * STG_TILE;
+    static constexpr int WP_ROWS = NPAD / 2;                              // this CTA's half of the prediction weights
+    static constexpr int WP_TILE = WP_ROWS * F_BLOCK_K * 2;
+    static constexpr int WP_BYTES = (F_NT / F_BLOCK_K) * WP_TILE;
+    static constexpr int CPA = (C + 15) / 16;
+    static constexpr int CH = (C + CPA - 1) / CPA;
+    static constexpr int CH4 = (CH + 3) / 4 * 4;
+    static constexpr int CBIAS_BYTES = 3 * CPA * CH4 * 4;
+    static constexpr int BIAS_BYTES = NPAD * 4;
+    static constexpr int SH_BYTES = 1024;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STG_BYTES + WP_BYTES + CBIAS_BYTES + BIAS_BYTES + SH_BYTES + 1024;
+    static_assert(WP_ROWS % 8 == 0 && NPAD % 16 == 0 && NPAD <= 128, "prediction width");
+    static_assert(3 * (5 + C) <= NPAD, "NPAD");
+    static_assert(SMEM_BYTES <= 227 * 1024, "shared memory");
+};
+
+struct FusedShared {
+    uint64_t full[4], empty[4];
+    uint64_t tip_full, tip_empty, wp_full, wp_empty, stg_full, stg_empty;
+    uint64_t pred_full[2], pred_empty[2];
+    uint32_t tmem_base;
+};
+
+template <int C, int NPAD>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(F_THREADS, 1)
+temporal_head_fused_kernel(const __grid_constant__ FusedMaps maps, const __grid_constant__ FusedParams p) {
+    using Cfg = FusedCfg<C, NPAD>;
+    constexpr int P = 5 + C;
+    constexpr int KB4 = F_NT / F_BLOCK_K;
+    extern __shared__ unsigned char smem_dyn[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+    unsigned char* ring = smem;
+    unsigned char* stg = ring + Cfg::STAGES * Cfg::STAGE_BYTES;            // staged tip chunk: KB4 tiles [128 rows x 64 ch], swizzled
+    unsigned char* wpb = stg + Cfg::STG_BYTES;                             // prediction weights of the chunk: KB4 tiles [WP_ROWS x 64 ch]
+    float* scbias = reinterpret_cast<float*>(wpb + Cfg::WP_BYTES);         // [3 anchors][CPA][CH4] class biases
+    float* sbias = scbias + Cfg::CBIAS_BYTES / 4;                          // [NPAD]
+    FusedShared* sh = reinterpret_cast<FusedShared*>(sbias + NPAD);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = tc::cluster_ctarank();
+    const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+
+    for (int i = threadIdx.x; i < NPAD; i += F_THREADS) sbias[i] = (p.bias && i < 3 * P) ? p.bias[i] : 0.0f;
+    for (int i = threadIdx.x; i < 3 * Cfg::CPA * Cfg::CH4; i += F_THREADS) {
+        const int a = i / (Cfg::CPA * Cfg::CH4), cc = (i / Cfg::CH4) % Cfg::CPA, ci = i % Cfg::CH4;
+        const int c = cc * Cfg::CH + ci;
+        scbias[i] = (p.bias && ci < Cfg::CH && c < C) ? p.bias[a * P + 5 + c] : 0.0f;
+    }
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < Cfg::STAGES; ++i) { tc::mbar_init(&sh->full[i], 1); tc::mbar_init(&sh->empty[i], 1); }
+        tc::mbar_init(&sh->tip_full, 1); tc::mbar_init(&sh->tip_empty, 16);
+        tc::mbar_init(&sh->wp_full, 1); tc::mbar_init(&sh->wp_empty, 1);
+        tc::mbar_init(&sh->stg_full, 16); tc::mbar_init(&sh->stg_empty, 1);
+        for (int i = 0; i < 2; ++i) { tc::mbar_init(&sh->pred_full[i], 1); tc::mbar_init(&sh->pred_empty[i], 16); }
+        tc::fence_barrier_init();
+        tc::prefetch_tmap(&maps.x); tc::prefetch_tmap(&maps.w); tc::prefetch_tmap(&maps.wp);
+    }
+    if (warp == 1) tc::tmem_alloc_2cta<512>(&sh->tmem_base);
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::cluster_sync_all();
+    tc::fence_after_sync();
+    const uint32_t tmem_base = sh->tmem_base;
+    const int kb_per_tap = p.Cin / F_BLOCK_K;
+    const int m_total = p.B * p.m_tiles;
+    const int total_items = (m_total + 1) >> 1;
+
+    auto coords = [&](int item, uint32_t r, int& b, int& mt) {
+        const int m = item * 2 + (int)r;
+        mt = m % p.m_tiles; b = m / p.m_tiles;                 // b == B: pure padding (zero rows in, nothing emitted)
+    };
+    auto tap_active1 = [&](int b, int mt, int dt) -> bool {
+        const int r0 = mt * F_BLOCK_M;
+        int r1 = r0 + F_BLOCK_M - 1; if (r1 > p.rows - 1) r1 = p.rows - 1;
+        return (b < p.B) && (r1 + dt * p.HW >= 0) && (r0 + dt * p.HW <= p.rows - 1);
+    };
+    auto tap_active = [&](int item, int dt) -> bool {
+        int b0, m0, b1, m1; coords(item, 0, b0, m0); coords(item, 1, b1, m1);
+        return tap_active1(b0, m0, dt) || tap_active1(b1, m1, dt);
+    };
+
+    if (warp == 0) {
+        // =========================== TMA producer (both CTAs) ===========================
+        if (tc::elect_one()) {
+            int stage = 0; uint32_t phase = 0; uint32_t cc = 0;
+            const uint32_t wp_bar = tc::mapa_u32(&sh->wp_full, 0u);
+            for (int item = cluster_id; item < total_items; item += num_clusters) {
+                int b, mt; coords(item, rank, b, mt);
+                int n_act = 0;
+                for (int tap = 0; tap < 3; ++tap) n_act += tap_active(item, tap - 1) ? 1 : 0;
+                const int n_kb = n_act * kb_per_tap;
+                // the chunk's prediction weights are requested with the chunk's LAST k-block: their (single) buffer is free once the previous
+                // chunk's prediction MMAs are done -- those are issued a few k-blocks into this chunk (MMA role) -- and they are needed
+                // only after this chunk's accumulator has been staged
+                const int wp_at = n_kb - 1;
+                for (int nt = 0; nt < p.n_chunks; ++nt, ++cc) {
+                    int kcount = 0;
+                    for (int tap = 0; tap < 3; ++tap) {
+                        const int dt = tap - 1;
+                        if (!tap_active(item, dt)) continue;
+                        for (int kb = 0; kb < kb_per_tap; ++kb, ++kcount) {
+                            if (kcount == wp_at) {
+                                if (p.stamps && blockIdx.x == 0 && cc < 200u) p.stamps[cc * 16 + 8] = clock64();
+                                tc::mbar_wait_cluster(&sh->wp_empty, (cc & 1u) ^ 1u);
+                                if (p.stamps && blockIdx.x == 0 && cc < 200u) p.stamps[cc * 16 + 9] = clock64();
+                                if (rank == 0) tc::mbar_expect_tx(&sh->wp_full, 2u * Cfg::WP_BYTES);
+#pragma unroll
+                                for (int j = 0; j < KB4; ++j)
+                                    tc::tma_load_2d_pair(wpb + j * Cfg::WP_TILE, &maps.wp, wp_bar, nt * F_NT + j * F_BLOCK_K, (int)rank * Cfg::WP_ROWS);
+                            }
+                            tc::mbar_wait_cluster(&sh->empty[stage], phase ^ 1u);
+                            unsigned char* a_dst = ring + stage * Cfg::STAGE_BYTES;
+                            if (rank == 0) tc::mbar_expect_tx(&sh->full[stage], 2u * Cfg::STAGE_BYTES);
+                            const uint32_t bar = tc::mapa_u32(&sh->full[stage], 0u);
+                            tc::tma_load_3d_pair(a_dst, &maps.x, bar, kb * F_BLOCK_K, mt * F_BLOCK_M + dt * p.HW, b);
+                            tc::tma_load_3d_pair(a_dst + Cfg::A_BYTES, &maps.w, bar, kb * F_BLOCK_K, nt * F_NT + (int)rank * (F_NT / 2), tap);
+                            if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // =========================== MMA issuer (leader CTA) ===========================
+        if (rank == 0 && tc::elect_one()) {
+            constexpr uint32_t idesc_tip = tc::make_idesc_bf16(2 * F_BLOCK_M, F_NT);
+            constexpr uint32_t idesc_pred = tc::make_idesc_bf16(2 * F_BLOCK_M, NPAD);
+            int stage = 0; uint32_t phase = 0; uint32_t cc = 0, ic = 0;
+            const uint32_t stg_addr = tc::smem_u32(stg), wp_addr = tc::smem_u32(wpb);
+            // The prediction GEMM of chunk c (A = the staged tip chunk of both CTAs, B = the chunk's prediction weights) is issued
+            // kPredAt k-blocks INTO the tip GEMM of chunk c + 1: by then the epilogue warps have staged chunk c, and the tensor pipe
+            // never waits for them (the tip accumulator itself is free as soon as they have read it)
+            constexpr int kPredAt = 3;
+            bool pending = false; uint32_t p_cc = 0, p_ic = 0; int p_nt = 0;
+            auto issue_pred = [&]() {
+                const uint32_t pb = p_ic & 1u;
+                const uint32_t d_pred = tmem_base + 256u + pb * 128u;
+                const bool st = p.stamps && blockIdx.x == 0 && p_cc < 200u;
+                if (st) p.stamps[p_cc * 16 + 3] = clock64();
+                tc::mbar_wait_cluster(&sh->wp_full, p_cc & 1u);
+                if (st) p.stamps[p_cc * 16 + 4] = clock64();
+                tc::mbar_wait_cluster(&sh->stg_full, p_cc & 1u);
+                if (p_nt == 0) tc::mbar_wait_cluster(&sh->pred_empty[pb], ((p_ic >> 1) & 1u) ^ 1u);
+                tc::fence_after_sync();
+                if (st) p.stamps[p_cc * 16 + 5] = clock64();
+#pragma unroll
+                for (int j = 0; j < KB4; ++j) {
+                    const uint64_t da = tc::make_smem_desc_sw128(stg_addr + (uint32_t)(j * Cfg::STG_TILE));
+                    const uint64_t db = tc::make_smem_desc_sw128(wp_addr + (uint32_t)(j * Cfg::WP_TILE));
+#pragma unroll
+                    for (int k = 0; k < F_BLOCK_K / 16; ++k)
+                        tc::umma_bf16_2cta(d_pred, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc_pred, (uint32_t)((p_nt | j | k) != 0));
+                }
+                tc::umma_commit_2cta(&sh->wp_empty);
+                tc::umma_commit_2cta(&sh->stg_empty);
+                if (p_nt == p.n_chunks - 1) tc::umma_commit_2cta(&sh->pred_full[pb]);
+                pending = false;
+            };
+            for (int item = cluster_id; item < total_items; item += num_clusters, ++ic) {
+                for (int nt = 0; nt < p.n_chunks; ++nt, ++cc) {
+                    const bool st = p.stamps && blockIdx.x == 0 && cc < 200u;
+                    if (st) p.stamps[cc * 16 + 0] = clock64();
+                    tc::mbar_wait_cluster(&sh->tip_empty, (cc & 1u) ^ 1u);          // the epilogue has read the previous chunk's accumulator
+                    tc::fence_after_sync();
+                    if (st) p.stamps[cc * 16 + 1] = clock64();
+                    uint32_t first = 1;
+                    int kcount = 0;
+                    for (int tap = 0; tap < 3; ++tap) {
+                        if (!tap_active(item, tap - 1)) continue;
+                        for (int kb = 0; kb < kb_per_tap; ++kb, ++kcount) {
+                            if (pending && kcount == kPredAt) issue_pred();
+                            tc::mbar_wait_cluster(&sh->full[stage], phase);
+                            tc::fence_after_sync();
+                            const uint32_t a_addr = tc::smem_u32(ring + stage * Cfg::STAGE_BYTES);
+                            const uint64_t da = tc::make_smem_desc_sw128(a_addr);
+                            const uint64_t db = tc::make_smem_desc_sw128(a_addr + Cfg::A_BYTES);
+#pragma unroll
+                            for (int k = 0; k < F_BLOCK_K / 16; ++k) {
+                                tc::umma_bf16_2cta(tmem_base, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc_tip, first ? 0u : 1u);
+                                first = 0;
+                            }
+                            tc::umma_commit_2cta(&sh->empty[stage]);
+                            if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
+                        }
+                    }
+                    if (pending) issue_pred();                                     // (a chunk shorter than kPredAt k-blocks)
+                    tc::umma_commit_2cta(&sh->tip_full);
+                    if (st) p.stamps[cc * 16 + 2] = clock64();
+                    pending = true; p_cc = cc; p_ic = ic; p_nt = nt;
+                }
+            }
+            if (pending) issue_pred();
+        }
+    } else {
+        // =========================== epilogue warps (both CTAs) ===========================
+        const int q = warp & 3;                               // TMEM lane quarter
+        const int half = (warp - 2) >> 2;                     // column half of the tip chunk / share of the class chunks
+        const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+        const int trow = q * 32 + lane;                       // row inside the tile
+        const uint32_t sw = (uint32_t)(trow & 7);
+        const uint32_t stg_row = tc::smem_u32(stg) + (uint32_t)trow * 128u;
+        const bool ws_ok = p.tile_counter[2] == p.ws_magic;   // the workspace holds thresholds of this layout
+        const int s = p.s;
+        const int HW = p.HW, Wd = p.g.W[s];
+        uint32_t cc = 0, ic = 0;
+        for (int item = cluster_id; item < total_items; item += num_clusters, ++ic) {
+            int b, mt; coords(item, rank, b, mt);
+            const int row = mt * F_BLOCK_M + trow;
+            const bool inb = (b < p.B) && (row < p.rows);
+            for (int nt = 0; nt < p.n_chunks; ++nt, ++cc) {
+                const bool st = p.stamps && blockIdx.x == 0 && warp == 2 && lane == 0 && cc < 200u;
+                tc::mbar_wait_cluster(&sh->tip_full, cc & 1u);
+                tc::fence_after_sync();
+                if (st) p.stamps[cc * 16 + 10] = clock64();
+                tc::mbar_wait_cluster(&sh->stg_empty, (cc & 1u) ^ 1u);             // the previous chunk's prediction MMAs have read the staging tiles
+                if (st) p.stamps[cc * 16 + 11] = clock64();
+                const uint32_t tbase = tmem_base + (uint32_t)(half * 128) + lane_addr;
+#pragma unroll 1
+                for (int pass = 0; pass < 2; ++pass) {
+                    uint32_t r[64];
+                    const uint32_t ta = tbase + (uint32_t)(pass * 64);
+                    tc::tmem_ld16(ta, r); tc::tmem_ld16(ta + 16, r + 16); tc::tmem_ld16(ta + 32, r + 32); tc::tmem_ld16(ta + 48, r + 48);
+                    tc::tmem_ld_wait();
+                    if (pass == 1) {                                              // this warp has read its share of the tip accumulator
+                        tc::fence_before_sync();
+                        __syncwarp();
+                        if (lane == 0) tc::mbar_arrive_cluster(&sh->tip_empty, 0u);
+                    }
+                    const int ch0 = nt * F_NT + half * 128 + pass * 64;
+                    // folded BN straight from global memory (2 x 4 KB at most, L1-resident): 8 KB of shared memory buy the 4th ring stage
+                    const float4* sc = reinterpret_cast<const float4*>(p.scale + ch0);
+                    const float4* sf = reinterpret_cast<const float4*>(p.shift + ch0);
+                    uint32_t packed[32];
+#pragma unroll
+                    for (int i = 0; i < 64; i += 4) {
+                        const float4 s4 = __ldg(sc + (i >> 2));
+                        const float4 f4 = __ldg(sf + (i >> 2));
+                        float v0 = fmaf(__uint_as_float(r[i]), s4.x, f4.x), v1 = fmaf(__uint_as_float(r[i + 1]), s4.y, f4.y);
+                        float v2 = fmaf(__uint_as_float(r[i + 2]), s4.z, f4.z), v3 = fmaf(__uint_as_float(r[i + 3]), s4.w, f4.w);
+                        v0 = v0 > 0.f ? v0 : v0 * p.slope; v1 = v1 > 0.f ? v1 : v1 * p.slope;
+                        v2 = v2 > 0.f ? v2 : v2 * p.slope; v3 = v3 > 0.f ? v3 : v3 * p.slope;
+                        __nv_bfloat162 h0 = __floats2bfloat162_rn(v0, v1), h1 = __floats2bfloat162_rn(v2, v3);
+                        packed[i / 2] = *reinterpret_cast<uint32_t*>(&h0); packed[i / 2 + 1] = *reinterpret_cast<uint32_t*>(&h1);
+                    }
+                    const uint32_t dst = stg_row + (uint32_t)((half * 2 + pass) * Cfg::STG_TILE);      // k-block (half*2+pass) of the chunk
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + (((uint32_t)j ^ sw) << 4)),
+                                     "r"(packed[4 * j]), "r"(packed[4 * j + 1]), "r"(packed[4 * j + 2]), "r"(packed[4 * j + 3]) : "memory");
+                }
+                tc::fence_proxy_async_smem();                                     // st.shared -> visible to the UMMA (async proxy) reads
+                __syncwarp();
+                if (lane == 0) tc::mbar_arrive_cluster(&sh->stg_full, 0u);
+                if (st) p.stamps[cc * 16 + 12] = clock64();
+            }
+
+            // ---- decode + speculative candidate filter on the item's prediction accumulator (head_kernel<EPI_SPEC>, per-lane frame)
+            const uint32_t pb = ic & 1u;
+            const bool st2 = p.stamps && blockIdx.x == 0 && warp == 2 && lane == 0 && cc - 1u < 200u;
+            tc::mbar_wait_cluster(&sh->pred_full[pb], (ic >> 1) & 1u);
+            tc::fence_after_sync();
+            if (st2) p.stamps[(cc - 1u) * 16 + 13] = clock64();
+            if (!(p.dbg & 1)) {
+                const int f = inb ? b * p.T + row / HW : 0;
+                const int cell = inb ? row % HW : 0;
+                uint32_t spec_tb;
+                {
+                    const uint32_t floor_b = p.valid_thresh > 0.0f ? __float_as_uint(p.valid_thresh) : 0u;
+                    const uint32_t hint = ws_ok ? __ldcg(p.spec_tau + f) : 0u;
+                    spec_tb = hint > floor_b ? hint : floor_b;
+                    if (spec_tb > 0x3f800001u) spec_tb = 0x3f800001u;
+                    if (!ws_ok) spec_tb = 0x3f800001u;                            // foreign workspace: emit nothing, the NMS kernel fails every frame
+                }
+                const uint32_t tb = tmem_base + 256u + pb * 128u + lane_addr;
+                float conf[3];
+                {
+                    uint32_t rb[3];
+#pragma unroll
+                    for (int a = 0; a < 3; ++a) tc::tmem_ld1(tb + (uint32_t)(a * P + 4), rb + a);
+                    tc::tmem_ld_wait();
+#pragma unroll
+                    for (int a = 0; a < 3; ++a) {
+                        conf[a] = vd_sigmoid(__uint_as_float(rb[a]) + sbias[a * P + 4]);
+                        if (!inb) conf[a] = __uint_as_float(0x7fc00000u);          // NaN: no score of a padding row passes `> valid_thresh`
+                    }
+                }
+                constexpr int CH = Cfg::CH, CPA = Cfg::CPA, CH4 = Cfg::CH4, REM = C - (CPA - 1) * CH;
+                const float vth = p.valid_thresh;
+                float ell[3];
+                {
+                    const float t = __fmul_rn(__uint_as_float(spec_tb), 0.999969482421875f);   // 1 - 2^-15
+#pragma unroll
+                    for (int a = 0; a < 3; ++a) {
+                        const float rr = __fmul_rn(t, vd_rcp(conf[a]));
+                        const float l = __fmul_rn(__fsub_rn(vd_lg2(rr), vd_lg2(__fsub_rn(1.0f, rr))), 0.6931471805599453f);
+                        float e = (rr < 1.0f) ? l : __uint_as_float(0x7f800000u);
+                        if (spec_tb == 0u) e = __uint_as_float(0xff800000u);
+                        if (!(conf[a] == conf[a])) e = __uint_as_float(0x7f800000u);
+                        if (spec_tb >= 0x3f800001u) e = __uint_as_float(0x7f800000u);
+                        ell[a] = e;
+                    }
+                }
+                const uint32_t HW3 = (uint32_t)HW * 3u;
+                const uint32_t row0 = (uint32_t)p.g.row_base[s] + (uint32_t)cell * 3u;       // + c*HW3 + a
+                uint64_t* fl = p.spec_lists + (size_t)f * kSpecCap;
+                uint32_t* fc = p.spec_cnt + f;
+                uint32_t emit_mask = 0u;
+                // the 3*CPA class chunks alternate between the two warps that share a TMEM lane quarter (half 0 / 1); the next chunk's
+                // TMEM read is in flight while the current one is compared
+                constexpr int NCH = 3 * CPA;
+                uint32_t rc[2][CH];
+                auto issue_j = [&](const int j, uint32_t* dst) {
+                    const int a = j / CPA, cx = j - a * CPA;
+                    const uint32_t col = tb + (uint32_t)(a * P + 5 + cx * CH);
+                    if (REM != CH && cx == CPA - 1) tc::tmem_ld<REM>(col, dst); else tc::tmem_ld<CH>(col, dst);
+                };
+                if (half < NCH) issue_j(half, rc[0]);
+                int par = 0;
+#pragma unroll 1
+                for (int j = half; j < NCH; j += 2, par ^= 1) {
+                    const int a = j / CPA, cx = j - a * CPA;
+                    const int n = (REM != CH && cx == CPA - 1) ? REM : CH;
+                    const float la = (a == 0) ? ell[0] : ((a == 1) ? ell[1] : ell[2]);
+                    const float ca = (a == 0) ? conf[0] : ((a == 1) ? conf[1] : conf[2]);
+                    float bv[CH4];
+#pragma unroll
+                    for (int i = 0; i < CH4; i += 4)
+                        *reinterpret_cast<float4*>(bv + i) = *reinterpret_cast<const float4*>(scbias + j * CH4 + i);
+                    tc::tmem_ld_wait();
+                    bool any = false;
+                    if (par == 0) {
+                        if (j + 2 < NCH) issue_j(j + 2, rc[1]);
+#pragma unroll
+                        for (int i = 0; i < CH; ++i) if (i < n) { bv[i] = __fadd_rn(__uint_as_float(rc[0][i]), bv[i]); any |= bv[i] >= la; }
+                    } else {
+                        if (j + 2 < NCH) issue_j(j + 2, rc[0]);
+#pragma unroll
+                        for (int i = 0; i < CH; ++i) if (i < n) { bv[i] = __fadd_rn(__uint_as_float(rc[1][i]), bv[i]); any |= bv[i] >= la; }
+                    }
+                    if (any) {                                                    // rare: ~0.3 % of the class logits pass
+#pragma unroll
+                        for (int i = 0; i < CH; ++i) {
+                            if (i < n && bv[i] >= la && cx * CH + i < p.c_valid) {
+                                const float scv = vd_score(bv[i], ca);
+                                if (scv > vth) {
+                                    emit_mask |= 1u << a;
+                                    const uint32_t kh = __float_as_uint(scv) | 0x80000000u;
+                                    const uint32_t krow = row0 + (uint32_t)(cx * CH + i) * HW3 + (uint32_t)a;
+                                    VD_DEV_CHECK(krow < (uint32_t)p.g.row_base[p.g.num_scales] && inb && f < p.frames);
+                                    const uint32_t pos = atomicAdd(fc, 1u);
+                                    if (pos < (uint32_t)kSpecCap) fl[pos] = ((uint64_t)kh << 32) | (uint32_t)~krow;
+                                }
+                            }
+                        }
+                    }
+                }
+                // raw box records of the emitting (pixel, anchor) pairs (decoded by the NMS kernel for the <= topk survivors)
+#pragma unroll
+                for (int a = 0; a < 3; ++a) {
+                    const bool mine = ((emit_mask >> a) & 1u) != 0u;
+                    if (__any_sync(0xffffffffu, mine)) {
+                        uint32_t r4[4];
+                        tc::tmem_ld<4>(tb + (uint32_t)(a * P), r4); tc::tmem_ld_wait();
+                        if (mine) p.boxes[(size_t)f * p.g.anc_base[p.g.num_scales] + p.g.anc_base[s] + cell * 3 + a] =
+                            make_float4(__uint_as_float(r4[0]) + sbias[a * P + 0], __uint_as_float(r4[1]) + sbias[a * P + 1],
+                                        __uint_as_float(r4[2]) + sbias[a * P + 2], __uint_as_float(r4[3]) + sbias[a * P + 3]);
+                    }
+                }
+                (void)Wd;
+            }
+            if (st2) p.stamps[(cc - 1u) * 16 + 14] = clock64();
+            tc::fence_before_sync();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive_cluster(&sh->pred_empty[pb], 0u);
+        }
+    }
+    __syncwarp();
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::cluster_sync_all();
+    if (warp == 1) tc::tmem_dealloc_2cta<512>(tmem_base);
+}
+
+template <int C, int NPAD>
+static int launch_tfused_t(const FusedMaps& maps, const FusedParams& p, cudaStream_t stream) {
+    using Cfg = FusedCfg<C, NPAD>;
+    auto kern = temporal_head_fused_kernel<C, NPAD>;
+    { int rc_ = configure_kernel((const void*)kern, Cfg::SMEM_BYTES, false); if (rc_) return rc_; }
+    const long long items = ((long long)p.B * p.m_tiles + 1) / 2;
+    long long clusters = sm_count() / 2; if (clusters > items) clusters = items;
+    if (clusters < 1) return VD_OK;
+    kern<<<(unsigned)(2 * clusters), F_THREADS, Cfg::SMEM_BYTES, stream>>>(maps, p);
+    VD_LAUNCH_CHECK();
+    return VD_OK;
+}
+
+// class counts the fused kernel is compiled for (the VID / VOC heads); anything else runs the unfused chain
+static bool tfused_supported(int C) { return C == 30 || C == 20; }
+
+static int launch_tfused(const FusedMaps& maps, const FusedParams& p, int C, cudaStream_t stream) {
+    switch (C) {
+        case 30: return launch_tfused_t<30, 112>(maps, p, stream);
+        case 20: return launch_tfused_t<20, 80>(maps, p, stream);
+        default: break;
+    }
+    return set_error(VD_ERR_UNSUPPORTED, "fused temporal head: no kernel shape for %d classes", C);
+}
+
+}  // namespace vd

@@ -476,8 +476,6 @@ def main():
                     help="iid: pool of distinct iid batches (default); video: batch t+1 = perturbed batch t; same: each session replays its own batch (r1 behaviour)")
     ap.add_argument("--pool", type=int, default=0, help="distinct resident input batches (default 32; 8 for the temporal workload)")
     ap.add_argument("--group", type=int, default=0, help="steps (batches) per persistent head-kernel launch (default %d; 1 for the temporal workload)" % GROUP)
-    ap.add_argument("--preroll-ms", type=float, default=-1.0, help="device-side pre-roll in front of the timed region (a spin kernel enqueued before the start event, so the timed launches are already queued when the clock starts); default 0.3")
-    ap.add_argument("--idle-ms", type=float, default=0.0, help="experiment: host sleep between the barrier and the timed region")
     ap.add_argument("--gather", default="peer", choices=["peer", "nccl"], help="multi-GPU detection gather: fused into the NMS sink over NVLink (peer) or staged NCCL all_gather")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -604,8 +602,6 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    preroll_ms = args.preroll_ms if args.preroll_ms >= 0 else 0.0
-    preroll_cycles = int(preroll_ms * 1e-3 * 1.9e9)
     sampler = make_sampler(local).start() if rank == 0 else None       # polling (and NVML's lazy init) is warm before the timed region
     # warm-up: at least --warmup steps, at least two turns of the ring (thresholds in every workspace), and every graph of the
     # timed region replayed once (the first replay of a CUDA graph pays its upload)
@@ -618,11 +614,7 @@ def main():
     st0 = [s.stats() for s in sessions]
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
-    if args.idle_ms > 0:
-        time.sleep(args.idle_ms * 1e-3)
     t_mono0 = time.monotonic()
-    if preroll_cycles:
-        torch.cuda._sleep(preroll_cycles)                 # untimed: the GPU is busy while the host enqueues the start event + the timed launches
     e0.record()
     run_steps(args.steps)
     if nccl_gather:

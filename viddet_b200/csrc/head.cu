@@ -1719,49 +1719,59 @@ static bool tfused_applicable(const VdHeadParams* hp, const HeadPlan& pl, bool s
         const VdHeadScale& sc = hp->scale[s];
         if (!sc.tconv_weight_bf16 || !sc.tconv_scale || !sc.tconv_shift || !sc.tconv_out_nhwc_bf16) return false;
         if (sc.Cin % F_NT || sc.Cin > 1024) return false;
-        if ((long long)(hp->frames / hp->T) * ceil_div(hp->T * sc.H * sc.W, F_BLOCK_M) < 2) return false;
+        const long long tiles = (long long)(hp->frames / hp->T) * ceil_div(hp->T * sc.H * sc.W, F_BLOCK_M);
+        if (tiles < 2 || tiles > 2 * 65000) return false;      // per-pair item ranges are 16-bit
     }
     return true;
 }
 
 static int run_tfused(const VdHeadParams* hp, const HeadPlan& pl, const HeadKernelParams& kp, cudaStream_t stream) {
     const char* e_dbg = getenv("VD_TFUSED_DBG");            // profiling aids (results are garbage): bit 0 = no decode / filter epilogue;
-    const char* e_scl = getenv("VD_TFUSED_SCALES");         // bit mask of the scales to launch
+    const char* e_scl = getenv("VD_TFUSED_SCALES");         // bit mask of the scales that get any work
     const int dbg = e_dbg ? atoi(e_dbg) : 0, scl = e_scl ? atoi(e_scl) : 7;
+    FusedParams fp;
+    FusedMaps maps;
+    memset(&fp, 0, sizeof(fp));
+    memset(&maps, 0, sizeof(maps));
+    fp.B = hp->frames / hp->T; fp.T = hp->T; fp.num_scales = hp->num_scales; fp.slope = 0.1f;
+    fp.g = kp.g; fp.c_valid = kp.c_valid; fp.valid_thresh = hp->valid_thresh;
+    fp.boxes = kp.boxes; fp.spec_lists = kp.spec_lists; fp.spec_cnt = kp.spec_cnt; fp.spec_tau = kp.spec_tau;
+    fp.tile_counter = kp.tile_counter; fp.ws_magic = kp.ws_magic; fp.frames = hp->frames; fp.dbg = dbg; fp.stamps = kp.stamps;
+    { const char* e = getenv("VD_TFUSED_PRED_AT"); fp.pred_at = e ? atoi(e) : 7; if (fp.pred_at < 0) fp.pred_at = 0; }   // tuning knob, see tfused.cuh
     for (int s = 0; s < hp->num_scales; ++s) {
         const VdHeadScale& sc = hp->scale[s];
-        if (!((scl >> s) & 1)) continue;
-        FusedParams fp;
-        memset(&fp, 0, sizeof(fp));
-        fp.B = hp->frames / hp->T; fp.T = hp->T; fp.HW = sc.H * sc.W; fp.Cin = sc.Cin; fp.rows = hp->T * sc.H * sc.W;
-        fp.m_tiles = ceil_div(fp.rows, F_BLOCK_M); fp.n_chunks = sc.Cin / F_NT;
-        fp.scale = sc.tconv_scale; fp.shift = sc.tconv_shift; fp.slope = 0.1f;
-        fp.s = s; fp.g = kp.g; fp.bias = kp.bias[s]; fp.c_valid = kp.c_valid; fp.valid_thresh = hp->valid_thresh;
-        fp.boxes = kp.boxes; fp.spec_lists = kp.spec_lists; fp.spec_cnt = kp.spec_cnt; fp.spec_tau = kp.spec_tau;
-        fp.tile_counter = kp.tile_counter; fp.ws_magic = kp.ws_magic; fp.frames = hp->frames; fp.dbg = dbg;
-        fp.stamps = kp.stamps;
-        FusedMaps maps;
+        FusedScale& q = fp.sc[s];
+        q.HW = sc.H * sc.W; q.Cin = sc.Cin; q.rows = hp->T * sc.H * sc.W;
+        q.m_tiles = ((scl >> s) & 1) ? ceil_div(q.rows, F_BLOCK_M) : 0; q.n_chunks = sc.Cin / F_NT;
+        q.scale = sc.tconv_scale; q.shift = sc.tconv_shift; q.bias = kp.bias[s];
         const uint64_t Cin = (uint64_t)sc.Cin, HW = (uint64_t)sc.H * sc.W;
         const int wstride = sc.tip_window_stride_frames > 0 ? sc.tip_window_stride_frames : hp->T;
-        uint64_t dimsX[3] = {Cin, (uint64_t)fp.rows, (uint64_t)fp.B};
+        uint64_t dimsX[3] = {Cin, (uint64_t)q.rows, (uint64_t)fp.B};
         uint64_t strX[2] = {Cin * 2, (uint64_t)wstride * HW * Cin * 2};
         uint32_t boxX[3] = {F_BLOCK_K, F_BLOCK_M, 1};
-        int rc = encode_tmap_bf16(&maps.x, sc.tip_nhwc_bf16, 3, dimsX, strX, boxX);
+        int rc = encode_tmap_bf16(&maps.x[s], sc.tip_nhwc_bf16, 3, dimsX, strX, boxX);
         if (rc) return rc;
         uint64_t dimsW[3] = {Cin, Cin, 3};
         uint64_t strW[2] = {Cin * 2, Cin * Cin * 2};
         uint32_t boxW[3] = {F_BLOCK_K, F_NT / 2, 1};
-        rc = encode_tmap_bf16(&maps.w, sc.tconv_weight_bf16, 3, dimsW, strW, boxW);
+        rc = encode_tmap_bf16(&maps.w[s], sc.tconv_weight_bf16, 3, dimsW, strW, boxW);
         if (rc) return rc;
         uint64_t dimsP[2] = {Cin, (uint64_t)3 * (5 + pl.C)};
         uint64_t strP[1] = {Cin * 2};
         uint32_t boxP[2] = {F_BLOCK_K, (uint32_t)(pl.n_pad / 2)};
-        rc = encode_tmap_bf16(&maps.wp, sc.weight_bf16, 2, dimsP, strP, boxP);
-        if (rc) return rc;
-        rc = launch_tfused(maps, fp, pl.C, stream);
+        rc = encode_tmap_bf16(&maps.wp[s], sc.weight_bf16, 2, dimsP, strP, boxP);
         if (rc) return rc;
     }
-    return VD_OK;
+    // The kernel takes every register of its SMs (168 x 12 warps' worth), so nothing shares them: the previous launch's per-frame NMS
+    // kernel runs in the gaps.  Leaving CTA pairs' SMs free for it (VD_TFUSED_SPARE_PAIRS = 1 / 2 / 4) measured 0.817 / 0.832 / 0.855 ms
+    // per step against 0.825 with none: no gain, off.
+    int spare = 0;
+    if (const char* e = getenv("VD_TFUSED_SPARE_PAIRS")) spare = atoi(e);
+    int clusters = sm_count() / 2 - (spare > 0 ? spare : 0);
+    if (clusters < 1) clusters = 1;
+    if (clusters > F_MAX_CLUSTERS) clusters = F_MAX_CLUSTERS;
+    tfused_schedule(&fp, clusters);
+    return launch_tfused(maps, fp, pl.C, clusters, stream);
 }
 
 }  // namespace vd
@@ -1795,7 +1805,8 @@ extern "C" int vd_head_launch_count(const VdHeadParams* hp) {
     if (make_plan(hp, &pl) != VD_OK) return -1;
     int n = getenv("VD_NO_SPEC") ? 1 + pl.n_pass : 2 + 2 * pl.n_pass;   // head kernel per class window + per-frame NMS kernel (+ the exact fallback pair, idle in the steady state)
     for (int s = 0; s < hp->num_scales; ++s) if (hp->scale[s].tconv_weight_bf16) ++n;
-    if (tfused_applicable(hp, pl, getenv("VD_NO_SPEC") == nullptr)) n += hp->num_scales - 1;     // fused: one kernel per scale instead of ONE head kernel; the tip cells (counted above) become the conditional launches of the exact path
+    // fused temporal head: same count -- ONE kernel (all scales) instead of the head kernel; the tip cells counted above become the
+    // conditional launches of the exact path
     if (pl.repack) n += hp->num_scales * pl.n_pass;               // weight re-layout per (scale, window)
     return n;
 }

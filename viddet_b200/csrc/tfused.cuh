@@ -27,23 +27,32 @@ constexpr int F_THREADS = 320;
 constexpr int F_BLOCK_M = 128;
 constexpr int F_BLOCK_K = 64;
 constexpr int F_NT = 256;                    // tip channels per chunk = K of one prediction-GEMM step
+constexpr int F_MAX_CLUSTERS = 80;           // CTA pairs of one launch (sm_count / 2 <= 80)
 
+// One launch covers every scale: an s32 item (4 chunks of K = 3072) costs ~14x an s8 item, and 224 of them over 74 CTA pairs were
+// 3.03 waves (a quarter of the launch lost to the last one).  The host deals the items of all scales to the pairs, largest first
+// (longest-processing-time greedy on a cost model), as one contiguous range per (scale, pair): beg[s][c] .. beg[s][c + 1].
+struct FusedScale {
+    int HW, Cin, rows, m_tiles, n_chunks;    // pixels per frame, channels, rows = T*HW, 128-row tiles per window, Cin / 256
+    const float* scale; const float* shift;  // folded BN of the tip cell
+    const float* bias;                       // prediction bias (3*(5+C)) or null
+};
 struct FusedParams {
-    int B, T, HW, Cin, rows;                 // windows, frames per window, pixels per frame, channels, rows = T*HW
-    int m_tiles, n_chunks;                   // 128-row tiles per window, Cin / 256
-    const float* scale; const float* shift; float slope;      // folded BN of the tip cell
-    int s;                                   // scale index in g
+    int B, T, num_scales;                    // windows, frames per window
+    float slope;
+    FusedScale sc[VD_MAX_SCALES];
+    unsigned short beg[VD_MAX_SCALES][F_MAX_CLUSTERS + 1];
     HeadGeom g;
-    const float* bias;                       // prediction bias of this scale (3*(5+C)) or null
     int c_valid;                             // classes actually present (<= C)
     float valid_thresh;
     float4* boxes; uint64_t* spec_lists; uint32_t* spec_cnt; const uint32_t* spec_tau;
     const unsigned int* tile_counter; unsigned int ws_magic;
     int frames;
+    int pred_at;                             // the prediction GEMM of a chunk is issued in front of k-block `pred_at` of the next chunk's tip GEMM
     int dbg;                                 // profiling aid (VD_TFUSED_DBG): 1 = skip the decode / filter epilogue
     long long* stamps;                       // profiling aid (VD_TFUSED_STAMPS): clock64 per chunk of cluster 0's leader CTA, [chunk][16]
 };
-struct FusedMaps { CUtensorMap x, w, wp; };
+struct FusedMaps { CUtensorMap x[VD_MAX_SCALES], w[VD_MAX_SCALES], wp[VD_MAX_SCALES]; };
 
 template <int C, int NPAD> struct FusedCfg {
     static constexpr int A_BYTES = F_BLOCK_M * F_BLOCK_K * 2;
@@ -54,58 +63,61 @@ template <int C, int NPAD> struct FusedCfg {
     static constexpr int STG_BYTES = (F_NT / F_BLOCK_K) * STG_TILE;
     static constexpr int WP_ROWS = NPAD / 2;                              // this CTA's half of the prediction weights
     static constexpr int WP_TILE = WP_ROWS * F_BLOCK_K * 2;
-    static constexpr int WP_BYTES = (F_NT / F_BLOCK_K) * WP_TILE;
+    static constexpr int WP_BYTES = (F_NT / F_BLOCK_K) * WP_TILE;          // one chunk's prediction weights travel through ONE ring stage
     static constexpr int CPA = (C + 15) / 16;
     static constexpr int CH = (C + CPA - 1) / CPA;
     static constexpr int CH4 = (CH + 3) / 4 * 4;
-    static constexpr int CBIAS_BYTES = 3 * CPA * CH4 * 4;
-    static constexpr int BIAS_BYTES = NPAD * 4;
+    static constexpr int CBIAS_BYTES = VD_MAX_SCALES * 3 * CPA * CH4 * 4;
+    static constexpr int BIAS_BYTES = VD_MAX_SCALES * NPAD * 4;
     static constexpr int SH_BYTES = 1024;
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STG_BYTES + WP_BYTES + CBIAS_BYTES + BIAS_BYTES + SH_BYTES + 1024;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STG_BYTES + CBIAS_BYTES + BIAS_BYTES + SH_BYTES + 1024;
     static_assert(WP_ROWS % 8 == 0 && NPAD % 16 == 0 && NPAD <= 128, "prediction width");
     static_assert(3 * (5 + C) <= NPAD, "NPAD");
-    static_assert(SMEM_BYTES <= 227 * 1024, "shared memory");
+    static_assert(SMEM_BYTES <= 227 * 1024 && WP_BYTES <= STAGE_BYTES, "shared memory");
 };
 
 struct FusedShared {
     uint64_t full[4], empty[4];
-    uint64_t tip_full, tip_empty, wp_full, wp_empty, stg_full, stg_empty;
+    uint64_t tip_full, tip_empty, stg_full, stg_empty;
     uint64_t pred_full[2], pred_empty[2];
     uint32_t tmem_base;
 };
 
 template <int C, int NPAD>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(F_THREADS, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(F_THREADS, 1)      // 168 registers: the register file is allocated as if for 12 warps (200 does not launch)
 temporal_head_fused_kernel(const __grid_constant__ FusedMaps maps, const __grid_constant__ FusedParams p) {
     using Cfg = FusedCfg<C, NPAD>;
     constexpr int P = 5 + C;
     constexpr int KB4 = F_NT / F_BLOCK_K;
+    const int kPredAt = p.pred_at;                                         // k-blocks of the next chunk in front of which a chunk's prediction GEMM runs
     extern __shared__ unsigned char smem_dyn[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
     unsigned char* ring = smem;
     unsigned char* stg = ring + Cfg::STAGES * Cfg::STAGE_BYTES;            // staged tip chunk: KB4 tiles [128 rows x 64 ch], swizzled
-    unsigned char* wpb = stg + Cfg::STG_BYTES;                             // prediction weights of the chunk: KB4 tiles [WP_ROWS x 64 ch]
-    float* scbias = reinterpret_cast<float*>(wpb + Cfg::WP_BYTES);         // [3 anchors][CPA][CH4] class biases
-    float* sbias = scbias + Cfg::CBIAS_BYTES / 4;                          // [NPAD]
-    FusedShared* sh = reinterpret_cast<FusedShared*>(sbias + NPAD);
+    float* scbias = reinterpret_cast<float*>(stg + Cfg::STG_BYTES);        // [scale][3 anchors][CPA][CH4] class biases
+    float* sbias = scbias + Cfg::CBIAS_BYTES / 4;                          // [scale][NPAD]
+    FusedShared* sh = reinterpret_cast<FusedShared*>(sbias + VD_MAX_SCALES * NPAD);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = tc::cluster_ctarank();
-    const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+    const int cluster_id = blockIdx.x >> 1;
 
-    for (int i = threadIdx.x; i < NPAD; i += F_THREADS) sbias[i] = (p.bias && i < 3 * P) ? p.bias[i] : 0.0f;
-    for (int i = threadIdx.x; i < 3 * Cfg::CPA * Cfg::CH4; i += F_THREADS) {
-        const int a = i / (Cfg::CPA * Cfg::CH4), cc = (i / Cfg::CH4) % Cfg::CPA, ci = i % Cfg::CH4;
+    for (int i = threadIdx.x; i < VD_MAX_SCALES * NPAD; i += F_THREADS) {
+        const int s_ = i / NPAD, n = i % NPAD;
+        sbias[i] = (s_ < p.num_scales && p.sc[s_].bias && n < 3 * P) ? p.sc[s_].bias[n] : 0.0f;
+    }
+    for (int i = threadIdx.x; i < VD_MAX_SCALES * 3 * Cfg::CPA * Cfg::CH4; i += F_THREADS) {
+        const int s_ = i / (3 * Cfg::CPA * Cfg::CH4), r_ = i % (3 * Cfg::CPA * Cfg::CH4);
+        const int a = r_ / (Cfg::CPA * Cfg::CH4), cc = (r_ / Cfg::CH4) % Cfg::CPA, ci = r_ % Cfg::CH4;
         const int c = cc * Cfg::CH + ci;
-        scbias[i] = (p.bias && ci < Cfg::CH && c < C) ? p.bias[a * P + 5 + c] : 0.0f;
+        scbias[i] = (s_ < p.num_scales && p.sc[s_].bias && ci < Cfg::CH && c < C) ? p.sc[s_].bias[a * P + 5 + c] : 0.0f;
     }
     if (threadIdx.x == 0) {
         for (int i = 0; i < Cfg::STAGES; ++i) { tc::mbar_init(&sh->full[i], 1); tc::mbar_init(&sh->empty[i], 1); }
         tc::mbar_init(&sh->tip_full, 1); tc::mbar_init(&sh->tip_empty, 16);
-        tc::mbar_init(&sh->wp_full, 1); tc::mbar_init(&sh->wp_empty, 1);
         tc::mbar_init(&sh->stg_full, 16); tc::mbar_init(&sh->stg_empty, 1);
         for (int i = 0; i < 2; ++i) { tc::mbar_init(&sh->pred_full[i], 1); tc::mbar_init(&sh->pred_empty[i], 16); }
         tc::fence_barrier_init();
-        tc::prefetch_tmap(&maps.x); tc::prefetch_tmap(&maps.w); tc::prefetch_tmap(&maps.wp);
+        for (int s_ = 0; s_ < p.num_scales; ++s_) { tc::prefetch_tmap(&maps.x[s_]); tc::prefetch_tmap(&maps.w[s_]); tc::prefetch_tmap(&maps.wp[s_]); }
     }
     if (warp == 1) tc::tmem_alloc_2cta<512>(&sh->tmem_base);
     tc::fence_before_sync();
@@ -113,64 +125,69 @@ temporal_head_fused_kernel(const __grid_constant__ FusedMaps maps, const __grid_
     tc::cluster_sync_all();
     tc::fence_after_sync();
     const uint32_t tmem_base = sh->tmem_base;
-    const int kb_per_tap = p.Cin / F_BLOCK_K;
-    const int m_total = p.B * p.m_tiles;
-    const int total_items = (m_total + 1) >> 1;
-
-    auto coords = [&](int item, uint32_t r, int& b, int& mt) {
+    // item of scale q -> (window b, row block mt) of CTA r; past the last tile: b == B (pure padding: zero rows in, nothing emitted)
+    auto coords = [&](const FusedScale& q, int item, uint32_t r, int& b, int& mt) {
         const int m = item * 2 + (int)r;
-        mt = m % p.m_tiles; b = m / p.m_tiles;                 // b == B: pure padding (zero rows in, nothing emitted)
+        mt = m % q.m_tiles; b = m / q.m_tiles;
     };
-    auto tap_active1 = [&](int b, int mt, int dt) -> bool {
+    auto tap_active1 = [&](const FusedScale& q, int b, int mt, int dt) -> bool {
         const int r0 = mt * F_BLOCK_M;
-        int r1 = r0 + F_BLOCK_M - 1; if (r1 > p.rows - 1) r1 = p.rows - 1;
-        return (b < p.B) && (r1 + dt * p.HW >= 0) && (r0 + dt * p.HW <= p.rows - 1);
+        int r1 = r0 + F_BLOCK_M - 1; if (r1 > q.rows - 1) r1 = q.rows - 1;
+        return (b < p.B) && (r1 + dt * q.HW >= 0) && (r0 + dt * q.HW <= q.rows - 1);
     };
-    auto tap_active = [&](int item, int dt) -> bool {
-        int b0, m0, b1, m1; coords(item, 0, b0, m0); coords(item, 1, b1, m1);
-        return tap_active1(b0, m0, dt) || tap_active1(b1, m1, dt);
+    auto tap_active = [&](const FusedScale& q, int item, int dt) -> bool {
+        int b0, m0, b1, m1; coords(q, item, 0, b0, m0); coords(q, item, 1, b1, m1);
+        return tap_active1(q, b0, m0, dt) || tap_active1(q, b1, m1, dt);
     };
 
     if (warp == 0) {
         // =========================== TMA producer (both CTAs) ===========================
         if (tc::elect_one()) {
-            int stage = 0; uint32_t phase = 0; uint32_t cc = 0;
-            const uint32_t wp_bar = tc::mapa_u32(&sh->wp_full, 0u);
-            for (int item = cluster_id; item < total_items; item += num_clusters) {
-                int b, mt; coords(item, rank, b, mt);
-                int n_act = 0;
-                for (int tap = 0; tap < 3; ++tap) n_act += tap_active(item, tap - 1) ? 1 : 0;
-                const int n_kb = n_act * kb_per_tap;
-                // the chunk's prediction weights are requested with the chunk's LAST k-block: their (single) buffer is free once the previous
-                // chunk's prediction MMAs are done -- those are issued a few k-blocks into this chunk (MMA role) -- and they are needed
-                // only after this chunk's accumulator has been staged
-                const int wp_at = n_kb - 1;
-                for (int nt = 0; nt < p.n_chunks; ++nt, ++cc) {
-                    int kcount = 0;
-                    for (int tap = 0; tap < 3; ++tap) {
-                        const int dt = tap - 1;
-                        if (!tap_active(item, dt)) continue;
-                        for (int kb = 0; kb < kb_per_tap; ++kb, ++kcount) {
-                            if (kcount == wp_at) {
-                                if (p.stamps && blockIdx.x == 0 && cc < 200u) p.stamps[cc * 16 + 8] = clock64();
-                                tc::mbar_wait_cluster(&sh->wp_empty, (cc & 1u) ^ 1u);
-                                if (p.stamps && blockIdx.x == 0 && cc < 200u) p.stamps[cc * 16 + 9] = clock64();
-                                if (rank == 0) tc::mbar_expect_tx(&sh->wp_full, 2u * Cfg::WP_BYTES);
+            int stage = 0; uint32_t phase = 0;
+            // Ring entries in the order the MMA role consumes them: the k-blocks of a chunk (A tile + half of the tap's weight tile), and,
+            // in front of k-block `pred_at` of the NEXT chunk, the prediction weights of the chunk before (KB4 tiles [WP_ROWS x 64 ch] in
+            // one stage) -- that is where the MMA role issues that chunk's prediction GEMM.  No separate buffer, no extra barriers.
+            bool pending = false; int p_s = 0, p_nt = 0;
+            auto load_wp = [&]() {
+                tc::mbar_wait_cluster(&sh->empty[stage], phase ^ 1u);
+                unsigned char* dst = ring + stage * Cfg::STAGE_BYTES;
+                if (rank == 0) tc::mbar_expect_tx(&sh->full[stage], 2u * Cfg::WP_BYTES);
+                const uint32_t bar = tc::mapa_u32(&sh->full[stage], 0u);
 #pragma unroll
-                                for (int j = 0; j < KB4; ++j)
-                                    tc::tma_load_2d_pair(wpb + j * Cfg::WP_TILE, &maps.wp, wp_bar, nt * F_NT + j * F_BLOCK_K, (int)rank * Cfg::WP_ROWS);
+                for (int j = 0; j < KB4; ++j)
+                    tc::tma_load_2d_pair(dst + j * Cfg::WP_TILE, &maps.wp[p_s], bar, p_nt * F_NT + j * F_BLOCK_K, (int)rank * Cfg::WP_ROWS);
+                if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
+                pending = false;
+            };
+            for (int s = 0; s < p.num_scales; ++s) {
+                const FusedScale& q = p.sc[s];
+                const int kb_per_tap = q.Cin / F_BLOCK_K;
+                for (int item = (int)p.beg[s][cluster_id]; item < (int)p.beg[s][cluster_id + 1]; ++item) {
+                    int b, mt; coords(q, item, rank, b, mt);
+                    int n_act = 0;
+                    for (int tap = 0; tap < 3; ++tap) n_act += tap_active(q, item, tap - 1) ? 1 : 0;
+                    const int pred_at = kPredAt < n_act * kb_per_tap - 1 ? kPredAt : n_act * kb_per_tap - 1;
+                    for (int nt = 0; nt < q.n_chunks; ++nt) {
+                        int kcount = 0;
+                        for (int tap = 0; tap < 3; ++tap) {
+                            const int dt = tap - 1;
+                            if (!tap_active(q, item, dt)) continue;
+                            for (int kb = 0; kb < kb_per_tap; ++kb, ++kcount) {
+                                if (pending && kcount == pred_at) load_wp();
+                                tc::mbar_wait_cluster(&sh->empty[stage], phase ^ 1u);
+                                unsigned char* a_dst = ring + stage * Cfg::STAGE_BYTES;
+                                if (rank == 0) tc::mbar_expect_tx(&sh->full[stage], 2u * Cfg::STAGE_BYTES);
+                                const uint32_t bar = tc::mapa_u32(&sh->full[stage], 0u);
+                                tc::tma_load_3d_pair(a_dst, &maps.x[s], bar, kb * F_BLOCK_K, mt * F_BLOCK_M + dt * q.HW, b);
+                                tc::tma_load_3d_pair(a_dst + Cfg::A_BYTES, &maps.w[s], bar, kb * F_BLOCK_K, nt * F_NT + (int)rank * (F_NT / 2), tap);
+                                if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
                             }
-                            tc::mbar_wait_cluster(&sh->empty[stage], phase ^ 1u);
-                            unsigned char* a_dst = ring + stage * Cfg::STAGE_BYTES;
-                            if (rank == 0) tc::mbar_expect_tx(&sh->full[stage], 2u * Cfg::STAGE_BYTES);
-                            const uint32_t bar = tc::mapa_u32(&sh->full[stage], 0u);
-                            tc::tma_load_3d_pair(a_dst, &maps.x, bar, kb * F_BLOCK_K, mt * F_BLOCK_M + dt * p.HW, b);
-                            tc::tma_load_3d_pair(a_dst + Cfg::A_BYTES, &maps.w, bar, kb * F_BLOCK_K, nt * F_NT + (int)rank * (F_NT / 2), tap);
-                            if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
                         }
+                        pending = true; p_s = s; p_nt = nt;
                     }
                 }
             }
+            if (pending) load_wp();
         }
     } else if (warp == 1) {
         // =========================== MMA issuer (leader CTA) ===========================
@@ -178,23 +195,24 @@ temporal_head_fused_kernel(const __grid_constant__ FusedMaps maps, const __grid_
             constexpr uint32_t idesc_tip = tc::make_idesc_bf16(2 * F_BLOCK_M, F_NT);
             constexpr uint32_t idesc_pred = tc::make_idesc_bf16(2 * F_BLOCK_M, NPAD);
             int stage = 0; uint32_t phase = 0; uint32_t cc = 0, ic = 0;
-            const uint32_t stg_addr = tc::smem_u32(stg), wp_addr = tc::smem_u32(wpb);
-            // The prediction GEMM of chunk c (A = the staged tip chunk of both CTAs, B = the chunk's prediction weights) is issued
-            // kPredAt k-blocks INTO the tip GEMM of chunk c + 1: by then the epilogue warps have staged chunk c, and the tensor pipe
-            // never waits for them (the tip accumulator itself is free as soon as they have read it)
-            constexpr int kPredAt = 3;
-            bool pending = false; uint32_t p_cc = 0, p_ic = 0; int p_nt = 0;
+            const uint32_t stg_addr = tc::smem_u32(stg);
+            // The prediction GEMM of chunk c (A = the staged tip chunk of both CTAs, B = the chunk's prediction weights, which arrive
+            // as a ring entry of their own) is issued kPredAt k-blocks INTO the tip GEMM of chunk c + 1: by then the epilogue warps have
+            // staged chunk c (~4 k cycles: BN, LeakyReLU, bf16 packing of 128 columns per thread is issue-bound), and the tensor pipe
+            // never waits for them (the tip accumulator itself is free as soon as they have read it).
+            bool pending = false, p_last = false; uint32_t p_cc = 0, p_ic = 0; int p_nt = 0;
             auto issue_pred = [&]() {
                 const uint32_t pb = p_ic & 1u;
                 const uint32_t d_pred = tmem_base + 256u + pb * 128u;
                 const bool st = p.stamps && blockIdx.x == 0 && p_cc < 200u;
                 if (st) p.stamps[p_cc * 16 + 3] = clock64();
-                tc::mbar_wait_cluster(&sh->wp_full, p_cc & 1u);
+                tc::mbar_wait_cluster(&sh->full[stage], phase);                   // the chunk's prediction weights (ring entry)
                 if (st) p.stamps[p_cc * 16 + 4] = clock64();
                 tc::mbar_wait_cluster(&sh->stg_full, p_cc & 1u);
                 if (p_nt == 0) tc::mbar_wait_cluster(&sh->pred_empty[pb], ((p_ic >> 1) & 1u) ^ 1u);
                 tc::fence_after_sync();
                 if (st) p.stamps[p_cc * 16 + 5] = clock64();
+                const uint32_t wp_addr = tc::smem_u32(ring + stage * Cfg::STAGE_BYTES);
 #pragma unroll
                 for (int j = 0; j < KB4; ++j) {
                     const uint64_t da = tc::make_smem_desc_sw128(stg_addr + (uint32_t)(j * Cfg::STG_TILE));
@@ -203,102 +221,114 @@ temporal_head_fused_kernel(const __grid_constant__ FusedMaps maps, const __grid_
                     for (int k = 0; k < F_BLOCK_K / 16; ++k)
                         tc::umma_bf16_2cta(d_pred, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc_pred, (uint32_t)((p_nt | j | k) != 0));
                 }
-                tc::umma_commit_2cta(&sh->wp_empty);
+                tc::umma_commit_2cta(&sh->empty[stage]);
+                if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
                 tc::umma_commit_2cta(&sh->stg_empty);
-                if (p_nt == p.n_chunks - 1) tc::umma_commit_2cta(&sh->pred_full[pb]);
+                if (p_last) tc::umma_commit_2cta(&sh->pred_full[pb]);
                 pending = false;
             };
-            for (int item = cluster_id; item < total_items; item += num_clusters, ++ic) {
-                for (int nt = 0; nt < p.n_chunks; ++nt, ++cc) {
-                    const bool st = p.stamps && blockIdx.x == 0 && cc < 200u;
-                    if (st) p.stamps[cc * 16 + 0] = clock64();
-                    tc::mbar_wait_cluster(&sh->tip_empty, (cc & 1u) ^ 1u);          // the epilogue has read the previous chunk's accumulator
-                    tc::fence_after_sync();
-                    if (st) p.stamps[cc * 16 + 1] = clock64();
-                    uint32_t first = 1;
-                    int kcount = 0;
-                    for (int tap = 0; tap < 3; ++tap) {
-                        if (!tap_active(item, tap - 1)) continue;
-                        for (int kb = 0; kb < kb_per_tap; ++kb, ++kcount) {
-                            if (pending && kcount == kPredAt) issue_pred();
-                            tc::mbar_wait_cluster(&sh->full[stage], phase);
-                            tc::fence_after_sync();
-                            const uint32_t a_addr = tc::smem_u32(ring + stage * Cfg::STAGE_BYTES);
-                            const uint64_t da = tc::make_smem_desc_sw128(a_addr);
-                            const uint64_t db = tc::make_smem_desc_sw128(a_addr + Cfg::A_BYTES);
+            for (int s = 0; s < p.num_scales; ++s) {
+                const FusedScale& q = p.sc[s];
+                const int kb_per_tap = q.Cin / F_BLOCK_K;
+                for (int item = (int)p.beg[s][cluster_id]; item < (int)p.beg[s][cluster_id + 1]; ++item, ++ic) {
+                    int n_act = 0;
+                    for (int tap = 0; tap < 3; ++tap) n_act += tap_active(q, item, tap - 1) ? 1 : 0;
+                    const int pred_at = kPredAt < n_act * kb_per_tap - 1 ? kPredAt : n_act * kb_per_tap - 1;      // same rule as the producer's
+                    for (int nt = 0; nt < q.n_chunks; ++nt, ++cc) {
+                        const bool st = p.stamps && blockIdx.x == 0 && cc < 200u;
+                        if (st) p.stamps[cc * 16 + 0] = clock64();
+                        tc::mbar_wait_cluster(&sh->tip_empty, (cc & 1u) ^ 1u);          // the epilogue has read the previous chunk's accumulator
+                        tc::fence_after_sync();
+                        if (st) p.stamps[cc * 16 + 1] = clock64();
+                        uint32_t first = 1;
+                        int kcount = 0;
+                        for (int tap = 0; tap < 3; ++tap) {
+                            if (!tap_active(q, item, tap - 1)) continue;
+                            for (int kb = 0; kb < kb_per_tap; ++kb, ++kcount) {
+                                if (pending && kcount == pred_at) issue_pred();
+                                tc::mbar_wait_cluster(&sh->full[stage], phase);
+                                tc::fence_after_sync();
+                                const uint32_t a_addr = tc::smem_u32(ring + stage * Cfg::STAGE_BYTES);
+                                const uint64_t da = tc::make_smem_desc_sw128(a_addr);
+                                const uint64_t db = tc::make_smem_desc_sw128(a_addr + Cfg::A_BYTES);
 #pragma unroll
-                            for (int k = 0; k < F_BLOCK_K / 16; ++k) {
-                                tc::umma_bf16_2cta(tmem_base, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc_tip, first ? 0u : 1u);
-                                first = 0;
+                                for (int k = 0; k < F_BLOCK_K / 16; ++k) {
+                                    tc::umma_bf16_2cta(tmem_base, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc_tip, first ? 0u : 1u);
+                                    first = 0;
+                                }
+                                tc::umma_commit_2cta(&sh->empty[stage]);
+                                if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
                             }
-                            tc::umma_commit_2cta(&sh->empty[stage]);
-                            if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
                         }
+                        tc::umma_commit_2cta(&sh->tip_full);
+                        if (st) p.stamps[cc * 16 + 2] = clock64();
+                        pending = true; p_cc = cc; p_ic = ic; p_nt = nt; p_last = (nt == q.n_chunks - 1);
                     }
-                    if (pending) issue_pred();                                     // (a chunk shorter than kPredAt k-blocks)
-                    tc::umma_commit_2cta(&sh->tip_full);
-                    if (st) p.stamps[cc * 16 + 2] = clock64();
-                    pending = true; p_cc = cc; p_ic = ic; p_nt = nt;
                 }
             }
             if (pending) issue_pred();
         }
     } else {
         // =========================== epilogue warps (both CTAs) ===========================
-        const int q = warp & 3;                               // TMEM lane quarter
+        const int lq = warp & 3;                              // TMEM lane quarter
         const int half = (warp - 2) >> 2;                     // column half of the tip chunk / share of the class chunks
-        const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
-        const int trow = q * 32 + lane;                       // row inside the tile
+        const uint32_t lane_addr = (uint32_t)(lq * 32) << 16;
+        const int trow = lq * 32 + lane;                      // row inside the tile
         const uint32_t sw = (uint32_t)(trow & 7);
         const uint32_t stg_row = tc::smem_u32(stg) + (uint32_t)trow * 128u;
         const bool ws_ok = p.tile_counter[2] == p.ws_magic;   // the workspace holds thresholds of this layout
-        const int s = p.s;
-        const int HW = p.HW, Wd = p.g.W[s];
         uint32_t cc = 0, ic = 0;
-        for (int item = cluster_id; item < total_items; item += num_clusters, ++ic) {
-            int b, mt; coords(item, rank, b, mt);
+        for (int s = 0; s < p.num_scales; ++s) {
+        const FusedScale& q = p.sc[s];
+        const int HW = q.HW;
+        const float* sbias_s = sbias + s * NPAD;
+        const float* scbias_s = scbias + s * (3 * Cfg::CPA * Cfg::CH4);
+        for (int item = (int)p.beg[s][cluster_id]; item < (int)p.beg[s][cluster_id + 1]; ++item, ++ic) {
+            int b, mt; coords(q, item, rank, b, mt);
             const int row = mt * F_BLOCK_M + trow;
-            const bool inb = (b < p.B) && (row < p.rows);
-            for (int nt = 0; nt < p.n_chunks; ++nt, ++cc) {
+            const bool inb = (b < p.B) && (row < q.rows);
+            for (int nt = 0; nt < q.n_chunks; ++nt, ++cc) {
                 const bool st = p.stamps && blockIdx.x == 0 && warp == 2 && lane == 0 && cc < 200u;
                 tc::mbar_wait_cluster(&sh->tip_full, cc & 1u);
                 tc::fence_after_sync();
                 if (st) p.stamps[cc * 16 + 10] = clock64();
+                // the warp's 128 accumulator columns go to registers in one go and the accumulator is handed back at once: it is
+                // single-buffered, the tensor pipe waits for exactly this
+                uint32_t r[128];
+                const uint32_t tbase = tmem_base + (uint32_t)(half * 128) + lane_addr;
+#pragma unroll
+                for (int g = 0; g < 8; ++g) tc::tmem_ld16(tbase + (uint32_t)(g * 16), r + g * 16);
+                tc::tmem_ld_wait();
+                tc::fence_before_sync();
+                __syncwarp();
+                if (lane == 0) tc::mbar_arrive_cluster(&sh->tip_empty, 0u);
                 tc::mbar_wait_cluster(&sh->stg_empty, (cc & 1u) ^ 1u);             // the previous chunk's prediction MMAs have read the staging tiles
                 if (st) p.stamps[cc * 16 + 11] = clock64();
-                const uint32_t tbase = tmem_base + (uint32_t)(half * 128) + lane_addr;
-#pragma unroll 1
-                for (int pass = 0; pass < 2; ++pass) {
-                    uint32_t r[64];
-                    const uint32_t ta = tbase + (uint32_t)(pass * 64);
-                    tc::tmem_ld16(ta, r); tc::tmem_ld16(ta + 16, r + 16); tc::tmem_ld16(ta + 32, r + 32); tc::tmem_ld16(ta + 48, r + 48);
-                    tc::tmem_ld_wait();
-                    if (pass == 1) {                                              // this warp has read its share of the tip accumulator
-                        tc::fence_before_sync();
-                        __syncwarp();
-                        if (lane == 0) tc::mbar_arrive_cluster(&sh->tip_empty, 0u);
-                    }
-                    const int ch0 = nt * F_NT + half * 128 + pass * 64;
-                    // folded BN straight from global memory (2 x 4 KB at most, L1-resident): 8 KB of shared memory buy the 4th ring stage
-                    const float4* sc = reinterpret_cast<const float4*>(p.scale + ch0);
-                    const float4* sf = reinterpret_cast<const float4*>(p.shift + ch0);
-                    uint32_t packed[32];
+                // folded BN straight from global memory (2 x 4 KB at most, L1-resident): 8 KB of shared memory buy the 4th ring stage
+                const float4* sc = reinterpret_cast<const float4*>(q.scale + nt * F_NT + half * 128);
+                const float4* sf = reinterpret_cast<const float4*>(q.shift + nt * F_NT + half * 128);
 #pragma unroll
-                    for (int i = 0; i < 64; i += 4) {
-                        const float4 s4 = __ldg(sc + (i >> 2));
-                        const float4 f4 = __ldg(sf + (i >> 2));
-                        float v0 = fmaf(__uint_as_float(r[i]), s4.x, f4.x), v1 = fmaf(__uint_as_float(r[i + 1]), s4.y, f4.y);
-                        float v2 = fmaf(__uint_as_float(r[i + 2]), s4.z, f4.z), v3 = fmaf(__uint_as_float(r[i + 3]), s4.w, f4.w);
-                        v0 = v0 > 0.f ? v0 : v0 * p.slope; v1 = v1 > 0.f ? v1 : v1 * p.slope;
-                        v2 = v2 > 0.f ? v2 : v2 * p.slope; v3 = v3 > 0.f ? v3 : v3 * p.slope;
-                        __nv_bfloat162 h0 = __floats2bfloat162_rn(v0, v1), h1 = __floats2bfloat162_rn(v2, v3);
-                        packed[i / 2] = *reinterpret_cast<uint32_t*>(&h0); packed[i / 2 + 1] = *reinterpret_cast<uint32_t*>(&h1);
-                    }
-                    const uint32_t dst = stg_row + (uint32_t)((half * 2 + pass) * Cfg::STG_TILE);      // k-block (half*2+pass) of the chunk
+                for (int t = 0; t < 2; ++t) {
+                    const uint32_t dst = stg_row + (uint32_t)((half * 2 + t) * Cfg::STG_TILE);      // k-block (half*2+t) of the chunk
 #pragma unroll
-                    for (int j = 0; j < 8; ++j)
+                    for (int j = 0; j < 8; ++j) {
+                        uint32_t pk[4];
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            const int i = t * 64 + j * 8 + h * 4;
+                            const float4 s4 = __ldg(sc + (i >> 2));
+                            const float4 f4 = __ldg(sf + (i >> 2));
+                            float v0 = fmaf(__uint_as_float(r[i]), s4.x, f4.x), v1 = fmaf(__uint_as_float(r[i + 1]), s4.y, f4.y);
+                            float v2 = fmaf(__uint_as_float(r[i + 2]), s4.z, f4.z), v3 = fmaf(__uint_as_float(r[i + 3]), s4.w, f4.w);
+                            // LeakyReLU as max(v, v * slope) (0 < slope < 1: the same bits as v > 0 ? v : v * slope, one instruction less)
+                            v0 = fmaxf(v0, v0 * p.slope); v1 = fmaxf(v1, v1 * p.slope);
+                            v2 = fmaxf(v2, v2 * p.slope); v3 = fmaxf(v3, v3 * p.slope);
+                            __nv_bfloat162 h0 = __floats2bfloat162_rn(v0, v1), h1 = __floats2bfloat162_rn(v2, v3);
+                            pk[2 * h] = *reinterpret_cast<uint32_t*>(&h0); pk[2 * h + 1] = *reinterpret_cast<uint32_t*>(&h1);
+                        }
                         asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + (((uint32_t)j ^ sw) << 4)),
-                                     "r"(packed[4 * j]), "r"(packed[4 * j + 1]), "r"(packed[4 * j + 2]), "r"(packed[4 * j + 3]) : "memory");
+                                     "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]) : "memory");
+                    }
                 }
                 tc::fence_proxy_async_smem();                                     // st.shared -> visible to the UMMA (async proxy) reads
                 __syncwarp();
@@ -332,7 +362,7 @@ temporal_head_fused_kernel(const __grid_constant__ FusedMaps maps, const __grid_
                     tc::tmem_ld_wait();
 #pragma unroll
                     for (int a = 0; a < 3; ++a) {
-                        conf[a] = vd_sigmoid(__uint_as_float(rb[a]) + sbias[a * P + 4]);
+                        conf[a] = vd_sigmoid(__uint_as_float(rb[a]) + sbias_s[a * P + 4]);
                         if (!inb) conf[a] = __uint_as_float(0x7fc00000u);          // NaN: no score of a padding row passes `> valid_thresh`
                     }
                 }
@@ -377,7 +407,7 @@ temporal_head_fused_kernel(const __grid_constant__ FusedMaps maps, const __grid_
                     float bv[CH4];
 #pragma unroll
                     for (int i = 0; i < CH4; i += 4)
-                        *reinterpret_cast<float4*>(bv + i) = *reinterpret_cast<const float4*>(scbias + j * CH4 + i);
+                        *reinterpret_cast<float4*>(bv + i) = *reinterpret_cast<const float4*>(scbias_s + j * CH4 + i);
                     tc::tmem_ld_wait();
                     bool any = false;
                     if (par == 0) {
@@ -414,16 +444,16 @@ temporal_head_fused_kernel(const __grid_constant__ FusedMaps maps, const __grid_
                         uint32_t r4[4];
                         tc::tmem_ld<4>(tb + (uint32_t)(a * P), r4); tc::tmem_ld_wait();
                         if (mine) p.boxes[(size_t)f * p.g.anc_base[p.g.num_scales] + p.g.anc_base[s] + cell * 3 + a] =
-                            make_float4(__uint_as_float(r4[0]) + sbias[a * P + 0], __uint_as_float(r4[1]) + sbias[a * P + 1],
-                                        __uint_as_float(r4[2]) + sbias[a * P + 2], __uint_as_float(r4[3]) + sbias[a * P + 3]);
+                            make_float4(__uint_as_float(r4[0]) + sbias_s[a * P + 0], __uint_as_float(r4[1]) + sbias_s[a * P + 1],
+                                        __uint_as_float(r4[2]) + sbias_s[a * P + 2], __uint_as_float(r4[3]) + sbias_s[a * P + 3]);
                     }
                 }
-                (void)Wd;
             }
             if (st2) p.stamps[(cc - 1u) * 16 + 14] = clock64();
             tc::fence_before_sync();
             __syncwarp();
             if (lane == 0) tc::mbar_arrive_cluster(&sh->pred_empty[pb], 0u);
+        }
         }
     }
     __syncwarp();
@@ -433,13 +463,51 @@ temporal_head_fused_kernel(const __grid_constant__ FusedMaps maps, const __grid_
     if (warp == 1) tc::tmem_dealloc_2cta<512>(tmem_base);
 }
 
+// Deals the items of every scale to `clusters` CTA pairs: scales in the order given (s32, s16, s8 = decreasing item cost), each item
+// to the pair with the least work so far (longest-processing-time greedy); a pair's items of one scale are a contiguous range.
+// Cost model of an item (k-cycles, from the per-chunk stamps of scripts/tfused_stamps.py): chunks x (0.7 per k-block + 1.5).
+static void tfused_schedule(FusedParams* p, int clusters) {
+    double load[F_MAX_CLUSTERS];
+    int cnt[F_MAX_CLUSTERS];
+    for (int c = 0; c < clusters; ++c) load[c] = 0.0;
+    for (int s = 0; s < VD_MAX_SCALES; ++s) {
+        for (int c = 0; c <= F_MAX_CLUSTERS; ++c) p->beg[s][c] = 0;
+        if (s >= p->num_scales) continue;
+        const FusedScale& q = p->sc[s];
+        const int items = q.m_tiles > 0 ? (int)(((long long)p->B * q.m_tiles + 1) / 2) : 0;
+        const double cost = q.n_chunks * (0.7 * 3.0 * (q.Cin / F_BLOCK_K) + 1.5);
+        for (int c = 0; c < clusters; ++c) cnt[c] = 0;
+        // water-filling: `items` equal items onto the current loads = repeatedly the least-loaded pair (a linear scan per item would be
+        // 4 k x 74 steps per call; levels are raised in bulk instead)
+        int left = items;
+        while (left > 0) {
+            int lo = 0;
+            for (int c = 1; c < clusters; ++c) if (load[c] < load[lo]) lo = c;
+            double next = 1e300;                     // the next higher load level
+            int at_lo = 0;
+            for (int c = 0; c < clusters; ++c) { if (load[c] <= load[lo] + 1e-9) ++at_lo; else if (load[c] < next) next = load[c]; }
+            // every pair at the lowest level takes k items, k = what lifts it to the next level (at least 1), bounded by what is left
+            long long k = next > 1e299 ? (left + at_lo - 1) / at_lo : (long long)((next - load[lo]) / cost);
+            if (k < 1) k = 1;
+            if (k * at_lo > left) k = left / at_lo;
+            if (k < 1) {                              // fewer items left than pairs at the level: one each
+                for (int c = 0; c < clusters && left > 0; ++c) if (load[c] <= load[lo] + 1e-9) { ++cnt[c]; load[c] += cost; --left; }
+                continue;
+            }
+            const double lvl = load[lo];
+            for (int c = 0; c < clusters; ++c) if (load[c] <= lvl + 1e-9) { cnt[c] += (int)k; load[c] += k * cost; left -= (int)k; }
+        }
+        int acc = 0;
+        for (int c = 0; c < clusters; ++c) { p->beg[s][c] = (unsigned short)acc; acc += cnt[c]; }
+        for (int c = clusters; c <= F_MAX_CLUSTERS; ++c) p->beg[s][c] = (unsigned short)acc;
+    }
+}
+
 template <int C, int NPAD>
-static int launch_tfused_t(const FusedMaps& maps, const FusedParams& p, cudaStream_t stream) {
+static int launch_tfused_t(const FusedMaps& maps, const FusedParams& p, int clusters, cudaStream_t stream) {
     using Cfg = FusedCfg<C, NPAD>;
     auto kern = temporal_head_fused_kernel<C, NPAD>;
     { int rc_ = configure_kernel((const void*)kern, Cfg::SMEM_BYTES, false); if (rc_) return rc_; }
-    const long long items = ((long long)p.B * p.m_tiles + 1) / 2;
-    long long clusters = sm_count() / 2; if (clusters > items) clusters = items;
     if (clusters < 1) return VD_OK;
     kern<<<(unsigned)(2 * clusters), F_THREADS, Cfg::SMEM_BYTES, stream>>>(maps, p);
     VD_LAUNCH_CHECK();
@@ -449,10 +517,10 @@ static int launch_tfused_t(const FusedMaps& maps, const FusedParams& p, cudaStre
 // class counts the fused kernel is compiled for (the VID / VOC heads); anything else runs the unfused chain
 static bool tfused_supported(int C) { return C == 30 || C == 20; }
 
-static int launch_tfused(const FusedMaps& maps, const FusedParams& p, int C, cudaStream_t stream) {
+static int launch_tfused(const FusedMaps& maps, const FusedParams& p, int C, int clusters, cudaStream_t stream) {
     switch (C) {
-        case 30: return launch_tfused_t<30, 112>(maps, p, stream);
-        case 20: return launch_tfused_t<20, 80>(maps, p, stream);
+        case 30: return launch_tfused_t<30, 112>(maps, p, clusters, stream);
+        case 20: return launch_tfused_t<20, 80>(maps, p, clusters, stream);
         default: break;
     }
     return set_error(VD_ERR_UNSUPPORTED, "fused temporal head: no kernel shape for %d classes", C);

@@ -577,16 +577,17 @@ def test_arbitrary_class_counts_valid_thresh_below_zero_and_heavy_ties():
             assert torch.equal(scores.view(torch.int32), out[:, :100, 1:2].contiguous().view(torch.int32))
 
 
-@pytest.mark.parametrize("C", [30, 20])
-def test_fused_tip_head_equals_separate_kernels_bit_exact(C):
+@pytest.mark.parametrize("C,B,size", [(30, 3, 160), (20, 3, 160), (30, 8, 256)])
+def test_fused_tip_head_equals_separate_kernels_bit_exact(C, B, size):
     """cfg 4 in ONE kernel per scale (tip cell -> BN/LReLU/bf16 tile in shared memory -> prediction GEMM -> decode + candidate
     filter, csrc/tfused.cuh) == the separate kernels (vd_temporal_conv -> head kernel), bit for bit: keep rows, ids, scores, boxes,
     on the cold call (every frame redone by the exact path, which recomputes the tip) and on steady calls with new inputs (no
     frame redone: the fused kernel's candidate lists are the ones that reach NMS).  Shapes: 3 windows (odd tile counts -> a
-    padding tile), materialised windows and windows over a resident clip."""
+    padding tile), 8 windows at 256^2 (the s8 scale then runs its strided rounds as well as contiguous item ranges), materialised
+    windows and windows over a resident clip."""
     import viddet_b200
-    rng = np.random.RandomState(21 + C)
-    B, T, size = 3, 5, 160
+    rng = np.random.RandomState(21 + C + B)
+    T = 5
     ws, bs = make_pred_weights(rng, C, bias_scale=0.1)
     heads = [build_head(C, ws, bs, temporal="conv21", fuse_tip=f) for f in (True, False)]
     for ch_i, ch in enumerate(CHANNELS):

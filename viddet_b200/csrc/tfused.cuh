@@ -42,6 +42,10 @@ struct FusedParams {
     float slope;
     FusedScale sc[VD_MAX_SCALES];
     unsigned short beg[VD_MAX_SCALES][F_MAX_CLUSTERS + 1];
+    // scales whose +-HW neighbour rows lie many tiles apart (s8: 21) first run `strided[s]` rounds of item = round * pairs + pair: tile m
+    // and the tiles its outer taps read (m +- HW/128) are then in flight on different pairs at the same time and share L2 (with
+    // contiguous ranges alone they are ~10 items = ~100 us apart on ONE pair: DRAM reads doubled); beg[][] covers what is left
+    int strided[VD_MAX_SCALES], pairs;
     HeadGeom g;
     int c_valid;                             // classes actually present (<= C)
     float valid_thresh;
@@ -135,6 +139,9 @@ temporal_head_fused_kernel(const __grid_constant__ FusedMaps maps, const __grid_
         int r1 = r0 + F_BLOCK_M - 1; if (r1 > q.rows - 1) r1 = q.rows - 1;
         return (b < p.B) && (r1 + dt * q.HW >= 0) && (r0 + dt * q.HW <= q.rows - 1);
     };
+    // k-th item of this CTA pair in scale s (see FusedParams::strided)
+    auto n_items = [&](int s) -> int { return p.strided[s] + (int)p.beg[s][cluster_id + 1] - (int)p.beg[s][cluster_id]; };
+    auto item_at = [&](int s, int k) -> int { return k < p.strided[s] ? k * p.pairs + cluster_id : (int)p.beg[s][cluster_id] + (k - p.strided[s]); };
     auto tap_active = [&](const FusedScale& q, int item, int dt) -> bool {
         int b0, m0, b1, m1; coords(q, item, 0, b0, m0); coords(q, item, 1, b1, m1);
         return tap_active1(q, b0, m0, dt) || tap_active1(q, b1, m1, dt);
@@ -162,7 +169,8 @@ temporal_head_fused_kernel(const __grid_constant__ FusedMaps maps, const __grid_
             for (int s = 0; s < p.num_scales; ++s) {
                 const FusedScale& q = p.sc[s];
                 const int kb_per_tap = q.Cin / F_BLOCK_K;
-                for (int item = (int)p.beg[s][cluster_id]; item < (int)p.beg[s][cluster_id + 1]; ++item) {
+                for (int ik = 0, ni = n_items(s); ik < ni; ++ik) {
+                    const int item = item_at(s, ik);
                     int b, mt; coords(q, item, rank, b, mt);
                     int n_act = 0;
                     for (int tap = 0; tap < 3; ++tap) n_act += tap_active(q, item, tap - 1) ? 1 : 0;
@@ -230,7 +238,8 @@ temporal_head_fused_kernel(const __grid_constant__ FusedMaps maps, const __grid_
             for (int s = 0; s < p.num_scales; ++s) {
                 const FusedScale& q = p.sc[s];
                 const int kb_per_tap = q.Cin / F_BLOCK_K;
-                for (int item = (int)p.beg[s][cluster_id]; item < (int)p.beg[s][cluster_id + 1]; ++item, ++ic) {
+                for (int ik = 0, ni = n_items(s); ik < ni; ++ik, ++ic) {
+                    const int item = item_at(s, ik);
                     int n_act = 0;
                     for (int tap = 0; tap < 3; ++tap) n_act += tap_active(q, item, tap - 1) ? 1 : 0;
                     const int pred_at = kPredAt < n_act * kb_per_tap - 1 ? kPredAt : n_act * kb_per_tap - 1;      // same rule as the producer's
@@ -283,7 +292,8 @@ temporal_head_fused_kernel(const __grid_constant__ FusedMaps maps, const __grid_
         const int HW = q.HW;
         const float* sbias_s = sbias + s * NPAD;
         const float* scbias_s = scbias + s * (3 * Cfg::CPA * Cfg::CH4);
-        for (int item = (int)p.beg[s][cluster_id]; item < (int)p.beg[s][cluster_id + 1]; ++item, ++ic) {
+        for (int ik = 0, ni = n_items(s); ik < ni; ++ik, ++ic) {
+            const int item = item_at(s, ik);
             int b, mt; coords(q, item, rank, b, mt);
             const int row = mt * F_BLOCK_M + trow;
             const bool inb = (b < p.B) && (row < q.rows);
@@ -470,8 +480,10 @@ static void tfused_schedule(FusedParams* p, int clusters) {
     double load[F_MAX_CLUSTERS];
     int cnt[F_MAX_CLUSTERS];
     for (int c = 0; c < clusters; ++c) load[c] = 0.0;
+    p->pairs = clusters;
     for (int s = 0; s < VD_MAX_SCALES; ++s) {
         for (int c = 0; c <= F_MAX_CLUSTERS; ++c) p->beg[s][c] = 0;
+        p->strided[s] = 0;
         if (s >= p->num_scales) continue;
         const FusedScale& q = p->sc[s];
         const int items = q.m_tiles > 0 ? (int)(((long long)p->B * q.m_tiles + 1) / 2) : 0;
@@ -497,8 +509,11 @@ static void tfused_schedule(FusedParams* p, int clusters) {
             const double lvl = load[lo];
             for (int c = 0; c < clusters; ++c) if (load[c] <= lvl + 1e-9) { cnt[c] += (int)k; load[c] += k * cost; left -= (int)k; }
         }
-        int acc = 0;
-        for (int c = 0; c < clusters; ++c) { p->beg[s][c] = (unsigned short)acc; acc += cnt[c]; }
+        int sr = 0;                                   // strided rounds: every pair takes part in them
+        if (q.HW >= 8 * F_BLOCK_M) { sr = cnt[0]; for (int c = 1; c < clusters; ++c) if (cnt[c] < sr) sr = cnt[c]; }
+        p->strided[s] = sr;
+        int acc = sr * clusters;
+        for (int c = 0; c < clusters; ++c) { p->beg[s][c] = (unsigned short)acc; acc += cnt[c] - sr; }
         for (int c = clusters; c <= F_MAX_CLUSTERS; ++c) p->beg[s][c] = (unsigned short)acc;
     }
 }

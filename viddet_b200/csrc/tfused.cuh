@@ -73,8 +73,9 @@ template <int C, int NPAD> struct FusedCfg {
     static constexpr int CH4 = (CH + 3) / 4 * 4;
     static constexpr int CBIAS_BYTES = VD_MAX_SCALES * 3 * CPA * CH4 * 4;
     static constexpr int BIAS_BYTES = VD_MAX_SCALES * NPAD * 4;
+    static constexpr int BN_BYTES = VD_MAX_SCALES * 2 * 1024 * 4;          // folded BN scale / shift of every scale (Cin <= 1024)
     static constexpr int SH_BYTES = 1024;
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STG_BYTES + CBIAS_BYTES + BIAS_BYTES + SH_BYTES + 1024;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STG_BYTES + BN_BYTES + CBIAS_BYTES + BIAS_BYTES + SH_BYTES + 1024;
     static_assert(WP_ROWS % 8 == 0 && NPAD % 16 == 0 && NPAD <= 128, "prediction width");
     static_assert(3 * (5 + C) <= NPAD, "NPAD");
     static_assert(SMEM_BYTES <= 227 * 1024 && WP_BYTES <= STAGE_BYTES, "shared memory");
@@ -98,13 +99,16 @@ temporal_head_fused_kernel(const __grid_constant__ FusedMaps maps, const __grid_
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
     unsigned char* ring = smem;
     unsigned char* stg = ring + Cfg::STAGES * Cfg::STAGE_BYTES;            // staged tip chunk: KB4 tiles [128 rows x 64 ch], swizzled
-    float* scbias = reinterpret_cast<float*>(stg + Cfg::STG_BYTES);        // [scale][3 anchors][CPA][CH4] class biases
+    float* sbn = reinterpret_cast<float*>(stg + Cfg::STG_BYTES);           // [scale][scale values (1024) | shift values (1024)]
+    float* scbias = sbn + Cfg::BN_BYTES / 4;                               // [scale][3 anchors][CPA][CH4] class biases
     float* sbias = scbias + Cfg::CBIAS_BYTES / 4;                          // [scale][NPAD]
     FusedShared* sh = reinterpret_cast<FusedShared*>(sbias + VD_MAX_SCALES * NPAD);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = tc::cluster_ctarank();
     const int cluster_id = blockIdx.x >> 1;
 
+    for (int s_ = 0; s_ < p.num_scales; ++s_)
+        for (int i = threadIdx.x; i < p.sc[s_].Cin; i += F_THREADS) { sbn[s_ * 2048 + i] = p.sc[s_].scale[i]; sbn[s_ * 2048 + 1024 + i] = p.sc[s_].shift[i]; }
     for (int i = threadIdx.x; i < VD_MAX_SCALES * NPAD; i += F_THREADS) {
         const int s_ = i / NPAD, n = i % NPAD;
         sbias[i] = (s_ < p.num_scales && p.sc[s_].bias && n < 3 * P) ? p.sc[s_].bias[n] : 0.0f;
@@ -314,9 +318,8 @@ temporal_head_fused_kernel(const __grid_constant__ FusedMaps maps, const __grid_
                 if (lane == 0) tc::mbar_arrive_cluster(&sh->tip_empty, 0u);
                 tc::mbar_wait_cluster(&sh->stg_empty, (cc & 1u) ^ 1u);             // the previous chunk's prediction MMAs have read the staging tiles
                 if (st) p.stamps[cc * 16 + 11] = clock64();
-                // folded BN straight from global memory (2 x 4 KB at most, L1-resident): 8 KB of shared memory buy the 4th ring stage
-                const float4* sc = reinterpret_cast<const float4*>(q.scale + nt * F_NT + half * 128);
-                const float4* sf = reinterpret_cast<const float4*>(q.shift + nt * F_NT + half * 128);
+                const float4* sc = reinterpret_cast<const float4*>(sbn + s * 2048 + nt * F_NT + half * 128);
+                const float4* sf = reinterpret_cast<const float4*>(sbn + s * 2048 + 1024 + nt * F_NT + half * 128);
 #pragma unroll
                 for (int t = 0; t < 2; ++t) {
                     const uint32_t dst = stg_row + (uint32_t)((half * 2 + t) * Cfg::STG_TILE);      // k-block (half*2+t) of the chunk
@@ -326,8 +329,8 @@ temporal_head_fused_kernel(const __grid_constant__ FusedMaps maps, const __grid_
 #pragma unroll
                         for (int h = 0; h < 2; ++h) {
                             const int i = t * 64 + j * 8 + h * 4;
-                            const float4 s4 = __ldg(sc + (i >> 2));
-                            const float4 f4 = __ldg(sf + (i >> 2));
+                            const float4 s4 = sc[i >> 2];
+                            const float4 f4 = sf[i >> 2];
                             float v0 = fmaf(__uint_as_float(r[i]), s4.x, f4.x), v1 = fmaf(__uint_as_float(r[i + 1]), s4.y, f4.y);
                             float v2 = fmaf(__uint_as_float(r[i + 2]), s4.z, f4.z), v3 = fmaf(__uint_as_float(r[i + 3]), s4.w, f4.w);
                             // LeakyReLU as max(v, v * slope) (0 < slope < 1: the same bits as v > 0 ? v : v * slope, one instruction less)

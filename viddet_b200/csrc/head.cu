@@ -1737,7 +1737,6 @@ static int run_tfused(const VdHeadParams* hp, const HeadPlan& pl, const HeadKern
     fp.g = kp.g; fp.c_valid = kp.c_valid; fp.valid_thresh = hp->valid_thresh;
     fp.boxes = kp.boxes; fp.spec_lists = kp.spec_lists; fp.spec_cnt = kp.spec_cnt; fp.spec_tau = kp.spec_tau;
     fp.tile_counter = kp.tile_counter; fp.ws_magic = kp.ws_magic; fp.frames = hp->frames; fp.dbg = dbg; fp.stamps = kp.stamps;
-    { const char* e = getenv("VD_TFUSED_PRED_AT"); fp.pred_at = e ? atoi(e) : 7; if (fp.pred_at < 0) fp.pred_at = 0; }   // tuning knob, see tfused.cuh
     for (int s = 0; s < hp->num_scales; ++s) {
         const VdHeadScale& sc = hp->scale[s];
         FusedScale& q = fp.sc[s];

@@ -52,7 +52,6 @@ struct FusedParams {
     float4* boxes; uint64_t* spec_lists; uint32_t* spec_cnt; const uint32_t* spec_tau;
     const unsigned int* tile_counter; unsigned int ws_magic;
     int frames;
-    int pred_at;                             // the prediction GEMM of a chunk is issued in front of k-block `pred_at` of the next chunk's tip GEMM
     int dbg;                                 // profiling aid (VD_TFUSED_DBG): 1 = skip the decode / filter epilogue
     long long* stamps;                       // profiling aid (VD_TFUSED_STAMPS): clock64 per chunk of cluster 0's leader CTA, [chunk][16]
 };
@@ -94,7 +93,6 @@ temporal_head_fused_kernel(const __grid_constant__ FusedMaps maps, const __grid_
     using Cfg = FusedCfg<C, NPAD>;
     constexpr int P = 5 + C;
     constexpr int KB4 = F_NT / F_BLOCK_K;
-    const int kPredAt = p.pred_at;                                         // k-blocks of the next chunk in front of which a chunk's prediction GEMM runs
     extern __shared__ unsigned char smem_dyn[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
     unsigned char* ring = smem;
@@ -156,8 +154,8 @@ temporal_head_fused_kernel(const __grid_constant__ FusedMaps maps, const __grid_
         if (tc::elect_one()) {
             int stage = 0; uint32_t phase = 0;
             // Ring entries in the order the MMA role consumes them: the k-blocks of a chunk (A tile + half of the tap's weight tile), and,
-            // in front of k-block `pred_at` of the NEXT chunk, the prediction weights of the chunk before (KB4 tiles [WP_ROWS x 64 ch] in
-            // one stage) -- that is where the MMA role issues that chunk's prediction GEMM.  No separate buffer, no extra barriers.
+            // behind the last k-block of the NEXT chunk, the prediction weights of the chunk before (KB4 tiles [WP_ROWS x 64 ch] in one
+            // stage) -- that is where the MMA role issues that chunk's prediction GEMM.  No separate buffer, no extra barriers.
             bool pending = false; int p_s = 0, p_nt = 0;
             auto load_wp = [&]() {
                 tc::mbar_wait_cluster(&sh->empty[stage], phase ^ 1u);
@@ -176,16 +174,11 @@ temporal_head_fused_kernel(const __grid_constant__ FusedMaps maps, const __grid_
                 for (int ik = 0, ni = n_items(s); ik < ni; ++ik) {
                     const int item = item_at(s, ik);
                     int b, mt; coords(q, item, rank, b, mt);
-                    int n_act = 0;
-                    for (int tap = 0; tap < 3; ++tap) n_act += tap_active(q, item, tap - 1) ? 1 : 0;
-                    const int pred_at = kPredAt < n_act * kb_per_tap - 1 ? kPredAt : n_act * kb_per_tap - 1;
                     for (int nt = 0; nt < q.n_chunks; ++nt) {
-                        int kcount = 0;
                         for (int tap = 0; tap < 3; ++tap) {
                             const int dt = tap - 1;
                             if (!tap_active(q, item, dt)) continue;
-                            for (int kb = 0; kb < kb_per_tap; ++kb, ++kcount) {
-                                if (pending && kcount == pred_at) load_wp();
+                            for (int kb = 0; kb < kb_per_tap; ++kb) {
                                 tc::mbar_wait_cluster(&sh->empty[stage], phase ^ 1u);
                                 unsigned char* a_dst = ring + stage * Cfg::STAGE_BYTES;
                                 if (rank == 0) tc::mbar_expect_tx(&sh->full[stage], 2u * Cfg::STAGE_BYTES);
@@ -195,6 +188,7 @@ temporal_head_fused_kernel(const __grid_constant__ FusedMaps maps, const __grid_
                                 if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
                             }
                         }
+                        if (pending) load_wp();
                         pending = true; p_s = s; p_nt = nt;
                     }
                 }
@@ -209,9 +203,9 @@ temporal_head_fused_kernel(const __grid_constant__ FusedMaps maps, const __grid_
             int stage = 0; uint32_t phase = 0; uint32_t cc = 0, ic = 0;
             const uint32_t stg_addr = tc::smem_u32(stg);
             // The prediction GEMM of chunk c (A = the staged tip chunk of both CTAs, B = the chunk's prediction weights, which arrive
-            // as a ring entry of their own) is issued kPredAt k-blocks INTO the tip GEMM of chunk c + 1: by then the epilogue warps have
-            // staged chunk c (~4 k cycles: BN, LeakyReLU, bf16 packing of 128 columns per thread is issue-bound), and the tensor pipe
-            // never waits for them (the tip accumulator itself is free as soon as they have read it).
+            // as a ring entry of their own) is issued right BEHIND the tip GEMM of chunk c + 1: the tip accumulator is single-buffered,
+            // so while the epilogue warps read chunk c + 1 back (~1.3 k cycles) the tensor pipe would idle -- it runs these ~0.9 k
+            // cycles of MMAs instead.  Chunk c was staged a whole chunk ago; its decode follows one chunk late as well (epilogue role).
             bool pending = false, p_last = false; uint32_t p_cc = 0, p_ic = 0; int p_nt = 0;
             auto issue_pred = [&]() {
                 const uint32_t pb = p_ic & 1u;
@@ -244,9 +238,6 @@ temporal_head_fused_kernel(const __grid_constant__ FusedMaps maps, const __grid_
                 const int kb_per_tap = q.Cin / F_BLOCK_K;
                 for (int ik = 0, ni = n_items(s); ik < ni; ++ik, ++ic) {
                     const int item = item_at(s, ik);
-                    int n_act = 0;
-                    for (int tap = 0; tap < 3; ++tap) n_act += tap_active(q, item, tap - 1) ? 1 : 0;
-                    const int pred_at = kPredAt < n_act * kb_per_tap - 1 ? kPredAt : n_act * kb_per_tap - 1;      // same rule as the producer's
                     for (int nt = 0; nt < q.n_chunks; ++nt, ++cc) {
                         const bool st = p.stamps && blockIdx.x == 0 && cc < 200u;
                         if (st) p.stamps[cc * 16 + 0] = clock64();
@@ -254,11 +245,9 @@ temporal_head_fused_kernel(const __grid_constant__ FusedMaps maps, const __grid_
                         tc::fence_after_sync();
                         if (st) p.stamps[cc * 16 + 1] = clock64();
                         uint32_t first = 1;
-                        int kcount = 0;
                         for (int tap = 0; tap < 3; ++tap) {
                             if (!tap_active(q, item, tap - 1)) continue;
-                            for (int kb = 0; kb < kb_per_tap; ++kb, ++kcount) {
-                                if (pending && kcount == pred_at) issue_pred();
+                            for (int kb = 0; kb < kb_per_tap; ++kb) {
                                 tc::mbar_wait_cluster(&sh->full[stage], phase);
                                 tc::fence_after_sync();
                                 const uint32_t a_addr = tc::smem_u32(ring + stage * Cfg::STAGE_BYTES);
@@ -275,6 +264,7 @@ temporal_head_fused_kernel(const __grid_constant__ FusedMaps maps, const __grid_
                         }
                         tc::umma_commit_2cta(&sh->tip_full);
                         if (st) p.stamps[cc * 16 + 2] = clock64();
+                        if (pending) issue_pred();                 // the previous chunk's prediction GEMM runs while this accumulator is read back
                         pending = true; p_cc = cc; p_ic = ic; p_nt = nt; p_last = (nt == q.n_chunks - 1);
                     }
                 }
@@ -290,71 +280,22 @@ temporal_head_fused_kernel(const __grid_constant__ FusedMaps maps, const __grid_
         const uint32_t sw = (uint32_t)(trow & 7);
         const uint32_t stg_row = tc::smem_u32(stg) + (uint32_t)trow * 128u;
         const bool ws_ok = p.tile_counter[2] == p.ws_magic;   // the workspace holds thresholds of this layout
-        uint32_t cc = 0, ic = 0;
-        for (int s = 0; s < p.num_scales; ++s) {
-        const FusedScale& q = p.sc[s];
-        const int HW = q.HW;
-        const float* sbias_s = sbias + s * NPAD;
-        const float* scbias_s = scbias + s * (3 * Cfg::CPA * Cfg::CH4);
-        for (int ik = 0, ni = n_items(s); ik < ni; ++ik, ++ic) {
-            const int item = item_at(s, ik);
+        // ---- decode + speculative candidate filter on an item's prediction accumulator (head_kernel<EPI_SPEC>, per-lane frame).  Runs one
+        // chunk LATE: the item's last prediction GEMM is issued behind the NEXT chunk's tip GEMM (MMA role), i.e. while these warps read
+        // that chunk's accumulator back and stage it; the decode of the previous item follows.
+        auto decode_item = [&](const int s, const int item, const uint32_t ic, const uint32_t scc) {
+            const FusedScale& q = p.sc[s];
+            const int HW = q.HW;
+            const float* sbias_s = sbias + s * NPAD;
+            const float* scbias_s = scbias + s * (3 * Cfg::CPA * Cfg::CH4);
             int b, mt; coords(q, item, rank, b, mt);
             const int row = mt * F_BLOCK_M + trow;
             const bool inb = (b < p.B) && (row < q.rows);
-            for (int nt = 0; nt < q.n_chunks; ++nt, ++cc) {
-                const bool st = p.stamps && blockIdx.x == 0 && warp == 2 && lane == 0 && cc < 200u;
-                tc::mbar_wait_cluster(&sh->tip_full, cc & 1u);
-                tc::fence_after_sync();
-                if (st) p.stamps[cc * 16 + 10] = clock64();
-                // the warp's 128 accumulator columns go to registers in one go and the accumulator is handed back at once: it is
-                // single-buffered, the tensor pipe waits for exactly this
-                uint32_t r[128];
-                const uint32_t tbase = tmem_base + (uint32_t)(half * 128) + lane_addr;
-#pragma unroll
-                for (int g = 0; g < 8; ++g) tc::tmem_ld16(tbase + (uint32_t)(g * 16), r + g * 16);
-                tc::tmem_ld_wait();
-                tc::fence_before_sync();
-                __syncwarp();
-                if (lane == 0) tc::mbar_arrive_cluster(&sh->tip_empty, 0u);
-                tc::mbar_wait_cluster(&sh->stg_empty, (cc & 1u) ^ 1u);             // the previous chunk's prediction MMAs have read the staging tiles
-                if (st) p.stamps[cc * 16 + 11] = clock64();
-                const float4* sc = reinterpret_cast<const float4*>(sbn + s * 2048 + nt * F_NT + half * 128);
-                const float4* sf = reinterpret_cast<const float4*>(sbn + s * 2048 + 1024 + nt * F_NT + half * 128);
-#pragma unroll
-                for (int t = 0; t < 2; ++t) {
-                    const uint32_t dst = stg_row + (uint32_t)((half * 2 + t) * Cfg::STG_TILE);      // k-block (half*2+t) of the chunk
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        uint32_t pk[4];
-#pragma unroll
-                        for (int h = 0; h < 2; ++h) {
-                            const int i = t * 64 + j * 8 + h * 4;
-                            const float4 s4 = sc[i >> 2];
-                            const float4 f4 = sf[i >> 2];
-                            float v0 = fmaf(__uint_as_float(r[i]), s4.x, f4.x), v1 = fmaf(__uint_as_float(r[i + 1]), s4.y, f4.y);
-                            float v2 = fmaf(__uint_as_float(r[i + 2]), s4.z, f4.z), v3 = fmaf(__uint_as_float(r[i + 3]), s4.w, f4.w);
-                            // LeakyReLU as max(v, v * slope) (0 < slope < 1: the same bits as v > 0 ? v : v * slope, one instruction less)
-                            v0 = fmaxf(v0, v0 * p.slope); v1 = fmaxf(v1, v1 * p.slope);
-                            v2 = fmaxf(v2, v2 * p.slope); v3 = fmaxf(v3, v3 * p.slope);
-                            __nv_bfloat162 h0 = __floats2bfloat162_rn(v0, v1), h1 = __floats2bfloat162_rn(v2, v3);
-                            pk[2 * h] = *reinterpret_cast<uint32_t*>(&h0); pk[2 * h + 1] = *reinterpret_cast<uint32_t*>(&h1);
-                        }
-                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + (((uint32_t)j ^ sw) << 4)),
-                                     "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]) : "memory");
-                    }
-                }
-                tc::fence_proxy_async_smem();                                     // st.shared -> visible to the UMMA (async proxy) reads
-                __syncwarp();
-                if (lane == 0) tc::mbar_arrive_cluster(&sh->stg_full, 0u);
-                if (st) p.stamps[cc * 16 + 12] = clock64();
-            }
-
-            // ---- decode + speculative candidate filter on the item's prediction accumulator (head_kernel<EPI_SPEC>, per-lane frame)
             const uint32_t pb = ic & 1u;
-            const bool st2 = p.stamps && blockIdx.x == 0 && warp == 2 && lane == 0 && cc - 1u < 200u;
+            const bool st2 = p.stamps && blockIdx.x == 0 && warp == 2 && lane == 0 && scc < 200u;
             tc::mbar_wait_cluster(&sh->pred_full[pb], (ic >> 1) & 1u);
             tc::fence_after_sync();
-            if (st2) p.stamps[(cc - 1u) * 16 + 13] = clock64();
+            if (st2) p.stamps[scc * 16 + 13] = clock64();
             if (!(p.dbg & 1)) {
                 const int f = inb ? b * p.T + row / HW : 0;
                 const int cell = inb ? row % HW : 0;
@@ -462,12 +403,69 @@ temporal_head_fused_kernel(const __grid_constant__ FusedMaps maps, const __grid_
                     }
                 }
             }
-            if (st2) p.stamps[(cc - 1u) * 16 + 14] = clock64();
+            if (st2) p.stamps[scc * 16 + 14] = clock64();
             tc::fence_before_sync();
             __syncwarp();
             if (lane == 0) tc::mbar_arrive_cluster(&sh->pred_empty[pb], 0u);
+        };
+        uint32_t cc = 0, ic = 0;
+        bool dec_pending = false; int d_s = 0, d_item = 0; uint32_t d_ic = 0, d_cc = 0;
+        for (int s = 0; s < p.num_scales; ++s) {
+        const FusedScale& q = p.sc[s];
+        for (int ik = 0, ni = n_items(s); ik < ni; ++ik, ++ic) {
+            const int item = item_at(s, ik);
+            for (int nt = 0; nt < q.n_chunks; ++nt, ++cc) {
+                const bool st = p.stamps && blockIdx.x == 0 && warp == 2 && lane == 0 && cc < 200u;
+                tc::mbar_wait_cluster(&sh->tip_full, cc & 1u);
+                tc::fence_after_sync();
+                if (st) p.stamps[cc * 16 + 10] = clock64();
+                // the warp's 128 accumulator columns go to registers in one go and the accumulator is handed back at once: it is
+                // single-buffered, the tensor pipe waits for exactly this
+                uint32_t r[128];
+                const uint32_t tbase = tmem_base + (uint32_t)(half * 128) + lane_addr;
+#pragma unroll
+                for (int g = 0; g < 8; ++g) tc::tmem_ld16(tbase + (uint32_t)(g * 16), r + g * 16);
+                tc::tmem_ld_wait();
+                tc::fence_before_sync();
+                __syncwarp();
+                if (lane == 0) tc::mbar_arrive_cluster(&sh->tip_empty, 0u);
+                tc::mbar_wait_cluster(&sh->stg_empty, (cc & 1u) ^ 1u);             // the previous chunk's prediction MMAs have read the staging tiles
+                if (st) p.stamps[cc * 16 + 11] = clock64();
+                const float4* sc = reinterpret_cast<const float4*>(sbn + s * 2048 + nt * F_NT + half * 128);
+                const float4* sf = reinterpret_cast<const float4*>(sbn + s * 2048 + 1024 + nt * F_NT + half * 128);
+#pragma unroll
+                for (int t = 0; t < 2; ++t) {
+                    const uint32_t dst = stg_row + (uint32_t)((half * 2 + t) * Cfg::STG_TILE);      // k-block (half*2+t) of the chunk
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        uint32_t pk[4];
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            const int i = t * 64 + j * 8 + h * 4;
+                            const float4 s4 = sc[i >> 2];
+                            const float4 f4 = sf[i >> 2];
+                            float v0 = fmaf(__uint_as_float(r[i]), s4.x, f4.x), v1 = fmaf(__uint_as_float(r[i + 1]), s4.y, f4.y);
+                            float v2 = fmaf(__uint_as_float(r[i + 2]), s4.z, f4.z), v3 = fmaf(__uint_as_float(r[i + 3]), s4.w, f4.w);
+                            // LeakyReLU as max(v, v * slope) (0 < slope < 1: the same bits as v > 0 ? v : v * slope, one instruction less)
+                            v0 = fmaxf(v0, v0 * p.slope); v1 = fmaxf(v1, v1 * p.slope);
+                            v2 = fmaxf(v2, v2 * p.slope); v3 = fmaxf(v3, v3 * p.slope);
+                            __nv_bfloat162 h0 = __floats2bfloat162_rn(v0, v1), h1 = __floats2bfloat162_rn(v2, v3);
+                            pk[2 * h] = *reinterpret_cast<uint32_t*>(&h0); pk[2 * h + 1] = *reinterpret_cast<uint32_t*>(&h1);
+                        }
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + (((uint32_t)j ^ sw) << 4)),
+                                     "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]) : "memory");
+                    }
+                }
+                tc::fence_proxy_async_smem();                                     // st.shared -> visible to the UMMA (async proxy) reads
+                __syncwarp();
+                if (lane == 0) tc::mbar_arrive_cluster(&sh->stg_full, 0u);
+                if (st) p.stamps[cc * 16 + 12] = clock64();
+                if (dec_pending) { decode_item(d_s, d_item, d_ic, d_cc); dec_pending = false; }
+            }
+            dec_pending = true; d_s = s; d_item = item; d_ic = ic; d_cc = cc - 1u;
         }
         }
+        if (dec_pending) decode_item(d_s, d_item, d_ic, d_cc);
     }
     __syncwarp();
     tc::fence_before_sync();

@@ -1446,7 +1446,7 @@ struct HeadPlan {
     bool repack;                   // weights / biases are re-laid out per window into the workspace (off_wrepack)
     size_t off_wrepack, wrepack_bytes, wrepack_w_bytes[VD_MAX_SCALES], wrepack_stride[VD_MAX_SCALES];
     int merge_levels;
-    size_t off_hints, off_ctr, off_hist, off_boxes, off_lists0, off_counts0, off_counts_hi, off_hint_hi, off_coarse, off_spec_lists, off_spec_cnt, off_spec_state, off_spec_tau, off_failed, off_listsA, off_listsB, off_countsA, off_countsB, total;
+    size_t off_hints, off_ctr, off_hist, off_boxes, off_lists0, off_counts0, off_counts_hi, off_hint_hi, off_coarse, off_spec_lists, off_spec_cnt, off_spec_state, off_spec_tau, off_failed, off_winlist, off_listsA, off_listsB, off_countsA, off_countsB, total;
 };
 
 }  // namespace vd
@@ -1553,6 +1553,7 @@ static int make_plan(const VdHeadParams* hp, HeadPlan* pl) {
     pl->off_spec_state = off; off += 256;
     pl->off_spec_tau = off; off += align_up(F * 4, 256);
     pl->off_failed = off; off += align_up(F * 4, 256);
+    pl->off_winlist = off; off += align_up((F + 64) * 4, 256);       // fused temporal head: windows of the failed frames ([0] = count, [64..] = first frame of each window)
     int n1 = ceil_div(tif, kMaxLists);
     pl->off_listsA = off; off += align_up(F * n1 * kListCap * 8, 256);
     pl->off_listsB = off; off += align_up(F * n1 * kListCap * 8, 256);
@@ -1709,12 +1710,35 @@ static int launch_pred(const HeadMaps& maps, const HeadKernelParams& kp, cudaStr
     return set_error(VD_ERR_INVALID_ARG, "pred_conv: bad padded width %d", kp.n_pad);
 }
 
+// Exact fallback of the fused temporal head: the failed FRAMES (queued by nms_spec_kernel) -> the distinct WINDOWS they belong to, so that
+// the conditional tip-cell launches recompute every such window once (on a cold workspace all T frames of every window are listed).
+// out[0] = number of windows, out[64 + i] = first frame of window i.  One CTA; a bitmap of the windows in shared memory.
+__global__ void __launch_bounds__(1024)
+failed_windows_kernel(const uint32_t* __restrict__ failed, const uint32_t* __restrict__ n_failed, int T, int n_windows, uint32_t* __restrict__ out) {
+    __shared__ uint32_t bits[2048];                    // up to 65 536 windows
+    __shared__ uint32_t n_out;
+    const uint32_t n = *n_failed;
+    if (n == 0u) { if (threadIdx.x == 0) out[0] = 0u; return; }
+    const int words = (n_windows + 31) >> 5;
+    for (int i = threadIdx.x; i < words; i += blockDim.x) bits[i] = 0u;
+    if (threadIdx.x == 0) n_out = 0u;
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) { const uint32_t w = failed[i] / (uint32_t)T; atomicOr(&bits[w >> 5], 1u << (w & 31u)); }
+    __syncthreads();
+    for (int i = threadIdx.x; i < words; i += blockDim.x) {
+        uint32_t m = bits[i];
+        while (m) { const int b = __ffs(m) - 1; m &= m - 1u; out[64u + atomicAdd(&n_out, 1u)] = (uint32_t)((i * 32 + b) * T); }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) out[0] = n_out;
+}
+
 // The fused tip-cell + head kernel (tfused.cuh) replaces the temporal_conv + head_kernel<EPI_SPEC> launches where it applies.
 static bool tfused_applicable(const VdHeadParams* hp, const HeadPlan& pl, bool spec) {
     static const bool on = []() { const char* e = getenv("VD_TFUSED"); return e ? atoi(e) != 0 : true; }();
     if (!on || !spec || (hp->flags & VD_HEAD_NO_FUSED_TIP)) return false;
     if (pl.n_pass != 1 || pl.repack || hp->precision != VD_PREC_BF16 || hp->join != VD_JOIN_NONE || pl.kp.K_frames != 1) return false;
-    if (!tfused_supported(pl.C) || hp->T < 1 || hp->frames <= 0 || hp->frames % hp->T) return false;
+    if (!tfused_supported(pl.C) || hp->T < 1 || hp->frames <= 0 || hp->frames % hp->T || hp->frames / hp->T > 65536) return false;
     for (int s = 0; s < hp->num_scales; ++s) {
         const VdHeadScale& sc = hp->scale[s];
         if (!sc.tconv_weight_bf16 || !sc.tconv_scale || !sc.tconv_shift || !sc.tconv_out_nhwc_bf16) return false;
@@ -1804,8 +1828,9 @@ extern "C" int vd_head_launch_count(const VdHeadParams* hp) {
     if (make_plan(hp, &pl) != VD_OK) return -1;
     int n = getenv("VD_NO_SPEC") ? 1 + pl.n_pass : 2 + 2 * pl.n_pass;   // head kernel per class window + per-frame NMS kernel (+ the exact fallback pair, idle in the steady state)
     for (int s = 0; s < hp->num_scales; ++s) if (hp->scale[s].tconv_weight_bf16) ++n;
-    // fused temporal head: same count -- ONE kernel (all scales) instead of the head kernel; the tip cells counted above become the
-    // conditional launches of the exact path
+    // fused temporal head: ONE kernel (all scales) instead of the head kernel; the tip cells counted above become the conditional launches
+    // of the exact path, behind the kernel that lists the failed windows
+    if (tfused_applicable(hp, pl, getenv("VD_NO_SPEC") == nullptr)) ++n;
     if (pl.repack) n += hp->num_scales * pl.n_pass;               // weight re-layout per (scale, window)
     return n;
 }
@@ -1929,11 +1954,15 @@ extern "C" int vd_head_forward_stages(const VdHeadParams* hp, float* ids, float*
     VD_LAUNCH_CHECK();
     // 2. exact path over the queued frames (both kernels return at once when the queue is empty -- the steady state)
     if (fused_tip) {
-        // the fused kernel kept the tip on chip: the exact path reads it from memory, so the tip cells run first -- only if a frame failed
+        // the fused kernel kept the tip on chip: the exact path reads it from memory, so the tip cells run first -- only if a frame failed,
+        // and only over the windows of the failed frames
+        uint32_t* winlist = (uint32_t*)(ws + pl.off_winlist);
+        failed_windows_kernel<<<1, 1024, 0, stream>>>(failed, kp.spec_state + 2, hp->T, hp->frames / hp->T, winlist);
+        VD_LAUNCH_CHECK();
         for (int s = 0; s < hp->num_scales; ++s) {
             const VdHeadScale& sc = hp->scale[s];
             rc = temporal_conv_impl(sc.tip_nhwc_bf16, sc.tconv_out_nhwc_bf16, hp->frames / hp->T, hp->T, sc.H, sc.W, sc.Cin, sc.tconv_weight_bf16,
-                                    sc.tconv_scale, sc.tconv_shift, 0.1f, VD_PREC_BF16, sc.tip_window_stride_frames, kp.spec_state + 2, failed, stream_);
+                                    sc.tconv_scale, sc.tconv_shift, 0.1f, VD_PREC_BF16, sc.tip_window_stride_frames, winlist, winlist + 64, stream_);
             if (rc) return rc;
         }
     }

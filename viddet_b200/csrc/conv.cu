@@ -34,17 +34,48 @@ struct ConvParams {
     const float* scale; const float* shift; float slope;
     __nv_bfloat16* y;
 };
-struct ConvMaps { CUtensorMap x; CUtensorMap w; };
+struct ConvMaps { CUtensorMap x; CUtensorMap w; CUtensorMap y; };      // y: output map of the TMA-store epilogues, box {64 ch, BW, BH, BF, 1}
 
+// Epilogue of the 128-wide kernel and of the CTA-pair kernel (r02): BN / LeakyReLU / bf16 -> shared-memory tile in the 128-byte-swizzled
+// layout of a TMA box -> ONE cp.async.bulk.tensor store per [tile rows x 64 ch] (out-of-frame rows are clipped by the map).  The
+// per-thread 16-byte global stores it replaces (32 rows x 16 B per instruction) cost ~4 k LSU cycles per tile: more than the whole
+// mainloop of a pointwise cell.  One staging tile per column half (4 epilogue warps), named barriers 1 / 2.
+constexpr int C_OUT_TILE_BYTES = C_BLOCK_M * 64 * 2;
 template <int NT> struct ConvCfg {
     static constexpr int A_BYTES = C_BLOCK_M * C_BLOCK_K * 2;
     static constexpr int B_BYTES = NT * C_BLOCK_K * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int STAGES = (200 * 1024) / STAGE_BYTES > 8 ? 8 : (200 * 1024) / STAGE_BYTES;
+    static constexpr bool TMA_STORE = (NT == 128);              // 256-wide 1-CTA tiles (48 KB stages) keep the direct stores; they run on CTA pairs normally
+    static constexpr int OUT_BYTES = TMA_STORE ? 2 * C_OUT_TILE_BYTES : 0;
+    static constexpr int STAGES = (200 * 1024 - OUT_BYTES) / STAGE_BYTES > 8 ? 8 : (200 * 1024 - OUT_BYTES) / STAGE_BYTES;
     static constexpr int BN_BYTES = 2 * 1024 * 4;
     static constexpr int TMEM_COLS = 2 * NT;
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BN_BYTES + 2048 + 1024;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + OUT_BYTES + BN_BYTES + 2048 + 1024;
 };
+__device__ __forceinline__ void conv_half_bar(int half) {
+    if (half == 0) asm volatile("bar.sync 1, 128;" ::: "memory"); else asm volatile("bar.sync 2, 128;" ::: "memory");
+}
+// one epilogue pass of a warp: 64 accumulator columns of its 32 rows -> BN -> LeakyReLU -> bf16 -> its 32 rows of the staging tile
+__device__ __forceinline__ void conv_stage_64(const uint32_t* v, const float* sc, const float* sf, float slope, uint32_t dst_row, uint32_t sw) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        uint32_t pk[4];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int i = j * 8 + h * 4;
+            const float4 s4 = *reinterpret_cast<const float4*>(sc + i);
+            const float4 f4 = *reinterpret_cast<const float4*>(sf + i);
+            float v0 = fmaf(__uint_as_float(v[i]), s4.x, f4.x), v1 = fmaf(__uint_as_float(v[i + 1]), s4.y, f4.y);
+            float v2 = fmaf(__uint_as_float(v[i + 2]), s4.z, f4.z), v3 = fmaf(__uint_as_float(v[i + 3]), s4.w, f4.w);
+            v0 = v0 > 0.f ? v0 : v0 * slope; v1 = v1 > 0.f ? v1 : v1 * slope;
+            v2 = v2 > 0.f ? v2 : v2 * slope; v3 = v3 > 0.f ? v3 : v3 * slope;
+            __nv_bfloat162 h0 = __floats2bfloat162_rn(v0, v1), h1 = __floats2bfloat162_rn(v2, v3);
+            pk[2 * h] = *reinterpret_cast<uint32_t*>(&h0); pk[2 * h + 1] = *reinterpret_cast<uint32_t*>(&h1);
+        }
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst_row + (((uint32_t)j ^ sw) << 4)),
+                     "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]) : "memory");
+    }
+}
 
 struct ConvShared {
     uint64_t full[8], empty[8], tmem_full[2], tmem_empty[2];
@@ -60,9 +91,10 @@ conv_bn_lrelu_kernel(const __grid_constant__ ConvMaps maps, const __grid_constan
     extern __shared__ unsigned char smem_dyn[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
     unsigned char* ring = smem;
-    float* sscale = reinterpret_cast<float*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+    unsigned char* outb = smem + Cfg::STAGES * Cfg::STAGE_BYTES;          // [half][tile rows x 128 B] staging of the TMA-store epilogue
+    float* sscale = reinterpret_cast<float*>(outb + Cfg::OUT_BYTES);
     float* sshift = sscale + 1024;
-    ConvShared* sh = reinterpret_cast<ConvShared*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES + Cfg::BN_BYTES);
+    ConvShared* sh = reinterpret_cast<ConvShared*>(outb + Cfg::OUT_BYTES + Cfg::BN_BYTES);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int i = threadIdx.x; i < p.Cout; i += C_THREADS) { sscale[i] = p.scale[i]; sshift[i] = p.shift[i]; }
     // rows of the A stages that no TMA box ever writes (BW*BH < 128) must still hold finite bf16 values: zero them once
@@ -73,7 +105,7 @@ conv_bn_lrelu_kernel(const __grid_constant__ ConvMaps maps, const __grid_constan
         for (int i = 0; i < Cfg::STAGES; ++i) { tc::mbar_init(&sh->full[i], 1); tc::mbar_init(&sh->empty[i], 1); }
         for (int i = 0; i < 2; ++i) { tc::mbar_init(&sh->tmem_full[i], 1); tc::mbar_init(&sh->tmem_empty[i], 8); }
         tc::fence_barrier_init();
-        tc::prefetch_tmap(&maps.x); tc::prefetch_tmap(&maps.w);
+        tc::prefetch_tmap(&maps.x); tc::prefetch_tmap(&maps.w); tc::prefetch_tmap(&maps.y);
     }
     if (warp == 1) tc::tmem_alloc<Cfg::TMEM_COLS>(&sh->tmem_base);
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy zero fill before async-proxy (TMA/UMMA) use
@@ -162,7 +194,38 @@ conv_bn_lrelu_kernel(const __grid_constant__ ConvMaps maps, const __grid_constan
         const int r = q * 32 + lane;                          // row of the tile = (frame lf, pixel ly, lx) of the box
         const int lx = r % p.BW, ly = (r / p.BW) % p.BH, lf = r / (p.BW * p.BH);
         uint32_t it = 0;
-        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+        if constexpr (Cfg::TMA_STORE) {
+            // NT == 128: each half's 4 warps own 64 columns = one staging tile and one TMA store per M tile
+            const bool issuer = (q == 0 && lane == 0);
+            unsigned char* obase = outb + half * C_OUT_TILE_BYTES;
+            const uint32_t orow = tc::smem_u32(obase) + (uint32_t)r * 128u;
+            const uint32_t sw = (uint32_t)(r & 7);
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+                const ConvTile c = coords(tile);
+                const uint32_t buf = it & 1u;
+                tc::mbar_wait(&sh->tmem_full[buf], (it >> 1) & 1u);
+                tc::fence_after_sync();
+                const uint32_t tb = tmem_base + buf * NT + (uint32_t)(half * NH) + lane_addr;
+                uint32_t v[64];
+                tc::tmem_ld16(tb, v); tc::tmem_ld16(tb + 16, v + 16); tc::tmem_ld16(tb + 32, v + 32); tc::tmem_ld16(tb + 48, v + 48);
+                tc::tmem_ld_wait();
+                tc::fence_before_sync();
+                __syncwarp();
+                if (lane == 0) tc::mbar_arrive(&sh->tmem_empty[buf]);
+                const int col0 = c.nt * NT + half * NH;
+                if (issuer) tc::tma_store_wait_read<0>();             // the previous tile's store has read the staging tile
+                __syncwarp();
+                conv_half_bar(half);
+                conv_stage_64(v, sscale + col0, sshift + col0, p.slope, orow, sw);
+                tc::fence_proxy_async_smem();
+                __syncwarp();
+                conv_half_bar(half);
+                if (issuer) { tc::tma_store_5d(&maps.y, obase, col0, c.x0, c.y0, c.f0, c.b); tc::tma_store_commit(); }
+            }
+            if (issuer) tc::tma_store_wait<0>();
+            it = 0xffffffffu;
+        }
+        for (int tile = blockIdx.x; tile < p.total_tiles && it != 0xffffffffu; tile += gridDim.x, ++it) {
             const ConvTile c = coords(tile);
             const uint32_t buf = it & 1u;
             const int x = c.x0 + lx, y = c.y0 + ly;
@@ -239,10 +302,11 @@ template <int NT> struct Conv2Cfg {
     static constexpr int A_BYTES = C_BLOCK_M * C_BLOCK_K * 2;
     static constexpr int B_BYTES = (NT / 2) * C_BLOCK_K * 2;          // this CTA's half of the weight tile
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int STAGES = (200 * 1024) / STAGE_BYTES > 8 ? 8 : (200 * 1024) / STAGE_BYTES;
+    static constexpr int OUT_BYTES = 2 * C_OUT_TILE_BYTES;            // one staging tile per column half (TMA-store epilogue)
+    static constexpr int STAGES = (212 * 1024 - OUT_BYTES) / STAGE_BYTES > 8 ? 8 : (212 * 1024 - OUT_BYTES) / STAGE_BYTES;
     static constexpr int BN_BYTES = 2 * 1024 * 4;
     static constexpr int TMEM_COLS = 2 * NT;
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BN_BYTES + 2048 + 1024;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + OUT_BYTES + BN_BYTES + 2048 + 1024;
 };
 
 template <int NT>
@@ -252,9 +316,10 @@ conv_bn_lrelu_pair_kernel(const __grid_constant__ ConvMaps maps, const __grid_co
     extern __shared__ unsigned char smem_dyn[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
     unsigned char* ring = smem;
-    float* sscale = reinterpret_cast<float*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+    unsigned char* outb = smem + Cfg::STAGES * Cfg::STAGE_BYTES;
+    float* sscale = reinterpret_cast<float*>(outb + Cfg::OUT_BYTES);
     float* sshift = sscale + 1024;
-    Conv2Shared* sh = reinterpret_cast<Conv2Shared*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES + Cfg::BN_BYTES);
+    Conv2Shared* sh = reinterpret_cast<Conv2Shared*>(outb + Cfg::OUT_BYTES + Cfg::BN_BYTES);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = tc::cluster_ctarank();
     const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
@@ -266,7 +331,7 @@ conv_bn_lrelu_pair_kernel(const __grid_constant__ ConvMaps maps, const __grid_co
         for (int i = 0; i < Cfg::STAGES; ++i) { tc::mbar_init(&sh->full[i], 1); tc::mbar_init(&sh->empty[i], 1); tc::mbar_init(&sh->peer_full[i], 1); }
         for (int i = 0; i < 2; ++i) { tc::mbar_init(&sh->tmem_full[i], 1); tc::mbar_init(&sh->tmem_empty[i], 16); }   // 8 epilogue warps x 2 CTAs
         tc::fence_barrier_init();
-        tc::prefetch_tmap(&maps.x); tc::prefetch_tmap(&maps.w);
+        tc::prefetch_tmap(&maps.x); tc::prefetch_tmap(&maps.w); tc::prefetch_tmap(&maps.y);
     }
     if (warp == 1) tc::tmem_alloc_2cta<Cfg::TMEM_COLS>(&sh->tmem_base);
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -365,47 +430,40 @@ conv_bn_lrelu_pair_kernel(const __grid_constant__ ConvMaps maps, const __grid_co
         constexpr int NH = NT / 2;
         const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
         const int r = q * 32 + lane;
-        const int lx = r % p.BW, ly = (r / p.BW) % p.BH, lf = r / (p.BW * p.BH);
+        const bool issuer = (q == 0 && lane == 0);
+        unsigned char* obase = outb + half * C_OUT_TILE_BYTES;
+        const uint32_t orow = tc::smem_u32(obase) + (uint32_t)r * 128u;
+        const uint32_t sw = (uint32_t)(r & 7);
         uint32_t it = 0;
         for (int pair = cluster_id; pair < total_pairs; pair += num_clusters, ++it) {
             const ConvTile c = coords(pair, rank);
             const uint32_t buf = it & 1u;
-            const int x = c.x0 + lx, y = c.y0 + ly, f = c.f0 + lf;
-            const bool inb = (lf < p.BF) && (x < p.W) && (y < p.H) && (f < p.F1) && (c.b < p.F2);
             tc::mbar_wait_cluster(&sh->tmem_full[buf], (it >> 1) & 1u);
             tc::fence_after_sync();
             const uint32_t tbase = tmem_base + buf * NT + (uint32_t)(half * NH) + lane_addr;
             const int col0 = c.nt * NT + half * NH;
-            const size_t pix = inb ? (((size_t)c.b * p.F1 + f) * p.H + y) * p.W + x : 0;
-            __nv_bfloat16* yrow = p.y + pix * p.Cout + col0;
-            const float* sc = sscale + col0;
-            const float* sf = sshift + col0;
 #pragma unroll 1
-            for (int n0 = 0; n0 < NH; n0 += 32) {
-                uint32_t v[32];
-                tc::tmem_ld16(tbase + n0, v); tc::tmem_ld16(tbase + n0 + 16, v + 16); tc::tmem_ld_wait();
-                uint32_t packed[16];
-#pragma unroll
-                for (int i = 0; i < 32; i += 4) {
-                    const float4 s4 = *reinterpret_cast<const float4*>(sc + n0 + i);
-                    const float4 f4 = *reinterpret_cast<const float4*>(sf + n0 + i);
-                    float v0 = fmaf(__uint_as_float(v[i]), s4.x, f4.x), v1 = fmaf(__uint_as_float(v[i + 1]), s4.y, f4.y);
-                    float v2 = fmaf(__uint_as_float(v[i + 2]), s4.z, f4.z), v3 = fmaf(__uint_as_float(v[i + 3]), s4.w, f4.w);
-                    v0 = v0 > 0.f ? v0 : v0 * p.slope; v1 = v1 > 0.f ? v1 : v1 * p.slope;
-                    v2 = v2 > 0.f ? v2 : v2 * p.slope; v3 = v3 > 0.f ? v3 : v3 * p.slope;
-                    __nv_bfloat162 h0 = __floats2bfloat162_rn(v0, v1), h1 = __floats2bfloat162_rn(v2, v3);
-                    packed[i / 2] = *reinterpret_cast<uint32_t*>(&h0); packed[i / 2 + 1] = *reinterpret_cast<uint32_t*>(&h1);
+            for (int pass = 0; pass < NH / 64; ++pass) {
+                uint32_t v[64];
+                const uint32_t ta = tbase + (uint32_t)(pass * 64);
+                tc::tmem_ld16(ta, v); tc::tmem_ld16(ta + 16, v + 16); tc::tmem_ld16(ta + 32, v + 32); tc::tmem_ld16(ta + 48, v + 48);
+                tc::tmem_ld_wait();
+                if (pass == NH / 64 - 1) {                           // this warp has read its share of the accumulator
+                    tc::fence_before_sync();
+                    __syncwarp();
+                    if (lane == 0) tc::mbar_arrive_cluster(&sh->tmem_empty[buf], 0u);
                 }
-                if (inb) {
-                    uint4* dst = reinterpret_cast<uint4*>(yrow + n0);
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) dst[i] = make_uint4(packed[4 * i], packed[4 * i + 1], packed[4 * i + 2], packed[4 * i + 3]);
-                }
+                if (issuer) tc::tma_store_wait_read<0>();             // the previous store has read the staging tile
+                __syncwarp();
+                conv_half_bar(half);
+                conv_stage_64(v, sscale + col0 + pass * 64, sshift + col0 + pass * 64, p.slope, orow, sw);
+                tc::fence_proxy_async_smem();
+                __syncwarp();
+                conv_half_bar(half);
+                if (issuer && c.b < p.F2) { tc::tma_store_5d(&maps.y, obase, col0 + pass * 64, c.x0, c.y0, c.f0, c.b); tc::tma_store_commit(); }
             }
-            tc::fence_before_sync();
-            __syncwarp();
-            if (lane == 0) tc::mbar_arrive_cluster(&sh->tmem_empty[buf], 0u);
         }
+        if (issuer) tc::tma_store_wait<0>();
     }
     __syncwarp();
     tc::fence_before_sync();
@@ -495,6 +553,11 @@ extern "C" int vd_conv_bn_lrelu(const void* x, void* y, int B, int T, int H, int
     const bool pair = pair_ok && NT == 256 && (long long)p.F2 * p.tiles_f * p.tiles_y * p.tiles_x >= 2;
     uint32_t boxW[3] = {C_BLOCK_K, (uint32_t)(pair ? NT / 2 : NT), 1};
     rc = encode_tmap_bf16(&maps.w, weight, 3, dimsW, strW, boxW);
+    if (rc) return rc;
+    uint64_t dimsY[5] = {(uint64_t)Cout, (uint64_t)p.W, (uint64_t)p.H, (uint64_t)p.F1, (uint64_t)p.F2};
+    uint64_t strY[4] = {Cout * e, (uint64_t)p.W * Cout * e, (uint64_t)p.H * p.W * Cout * e, (uint64_t)p.F1 * p.H * p.W * Cout * e};
+    uint32_t boxY[5] = {64, (uint32_t)p.BW, (uint32_t)p.BH, (uint32_t)p.BF, 1};
+    rc = encode_tmap_bf16(&maps.y, y, 5, dimsY, strY, boxY);
     if (rc) return rc;
     if (pair) return launch_conv_pair(maps, p, (cudaStream_t)stream_);
     if (NT == 256) return launch_conv<256>(maps, p, (cudaStream_t)stream_);

@@ -670,12 +670,16 @@ def main():
         f_tconv = 2.0 * (3 * TEMPORAL_T - 2) * hw_c2 * windows
         f_all = f_tconv + 2.0 * 3 * (5 + C) * hw_c * TEMPORAL_T * windows
         tpeak, tkind = measured_tensor_peak()
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "traffic_temporal_head_fused_%s.json" % args.workload)
+        if sessions[0].fused_tip and os.path.exists(tpath):
+            traffic = json.load(open(tpath)).get("traffic_bytes_per_launch")
         if sessions[0].fused_tip:
             # tip cell + prediction conv + decode + candidate filter as ONE kernel per scale (csrc/tfused.cuh): the dominant kernels
             # carry both GEMMs; the tip never goes to HBM
             roof = {"bound": "tensor", "kernel": "temporal_head_fused_kernel x3 scales (tcgen05 cta_group::2: tip-cell implicit GEMM -> BN/LReLU/bf16 tile in shared memory -> prediction GEMM -> decode + candidate filter; layers.py:82-89 + yolo3.py:157-199)",
                     "achieved": f_all / (head_ms * 1e-3) / 1e12, "peak": tpeak, "peak_kind": tkind, "unit": "TFLOP/s",
-                    "frac": f_all / (head_ms * 1e-3) / 1e12 / tpeak, "traffic": None, "algorithmic_flops_per_launch": f_all,
+                    "frac": f_all / (head_ms * 1e-3) / 1e12 / tpeak, "traffic": traffic, "algorithmic_flops_per_launch": f_all,
                     "kernel_ms": head_ms, "head_kernel_ms": None, "nms_kernel_ms": nms_ms,
                     "path_frac": f_all / (step_ms * 1e-3) / 1e12 / tpeak, "path_flops_per_step": f_all}
         else:

@@ -431,6 +431,7 @@ temporal_head_fused_kernel(const __grid_constant__ FusedMaps maps, const __grid_
                 if (lane == 0) tc::mbar_arrive_cluster(&sh->tip_empty, 0u);
                 tc::mbar_wait_cluster(&sh->stg_empty, (cc & 1u) ^ 1u);             // the previous chunk's prediction MMAs have read the staging tiles
                 if (st) p.stamps[cc * 16 + 11] = clock64();
+                const float2 slope2 = make_float2(p.slope, p.slope);
                 const float4* sc = reinterpret_cast<const float4*>(sbn + s * 2048 + nt * F_NT + half * 128);
                 const float4* sf = reinterpret_cast<const float4*>(sbn + s * 2048 + 1024 + nt * F_NT + half * 128);
 #pragma unroll
@@ -444,12 +445,12 @@ temporal_head_fused_kernel(const __grid_constant__ FusedMaps maps, const __grid_
                             const int i = t * 64 + j * 8 + h * 4;
                             const float4 s4 = sc[i >> 2];
                             const float4 f4 = sf[i >> 2];
-                            float v0 = fmaf(__uint_as_float(r[i]), s4.x, f4.x), v1 = fmaf(__uint_as_float(r[i + 1]), s4.y, f4.y);
-                            float v2 = fmaf(__uint_as_float(r[i + 2]), s4.z, f4.z), v3 = fmaf(__uint_as_float(r[i + 3]), s4.w, f4.w);
-                            // LeakyReLU as max(v, v * slope) (0 < slope < 1: the same bits as v > 0 ? v : v * slope, one instruction less)
-                            v0 = fmaxf(v0, v0 * p.slope); v1 = fmaxf(v1, v1 * p.slope);
-                            v2 = fmaxf(v2, v2 * p.slope); v3 = fmaxf(v3, v3 * p.slope);
-                            __nv_bfloat162 h0 = __floats2bfloat162_rn(v0, v1), h1 = __floats2bfloat162_rn(v2, v3);
+                            // packed fp32x2 FMA / MUL (sm_100: two lanes per instruction, each rounded like the scalar form); LeakyReLU as
+                            // max(v, v * slope) (0 < slope < 1: the same bits as v > 0 ? v : v * slope)
+                            const float2 v01 = __ffma2_rn(make_float2(__uint_as_float(r[i]), __uint_as_float(r[i + 1])), make_float2(s4.x, s4.y), make_float2(f4.x, f4.y));
+                            const float2 v23 = __ffma2_rn(make_float2(__uint_as_float(r[i + 2]), __uint_as_float(r[i + 3])), make_float2(s4.z, s4.w), make_float2(f4.z, f4.w));
+                            const float2 m01 = __fmul2_rn(v01, slope2), m23 = __fmul2_rn(v23, slope2);
+                            __nv_bfloat162 h0 = __floats2bfloat162_rn(fmaxf(v01.x, m01.x), fmaxf(v01.y, m01.y)), h1 = __floats2bfloat162_rn(fmaxf(v23.x, m23.x), fmaxf(v23.y, m23.y));
                             pk[2 * h] = *reinterpret_cast<uint32_t*>(&h0); pk[2 * h + 1] = *reinterpret_cast<uint32_t*>(&h1);
                         }
                         asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + (((uint32_t)j ^ sw) << 4)),

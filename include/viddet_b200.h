@@ -214,6 +214,11 @@ int vd_head_launch_count(const VdHeadParams* p);
 /* 1 if vd_head_forward runs the temporal tip cell and the head as ONE kernel per scale for these parameters (the tip tile stays in
  * shared memory between the two GEMMs: yolo3_temporal.py:226-227 + yolo3.py:157-199 fused), 0 if as separate kernels, -1 on bad params. */
 int vd_head_fused_tip(const VdHeadParams* p);
+/* Host-side work plan of that kernel for `pairs` CTA pairs (<= 80), for tests and tooling -- no device work: items_out[s] = items (pairs
+ * of 128-row tiles) of scale s; pair c runs strided_out[s] rounds of item = round * pairs + c, then the contiguous items
+ * beg_out[s * 81 + c] .. beg_out[s * 81 + c + 1]; together the pairs cover every item exactly once.  items_out / strided_out: 3 ints,
+ * beg_out: 3 * 81 ints. */
+int vd_head_fused_tip_plan(const VdHeadParams* p, int pairs, int* items_out, int* strided_out, int* beg_out);
 /* Same conv + decode, but materialises the reference's (frames, rows, 6) detection tensor
  * (what `concat(all_detections)` holds at yolo3.py:523) instead of running NMS. */
 int vd_head_detections(const VdHeadParams* p, float* det, void* workspace, size_t workspace_bytes,

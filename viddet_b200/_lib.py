@@ -74,6 +74,7 @@ SIGNATURES = {
     "vd_head_forward_stages": (_i, [ctypes.POINTER(VdHeadParams), _vp, _vp, _vp, _vp, _vp, _sz, _vp, _i]),
     "vd_head_launch_count": (_i, [ctypes.POINTER(VdHeadParams)]),
     "vd_head_fused_tip": (_i, [ctypes.POINTER(VdHeadParams)]),
+    "vd_head_fused_tip_plan": (_i, [ctypes.POINTER(VdHeadParams), _i, _ip, _ip, _ip]),
     "vd_head_stats_offset": (_sz, [ctypes.POINTER(VdHeadParams)]),
     "vd_head_debug_offset": (_sz, [ctypes.POINTER(VdHeadParams)]),
     "vd_head_detections": (_i, [ctypes.POINTER(VdHeadParams), _vp, _vp, _sz, _vp]),

@@ -1835,6 +1835,29 @@ extern "C" int vd_head_launch_count(const VdHeadParams* hp) {
     return n;
 }
 
+extern "C" int vd_head_fused_tip_plan(const VdHeadParams* hp, int pairs, int* items_out, int* strided_out, int* beg_out) {
+    VD_CHECK_ARG(hp && items_out && strided_out && beg_out && pairs >= 1 && pairs <= F_MAX_CLUSTERS, "fused_tip_plan: bad arguments");
+    HeadPlan pl;
+    int rc = make_plan(hp, &pl);
+    if (rc) return rc;
+    VD_CHECK_ARG(hp->T >= 1 && hp->frames % hp->T == 0, "fused_tip_plan: frames %d not a multiple of T %d", hp->frames, hp->T);
+    FusedParams fp;
+    memset(&fp, 0, sizeof(fp));
+    fp.B = hp->frames / hp->T; fp.T = hp->T; fp.num_scales = hp->num_scales;
+    for (int s = 0; s < hp->num_scales; ++s) {
+        const VdHeadScale& sc = hp->scale[s];
+        fp.sc[s].HW = sc.H * sc.W; fp.sc[s].Cin = sc.Cin; fp.sc[s].rows = hp->T * sc.H * sc.W;
+        fp.sc[s].m_tiles = ceil_div(fp.sc[s].rows, F_BLOCK_M); fp.sc[s].n_chunks = sc.Cin / F_NT;
+    }
+    tfused_schedule(&fp, pairs);
+    for (int s = 0; s < VD_MAX_SCALES; ++s) {
+        items_out[s] = s < hp->num_scales ? (int)(((long long)fp.B * fp.sc[s].m_tiles + 1) / 2) : 0;
+        strided_out[s] = fp.strided[s];
+        for (int c = 0; c <= pairs; ++c) beg_out[s * (F_MAX_CLUSTERS + 1) + c] = (int)fp.beg[s][c];
+    }
+    return VD_OK;
+}
+
 extern "C" int vd_head_fused_tip(const VdHeadParams* hp) {
     HeadPlan pl;
     if (make_plan(hp, &pl) != VD_OK) return -1;

@@ -1,4 +1,4 @@
-// temporal_head_fused_kernel -- cfg 4 in ONE kernel per scale (SURVEY section 7, K4 -> K1):
+// temporal_head_fused_kernel -- cfg 4 in ONE kernel, all scales in one launch (SURVEY section 7, K4 -> K1):
 //   temporal (3,1,1) tip cell (Conv3D + BN + LeakyReLU, layers.py:82-89; yolo3_temporal.py:226-227)
 //   -> 1x1 prediction conv (yolo3.py:62,157) -> YOLOOutputV3 decode (yolo3.py:158-199) -> speculative candidate filter
 // The tip tile never leaves the SM: the tip GEMM's accumulator (TMEM) goes through BN / LeakyReLU / bf16 rounding into shared
@@ -6,19 +6,23 @@
 // Included by head.cu (uses HeadGeom / kSpecCap and the decode math of common.cuh); results are bit-identical to the unfused
 // chain temporal_conv_pair_kernel -> head_kernel<EPI_SPEC> (same bf16 tip bits, same K order of the prediction GEMM).
 //
-// CTA pair (tcgen05 cta_group::2), persistent; an item = two consecutive 128-row tiles of the flattened (window, T*HW) row axis,
-// all channel chunks of 256:
-//   warp 0 (both CTAs)   TMA producer: per k-block its own A tile [128 rows x 64 ch] of the shifted frame + half of the tap's weight
-//                        tile [128 x 64]; per chunk its half of the prediction weights [NPAD/2 x 256 ch]
-//   warp 1 (leader CTA)  MMA issuer: tip GEMM M256 x N256 x K(3 taps x Cin) into TMEM cols [0,256) (single buffer), then the
-//                        prediction GEMM M256 x NPAD x K256 from the staged tip chunk into one of two prediction accumulators
-//                        (TMEM cols [256,384) / [384,512)): accumulates over the chunks
-//   warps 2-9            per chunk: tcgen05.ld -> BN -> LeakyReLU -> bf16 -> st.shared (swizzled) -> fence.proxy.async -> arrive;
-//                        after an item's last chunk: decode + candidate filter on the prediction accumulator (the EPI_SPEC epilogue of
-//                        head_kernel; a tile spans up to two frames here, so frame / cell are per lane and candidates go to their
-//                        frame's list with one atomic each -- ~0.3 % of the class logits pass)
-// The tip accumulator is single-buffered: these kernels are bound by the L2 -> SM operand traffic, not by the tensor pipe (measured:
-// same time at 1.9 and 1.5 GHz SM clock), so the pipe has slack and the operand ring keeps filling while an accumulator drains.
+// CTA pair (tcgen05 cta_group::2), persistent; an item = two consecutive 128-row tiles of the flattened (window, T*HW) row axis of
+// one scale, all its channel chunks of 256; the host deals the items of all scales to the pairs (tfused_schedule):
+//   warp 0 (both CTAs)   TMA producer.  Ring entries in consumption order: per k-block the CTA's A tile [128 rows x 64 ch] of the
+//                        shifted frame + half of the tap's weight tile [128 x 64]; behind the k-blocks of chunk c + 1 one entry with
+//                        the CTA's half of chunk c's prediction weights [NPAD/2 x 256 ch]
+//   warp 1 (leader CTA)  MMA issuer: tip GEMM M256 x N256 x K(3 taps x Cin) of chunk c + 1 into TMEM cols [0,256) (single buffer),
+//                        commit, then the prediction GEMM M256 x NPAD x K256 of chunk c from the staged tip chunk into one of two
+//                        prediction accumulators (TMEM cols [256,384) / [384,512), accumulating over an item's chunks): the tensor
+//                        pipe runs it while the epilogue warps read the tip accumulator back
+//   warps 2-9            per chunk: tcgen05.ld of the warp's 128 columns -> accumulator handed back -> BN (shared memory) -> LeakyReLU
+//                        -> bf16 -> st.shared (swizzled) -> fence.proxy.async -> arrive; then, one chunk late, the decode + candidate
+//                        filter of the item whose last prediction GEMM has just run (the EPI_SPEC epilogue of head_kernel; a tile
+//                        spans up to two frames here, so frame / cell are per lane and candidates go to their frame's list with one
+//                        atomic each -- ~0.3 % of the class logits pass)
+// The tip accumulator is single-buffered (TMEM: 256 + 2 x 128 columns); the tip GEMM of these shapes is bound by the operand traffic
+// L2 -> SM rather than by the tensor pipe (same time at 1.9 and 1.5 GHz SM clock), so the ring keeps filling during the read-back.
+// Measured step by step in DESIGN.md section 4.5.
 #pragma once
 
 namespace vd {

@@ -72,5 +72,10 @@ def test_fused_tip_flag_and_applicability():
     assert lib.vd_head_fused_tip(ctypes.byref(p)) == 0
     p.num_class = 20
     assert lib.vd_head_fused_tip(ctypes.byref(p)) == 1
+    p.num_class = 23                                    # padded onto the 30-class shape
+    assert lib.vd_head_fused_tip(ctypes.byref(p)) == 1
+    p.num_class = 31                                    # two class windows of the 80-class shape: separate kernels
+    assert lib.vd_head_fused_tip(ctypes.byref(p)) == 0
+    p.num_class = 20
     p.scale[2].Cin = 128                                # channel counts must be multiples of 256
     assert lib.vd_head_fused_tip(ctypes.byref(p)) == 0

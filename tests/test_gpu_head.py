@@ -577,7 +577,7 @@ def test_arbitrary_class_counts_valid_thresh_below_zero_and_heavy_ties():
             assert torch.equal(scores.view(torch.int32), out[:, :100, 1:2].contiguous().view(torch.int32))
 
 
-@pytest.mark.parametrize("C,B,size", [(30, 3, 160), (20, 3, 160), (30, 8, 256)])
+@pytest.mark.parametrize("C,B,size", [(30, 3, 160), (20, 3, 160), (30, 8, 256), (23, 3, 160), (7, 3, 160)])      # 23 / 7 classes: padded onto the 30 / 20 shapes
 def test_fused_tip_head_equals_separate_kernels_bit_exact(C, B, size):
     """cfg 4 in ONE kernel per scale (tip cell -> BN/LReLU/bf16 tile in shared memory -> prediction GEMM -> decode + candidate
     filter, csrc/tfused.cuh) == the separate kernels (vd_temporal_conv -> head kernel), bit for bit: keep rows, ids, scores, boxes,

@@ -1737,7 +1737,7 @@ failed_windows_kernel(const uint32_t* __restrict__ failed, const uint32_t* __res
 static bool tfused_applicable(const VdHeadParams* hp, const HeadPlan& pl, bool spec) {
     static const bool on = []() { const char* e = getenv("VD_TFUSED"); return e ? atoi(e) != 0 : true; }();
     if (!on || !spec || (hp->flags & VD_HEAD_NO_FUSED_TIP)) return false;
-    if (pl.n_pass != 1 || pl.repack || hp->precision != VD_PREC_BF16 || hp->join != VD_JOIN_NONE || pl.kp.K_frames != 1) return false;
+    if (pl.n_pass != 1 || hp->precision != VD_PREC_BF16 || hp->join != VD_JOIN_NONE || pl.kp.K_frames != 1) return false;      // class counts below a compiled shape run padded (weights re-laid out, padding classes masked), like head_kernel
     if (!tfused_supported(pl.C) || hp->T < 1 || hp->frames <= 0 || hp->frames % hp->T || hp->frames / hp->T > 65536) return false;
     for (int s = 0; s < hp->num_scales; ++s) {
         const VdHeadScale& sc = hp->scale[s];
@@ -1749,7 +1749,7 @@ static bool tfused_applicable(const VdHeadParams* hp, const HeadPlan& pl, bool s
     return true;
 }
 
-static int run_tfused(const VdHeadParams* hp, const HeadPlan& pl, const HeadKernelParams& kp, cudaStream_t stream) {
+static int run_tfused(const VdHeadParams* hp, const HeadPlan& pl, const HeadKernelParams& kp, const void* const* wptr, cudaStream_t stream) {
     const char* e_dbg = getenv("VD_TFUSED_DBG");            // profiling aids (results are garbage): bit 0 = no decode / filter epilogue;
     const char* e_scl = getenv("VD_TFUSED_SCALES");         // bit mask of the scales that get any work
     const int dbg = e_dbg ? atoi(e_dbg) : 0, scl = e_scl ? atoi(e_scl) : 7;
@@ -1782,7 +1782,7 @@ static int run_tfused(const VdHeadParams* hp, const HeadPlan& pl, const HeadKern
         uint64_t dimsP[2] = {Cin, (uint64_t)3 * (5 + pl.C)};
         uint64_t strP[1] = {Cin * 2};
         uint32_t boxP[2] = {F_BLOCK_K, (uint32_t)(pl.n_pad / 2)};
-        rc = encode_tmap_bf16(&maps.wp[s], sc.weight_bf16, 2, dimsP, strP, boxP);
+        rc = encode_tmap_bf16(&maps.wp[s], wptr[s], 2, dimsP, strP, boxP);
         if (rc) return rc;
     }
     // The kernel takes every register of its SMs (168 x 12 warps' worth), so nothing shares them: the previous launch's per-frame NMS
@@ -1931,7 +1931,7 @@ extern "C" int vd_head_forward_stages(const VdHeadParams* hp, float* ids, float*
         if (rc) return rc;
         if (fused_tip) {
             window_params(hp, pl, ws, 0, &kp, wptr);
-            rc = run_tfused(hp, pl, kp, stream);
+            rc = run_tfused(hp, pl, kp, wptr, stream);
             if (rc) return rc;
         }
         for (int ps = 0; ps < pl.n_pass && !fused_tip; ++ps) {       // one launch per class window (1 unless num_class > 80), all appending to the frames' lists

@@ -148,6 +148,7 @@ typedef struct VdHeadScale {
 #define VD_HEAD_NO_FUSED_TIP 1  /* temporal heads: run the tip cell and the head as separate kernels (vd_temporal_conv -> head kernel) even
                                  * where the fused kernel applies (bf16, num_class <= 30 -- 6..19 and 21..29 padded onto the 20 / 30 shapes --, Cin % 256 == 0);
                                  * results are bit-identical */
+#define VD_HEAD_NO_PAIR_KERNEL 2 /* wide heads (num_class 31..80): keep the 1-CTA head kernel instead of the CTA-pair one (same results) */
 typedef struct VdHeadParams {
     int num_scales;              /* 3, output order s32, s16, s8 (yolo3.py:416-417)             */
     int num_class;

@@ -626,6 +626,34 @@ def test_fused_tip_head_equals_separate_kernels_bit_exact(C, B, size):
         assert torch.equal(a.view(torch.int32), b2.view(torch.int32))
 
 
+@pytest.mark.parametrize("C,B,size", [(80, 5, 160), (80, 3, 608), (45, 4, 224)])
+def test_pair_head_kernel_equals_one_cta_kernel_bit_exact(C, B, size):
+    """Wide heads (num_class 31..80 on the 256-column shape): the speculative head kernel on CTA pairs (csrc/hpair.cuh, flattened
+    frames*HW row axis, per-lane frames) == the 1-CTA head kernel, bit for bit: keep rows, ids, scores, boxes on the cold call and on
+    steady calls with new inputs; odd tile counts (padding tiles), a padded class count (45 -> 80)."""
+    rng = np.random.RandomState(31 + C + B)
+    ws, bs = make_pred_weights(rng, C, bias_scale=0.1)
+    heads = [build_head(C, ws, bs, pair_kernel=f) for f in (True, False)]
+    for h in heads:
+        h.set_nms(0.45, 400, 100)
+    batches = [[cuda(t) for t in make_tips(rng, B, size=size)] for _ in range(3)]
+    sess = [h.session([t.clone() for t in batches[0]], return_keep=True) for h in heads]
+    for call, batch in enumerate(batches + [batches[1]]):
+        for s_ in sess:
+            for dst, src in zip(s_.tips, batch):
+                dst.copy_(src)
+            s_.run()
+        torch.cuda.synchronize()
+        f_, u_ = sess
+        assert torch.equal(f_.keep, u_.keep), (C, call)
+        assert torch.equal(f_.ids.view(torch.int32), u_.ids.view(torch.int32)), (C, call)
+        assert torch.equal(f_.scores.view(torch.int32), u_.scores.view(torch.int32)), (C, call)
+        assert torch.equal(f_.bboxes.view(torch.int32), u_.bboxes.view(torch.int32)), (C, call)
+        assert int((f_.keep >= 0).sum()) > 0
+        if call >= 1:
+            assert f_.redone_frames() == u_.redone_frames() and f_.redone_frames() <= max(1, B // 2), (C, call, f_.redone_frames(), u_.redone_frames())
+
+
 def test_clip_windows_equal_materialised_windows_bit_exact():
     """Temporal head on windows sliding over a RESIDENT clip (ClipWindows: one overlapping TMA map, no copies) == the same head on
     the materialised (B,T,C,H,W) windows, bit for bit; the clamped windows at the clip's ends (datasets/imgnetvid.py:480-506) go

@@ -16,7 +16,7 @@ VD_MAX_MIRRORS = 7
 VD_MODE_INFER, VD_MODE_TRAIN, VD_MODE_AGNOSTIC = 0, 1, 2
 VD_JOIN_NONE, VD_JOIN_CAT, VD_JOIN_MAX, VD_JOIN_MEAN = 0, 1, 2, 3
 VD_STAGE_TCONV, VD_STAGE_HEAD, VD_STAGE_NMS, VD_STAGE_ALL = 1, 2, 4, 7
-VD_HEAD_NO_FUSED_TIP = 1          # VdHeadParams.flags
+VD_HEAD_NO_FUSED_TIP, VD_HEAD_NO_PAIR_KERNEL = 1, 2          # VdHeadParams.flags
 VD_PREC_BF16, VD_PREC_FP32_SPLIT, VD_PREC_BF16X2 = 0, 1, 2
 PLANES = {VD_PREC_BF16: 1, VD_PREC_FP32_SPLIT: 3, VD_PREC_BF16X2: 2}
 ERR_NAMES = {-1: "VD_ERR_INVALID_ARG", -2: "VD_ERR_UNSUPPORTED", -3: "VD_ERR_WORKSPACE", -4: "VD_ERR_CUDA"}

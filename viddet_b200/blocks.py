@@ -608,11 +608,12 @@ class YOLOV3Head:
     """
 
     def __init__(self, classes, anchors=None, strides=None, channels=None, nms_thresh=0.45, nms_topk=400,
-                 post_nms=100, temporal=None, k=1, agnostic=False, precision="bf16", fuse_tip=True):
+                 post_nms=100, temporal=None, k=1, agnostic=False, precision="bf16", fuse_tip=True, pair_kernel=True):
         """precision 'bf16' (default): bf16 operands, fp32 accumulate -- 1e-3 relative vs the fp32 reference on bf16-representable
         inputs.  precision 'fp32': fp32 NCHW tips / weights are split into three bf16 planes, six plane products -- 1e-5
         relative (VD_PREC_FP32_SPLIT); 'bf16x2': two planes, three products -- 1e-4 (VD_PREC_BF16X2).  Per-frame heads only."""
         self._precision = _precision_code(precision)
+        self.pair_kernel = bool(pair_kernel)   # wide heads (31..80 classes): speculative head kernel on CTA pairs (bit-identical results; False = 1-CTA kernel)
         self.fuse_tip = bool(fuse_tip)     # temporal='conv21': tip cell + head in one kernel per scale where it applies (bit-identical; False = separate kernels)
         if self._precision != _lib.VD_PREC_BF16 and temporal not in (None, "conv21"):
             raise NotImplementedError("the fp32-parity modes cover the per-frame head and the 'conv21' temporal head")
@@ -681,7 +682,7 @@ class YOLOV3Head:
         p.nms_thresh, p.valid_thresh = float(self.nms_thresh), float(self.valid_thresh)
         p.nms_topk, p.post_nms = int(self.nms_topk), int(self.post_nms)
         p.precision = self._precision
-        p.flags = 0 if self.fuse_tip else _lib.VD_HEAD_NO_FUSED_TIP
+        p.flags = (0 if self.fuse_tip else _lib.VD_HEAD_NO_FUSED_TIP) | (0 if self.pair_kernel else _lib.VD_HEAD_NO_PAIR_KERNEL)
         planes = _lib.PLANES[self._precision]
         split = planes > 1
         frames = None

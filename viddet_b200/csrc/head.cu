@@ -1451,6 +1451,7 @@ struct HeadPlan {
 
 }  // namespace vd
 #include "tfused.cuh"
+#include "hpair.cuh"
 namespace vd {
 
 static int head_npad(int C) { int n = 3 * (5 + C); return (n + 15) / 16 * 16; }
@@ -1710,6 +1711,60 @@ static int launch_pred(const HeadMaps& maps, const HeadKernelParams& kp, cudaStr
     return set_error(VD_ERR_INVALID_ARG, "pred_conv: bad padded width %d", kp.n_pad);
 }
 
+// Wide heads (256 prediction columns) run the speculative head kernel on CTA pairs (hpair.cuh) where it applies.
+static bool hpair_applicable(const VdHeadParams* hp, const HeadPlan& pl, bool spec) {
+    static const bool on = []() { const char* e = getenv("VD_HEAD_PAIR"); return e ? atoi(e) != 0 : true; }();
+    if (!on || !spec || (hp->flags & VD_HEAD_NO_PAIR_KERNEL) || pl.n_pass != 1 || hp->precision != VD_PREC_BF16 || hp->join != VD_JOIN_NONE || pl.kp.K_frames != 1) return false;
+    if (!hpair_supported(pl.C) || hp->frames <= 0) return false;
+    for (int s = 0; s < hp->num_scales; ++s) {
+        const VdHeadScale& sc = hp->scale[s];
+        if (sc.tconv_weight_bf16) return false;
+        const long long tiles = ceil_div((long long)hp->frames * sc.H * sc.W, 128);
+        if (tiles < 2 || tiles > 2 * 65000) return false;
+    }
+    return true;
+}
+
+static int run_hpair(const VdHeadParams* hp, const HeadPlan& pl, const HeadKernelParams& kp, const void* const* wptr, cudaStream_t stream) {
+    PairParams pp;
+    PairMaps maps;
+    memset(&pp, 0, sizeof(pp));
+    memset(&maps, 0, sizeof(maps));
+    pp.num_scales = hp->num_scales; pp.frames = hp->frames;
+    pp.g = kp.g; pp.c_valid = kp.c_valid; pp.valid_thresh = hp->valid_thresh;
+    pp.boxes = kp.boxes; pp.spec_lists = kp.spec_lists; pp.spec_cnt = kp.spec_cnt; pp.spec_tau = kp.spec_tau;
+    pp.tile_counter = kp.tile_counter; pp.ws_magic = kp.ws_magic;
+    { const char* e = getenv("VD_HEAD_PAIR_DBG"); pp.dbg = e ? atoi(e) : 0; }
+    int clusters = sm_count() / 2;
+    if (clusters > F_MAX_CLUSTERS) clusters = F_MAX_CLUSTERS;
+    pp.pairs = clusters;
+    double load[F_MAX_CLUSTERS];
+    int cnt[F_MAX_CLUSTERS];
+    for (int c = 0; c < clusters; ++c) load[c] = 0.0;
+    for (int s = 0; s < hp->num_scales; ++s) {
+        const VdHeadScale& sc = hp->scale[s];
+        PairScale& q = pp.sc[s];
+        q.HW = sc.H * sc.W; q.Cin = sc.Cin; q.rows = hp->frames * sc.H * sc.W; q.m_tiles = ceil_div(q.rows, 128); q.bias = kp.bias[s];
+        const uint64_t Cin = (uint64_t)sc.Cin;
+        uint64_t dimsA[2] = {Cin, (uint64_t)q.rows};
+        uint64_t strA[1] = {Cin * 2};
+        uint32_t boxA[2] = {64, 128};
+        int rc = encode_tmap_bf16(&maps.a[s], sc.tip_nhwc_bf16, 2, dimsA, strA, boxA);
+        if (rc) return rc;
+        uint64_t dimsW[2] = {Cin, (uint64_t)3 * (5 + pl.C)};
+        uint32_t boxW[2] = {64, (uint32_t)(pl.n_pad / 2)};
+        rc = encode_tmap_bf16(&maps.w[s], wptr[s], 2, dimsW, strA, boxW);
+        if (rc) return rc;
+        // scales in the order given (deep -> shallow = decreasing K): an item costs its k-blocks + the decode of two tiles
+        const int items = (q.m_tiles + 1) / 2;
+        lpt_fill(load, clusters, items, 0.55 * (sc.Cin / 64) + 3.0, cnt);
+        int acc = 0;
+        for (int c = 0; c < clusters; ++c) { pp.beg[s][c] = (unsigned short)acc; acc += cnt[c]; }
+        for (int c = clusters; c <= F_MAX_CLUSTERS; ++c) pp.beg[s][c] = (unsigned short)acc;
+    }
+    return launch_hpair(maps, pp, pl.C, clusters, stream);
+}
+
 // Exact fallback of the fused temporal head: the failed FRAMES (queued by nms_spec_kernel) -> the distinct WINDOWS they belong to, so that
 // the conditional tip-cell launches recompute every such window once (on a cold workspace all T frames of every window are listed).
 // out[0] = number of windows, out[64 + i] = first frame of window i.  One CTA; a bitmap of the windows in shared memory.
@@ -1929,12 +1984,13 @@ extern "C" int vd_head_forward_stages(const VdHeadParams* hp, float* ids, float*
         // any other state is detected on the device and handled exactly
         rc = repack_windows(hp, pl, ws, stream);
         if (rc) return rc;
-        if (fused_tip) {
+        const bool pair_head = !fused_tip && hpair_applicable(hp, pl, spec);      // wide heads: the speculative kernel on CTA pairs (hpair.cuh)
+        if (fused_tip || pair_head) {
             window_params(hp, pl, ws, 0, &kp, wptr);
-            rc = run_tfused(hp, pl, kp, wptr, stream);
+            rc = fused_tip ? run_tfused(hp, pl, kp, wptr, stream) : run_hpair(hp, pl, kp, wptr, stream);
             if (rc) return rc;
         }
-        for (int ps = 0; ps < pl.n_pass && !fused_tip; ++ps) {       // one launch per class window (1 unless num_class > 80), all appending to the frames' lists
+        for (int ps = 0; ps < pl.n_pass && !fused_tip && !pair_head; ++ps) {       // one launch per class window (1 unless num_class > 80), all appending to the frames' lists
             window_params(hp, pl, ws, ps, &kp, wptr);
             rc = make_maps(hp, pl, &maps, wptr);
             if (rc) return rc;

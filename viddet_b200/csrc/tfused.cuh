@@ -33,6 +33,34 @@ constexpr int F_BLOCK_K = 64;
 constexpr int F_NT = 256;                    // tip channels per chunk = K of one prediction-GEMM step
 constexpr int F_MAX_CLUSTERS = 80;           // CTA pairs of one launch (sm_count / 2 <= 80)
 
+// Class-bias tables of spec_decode_lane in shared memory, per scale: [3 anchors][CPA chunks][CH4] biases (chunks padded for 128-bit
+// loads), then [3][CPA] = the largest bias of each chunk (the class loop's first test compares the raw logits against
+// threshold - max bias: no add and no bias load unless a logit of the chunk can pass).
+template <int C> struct SpecTables {
+    static constexpr int CPA = (C + 15) / 16;
+    static constexpr int CH = (C + CPA - 1) / CPA;
+    static constexpr int CH4 = (CH + 3) / 4 * 4;
+    static constexpr int NCH = 3 * CPA;
+    static constexpr int BLK = (NCH * CH4 + NCH + 3) / 4 * 4;          // floats per scale
+};
+template <int C>
+__device__ __forceinline__ void spec_stage_tables(float* scbias, const float* bias, int s, int tid, int nthreads) {
+    using T = SpecTables<C>;
+    constexpr int P = 5 + C;
+    float* blk = scbias + s * T::BLK;
+    for (int i = tid; i < T::NCH * T::CH4; i += nthreads) {
+        const int a = i / (T::CPA * T::CH4), cc = (i / T::CH4) % T::CPA, ci = i % T::CH4;
+        const int c = cc * T::CH + ci;
+        blk[i] = (bias && ci < T::CH && c < C) ? bias[a * P + 5 + c] : 0.0f;
+    }
+    for (int j = tid; j < T::NCH; j += nthreads) {
+        const int a = j / T::CPA, cc = j - a * T::CPA;
+        float m = 0.0f;                                                // padding classes carry bias 0
+        for (int ci = 0; ci < T::CH; ++ci) { const int c = cc * T::CH + ci; if (bias && c < C) m = fmaxf(m, bias[a * P + 5 + c]); }
+        blk[T::NCH * T::CH4 + j] = m;
+    }
+}
+
 // One launch covers every scale: an s32 item (4 chunks of K = 3072) costs ~14x an s8 item, and 224 of them over 74 CTA pairs were
 // 3.03 waves (a quarter of the launch lost to the last one).  The host deals the items of all scales to the pairs, largest first
 // (longest-processing-time greedy on a cost model), as one contiguous range per (scale, pair): beg[s][c] .. beg[s][c + 1].
@@ -74,7 +102,7 @@ template <int C, int NPAD> struct FusedCfg {
     static constexpr int CPA = (C + 15) / 16;
     static constexpr int CH = (C + CPA - 1) / CPA;
     static constexpr int CH4 = (CH + 3) / 4 * 4;
-    static constexpr int CBIAS_BYTES = VD_MAX_SCALES * 3 * CPA * CH4 * 4;
+    static constexpr int CBIAS_BYTES = VD_MAX_SCALES * SpecTables<C>::BLK * 4;
     static constexpr int BIAS_BYTES = VD_MAX_SCALES * NPAD * 4;
     static constexpr int BN_BYTES = VD_MAX_SCALES * 2 * 1024 * 4;          // folded BN scale / shift of every scale (Cin <= 1024)
     static constexpr int SH_BYTES = 1024;
@@ -90,6 +118,137 @@ struct FusedShared {
     uint64_t pred_full[2], pred_empty[2];
     uint32_t tmem_base;
 };
+
+// Where the decode + speculative candidate filter of one accumulator row puts its results (head workspace, see head.cu).
+struct SpecOut {
+    int rows_total, anc_total;               // rows of a frame's (rows, 6) tensor / anchor slots of a frame, over all scales
+    int c_valid; float valid_thresh;
+    float4* boxes; uint64_t* spec_lists; uint32_t* spec_cnt; const uint32_t* spec_tau;
+    int frames;
+};
+
+// Decode + speculative candidate filter of ONE pixel's prediction logits (the EPI_SPEC epilogue of head_kernel with a per-lane frame):
+// `tb` = TMEM address of the lane's accumulator row (3 anchors x (5 + C) columns), `half` / `nhalf` = which share of the 3*CPA class
+// chunks this warp takes (the warps that share a TMEM lane quarter split them), (f, cell) = frame and pixel of the lane (inb = false:
+// padding row, nothing is emitted), row_base_s / anc_base_s = the scale's first row / anchor slot.  sbias_s [NPAD] / scbias_s (SpecTables block) = the scale's biases in shared memory.
+// Every candidate whose score can reach the frame slot's threshold tau is scored and appended to its FRAME's list with one atomic
+// (~0.3 % of the class logits pass); the raw box records of the emitting (pixel, anchor) pairs go to the workspace.
+template <int C>
+__device__ __forceinline__ void spec_decode_lane(const uint32_t tb, const int half, const int nhalf, const bool inb, const int f, const int cell, const int row_base_s, const int anc_base_s, const int HW,
+                                                 const float* sbias_s, const float* scbias_s, const bool ws_ok, const SpecOut& o) {
+    constexpr int P = 5 + C;
+    constexpr int CPA_ = (C + 15) / 16, CH_ = (C + CPA_ - 1) / CPA_, CH4_ = (CH_ + 3) / 4 * 4;
+        uint32_t spec_tb;
+        {
+            const uint32_t floor_b = o.valid_thresh > 0.0f ? __float_as_uint(o.valid_thresh) : 0u;
+            const uint32_t hint = ws_ok ? __ldcg(o.spec_tau + f) : 0u;
+            spec_tb = hint > floor_b ? hint : floor_b;
+            if (spec_tb > 0x3f800001u) spec_tb = 0x3f800001u;
+            if (!ws_ok) spec_tb = 0x3f800001u;                            // foreign workspace: emit nothing, the NMS kernel fails every frame
+        }
+        float conf[3];
+        {
+            uint32_t rb[3];
+#pragma unroll
+            for (int a = 0; a < 3; ++a) tc::tmem_ld1(tb + (uint32_t)(a * P + 4), rb + a);
+            tc::tmem_ld_wait();
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                conf[a] = vd_sigmoid(__uint_as_float(rb[a]) + sbias_s[a * P + 4]);
+                if (!inb) conf[a] = __uint_as_float(0x7fc00000u);          // NaN: no score of a padding row passes `> valid_thresh`
+            }
+        }
+        constexpr int CH = CH_, CPA = CPA_, CH4 = CH4_, REM = C - (CPA - 1) * CH;
+        const float vth = o.valid_thresh;
+        float ell[3];
+        {
+            const float t = __fmul_rn(__uint_as_float(spec_tb), 0.999969482421875f);   // 1 - 2^-15
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                const float rr = __fmul_rn(t, vd_rcp(conf[a]));
+                const float l = __fmul_rn(__fsub_rn(vd_lg2(rr), vd_lg2(__fsub_rn(1.0f, rr))), 0.6931471805599453f);
+                float e = (rr < 1.0f) ? l : __uint_as_float(0x7f800000u);
+                if (spec_tb == 0u) e = __uint_as_float(0xff800000u);
+                if (!(conf[a] == conf[a])) e = __uint_as_float(0x7f800000u);
+                if (spec_tb >= 0x3f800001u) e = __uint_as_float(0x7f800000u);
+                ell[a] = e;
+            }
+        }
+        const uint32_t HW3 = (uint32_t)HW * 3u;
+        const uint32_t row0 = (uint32_t)row_base_s + (uint32_t)cell * 3u;       // + c*HW3 + a
+        uint64_t* fl = o.spec_lists + (size_t)f * kSpecCap;
+        uint32_t* fc = o.spec_cnt + f;
+        uint32_t emit_mask = 0u;
+        // the 3*CPA class chunks alternate between the two warps that share a TMEM lane quarter (half 0 / 1); the next chunk's
+        // TMEM read is in flight while the current one is compared
+        constexpr int NCH = 3 * CPA;
+        uint32_t rc[2][CH];
+        auto issue_j = [&](const int j, uint32_t* dst) {
+            const int a = j / CPA, cx = j - a * CPA;
+            const uint32_t col = tb + (uint32_t)(a * P + 5 + cx * CH);
+            if (REM != CH && cx == CPA - 1) tc::tmem_ld<REM>(col, dst); else tc::tmem_ld<CH>(col, dst);
+        };
+        if (half < NCH) issue_j(half, rc[0]);
+        int par = 0;
+#pragma unroll 1
+        for (int j = half; j < NCH; j += nhalf, par ^= 1) {
+            const int a = j / CPA, cx = j - a * CPA;
+            const int n = (REM != CH && cx == CPA - 1) ? REM : CH;
+            const float la = (a == 0) ? ell[0] : ((a == 1) ? ell[1] : ell[2]);
+            const float ca = (a == 0) ? conf[0] : ((a == 1) ? conf[1] : conf[2]);
+            // first test on the RAW logits: x + b_i >= la needs x >= la - max b (a margin covers the roundings of both sides), so the
+            // common case costs one compare per logit -- no add, no bias load
+            const float bmax = scbias_s[NCH * CH4 + j];
+            float thr = __fsub_rd(la, bmax);
+            thr = __fsub_rd(thr, __fmaf_rn(1e-6f, __fadd_rn(fabsf(la), fabsf(bmax)), 1e-20f));
+            tc::tmem_ld_wait();
+            bool any = false;
+            float xv[CH];
+            if (par == 0) {
+                if (j + nhalf < NCH) issue_j(j + nhalf, rc[1]);
+#pragma unroll
+                for (int i = 0; i < CH; ++i) { xv[i] = __uint_as_float(rc[0][i]); if (i < n) any |= xv[i] >= thr; }
+            } else {
+                if (j + nhalf < NCH) issue_j(j + nhalf, rc[0]);
+#pragma unroll
+                for (int i = 0; i < CH; ++i) { xv[i] = __uint_as_float(rc[1][i]); if (i < n) any |= xv[i] >= thr; }
+            }
+            if (any) {                                                    // rare: ~0.3 % of the class logits pass
+                float bv[CH4];
+#pragma unroll
+                for (int i = 0; i < CH4; i += 4)
+                    *reinterpret_cast<float4*>(bv + i) = *reinterpret_cast<const float4*>(scbias_s + j * CH4 + i);
+#pragma unroll
+                for (int i = 0; i < CH; ++i) bv[i] = __fadd_rn(xv[i], bv[i]);
+#pragma unroll
+                for (int i = 0; i < CH; ++i) {
+                    if (i < n && bv[i] >= la && cx * CH + i < o.c_valid) {
+                        const float scv = vd_score(bv[i], ca);
+                        if (scv > vth) {
+                            emit_mask |= 1u << a;
+                            const uint32_t kh = __float_as_uint(scv) | 0x80000000u;
+                            const uint32_t krow = row0 + (uint32_t)(cx * CH + i) * HW3 + (uint32_t)a;
+                            VD_DEV_CHECK(krow < (uint32_t)o.rows_total && inb && f < o.frames);
+                            const uint32_t pos = atomicAdd(fc, 1u);
+                            if (pos < (uint32_t)kSpecCap) fl[pos] = ((uint64_t)kh << 32) | (uint32_t)~krow;
+                        }
+                    }
+                }
+            }
+        }
+        // raw box records of the emitting (pixel, anchor) pairs (decoded by the NMS kernel for the <= topk survivors)
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            const bool mine = ((emit_mask >> a) & 1u) != 0u;
+            if (__any_sync(0xffffffffu, mine)) {
+                uint32_t r4[4];
+                tc::tmem_ld<4>(tb + (uint32_t)(a * P), r4); tc::tmem_ld_wait();
+                if (mine) o.boxes[(size_t)f * o.anc_total + anc_base_s + cell * 3 + a] =
+                    make_float4(__uint_as_float(r4[0]) + sbias_s[a * P + 0], __uint_as_float(r4[1]) + sbias_s[a * P + 1],
+                                __uint_as_float(r4[2]) + sbias_s[a * P + 2], __uint_as_float(r4[3]) + sbias_s[a * P + 3]);
+            }
+        }
+}
 
 template <int C, int NPAD>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(F_THREADS, 1)      // 168 registers: the register file is allocated as if for 12 warps (200 does not launch)
@@ -115,12 +274,7 @@ temporal_head_fused_kernel(const __grid_constant__ FusedMaps maps, const __grid_
         const int s_ = i / NPAD, n = i % NPAD;
         sbias[i] = (s_ < p.num_scales && p.sc[s_].bias && n < 3 * P) ? p.sc[s_].bias[n] : 0.0f;
     }
-    for (int i = threadIdx.x; i < VD_MAX_SCALES * 3 * Cfg::CPA * Cfg::CH4; i += F_THREADS) {
-        const int s_ = i / (3 * Cfg::CPA * Cfg::CH4), r_ = i % (3 * Cfg::CPA * Cfg::CH4);
-        const int a = r_ / (Cfg::CPA * Cfg::CH4), cc = (r_ / Cfg::CH4) % Cfg::CPA, ci = r_ % Cfg::CH4;
-        const int c = cc * Cfg::CH + ci;
-        scbias[i] = (s_ < p.num_scales && p.sc[s_].bias && ci < Cfg::CH && c < C) ? p.sc[s_].bias[a * P + 5 + c] : 0.0f;
-    }
+    for (int s_ = 0; s_ < VD_MAX_SCALES; ++s_) spec_stage_tables<C>(scbias, s_ < p.num_scales ? p.sc[s_].bias : nullptr, s_, (int)threadIdx.x, F_THREADS);
     if (threadIdx.x == 0) {
         for (int i = 0; i < Cfg::STAGES; ++i) { tc::mbar_init(&sh->full[i], 1); tc::mbar_init(&sh->empty[i], 1); }
         tc::mbar_init(&sh->tip_full, 1); tc::mbar_init(&sh->tip_empty, 16);
@@ -284,6 +438,9 @@ temporal_head_fused_kernel(const __grid_constant__ FusedMaps maps, const __grid_
         const uint32_t sw = (uint32_t)(trow & 7);
         const uint32_t stg_row = tc::smem_u32(stg) + (uint32_t)trow * 128u;
         const bool ws_ok = p.tile_counter[2] == p.ws_magic;   // the workspace holds thresholds of this layout
+        SpecOut sout;
+        sout.rows_total = p.g.row_base[p.g.num_scales]; sout.anc_total = p.g.anc_base[p.g.num_scales]; sout.c_valid = p.c_valid; sout.valid_thresh = p.valid_thresh; sout.boxes = p.boxes; sout.spec_lists = p.spec_lists;
+        sout.spec_cnt = p.spec_cnt; sout.spec_tau = p.spec_tau; sout.frames = p.frames;
         // ---- decode + speculative candidate filter on an item's prediction accumulator (head_kernel<EPI_SPEC>, per-lane frame).  Runs one
         // chunk LATE: the item's last prediction GEMM is issued behind the NEXT chunk's tip GEMM (MMA role), i.e. while these warps read
         // that chunk's accumulator back and stage it; the decode of the previous item follows.
@@ -291,7 +448,7 @@ temporal_head_fused_kernel(const __grid_constant__ FusedMaps maps, const __grid_
             const FusedScale& q = p.sc[s];
             const int HW = q.HW;
             const float* sbias_s = sbias + s * NPAD;
-            const float* scbias_s = scbias + s * (3 * Cfg::CPA * Cfg::CH4);
+            const float* scbias_s = scbias + s * SpecTables<C>::BLK;
             int b, mt; coords(q, item, rank, b, mt);
             const int row = mt * F_BLOCK_M + trow;
             const bool inb = (b < p.B) && (row < q.rows);
@@ -303,109 +460,7 @@ temporal_head_fused_kernel(const __grid_constant__ FusedMaps maps, const __grid_
             if (!(p.dbg & 1)) {
                 const int f = inb ? b * p.T + row / HW : 0;
                 const int cell = inb ? row % HW : 0;
-                uint32_t spec_tb;
-                {
-                    const uint32_t floor_b = p.valid_thresh > 0.0f ? __float_as_uint(p.valid_thresh) : 0u;
-                    const uint32_t hint = ws_ok ? __ldcg(p.spec_tau + f) : 0u;
-                    spec_tb = hint > floor_b ? hint : floor_b;
-                    if (spec_tb > 0x3f800001u) spec_tb = 0x3f800001u;
-                    if (!ws_ok) spec_tb = 0x3f800001u;                            // foreign workspace: emit nothing, the NMS kernel fails every frame
-                }
-                const uint32_t tb = tmem_base + 256u + pb * 128u + lane_addr;
-                float conf[3];
-                {
-                    uint32_t rb[3];
-#pragma unroll
-                    for (int a = 0; a < 3; ++a) tc::tmem_ld1(tb + (uint32_t)(a * P + 4), rb + a);
-                    tc::tmem_ld_wait();
-#pragma unroll
-                    for (int a = 0; a < 3; ++a) {
-                        conf[a] = vd_sigmoid(__uint_as_float(rb[a]) + sbias_s[a * P + 4]);
-                        if (!inb) conf[a] = __uint_as_float(0x7fc00000u);          // NaN: no score of a padding row passes `> valid_thresh`
-                    }
-                }
-                constexpr int CH = Cfg::CH, CPA = Cfg::CPA, CH4 = Cfg::CH4, REM = C - (CPA - 1) * CH;
-                const float vth = p.valid_thresh;
-                float ell[3];
-                {
-                    const float t = __fmul_rn(__uint_as_float(spec_tb), 0.999969482421875f);   // 1 - 2^-15
-#pragma unroll
-                    for (int a = 0; a < 3; ++a) {
-                        const float rr = __fmul_rn(t, vd_rcp(conf[a]));
-                        const float l = __fmul_rn(__fsub_rn(vd_lg2(rr), vd_lg2(__fsub_rn(1.0f, rr))), 0.6931471805599453f);
-                        float e = (rr < 1.0f) ? l : __uint_as_float(0x7f800000u);
-                        if (spec_tb == 0u) e = __uint_as_float(0xff800000u);
-                        if (!(conf[a] == conf[a])) e = __uint_as_float(0x7f800000u);
-                        if (spec_tb >= 0x3f800001u) e = __uint_as_float(0x7f800000u);
-                        ell[a] = e;
-                    }
-                }
-                const uint32_t HW3 = (uint32_t)HW * 3u;
-                const uint32_t row0 = (uint32_t)p.g.row_base[s] + (uint32_t)cell * 3u;       // + c*HW3 + a
-                uint64_t* fl = p.spec_lists + (size_t)f * kSpecCap;
-                uint32_t* fc = p.spec_cnt + f;
-                uint32_t emit_mask = 0u;
-                // the 3*CPA class chunks alternate between the two warps that share a TMEM lane quarter (half 0 / 1); the next chunk's
-                // TMEM read is in flight while the current one is compared
-                constexpr int NCH = 3 * CPA;
-                uint32_t rc[2][CH];
-                auto issue_j = [&](const int j, uint32_t* dst) {
-                    const int a = j / CPA, cx = j - a * CPA;
-                    const uint32_t col = tb + (uint32_t)(a * P + 5 + cx * CH);
-                    if (REM != CH && cx == CPA - 1) tc::tmem_ld<REM>(col, dst); else tc::tmem_ld<CH>(col, dst);
-                };
-                if (half < NCH) issue_j(half, rc[0]);
-                int par = 0;
-#pragma unroll 1
-                for (int j = half; j < NCH; j += 2, par ^= 1) {
-                    const int a = j / CPA, cx = j - a * CPA;
-                    const int n = (REM != CH && cx == CPA - 1) ? REM : CH;
-                    const float la = (a == 0) ? ell[0] : ((a == 1) ? ell[1] : ell[2]);
-                    const float ca = (a == 0) ? conf[0] : ((a == 1) ? conf[1] : conf[2]);
-                    float bv[CH4];
-#pragma unroll
-                    for (int i = 0; i < CH4; i += 4)
-                        *reinterpret_cast<float4*>(bv + i) = *reinterpret_cast<const float4*>(scbias_s + j * CH4 + i);
-                    tc::tmem_ld_wait();
-                    bool any = false;
-                    if (par == 0) {
-                        if (j + 2 < NCH) issue_j(j + 2, rc[1]);
-#pragma unroll
-                        for (int i = 0; i < CH; ++i) if (i < n) { bv[i] = __fadd_rn(__uint_as_float(rc[0][i]), bv[i]); any |= bv[i] >= la; }
-                    } else {
-                        if (j + 2 < NCH) issue_j(j + 2, rc[0]);
-#pragma unroll
-                        for (int i = 0; i < CH; ++i) if (i < n) { bv[i] = __fadd_rn(__uint_as_float(rc[1][i]), bv[i]); any |= bv[i] >= la; }
-                    }
-                    if (any) {                                                    // rare: ~0.3 % of the class logits pass
-#pragma unroll
-                        for (int i = 0; i < CH; ++i) {
-                            if (i < n && bv[i] >= la && cx * CH + i < p.c_valid) {
-                                const float scv = vd_score(bv[i], ca);
-                                if (scv > vth) {
-                                    emit_mask |= 1u << a;
-                                    const uint32_t kh = __float_as_uint(scv) | 0x80000000u;
-                                    const uint32_t krow = row0 + (uint32_t)(cx * CH + i) * HW3 + (uint32_t)a;
-                                    VD_DEV_CHECK(krow < (uint32_t)p.g.row_base[p.g.num_scales] && inb && f < p.frames);
-                                    const uint32_t pos = atomicAdd(fc, 1u);
-                                    if (pos < (uint32_t)kSpecCap) fl[pos] = ((uint64_t)kh << 32) | (uint32_t)~krow;
-                                }
-                            }
-                        }
-                    }
-                }
-                // raw box records of the emitting (pixel, anchor) pairs (decoded by the NMS kernel for the <= topk survivors)
-#pragma unroll
-                for (int a = 0; a < 3; ++a) {
-                    const bool mine = ((emit_mask >> a) & 1u) != 0u;
-                    if (__any_sync(0xffffffffu, mine)) {
-                        uint32_t r4[4];
-                        tc::tmem_ld<4>(tb + (uint32_t)(a * P), r4); tc::tmem_ld_wait();
-                        if (mine) p.boxes[(size_t)f * p.g.anc_base[p.g.num_scales] + p.g.anc_base[s] + cell * 3 + a] =
-                            make_float4(__uint_as_float(r4[0]) + sbias_s[a * P + 0], __uint_as_float(r4[1]) + sbias_s[a * P + 1],
-                                        __uint_as_float(r4[2]) + sbias_s[a * P + 2], __uint_as_float(r4[3]) + sbias_s[a * P + 3]);
-                    }
-                }
+                spec_decode_lane<C>(tmem_base + 256u + pb * 128u + lane_addr, half, 2, inb, f, cell, p.g.row_base[s], p.g.anc_base[s], HW, sbias_s, scbias_s, ws_ok, sout);
             }
             if (st2) p.stamps[scc * 16 + 14] = clock64();
             tc::fence_before_sync();
@@ -479,8 +534,33 @@ temporal_head_fused_kernel(const __grid_constant__ FusedMaps maps, const __grid_
     if (warp == 1) tc::tmem_dealloc_2cta<512>(tmem_base);
 }
 
+// `items` equal items of `cost` each onto the current loads of `clusters` workers, each item to the least-loaded worker (longest-processing-
+// time greedy when called for the costliest items first); cnt[c] = items worker c gets.  Levels are raised in bulk (a linear scan per
+// item would be 4 k x 74 steps per call).
+static void lpt_fill(double* load, int clusters, int items, double cost, int* cnt) {
+    for (int c = 0; c < clusters; ++c) cnt[c] = 0;
+    int left = items;
+    while (left > 0) {
+        int lo = 0;
+        for (int c = 1; c < clusters; ++c) if (load[c] < load[lo]) lo = c;
+        double next = 1e300;                     // the next higher load level
+        int at_lo = 0;
+        for (int c = 0; c < clusters; ++c) { if (load[c] <= load[lo] + 1e-9) ++at_lo; else if (load[c] < next) next = load[c]; }
+        // every worker at the lowest level takes k items, k = what lifts it to the next level (at least 1), bounded by what is left
+        long long k = next > 1e299 ? (left + at_lo - 1) / at_lo : (long long)((next - load[lo]) / cost);
+        if (k < 1) k = 1;
+        if (k * at_lo > left) k = left / at_lo;
+        if (k < 1) {                              // fewer items left than workers at the level: one each
+            for (int c = 0; c < clusters && left > 0; ++c) if (load[c] <= load[lo] + 1e-9) { ++cnt[c]; load[c] += cost; --left; }
+            continue;
+        }
+        const double lvl = load[lo];
+        for (int c = 0; c < clusters; ++c) if (load[c] <= lvl + 1e-9) { cnt[c] += (int)k; load[c] += k * cost; left -= (int)k; }
+    }
+}
+
 // Deals the items of every scale to `clusters` CTA pairs: scales in the order given (s32, s16, s8 = decreasing item cost), each item
-// to the pair with the least work so far (longest-processing-time greedy); a pair's items of one scale are a contiguous range.
+// to the pair with the least work so far; a pair's items of one scale are `strided` rounds + a contiguous range.
 // Cost model of an item (k-cycles, from the per-chunk stamps of scripts/tfused_stamps.py): chunks x (0.7 per k-block + 1.5).
 static void tfused_schedule(FusedParams* p, int clusters) {
     double load[F_MAX_CLUSTERS];
@@ -494,27 +574,7 @@ static void tfused_schedule(FusedParams* p, int clusters) {
         const FusedScale& q = p->sc[s];
         const int items = q.m_tiles > 0 ? (int)(((long long)p->B * q.m_tiles + 1) / 2) : 0;
         const double cost = q.n_chunks * (0.7 * 3.0 * (q.Cin / F_BLOCK_K) + 1.5);
-        for (int c = 0; c < clusters; ++c) cnt[c] = 0;
-        // water-filling: `items` equal items onto the current loads = repeatedly the least-loaded pair (a linear scan per item would be
-        // 4 k x 74 steps per call; levels are raised in bulk instead)
-        int left = items;
-        while (left > 0) {
-            int lo = 0;
-            for (int c = 1; c < clusters; ++c) if (load[c] < load[lo]) lo = c;
-            double next = 1e300;                     // the next higher load level
-            int at_lo = 0;
-            for (int c = 0; c < clusters; ++c) { if (load[c] <= load[lo] + 1e-9) ++at_lo; else if (load[c] < next) next = load[c]; }
-            // every pair at the lowest level takes k items, k = what lifts it to the next level (at least 1), bounded by what is left
-            long long k = next > 1e299 ? (left + at_lo - 1) / at_lo : (long long)((next - load[lo]) / cost);
-            if (k < 1) k = 1;
-            if (k * at_lo > left) k = left / at_lo;
-            if (k < 1) {                              // fewer items left than pairs at the level: one each
-                for (int c = 0; c < clusters && left > 0; ++c) if (load[c] <= load[lo] + 1e-9) { ++cnt[c]; load[c] += cost; --left; }
-                continue;
-            }
-            const double lvl = load[lo];
-            for (int c = 0; c < clusters; ++c) if (load[c] <= lvl + 1e-9) { cnt[c] += (int)k; load[c] += k * cost; left -= (int)k; }
-        }
+        lpt_fill(load, clusters, items, cost, cnt);
         int sr = 0;                                   // strided rounds: every pair takes part in them
         if (q.HW >= 8 * F_BLOCK_M) { sr = cnt[0]; for (int c = 1; c < clusters; ++c) if (cnt[c] < sr) sr = cnt[c]; }
         p->strided[s] = sr;

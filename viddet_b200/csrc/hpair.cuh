@@ -156,10 +156,11 @@ head_pair_kernel(const __grid_constant__ PairMaps maps, const __grid_constant__ 
                 const int row = (item * 2 + (int)rank) * 128 + trow;
                 const bool inb = row < rows;
                 const int f = inb ? row / HW : 0, cell = inb ? row - (row / HW) * HW : 0;
+                const uint32_t tau_hint = ws_ok ? __ldcg(p.spec_tau + f) : 0u;       // its L2 latency hides behind the wait for the accumulator
                 tc::mbar_wait_cluster(&sh->acc_full[buf], (it >> 1) & 1u);
                 tc::fence_after_sync();
                 if (!(p.dbg & 1))
-                    spec_decode_lane<C>(tmem_base + buf * NPAD + lane_addr, half, HP_EPI_GROUPS, inb, f, cell, row_base_s, anc_base_s, HW, sbias_s, scbias_s, ws_ok, sout);
+                    spec_decode_lane<C>(tmem_base + buf * NPAD + lane_addr, half, HP_EPI_GROUPS, inb, f, cell, row_base_s, anc_base_s, HW, sbias_s, scbias_s, ws_ok, tau_hint, sout);
                 tc::fence_before_sync();
                 __syncwarp();
                 if (lane == 0) tc::mbar_arrive_cluster(&sh->acc_empty[buf], 0u);

@@ -135,13 +135,13 @@ struct SpecOut {
 // (~0.3 % of the class logits pass); the raw box records of the emitting (pixel, anchor) pairs go to the workspace.
 template <int C>
 __device__ __forceinline__ void spec_decode_lane(const uint32_t tb, const int half, const int nhalf, const bool inb, const int f, const int cell, const int row_base_s, const int anc_base_s, const int HW,
-                                                 const float* sbias_s, const float* scbias_s, const bool ws_ok, const SpecOut& o) {
+                                                 const float* sbias_s, const float* scbias_s, const bool ws_ok, const uint32_t tau_hint, const SpecOut& o) {
     constexpr int P = 5 + C;
     constexpr int CPA_ = (C + 15) / 16, CH_ = (C + CPA_ - 1) / CPA_, CH4_ = (CH_ + 3) / 4 * 4;
         uint32_t spec_tb;
         {
             const uint32_t floor_b = o.valid_thresh > 0.0f ? __float_as_uint(o.valid_thresh) : 0u;
-            const uint32_t hint = ws_ok ? __ldcg(o.spec_tau + f) : 0u;
+            const uint32_t hint = ws_ok ? tau_hint : 0u;          // the frame slot's threshold, loaded by the caller BEFORE it waits for the accumulator
             spec_tb = hint > floor_b ? hint : floor_b;
             if (spec_tb > 0x3f800001u) spec_tb = 0x3f800001u;
             if (!ws_ok) spec_tb = 0x3f800001u;                            // foreign workspace: emit nothing, the NMS kernel fails every frame
@@ -454,13 +454,14 @@ temporal_head_fused_kernel(const __grid_constant__ FusedMaps maps, const __grid_
             const bool inb = (b < p.B) && (row < q.rows);
             const uint32_t pb = ic & 1u;
             const bool st2 = p.stamps && blockIdx.x == 0 && warp == 2 && lane == 0 && scc < 200u;
+            const uint32_t tau_hint = (ws_ok && inb) ? __ldcg(p.spec_tau + (b * p.T + row / HW)) : 0u;
             tc::mbar_wait_cluster(&sh->pred_full[pb], (ic >> 1) & 1u);
             tc::fence_after_sync();
             if (st2) p.stamps[scc * 16 + 13] = clock64();
             if (!(p.dbg & 1)) {
                 const int f = inb ? b * p.T + row / HW : 0;
                 const int cell = inb ? row % HW : 0;
-                spec_decode_lane<C>(tmem_base + 256u + pb * 128u + lane_addr, half, 2, inb, f, cell, p.g.row_base[s], p.g.anc_base[s], HW, sbias_s, scbias_s, ws_ok, sout);
+                spec_decode_lane<C>(tmem_base + 256u + pb * 128u + lane_addr, half, 2, inb, f, cell, p.g.row_base[s], p.g.anc_base[s], HW, sbias_s, scbias_s, ws_ok, tau_hint, sout);
             }
             if (st2) p.stamps[scc * 16 + 14] = clock64();
             tc::fence_before_sync();

@@ -146,11 +146,20 @@ __device__ __forceinline__ void spec_decode_lane(const uint32_t tb, const int ha
             if (spec_tb > 0x3f800001u) spec_tb = 0x3f800001u;
             if (!ws_ok) spec_tb = 0x3f800001u;                            // foreign workspace: emit nothing, the NMS kernel fails every frame
         }
+        constexpr int CH = CH_, CPA = CPA_, CH4 = CH4_, REM = C - (CPA - 1) * CH;
+        constexpr int NCH = 3 * CPA;
+        uint32_t rc[2][CH];
+        auto issue_j = [&](const int j, uint32_t* dst) {
+            const int a = j / CPA, cx = j - a * CPA;
+            const uint32_t col = tb + (uint32_t)(a * P + 5 + cx * CH);
+            if (REM != CH && cx == CPA - 1) tc::tmem_ld<REM>(col, dst); else tc::tmem_ld<CH>(col, dst);
+        };
         float conf[3];
         {
             uint32_t rb[3];
 #pragma unroll
             for (int a = 0; a < 3; ++a) tc::tmem_ld1(tb + (uint32_t)(a * P + 4), rb + a);
+            if (half < NCH) issue_j(half, rc[0]);                         // the warp's first class chunk rides along with the objectness columns
             tc::tmem_ld_wait();
 #pragma unroll
             for (int a = 0; a < 3; ++a) {
@@ -158,7 +167,6 @@ __device__ __forceinline__ void spec_decode_lane(const uint32_t tb, const int ha
                 if (!inb) conf[a] = __uint_as_float(0x7fc00000u);          // NaN: no score of a padding row passes `> valid_thresh`
             }
         }
-        constexpr int CH = CH_, CPA = CPA_, CH4 = CH4_, REM = C - (CPA - 1) * CH;
         const float vth = o.valid_thresh;
         float ell[3];
         {
@@ -181,14 +189,6 @@ __device__ __forceinline__ void spec_decode_lane(const uint32_t tb, const int ha
         uint32_t emit_mask = 0u;
         // the 3*CPA class chunks alternate between the two warps that share a TMEM lane quarter (half 0 / 1); the next chunk's
         // TMEM read is in flight while the current one is compared
-        constexpr int NCH = 3 * CPA;
-        uint32_t rc[2][CH];
-        auto issue_j = [&](const int j, uint32_t* dst) {
-            const int a = j / CPA, cx = j - a * CPA;
-            const uint32_t col = tb + (uint32_t)(a * P + 5 + cx * CH);
-            if (REM != CH && cx == CPA - 1) tc::tmem_ld<REM>(col, dst); else tc::tmem_ld<CH>(col, dst);
-        };
-        if (half < NCH) issue_j(half, rc[0]);
         int par = 0;
 #pragma unroll 1
         for (int j = half; j < NCH; j += nhalf, par ^= 1) {

@@ -15,9 +15,9 @@
 
 namespace vd {
 
-constexpr int HP_EPI_GROUPS = 4;                           // epilogue warps per TMEM lane quarter: they split the class chunks (240 class logits per pixel at C = 80:
-                                                          // with 2 the decode, not the mainloop, bound the kernel: 100 us per 64 frames against 58 us of mainloop)
-constexpr int HP_THREADS = 64 + HP_EPI_GROUPS * 128;
+// EG = epilogue warps per TMEM lane quarter: they split the class chunks.  4 for the 256-column heads (240 class logits per pixel at C = 80: with 2
+// the decode, not the mainloop, bound the kernel: 100 us per 64 frames against 58 us of mainloop); 2 for narrow heads.
+constexpr int hp_threads(int EG) { return 64 + EG * 128; }
 
 struct PairScale {
     int HW, Cin, rows, m_tiles;              // pixels per frame, channels, rows = frames*HW, 128-row tiles
@@ -35,7 +35,11 @@ struct PairParams {
 };
 struct PairMaps { CUtensorMap a[VD_MAX_SCALES], w[VD_MAX_SCALES]; };
 
-template <int C, int NPAD> struct PairCfg {
+template <int C, int NPAD, int EG> struct PairCfg {
+    static constexpr int THREADS = hp_threads(EG);
+    static constexpr int ACC_STRIDE = (NPAD + 31) / 32 * 32;              // TMEM columns between the two accumulators
+    static constexpr int TMEM_COLS = 2 * ACC_STRIDE <= 256 ? 256 : 512;
+    static constexpr int SMEM_BUDGET = (NPAD > 128 ? 212 : 200) * 1024;   // narrow heads leave the co-scheduled NMS CTA its 22 KB
     static constexpr int A_BYTES = 128 * 64 * 2;
     static constexpr int B_BYTES = (NPAD / 2) * 64 * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
@@ -45,10 +49,10 @@ template <int C, int NPAD> struct PairCfg {
     static constexpr int CBIAS_BYTES = VD_MAX_SCALES * SpecTables<C>::BLK * 4;
     static constexpr int BIAS_BYTES = VD_MAX_SCALES * NPAD * 4;
     static constexpr int SH_BYTES = 1024;
-    static constexpr int STAGES_RAW = (212 * 1024 - CBIAS_BYTES - BIAS_BYTES - SH_BYTES) / STAGE_BYTES;
+    static constexpr int STAGES_RAW = (SMEM_BUDGET - CBIAS_BYTES - BIAS_BYTES - SH_BYTES - 1024) / STAGE_BYTES;
     static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + CBIAS_BYTES + BIAS_BYTES + SH_BYTES + 1024;
-    static_assert(NPAD % 32 == 0 && NPAD <= 256 && 3 * (5 + C) <= NPAD, "prediction width");
+    static_assert(NPAD % 16 == 0 && (NPAD / 2) % 8 == 0 && NPAD <= 256 && 3 * (5 + C) <= NPAD, "prediction width");
     static_assert(STAGE_BYTES % 1024 == 0 && STAGES >= 3 && SMEM_BYTES <= 227 * 1024, "shared memory");
 };
 struct PairShared {
@@ -56,10 +60,12 @@ struct PairShared {
     uint32_t tmem_base;
 };
 
-template <int C, int NPAD>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(HP_THREADS, 1)
+template <int C, int NPAD, int EG>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(hp_threads(EG), 1)
 head_pair_kernel(const __grid_constant__ PairMaps maps, const __grid_constant__ PairParams p) {
-    using Cfg = PairCfg<C, NPAD>;
+    using Cfg = PairCfg<C, NPAD, EG>;
+    constexpr int HP_THREADS = Cfg::THREADS;
+    constexpr int HP_EPI_GROUPS = EG;
     constexpr int P = 5 + C;
     extern __shared__ unsigned char smem_dyn[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
@@ -82,7 +88,7 @@ head_pair_kernel(const __grid_constant__ PairMaps maps, const __grid_constant__ 
         tc::fence_barrier_init();
         for (int s_ = 0; s_ < p.num_scales; ++s_) { tc::prefetch_tmap(&maps.a[s_]); tc::prefetch_tmap(&maps.w[s_]); }
     }
-    if (warp == 1) tc::tmem_alloc_2cta<512>(&sh->tmem_base);
+    if (warp == 1) tc::tmem_alloc_2cta<Cfg::TMEM_COLS>(&sh->tmem_base);
     tc::fence_before_sync();
     __syncthreads();
     tc::cluster_sync_all();
@@ -118,7 +124,7 @@ head_pair_kernel(const __grid_constant__ PairMaps maps, const __grid_constant__ 
                     const uint32_t buf = it & 1u;
                     tc::mbar_wait_cluster(&sh->acc_empty[buf], ((it >> 1) & 1u) ^ 1u);
                     tc::fence_after_sync();
-                    const uint32_t d_tmem = tmem_base + buf * NPAD;
+                    const uint32_t d_tmem = tmem_base + buf * Cfg::ACC_STRIDE;
                     for (int kb = 0; kb < nkb; ++kb) {
                         tc::mbar_wait_cluster(&sh->full[stage], phase);
                         tc::fence_after_sync();
@@ -160,7 +166,7 @@ head_pair_kernel(const __grid_constant__ PairMaps maps, const __grid_constant__ 
                 tc::mbar_wait_cluster(&sh->acc_full[buf], (it >> 1) & 1u);
                 tc::fence_after_sync();
                 if (!(p.dbg & 1))
-                    spec_decode_lane<C>(tmem_base + buf * NPAD + lane_addr, half, HP_EPI_GROUPS, inb, f, cell, row_base_s, anc_base_s, HW, sbias_s, scbias_s, ws_ok, tau_hint, sout);
+                    spec_decode_lane<C>(tmem_base + buf * Cfg::ACC_STRIDE + lane_addr, half, HP_EPI_GROUPS, inb, f, cell, row_base_s, anc_base_s, HW, sbias_s, scbias_s, ws_ok, tau_hint, sout);
                 tc::fence_before_sync();
                 __syncwarp();
                 if (lane == 0) tc::mbar_arrive_cluster(&sh->acc_empty[buf], 0u);
@@ -171,24 +177,27 @@ head_pair_kernel(const __grid_constant__ PairMaps maps, const __grid_constant__ 
     tc::fence_before_sync();
     __syncthreads();
     tc::cluster_sync_all();
-    if (warp == 1) tc::tmem_dealloc_2cta<512>(tmem_base);
+    if (warp == 1) tc::tmem_dealloc_2cta<Cfg::TMEM_COLS>(tmem_base);
 }
 
-template <int C, int NPAD>
+template <int C, int NPAD, int EG>
 static int launch_hpair_t(const PairMaps& maps, const PairParams& p, int clusters, cudaStream_t stream) {
-    using Cfg = PairCfg<C, NPAD>;
-    auto kern = head_pair_kernel<C, NPAD>;
-    { int rc_ = configure_kernel((const void*)kern, Cfg::SMEM_BYTES, false); if (rc_) return rc_; }
+    using Cfg = PairCfg<C, NPAD, EG>;
+    auto kern = head_pair_kernel<C, NPAD, EG>;
+    { int rc_ = configure_kernel((const void*)kern, Cfg::SMEM_BYTES, NPAD <= 128); if (rc_) return rc_; }      // narrow heads: same carve-out as the NMS kernel that shares the SM
     if (clusters < 1) return VD_OK;
-    kern<<<(unsigned)(2 * clusters), HP_THREADS, Cfg::SMEM_BYTES, stream>>>(maps, p);
+    kern<<<(unsigned)(2 * clusters), Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(maps, p);
     VD_LAUNCH_CHECK();
     return VD_OK;
 }
 
+// Compiled for the 256-column shape only.  The narrow VOC / VID shapes (<20,80,2>, <30,112,2>, NMS CTA co-resident) were measured and
+// rejected: 48.7 us per VOC step against 33.9 us for head_kernel (its dynamic tile scheduler, three epilogue groups with per-warp
+// staging and the 7-stage ring are what an HBM-bound head needs; the operand traffic this kernel saves does not bind there).
 static bool hpair_supported(int C) { return C == 80; }
 
 static int launch_hpair(const PairMaps& maps, const PairParams& p, int C, int clusters, cudaStream_t stream) {
-    if (C == 80) return launch_hpair_t<80, 256>(maps, p, clusters, stream);
+    if (C == 80) return launch_hpair_t<80, 256, 4>(maps, p, clusters, stream);
     return set_error(VD_ERR_UNSUPPORTED, "pair head: no kernel shape for %d classes", C);
 }
 

@@ -709,7 +709,8 @@ def main():
         tf = launch_flops / (head_ms * 1e-3) / 1e12
         hbm_frac, tensor_frac = achieved / peak, tf / tpeak
         tensor_bound = (launch_flops / (tpeak * 1e12)) > (launch_bytes / (peak * 1e9))
-        roof = {"bound": "tensor" if tensor_bound else "hbm", "kernel": "head_kernel<EPI_SPEC> (tcgen05 pred conv + decode + speculative candidate filter; exact EPI_FILTER fallback idle in the steady state)",
+        pair_kernel = 31 <= C <= 80 and os.environ.get("VD_HEAD_PAIR", "1") != "0"        # wide heads run on CTA pairs (csrc/hpair.cuh)
+        roof = {"bound": "tensor" if tensor_bound else "hbm", "kernel": ("head_pair_kernel<80,256> (tcgen05 cta_group::2 pred conv + decode + speculative candidate filter on CTA pairs; exact EPI_FILTER fallback idle in the steady state)" if pair_kernel else "head_kernel<EPI_SPEC> (tcgen05 pred conv + decode + speculative candidate filter; exact EPI_FILTER fallback idle in the steady state)"),
                 "achieved": tf if tensor_bound else achieved, "peak": tpeak if tensor_bound else peak, "peak_kind": tkind if tensor_bound else peak_kind,
                 "unit": "TFLOP/s" if tensor_bound else "GB/s",
                 "frac": tensor_frac if tensor_bound else hbm_frac, "hbm_frac": hbm_frac, "tensor_frac": tensor_frac,
